@@ -1,0 +1,146 @@
+/*
+ * mpc_b200.h -- C ABI of libmpc_b200.so, the B200-native batched solver for the
+ * kinematic-bicycle path-following NLP.
+ *
+ * Drop-in boundary.  The reference has no FFI layer; its boundary is the Julia module
+ * API of scripts/mpc_utils/MKZMPCPathFollower.jl as called from scripts/mpc_cmd_pub.jl.
+ * Each entry point below names the reference interface it replaces.  A Julia shim
+ * (julia/MKZMPCPathFollower.jl, ccall) and a Python ctypes binding
+ * (mkz_mpc_path_follower_b200/capi.py) sit on top; see INTEGRATION.md.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative
+ * MPCB200_E* code (message via mpcb200_last_error); the caller owns every buffer, the
+ * library owns the opaque handle, its device scratch and its CUDA stream.  Calls on one
+ * handle must be serialised by the caller; distinct handles are independent.  There is
+ * no CPU fallback: without a CUDA device mpcb200_create fails with MPCB200_ENODEVICE.
+ */
+#ifndef MPC_B200_H
+#define MPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB200_VERSION 1
+
+/* error codes */
+#define MPCB200_OK          0
+#define MPCB200_EINVAL     -1  /* bad argument (NULL pointer, N out of range, B < 0, ...) */
+#define MPCB200_ENODEVICE  -2  /* no usable CUDA device: the library has no CPU path */
+#define MPCB200_ECUDA      -3  /* CUDA runtime error, text in mpcb200_last_error */
+#define MPCB200_ENOMEM     -4
+
+/* solve status, one per problem: the JuMP status symbols solve_model() returns
+ * (MKZMPCPathFollower.jl:176-182) through Ipopt.jl's mapping */
+#define MPCB200_OPTIMAL     0  /* :Optimal    Solve_Succeeded / Solved_To_Acceptable_Level */
+#define MPCB200_INFEASIBLE  1  /* :Infeasible */
+#define MPCB200_UNBOUNDED   2  /* :Unbounded  diverging iterates */
+#define MPCB200_USERLIMIT   3  /* :UserLimit  iteration cap (stands in for max_cpu_time, :29) */
+#define MPCB200_ERROR       4  /* :Error      everything else */
+
+/* mem_space */
+#define MPCB200_HOST   0  /* pointers are host memory; the call copies H2D/D2H and synchronises */
+#define MPCB200_DEVICE 1  /* pointers are device memory on the handle's device; the call only
+                             enqueues work on the handle's stream (no synchronisation) */
+
+/* start_mode when warm == NULL */
+#define MPCB200_START_ZERO    0  /* every variable 0.0, as `start=0.0` in MKZMPCPathFollower.jl:65-72 */
+#define MPCB200_START_ROLLOUT 1  /* states = bicycle-model rollout of the previous command from the
+                                    measured state (not a reference behaviour; opt-in) */
+
+/* Replaces the module-level constants of MKZMPCPathFollower.jl:28-48. */
+typedef struct {
+    int32_t N;            /* horizon (:34), 3 <= N <= 31 in this build */
+    int32_t max_iter;     /* iteration cap -> MPCB200_USERLIMIT */
+    int32_t start_mode;   /* MPCB200_START_* */
+    int32_t device;       /* CUDA device ordinal */
+    double  dt;           /* :33 */
+    double  dt_control;   /* :28 */
+    double  L_a, L_b;     /* :31-32 */
+    double  v_min, v_max; /* :47-48 */
+    double  a_max;        /* :44 */
+    double  steer_max;    /* :41 */
+    double  a_dmax;       /* :45 */
+    double  steer_dmax;   /* :42 */
+    double  tol;          /* Ipopt tol, default 1e-8 */
+} mpcb200_config;
+
+typedef struct mpcb200_handle mpcb200_handle;
+
+/* Fill *cfg with the reference's constants (MKZMPCPathFollower.jl:28-48) for horizon N. */
+int mpcb200_default_config(mpcb200_config* cfg, int32_t N);
+
+/* Replaces module load (`import MKZMPCPathFollower`, mpc_cmd_pub.jl:45-47): builds the solver
+ * for one horizon on one GPU.  Weights start at the module defaults (:51-59). */
+int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg);
+int mpcb200_destroy(mpcb200_handle* h);
+
+/* Replaces update_cost(cx, cy, cp, cv, cda, cdd, ca, cd) (MKZMPCPathFollower.jl:158-169);
+ * same argument order. */
+int mpcb200_set_cost(mpcb200_handle* h, const double w[8]);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of this handle;
+ * NULL restores the handle's own stream. */
+int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
+
+/*
+ * Replaces, for B independent problems at once, the per-step sequence of mpc_cmd_pub.jl:115-141:
+ *   update_init_cond(x, y, psi, v)                 -> state  [B][4]
+ *   update_reference(x_ref, y_ref, psi_ref, v_des) -> ref    [B][3][N+1]  and v_des [B] (NULL = 0)
+ *   update_current_input(c_swa, c_acc)             -> u_prev [B][2]   (steering first, :151)
+ *   solve_model() -> (acc, d_f, status)            -> u0     [B][2]   (acceleration first, :182),
+ *                                                     status [B], plus cost [B] and iters [B]
+ *   get_solver_results()                           -> traj   [B][6N+4] in the order
+ *        x[N+1], y[N+1], v[N+1], psi[N+1], d_f[N], acc[N]   (:188-206); may be NULL
+ * warm [B][6N+4] (same layout as traj): in = start point (the reference re-solves from the
+ * previous solution), out = this solution.  NULL = start_mode of the config.
+ * cost, status, iters, traj, warm may each be NULL.  All problem-major, contiguous.
+ */
+int mpcb200_solve_batch(mpcb200_handle* h, int64_t B,
+                        const double* state, const double* ref, const double* v_des,
+                        const double* u_prev, double* warm,
+                        double* u0, double* cost, int32_t* status, int32_t* iters,
+                        double* traj, int32_t mem_space);
+
+/* Path table for on-device reference generation (ref_gps_traj.py:106): columns t, X, Y, psi, s
+ * of the trajectory matrix, n samples each, host pointers; copied to the device. */
+int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n,
+                     const double* t, const double* X, const double* Y,
+                     const double* psi, const double* s);
+
+/*
+ * Closed-loop Monte-Carlo rollout (mpc_cmd_pub.jl:86-157 driving vehicle_simulator.py:58-112):
+ * B vehicles x T control steps, each step = 10 plant publishes (100 Euler sub-steps), on-device
+ * reference generation (time mode if target_vel <= 0 ... see track_using_time), warm-started solve,
+ * command feedback, stop latch.
+ *   pose0    [B][3]  X0, Y0, Psi0 ;  path_of [B] path_id per vehicle
+ *   log      [T][B][8]  x, y, psi, v, acc_cmd, df_cmd, status, iters  (may be NULL)
+ *   final    [B][8]  plant state X,Y,psi,vx,vy,wz,acc,df after T steps (may be NULL)
+ * Host pointers only.
+ */
+int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T,
+                    const double* pose0, const int32_t* path_of,
+                    int32_t track_using_time, double target_vel,
+                    double* log, double* final_state);
+
+/* Counters of the last solve_batch/rollout call on this handle. */
+typedef struct {
+    int64_t kernel_launches;   /* kernels of this library launched by the call */
+    int64_t h2d_bytes, d2h_bytes;
+    float   kernel_ms;         /* device time of the solver kernel(s) (CUDA events), HOST mode only */
+} mpcb200_stats;
+int mpcb200_get_stats(mpcb200_handle* h, mpcb200_stats* out);
+
+/* FP64 FMA micro-benchmark on the handle's device: returns achieved TFLOP/s (2 flop per FMA).
+ * Used for the roofline denominator (MEASURED_PEAKS.json has no FP64 entry). */
+int mpcb200_fp64_peak(mpcb200_handle* h, double* tflops);
+
+const char* mpcb200_last_error(mpcb200_handle* h);
+int mpcb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

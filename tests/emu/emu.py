@@ -1,0 +1,57 @@
+"""TEST ONLY: ctypes binding of the CPU warp emulation of the CUDA solver (tests/emu)."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = os.path.join(_HERE, "libmpc_emu.so")
+_SRCS = [os.path.join(_HERE, "emu_driver.cpp"), os.path.join(_HERE, "warp_emu.h"),
+         os.path.join(_ROOT, "mkz_mpc_path_follower_b200", "csrc", "mpc_kernel.cuh")]
+
+
+class KCfg(C.Structure):
+    _fields_ = [("N", C.c_int), ("max_iter", C.c_int), ("start_mode", C.c_int), ("pad_", C.c_int),
+                ("dt", C.c_double), ("dtc", C.c_double), ("La", C.c_double), ("Lb", C.c_double),
+                ("vmin", C.c_double), ("vmax", C.c_double), ("amax", C.c_double), ("smax", C.c_double),
+                ("admax", C.c_double), ("sdmax", C.c_double), ("tol", C.c_double), ("w", C.c_double * 8)]
+
+
+def build():
+    if (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in _SRCS):
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DMPC_HOST_EMU",
+                               "-I" + _HERE, "-I" + os.path.join(_ROOT, "mkz_mpc_path_follower_b200", "csrc"),
+                               "-x", "c++", _SRCS[0], "-o", _LIB])
+    return _LIB
+
+
+def kcfg_from_oracle(ocfg, start_mode=0):
+    k = KCfg()
+    k.N = ocfg.N; k.max_iter = ocfg.max_iter; k.start_mode = start_mode
+    k.dt = ocfg.dt; k.dtc = ocfg.dt_control; k.La = ocfg.L_a; k.Lb = ocfg.L_b
+    k.vmin = ocfg.v_min; k.vmax = ocfg.v_max; k.amax = ocfg.a_max; k.smax = ocfg.steer_max
+    k.admax = ocfg.a_dmax; k.sdmax = ocfg.steer_dmax; k.tol = ocfg.tol
+    for i in range(8):
+        k.w[i] = ocfg.w[i]
+    return k
+
+
+def solve_batch(kcfg, state, ref, v_des, u_prev, warm=None, want_traj=False):
+    lib = C.CDLL(build())
+    assert lib.emu_kcfg_size() == C.sizeof(KCfg)
+    dp = C.POINTER(C.c_double)
+    N = kcfg.N
+    B = state.shape[0]
+    p = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)
+    state = np.ascontiguousarray(state, dtype=np.float64); ref = np.ascontiguousarray(ref, dtype=np.float64)
+    u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+    v_des = None if v_des is None else np.ascontiguousarray(v_des, dtype=np.float64)
+    u0 = np.empty((B, 2)); cost = np.empty(B); status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
+    traj = np.empty((B, 6 * N + 4)) if want_traj else None
+    lib.emu_solve_batch.argtypes = [C.POINTER(KCfg), C.c_long, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp]
+    lib.emu_solve_batch(C.byref(kcfg), B, p(state), p(ref), p(v_des), p(u_prev),
+                        None if warm is None else warm.ctypes.data_as(dp), p(u0), p(cost),
+                        status.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)),
+                        None if traj is None else traj.ctypes.data_as(dp))
+    return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}

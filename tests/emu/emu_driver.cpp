@@ -1,0 +1,63 @@
+// emu_driver.cpp -- TEST ONLY: runs mpc_kernel.cuh on the CPU warp emulator.
+#define MPC_HOST_EMU 1
+#include "warp_emu.h"
+#include "mpc_kernel.cuh"
+
+#include <vector>
+
+namespace mpcb200 { namespace emu {
+thread_local Warp* W = nullptr;
+
+static void trampoline(int lane) {
+    Warp* w = W;
+    w->fn(lane, w->arg);
+    w->done[lane] = 1;
+    // hand over to the next unfinished lane, or back to main when all are done
+    for (int i = 1; i <= 32; i++) {
+        int c = (lane + i) & 31;
+        if (!w->done[c]) { w->cur = c; setcontext(&w->ctx[c]); }
+    }
+    setcontext(&w->main_ctx);
+}
+
+void run_warp(void (*fn)(int, void*), void* arg) {
+    Warp w;
+    memset(&w, 0, sizeof(w));
+    const size_t STK = 1 << 18;
+    w.stacks = (char*)malloc(32 * STK);
+    w.fn = fn; w.arg = arg;
+    W = &w;
+    for (int l = 0; l < 32; l++) {
+        getcontext(&w.ctx[l]);
+        w.ctx[l].uc_stack.ss_sp = w.stacks + l * STK;
+        w.ctx[l].uc_stack.ss_size = STK;
+        w.ctx[l].uc_link = &w.main_ctx;
+        makecontext(&w.ctx[l], (void (*)())trampoline, 1, l);
+    }
+    w.cur = 0;
+    swapcontext(&w.main_ctx, &w.ctx[0]);
+    free(w.stacks);
+    W = nullptr;
+}
+}}  // namespace
+
+using namespace mpcb200;
+
+struct Job { const KCfg* cfg; const BatchPtrs* io; long b; double* smem; };
+static void lane_main(int, void* a) {
+    Job* j = (Job*)a;
+    solve_problem(*j->cfg, *j->io, j->b, j->smem);
+}
+
+extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, const double* ref, const double* v_des,
+                               const double* u_prev, double* warm, double* u0, double* cost, int* status, int* iters,
+                               double* traj) {
+    BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj};
+    std::vector<double> smem(4096, 0.0);
+    for (long b = 0; b < B; b++) {
+        Job j{cfg, &io, b, smem.data()};
+        emu::run_warp(lane_main, &j);
+    }
+    return 0;
+}
+extern "C" int emu_kcfg_size() { return (int)sizeof(KCfg); }
