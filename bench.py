@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- converged MPC solves/s at batch 64K, N=20 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 5 --warmup 3
+    python bench.py --impl reference ...      # CPU arm: the oracle (restated interior point, NOT Ipopt)
+
+A step = one pass of the hot path (cold-start solve of every problem of the batch) over one
+synthetic batch: BASELINE.json configs[2], 65,536 problems per GPU at N=20 along paths 1-3
+(SURVEY.md 8d).  Weak scaling: every rank solves its own contiguous 65,536-problem slice of the
+counter-based stream; the only inter-GPU traffic is one NCCL all-gather of the 32 B/problem
+result record.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F_RIC, F_EVAL = 1235, 310  # algorithmic flops per stage per interior-point iteration
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=65536, help="problems per GPU")
+    ap.add_argument("--horizon", type=int, default=20)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-latency", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_baseline(N, sample, threads, start_b0=0):
+    """The oracle (restated CPU interior point, NOT Ipopt) on a bounded sample of the same workload."""
+    from oracle import oracle as O
+    from mkz_mpc_path_follower_b200 import workload
+    O.build()
+    b = workload.make_batch(sample, N, b0=start_b0)
+    cfg = O.default_cfg(N)
+    t0 = time.perf_counter()
+    r = O.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=threads)
+    dt = time.perf_counter() - t0
+    conv = int((r["status"] == 0).sum())
+    return conv / dt, dt, conv, r
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  Julia/JuMP/Ipopt cannot run here, so
+    this arm times the oracle port with every host core, one bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N = args.horizon
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or max(256, 64 * cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(N, min(sample, 256), cores)
+    t_tot, conv_tot = 0.0, 0
+    for s in range(args.steps):
+        v, dt, conv, _ = cpu_baseline(N, sample, cores, start_b0=s * sample)
+        t_tot += dt
+        conv_tot += conv
+    val = conv_tot / t_tot
+    line = {
+        "impl": "reference", "metric": "converged MPC solves/sec at batch 64K, N=20", "value": val,
+        "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: N=%d cold-start solves along path1-3, bounded sample of %d problems/step" % (N, sample)},
+        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
+                         "sample": "%d problems/step x %d steps, restated CPU interior point (oracle), NOT Ipopt" % (sample, args.steps)},
+        "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from mkz_mpc_path_follower_b200 import capi, workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the solver has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, B = args.horizon, args.batch
+    nt = 6 * N + 4
+
+    # ---- synthetic batch: this rank's contiguous slice of the problem stream
+    b = workload.make_batch(B, N, b0=rank * B)
+    solver = capi.Solver(N, device=local)
+    stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream shared by torch and the library
+    torch.cuda.set_stream(stream)
+    solver.set_stream(stream.cuda_stream)
+    d_state = torch.from_numpy(b["state"]).to(dev)
+    d_ref = torch.from_numpy(b["ref"]).to(dev)
+    d_uprev = torch.from_numpy(b["u_prev"]).to(dev)
+    d_vdes = torch.from_numpy(b["v_des"]).to(dev)
+    d_u0 = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    d_cost = torch.empty(B, dtype=torch.float64, device=dev)
+    d_status = torch.empty(B, dtype=torch.int32, device=dev)
+    d_iters = torch.empty(B, dtype=torch.int32, device=dev)
+    # 32 B/problem record for the all-gather: acc, df, cost (f64) + status, iters (i32)
+    d_rec = torch.empty((B, 4), dtype=torch.float64, device=dev)
+    d_all = torch.empty((world * B, 4), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        flush.zero_()  # L2 flush between timed iterations (inputs are 36 MB < L2)
+        solver.solve_batch_device(B, d_state, d_ref, d_uprev, d_u0, v_des=d_vdes, cost=d_cost, status=d_status, iters=d_iters)
+        if world > 1:
+            d_rec[:, 0:2] = d_u0
+            d_rec[:, 2] = d_cost
+            d_rec[:, 3] = torch.stack((d_status, d_iters), dim=1).view(torch.float64).squeeze(1)
+            dist.all_gather_into_tensor(d_all, d_rec)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    # kernel-only time of one step (events directly around the kernel) for the roofline
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms = []
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0.record()
+        solver.solve_batch_device(B, d_state, d_ref, d_uprev, d_u0, v_des=d_vdes, cost=d_cost, status=d_status, iters=d_iters)
+        e1.record()
+        if world > 1:
+            d_rec[:, 0:2] = d_u0
+            d_rec[:, 2] = d_cost
+            d_rec[:, 3] = torch.stack((d_status, d_iters), dim=1).view(torch.float64).squeeze(1)
+            dist.all_gather_into_tensor(d_all, d_rec)
+        e1.synchronize()
+        kern_ms.append(e0.elapsed_time(e1))
+    t1.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = t0.elapsed_time(t1)
+    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms = float(tm.item())
+
+    status = d_status.cpu().numpy(); iters = d_iters.cpu().numpy()
+    conv_local = int((status == 0).sum())
+    cnt = torch.tensor([conv_local, int(iters.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    conv_total, iters_total = float(cnt[0].item()), float(cnt[1].item())
+    value = conv_total * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers (H2D + kernel + D2H timed)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    h_state, h_ref, h_uprev, h_vdes = pin(b["state"]), pin(b["ref"]), pin(b["u_prev"]), pin(b["v_des"])
+    solver.set_stream(None)  # back to the handle's own stream
+    for _ in range(2):
+        solver.solve_batch(h_state, h_ref, h_uprev, v_des=h_vdes)
+    barrier()
+    w0 = time.perf_counter()
+    h2d = d2h = launches = 0
+    for _ in range(args.steps):
+        r = solver.solve_batch(h_state, h_ref, h_uprev, v_des=h_vdes)
+        st = solver.stats()
+        h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
+        launches += st["kernel_launches"]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = conv_total * args.steps / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel: FP64 CUDA-core pipe, SURVEY 8(d)
+    fp64_peak = solver.fp64_peak_tflops()
+    k_ms = float(np.mean(kern_ms))
+    flops = float(iters.sum()) * (F_RIC + F_EVAL) * N
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    io_bytes = B * ((4 + 2 + 3 * (N + 1) + 1) * 8 + 3 * 8 + 2 * 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    tr_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    if os.path.exists(tr_file):
+        try:
+            traffic = json.load(open(tr_file)).get("bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {
+        "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+        "traffic": traffic,
+        "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
+        "flops_model": "sum_p iters_p * (1235 + 310) * N, SURVEY.md 8(d)",
+        "kernel": "mpc_solve_kernel", "kernel_ms": k_ms,
+        "hbm": {"achieved": io_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": io_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md",
+                "algorithmic_bytes_per_solve": io_bytes // B},
+    }
+
+    # ---- CPU baseline beside it: oracle on a bounded sample, all cores
+    cores = os.cpu_count() or 1
+    sample = args.cpu_sample or max(256, 48 * cores)
+    cpu_v, cpu_dt, cpu_conv, cpu_r = cpu_baseline(N, sample, cores)
+    ok = (cpu_r["status"] == 0) & (status[:sample] == 0) if rank == 0 else None
+    u0 = d_u0.cpu().numpy()
+    parity = {
+        "sample": sample, "status_equal": bool((cpu_r["status"] == status[:sample]).all()),
+        "max_abs_du": float(np.abs(u0[:sample] - cpu_r["u0"])[ok].max()) if ok.any() else None,
+    }
+
+    line = {
+        "metric": "converged MPC solves/sec at batch 64K, N=20", "value": value, "unit": "solves/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[2]: %d cold-start (start=0.0) solves per GPU, N=%d, paths 1-3 round-robin, "
+                               "perturbed states (SURVEY 8d)" % (B, N),
+                   "batch_per_gpu": B, "horizon": N, "l2": "256 MiB flush between steps (inputs 36 MB < L2)",
+                   "start": "zero", "max_iter": int(solver.cfg.max_iter)},
+        "converged_frac": conv_total / (world * B), "mean_iters": iters_total / (world * B),
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port",
+                         "sample": "first %d problems of the same batch, restated CPU interior point (oracle), NOT Ipopt" % sample},
+        "parity_vs_oracle": parity,
+        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(args.steps * 1),
+        "clocks": clocks,
+    }
+
+    if not args.no_latency:
+        # single-solve latency through the C ABI (host buffers, H2D + kernel + D2H), warm-started like the
+        # control loop; CPU oracle beside it
+        from oracle import oracle as O
+        s1 = capi.Solver(N, device=local)
+        ocfg = O.default_cfg(N)
+        nl = 200
+        warm_g = np.zeros((1, nt)); lat_g, lat_c = [], []
+        r0 = O.solve(ocfg, b["state"][0], b["ref"][0], 1.0, b["u_prev"][0])
+        warm_g[0] = r0["traj"]; warm_c = r0["traj"].copy()
+        for i in range(nl):
+            j = i % 64
+            w = warm_g.copy()
+            a = time.perf_counter()
+            s1.solve_batch(b["state"][j:j + 1], b["ref"][j:j + 1], b["u_prev"][j:j + 1], v_des=b["v_des"][j:j + 1], warm=w)
+            lat_g.append(time.perf_counter() - a)
+            a = time.perf_counter()
+            O.solve(ocfg, b["state"][j], b["ref"][j], 1.0, b["u_prev"][j], warm=warm_c)
+            lat_c.append(time.perf_counter() - a)
+        line["latency"] = {"gpu_p50_ms": 1e3 * float(np.percentile(lat_g[20:], 50)), "gpu_p99_ms": 1e3 * float(np.percentile(lat_g[20:], 99)),
+                           "cpu_oracle_p50_ms": 1e3 * float(np.percentile(lat_c[20:], 50)),
+                           "what": "batch of 1 through the C ABI incl. H2D/D2H, start = a neighbouring solution"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,163 @@
+"""ctypes binding of libmpc_b200.so (include/mpc_b200.h).
+
+The library is the product: if it is missing or cannot be loaded this module raises --
+there is no CPU or PyTorch fallback anywhere in the package.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+
+OPTIMAL, INFEASIBLE, UNBOUNDED, USERLIMIT, ERROR = 0, 1, 2, 3, 4
+STATUS_SYMBOLS = {0: "Optimal", 1: "Infeasible", 2: "Unbounded", 3: "UserLimit", 4: "Error"}
+HOST, DEVICE = 0, 1
+START_ZERO, START_ROLLOUT = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [("N", C.c_int32), ("max_iter", C.c_int32), ("start_mode", C.c_int32), ("device", C.c_int32),
+                ("dt", C.c_double), ("dt_control", C.c_double), ("L_a", C.c_double), ("L_b", C.c_double),
+                ("v_min", C.c_double), ("v_max", C.c_double), ("a_max", C.c_double), ("steer_max", C.c_double),
+                ("a_dmax", C.c_double), ("steer_dmax", C.c_double), ("tol", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
+                ("kernel_ms", C.c_float)]
+
+
+class MpcB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "libmpc_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libmpc_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "or `make -C mkz_mpc_path_follower_b200/csrc`.  There is no fallback path." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_void_p
+    L.mpcb200_version.restype = C.c_int
+    L.mpcb200_default_config.argtypes = [C.POINTER(Config), C.c_int32]
+    L.mpcb200_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    L.mpcb200_destroy.argtypes = [vp]
+    L.mpcb200_set_cost.argtypes = [vp, dp]
+    L.mpcb200_set_stream.argtypes = [vp, vp]
+    L.mpcb200_solve_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
+    L.mpcb200_set_path.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, dp, dp]
+    L.mpcb200_rollout.argtypes = [vp, C.c_int64, C.c_int32, dp, ip, C.c_int32, C.c_double, dp, dp]
+    L.mpcb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.mpcb200_fp64_peak.argtypes = [vp, dp]
+    L.mpcb200_last_error.argtypes = [vp]
+    L.mpcb200_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def default_config(N=8, **overrides):
+    c = Config()
+    rc = lib().mpcb200_default_config(C.byref(c), N)
+    if rc != 0:
+        raise MpcB200Error(rc, "default_config")
+    for k, v in overrides.items():
+        setattr(c, k, v)
+    return c
+
+
+def _ptr(a):
+    """numpy array -> host pointer; torch CUDA tensor -> device pointer; None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+class Solver(object):
+    """One handle = one GPU + one stream (mpcb200_create)."""
+
+    def __init__(self, N=8, config=None, **overrides):
+        self.cfg = config if config is not None else default_config(N, **overrides)
+        self.N = self.cfg.N
+        self._h = C.c_void_p()
+        rc = lib().mpcb200_create(C.byref(self._h), C.byref(self.cfg))
+        if rc != 0:
+            raise MpcB200Error(rc, lib().mpcb200_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().mpcb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MpcB200Error(rc, lib().mpcb200_last_error(self._h).decode())
+
+    def set_cost(self, w):
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        assert w.shape == (8,)
+        self._check(lib().mpcb200_set_cost(self._h, w.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(lib().mpcb200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def solve_batch(self, state, ref, u_prev, v_des=None, warm=None, want_traj=False, want_aux=True):
+        """Host (numpy) arrays in, numpy arrays out.  state (B,4); ref (B,3,N+1); u_prev (B,2)
+        = (d_f_current, acc_current); v_des (B,) or None; warm (B,6N+4) in/out or None."""
+        N = self.N
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        B = state.shape[0]
+        ref = np.ascontiguousarray(ref, dtype=np.float64)
+        u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+        if state.shape != (B, 4) or ref.shape != (B, 3, N + 1) or u_prev.shape != (B, 2):
+            raise ValueError("solve_batch: expected state (B,4), ref (B,3,N+1), u_prev (B,2)")
+        if v_des is not None:
+            v_des = np.ascontiguousarray(v_des, dtype=np.float64)
+            if v_des.shape != (B,):
+                raise ValueError("solve_batch: v_des must be (B,)")
+        if warm is not None:
+            if not (isinstance(warm, np.ndarray) and warm.dtype == np.float64 and warm.flags.c_contiguous
+                    and warm.shape == (B, 6 * N + 4)):
+                raise ValueError("solve_batch: warm must be a C-contiguous float64 (B,6N+4) array (updated in place)")
+        u0 = np.empty((B, 2))
+        cost = np.empty(B) if want_aux else None
+        status = np.empty(B, dtype=np.int32) if want_aux else None
+        iters = np.empty(B, dtype=np.int32) if want_aux else None
+        traj = np.empty((B, 6 * N + 4)) if want_traj else None
+        self._check(lib().mpcb200_solve_batch(self._h, B, _ptr(state), _ptr(ref), _ptr(v_des), _ptr(u_prev), _ptr(warm),
+                                              _ptr(u0), _ptr(cost), _ptr(status), _ptr(iters), _ptr(traj), HOST))
+        return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+    def solve_batch_device(self, B, state, ref, u_prev, u0, v_des=None, warm=None, cost=None, status=None,
+                           iters=None, traj=None):
+        """Device pointers (torch CUDA tensors, float64 / int32, contiguous); only enqueues on the
+        handle's stream."""
+        self._check(lib().mpcb200_solve_batch(self._h, B, _ptr(state), _ptr(ref), _ptr(v_des), _ptr(u_prev), _ptr(warm),
+                                              _ptr(u0), _ptr(cost), _ptr(status), _ptr(iters), _ptr(traj), DEVICE))
+
+    def stats(self):
+        s = Stats()
+        self._check(lib().mpcb200_get_stats(self._h, C.byref(s)))
+        return {"kernel_launches": s.kernel_launches, "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes,
+                "kernel_ms": s.kernel_ms}
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self._check(lib().mpcb200_fp64_peak(self._h, C.byref(v)))
+        return v.value

@@ -1,0 +1,320 @@
+// mpc_b200.cu -- C ABI (include/mpc_b200.h) and kernel launches for sm_100a.
+//
+// One handle = one GPU + one stream.  Problems are independent: a persistent grid of warps
+// pulls problem indices from a device counter (iteration counts differ per problem, so a
+// dynamic queue keeps the SMs level), solves each with mpc_kernel.cuh::solve_problem and
+// writes the per-problem record.  No CPU path exists in this library.
+#include "../../include/mpc_b200.h"
+#include "mpc_kernel.cuh"
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+using namespace mpcb200;
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 4;
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned long long* counter) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5;
+    double* smem = smem_all + (size_t)warp * smem_doubles_per_warp(cfg.N);
+    for (;;) {
+        unsigned long long b = 0;
+        if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned long long)B) break;
+        solve_problem(cfg, io, (long)b, smem);
+        __syncwarp();
+    }
+}
+
+// FP64 FMA throughput probe: 8 independent chains per thread
+__global__ void fp64_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct mpcb200_handle {
+    mpcb200_config cfg;
+    double w[8];
+    int device = 0;
+    int num_sms = 0;
+    int blocks_per_sm = 0;
+    size_t smem_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long* d_counter = nullptr;
+    DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
+    mpcb200_stats stats;
+    char err[512];
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(mpcb200_handle* h, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    char* dst = h ? h->err : g_err;
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                          \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail(h, MPCB200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+static int ensure(mpcb200_handle* h, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CUDA_TRY(h, cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t cap = bytes + bytes / 4;
+    CUDA_TRY(h, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return 0;
+}
+
+static KCfg make_kcfg(const mpcb200_handle* h) {
+    KCfg k;
+    memset(&k, 0, sizeof(k));
+    const mpcb200_config& c = h->cfg;
+    k.N = c.N; k.max_iter = c.max_iter; k.start_mode = c.start_mode;
+    k.dt = c.dt; k.dtc = c.dt_control; k.La = c.L_a; k.Lb = c.L_b;
+    k.vmin = c.v_min; k.vmax = c.v_max; k.amax = c.a_max; k.smax = c.steer_max;
+    k.admax = c.a_dmax; k.sdmax = c.steer_dmax; k.tol = c.tol;
+    for (int i = 0; i < 8; i++) k.w[i] = h->w[i];
+    return k;
+}
+
+extern "C" {
+
+int mpcb200_version(void) { return MPCB200_VERSION; }
+
+int mpcb200_default_config(mpcb200_config* c, int32_t N) {
+    if (!c) return MPCB200_EINVAL;
+    memset(c, 0, sizeof(*c));
+    c->N = N;
+    c->max_iter = 200;
+    c->start_mode = MPCB200_START_ZERO;
+    c->device = 0;
+    c->dt = 0.20;          /* MKZMPCPathFollower.jl:33 */
+    c->dt_control = 0.10;  /* :28 */
+    c->L_a = 1.108;        /* :31 */
+    c->L_b = 1.742;        /* :32 */
+    c->v_min = 0.0;        /* :47 */
+    c->v_max = 20.0;       /* :48 */
+    c->a_max = 1.0;        /* :44 */
+    c->steer_max = 0.5;    /* :41 */
+    c->a_dmax = 1.5;       /* :45 */
+    c->steer_dmax = 0.5;   /* :42 */
+    c->tol = 1e-8;
+    return MPCB200_OK;
+}
+
+int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
+    if (!out || !cfg) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: NULL argument");
+    *out = nullptr;
+    if (cfg->N < 3 || cfg->N > 31) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: horizon N=%d outside [3,31]", cfg->N);
+    if (!(cfg->dt > 0) || !(cfg->dt_control > 0) || !(cfg->L_b > 0) || !(cfg->v_max > cfg->v_min) || !(cfg->a_max > 0) ||
+        !(cfg->steer_max > 0 && cfg->steer_max < 1.5) || !(cfg->a_dmax > 0) || !(cfg->steer_dmax > 0) || !(cfg->tol > 0) ||
+        cfg->max_iter < 0)
+        return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: invalid model constants");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, MPCB200_ENODEVICE, "mpcb200_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: device %d of %d", cfg->device, ndev);
+    mpcb200_handle* h = new (std::nothrow) mpcb200_handle();
+    if (!h) return fail(nullptr, MPCB200_ENOMEM, "mpcb200_create: out of host memory");
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    h->err[0] = 0;
+    memset(&h->stats, 0, sizeof(h->stats));
+    /* defaults of MKZMPCPathFollower.jl:51-59 in update_cost order */
+    const double w0[8] = {9.0, 9.0, 10.0, 0.0, 100.0, 1000.0, 0.0, 0.0};
+    memcpy(h->w, w0, sizeof(w0));
+#define TRY_OR_FREE(expr)                                                                 \
+    do {                                                                                  \
+        cudaError_t e2 = (expr);                                                          \
+        if (e2 != cudaSuccess) {                                                          \
+            fail(nullptr, MPCB200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e2));        \
+            delete h;                                                                     \
+            return MPCB200_ECUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+    TRY_OR_FREE(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    TRY_OR_FREE(cudaGetDeviceProperties(&prop, h->device));
+    h->num_sms = prop.multiProcessorCount;
+    TRY_OR_FREE(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    TRY_OR_FREE(cudaEventCreate(&h->ev0));
+    TRY_OR_FREE(cudaEventCreate(&h->ev1));
+    TRY_OR_FREE(cudaMalloc((void**)&h->d_counter, sizeof(unsigned long long)));
+    h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_warp(cfg->N) * sizeof(double);
+    TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
+    if (h->blocks_per_sm < 1) h->blocks_per_sm = 1;
+#undef TRY_OR_FREE
+    *out = h;
+    return MPCB200_OK;
+}
+
+int mpcb200_destroy(mpcb200_handle* h) {
+    if (!h) return MPCB200_EINVAL;
+    cudaSetDevice(h->device);
+    DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj};
+    for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+    if (h->d_counter) cudaFree(h->d_counter);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return MPCB200_OK;
+}
+
+int mpcb200_set_cost(mpcb200_handle* h, const double w[8]) {
+    if (!h || !w) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost: NULL argument");
+    for (int i = 0; i < 8; i++) if (!(w[i] >= 0.0)) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost: weight %d is negative or NaN", i);
+    memcpy(h->w, w, 8 * sizeof(double));
+    return MPCB200_OK;
+}
+
+int mpcb200_set_stream(mpcb200_handle* h, void* s) {
+    if (!h) return MPCB200_EINVAL;
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return MPCB200_OK;
+}
+
+static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io) {
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), h->stream));
+    long long blocks_needed = (B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    long long max_blocks = (long long)h->num_sms * h->blocks_per_sm;
+    int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
+    if (grid < 1) grid = 1;
+    mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, (long long)B, h->d_counter);
+    CUDA_TRY(h, cudaGetLastError());
+    h->stats.kernel_launches += 1;
+    return 0;
+}
+
+int mpcb200_solve_batch(mpcb200_handle* h, int64_t B, const double* state, const double* ref, const double* v_des,
+                        const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
+                        double* traj, int32_t mem_space) {
+    if (!h) return MPCB200_EINVAL;
+    if (B < 0) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch: B=%lld", (long long)B);
+    if (mem_space != MPCB200_HOST && mem_space != MPCB200_DEVICE) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch: mem_space=%d", mem_space);
+    memset(&h->stats, 0, sizeof(h->stats));
+    if (B == 0) return MPCB200_OK;
+    if (!state || !ref || !u_prev || !u0) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch: state, ref, u_prev and u0 are required");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = h->cfg.N;
+    const size_t nt = 6 * (size_t)N + 4, nr = 3 * ((size_t)N + 1);
+    if (mem_space == MPCB200_DEVICE) {
+        BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj};
+        return launch_solve(h, B, io);
+    }
+    /* host pointers: stage through the handle's device buffers */
+    const size_t bs = B * 4 * sizeof(double), br = B * nr * sizeof(double), bu = B * 2 * sizeof(double), bt = B * nt * sizeof(double);
+    int rc;
+    if ((rc = ensure(h, h->d_state, bs))) return rc;
+    if ((rc = ensure(h, h->d_ref, br))) return rc;
+    if ((rc = ensure(h, h->d_uprev, bu))) return rc;
+    if ((rc = ensure(h, h->d_u0, bu))) return rc;
+    if (v_des && (rc = ensure(h, h->d_vdes, B * sizeof(double)))) return rc;
+    if (warm && (rc = ensure(h, h->d_warm, bt))) return rc;
+    if (cost && (rc = ensure(h, h->d_cost, B * sizeof(double)))) return rc;
+    if (status && (rc = ensure(h, h->d_status, B * sizeof(int32_t)))) return rc;
+    if (iters && (rc = ensure(h, h->d_iters, B * sizeof(int32_t)))) return rc;
+    if (traj && (rc = ensure(h, h->d_traj, bt))) return rc;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, state, bs, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_ref.p, ref, br, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_uprev.p, u_prev, bu, cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += bs + br + bu;
+    if (v_des) { CUDA_TRY(h, cudaMemcpyAsync(h->d_vdes.p, v_des, B * sizeof(double), cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += B * sizeof(double); }
+    if (warm) { CUDA_TRY(h, cudaMemcpyAsync(h->d_warm.p, warm, bt, cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += bt; }
+    BatchPtrs io{(const double*)h->d_state.p, (const double*)h->d_ref.p, v_des ? (const double*)h->d_vdes.p : nullptr,
+                 (const double*)h->d_uprev.p, warm ? (double*)h->d_warm.p : nullptr, (double*)h->d_u0.p,
+                 cost ? (double*)h->d_cost.p : nullptr, status ? (int*)h->d_status.p : nullptr,
+                 iters ? (int*)h->d_iters.p : nullptr, traj ? (double*)h->d_traj.p : nullptr};
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    if ((rc = launch_solve(h, B, io))) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaMemcpyAsync(u0, h->d_u0.p, bu, cudaMemcpyDeviceToHost, s));
+    h->stats.d2h_bytes += bu;
+    if (cost) { CUDA_TRY(h, cudaMemcpyAsync(cost, h->d_cost.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(double); }
+    if (status) { CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
+    if (iters) { CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
+    if (traj) { CUDA_TRY(h, cudaMemcpyAsync(traj, h->d_traj.p, bt, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bt; }
+    if (warm) { CUDA_TRY(h, cudaMemcpyAsync(warm, h->d_warm.p, bt, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bt; }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return MPCB200_OK;
+}
+
+int mpcb200_set_path(mpcb200_handle* h, int32_t, int32_t, const double*, const double*, const double*, const double*, const double*) {
+    return fail(h, MPCB200_EINVAL, "mpcb200_set_path: on-device reference generation is not built yet");
+}
+
+int mpcb200_rollout(mpcb200_handle* h, int64_t, int32_t, const double*, const int32_t*, int32_t, double, double*, double*) {
+    return fail(h, MPCB200_EINVAL, "mpcb200_rollout: closed-loop rollout is not built yet");
+}
+
+int mpcb200_get_stats(mpcb200_handle* h, mpcb200_stats* out) {
+    if (!h || !out) return MPCB200_EINVAL;
+    *out = h->stats;
+    return MPCB200_OK;
+}
+
+int mpcb200_fp64_peak(mpcb200_handle* h, double* tflops) {
+    if (!h || !tflops) return MPCB200_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int threads = 256, blocks = h->num_sms * 8, iters = 1 << 15;
+    double* d = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&d, (size_t)threads * blocks * sizeof(double)));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, h->stream>>>(d, iters);
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    const double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return MPCB200_OK;
+}
+
+const char* mpcb200_last_error(mpcb200_handle* h) { return h ? h->err : g_err; }
+
+}  // extern "C"

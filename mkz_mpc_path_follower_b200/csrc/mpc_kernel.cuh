@@ -92,7 +92,12 @@ struct KCfg {
 #define SDS 51      // odd stride: lane-k writes of one field are bank-conflict free
 #define KST_STRIDE 14
 
-MPC_DEV int smem_doubles_per_warp(int N) { return W_SD + (N + 1) * SDS + N * KST_STRIDE + 2; }
+#ifdef MPC_HOST_EMU
+#define MPC_HD inline
+#else
+#define MPC_HD __host__ __device__ __forceinline__
+#endif
+MPC_HD int smem_doubles_per_warp(int N) { return W_SD + (N + 1) * SDS + N * KST_STRIDE + 2; }
 
 MPC_DEV double warp_sum(double v) {
     for (int o = 16; o; o >>= 1) v += shfl_xor(v, o);

@@ -1,0 +1,34 @@
+"""CPU check of the CUDA solver's source: mpc_kernel.cuh compiled by g++ against a 32-lane
+coroutine emulator (tests/emu, test infrastructure only) must follow the oracle iterate for
+iterate.  This is what lets kernel changes be checked without a GPU; the real parity tests are
+the -m gpu ones, through the C ABI."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from mkz_mpc_path_follower_b200 import workload as W
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+
+@pytest.mark.parametrize("N,B", [(8, 24), (20, 10), (3, 4)])
+def test_emulated_kernel_matches_oracle(oracle, N, B):
+    import emu as E
+    cfg = oracle.default_cfg(N)
+    b = W.make_batch(B, N)
+    o = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], want_traj=True, n_threads=4)
+    e = E.solve_batch(E.kcfg_from_oracle(cfg), b["state"], b["ref"], b["v_des"], b["u_prev"], want_traj=True)
+    assert (o["status"] == e["status"]).all()
+    ok = o["status"] == 0
+    assert ok.sum() >= B // 2
+    assert np.abs(o["u0"] - e["u0"])[ok].max() <= 1e-9
+    assert (np.abs(o["cost"] - e["cost"])[ok] <= 1e-9 * np.maximum(1, np.abs(o["cost"][ok]))).all()
+    assert np.abs(o["traj"] - e["traj"])[ok].max() <= 1e-8
+    # warm start path
+    warm_o = o["traj"].copy(); warm_e = o["traj"].copy()
+    o2 = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], warm=warm_o, n_threads=4)
+    e2 = E.solve_batch(E.kcfg_from_oracle(cfg), b["state"], b["ref"], b["v_des"], b["u_prev"], warm=warm_e)
+    assert (o2["status"] == e2["status"]).all() and (o2["iters"] == e2["iters"]).all()
+    assert np.abs(o2["u0"] - e2["u0"])[o2["status"] == 0].max() <= 1e-9

@@ -1,0 +1,195 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libmpc_b200.so), against the CPU
+oracle on the same seeded inputs.  Tolerances are BASELINE.json's: same status, |du| <= 1e-5 on
+(acc, d_f), relative cost <= 1e-6."""
+import numpy as np
+import pytest
+
+from mkz_mpc_path_follower_b200 import workload as W
+
+pytestmark = pytest.mark.gpu
+
+U_TOL = 1e-5
+COST_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from mkz_mpc_path_follower_b200 import capi as c
+    c.lib()
+    return c
+
+
+def _ocfg(oracle, solver):
+    c = solver.cfg
+    return oracle.default_cfg(c.N, tol=c.tol, max_iter=c.max_iter)
+
+
+def _compare(g, o, min_conv=0.9):
+    assert (g["status"] == o["status"]).all(), np.nonzero(g["status"] != o["status"])
+    ok = o["status"] == 0
+    assert ok.mean() >= min_conv
+    du = np.abs(g["u0"] - o["u0"])[ok]
+    assert du.max() <= U_TOL, du.max()
+    rc = np.abs(g["cost"] - o["cost"])[ok] / np.maximum(1.0, np.abs(o["cost"][ok]))
+    assert rc.max() <= COST_RTOL, rc.max()
+    return ok
+
+
+@pytest.mark.parametrize("N,B,paths", [(8, 256, (1,)), (20, 192, (1, 2, 3)), (3, 32, (2,)), (31, 24, (3,))])
+def test_cold_parity(capi, oracle, N, B, paths):
+    s = capi.Solver(N)
+    b = W.make_batch(B, N, path_ids=paths)
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], want_traj=True, n_threads=8)
+    ok = _compare(g, o, min_conv=0.7 if N == 31 else 0.9)
+    assert np.abs(g["traj"] - o["traj"])[ok].max() <= 1e-5
+    st = s.stats()
+    assert st["kernel_launches"] == 1 and st["h2d_bytes"] > 0 and st["d2h_bytes"] > 0
+
+
+@pytest.mark.parametrize("N,B", [(8, 128), (20, 96)])
+def test_warm_parity_and_inout_buffer(capi, oracle, N, B):
+    s = capi.Solver(N)
+    b = W.make_batch(B, N)
+    ocfg = _ocfg(oracle, s)
+    o1 = oracle.solve_batch(ocfg, b["state"], b["ref"], b["v_des"], b["u_prev"], want_traj=True, n_threads=8)
+    # perturb the state a little: "next control step" from the previous solution
+    rng = np.random.default_rng(5)
+    st2 = b["state"] + rng.normal(scale=[0.05, 0.05, 0.005, 0.05], size=(B, 4))
+    st2[:, 3] = np.clip(st2[:, 3], 0, 20)
+    warm_o = o1["traj"].copy(); warm_g = o1["traj"].copy()
+    o2 = oracle.solve_batch(ocfg, st2, b["ref"], b["v_des"], b["u_prev"], warm=warm_o, n_threads=8)
+    g2 = s.solve_batch(st2, b["ref"], b["u_prev"], v_des=b["v_des"], warm=warm_g)
+    ok = _compare(g2, o2)
+    assert np.abs(warm_g - warm_o)[ok].max() <= 1e-5      # warm is written back with the solution
+    assert g2["iters"][ok].mean() < 20
+
+
+def test_weights_and_vdes(capi, oracle):
+    N, B = 8, 64
+    w = [5.0, 7.0, 20.0, 3.0, 50.0, 500.0, 0.5, 2.0]
+    s = capi.Solver(N); s.set_cost(w)
+    b = W.make_batch(B, N, v_des=6.0)
+    ocfg = oracle.default_cfg(N, weights=w, max_iter=s.cfg.max_iter)
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
+    o = oracle.solve_batch(ocfg, b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=8)
+    _compare(g, o, min_conv=0.8)
+
+
+def test_edge_cases(capi, oracle):
+    N = 8
+    s = capi.Solver(N)
+    b = W.make_batch(4, N)
+    # empty batch
+    g = s.solve_batch(b["state"][:0], b["ref"][:0], b["u_prev"][:0])
+    assert g["u0"].shape == (0, 2)
+    # batch of one, v_des NULL
+    g = s.solve_batch(b["state"][:1], b["ref"][:1], b["u_prev"][:1])
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"][:1], b["ref"][:1], None, b["u_prev"][:1])
+    _compare(g, o, min_conv=0.0)
+    # infeasible inputs: v0 < v_min, previous steering outside box + rate step
+    st = b["state"].copy(); st[0, 3] = -0.5
+    up = b["u_prev"].copy(); up[1, 0] = 0.7
+    g = s.solve_batch(st, b["ref"], up, v_des=b["v_des"])
+    o = oracle.solve_batch(_ocfg(oracle, s), st, b["ref"], b["v_des"], up)
+    assert g["status"][0] == capi.INFEASIBLE and g["status"][1] == capi.INFEASIBLE
+    assert (g["status"] == o["status"]).all()
+    # iteration cap -> UserLimit
+    s2 = capi.Solver(N, max_iter=3)
+    g = s2.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
+    assert (g["status"] == capi.USERLIMIT).all() and (g["iters"] == 3).all()
+    # argument validation
+    with pytest.raises(ValueError):
+        s.solve_batch(b["state"], b["ref"][:, :, :-1], b["u_prev"])
+    with pytest.raises(capi.MpcB200Error):
+        capi.Solver(64)
+    with pytest.raises(capi.MpcB200Error):
+        s.set_cost([-1.0] * 8)
+
+
+def test_standstill_start(capi, oracle):
+    """The simulator starts at v = 0 exactly on the bound v_min (vehicle_simulator.py:31)."""
+    N = 8
+    s = capi.Solver(N)
+    b = W.make_batch(16, N, path_ids=(3,))
+    st = b["state"].copy(); st[:, 3] = 0.0
+    up = np.zeros((16, 2))
+    g = s.solve_batch(st, b["ref"], up, v_des=b["v_des"])
+    o = oracle.solve_batch(_ocfg(oracle, s), st, b["ref"], b["v_des"], up, n_threads=4)
+    _compare(g, o, min_conv=0.5)
+
+
+def _feasibility(cfg, b, g, N):
+    """size-independent property: a point returned as Optimal satisfies the reference NLP's
+    constraints (dynamics of MKZMPCPathFollower.jl:115-123, bounds, rate rows)."""
+    t = g["traj"]
+    x, y, v, psi = (t[:, i * (N + 1):(i + 1) * (N + 1)] for i in range(4))
+    df = t[:, 4 * (N + 1):4 * (N + 1) + N]; acc = t[:, 4 * (N + 1) + N:]
+    r = cfg.L_b / (cfg.L_a + cfg.L_b)
+    bta = np.arctan(r * np.tan(df))
+    res = np.stack((x[:, 1:] - (x[:, :-1] + cfg.dt * v[:, :-1] * np.cos(psi[:, :-1] + bta)),
+                    y[:, 1:] - (y[:, :-1] + cfg.dt * v[:, :-1] * np.sin(psi[:, :-1] + bta)),
+                    psi[:, 1:] - (psi[:, :-1] + cfg.dt * v[:, :-1] / cfg.L_b * np.sin(bta)),
+                    v[:, 1:] - (v[:, :-1] + cfg.dt * acc)))
+    init = np.abs(np.stack((x[:, 0], y[:, 0], psi[:, 0], v[:, 0]), axis=1) - b["state"]).max(axis=1)
+    dyn = np.abs(res).max(axis=(0, 2))
+    bnd = np.maximum.reduce([(-v).max(axis=1), (v - cfg.v_max).max(axis=1), (np.abs(acc) - cfg.a_max).max(axis=1),
+                             (np.abs(df) - cfg.steer_max).max(axis=1)])
+    first = np.maximum(np.abs(df[:, 0] - b["u_prev"][:, 0]) - cfg.steer_dmax * cfg.dt_control,
+                       np.abs(acc[:, 0] - b["u_prev"][:, 1]) - cfg.a_dmax * cfg.dt_control)
+    later = np.maximum((np.abs(np.diff(df, axis=1))[:, 1:] - cfg.steer_dmax * cfg.dt).max(axis=1),
+                       (np.abs(np.diff(acc, axis=1))[:, 1:] - cfg.a_dmax * cfg.dt).max(axis=1))
+    return np.maximum.reduce([init, dyn, bnd, first, later])
+
+
+@pytest.mark.parametrize("N,B,paths", [(8, 4096, (1,)), (20, 65536, (1, 2, 3))])
+def test_full_size_properties(capi, oracle, N, B, paths):
+    """BASELINE.json configs[1] and configs[2] at full size: feasibility of every Optimal point,
+    slice reproducibility (any contiguous slice gives bit-identical results), idempotence of a
+    warm re-solve, and oracle parity on a random subset."""
+    s = capi.Solver(N)
+    b = W.make_batch(B, N, path_ids=paths)
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    ok = g["status"] == 0
+    assert ok.mean() > 0.93
+    viol = _feasibility(s.cfg, b, g, N)
+    assert viol[ok].max() <= 2e-8
+    # slice reproducibility
+    lo, hi = B // 3, B // 3 + 500
+    bs = W.make_batch(hi - lo, N, path_ids=paths, b0=lo)
+    assert np.array_equal(bs["state"], b["state"][lo:hi])
+    g2 = s.solve_batch(bs["state"], bs["ref"], bs["u_prev"], v_des=bs["v_des"])
+    assert np.array_equal(g2["u0"], g["u0"][lo:hi]) and np.array_equal(g2["status"], g["status"][lo:hi])
+    assert np.array_equal(g2["iters"], g["iters"][lo:hi])
+    # idempotence
+    warm = g["traj"].copy()
+    g3 = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], warm=warm)
+    both = ok & (g3["status"] == 0)
+    assert both.sum() >= 0.99 * ok.sum()
+    assert np.abs(g3["u0"] - g["u0"])[both].max() <= 2e-5   # two iterate paths, stopping-rule accuracy
+    # oracle on a subset
+    idx = np.random.default_rng(11).choice(B, size=384, replace=False)
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"][idx], b["ref"][idx], b["v_des"][idx], b["u_prev"][idx], n_threads=8)
+    _compare({k: g[k][idx] for k in ("u0", "cost", "status")}, o)
+
+
+def test_julia_module_mirror(capi, oracle):
+    """The six-function API of MKZMPCPathFollower.jl:132-207, batch of one, one control step."""
+    from mkz_mpc_path_follower_b200.mpc_path_follower import MKZMPCPathFollower
+    kmpc = MKZMPCPathFollower(N=8)
+    assert kmpc.N == 8 and kmpc.dt == 0.2
+    kmpc.update_cost(9.0, 9.0, 10.0, 0.0, 100.0, 1000.0, 0.0, 0.0)
+    b = W.make_batch(1, 8, path_ids=(3,))
+    x, y, psi, v = b["state"][0]
+    kmpc.update_init_cond(x, y, psi, v)
+    kmpc.update_reference(b["ref"][0, 0], b["ref"][0, 1], b["ref"][0, 2], 1.0)
+    kmpc.update_current_input(b["u_prev"][0, 0], b["u_prev"][0, 1])
+    a_opt, df_opt, is_opt = kmpc.solve_model()
+    res = kmpc.get_solver_results()
+    assert len(res) == 9 and res[0].shape == (9,) and res[7].shape == (8,)
+    assert is_opt in ("Optimal", "Error", "UserLimit")
+    if is_opt == "Optimal":
+        assert res[8][0] == a_opt and res[7][0] == df_opt       # acc_opt[1], d_f_opt[1]
+        assert abs(res[0][0] - x) < 1e-7 and abs(res[2][0] - v) < 1e-7   # x_mpc[1], v_mpc[1]: order x,y,v,psi
+    with pytest.raises(TypeError):
+        kmpc.update_reference(np.zeros(3), np.zeros(9), np.zeros(9), 1.0)
