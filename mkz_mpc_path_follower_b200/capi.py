@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpc_b200.so")
+LIB_PATH = os.environ.get("MPCB200_LIB") or os.path.join(_HERE, "libmpc_b200.so")
 
 OPTIMAL, INFEASIBLE, UNBOUNDED, USERLIMIT, ERROR = 0, 1, 2, 3, 4
 STATUS_SYMBOLS = {0: "Optimal", 1: "Infeasible", 2: "Unbounded", 3: "UserLimit", 4: "Error"}

@@ -21,11 +21,15 @@ namespace {
 
 constexpr int WARPS_PER_BLOCK = 4;
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+#ifndef MPC_MIN_BLOCKS
+#define MPC_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MPC_MIN_BLOCKS)
 mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
-    double* smem = smem_all + (size_t)warp * smem_doubles_per_warp(cfg.N);
+    const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_warp(cfg.N));
+    WarpSolver::init_work(smem);
     for (;;) {
         unsigned long long b = 0;
         if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
@@ -106,6 +110,7 @@ static KCfg make_kcfg(const mpcb200_handle* h) {
     k.vmin = c.v_min; k.vmax = c.v_max; k.amax = c.a_max; k.smax = c.steer_max;
     k.admax = c.a_dmax; k.sdmax = c.steer_dmax; k.tol = c.tol;
     for (int i = 0; i < 8; i++) k.w[i] = h->w[i];
+    kcfg_finalize(k);
     return k;
 }
 
@@ -177,8 +182,10 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
     TRY_OR_FREE(cudaMalloc((void**)&h->d_counter, sizeof(unsigned long long)));
     h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_warp(cfg->N) * sizeof(double);
     TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
     if (h->blocks_per_sm < 1) h->blocks_per_sm = 1;
+    if (const char* e = getenv("MPCB200_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v; }  /* tuning aid */
 #undef TRY_OR_FREE
     *out = h;
     return MPCB200_OK;

@@ -11,25 +11,42 @@
 // input (acc,df), the multipliers of the equality rows that define s_k, its bound multipliers
 // and the rate row that ends at u_k.  Stage-parallel work (model evaluation, residuals,
 // multiplier updates, norms) runs with lanes = stages; the serial Riccati recursion switches
-// to lanes = matrix entries, with per-stage data staged in shared memory.
+// to lanes = matrix entries, with per-stage records staged in shared memory.
 //
 // The iteration follows oracle/mpc_oracle.c step for step (same formulas, same constants);
 // only the linear algebra differs (condensed Riccati here, full-space Bunch-Kaufman there).
+//
+// Control flow is a warp-uniform phase machine so that every heavy routine (record assembly,
+// Riccati backward/forward, dual recovery, trial-point evaluation) exists exactly once in the
+// instruction stream: least-squares multiplier solve, Newton solves with inertia-correction
+// retries, second-order corrections and line-search trials all pass through the same code.
+// Per-lane state carried across the Riccati passes is kept small (the iterate, the step and a
+// dozen scalars) so that 16 warps per SM fit in the register file.
 #pragma once
 #include "warp_prims.cuh"
 
 namespace mpcb200 {
 
+#ifdef MPC_HOST_EMU
+#define MPC_HD inline
+#else
+#define MPC_HD __host__ __device__ __forceinline__
+#endif
+
 struct KCfg {
     int N, max_iter, start_mode, pad_;
     double dt, dtc, La, Lb, vmin, vmax, amax, smax, admax, sdmax, tol;
     double w[8];  // cx, cy, cpsi, cv, cdacc, cddf, cacc, cdf
+    // derived on the host by kcfg_finalize(): bounds relaxed by Ipopt's bound_relax_factor etc.
+    double vLo, vHi, aLo, aHi, dLo, dHi;
+    double rHiFirst[2], rHiLater[2];  // relaxed half-width of the rate rows [steer, acc]; rLo = -rHi
+    double rfrac;                     // L_b / (L_a + L_b)
+    double mu_min;
 };
 
 // ---- Ipopt 3.12 default constants (same values as oracle/mpc_oracle.c) ----
 #define K_KAPPA_EPS 10.0
 #define K_KAPPA_MU 0.2
-#define K_THETA_MU 1.5
 #define K_MU_INIT 0.1
 #define K_TAU_MIN 0.99
 #define K_BOUND_PUSH 1e-2
@@ -59,20 +76,41 @@ struct KCfg {
 #define K_ACCEPT_ITER 15
 #define K_EPS 2.220446049250313e-16
 
-// ---- shared-memory layout of one warp, in doubles ----
-// work area
+MPC_HD void kcfg_finalize(KCfg& c) {
+    auto mx = [](double a, double b) { return a > b ? a : b; };
+    auto ab = [](double a) { return a < 0 ? -a : a; };
+    c.vLo = c.vmin - K_BOUND_RELAX * mx(1.0, ab(c.vmin)); c.vHi = c.vmax + K_BOUND_RELAX * mx(1.0, ab(c.vmax));
+    c.aLo = -c.amax - K_BOUND_RELAX * mx(1.0, c.amax); c.aHi = c.amax + K_BOUND_RELAX * mx(1.0, c.amax);
+    c.dLo = -c.smax - K_BOUND_RELAX * mx(1.0, c.smax); c.dHi = c.smax + K_BOUND_RELAX * mx(1.0, c.smax);
+    const double h[2] = {c.dtc, c.dt};
+    for (int i = 0; i < 2; i++) {
+        const double ld = c.sdmax * h[i], la = c.admax * h[i];
+        double* dst = (i == 0) ? c.rHiFirst : c.rHiLater;
+        dst[0] = ld + K_BOUND_RELAX * mx(1.0, ld);
+        dst[1] = la + K_BOUND_RELAX * mx(1.0, la);
+    }
+    c.rfrac = c.Lb / (c.La + c.Lb);
+    const double t = c.tol < 1e-4 ? c.tol : 1e-4;
+    c.mu_min = t / (K_KAPPA_EPS + 1.0);
+}
+
+// ---- shared-memory layout of one warp, in doubles (every pair used by a 16-byte load is even-aligned) ----
 #define W_P 0       // 6x6 cost-to-go Hessian, full symmetric storage, row stride 6
 #define W_PV 36     // 6   cost-to-go gradient
-#define W_T 42      // 6x6: columns psi,v,a,df of P*M and column 4 = P*r + p
-#define W_F 78      // 6x6 stage Hessian F over (x,y,psi,v,a,df)
-#define W_FV 114    // 6   stage gradient f
-#define W_EX 120    // 6   unit vector e_x
-#define W_EY 126    // 6   unit vector e_y
-#define W_Z 132     // constant 0.0
-#define W_DUMMY 133 // sink for inactive lanes
-#define W_SD 134    // stage records start here
-// stage record (dense)
-#define SD_MT 0     // 5 columns x 6: d(next state, next prev-input)/d(psi | v | a | df) and residual r
+#define W_TT 42     // 5x6: TT[c][i] = (P*M)[i][c] for c = psi,v,a,df and c = 4: P r + p
+#define W_F 72      // 6x6 stage Hessian F over (x,y,psi,v,a,df)
+#define W_FV 108    // 6   stage gradient f
+#define W_EX 114    // 6   unit vector e_x
+#define W_EY 120    // 6   unit vector e_y
+#define W_Z 126     // 6   zeros
+#define W_C 132     // Ca, Cd of the current stage (copied from the record by idle lanes of round B)
+#define W_NC 134    // (-Ca, 0), (0, -Cd) of the current stage
+#define W_DUMMY 138 // sink for inactive lanes (2)
+#define W_CONST 140 // problem constants: state[4], u_prev[2], v_des, pad
+#define W_SD 148    // stage records start here
+// stage record
+#define SD_MT 0     // 5 columns x 6: d(next state, next prev-input)/d(psi | v | a | df), then residual r
+#define SD_R 24     //   r column (dynamics residual; record N: initial-condition residual)
 #define SD_HXX 30
 #define SD_HYY 31
 #define SD_HPP 32
@@ -84,25 +122,20 @@ struct KCfg {
 #define SD_HDD 38
 #define SD_CA 39
 #define SD_CD 40
-#define SD_NCA 41
-#define SD_ZERO2 42
-#define SD_NCD 43
-#define SD_GX 44  // GX,GY,GP,GV,GA,GD
-#define SD_NF 50
-#define SDS 51      // odd stride: lane-k writes of one field are bank-conflict free
+#define SD_ZERO 41  // constant 0 (H entries that are structurally zero point here)
+#define SD_NCA 42   // -Ca
+#define SD_NCD 43   // -Cd
+#define SD_GX 46    // GX,GY,GP,GV,GA,GD (condensed gradient)
+#define SD_SRW 52   // (Sigma_s + delta_w) of the rate row [steer, acc]
+#define SD_BR 54    // -mu/ss_L + mu/ss_U of the rate row
+#define SD_DR 56    // rate-row residual used as right-hand side
+#define SDS 58      // even: records are 16-byte aligned
 #define KST_STRIDE 14
 
-#ifdef MPC_HOST_EMU
-#define MPC_HD inline
-#else
-#define MPC_HD __host__ __device__ __forceinline__
-#endif
-MPC_HD int smem_doubles_per_warp(int N) { return W_SD + (N + 1) * SDS + N * KST_STRIDE + 2; }
+MPC_HD int smem_doubles_per_warp(int N) { return W_SD + (N + 1) * SDS + N * KST_STRIDE; }
 
-MPC_DEV double warp_sum(double v) {
-    for (int o = 16; o; o >>= 1) v += shfl_xor(v, o);
-    return v;
-}
+MPC_DEV double dmax_(double a, double b) { return a > b ? a : b; }
+MPC_DEV double dmin_(double a, double b) { return a < b ? a : b; }
 MPC_DEV double warp_max(double v) {
     for (int o = 16; o; o >>= 1) { double t = shfl_xor(v, o); v = (t > v || t != t) ? t : v; }
     return v;
@@ -111,873 +144,870 @@ MPC_DEV double warp_min(double v) {
     for (int o = 16; o; o >>= 1) { double t = shfl_xor(v, o); v = (t < v) ? t : v; }
     return v;
 }
+MPC_DEV double warp_sum(double v) {
+    for (int o = 16; o; o >>= 1) v += shfl_xor(v, o);
+    return v;
+}
 // inclusive suffix sum over lanes: out_k = sum_{j >= k} v_j
-MPC_DEV double warp_suffix_sum(double v) {
-    const int l = lane_id();
+MPC_DEV double warp_suffix_sum(double v, int l) {
     for (int o = 1; o < 32; o <<= 1) { double t = shfl_down(v, o); if (l + o < 32) v += t; }
     return v;
 }
-MPC_DEV double dmax_(double a, double b) { return a > b ? a : b; }
-MPC_DEV double dmin_(double a, double b) { return a < b ? a : b; }
-
 MPC_DEV void push_interior(double& v, double lo, double hi) {
-    double pl = dmin_(K_BOUND_PUSH * dmax_(1.0, fabs(lo)), K_BOUND_FRAC * (hi - lo));
-    double pu = dmin_(K_BOUND_PUSH * dmax_(1.0, fabs(hi)), K_BOUND_FRAC * (hi - lo));
+    const double pl = dmin_(K_BOUND_PUSH * dmax_(1.0, fabs(lo)), K_BOUND_FRAC * (hi - lo));
+    const double pu = dmin_(K_BOUND_PUSH * dmax_(1.0, fabs(hi)), K_BOUND_FRAC * (hi - lo));
     if (v < lo + pl) v = lo + pl;
     if (v > hi - pu) v = hi - pu;
 }
 MPC_DEV bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * K_EPS * fabs(bas); }
 
-// Stage model f(s,u) (MKZMPCPathFollower.jl:115-123) with the trig terms kept for derivatives.
-struct StageTrig {
-    double cs, sn;   // cos, sin (psi + beta)
-    double cb, sb;   // cos, sin beta
-    double b1, b2;   // beta', beta''
-};
-MPC_DEV void stage_trig(const KCfg& c, double psi, double df, StageTrig& t) {
-    // beta = atan(r tan df): sin/cos beta in closed form, valid for |df| < pi/2 (bounds keep |df| <= 0.5)
-    const double r = c.Lb / (c.La + c.Lb);
-    double sd, cd, sp, cp;
-    mpc_sincos(df, &sd, &cd);
-    mpc_sincos(psi, &sp, &cp);
-    const double D = cd * cd + r * r * sd * sd;
-    const double inv = 1.0 / sqrt(D);
-    t.cb = cd * inv;
-    t.sb = r * sd * inv;
-    t.cs = cp * t.cb - sp * t.sb;
-    t.sn = sp * t.cb + cp * t.sb;
-    t.b1 = r / D;
-    t.b2 = r * (1.0 - r * r) * (2.0 * sd * cd) / (D * D);
-}
-
-// Everything one lane (= one stage) carries through the iteration.
 struct LaneState {
-    // primal
-    double sx, sy, sp, sv, ua, ud;
-    // equality multipliers of the rows that define s_k (init rows for k = 0, dynamics rows k-1 -> k)
-    double yx, yy, yp, yv;
-    // bound multipliers
-    double zvL, zvU, zaL, zaU, zdL, zdU;
-    // rate row ending at u_k: [0] steering, [1] acceleration: slack, y_d, slack-bound multipliers
-    double rs[2], ryd[2], rvL[2], rvU[2];
+    double sx, sy, sp, sv, ua, ud;        // primal
+    double yx, yy, yp, yv;                // multipliers of the equality rows that define s_k
+    double zvL, zvU, zaL, zaU, zdL, zdU;  // bound multipliers
+    double rs[2], ryd[2], rvL[2], rvU[2]; // rate row ending at u_k: [0] steering, [1] acceleration
 };
-
 struct StepState {
     double dsx, dsy, dsp, dsv, dua, dud;  // primal step
     double drs[2];                        // slack step
     double nyx, nyy, nyp, nyv;            // NEW equality multipliers (y + dy)
-    double nyd[2];                        // NEW range multipliers
+    double nyd[2];                        // NEW rate-row multipliers
 };
+struct EvalState {        // model evaluation at the last evaluated point
+    double cs, sn, cb, sb, b1, b2;  // cos/sin(psi+beta), cos/sin(beta), beta', beta''
+    double rd[4];         // k < N: f(s_k,u_k) - s_{k+1};  k = N: state - s_0;  else 0
+    double dr[2];         // rate-row defect d(x) - slack
+    double f, lb, theta;  // objective (unscaled), sum of log slacks, 1-norm constraint violation
+};
+// reciprocals of the ten bound slacks of a lane, from ONE division
+struct Recips { double vL, vU, aL, aU, dL, dU, r0L, r0U, r1L, r1U; };
 
-// The solver for one problem; all 32 lanes of the warp call it together.
+struct Result { int status; int iters; double cost; };
+
 struct WarpSolver {
     const KCfg& c;
-    double* sm;    // this warp's shared memory
-    const int k;   // lane = stage
+    const smem_t sm;   // this warp's shared memory (opaque base)
+    const int k;       // lane = stage
     const int N;
     const bool isS, isU, isR;  // lane owns a state / an input / a rate row
-    // bounds (relaxed by bound_relax_factor)
-    double vLo, vHi, aLo, aHi, dLo, dHi, rLo[2], rHi[2];
-    // problem data
-    double xr, yr, pr, vdes, st0[4], uprev[2];
-    double wx, wy, wp, wv;  // stage cost weights (0 where the sum does not run)
-    double sigma;           // objective scaling
+    double xr, yr, pr;         // this stage's reference sample
+    double sigma;
     LaneState L;
     StepState D;
-    // per-iteration evaluation products
-    StageTrig tg;
-    double rdyn[4];   // f(s_k,u_k) - s_{k+1}   (= -c of the rows entering k+1), lanes k < N
-    double rinit[4];  // state - s_0            (= -c of the init rows), lane 0
-    double dres[2];   // d(x) - slack of this lane's rate row
-    double gx, gy, gp, gv, ga, gd;  // scaled objective gradient of this stage's variables
+    EvalState ev;
 
-    MPC_DEV WarpSolver(const KCfg& cfg, double* smem)
-        : c(cfg), sm(smem), k(lane_id()), N(cfg.N),
-          isS(lane_id() <= cfg.N), isU(lane_id() < cfg.N),
+    MPC_DEV WarpSolver(const KCfg& cfg, smem_t smem)
+        : c(cfg), sm(smem), k(lane_id()), N(cfg.N), isS(lane_id() <= cfg.N), isU(lane_id() < cfg.N),
           isR((lane_id() == 0 || lane_id() >= 2) && lane_id() < cfg.N) {}
 
-    // ------------------------------------------------------------------
-    // model evaluation at (s,u) given per lane; fills rd[4] (dynamics defect of rows k -> k+1),
-    // ri[4] (init defect, lane 0) and dr[2] (rate-row defect d(x) - slack)
-    // ------------------------------------------------------------------
-    MPC_DEV void eval_defects(double sx, double sy, double sp, double sv, double ua, double ud,
-                              const double* slack, StageTrig& t, double* rd, double* ri, double* dr) const {
-        stage_trig(c, sp, ud, t);
-        const double fx = sx + c.dt * (sv * t.cs);
-        const double fy = sy + c.dt * (sv * t.sn);
-        const double fp = sp + c.dt * (sv / c.Lb * t.sb);
-        const double fv = sv + c.dt * ua;
-        const double nx = shfl_down(sx, 1), ny = shfl_down(sy, 1), np = shfl_down(sp, 1), nv = shfl_down(sv, 1);
-        rd[0] = isU ? fx - nx : 0.0;
-        rd[1] = isU ? fy - ny : 0.0;
-        rd[2] = isU ? fp - np : 0.0;
-        rd[3] = isU ? fv - nv : 0.0;
-        const bool l0 = (k == 0);
-        ri[0] = l0 ? st0[0] - sx : 0.0;
-        ri[1] = l0 ? st0[1] - sy : 0.0;
-        ri[2] = l0 ? st0[2] - sp : 0.0;
-        ri[3] = l0 ? st0[3] - sv : 0.0;
-        // rate rows: k = 0: u_0 - u_prev ; k >= 2: u_k - u_{k-1}
-        const double pa = shfl_up(ua, 1), pd = shfl_up(ud, 1);
-        const double ba = l0 ? uprev[1] : pa, bd = l0 ? uprev[0] : pd;
-        dr[0] = isR ? (ud - bd) - slack[0] : 0.0;
-        dr[1] = isR ? (ua - ba) - slack[1] : 0.0;
-    }
+    // cheap per-use reconstruction of lane constants (keeps them out of the register file)
+    MPC_DEV double wx() const { return (k >= 1 && k <= N) ? c.w[0] : 0.0; }
+    MPC_DEV double wy() const { return (k >= 1 && k <= N) ? c.w[1] : 0.0; }
+    MPC_DEV double wp() const { return (k >= 1 && k <= N) ? c.w[2] : 0.0; }
+    MPC_DEV double wv() const { return (k >= 1 && k <= N - 1) ? c.w[3] : 0.0; }
+    MPC_DEV double rHi(int i) const { return (k == 0) ? c.rHiFirst[i] : c.rHiLater[i]; }
+    MPC_DEV double cst(int i) const { return lds(sm, SO(W_CONST + i)); }  // state[0..3], u_prev[0..1], v_des
+    MPC_DEV int rec() const { return SO(W_SD + (isS ? k : 0) * SDS); }    // this lane's own stage record
 
-    MPC_DEV double theta_of(const double* rd, const double* ri, const double* dr) const {
-        double t = fabs(rd[0]) + fabs(rd[1]) + fabs(rd[2]) + fabs(rd[3]) + fabs(ri[0]) + fabs(ri[1]) + fabs(ri[2]) +
-                   fabs(ri[3]) + fabs(dr[0]) + fabs(dr[1]);
-        return warp_sum(t);
-    }
-
-    // unscaled objective (MKZMPCPathFollower.jl:97-103) at a per-lane point
-    MPC_DEV double objective(double sx, double sy, double sp, double sv, double ua, double ud) const {
-        const double na = shfl_down(ua, 1), nd = shfl_down(ud, 1);
-        double f = 0.0;
-        const double ex = sx - xr, ey = sy - yr, ep = sp - pr, ev = sv - vdes;
-        f += wx * ex * ex + wy * ey * ey + wp * ep * ep + wv * ev * ev;
-        if (isU) {
-            f += c.w[6] * ua * ua + c.w[7] * ud * ud;
-            if (k + 1 < N) { const double da = na - ua, dd = nd - ud; f += c.w[4] * da * da + c.w[5] * dd * dd; }
-        }
-        return warp_sum(f);
-    }
-
-    // sum of log slacks of this lane's bounds at a per-lane point
-    MPC_DEV double log_barrier(double sv, double ua, double ud, const double* slack) const {
-        double p = 1.0;
-        if (isS) p *= (sv - vLo) * (vHi - sv);
-        if (isU) p *= (ua - aLo) * (aHi - ua) * (ud - dLo) * (dHi - ud);
-        if (isR) p *= (slack[0] - rLo[0]) * (rHi[0] - slack[0]) * (slack[1] - rLo[1]) * (rHi[1] - slack[1]);
-        return warp_sum(log(p));
-    }
-
-    // scaled objective gradient at the current iterate -> gx..gd
-    MPC_DEV void objective_gradient() {
-        const double na = shfl_down(L.ua, 1), nd = shfl_down(L.ud, 1);
-        const double pa = shfl_up(L.ua, 1), pd = shfl_up(L.ud, 1);
-        gx = 2.0 * sigma * wx * (L.sx - xr);
-        gy = 2.0 * sigma * wy * (L.sy - yr);
-        gp = 2.0 * sigma * wp * (L.sp - pr);
-        gv = 2.0 * sigma * wv * (L.sv - vdes);
-        ga = 0.0; gd = 0.0;
-        if (isU) {
-            ga = 2.0 * sigma * c.w[6] * L.ua;
-            gd = 2.0 * sigma * c.w[7] * L.ud;
-            if (k >= 1) { ga += 2.0 * sigma * c.w[4] * (L.ua - pa); gd += 2.0 * sigma * c.w[5] * (L.ud - pd); }
-            if (k + 1 < N) { ga -= 2.0 * sigma * c.w[4] * (na - L.ua); gd -= 2.0 * sigma * c.w[5] * (nd - L.ud); }
-        }
-    }
-
-    // ------------------------------------------------------------------
-    // Stage record assembly.  mode 0: least-squares multiplier system (identity Hessian,
-    // unit slack weights); mode 1: primal-dual system with Lagrangian Hessian, Sigma, delta_w.
-    // gs*/gu*: condensed gradient of this stage's variables; rr/ri: residual r_k and init step.
-    // ------------------------------------------------------------------
-    struct Cond {       // per-lane condensed quantities reused after the solve
-        double Hxx, Hyy, Hpp, Hpv, Hvv, Hpd, Hvd;  // state/cross blocks (without the +C input parts)
-        double Haa, Hdd;                           // input diagonal INCLUDING coupling C of this stage
-        double Ca, Cd;                             // coupling with the previous input
-        double gsx, gsy, gsp, gsv, gua, gud;       // condensed gradient
-        double SrW[2];                             // (Sigma_s + delta_w) of this lane's rate row
-        double br[2];                              // -mu/ss_L + mu/ss_U of the rate row
-    };
-
-    MPC_DEV void write_record(const Cond& q, const double* rr) {
-        double* r = sm + W_SD + k * SDS;
-        const double A02 = isU ? -c.dt * L.sv * tg.sn : 0.0, A03 = isU ? c.dt * tg.cs : 0.0;
-        const double A12 = isU ? c.dt * L.sv * tg.cs : 0.0, A13 = isU ? c.dt * tg.sn : 0.0;
-        const double A23 = isU ? c.dt * tg.sb / c.Lb : 0.0;
-        const double b0 = A02 * tg.b1, b1v = A12 * tg.b1, b2v = isU ? c.dt * L.sv * tg.cb * tg.b1 / c.Lb : 0.0;
-        // columns of [A B; 0 I] over rows (x,y,psi,v,prev_a,prev_df)
-        r[SD_MT + 0] = A02; r[SD_MT + 1] = A12; r[SD_MT + 2] = 1.0; r[SD_MT + 3] = 0.0; r[SD_MT + 4] = 0.0; r[SD_MT + 5] = 0.0;      // psi
-        r[SD_MT + 6] = A03; r[SD_MT + 7] = A13; r[SD_MT + 8] = A23; r[SD_MT + 9] = 1.0; r[SD_MT + 10] = 0.0; r[SD_MT + 11] = 0.0;    // v
-        r[SD_MT + 12] = 0.0; r[SD_MT + 13] = 0.0; r[SD_MT + 14] = 0.0; r[SD_MT + 15] = c.dt; r[SD_MT + 16] = 1.0; r[SD_MT + 17] = 0.0; // a
-        r[SD_MT + 18] = b0; r[SD_MT + 19] = b1v; r[SD_MT + 20] = b2v; r[SD_MT + 21] = 0.0; r[SD_MT + 22] = 0.0; r[SD_MT + 23] = 1.0; // df
-        r[SD_MT + 24] = rr[0]; r[SD_MT + 25] = rr[1]; r[SD_MT + 26] = rr[2]; r[SD_MT + 27] = rr[3]; r[SD_MT + 28] = 0.0; r[SD_MT + 29] = 0.0;
-        r[SD_HXX] = q.Hxx; r[SD_HYY] = q.Hyy; r[SD_HPP] = q.Hpp; r[SD_HPV] = q.Hpv; r[SD_HVV] = q.Hvv;
-        r[SD_HPD] = q.Hpd; r[SD_HVD] = q.Hvd; r[SD_HAA] = q.Haa; r[SD_HDD] = q.Hdd;
-        r[SD_CA] = q.Ca; r[SD_CD] = q.Cd; r[SD_NCA] = -q.Ca; r[SD_ZERO2] = 0.0; r[SD_NCD] = -q.Cd;
-        r[SD_GX + 0] = q.gsx; r[SD_GX + 1] = q.gsy; r[SD_GX + 2] = q.gsp; r[SD_GX + 3] = q.gsv;
-        r[SD_GX + 4] = q.gua; r[SD_GX + 5] = q.gud;
-    }
-
-    // only the pieces that change between inertia-correction attempts / SOC right-hand sides
-    MPC_DEV void patch_record_diag(const Cond& q) {
-        double* r = sm + W_SD + k * SDS;
-        r[SD_HXX] = q.Hxx; r[SD_HYY] = q.Hyy; r[SD_HPP] = q.Hpp; r[SD_HVV] = q.Hvv; r[SD_HAA] = q.Haa; r[SD_HDD] = q.Hdd;
-        r[SD_CA] = q.Ca; r[SD_CD] = q.Cd; r[SD_NCA] = -q.Ca; r[SD_NCD] = -q.Cd;
-        r[SD_GX + 4] = q.gua; r[SD_GX + 5] = q.gud;
-    }
-    MPC_DEV void patch_record_rhs(const Cond& q, const double* rr) {
-        double* r = sm + W_SD + k * SDS;
-        r[SD_MT + 24] = rr[0]; r[SD_MT + 25] = rr[1]; r[SD_MT + 26] = rr[2]; r[SD_MT + 27] = rr[3];
-        r[SD_GX + 4] = q.gua; r[SD_GX + 5] = q.gud;
-    }
-
-    // condensed Hessian/gradient for the primal-dual system at the current iterate.
-    // rdr: rate-row residual to use (dres, or the SOC-accumulated one)
-    MPC_DEV void build_cond_pd(Cond& q, double mu, double dw, const double* rdr) {
-        // multipliers of the rows leaving this stage (held by lane k+1)
-        const double y1x = shfl_down(L.yx, 1), y1y = shfl_down(L.yy, 1), y1p = shfl_down(L.yp, 1);
-        double hpp = 0.0, hpv = 0.0, hpd = 0.0, hvd = 0.0, hdd = 0.0;
-        if (isU) {
-            const double v = L.sv, dt = c.dt;
-            const double e1 = y1x * tg.cs + y1y * tg.sn;  // -> d2/dpsi2 direction
-            const double e2 = y1x * tg.sn - y1y * tg.cs;
-            hpp = dt * v * e1;
-            hpv = dt * e2;
-            hpd = tg.b1 * hpp;
-            hvd = tg.b1 * hpv - y1p * dt * tg.cb * tg.b1 / c.Lb;
-            hdd = tg.b1 * tg.b1 * hpp + v * tg.b2 * hpv - y1p * (dt * v / c.Lb) * (tg.cb * tg.b2 - tg.sb * tg.b1 * tg.b1);
-        }
-        double Sv = 0.0, bv = 0.0, Sa = 0.0, ba = 0.0, Sd = 0.0, bd = 0.0;
-        if (isS) {
-            const double sl = L.sv - vLo, su = vHi - L.sv;
-            Sv = L.zvL / sl + L.zvU / su; bv = -mu / sl + mu / su;
-        }
-        if (isU) {
-            double sl = L.ua - aLo, su = aHi - L.ua;
-            Sa = L.zaL / sl + L.zaU / su; ba = -mu / sl + mu / su;
-            sl = L.ud - dLo; su = dHi - L.ud;
-            Sd = L.zdL / sl + L.zdU / su; bd = -mu / sl + mu / su;
-        }
-        double wrow[2] = {0.0, 0.0};
-        q.SrW[0] = q.SrW[1] = 0.0; q.br[0] = q.br[1] = 0.0;
-        if (isR) {
-            for (int i = 0; i < 2; i++) {
-                const double sl = L.rs[i] - rLo[i], su = rHi[i] - L.rs[i];
-                q.SrW[i] = L.rvL[i] / sl + L.rvU[i] / su + dw;
-                q.br[i] = -mu / sl + mu / su;
-                wrow[i] = q.br[i] + q.SrW[i] * rdr[i];
-            }
-        }
-        const double wn0 = shfl_down(wrow[0], 1), wn1 = shfl_down(wrow[1], 1);  // row ending at u_{k+1}
-        q.Hxx = (isS ? 2.0 * sigma * wx : 0.0) + dw;
-        q.Hyy = (isS ? 2.0 * sigma * wy : 0.0) + dw;
-        q.Hpp = (isS ? 2.0 * sigma * wp : 0.0) + hpp + dw;
-        q.Hpv = hpv;
-        q.Hvv = (isS ? 2.0 * sigma * wv : 0.0) + Sv + dw;
-        q.Hpd = hpd; q.Hvd = hvd;
-        // coupling with the previous input: rate cost for k >= 1, rate row for k == 0 or k >= 2
-        q.Ca = 0.0; q.Cd = 0.0;
-        if (isU) {
-            if (k >= 1) { q.Ca = 2.0 * sigma * c.w[4]; q.Cd = 2.0 * sigma * c.w[5]; }
-            if (isR) { q.Ca += q.SrW[1]; q.Cd += q.SrW[0]; }
-        }
-        q.Haa = isU ? 2.0 * sigma * c.w[6] + Sa + dw + q.Ca : 1.0;
-        q.Hdd = isU ? 2.0 * sigma * c.w[7] + Sd + dw + q.Cd + hdd : 1.0;
-        q.gsx = gx; q.gsy = gy; q.gsp = gp; q.gsv = gv + bv;
-        q.gua = isU ? ga + ba + wrow[1] - ((k + 1 < N) ? wn1 : 0.0) : 0.0;
-        q.gud = isU ? gd + bd + wrow[0] - ((k + 1 < N) ? wn0 : 0.0) : 0.0;
-    }
-
-    // least-squares multiplier system: Hessian = I, slack weights = 1, no residuals
-    MPC_DEV void build_cond_ls(Cond& q) {
-        double wrow[2] = {0.0, 0.0};
-        q.SrW[0] = q.SrW[1] = 0.0; q.br[0] = q.br[1] = 0.0;
-        if (isR) for (int i = 0; i < 2; i++) { q.SrW[i] = 1.0; q.br[i] = -(L.rvL[i] - L.rvU[i]); wrow[i] = q.br[i]; }
-        const double wn0 = shfl_down(wrow[0], 1), wn1 = shfl_down(wrow[1], 1);
-        q.Hxx = q.Hyy = q.Hpp = q.Hvv = 1.0; q.Hpv = q.Hpd = q.Hvd = 0.0;
-        q.Ca = (isU && isR) ? 1.0 : 0.0; q.Cd = q.Ca;
-        q.Haa = 1.0 + q.Ca; q.Hdd = 1.0 + q.Cd;
-        q.gsx = gx; q.gsy = gy; q.gsp = gp; q.gsv = gv + (isS ? (-L.zvL + L.zvU) : 0.0);
-        q.gua = isU ? ga - L.zaL + L.zaU + wrow[1] - ((k + 1 < N) ? wn1 : 0.0) : 0.0;
-        q.gud = isU ? gd - L.zdL + L.zdU + wrow[0] - ((k + 1 < N) ? wn0 : 0.0) : 0.0;
-    }
-
-    // ------------------------------------------------------------------
-    // Riccati backward recursion over the stage records; lanes = matrix entries.
-    // Returns false if some stage's reduced input Hessian is not positive definite
-    // (the inertia of the full KKT matrix is wrong).  Gains go to the KST area.
-    // ------------------------------------------------------------------
-    struct Roles {
-        int a_pb, a_mb, a_ex, a_out;
-        int b_mb, b_mk, b_tb, b_h, b_hk, b_o1, b_o2;
-        int d_xb, d_xk, d_r, d_out;
-        int e_f0, e_f0k, e_f1, e_f1k, e_kb, e_o1, e_o2;
-    };
-    Roles R;
-
-    MPC_DEV void init_roles() {
-        const int l = k;
-        // Round A: lanes 0..23 -> T[i][cc], lanes 24..29 -> T[i][4] (vector)
-        {
-            const int i = (l < 24) ? l / 4 : (l < 30 ? l - 24 : 0);
-            const int cc = (l < 24) ? l % 4 : 4;
-            R.a_pb = W_P + 6 * i;
-            R.a_mb = W_SD + SD_MT + 6 * cc;
-            R.a_ex = (l >= 24 && l < 30) ? W_PV + i : W_Z;
-            R.a_out = (l < 30) ? W_T + 6 * i + cc : W_DUMMY;
-        }
-        // Round B: 21 symmetric pairs (c1 <= c2) then 6 vector entries
-        {
-            int c1 = 0, c2 = 0, vec = 0, act = 1;
-            if (l < 21) { int t = l; c1 = 0; while (t >= 6 - c1) { t -= 6 - c1; c1++; } c2 = c1 + t; }
-            else if (l < 27) { c1 = l - 21; vec = 1; }
-            else act = 0;
-            // coefficient column c1 of [A B; 0 I]: unit vectors for x,y, stage record otherwise
-            if (c1 < 2) { R.b_mb = (c1 == 0) ? W_EX : W_EY; R.b_mk = 0; }
-            else { R.b_mb = W_SD + SD_MT + 6 * (c1 - 2); R.b_mk = SDS; }
-            if (vec) R.b_tb = W_T + 4;
-            else R.b_tb = (c2 < 2) ? W_P + c2 : W_T + (c2 - 2);
-            // H entry
-            int h = -1;
-            if (vec) h = SD_GX + c1;
-            else if (c1 == c2) { const int dg[6] = {SD_HXX, SD_HYY, SD_HPP, SD_HVV, SD_HAA, SD_HDD}; h = dg[c1]; }
-            else if (c1 == 2 && c2 == 3) h = SD_HPV;
-            else if (c1 == 2 && c2 == 5) h = SD_HPD;
-            else if (c1 == 3 && c2 == 5) h = SD_HVD;
-            if (h >= 0) { R.b_h = W_SD + h; R.b_hk = SDS; } else { R.b_h = W_Z; R.b_hk = 0; }
-            if (!act) { R.b_o1 = R.b_o2 = W_DUMMY; }
-            else if (vec) { R.b_o1 = R.b_o2 = W_FV + c1; }
-            else { R.b_o1 = W_F + 6 * c1 + c2; R.b_o2 = W_F + 6 * c2 + c1; }
-        }
-        // Round D: lanes 0..13 -> K[r][cidx], cidx over (x,y,psi,v,prev_a,prev_df,const)
-        {
-            const int r = (l < 14) ? l / 7 : 0, ci = (l < 14) ? l % 7 : 0;
-            R.d_r = r;
-            if (ci < 4) { R.d_xb = W_F + 6 * ci + 4; R.d_xk = 0; }
-            else if (ci == 4) { R.d_xb = W_SD + SD_NCA; R.d_xk = SDS; }
-            else if (ci == 5) { R.d_xb = W_SD + SD_ZERO2; R.d_xk = SDS; }
-            else { R.d_xb = W_FV + 4; R.d_xk = 0; }
-            R.d_out = (l < 14) ? r * 7 + ci : -1;
-        }
-        // Round E: 21 symmetric pairs over (x,y,psi,v,prev_a,prev_df) then 6 vector entries
-        {
-            int i = 0, j = 0, vec = 0, act = 1;
-            if (l < 21) { int t = l; i = 0; while (t >= 6 - i) { t -= 6 - i; i++; } j = i + t; }
-            else if (l < 27) { i = l - 21; vec = 1; }
-            else act = 0;
-            // F8[i][j]
-            if (vec) { if (i < 4) { R.e_f0 = W_FV + i; R.e_f0k = 0; } else { R.e_f0 = W_Z; R.e_f0k = 0; } }
-            else if (i < 4 && j < 4) { R.e_f0 = W_F + 6 * i + j; R.e_f0k = 0; }
-            else if (i == 4 && j == 4) { R.e_f0 = W_SD + SD_CA; R.e_f0k = SDS; }
-            else if (i == 5 && j == 5) { R.e_f0 = W_SD + SD_CD; R.e_f0k = SDS; }
-            else { R.e_f0 = W_Z; R.e_f0k = 0; }
-            // (F8[i][a], F8[i][df])
-            if (i < 4) { R.e_f1 = W_F + 6 * i + 4; R.e_f1k = 0; }
-            else if (i == 4) { R.e_f1 = W_SD + SD_NCA; R.e_f1k = SDS; }
-            else { R.e_f1 = W_SD + SD_ZERO2; R.e_f1k = SDS; }
-            R.e_kb = vec ? 6 : j;
-            if (!act) { R.e_o1 = R.e_o2 = W_DUMMY; }
-            else if (vec) { R.e_o1 = R.e_o2 = W_PV + i; }
-            else { R.e_o1 = W_P + 6 * i + j; R.e_o2 = W_P + 6 * j + i; }
-        }
-        // constants in the work area
-        if (l < 6) { sm[W_EX + l] = (l == 0) ? 1.0 : 0.0; sm[W_EY + l] = (l == 1) ? 1.0 : 0.0; }
-        if (l == 0) { sm[W_Z] = 0.0; sm[W_DUMMY] = 0.0; }
+    MPC_DEV static void init_work(smem_t sm) {
+        const int l = lane_id();
+        if (l < 6) { sts(sm, SO(W_EX + l), (l == 0) ? 1.0 : 0.0); sts(sm, SO(W_EY + l), (l == 1) ? 1.0 : 0.0); sts(sm, SO(W_Z + l), 0.0); }
+        if (l < 4) sts(sm, SO(W_NC + l), 0.0);
+        if (l < 2) sts(sm, SO(W_DUMMY + l), 0.0);
         syncwarp();
     }
 
+    MPC_DEV void recips(Recips& q) const {
+        const double vl = isS ? L.sv - c.vLo : 1.0, vu = isS ? c.vHi - L.sv : 1.0;
+        const double al = isU ? L.ua - c.aLo : 1.0, au = isU ? c.aHi - L.ua : 1.0;
+        const double dl = isU ? L.ud - c.dLo : 1.0, du = isU ? c.dHi - L.ud : 1.0;
+        const double h0 = rHi(0), h1 = rHi(1);
+        const double r0l = isR ? L.rs[0] + h0 : 1.0, r0u = isR ? h0 - L.rs[0] : 1.0;
+        const double r1l = isR ? L.rs[1] + h1 : 1.0, r1u = isR ? h1 - L.rs[1] : 1.0;
+        const double pv = vl * vu, pa_ = al * au, pd_ = dl * du, p0 = r0l * r0u, p1 = r1l * r1u;
+        const double pva = pv * pa_, p01 = p0 * p1, pvad = pva * pd_;
+        const double iall = 1.0 / (pvad * p01);
+        const double i01 = iall * pvad, ivad = iall * p01;  // 1/(p0 p1), 1/(pv pa pd)
+        const double ip0 = i01 * p1, ip1 = i01 * p0;
+        const double ipd = ivad * pva, iva = ivad * pd_;
+        const double ipv = iva * pa_, ipa = iva * pv;
+        q.vL = vu * ipv; q.vU = vl * ipv; q.aL = au * ipa; q.aU = al * ipa; q.dL = du * ipd; q.dU = dl * ipd;
+        q.r0L = r0u * ip0; q.r0U = r0l * ip0; q.r1L = r1u * ip1; q.r1U = r1l * ip1;
+    }
+
+    // ------------------------------------------------------------------
+    // model evaluation at the point  L + a * D  (a = 0: the current iterate) -> ev
+    // ------------------------------------------------------------------
+    MPC_DEV void eval_point(double a) {
+        const double sx = L.sx + a * D.dsx, sy = L.sy + a * D.dsy, sp = L.sp + a * D.dsp, sv = L.sv + a * D.dsv;
+        const double ua = L.ua + a * D.dua, ud = L.ud + a * D.dud;
+        const double s0 = L.rs[0] + a * D.drs[0], s1 = L.rs[1] + a * D.drs[1];
+        // trig: beta = atan(r tan df) in closed form, valid for |df| < pi/2 (bounds keep |df| <= 0.5)
+        {
+            const double r = c.rfrac;
+            double sd, cd, sps, cps;
+            mpc_sincos(ud, &sd, &cd);
+            mpc_sincos(sp, &sps, &cps);
+            const double Dn = cd * cd + r * r * sd * sd;
+            const double iD = 1.0 / Dn;
+            const double inv = sqrt(iD);
+            ev.cb = cd * inv;
+            ev.sb = r * sd * inv;
+            ev.cs = cps * ev.cb - sps * ev.sb;
+            ev.sn = sps * ev.cb + cps * ev.sb;
+            ev.b1 = r * iD;
+            ev.b2 = r * (1.0 - r * r) * (2.0 * sd * cd) * (iD * iD);
+        }
+        const double fx = sx + c.dt * (sv * ev.cs);
+        const double fy = sy + c.dt * (sv * ev.sn);
+        const double fp = sp + c.dt * (sv / c.Lb * ev.sb);
+        const double fv = sv + c.dt * ua;
+        // lane k < N takes s_{k+1}; lane N takes s_0 (for the initial-condition rows)
+        const int src = (k == N) ? 0 : ((k + 1) & 31);
+        const double nx = shfl(sx, src), ny = shfl(sy, src), np = shfl(sp, src), nv = shfl(sv, src);
+        if (isU) { ev.rd[0] = fx - nx; ev.rd[1] = fy - ny; ev.rd[2] = fp - np; ev.rd[3] = fv - nv; }
+        else if (k == N) { ev.rd[0] = cst(0) - nx; ev.rd[1] = cst(1) - ny; ev.rd[2] = cst(2) - np; ev.rd[3] = cst(3) - nv; }
+        else { ev.rd[0] = ev.rd[1] = ev.rd[2] = ev.rd[3] = 0.0; }
+        const double pa = shfl_up(ua, 1), pd = shfl_up(ud, 1);
+        const bool l0 = (k == 0);
+        const double ba = l0 ? cst(5) : pa, bd = l0 ? cst(4) : pd;
+        ev.dr[0] = isR ? (ud - bd) - s0 : 0.0;
+        ev.dr[1] = isR ? (ua - ba) - s1 : 0.0;
+        // objective (MKZMPCPathFollower.jl:97-103): stage terms + rate terms counted at the later input
+        double f;
+        {
+            const double ex = sx - xr, ey = sy - yr, ep = sp - pr, evv = sv - cst(6);
+            f = wx() * ex * ex + wy() * ey * ey + wp() * ep * ep + wv() * evv * evv;
+            if (isU) {
+                f += c.w[6] * ua * ua + c.w[7] * ud * ud;
+                if (k >= 1) { const double da = ua - pa, dd = ud - pd; f += c.w[4] * da * da + c.w[5] * dd * dd; }
+            }
+        }
+        double p = 1.0;
+        if (isS) p *= (sv - c.vLo) * (c.vHi - sv);
+        if (isU) p *= (ua - c.aLo) * (c.aHi - ua) * (ud - c.dLo) * (c.dHi - ud);
+        if (isR) { const double h0 = rHi(0), h1 = rHi(1); p *= (s0 + h0) * (h0 - s0) * (s1 + h1) * (h1 - s1); }
+        double lb = log(p);
+        double th = fabs(ev.rd[0]) + fabs(ev.rd[1]) + fabs(ev.rd[2]) + fabs(ev.rd[3]) + fabs(ev.dr[0]) + fabs(ev.dr[1]);
+        for (int o = 16; o; o >>= 1) { f += shfl_xor(f, o); lb += shfl_xor(lb, o); th += shfl_xor(th, o); }
+        ev.f = f; ev.lb = lb; ev.theta = th;
+    }
+
+    // scaled objective gradient at the current iterate (recomputed where needed: cheaper than six
+    // doubles kept alive across the Riccati passes)
+    struct Grad { double x, y, p, v, a, d; };
+    MPC_DEV Grad objective_gradient() const {
+        Grad g;
+        const int src = (k + 1) & 31;
+        const double na = shfl(L.ua, src), nd = shfl(L.ud, src);
+        const double pa = shfl_up(L.ua, 1), pd = shfl_up(L.ud, 1);
+        const double s2 = 2.0 * sigma;
+        g.x = s2 * wx() * (L.sx - xr);
+        g.y = s2 * wy() * (L.sy - yr);
+        g.p = s2 * wp() * (L.sp - pr);
+        g.v = s2 * wv() * (L.sv - cst(6));
+        g.a = 0.0; g.d = 0.0;
+        if (isU) {
+            g.a = s2 * c.w[6] * L.ua;
+            g.d = s2 * c.w[7] * L.ud;
+            if (k >= 1) { g.a += s2 * c.w[4] * (L.ua - pa); g.d += s2 * c.w[5] * (L.ud - pd); }
+            if (k + 1 < N) { g.a -= s2 * c.w[4] * (na - L.ua); g.d -= s2 * c.w[5] * (nd - L.ud); }
+        }
+        return g;
+    }
+
+    // ------------------------------------------------------------------
+    // Stage record assembly (lane k writes record k).
+    //   req 0: least-squares multiplier system (identity Hessian, unit slack weights, zero residuals)
+    //   req 1: primal-dual system, full record, residuals from `ev` (which holds the current point)
+    //   req 2: primal-dual system after a change of delta_w: only the touched entries
+    //   req 3: primal-dual system with the residuals already in the record (second-order correction)
+    // ------------------------------------------------------------------
+    MPC_DEV void assemble(int req, double mu, double dw) {
+        const int r = rec();
+        const Grad g = objective_gradient();
+        const double gx = g.x, gy = g.y, gp = g.p, gv = g.v, ga = g.a, gd = g.d;
+        double Hxx, Hyy, Hpp, Hpv = 0.0, Hvv, Hpd = 0.0, Hvd = 0.0, Haa, Hdd, Ca = 0.0, Cd = 0.0;
+        double gsv, gua = 0.0, gud = 0.0;
+        double SrW[2] = {0.0, 0.0}, br[2] = {0.0, 0.0}, wrow[2] = {0.0, 0.0}, rdr[2] = {0.0, 0.0};
+        if (req == 0) {
+            if (isR) for (int i = 0; i < 2; i++) { SrW[i] = 1.0; br[i] = -(L.rvL[i] - L.rvU[i]); wrow[i] = br[i]; }
+            Hxx = Hyy = Hpp = Hvv = 1.0;
+            Ca = (isU && isR) ? 1.0 : 0.0; Cd = Ca;
+            Haa = 1.0 + Ca; Hdd = 1.0 + Cd;
+            gsv = gv + (isS ? (-L.zvL + L.zvU) : 0.0);
+            if (isU) { gua = ga - L.zaL + L.zaU; gud = gd - L.zdL + L.zdU; }
+        } else {
+            // multipliers of the rows leaving this stage (held by lane k+1)
+            const double y1x = shfl_down(L.yx, 1), y1y = shfl_down(L.yy, 1), y1p = shfl_down(L.yp, 1);
+            double hpp = 0.0, hdd = 0.0;
+            if (isU) {
+                const double v = L.sv, dt = c.dt;
+                const double e1 = y1x * ev.cs + y1y * ev.sn;
+                const double e2 = y1x * ev.sn - y1y * ev.cs;
+                hpp = dt * v * e1;
+                Hpv = dt * e2;
+                Hpd = ev.b1 * hpp;
+                Hvd = ev.b1 * Hpv - y1p * dt * ev.cb * ev.b1 / c.Lb;
+                hdd = ev.b1 * ev.b1 * hpp + v * ev.b2 * Hpv - y1p * (dt * v / c.Lb) * (ev.cb * ev.b2 - ev.sb * ev.b1 * ev.b1);
+            }
+            Recips q;
+            recips(q);
+            // Sigma = zL/sl + zU/su ; barrier gradient b = -mu/sl + mu/su
+            const double Sv = isS ? L.zvL * q.vL + L.zvU * q.vU : 0.0, bv = isS ? mu * (q.vU - q.vL) : 0.0;
+            const double Sa = isU ? L.zaL * q.aL + L.zaU * q.aU : 0.0, ba = isU ? mu * (q.aU - q.aL) : 0.0;
+            const double Sd = isU ? L.zdL * q.dL + L.zdU * q.dU : 0.0, bd = isU ? mu * (q.dU - q.dL) : 0.0;
+            if (isR) {
+                SrW[0] = L.rvL[0] * q.r0L + L.rvU[0] * q.r0U + dw; br[0] = mu * (q.r0U - q.r0L);
+                SrW[1] = L.rvL[1] * q.r1L + L.rvU[1] * q.r1U + dw; br[1] = mu * (q.r1U - q.r1L);
+                if (req == 3) { rdr[0] = lds(sm, r + SO(SD_DR)); rdr[1] = lds(sm, r + SO(SD_DR + 1)); }
+                else { rdr[0] = ev.dr[0]; rdr[1] = ev.dr[1]; }
+                wrow[0] = br[0] + SrW[0] * rdr[0];
+                wrow[1] = br[1] + SrW[1] * rdr[1];
+            }
+            const double s2 = 2.0 * sigma;
+            Hxx = s2 * wx() + dw; Hyy = s2 * wy() + dw; Hpp = s2 * wp() + hpp + dw; Hvv = s2 * wv() + Sv + dw;
+            if (isU) {
+                if (k >= 1) { Ca = s2 * c.w[4]; Cd = s2 * c.w[5]; }
+                if (isR) { Ca += SrW[1]; Cd += SrW[0]; }
+            }
+            Haa = isU ? s2 * c.w[6] + Sa + dw + Ca : 1.0;
+            Hdd = isU ? s2 * c.w[7] + Sd + dw + Cd + hdd : 1.0;
+            gsv = gv + bv;
+            if (isU) { gua = ga + ba; gud = gd + bd; }
+        }
+        // rate-row terms: +w of the row ending at u_k, -w of the row ending at u_{k+1}
+        const double wn0 = shfl_down(wrow[0], 1), wn1 = shfl_down(wrow[1], 1);
+        if (isU) {
+            gua += wrow[1] - ((k + 1 < N) ? wn1 : 0.0);
+            gud += wrow[0] - ((k + 1 < N) ? wn0 : 0.0);
+        }
+        if (!isS) return;
+        if (req == 0 || req == 1) {
+            const double A02 = isU ? -c.dt * L.sv * ev.sn : 0.0, A03 = isU ? c.dt * ev.cs : 0.0;
+            const double A12 = isU ? c.dt * L.sv * ev.cs : 0.0, A13 = isU ? c.dt * ev.sn : 0.0;
+            const double A23 = isU ? c.dt * ev.sb / c.Lb : 0.0;
+            const double b0 = A02 * ev.b1, b1v = A12 * ev.b1, b2v = isU ? c.dt * L.sv * ev.cb * ev.b1 / c.Lb : 0.0;
+            const double one = 1.0, zero = 0.0;
+            sts(sm, r + SO(SD_MT + 0), A02); sts(sm, r + SO(SD_MT + 1), A12); sts(sm, r + SO(SD_MT + 2), one);
+            sts(sm, r + SO(SD_MT + 3), zero); sts(sm, r + SO(SD_MT + 4), zero); sts(sm, r + SO(SD_MT + 5), zero);
+            sts(sm, r + SO(SD_MT + 6), A03); sts(sm, r + SO(SD_MT + 7), A13); sts(sm, r + SO(SD_MT + 8), A23);
+            sts(sm, r + SO(SD_MT + 9), one); sts(sm, r + SO(SD_MT + 10), zero); sts(sm, r + SO(SD_MT + 11), zero);
+            sts(sm, r + SO(SD_MT + 12), zero); sts(sm, r + SO(SD_MT + 13), zero); sts(sm, r + SO(SD_MT + 14), zero);
+            sts(sm, r + SO(SD_MT + 15), c.dt); sts(sm, r + SO(SD_MT + 16), one); sts(sm, r + SO(SD_MT + 17), zero);
+            sts(sm, r + SO(SD_MT + 18), b0); sts(sm, r + SO(SD_MT + 19), b1v); sts(sm, r + SO(SD_MT + 20), b2v);
+            sts(sm, r + SO(SD_MT + 21), zero); sts(sm, r + SO(SD_MT + 22), zero); sts(sm, r + SO(SD_MT + 23), one);
+            const bool z = (req == 0);
+            sts(sm, r + SO(SD_R + 0), z ? 0.0 : ev.rd[0]); sts(sm, r + SO(SD_R + 1), z ? 0.0 : ev.rd[1]);
+            sts(sm, r + SO(SD_R + 2), z ? 0.0 : ev.rd[2]); sts(sm, r + SO(SD_R + 3), z ? 0.0 : ev.rd[3]);
+            sts(sm, r + SO(SD_R + 4), zero); sts(sm, r + SO(SD_R + 5), zero);
+            sts(sm, r + SO(SD_HPV), Hpv); sts(sm, r + SO(SD_HPD), Hpd); sts(sm, r + SO(SD_HVD), Hvd);
+            sts(sm, r + SO(SD_ZERO), zero);
+            sts(sm, r + SO(SD_GX + 0), gx); sts(sm, r + SO(SD_GX + 1), gy); sts(sm, r + SO(SD_GX + 2), gp); sts(sm, r + SO(SD_GX + 3), gsv);
+            sts(sm, r + SO(SD_BR), br[0]); sts(sm, r + SO(SD_BR + 1), br[1]);
+            sts(sm, r + SO(SD_DR), rdr[0]); sts(sm, r + SO(SD_DR + 1), rdr[1]);
+        }
+        if (req != 3) {
+            sts(sm, r + SO(SD_HXX), Hxx); sts(sm, r + SO(SD_HYY), Hyy); sts(sm, r + SO(SD_HPP), Hpp); sts(sm, r + SO(SD_HVV), Hvv);
+            sts(sm, r + SO(SD_HAA), Haa); sts(sm, r + SO(SD_HDD), Hdd);
+            sts(sm, r + SO(SD_CA), Ca); sts(sm, r + SO(SD_CD), Cd); sts(sm, r + SO(SD_NCA), -Ca); sts(sm, r + SO(SD_NCD), -Cd);
+            sts(sm, r + SO(SD_SRW), SrW[0]); sts(sm, r + SO(SD_SRW + 1), SrW[1]);
+        }
+        sts(sm, r + SO(SD_GX + 4), gua); sts(sm, r + SO(SD_GX + 5), gud);
+    }
+
+    // ------------------------------------------------------------------
+    // Riccati backward recursion; lanes = matrix entries.  Returns false if some stage's reduced
+    // input Hessian is not positive definite (= wrong inertia of the full KKT matrix).
+    //
+    // Per stage s (xi = (x,y,psi,v,prev_a,prev_df), M = [A B; 0 I]):
+    //   round A: TT = columns psi|v|a|df of P M, and P r + p                 (30 lanes)
+    //   round B: F = H + M' (P M), f = g + M' (P r + p); idle lanes stage Ca, Cd, -Ca, -Cd  (31 lanes)
+    //   round E: Fuu^{-1} (every lane), gains K, cost-to-go P <- F_xixi + F_xi,u K   (27 lanes)
+    // ------------------------------------------------------------------
     MPC_DEV bool riccati_backward() {
         const int l = k;
-        double* kst = sm + W_SD + (N + 1) * SDS;
-        // terminal cost-to-go from record N
+        // lane roles: shared-memory offsets, recomputed per call and laundered so that they stay in
+        // registers through the stage loop instead of being rematerialised at every use
+        int a_p, a_m, a_ex, a_out, b_m, b_mk, b_t, b_h, b_o1, b_o2, e_f0, e_fi, e_fj, e_o1, e_o2, e_k0, e_k1;
         {
-            const double* rN = sm + W_SD + N * SDS;
+            const int i = (l < 24) ? (l >> 2) : (l < 30 ? l - 24 : 0);
+            const int cc = (l < 24) ? (l & 3) : 4;
+            a_p = launder(SO(W_P + 6 * i));
+            a_m = launder(SO(W_SD + SD_MT + 6 * cc));
+            a_ex = launder((l >= 24 && l < 30) ? SO(W_PV + i) : SO(W_Z));
+            a_out = launder((l < 30) ? SO(W_TT + 6 * cc + i) : SO(W_DUMMY));
+        }
+        {
+            // 21 symmetric pairs (c1 <= c2) over (x,y,psi,v,a,df); 6 vector entries; 4 copy lanes
+            int c1 = 0, c2 = 0, kind = 0;  // 0 pair, 1 vector, 2 copy, 3 idle
+            if (l < 21) { int t = l; while (t >= 6 - c1) { t -= 6 - c1; c1++; } c2 = c1 + t; }
+            else if (l < 27) { c1 = l - 21; kind = 1; }
+            else if (l < 31) kind = 2;
+            else kind = 3;
+            int mb, mk, tb, h, o1, o2;
+            if (kind >= 2) { mb = SO(W_Z); mk = 0; }
+            else if (c1 < 2) { mb = (c1 == 0) ? SO(W_EX) : SO(W_EY); mk = 0; }
+            else { mb = SO(W_SD + SD_MT + 6 * (c1 - 2)); mk = 1; }
+            if (kind == 1) tb = SO(W_TT + 24);
+            else if (kind == 0) tb = (c2 < 2) ? SO(W_P + 6 * c2) : SO(W_TT + 6 * (c2 - 2));  // P symmetric: column = row
+            else tb = SO(W_Z);
+            int hf = SD_ZERO;
+            if (kind == 1) hf = SD_GX + c1;
+            else if (kind == 0) {
+                if (c1 == c2) hf = (c1 == 0) ? SD_HXX : (c1 == 1) ? SD_HYY : (c1 == 2) ? SD_HPP : (c1 == 3) ? SD_HVV : (c1 == 4) ? SD_HAA : SD_HDD;
+                else if (c1 == 2 && c2 == 3) hf = SD_HPV;
+                else if (c1 == 2 && c2 == 5) hf = SD_HPD;
+                else if (c1 == 3 && c2 == 5) hf = SD_HVD;
+            } else if (kind == 2) hf = (l == 27) ? SD_CA : (l == 28) ? SD_CD : (l == 29) ? SD_NCA : SD_NCD;
+            h = SO(W_SD + hf);
+            if (kind == 0) { o1 = SO(W_F + 6 * c1 + c2); o2 = SO(W_F + 6 * c2 + c1); }
+            else if (kind == 1) { o1 = o2 = SO(W_FV + c1); }
+            else if (kind == 2) { o1 = o2 = (l == 27) ? SO(W_C) : (l == 28) ? SO(W_C + 1) : (l == 29) ? SO(W_NC) : SO(W_NC + 3); }
+            else { o1 = o2 = SO(W_DUMMY); }
+            b_m = launder(mb); b_mk = launder(mk); b_t = launder(tb); b_h = launder(h); b_o1 = launder(o1); b_o2 = launder(o2);
+        }
+        {
+            // 21 symmetric pairs (i <= j) over xi, then 6 vector entries.
+            // P'[i][j] = F8[i][j] + F8[i][a] K[0][j] + F8[i][df] K[1][j],  K[.][j] = -Fuu^{-1} (F8[j][a], F8[j][df])
+            int i = 0, j = 0, vec = 0, act = 1;
+            if (l < 21) { int t = l; while (t >= 6 - i) { t -= 6 - i; i++; } j = i + t; }
+            else if (l < 27) { i = l - 21; vec = 1; }
+            else act = 0;
+            int f0;
+            if (vec) f0 = (i < 4) ? SO(W_FV + i) : SO(W_Z);
+            else if (i < 4 && j < 4) f0 = SO(W_F + 6 * i + j);
+            else if (i == 4 && j == 4) f0 = SO(W_C);
+            else if (i == 5 && j == 5) f0 = SO(W_C + 1);
+            else f0 = SO(W_Z);
+            auto pairof = [](int q) {   // (F8[q][a], F8[q][df]) for q over xi; q = 6: (f_a, f_df)
+                return (q < 4) ? SO(W_F + 6 * q + 4) : (q == 4) ? SO(W_NC) : (q == 5) ? SO(W_NC + 2) : SO(W_FV + 4);
+            };
+            const int fi = pairof(i), fj = pairof(vec ? 6 : j);
+            int o1, o2;
+            if (!act) { o1 = o2 = SO(W_DUMMY); }
+            else if (vec) { o1 = o2 = SO(W_PV + i); }
+            else { o1 = SO(W_P + 6 * i + j); o2 = SO(W_P + 6 * j + i); }
+            // gain storage: the diagonal pairs (j,j) hold K[.][j], vector lane i = 0 holds K[.][6]
+            int ks = -1;
+            if (act && !vec && i == j) ks = j;
+            if (act && vec && i == 0) ks = 6;
+            const int kb = SO(W_SD + (N + 1) * SDS + (N - 1) * KST_STRIDE);  // gains of stage N-1
+            e_f0 = launder(f0); e_fi = launder(fi); e_fj = launder(fj); e_o1 = launder(o1); e_o2 = launder(o2);
+            e_k0 = launder(ks >= 0 ? kb + SO(ks) : SO(W_DUMMY));
+            e_k1 = launder(ks >= 0 ? kb + SO(7 + ks) : SO(W_DUMMY));
+        }
+        const int kstep = launder((e_k0 == SO(W_DUMMY)) ? 0 : SO(KST_STRIDE));
+        {   // terminal cost-to-go from record N
+            const int rN = SO(W_SD + N * SDS);
             for (int e = l; e < 36; e += 32) {
-                const int i = e / 6, j = e % 6;
+                const int i = e / 6, j = e - 6 * i;
                 double v = 0.0;
-                if (i == j && i < 4) v = rN[SD_HXX + (i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 2 : 4)];
-                sm[W_P + e] = v;
+                if (i == j && i < 4) v = lds(sm, rN + SO((i == 0) ? SD_HXX : (i == 1) ? SD_HYY : (i == 2) ? SD_HPP : SD_HVV));
+                sts(sm, SO(W_P + e), v);
             }
-            if (l < 6) sm[W_PV + l] = (l < 4) ? rN[SD_GX + l] : 0.0;
+            if (l < 6) sts(sm, SO(W_PV + l), (l < 4) ? lds(sm, rN + SO(SD_GX + l)) : 0.0);
         }
         syncwarp();
         bool ok = true;
+        int so = SO((N - 1) * SDS);   // byte offset of the current stage's record relative to record 0
         for (int s = N - 1; s >= 0; s--) {
-            const int so = s * SDS;
-            // ---- Round A: T = P * [A B; 0 I](:, psi|v|a|df),  t = P r + p
-            {
-                const double* p = sm + R.a_pb;
-                const double* m = sm + R.a_mb + so;
-                const double t0 = p[0] * m[0] + p[1] * m[1] + p[2] * m[2];
-                const double t1 = p[3] * m[3] + p[4] * m[4] + p[5] * m[5] + sm[R.a_ex];
-                sm[R.a_out] = t0 + t1;
+            {   // ---- Round A
+                const d2 p0 = lds2(sm, a_p), p1 = lds2(sm, a_p + SO(2)), p2 = lds2(sm, a_p + SO(4));
+                const int m = a_m + so;
+                const d2 m0 = lds2(sm, m), m1 = lds2(sm, m + SO(2)), m2 = lds2(sm, m + SO(4));
+                const double ex = lds(sm, a_ex);
+                const double t0 = p0.x * m0.x + p0.y * m0.y;
+                const double t1 = p1.x * m1.x + p1.y * m1.y;
+                const double t2 = p2.x * m2.x + p2.y * m2.y + ex;
+                sts(sm, a_out, (t0 + t1) + t2);
             }
             syncwarp();
-            // ---- Round B: F = H + M' T,  f = g + M' t
-            {
-                const double* m = sm + R.b_mb + (R.b_mk ? so : 0);
-                const double* t = sm + R.b_tb;
-                const double h = sm[R.b_h + (R.b_hk ? so : 0)];
-                const double t0 = m[0] * t[0] + m[1] * t[6] + m[2] * t[12];
-                const double t1 = m[3] * t[18] + m[4] * t[24] + m[5] * t[30] + h;
-                const double o = t0 + t1;
-                sm[R.b_o1] = o; sm[R.b_o2] = o;
+            {   // ---- Round B
+                const int m = b_m + b_mk * so;
+                const d2 m0 = lds2(sm, m), m1 = lds2(sm, m + SO(2)), m2 = lds2(sm, m + SO(4));
+                const d2 q0 = lds2(sm, b_t), q1 = lds2(sm, b_t + SO(2)), q2 = lds2(sm, b_t + SO(4));
+                const double h = lds(sm, b_h + so);
+                const double t0 = m0.x * q0.x + m0.y * q0.y;
+                const double t1 = m1.x * q1.x + m1.y * q1.y;
+                const double t2 = m2.x * q2.x + m2.y * q2.y + h;
+                const double o = (t0 + t1) + t2;
+                sts(sm, b_o1, o); sts(sm, b_o2, o);
             }
             syncwarp();
-            // ---- Round C: 2x2 input block, inertia check, inverse (all lanes redundantly)
-            const double faa = sm[W_F + 28], fad = sm[W_F + 29], fdd = sm[W_F + 35];
-            const double det = faa * fdd - fad * fad;
-            if (!(faa > 0.0) || !(det > 0.0)) { ok = false; break; }
-            const double idet = 1.0 / det;
-            const double i00 = fdd * idet, i01 = -fad * idet, i11 = faa * idet;
-            // ---- Round D: gains K = -Fuu^{-1} [F_u,xi | f_u]
-            {
-                const double* x = sm + R.d_xb + (R.d_xk ? so : 0);
-                const double x0 = x[0], x1 = x[1];
-                const double g = (R.d_r == 0) ? -(i00 * x0 + i01 * x1) : -(i01 * x0 + i11 * x1);
-                if (R.d_out >= 0) kst[s * KST_STRIDE + R.d_out] = g;
+            {   // ---- Round E (with the 2x2 inverse computed by every lane)
+                const d2 fa = lds2(sm, SO(W_F + 28));
+                const double fdd = lds(sm, SO(W_F + 35));
+                const d2 fj = lds2(sm, e_fj);
+                const d2 fi = lds2(sm, e_fi);
+                const double f0 = lds(sm, e_f0);
+                const double faa = fa.x, fad = fa.y;
+                const double det = faa * fdd - fad * fad;
+                if (!(faa > 0.0) || !(det > 0.0)) { ok = false; break; }
+                const double idet = 1.0 / det;
+                const double i00 = fdd * idet, i01 = -fad * idet, i11 = faa * idet;
+                const double k0 = -(i00 * fj.x + i01 * fj.y), k1 = -(i01 * fj.x + i11 * fj.y);
+                sts(sm, e_k0, k0); sts(sm, e_k1, k1);
+                const double o = f0 + (fi.x * k0 + fi.y * k1);
+                sts(sm, e_o1, o); sts(sm, e_o2, o);
             }
             syncwarp();
-            // ---- Round E: P <- F_xixi + F_xi,u K ; p <- f_xi + F_xi,u k   (not needed for s = 0)
-            if (s > 0) {
-                const double f0 = sm[R.e_f0 + (R.e_f0k ? so : 0)];
-                const double* f1 = sm + R.e_f1 + (R.e_f1k ? so : 0);
-                const double* kk = kst + s * KST_STRIDE + R.e_kb;
-                const double o = f0 + (f1[0] * kk[0] + f1[1] * kk[7]);
-                sm[R.e_o1] = o; sm[R.e_o2] = o;
-                syncwarp();
-            }
+            so -= SO(SDS); e_k0 -= kstep; e_k1 -= kstep;
         }
         return ok;
     }
 
     // forward sweep (every lane runs the scalar recursion; lane k keeps stage k)
-    MPC_DEV void riccati_forward(const double* ds0) {
-        const double* kst = sm + W_SD + (N + 1) * SDS;
-        double s0 = shfl(ds0[0], 0), s1 = shfl(ds0[1], 0), s2 = shfl(ds0[2], 0), s3 = shfl(ds0[3], 0);
+    MPC_DEV void riccati_forward() {
+        int kp = SO(W_SD + (N + 1) * SDS);
+        int r = SO(W_SD);
+        const d2 i01 = lds2(sm, SO(W_SD + N * SDS + SD_R)), i23 = lds2(sm, SO(W_SD + N * SDS + SD_R + 2));  // ds_0
+        double s0 = i01.x, s1 = i01.y, s2 = i23.x, s3 = i23.y;
         double pa = 0.0, pd = 0.0;
         D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0;
         for (int s = 0; s < N; s++) {
-            const double* K = kst + s * KST_STRIDE;
-            const double* r = sm + W_SD + s * SDS;
-            const double ua = (K[0] * s0 + K[1] * s1 + K[2] * s2) + (K[3] * s3 + K[4] * pa + K[5] * pd) + K[6];
-            const double ud = (K[7] * s0 + K[8] * s1 + K[9] * s2) + (K[10] * s3 + K[11] * pa + K[12] * pd) + K[13];
+            const d2 ka0 = lds2(sm, kp), ka1 = lds2(sm, kp + SO(2)), ka2 = lds2(sm, kp + SO(4)), kx = lds2(sm, kp + SO(6));
+            const d2 kd0 = lds2(sm, kp + SO(8)), kd1 = lds2(sm, kp + SO(10)), kd2 = lds2(sm, kp + SO(12));
+            const d2 cp = lds2(sm, r + SO(SD_MT + 0)), cv = lds2(sm, r + SO(SD_MT + 6)), cd = lds2(sm, r + SO(SD_MT + 18));
+            const double a23 = lds(sm, r + SO(SD_MT + 8)), b2 = lds(sm, r + SO(SD_MT + 20));
+            const d2 r01 = lds2(sm, r + SO(SD_R)), r23 = lds2(sm, r + SO(SD_R + 2));
+            const double ua = (ka0.x * s0 + ka0.y * s1 + ka1.x * s2) + (ka1.y * s3 + ka2.x * pa + ka2.y * pd) + kx.x;
+            const double ud = (kx.y * s0 + kd0.x * s1 + kd0.y * s2) + (kd1.x * s3 + kd1.y * pa + kd2.x * pd) + kd2.y;
             if (s == k) { D.dsx = s0; D.dsy = s1; D.dsp = s2; D.dsv = s3; D.dua = ua; D.dud = ud; }
-            // next state: columns psi (0..5), v (6..11), a (12..17), df (18..23), r (24..29)
-            const double n0 = s0 + r[SD_MT + 0] * s2 + r[SD_MT + 6] * s3 + r[SD_MT + 18] * ud + r[SD_MT + 24];
-            const double n1 = s1 + r[SD_MT + 1] * s2 + r[SD_MT + 7] * s3 + r[SD_MT + 19] * ud + r[SD_MT + 25];
-            const double n2 = s2 + r[SD_MT + 8] * s3 + r[SD_MT + 20] * ud + r[SD_MT + 26];
-            const double n3 = s3 + r[SD_MT + 15] * ua + r[SD_MT + 27];
+            const double n0 = s0 + cp.x * s2 + cv.x * s3 + cd.x * ud + r01.x;
+            const double n1 = s1 + cp.y * s2 + cv.y * s3 + cd.y * ud + r01.y;
+            const double n2 = s2 + a23 * s3 + b2 * ud + r23.x;
+            const double n3 = s3 + c.dt * ua + r23.y;
             s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
+            kp += SO(KST_STRIDE); r += SO(SDS);
         }
         if (k == N) { D.dsx = s0; D.dsy = s1; D.dsp = s2; D.dsv = s3; }
     }
 
     // new equality multipliers from stationarity in the state variables (parallel suffix sums),
-    // new rate-row multipliers and slack steps.  rdr = rate-row residual used in the solve.
-    MPC_DEV void recover_duals(const Cond& q, const double* rdr) {
-        // local_k = -(H_ss ds + H_su du + g_s)
+    // new rate-row multipliers and slack steps; the condensed blocks are read back from the record
+    MPC_DEV void recover_duals() {
+        const int r = rec();
         double lx = 0.0, ly = 0.0, lp = 0.0, lv = 0.0;
+        const double hpv = lds(sm, r + SO(SD_HPV));
         if (isS) {
-            lx = -(q.Hxx * D.dsx + q.gsx);
-            ly = -(q.Hyy * D.dsy + q.gsy);
-            lp = -(q.Hpp * D.dsp + q.Hpv * D.dsv + q.Hpd * D.dud + q.gsp);
-            lv = -(q.Hpv * D.dsp + q.Hvv * D.dsv + q.Hvd * D.dud + q.gsv);
+            lx = -(lds(sm, r + SO(SD_HXX)) * D.dsx + lds(sm, r + SO(SD_GX)));
+            ly = -(lds(sm, r + SO(SD_HYY)) * D.dsy + lds(sm, r + SO(SD_GX + 1)));
+            lp = -(lds(sm, r + SO(SD_HPP)) * D.dsp + hpv * D.dsv + lds(sm, r + SO(SD_HPD)) * D.dud + lds(sm, r + SO(SD_GX + 2)));
+            lv = -(hpv * D.dsp + lds(sm, r + SO(SD_HVV)) * D.dsv + lds(sm, r + SO(SD_HVD)) * D.dud + lds(sm, r + SO(SD_GX + 3)));
         }
-        // y_k = local_k + A_k' y_{k+1}
-        const double* r = sm + W_SD + (isS ? k : 0) * SDS;
-        const double A02 = r[SD_MT + 0], A12 = r[SD_MT + 1], A03 = r[SD_MT + 6], A13 = r[SD_MT + 7], A23 = r[SD_MT + 8];
-        D.nyx = warp_suffix_sum(lx);
-        D.nyy = warp_suffix_sum(ly);
-        const double nx1 = shfl_down(D.nyx, 1), ny1 = shfl_down(D.nyy, 1);
         const double hasn = isU ? 1.0 : 0.0;
-        D.nyp = warp_suffix_sum(lp + hasn * (A02 * nx1 + A12 * ny1));
+        const d2 c0 = lds2(sm, r + SO(SD_MT + 0)), c1 = lds2(sm, r + SO(SD_MT + 6));   // (A02, A12), (A03, A13)
+        const double A23 = lds(sm, r + SO(SD_MT + 8));
+        for (int o = 1; o < 32; o <<= 1) {   // y_x, y_y: two interleaved suffix sums
+            const double tx = shfl_down(lx, o), ty = shfl_down(ly, o);
+            if (k + o < 32) { lx += tx; ly += ty; }
+        }
+        D.nyx = lx; D.nyy = ly;
+        const double nx1 = shfl_down(lx, 1), ny1 = shfl_down(ly, 1);
+        D.nyp = warp_suffix_sum(lp + hasn * (c0.x * nx1 + c0.y * ny1), k);
         const double np1 = shfl_down(D.nyp, 1);
-        D.nyv = warp_suffix_sum(lv + hasn * (A03 * nx1 + A13 * ny1 + A23 * np1));
-        // rate rows
+        D.nyv = warp_suffix_sum(lv + hasn * (c1.x * nx1 + c1.y * ny1 + A23 * np1), k);
         const double pa = shfl_up(D.dua, 1), pd = shfl_up(D.dud, 1);
         D.drs[0] = D.drs[1] = 0.0; D.nyd[0] = D.nyd[1] = 0.0;
         if (isR) {
             const double ba = (k == 0) ? 0.0 : pa, bd = (k == 0) ? 0.0 : pd;
-            D.drs[0] = (D.dud - bd) + rdr[0];
-            D.drs[1] = (D.dua - ba) + rdr[1];
-            D.nyd[0] = q.SrW[0] * D.drs[0] + q.br[0];
-            D.nyd[1] = q.SrW[1] * D.drs[1] + q.br[1];
+            const d2 srw = lds2(sm, r + SO(SD_SRW)), brr = lds2(sm, r + SO(SD_BR)), drr = lds2(sm, r + SO(SD_DR));
+            D.drs[0] = (D.dud - bd) + drr.x;
+            D.drs[1] = (D.dua - ba) + drr.y;
+            D.nyd[0] = srw.x * D.drs[0] + brr.x;
+            D.nyd[1] = srw.y * D.drs[1] + brr.y;
         }
     }
 
-    // fraction-to-the-boundary for the primal step
+    // fraction-to-the-boundary for the primal step: tau / max_i( -dx_i / slack_i ), division-free per element
     MPC_DEV double alpha_primal(double tau) const {
-        double a = 1.0;
-        if (isS) {
-            if (D.dsv < 0.0) a = dmin_(a, -tau * (L.sv - vLo) / D.dsv);
-            if (D.dsv > 0.0) a = dmin_(a, tau * (vHi - L.sv) / D.dsv);
-        }
-        if (isU) {
-            if (D.dua < 0.0) a = dmin_(a, -tau * (L.ua - aLo) / D.dua);
-            if (D.dua > 0.0) a = dmin_(a, tau * (aHi - L.ua) / D.dua);
-            if (D.dud < 0.0) a = dmin_(a, -tau * (L.ud - dLo) / D.dud);
-            if (D.dud > 0.0) a = dmin_(a, tau * (dHi - L.ud) / D.dud);
-        }
-        if (isR) for (int i = 0; i < 2; i++) {
-            if (D.drs[i] < 0.0) a = dmin_(a, -tau * (L.rs[i] - rLo[i]) / D.drs[i]);
-            if (D.drs[i] > 0.0) a = dmin_(a, tau * (rHi[i] - L.rs[i]) / D.drs[i]);
-        }
-        return warp_min(a);
+        double num = 0.0, den = 1.0;   // largest ratio num/den (num >= 0, den > 0) by cross-multiplication
+        auto upd = [&](double dx, double sl, double su) {
+            const double n = fabs(dx), d = (dx < 0.0) ? sl : su;
+            if (n * den > num * d) { num = n; den = d; }
+        };
+        if (isS) upd(D.dsv, L.sv - c.vLo, c.vHi - L.sv);
+        if (isU) { upd(D.dua, L.ua - c.aLo, c.aHi - L.ua); upd(D.dud, L.ud - c.dLo, c.dHi - L.ud); }
+        if (isR) { const double h0 = rHi(0), h1 = rHi(1); upd(D.drs[0], L.rs[0] + h0, h0 - L.rs[0]); upd(D.drs[1], L.rs[1] + h1, h1 - L.rs[1]); }
+        const double a = (num > 0.0) ? tau * den / num : 1.0;  // num == 0: no limit from this lane
+        return dmin_(1.0, warp_min(a));
     }
-
-    // bound-multiplier steps: dz = mu/sl - z - (z/sl) dx  (lower),  mu/su - z + (z/su) dx (upper)
-    MPC_DEV static double dzl(double mu, double z, double sl, double dx) { return mu / sl - z - z / sl * dx; }
-    MPC_DEV static double dzu(double mu, double z, double su, double dx) { return mu / su - z + z / su * dx; }
-
-    // ------------------------------------------------------------------
-    // the whole solve
-    // ------------------------------------------------------------------
-    struct Result { int status; int iters; double cost; };
 
     MPC_DEV bool nlp_feasible() const {
         const double e = 1e-8;
         const double lim_d = c.sdmax * c.dtc, lim_a = c.admax * c.dtc;
-        if (st0[3] < c.vmin - e * dmax_(1.0, fabs(c.vmin))) return false;
-        if (st0[3] > c.vmax + e * dmax_(1.0, fabs(c.vmax))) return false;
-        if (uprev[0] - lim_d > c.smax + 2 * e || uprev[0] + lim_d < -c.smax - 2 * e) return false;
-        if (uprev[1] - lim_a > c.amax + 2 * e || uprev[1] + lim_a < -c.amax - 2 * e) return false;
+        const double v0 = cst(3), up0 = cst(4), up1 = cst(5);
+        if (v0 < c.vmin - e * dmax_(1.0, fabs(c.vmin))) return false;
+        if (v0 > c.vmax + e * dmax_(1.0, fabs(c.vmax))) return false;
+        if (up0 - lim_d > c.smax + 2 * e || up0 + lim_d < -c.smax - 2 * e) return false;
+        if (up1 - lim_a > c.amax + 2 * e || up1 + lim_a < -c.amax - 2 * e) return false;
         return true;
     }
 
+    // ------------------------------------------------------------------
+    // the whole solve
+    // ------------------------------------------------------------------
     MPC_DEV Result solve() {
         Result res; res.status = 4; res.iters = 0; res.cost = 0.0;
-        // ---- bounds, relaxed by bound_relax_factor
-        vLo = c.vmin - K_BOUND_RELAX * dmax_(1.0, fabs(c.vmin)); vHi = c.vmax + K_BOUND_RELAX * dmax_(1.0, fabs(c.vmax));
-        aLo = -c.amax - K_BOUND_RELAX * dmax_(1.0, c.amax); aHi = c.amax + K_BOUND_RELAX * dmax_(1.0, c.amax);
-        dLo = -c.smax - K_BOUND_RELAX * dmax_(1.0, c.smax); dHi = c.smax + K_BOUND_RELAX * dmax_(1.0, c.smax);
-        {
-            const double h = (k == 0) ? c.dtc : c.dt;
-            const double ld = c.sdmax * h, la = c.admax * h;
-            rLo[0] = -ld - K_BOUND_RELAX * dmax_(1.0, ld); rHi[0] = ld + K_BOUND_RELAX * dmax_(1.0, ld);
-            rLo[1] = -la - K_BOUND_RELAX * dmax_(1.0, la); rHi[1] = la + K_BOUND_RELAX * dmax_(1.0, la);
-        }
-        wx = (k >= 1 && k <= N) ? c.w[0] : 0.0;
-        wy = (k >= 1 && k <= N) ? c.w[1] : 0.0;
-        wp = (k >= 1 && k <= N) ? c.w[2] : 0.0;
-        wv = (k >= 1 && k <= N - 1) ? c.w[3] : 0.0;
+        D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0; D.drs[0] = D.drs[1] = 0.0;
+        D.nyx = D.nyy = D.nyp = D.nyv = 0.0; D.nyd[0] = D.nyd[1] = 0.0;
+        L.rs[0] = L.rs[1] = 0.0;
+        L.zvL = L.zvU = L.zaL = L.zaU = L.zdL = L.zdU = 0.0;
+        L.rvL[0] = L.rvL[1] = L.rvU[0] = L.rvU[1] = 0.0;
+        L.ryd[0] = L.ryd[1] = 0.0; L.yx = L.yy = L.yp = L.yv = 0.0;
 
-        if (!nlp_feasible()) {
-            res.status = 1; res.iters = 0;
-            res.cost = objective(L.sx, L.sy, L.sp, L.sv, L.ua, L.ud);
-            return res;
-        }
+        const bool feasible = nlp_feasible();
+        int ret = feasible ? -1 : 2;
 
         // ---- objective scaling from the gradient at the user's start point
         sigma = 1.0;
-        objective_gradient();
         {
-            double gm = dmax_(dmax_(fabs(gx), fabs(gy)), dmax_(fabs(gp), fabs(gv)));
-            gm = dmax_(gm, dmax_(fabs(ga), fabs(gd)));
-            gm = warp_max(gm);
+            const Grad g = objective_gradient();
+            double gm = dmax_(dmax_(fabs(g.x), fabs(g.y)), dmax_(fabs(g.p), fabs(g.v)));
+            gm = warp_max(dmax_(gm, dmax_(fabs(g.a), fabs(g.d))));
             sigma = (gm > K_SCALE_MAX_GRAD) ? dmax_(K_SCALE_MAX_GRAD / gm, 1e-8) : 1.0;
         }
-        // ---- push into the interior, slacks, bound multipliers
-        if (isS) push_interior(L.sv, vLo, vHi);
-        if (isU) { push_interior(L.ua, aLo, aHi); push_interior(L.ud, dLo, dHi); }
-        {
-            double zero2[2] = {0.0, 0.0};
-            eval_defects(L.sx, L.sy, L.sp, L.sv, L.ua, L.ud, zero2, tg, rdyn, rinit, dres);
-            L.rs[0] = dres[0]; L.rs[1] = dres[1];
-            if (isR) { push_interior(L.rs[0], rLo[0], rHi[0]); push_interior(L.rs[1], rLo[1], rHi[1]); }
-        }
-        L.zvL = L.zvU = isS ? 1.0 : 0.0;
-        L.zaL = L.zaU = L.zdL = L.zdU = isU ? 1.0 : 0.0;
-        L.rvL[0] = L.rvL[1] = L.rvU[0] = L.rvU[1] = isR ? 1.0 : 0.0;
-        L.ryd[0] = L.ryd[1] = 0.0;
-        L.yx = L.yy = L.yp = L.yv = 0.0;
-
-        Cond q;
-        // ---- least-squares equality multipliers
-        {
-            objective_gradient();
-            eval_defects(L.sx, L.sy, L.sp, L.sv, L.ua, L.ud, L.rs, tg, rdyn, rinit, dres);
-            build_cond_ls(q);
-            const double zr[4] = {0.0, 0.0, 0.0, 0.0};
-            const double zd[2] = {0.0, 0.0};
-            if (isS) write_record(q, zr);
-            syncwarp();
-            const bool ok = riccati_backward();
-            bool use = ok;
-            if (ok) {
-                riccati_forward(zr);
-                recover_duals(q, zd);
-                double ym = dmax_(dmax_(fabs(D.nyx), fabs(D.nyy)), dmax_(fabs(D.nyp), fabs(D.nyv)));
-                ym = dmax_(ym, dmax_(fabs(D.nyd[0]), fabs(D.nyd[1])));
-                ym = isS ? ym : 0.0;
-                ym = warp_max(ym);
-                use = (ym <= K_Y_INIT_MAX);
+        if (feasible) {
+            // ---- push into the interior, slacks = d(x) pushed, bound multipliers = 1
+            if (isS) push_interior(L.sv, c.vLo, c.vHi);
+            if (isU) { push_interior(L.ua, c.aLo, c.aHi); push_interior(L.ud, c.dLo, c.dHi); }
+            const double pa = shfl_up(L.ua, 1), pd = shfl_up(L.ud, 1);
+            if (isR) {
+                const double h0 = rHi(0), h1 = rHi(1);
+                L.rs[0] = L.ud - ((k == 0) ? cst(4) : pd);
+                L.rs[1] = L.ua - ((k == 0) ? cst(5) : pa);
+                push_interior(L.rs[0], -h0, h0); push_interior(L.rs[1], -h1, h1);
             }
-            if (use && isS) { L.yx = D.nyx; L.yy = D.nyy; L.yp = D.nyp; L.yv = D.nyv; L.ryd[0] = D.nyd[0]; L.ryd[1] = D.nyd[1]; }
-            syncwarp();
+            L.zvL = L.zvU = isS ? 1.0 : 0.0;
+            L.zaL = L.zaU = L.zdL = L.zdU = isU ? 1.0 : 0.0;
+            L.rvL[0] = L.rvL[1] = L.rvU[0] = L.rvU[1] = isR ? 1.0 : 0.0;
         }
+
+        enum { PH_EVAL0 = 0, PH_LS, PH_BEGIN, PH_PD, PH_RESOLVE_EVAL, PH_RESOLVE, PH_TRIAL, PH_SOC };
+        int phase = PH_EVAL0;
+        bool do_solve = false, do_eval = true, eval_ftb = false;
+        int req = 0;
+        double ev_alpha = 0.0;
 
         double mu = K_MU_INIT, tau = dmax_(K_TAU_MIN, 1.0 - K_MU_INIT);
-        const double mu_min = dmin_(c.tol, 1e-4) / (K_KAPPA_EPS + 1.0);
-        double dw_last = 0.0, theta_max = -1.0, theta_min = -1.0;
+        double dw = 0.0, dw_last = 0.0, theta_max = -1.0, theta_min = -1.0;
         double f_phi = 0.0, f_theta = 0.0;  // this lane's filter entry (entry e lives in lane e)
-        int nfilt = 0, accept_count = 0, iter = 0, ret = -1;
-        bool tiny_last = false;
+        int nfilt = 0, accept_count = 0, iter = 0;
+        bool tiny_last = false, tiny = false, solve_ok = false;
+        // current-point scalars and line-search state of the current iteration
+        double cur_theta = 0.0, cur_f = 0.0, cur_lb = 0.0;
+        double phi = 0.0, gBd = 0.0, alpha = 1.0, alpha_max = 1.0, Rft = 0.0, a_soc = 0.0;
+        double th_soc_old = 0.0;
+        int nsteps = 0, soc_cnt = 0;
         const int nz = 2 * (3 * N + 1) + 4 * (N - 1);  // bound multipliers: x-bounds + slack bounds
         const int my = 4 * (N + 1) + 2 * (N - 1);      // equality multipliers y_c, y_d
 
-        for (;;) {
-            // ---- evaluate at the current iterate
-            objective_gradient();
-            eval_defects(L.sx, L.sy, L.sp, L.sv, L.ua, L.ud, L.rs, tg, rdyn, rinit, dres);
-            const double theta = theta_of(rdyn, rinit, dres);
-            // stage Jacobian entries (also used for the record)
-            const double A02 = isU ? -c.dt * L.sv * tg.sn : 0.0, A03 = isU ? c.dt * tg.cs : 0.0;
-            const double A12 = isU ? c.dt * L.sv * tg.cs : 0.0, A13 = isU ? c.dt * tg.sn : 0.0;
-            const double A23 = isU ? c.dt * tg.sb / c.Lb : 0.0;
-            const double b0 = A02 * tg.b1, b1v = A12 * tg.b1, b2v = isU ? c.dt * L.sv * tg.cb * tg.b1 / c.Lb : 0.0;
-            // dual infeasibility of this stage's variables
-            double di, cv, sumy, sumz;
-            {
-                const double y1x = shfl_down(L.yx, 1), y1y = shfl_down(L.yy, 1), y1p = shfl_down(L.yp, 1), y1v = shfl_down(L.yv, 1);
-                const double yd1_0 = shfl_down(L.ryd[0], 1), yd1_1 = shfl_down(L.ryd[1], 1);
-                const double hn = isU ? 1.0 : 0.0;
-                const double glx = gx + L.yx - hn * y1x;
-                const double gly = gy + L.yy - hn * y1y;
-                const double glp = gp + L.yp - hn * (A02 * y1x + A12 * y1y + y1p);
-                const double glv = gv + L.yv - hn * (A03 * y1x + A13 * y1y + A23 * y1p + y1v) - L.zvL + L.zvU;
-                const double nd0 = (k + 1 < N) ? yd1_0 : 0.0, nd1 = (k + 1 < N) ? yd1_1 : 0.0;
-                const double gla = ga - hn * c.dt * y1v + (L.ryd[1] - nd1) - L.zaL + L.zaU;
-                const double gld = gd - hn * (b0 * y1x + b1v * y1y + b2v * y1p) + (L.ryd[0] - nd0) - L.zdL + L.zdU;
-                di = dmax_(dmax_(fabs(glx), fabs(gly)), dmax_(fabs(glp), fabs(glv)));
-                di = dmax_(di, dmax_(fabs(gla), fabs(gld)));
-                di = dmax_(di, dmax_(fabs(-L.ryd[0] - L.rvL[0] + L.rvU[0]), fabs(-L.ryd[1] - L.rvL[1] + L.rvU[1])));
-                di = isS ? di : 0.0;
-                cv = dmax_(dmax_(fabs(rdyn[0]), fabs(rdyn[1])), dmax_(fabs(rdyn[2]), fabs(rdyn[3])));
-                cv = dmax_(cv, dmax_(dmax_(fabs(rinit[0]), fabs(rinit[1])), dmax_(fabs(rinit[2]), fabs(rinit[3]))));
-                cv = dmax_(cv, dmax_(fabs(dres[0]), fabs(dres[1])));
-                sumy = isS ? fabs(L.yx) + fabs(L.yy) + fabs(L.yp) + fabs(L.yv) + fabs(L.ryd[0]) + fabs(L.ryd[1]) : 0.0;
-                sumz = L.zvL + L.zvU + L.zaL + L.zaU + L.zdL + L.zdU + L.rvL[0] + L.rvL[1] + L.rvU[0] + L.rvU[1];
-                di = warp_max(di); cv = warp_max(cv); sumy = warp_sum(sumy); sumz = warp_sum(sumz);
-            }
-            const double sd = dmax_(K_S_MAX, (sumy + sumz) / (double)(my + nz)) / K_S_MAX;
-            const double sc = dmax_(K_S_MAX, sumz / (double)nz) / K_S_MAX;
-            // complementarity for target t: max |sl*z - t|
-            auto compl_err = [&](double t) {
-                double m = 0.0;
-                if (isS) { m = dmax_(m, fabs((L.sv - vLo) * L.zvL - t)); m = dmax_(m, fabs((vHi - L.sv) * L.zvU - t)); }
-                if (isU) {
-                    m = dmax_(m, fabs((L.ua - aLo) * L.zaL - t)); m = dmax_(m, fabs((aHi - L.ua) * L.zaU - t));
-                    m = dmax_(m, fabs((L.ud - dLo) * L.zdL - t)); m = dmax_(m, fabs((dHi - L.ud) * L.zdU - t));
-                }
-                if (isR) for (int i = 0; i < 2; i++) {
-                    m = dmax_(m, fabs((L.rs[i] - rLo[i]) * L.rvL[i] - t)); m = dmax_(m, fabs((rHi[i] - L.rs[i]) * L.rvU[i] - t));
-                }
-                return warp_max(m);
-            };
-            // ---- convergence
-            {
-                const double cm0 = compl_err(0.0);
-                const double E0 = dmax_(dmax_(di / sd, cv), cm0 / sc);
-                const double du = di / sigma, mc = cm0 / sigma;
-                if (E0 <= c.tol && du <= 1.0 && cv <= 1e-4 && mc <= 1e-4) { ret = 0; break; }
-                if (E0 <= K_ACCEPT_TOL && du <= 1e10 && cv <= 1e-2 && mc <= 1e-2) {
-                    if (++accept_count >= K_ACCEPT_ITER) { ret = 1; break; }
-                } else accept_count = 0;
-            }
-            if (iter >= c.max_iter) { ret = -1; break; }
-            {
-                double xm = dmax_(dmax_(fabs(L.sx), fabs(L.sy)), dmax_(fabs(L.sp), fabs(L.sv)));
-                xm = isS ? xm : 0.0;
-                xm = warp_max(xm);
-                if (!(xm <= 1e20)) { ret = -5; break; }
-            }
-            // ---- monotone barrier update
-            for (;;) {
-                const double cm = compl_err(mu);
-                const double Emu = dmax_(dmax_(di / sd, cv), cm / sc);
-                if (!(Emu <= K_KAPPA_EPS * mu) && !tiny_last) break;
-                const double nm = dmax_(mu_min, dmin_(K_KAPPA_MU * mu, pow(mu, K_THETA_MU)));
-                if (nm >= mu) { if (tiny_last) ret = -3; break; }
-                mu = nm; tau = dmax_(K_TAU_MIN, 1.0 - mu);
-                nfilt = 0;
-                if (tiny_last) { tiny_last = false; break; }
-            }
-            if (ret == -3) break;
-
-            // ---- primal-dual system: assemble, factorise with inertia correction, solve
-            double dw = 0.0;
-            {
-                bool ok = false;
-                const double rr[4] = {rdyn[0], rdyn[1], rdyn[2], rdyn[3]};
-                build_cond_pd(q, mu, dw, dres);
-                if (isS) write_record(q, rr);
+        while (feasible) {
+            // ================= shared heavy work =================
+            if (do_solve) {
+                assemble(req, mu, dw);
                 syncwarp();
-                for (;;) {
-                    ok = riccati_backward();
-                    if (ok) break;
-                    if (dw == 0.0) dw = (dw_last == 0.0) ? K_DW_INIT : dmax_(K_DW_MIN, dw_last * K_DW_DEC);
-                    else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? K_DW_INC_FIRST * dw : K_DW_INC * dw;
-                    if (dw > K_DW_MAX) break;
-                    syncwarp();
-                    build_cond_pd(q, mu, dw, dres);
-                    if (isS) patch_record_diag(q);
-                    syncwarp();
-                }
-                if (!ok) { ret = -4; break; }
-                if (dw > 0.0) dw_last = dw;
+                solve_ok = riccati_backward();
+                if (solve_ok) { riccati_forward(); recover_duals(); }
+                syncwarp();
             }
-            riccati_forward(rinit);
-            recover_duals(q, dres);
+            if (do_eval) {
+                if (eval_ftb) { ev_alpha = alpha_primal(tau); a_soc = ev_alpha; }
+                eval_point(ev_alpha);
+            }
+            do_solve = false; do_eval = false; eval_ftb = false;
 
-            // ---- line search quantities at the current point
-            const double fcur = objective(L.sx, L.sy, L.sp, L.sv, L.ua, L.ud);
-            const double phi = sigma * fcur - mu * log_barrier(L.sv, L.ua, L.ud, L.rs);
-            double gBd;
-            {
-                double t = gx * D.dsx + gy * D.dsy + gp * D.dsp + ga * D.dua + gd * D.dud;
-                if (isS) t += (gv - mu / (L.sv - vLo) + mu / (vHi - L.sv)) * D.dsv;
-                if (isU) {
-                    t += (-mu / (L.ua - aLo) + mu / (aHi - L.ua)) * D.dua;
-                    t += (-mu / (L.ud - dLo) + mu / (dHi - L.ud)) * D.dud;
-                }
-                if (isR) t += q.br[0] * D.drs[0] + q.br[1] * D.drs[1];
-                t = isS ? t : 0.0;
-                gBd = warp_sum(t);
-            }
-            if (theta_max < 0.0) { theta_max = 1e4 * dmax_(1.0, theta); theta_min = 1e-4 * dmax_(1.0, theta); }
-            double alpha_max = alpha_primal(tau);
-            double alpha_min = K_GAMMA_THETA;
-            if (gBd < 0.0) {
-                alpha_min = dmin_(K_GAMMA_THETA, K_GAMMA_PHI * theta / (-gBd));
-                if (theta <= theta_min) alpha_min = dmin_(alpha_min, K_DELTA * pow(theta, K_S_THETA) / pow(-gBd, K_S_PHI));
-            }
-            alpha_min *= K_ALPHA_MIN_FRAC;
-            bool tiny;
-            {
-                double m = 0.0;
-                if (isS) {
-                    m = dmax_(dmax_(fabs(D.dsx) / (1.0 + fabs(L.sx)), fabs(D.dsy) / (1.0 + fabs(L.sy))),
-                              dmax_(fabs(D.dsp) / (1.0 + fabs(L.sp)), fabs(D.dsv) / (1.0 + fabs(L.sv))));
-                    m = dmax_(m, dmax_(fabs(D.dua) / (1.0 + fabs(L.ua)), fabs(D.dud) / (1.0 + fabs(L.ud))));
-                    m = dmax_(m, dmax_(fabs(D.drs[0]) / (1.0 + fabs(L.rs[0])), fabs(D.drs[1]) / (1.0 + fabs(L.rs[1]))));
-                }
-                m = warp_max(m);
-                tiny = (m < 10.0 * K_EPS) && (theta < 1e-4);
-            }
-
-            // trial point storage
-            double tx, ty, tp, tv, ta, td, ts[2];
-            double alpha = alpha_max;
-            bool accepted = false, ftype_arm = false;
-            const double pw_gbd = (gBd < 0.0) ? pow(-gBd, K_S_PHI) : 0.0;
-            const double pw_th = K_DELTA * pow(theta, K_S_THETA);
-            auto make_trial = [&](double a) {
-                tx = L.sx + a * D.dsx; ty = L.sy + a * D.dsy; tp = L.sp + a * D.dsp; tv = L.sv + a * D.dsv;
-                ta = L.ua + a * D.dua; td = L.ud + a * D.dud; ts[0] = L.rs[0] + a * D.drs[0]; ts[1] = L.rs[1] + a * D.drs[1];
-            };
-            auto is_ftype = [&](double a) { return gBd < 0.0 && a * pw_gbd > pw_th; };
-            auto armijo = [&](double a, double pht) { return cmp_le(pht - phi, K_ETA_PHI * a * gBd, phi); };
-            auto accept_test = [&](double a, double tht, double pht) {
-                bool ok = (tht == tht) && (pht == pht);
-                if (ok && !cmp_le(tht, theta_max, theta)) ok = false;
-                if (ok) {
-                    if (is_ftype(a) && theta <= theta_min) ok = armijo(a, pht);
-                    else {
-                        if (pht > phi) {
-                            double bas = 1.0; if (fabs(phi) > 10.0) bas = log10(fabs(phi));
-                            if (log10(pht - phi) > K_OBJ_MAX_INC + bas) ok = false;
+            // ================= driver =================
+            if (phase == PH_TRIAL || phase == PH_SOC) {
+                const double alpha_test = (phase == PH_SOC) ? alpha_max : alpha;
+                const double th_t = ev.theta;
+                const double ph_t = sigma * ev.f - mu * ev.lb;
+                const double theta = cur_theta;
+                const bool ftype = (gBd < 0.0) && (alpha_test > K_DELTA * Rft);
+                const bool arm = cmp_le(ph_t - phi, K_ETA_PHI * alpha_test * gBd, phi);
+                bool ok = tiny;
+                if (!tiny) {
+                    ok = (th_t == th_t) && (ph_t == ph_t);
+                    if (ok && !cmp_le(th_t, theta_max, theta)) ok = false;
+                    if (ok) {
+                        if (ftype && theta <= theta_min) ok = arm;
+                        else {
+                            if (ph_t > phi) {
+                                double bas = 1.0; if (fabs(phi) > 10.0) bas = log10(fabs(phi));
+                                if (log10(ph_t - phi) > K_OBJ_MAX_INC + bas) ok = false;
+                            }
+                            if (ok) ok = cmp_le(th_t, (1.0 - K_GAMMA_THETA) * theta, theta) || cmp_le(ph_t - phi, -K_GAMMA_PHI * theta, phi);
                         }
-                        if (ok) ok = cmp_le(tht, (1.0 - K_GAMMA_THETA) * theta, theta) || cmp_le(pht - phi, -K_GAMMA_PHI * theta, phi);
                     }
+                    const bool mine = (k >= nfilt) || cmp_le(ph_t, f_phi, f_phi) || cmp_le(th_t, f_theta, f_theta);
+                    ok = warp_all(mine) && ok;
                 }
-                // filter: entry e lives in lane e
-                const bool mine = (k >= nfilt) || cmp_le(pht, f_phi, f_phi) || cmp_le(tht, f_theta, f_theta);
-                const bool fok = warp_all(mine);
-                return ok && fok;
-            };
-            StageTrig ttg;
-            double trd[4], tri[4], tdr[4];
-            if (tiny) { make_trial(alpha); accepted = true; }
-            int nsteps = 0;
-            while (!accepted && (alpha > alpha_min || nsteps == 0)) {
-                make_trial(alpha);
-                eval_defects(tx, ty, tp, tv, ta, td, ts, ttg, trd, tri, tdr);
-                const double th_t = theta_of(trd, tri, tdr);
-                const double ph_t = sigma * objective(tx, ty, tp, tv, ta, td) - mu * log_barrier(tv, ta, td, ts);
-                if (accept_test(alpha, th_t, ph_t)) { accepted = true; ftype_arm = is_ftype(alpha) && armijo(alpha, ph_t); break; }
-                // ---- second-order correction on the first trial
-                if (nsteps == 0 && theta <= th_t && K_MAX_SOC > 0) {
-                    double csoc[4] = {rdyn[0], rdyn[1], rdyn[2], rdyn[3]};
-                    double isoc[4] = {rinit[0], rinit[1], rinit[2], rinit[3]};
-                    double dsoc[2] = {dres[0], dres[1]};
-                    double th_old = 0.0, th_soc = th_t, a_soc = alpha;
-                    const StepState D0 = D;
-                    int cnt = 0;
-                    while (cnt < K_MAX_SOC && !accepted && (cnt == 0 || th_soc <= K_KAPPA_SOC * th_old)) {
-                        th_old = th_soc;
-                        for (int i = 0; i < 4; i++) { csoc[i] = a_soc * csoc[i] + trd[i]; isoc[i] = a_soc * isoc[i] + tri[i]; }
-                        for (int i = 0; i < 2; i++) dsoc[i] = a_soc * dsoc[i] + tdr[i];
-                        syncwarp();
-                        build_cond_pd(q, mu, dw, dsoc);
-                        if (isS) patch_record_rhs(q, csoc);
-                        syncwarp();
-                        (void)riccati_backward();
-                        riccati_forward(isoc);
-                        recover_duals(q, dsoc);
-                        a_soc = alpha_primal(tau);
-                        make_trial(a_soc);
-                        eval_defects(tx, ty, tp, tv, ta, td, ts, ttg, trd, tri, tdr);
-                        th_soc = theta_of(trd, tri, tdr);
-                        const double ph_s = sigma * objective(tx, ty, tp, tv, ta, td) - mu * log_barrier(tv, ta, td, ts);
-                        if (accept_test(alpha, th_soc, ph_s)) {
-                            accepted = true; ftype_arm = is_ftype(alpha) && armijo(alpha, ph_s);
-                            alpha = a_soc;
-                        } else cnt++;
+                if (!ok) {
+                    bool want_soc = false;
+                    if (phase == PH_TRIAL) {
+                        if (nsteps == 0 && theta <= th_t && K_MAX_SOC > 0) { want_soc = true; soc_cnt = 0; a_soc = alpha; }
+                    } else {
+                        soc_cnt++;
+                        want_soc = (soc_cnt < K_MAX_SOC) && (th_t <= K_KAPPA_SOC * th_soc_old);
                     }
-                    if (accepted) break;
-                    D = D0;  // back to the uncorrected direction for the backtracking steps
-                    // the record's right-hand side is restored on the next assembly
+                    if (want_soc) {
+                        // c_soc <- a_soc * c_soc + c(trial), accumulated in the record's right-hand-side fields
+                        th_soc_old = th_t;
+                        if (isS) {
+                            const int r = rec();
+                            for (int i = 0; i < 4; i++) sts(sm, r + SO(SD_R + i), a_soc * lds(sm, r + SO(SD_R + i)) + ev.rd[i]);
+                            sts(sm, r + SO(SD_DR), a_soc * lds(sm, r + SO(SD_DR)) + ev.dr[0]);
+                            sts(sm, r + SO(SD_DR + 1), a_soc * lds(sm, r + SO(SD_DR + 1)) + ev.dr[1]);
+                        }
+                        syncwarp();
+                        phase = PH_SOC; do_solve = true; req = 3; do_eval = true; eval_ftb = true;
+                        continue;
+                    }
+                    if (phase == PH_SOC) {
+                        // corrections exhausted: re-evaluate the current point, recompute the Newton direction, backtrack
+                        phase = PH_RESOLVE_EVAL; do_eval = true; ev_alpha = 0.0;
+                        D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0; D.drs[0] = D.drs[1] = 0.0;
+                        continue;
+                    }
+                    // plain backtracking
+                    double alpha_min = K_GAMMA_THETA;
+                    if (gBd < 0.0) {
+                        alpha_min = dmin_(K_GAMMA_THETA, K_GAMMA_PHI * theta / (-gBd));
+                        if (theta <= theta_min) alpha_min = dmin_(alpha_min, K_DELTA * Rft);
+                    }
+                    alpha_min *= K_ALPHA_MIN_FRAC;
+                    alpha *= 0.5; nsteps++;
+                    if (!(alpha > alpha_min)) { ret = -2; break; }  // Ipopt would enter the restoration phase
+                    ev_alpha = alpha; do_eval = true; phase = PH_TRIAL;
+                    continue;
                 }
-                alpha *= 0.5; nsteps++;
-            }
-            if (!accepted) { ret = -2; break; }  // Ipopt would enter the restoration phase
-
-            // ---- filter augmentation
-            if (!tiny && !ftype_arm) {
-                if (nfilt < 32) {
+                // ---------------- accepted ----------------
+                if (phase == PH_SOC) alpha = a_soc;
+                if (!tiny && !(ftype && arm) && nfilt < 32) {
                     if (k == nfilt) { f_phi = phi - K_GAMMA_PHI * theta; f_theta = (1.0 - K_GAMMA_THETA) * theta; }
                     nfilt++;
                 }
+                {
+                    // bound-multiplier steps from the accepted direction: dz = (mu -/+ z dx)/slack - z
+                    Recips q;
+                    recips(q);
+                    double dzvL = 0, dzvU = 0, dzaL = 0, dzaU = 0, dzdL = 0, dzdU = 0, drvL[2] = {0, 0}, drvU[2] = {0, 0};
+                    if (isS) { dzvL = (mu - L.zvL * D.dsv) * q.vL - L.zvL; dzvU = (mu + L.zvU * D.dsv) * q.vU - L.zvU; }
+                    if (isU) {
+                        dzaL = (mu - L.zaL * D.dua) * q.aL - L.zaL; dzaU = (mu + L.zaU * D.dua) * q.aU - L.zaU;
+                        dzdL = (mu - L.zdL * D.dud) * q.dL - L.zdL; dzdU = (mu + L.zdU * D.dud) * q.dU - L.zdU;
+                    }
+                    if (isR) {
+                        drvL[0] = (mu - L.rvL[0] * D.drs[0]) * q.r0L - L.rvL[0]; drvU[0] = (mu + L.rvU[0] * D.drs[0]) * q.r0U - L.rvU[0];
+                        drvL[1] = (mu - L.rvL[1] * D.drs[1]) * q.r1L - L.rvL[1]; drvU[1] = (mu + L.rvU[1] * D.drs[1]) * q.r1U - L.rvU[1];
+                    }
+                    double num = 0.0, den = 1.0;   // dual fraction-to-the-boundary: largest -dz/z by cross-multiplication
+                    auto lim = [&](double z, double dz) { if (dz < 0.0 && -dz * den > num * z) { num = -dz; den = z; } };
+                    lim(L.zvL, dzvL); lim(L.zvU, dzvU); lim(L.zaL, dzaL); lim(L.zaU, dzaU); lim(L.zdL, dzdL); lim(L.zdU, dzdU);
+                    lim(L.rvL[0], drvL[0]); lim(L.rvU[0], drvU[0]); lim(L.rvL[1], drvL[1]); lim(L.rvU[1], drvU[1]);
+                    const double az = dmin_(1.0, warp_min(num > 0.0 ? tau * den / num : 1.0));
+                    // primal, equality multipliers (primal step size), bound multipliers (dual step size)
+                    L.sx += alpha * D.dsx; L.sy += alpha * D.dsy; L.sp += alpha * D.dsp; L.sv += alpha * D.dsv;
+                    L.ua += alpha * D.dua; L.ud += alpha * D.dud; L.rs[0] += alpha * D.drs[0]; L.rs[1] += alpha * D.drs[1];
+                    L.yx += alpha * (D.nyx - L.yx); L.yy += alpha * (D.nyy - L.yy); L.yp += alpha * (D.nyp - L.yp); L.yv += alpha * (D.nyv - L.yv);
+                    L.ryd[0] += alpha * (D.nyd[0] - L.ryd[0]); L.ryd[1] += alpha * (D.nyd[1] - L.ryd[1]);
+                    auto upd = [&](double& z, double dz, double sl) {
+                        z += az * dz;
+                        const double pz = z * sl;   // kappa_sigma safeguard without a division in the common case
+                        if (pz > K_KAPPA_SIGMA * mu) z = K_KAPPA_SIGMA * mu / sl;
+                        else if (pz * K_KAPPA_SIGMA < mu) z = mu / (K_KAPPA_SIGMA * sl);
+                    };
+                    if (isS) { upd(L.zvL, dzvL, L.sv - c.vLo); upd(L.zvU, dzvU, c.vHi - L.sv); }
+                    if (isU) {
+                        upd(L.zaL, dzaL, L.ua - c.aLo); upd(L.zaU, dzaU, c.aHi - L.ua);
+                        upd(L.zdL, dzdL, L.ud - c.dLo); upd(L.zdU, dzdU, c.dHi - L.ud);
+                    }
+                    if (isR) {
+                        const double h0 = rHi(0), h1 = rHi(1);
+                        upd(L.rvL[0], drvL[0], L.rs[0] + h0); upd(L.rvU[0], drvU[0], h0 - L.rs[0]);
+                        upd(L.rvL[1], drvL[1], L.rs[1] + h1); upd(L.rvU[1], drvU[1], h1 - L.rs[1]);
+                    }
+                }
+                // the accepted trial evaluation (in ev) is the next iteration's current evaluation
+                cur_theta = ev.theta; cur_f = ev.f; cur_lb = ev.lb;
+                tiny_last = tiny;
+                iter++;
+                phase = PH_BEGIN;
             }
-            // ---- accept the trial point: duals
-            double az = 1.0;
-            {
-                // bound multiplier steps with the (possibly corrected) primal step
-                double dzvL = 0, dzvU = 0, dzaL = 0, dzaU = 0, dzdL = 0, dzdU = 0, drvL[2] = {0, 0}, drvU[2] = {0, 0};
-                if (isS) { dzvL = dzl(mu, L.zvL, L.sv - vLo, D.dsv); dzvU = dzu(mu, L.zvU, vHi - L.sv, D.dsv); }
-                if (isU) {
-                    dzaL = dzl(mu, L.zaL, L.ua - aLo, D.dua); dzaU = dzu(mu, L.zaU, aHi - L.ua, D.dua);
-                    dzdL = dzl(mu, L.zdL, L.ud - dLo, D.dud); dzdU = dzu(mu, L.zdU, dHi - L.ud, D.dud);
+            if (phase == PH_EVAL0) {
+                cur_theta = ev.theta; cur_f = ev.f; cur_lb = ev.lb;
+                phase = PH_LS; do_solve = true; req = 0;
+                continue;
+            }
+            if (phase == PH_LS) {
+                bool use = solve_ok;
+                if (solve_ok) {
+                    double ym = dmax_(dmax_(fabs(D.nyx), fabs(D.nyy)), dmax_(fabs(D.nyp), fabs(D.nyv)));
+                    ym = dmax_(ym, dmax_(fabs(D.nyd[0]), fabs(D.nyd[1])));
+                    ym = warp_max(isS ? ym : 0.0);
+                    use = (ym <= K_Y_INIT_MAX);
                 }
-                if (isR) for (int i = 0; i < 2; i++) {
-                    drvL[i] = dzl(mu, L.rvL[i], L.rs[i] - rLo[i], D.drs[i]); drvU[i] = dzu(mu, L.rvU[i], rHi[i] - L.rs[i], D.drs[i]);
+                if (use && isS) { L.yx = D.nyx; L.yy = D.nyy; L.yp = D.nyp; L.yv = D.nyv; L.ryd[0] = D.nyd[0]; L.ryd[1] = D.nyd[1]; }
+                phase = PH_BEGIN;
+            }
+            if (phase == PH_BEGIN) {
+                const Grad g = objective_gradient();
+                const double gx = g.x, gy = g.y, gp = g.p, gv = g.v, ga = g.a, gd = g.d;
+                const double A02 = isU ? -c.dt * L.sv * ev.sn : 0.0, A03 = isU ? c.dt * ev.cs : 0.0;
+                const double A12 = isU ? c.dt * L.sv * ev.cs : 0.0, A13 = isU ? c.dt * ev.sn : 0.0;
+                const double A23 = isU ? c.dt * ev.sb / c.Lb : 0.0;
+                const double b0 = A02 * ev.b1, b1v = A12 * ev.b1, b2v = isU ? c.dt * L.sv * ev.cb * ev.b1 / c.Lb : 0.0;
+                double di, cv, cm0, cmm, sumy, sumz;
+                {
+                    const double y1x = shfl_down(L.yx, 1), y1y = shfl_down(L.yy, 1), y1p = shfl_down(L.yp, 1), y1v = shfl_down(L.yv, 1);
+                    const double yd1_0 = shfl_down(L.ryd[0], 1), yd1_1 = shfl_down(L.ryd[1], 1);
+                    const double hn = isU ? 1.0 : 0.0;
+                    const double glx = gx + L.yx - hn * y1x;
+                    const double gly = gy + L.yy - hn * y1y;
+                    const double glp = gp + L.yp - hn * (A02 * y1x + A12 * y1y + y1p);
+                    const double glv = gv + L.yv - hn * (A03 * y1x + A13 * y1y + A23 * y1p + y1v) - L.zvL + L.zvU;
+                    const double nd0 = (k + 1 < N) ? yd1_0 : 0.0, nd1 = (k + 1 < N) ? yd1_1 : 0.0;
+                    const double gla = ga - hn * c.dt * y1v + (L.ryd[1] - nd1) - L.zaL + L.zaU;
+                    const double gld = gd - hn * (b0 * y1x + b1v * y1y + b2v * y1p) + (L.ryd[0] - nd0) - L.zdL + L.zdU;
+                    di = dmax_(dmax_(fabs(glx), fabs(gly)), dmax_(fabs(glp), fabs(glv)));
+                    di = dmax_(di, dmax_(fabs(gla), fabs(gld)));
+                    di = dmax_(di, dmax_(fabs(-L.ryd[0] - L.rvL[0] + L.rvU[0]), fabs(-L.ryd[1] - L.rvL[1] + L.rvU[1])));
+                    di = isS ? di : 0.0;
+                    cv = dmax_(dmax_(fabs(ev.rd[0]), fabs(ev.rd[1])), dmax_(fabs(ev.rd[2]), fabs(ev.rd[3])));
+                    cv = dmax_(cv, dmax_(fabs(ev.dr[0]), fabs(ev.dr[1])));
+                    sumy = isS ? fabs(L.yx) + fabs(L.yy) + fabs(L.yp) + fabs(L.yv) + fabs(L.ryd[0]) + fabs(L.ryd[1]) : 0.0;
+                    sumz = L.zvL + L.zvU + L.zaL + L.zaU + L.zdL + L.zdU + L.rvL[0] + L.rvL[1] + L.rvU[0] + L.rvU[1];
+                    for (int o = 16; o; o >>= 1) { sumy += shfl_xor(sumy, o); sumz += shfl_xor(sumz, o); }
                 }
-                auto lim = [&](double a, double z, double dz) { return (dz < 0.0) ? dmin_(a, -tau * z / dz) : a; };
-                az = lim(az, L.zvL, dzvL); az = lim(az, L.zvU, dzvU); az = lim(az, L.zaL, dzaL); az = lim(az, L.zaU, dzaU);
-                az = lim(az, L.zdL, dzdL); az = lim(az, L.zdU, dzdU);
-                az = lim(az, L.rvL[0], drvL[0]); az = lim(az, L.rvU[0], drvU[0]); az = lim(az, L.rvL[1], drvL[1]); az = lim(az, L.rvU[1], drvU[1]);
-                az = warp_min(az);
-                // primal
-                L.sx = tx; L.sy = ty; L.sp = tp; L.sv = tv; L.ua = ta; L.ud = td; L.rs[0] = ts[0]; L.rs[1] = ts[1];
-                // equality multipliers with the primal step size
-                L.yx += alpha * (D.nyx - L.yx); L.yy += alpha * (D.nyy - L.yy); L.yp += alpha * (D.nyp - L.yp); L.yv += alpha * (D.nyv - L.yv);
-                L.ryd[0] += alpha * (D.nyd[0] - L.ryd[0]); L.ryd[1] += alpha * (D.nyd[1] - L.ryd[1]);
-                auto upd = [&](double& z, double dz, double sl) {
-                    z += az * dz;
-                    z = dmax_(dmin_(z, K_KAPPA_SIGMA * mu / sl), mu / (K_KAPPA_SIGMA * sl));
+                const double sd = dmax_(K_S_MAX, (sumy + sumz) / (double)(my + nz)) / K_S_MAX;
+                const double sc = dmax_(K_S_MAX, sumz / (double)nz) / K_S_MAX;
+                // complementarity of this lane: max |slack * z - t| over its bound pairs
+                auto compl_local = [&](double t) {
+                    double m = 0.0;
+                    if (isS) { m = dmax_(m, fabs((L.sv - c.vLo) * L.zvL - t)); m = dmax_(m, fabs((c.vHi - L.sv) * L.zvU - t)); }
+                    if (isU) {
+                        m = dmax_(m, fabs((L.ua - c.aLo) * L.zaL - t)); m = dmax_(m, fabs((c.aHi - L.ua) * L.zaU - t));
+                        m = dmax_(m, fabs((L.ud - c.dLo) * L.zdL - t)); m = dmax_(m, fabs((c.dHi - L.ud) * L.zdU - t));
+                    }
+                    if (isR) for (int i = 0; i < 2; i++) {
+                        const double h = rHi(i);
+                        m = dmax_(m, fabs((L.rs[i] + h) * L.rvL[i] - t)); m = dmax_(m, fabs((h - L.rs[i]) * L.rvU[i] - t));
+                    }
+                    return m;
                 };
-                if (isS) { upd(L.zvL, dzvL, L.sv - vLo); upd(L.zvU, dzvU, vHi - L.sv); }
-                if (isU) {
-                    upd(L.zaL, dzaL, L.ua - aLo); upd(L.zaU, dzaU, aHi - L.ua);
-                    upd(L.zdL, dzdL, L.ud - dLo); upd(L.zdU, dzdU, dHi - L.ud);
+                cm0 = compl_local(0.0); cmm = compl_local(mu);
+                // E_0 and E_mu in one pass
+                const double dcv = dmax_(di / sd, cv);
+                double e0 = dmax_(dcv, cm0 / sc), em = dmax_(dcv, cmm / sc);
+                for (int o = 16; o; o >>= 1) {
+                    const double t0 = shfl_xor(e0, o), t1 = shfl_xor(em, o);
+                    e0 = (t0 > e0 || t0 != t0) ? t0 : e0; em = (t1 > em || t1 != t1) ? t1 : em;
                 }
-                if (isR) for (int i = 0; i < 2; i++) { upd(L.rvL[i], drvL[i], L.rs[i] - rLo[i]); upd(L.rvU[i], drvU[i], rHi[i] - L.rs[i]); }
+                // ---- convergence (OptimalityErrorConvergenceCheck)
+                if (e0 <= dmax_(K_ACCEPT_TOL, c.tol)) {   // the unscaled checks need three more reductions: only near the end
+                    const double du = warp_max(di) / sigma, cvm = warp_max(cv), mc = warp_max(cm0) / sigma;
+                    if (e0 <= c.tol && du <= 1.0 && cvm <= 1e-4 && mc <= 1e-4) { ret = 0; break; }
+                    if (e0 <= K_ACCEPT_TOL && du <= 1e10 && cvm <= 1e-2 && mc <= 1e-2) { if (++accept_count >= K_ACCEPT_ITER) { ret = 1; break; } }
+                    else accept_count = 0;
+                } else accept_count = 0;
+                if (iter >= c.max_iter) { ret = -1; break; }
+                {
+                    const double xm = dmax_(dmax_(fabs(L.sx), fabs(L.sy)), dmax_(fabs(L.sp), fabs(L.sv)));
+                    if (!warp_all(!isS || xm <= 1e20)) { ret = -5; break; }
+                }
+                // ---- monotone barrier update
+                for (;;) {
+                    if (!(em <= K_KAPPA_EPS * mu) && !tiny_last) break;
+                    const double nm = dmax_(c.mu_min, dmin_(K_KAPPA_MU * mu, mu * sqrt(mu)));
+                    if (nm >= mu) { if (tiny_last) ret = -3; break; }
+                    mu = nm; tau = dmax_(K_TAU_MIN, 1.0 - mu);
+                    nfilt = 0;
+                    if (tiny_last) { tiny_last = false; break; }
+                    em = warp_max(dmax_(dcv, compl_local(mu) / sc));
+                }
+                if (ret == -3) break;
+                dw = 0.0;
+                phase = PH_PD; do_solve = true; req = 1;
+                continue;
             }
-            tiny_last = tiny;
-            iter++;
-            syncwarp();
+            if (phase == PH_RESOLVE_EVAL) {
+                phase = PH_RESOLVE; do_solve = true; req = 1;
+                continue;
+            }
+            if (phase == PH_PD || phase == PH_RESOLVE) {
+                if (!solve_ok) {
+                    // PDPerturbationHandler::PerturbForWrongInertia
+                    if (dw == 0.0) dw = (dw_last == 0.0) ? K_DW_INIT : dmax_(K_DW_MIN, dw_last * K_DW_DEC);
+                    else dw = (dw_last == 0.0 || 1e5 * dw_last < dw) ? K_DW_INC_FIRST * dw : K_DW_INC * dw;
+                    if (dw > K_DW_MAX) { ret = -4; break; }
+                    do_solve = true; req = 2;
+                    continue;
+                }
+                if (phase == PH_RESOLVE) {
+                    alpha = alpha_max * 0.5; nsteps = 1;
+                    double alpha_min = K_GAMMA_THETA;
+                    if (gBd < 0.0) {
+                        alpha_min = dmin_(K_GAMMA_THETA, K_GAMMA_PHI * cur_theta / (-gBd));
+                        if (cur_theta <= theta_min) alpha_min = dmin_(alpha_min, K_DELTA * Rft);
+                    }
+                    if (!(alpha > alpha_min * K_ALPHA_MIN_FRAC)) { ret = -2; break; }
+                    ev_alpha = alpha; do_eval = true; phase = PH_TRIAL;
+                    continue;
+                }
+                if (dw > 0.0) dw_last = dw;
+                // ---- line-search quantities at the current point
+                const double theta = cur_theta;
+                phi = sigma * cur_f - mu * cur_lb;
+                {
+                    // grad(phi)'d from the condensed gradient in the record:
+                    //   sum g~ dx + sum_rows [ br rdr - SrW rdr (drs - rdr) ]
+                    const int r = rec();
+                    double t = 0.0;
+                    bool tl = true;  // all |dx_i| < 10 eps (1 + |x_i|)
+                    const double tt = 10.0 * K_EPS;
+                    if (isS) {
+                        const d2 g01 = lds2(sm, r + SO(SD_GX)), g23 = lds2(sm, r + SO(SD_GX + 2)), g45 = lds2(sm, r + SO(SD_GX + 4));
+                        t = g01.x * D.dsx + g01.y * D.dsy + g23.x * D.dsp + g23.y * D.dsv + g45.x * D.dua + g45.y * D.dud;
+                        tl = fabs(D.dsx) < tt * (1.0 + fabs(L.sx)) && fabs(D.dsy) < tt * (1.0 + fabs(L.sy)) &&
+                             fabs(D.dsp) < tt * (1.0 + fabs(L.sp)) && fabs(D.dsv) < tt * (1.0 + fabs(L.sv)) &&
+                             fabs(D.dua) < tt * (1.0 + fabs(L.ua)) && fabs(D.dud) < tt * (1.0 + fabs(L.ud)) &&
+                             fabs(D.drs[0]) < tt * (1.0 + fabs(L.rs[0])) && fabs(D.drs[1]) < tt * (1.0 + fabs(L.rs[1]));
+                    }
+                    if (isR) {
+                        const d2 srw = lds2(sm, r + SO(SD_SRW)), brr = lds2(sm, r + SO(SD_BR)), drr = lds2(sm, r + SO(SD_DR));
+                        t += brr.x * drr.x - srw.x * drr.x * (D.drs[0] - drr.x);
+                        t += brr.y * drr.y - srw.y * drr.y * (D.drs[1] - drr.y);
+                    }
+                    gBd = warp_sum(t);
+                    tiny = warp_all(tl) && (theta < 1e-4);
+                }
+                if (theta_max < 0.0) { theta_max = 1e4 * dmax_(1.0, theta); theta_min = 1e-4 * dmax_(1.0, theta); }
+                // switching-condition ratio theta^s_theta / (-gBd)^s_phi: a threshold test, single precision suffices
+                Rft = (gBd < 0.0) ? (double)fast_exp2((float)K_S_THETA * fast_log2((float)theta) - (float)K_S_PHI * fast_log2((float)(-gBd))) : 0.0;
+                alpha_max = alpha_primal(tau);
+                alpha = alpha_max; nsteps = 0;
+                ev_alpha = alpha; do_eval = true; phase = PH_TRIAL;
+                continue;
+            }
         }
         res.iters = iter;
-        res.status = (ret == 0 || ret == 1) ? 0 : (ret == -1 ? 3 : (ret == -5 ? 2 : 4));
+        res.status = (ret == 0 || ret == 1) ? 0 : (ret == 2 ? 1 : (ret == -1 ? 3 : (ret == -5 ? 2 : 4)));
         // honor_original_bounds
-        if (isS) L.sv = dmin_(dmax_(L.sv, c.vmin), c.vmax);
-        if (isU) { L.ua = dmin_(dmax_(L.ua, -c.amax), c.amax); L.ud = dmin_(dmax_(L.ud, -c.smax), c.smax); }
-        res.cost = objective(L.sx, L.sy, L.sp, L.sv, L.ua, L.ud);
+        if (feasible) {
+            if (isS) L.sv = dmin_(dmax_(L.sv, c.vmin), c.vmax);
+            if (isU) { L.ua = dmin_(dmax_(L.ua, -c.amax), c.amax); L.ud = dmin_(dmax_(L.ud, -c.smax), c.smax); }
+        }
+        {   // unscaled objective at the returned point
+            const double pa = shfl_up(L.ua, 1), pd = shfl_up(L.ud, 1);
+            const double ex = L.sx - xr, ey = L.sy - yr, ep = L.sp - pr, evv = L.sv - cst(6);
+            double f = wx() * ex * ex + wy() * ey * ey + wp() * ep * ep + wv() * evv * evv;
+            if (isU) {
+                f += c.w[6] * L.ua * L.ua + c.w[7] * L.ud * L.ud;
+                if (k >= 1) { const double da = L.ua - pa, dd = L.ud - pd; f += c.w[4] * da * da + c.w[5] * dd * dd; }
+            }
+            res.cost = warp_sum(f);
+        }
         return res;
     }
 };
@@ -996,23 +1026,23 @@ struct BatchPtrs {
     double* traj;          // [B][6N+4] or null
 };
 
-MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, double* smem) {
+MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t smem) {
     WarpSolver S(cfg, smem);
     const int k = S.k, N = cfg.N;
     const long nr = 3L * (N + 1), nt = 6L * N + 4;
-    S.init_roles();
-    // ---- coalesced loads: lane k takes stage k's reference sample; lanes 0..3 the state
+    // ---- coalesced loads: lane k takes stage k's reference sample; lanes 0..6 the problem constants
     const double* rf = io.ref + nr * b;
     S.xr = (k <= N) ? rf[k] : 0.0;
     S.yr = (k <= N) ? rf[(N + 1) + k] : 0.0;
     S.pr = (k <= N) ? rf[2 * (N + 1) + k] : 0.0;
     {
-        const double sv = (k < 4) ? io.state[4 * b + k] : 0.0;
-        for (int i = 0; i < 4; i++) S.st0[i] = shfl(sv, i);
-        const double uv = (k < 2) ? io.u_prev[2 * b + k] : 0.0;
-        S.uprev[0] = shfl(uv, 0); S.uprev[1] = shfl(uv, 1);
+        double cv = 0.0;
+        if (k < 4) cv = io.state[4 * b + k];
+        else if (k < 6) cv = io.u_prev[2 * b + (k - 4)];
+        else if (k == 6) cv = io.v_des ? io.v_des[b] : 0.0;
+        if (k < 8) sts(smem, SO(W_CONST + k), cv);
+        syncwarp();
     }
-    S.vdes = io.v_des ? io.v_des[b] : 0.0;
     // ---- start point
     S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;
     if (io.warm) {
@@ -1020,7 +1050,7 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, double*
         if (k <= N) { S.L.sx = w[k]; S.L.sy = w[(N + 1) + k]; S.L.sv = w[2 * (N + 1) + k]; S.L.sp = w[3 * (N + 1) + k]; }
         if (k < N) { S.L.ud = w[4 * (N + 1) + k]; S.L.ua = w[4 * (N + 1) + N + k]; }
     }
-    WarpSolver::Result r = S.solve();
+    const Result r = S.solve();
     // ---- results
     const double a0 = shfl(S.L.ua, 0), d0 = shfl(S.L.ud, 0);
     if (k == 0) {
@@ -1036,6 +1066,7 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, double*
         if (k <= N) { t[k] = S.L.sx; t[(N + 1) + k] = S.L.sy; t[2 * (N + 1) + k] = S.L.sv; t[3 * (N + 1) + k] = S.L.sp; }
         if (k < N) { t[4 * (N + 1) + k] = S.L.ud; t[4 * (N + 1) + N + k] = S.L.ua; }
     }
+    syncwarp();
 }
 
 }  // namespace mpcb200

@@ -22,9 +22,31 @@ MPC_DEV int shfl(int v, int src) { return __shfl_sync(MPC_FULL, v, src); }
 MPC_DEV double shfl_down(double v, int d) { return __shfl_down_sync(MPC_FULL, v, d); }
 MPC_DEV double shfl_up(double v, int d) { return __shfl_up_sync(MPC_FULL, v, d); }
 MPC_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(MPC_FULL, v, m); }
-MPC_DEV void syncwarp() { __syncwarp(); }
+MPC_DEV void syncwarp() { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory"); }
 MPC_DEV bool warp_all(bool p) { return __all_sync(MPC_FULL, p); }
 MPC_DEV bool warp_any(bool p) { return __any_sync(MPC_FULL, p); }
 MPC_DEV void mpc_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+MPC_DEV float fast_log2(float x) { return __log2f(x); }
+MPC_DEV float fast_exp2(float x) { return exp2f(x); }
+
+// Shared memory through 32-bit shared-window addresses and explicit ld/st.shared: the base is an
+// opaque register value, so the compiler cannot rematerialise generic->shared conversions or lane
+// role arithmetic inside the Riccati loops.  Offsets are in BYTES on the device.
+typedef unsigned smem_t;
+#define SO(x) ((x) * 8)
+MPC_DEV smem_t smem_base(double* p) { return (smem_t)__cvta_generic_to_shared(p); }
+MPC_DEV double lds(smem_t b, int off) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(b + off) : "memory");
+    return v;
+}
+struct d2 { double x, y; };
+MPC_DEV d2 lds2(smem_t b, int off) {
+    d2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(b + off) : "memory");
+    return v;
+}
+MPC_DEV void sts(smem_t b, int off, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(b + off), "d"(v) : "memory"); }
+MPC_DEV int launder(int v) { int r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 }  // namespace mpcb200
 #endif

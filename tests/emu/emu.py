@@ -15,7 +15,11 @@ class KCfg(C.Structure):
     _fields_ = [("N", C.c_int), ("max_iter", C.c_int), ("start_mode", C.c_int), ("pad_", C.c_int),
                 ("dt", C.c_double), ("dtc", C.c_double), ("La", C.c_double), ("Lb", C.c_double),
                 ("vmin", C.c_double), ("vmax", C.c_double), ("amax", C.c_double), ("smax", C.c_double),
-                ("admax", C.c_double), ("sdmax", C.c_double), ("tol", C.c_double), ("w", C.c_double * 8)]
+                ("admax", C.c_double), ("sdmax", C.c_double), ("tol", C.c_double), ("w", C.c_double * 8),
+                # derived fields, filled by kcfg_finalize() inside the driver
+                ("vLo", C.c_double), ("vHi", C.c_double), ("aLo", C.c_double), ("aHi", C.c_double),
+                ("dLo", C.c_double), ("dHi", C.c_double), ("rHiFirst", C.c_double * 2), ("rHiLater", C.c_double * 2),
+                ("rfrac", C.c_double), ("mu_min", C.c_double)]
 
 
 def build():

@@ -46,6 +46,7 @@ using namespace mpcb200;
 struct Job { const KCfg* cfg; const BatchPtrs* io; long b; double* smem; };
 static void lane_main(int, void* a) {
     Job* j = (Job*)a;
+    WarpSolver::init_work(j->smem);
     solve_problem(*j->cfg, *j->io, j->b, j->smem);
 }
 
@@ -53,9 +54,13 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
                                const double* u_prev, double* warm, double* u0, double* cost, int* status, int* iters,
                                double* traj) {
     BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj};
-    std::vector<double> smem(4096, 0.0);
+    KCfg kc = *cfg;
+    kcfg_finalize(kc);
+    std::vector<double> smem_raw(4096 + 2, 0.0);
+    double* smem = smem_raw.data();
+    if (((size_t)smem) & 15) smem++;   // 16-byte alignment like the device's shared memory
     for (long b = 0; b < B; b++) {
-        Job j{cfg, &io, b, smem.data()};
+        Job j{&kc, &io, b, smem};
         emu::run_warp(lane_main, &j);
     }
     return 0;

@@ -88,4 +88,15 @@ MPC_DEV bool warp_any(bool p) {
     int r = 0; for (int i = 0; i < 32; i++) r |= w->islot[b][i]; return r != 0;
 }
 MPC_DEV void mpc_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+MPC_DEV float fast_log2(float x) { return log2f(x); }
+MPC_DEV float fast_exp2(float x) { return exp2f(x); }
+// shared memory: a plain double array, offsets in doubles
+typedef double* smem_t;
+#define SO(x) (x)
+MPC_DEV smem_t smem_base(double* p) { return p; }
+MPC_DEV double lds(smem_t b, int off) { return b[off]; }
+struct d2 { double x, y; };
+MPC_DEV d2 lds2(smem_t b, int off) { d2 r; r.x = b[off]; r.y = b[off + 1]; return r; }
+MPC_DEV void sts(smem_t b, int off, double v) { b[off] = v; }
+MPC_DEV int launder(int v) { return v; }
 }  // namespace mpcb200
