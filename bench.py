@@ -17,7 +17,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -41,42 +40,50 @@ def parse():
     return ap.parse_args()
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler(object):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md): one
+    `nvidia-smi -lms 100` child for the whole region, parsed when it is stopped."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        threading.Thread.__init__(self, daemon=True)
         self.index = index
-        self.samples = []
-        self._halt = threading.Event()
+        self.proc = None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.samples.append(f)
-            except Exception:
-                pass
-            self._halt.wait(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=3)
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        n = 0
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            n += 1
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                pass
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": n}
 
 
 def cpu_baseline(N, sample, threads, start_b0=0):
@@ -131,7 +138,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from mkz_mpc_path_follower_b200 import capi, workload
+    from mkz_mpc_path_follower_b200 import capi, sharding, workload
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -159,19 +166,13 @@ def main():
     d_cost = torch.empty(B, dtype=torch.float64, device=dev)
     d_status = torch.empty(B, dtype=torch.int32, device=dev)
     d_iters = torch.empty(B, dtype=torch.int32, device=dev)
-    # 32 B/problem record for the all-gather: acc, df, cost (f64) + status, iters (i32)
-    d_rec = torch.empty((B, 4), dtype=torch.float64, device=dev)
-    d_all = torch.empty((world * B, 4), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step():
         flush.zero_()  # L2 flush between timed iterations (inputs are 36 MB < L2)
         solver.solve_batch_device(B, d_state, d_ref, d_uprev, d_u0, v_des=d_vdes, cost=d_cost, status=d_status, iters=d_iters)
-        if world > 1:
-            d_rec[:, 0:2] = d_u0
-            d_rec[:, 2] = d_cost
-            d_rec[:, 3] = torch.stack((d_status, d_iters), dim=1).view(torch.float64).squeeze(1)
-            dist.all_gather_into_tensor(d_all, d_rec)
+        if world > 1:   # the one exchange step: all-gather of the 32 B/problem result record
+            sharding.all_gather_records(sharding.pack_records(d_u0, d_cost, d_status, d_iters))
 
     def barrier():
         if world > 1:
@@ -194,11 +195,8 @@ def main():
         e0.record()
         solver.solve_batch_device(B, d_state, d_ref, d_uprev, d_u0, v_des=d_vdes, cost=d_cost, status=d_status, iters=d_iters)
         e1.record()
-        if world > 1:
-            d_rec[:, 0:2] = d_u0
-            d_rec[:, 2] = d_cost
-            d_rec[:, 3] = torch.stack((d_status, d_iters), dim=1).view(torch.float64).squeeze(1)
-            dist.all_gather_into_tensor(d_all, d_rec)
+        if world > 1:   # the one exchange step: all-gather of the 32 B/problem result record
+            sharding.all_gather_records(sharding.pack_records(d_u0, d_cost, d_status, d_iters))
         e1.synchronize()
         kern_ms.append(e0.elapsed_time(e1))
     t1.record()

@@ -199,3 +199,26 @@ def test_julia_module_mirror(capi, oracle):
         assert abs(res[0][0] - x) < 1e-7 and abs(res[2][0] - v) < 1e-7   # x_mpc[1], v_mpc[1]: order x,y,v,psi
     with pytest.raises(TypeError):
         kmpc.update_reference(np.zeros(3), np.zeros(9), np.zeros(9), 1.0)
+
+
+def test_closed_loop_reference_workload(capi, oracle):
+    """BASELINE.json configs[0]: the launch file's closed-loop lane keep (path3, X0=0, Y0=3, Psi0=-1.5,
+    launch/sim_path_follow.launch:13,23-25), N=8, time-mode references, warm-started; first 12 s against
+    the oracle's closed loop, plus path1 from its own start."""
+    from mkz_mpc_path_follower_b200 import closed_loop
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    T = 120
+    for pid, pose in ((3, (0.0, 3.0, -1.5)), (1, None)):
+        g = GPSRefTrajectory(mat_filename=pid)
+        if pose is None:
+            pose = (g.trajectory[0, 4] + 0.5, g.trajectory[0, 5] - 0.5, g.trajectory[0, 3] + 0.05)
+        out = closed_loop.run([pid], [pose], T, N=8)
+        path, keep = oracle.make_path(g.trajectory)
+        olog = oracle.closed_loop(oracle.default_cfg(8), path, pose, T, track_using_time=True, target_vel=1.0, warm_start=True)
+        glog = out["log"][:, 0, :]
+        assert np.array_equal(glog[:, 6], olog[:, 6])                      # same status every step
+        assert np.abs(glog[:, 4:6] - olog[:, 4:6]).max() <= 1e-5           # same published commands
+        assert np.abs(glog[:, 0:4] - olog[:, 0:4]).max() <= 1e-4           # same closed-loop trajectory
+        assert (glog[:, 6] == 0).mean() > 0.95
+        err = closed_loop.path_errors(out["log"][20:], g.trajectory)
+        assert err.max() < 1.5                                             # it follows the path

@@ -1,0 +1,57 @@
+"""N > 1 path on the CPU: two gloo ranks each take their contiguous slice of one synthetic batch,
+"solve" it (with the oracle standing in for the GPU, which is absent here), all-gather the 32-byte
+records and must reproduce the single-rank result bit for bit, in problem order."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, total, N, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from mkz_mpc_path_follower_b200 import sharding, workload
+    from oracle import oracle as O
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.shard_range(total, world, rank)
+    b = workload.make_batch(hi - lo, N, b0=lo)
+    r = O.solve_batch(O.default_cfg(N), b["state"], b["ref"], b["v_des"], b["u_prev"])
+    rec = sharding.pack_records(torch.from_numpy(r["u0"]), torch.from_numpy(r["cost"]),
+                                torch.from_numpy(r["status"]), torch.from_numpy(r["iters"]))
+    sizes = [sharding.shard_range(total, world, q)[1] - sharding.shard_range(total, world, q)[0] for q in range(world)]
+    allrec = sharding.all_gather_records(rec, sizes)
+    u0, cost, status, iters = sharding.unpack_records(allrec)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), u0=u0.numpy(), cost=cost.numpy(), status=status.numpy(), iters=iters.numpy())
+    dist.destroy_process_group()
+
+
+def test_shard_ranges():
+    from mkz_mpc_path_follower_b200 import sharding
+    for total, world in ((65536, 8), (10, 3), (7, 8), (0, 2)):
+        cuts = [sharding.shard_range(total, world, r) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == total
+        assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+        sz = [b - a for a, b in cuts]
+        assert max(sz) - min(sz) <= 1
+
+
+@pytest.mark.parametrize("total", [24, 25])   # even and ragged split
+def test_two_rank_gather_equals_single_rank(tmp_path, total):
+    import torch.multiprocessing as mp
+    from mkz_mpc_path_follower_b200 import workload
+    from oracle import oracle as O
+    N, world = 8, 2
+    port = 29500 + (os.getpid() % 2000) + total
+    mp.spawn(_worker, args=(world, port, total, N, str(tmp_path)), nprocs=world, join=True)
+    b = workload.make_batch(total, N)
+    ref = O.solve_batch(O.default_cfg(N), b["state"], b["ref"], b["v_des"], b["u_prev"])
+    for r in range(world):
+        g = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        assert np.array_equal(g["u0"], ref["u0"]) and np.array_equal(g["cost"], ref["cost"])
+        assert np.array_equal(g["status"], ref["status"]) and np.array_equal(g["iters"], ref["iters"])
