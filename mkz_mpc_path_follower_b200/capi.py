@@ -151,6 +151,28 @@ class Solver(object):
         self._check(lib().mpcb200_solve_batch(self._h, B, _ptr(state), _ptr(ref), _ptr(v_des), _ptr(u_prev), _ptr(warm),
                                               _ptr(u0), _ptr(cost), _ptr(status), _ptr(iters), _ptr(traj), DEVICE))
 
+    def set_path(self, path_id, traj_table):
+        """traj_table: the (n,7) table of GPSRefTrajectory.trajectory (ref_gps_traj.py:106); path_id 0..2."""
+        cols = [np.ascontiguousarray(traj_table[:, i], dtype=np.float64) for i in (0, 4, 5, 3, 6)]
+        dp = C.POINTER(C.c_double)
+        self._check(lib().mpcb200_set_path(self._h, int(path_id), int(traj_table.shape[0]), *[c.ctypes.data_as(dp) for c in cols]))
+
+    def rollout(self, pose0, path_of, T, track_using_time=True, target_vel=1.0, want_log=True):
+        """Closed-loop Monte-Carlo rollout on the device (mpcb200_rollout).  pose0 (B,3); path_of (B,) in 0..2
+        (ids given to set_path).  Returns log (T,B,8) = x,y,psi,v,acc_cmd,df_cmd,status,iters and final (B,8)."""
+        pose0 = np.ascontiguousarray(np.atleast_2d(pose0), dtype=np.float64)
+        B = pose0.shape[0]
+        path_of = np.ascontiguousarray(path_of, dtype=np.int32)
+        if pose0.shape != (B, 3) or path_of.shape != (B,):
+            raise ValueError("rollout: pose0 must be (B,3) and path_of (B,)")
+        log = np.empty((T, B, 8)) if want_log else None
+        final = np.empty((B, 8))
+        dp = C.POINTER(C.c_double)
+        self._check(lib().mpcb200_rollout(self._h, B, int(T), pose0.ctypes.data_as(dp), path_of.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          int(bool(track_using_time)), float(target_vel),
+                                          None if log is None else log.ctypes.data_as(dp), final.ctypes.data_as(dp)))
+        return {"log": log, "final_state": final}
+
     def stats(self):
         s = Stats()
         self._check(lib().mpcb200_get_stats(self._h, C.byref(s)))

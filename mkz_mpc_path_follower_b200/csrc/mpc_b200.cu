@@ -40,6 +40,22 @@ mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned
     }
 }
 
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MPC_MIN_BLOCKS)
+mpc_rollout_kernel(const KCfg cfg, const RolloutArgs args, unsigned long long* counter) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5;
+    const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_warp(cfg.N));
+    WarpSolver::init_work(smem);
+    for (;;) {
+        unsigned long long b = 0;
+        if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned long long)args.B) break;
+        rollout_vehicle(cfg, args, (long)b, smem);
+        __syncwarp();
+    }
+}
+
 // FP64 FMA throughput probe: 8 independent chains per thread
 __global__ void fp64_peak_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -70,6 +86,9 @@ struct mpcb200_handle {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long* d_counter = nullptr;
     DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
+    DevBuf d_path[3], d_pose, d_pathof, d_log, d_final;
+    int path_n[3] = {0, 0, 0};
+    int rollout_blocks_per_sm = 0;
     mpcb200_stats stats;
     char err[512];
 };
@@ -185,6 +204,10 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
     TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
     if (h->blocks_per_sm < 1) h->blocks_per_sm = 1;
+    TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, mpc_rollout_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
+    if (h->rollout_blocks_per_sm < 1) h->rollout_blocks_per_sm = 1;
     if (const char* e = getenv("MPCB200_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v; }  /* tuning aid */
 #undef TRY_OR_FREE
     *out = h;
@@ -194,7 +217,8 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
 int mpcb200_destroy(mpcb200_handle* h) {
     if (!h) return MPCB200_EINVAL;
     cudaSetDevice(h->device);
-    DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj};
+    DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj,
+                      &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -286,12 +310,70 @@ int mpcb200_solve_batch(mpcb200_handle* h, int64_t B, const double* state, const
     return MPCB200_OK;
 }
 
-int mpcb200_set_path(mpcb200_handle* h, int32_t, int32_t, const double*, const double*, const double*, const double*, const double*) {
-    return fail(h, MPCB200_EINVAL, "mpcb200_set_path: on-device reference generation is not built yet");
+int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n, const double* t, const double* X, const double* Y,
+                     const double* psi, const double* s) {
+    if (!h) return MPCB200_EINVAL;
+    if (path_id < 0 || path_id > 2) return fail(h, MPCB200_EINVAL, "mpcb200_set_path: path_id %d outside [0,2]", path_id);
+    if (n < 2 || !t || !X || !Y || !psi || !s) return fail(h, MPCB200_EINVAL, "mpcb200_set_path: need n >= 2 samples and five columns");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = ensure(h, h->d_path[path_id], (size_t)5 * n * sizeof(double));
+    if (rc) return rc;
+    const double* cols[5] = {t, X, Y, psi, s};
+    for (int i = 0; i < 5; i++)
+        CUDA_TRY(h, cudaMemcpyAsync((double*)h->d_path[path_id].p + (size_t)i * n, cols[i], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->path_n[path_id] = n;
+    return MPCB200_OK;
 }
 
-int mpcb200_rollout(mpcb200_handle* h, int64_t, int32_t, const double*, const int32_t*, int32_t, double, double*, double*) {
-    return fail(h, MPCB200_EINVAL, "mpcb200_rollout: closed-loop rollout is not built yet");
+int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T, const double* pose0, const int32_t* path_of, int32_t track_using_time,
+                    double target_vel, double* log, double* final_state) {
+    if (!h) return MPCB200_EINVAL;
+    if (B < 0 || T < 0) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: B=%lld T=%d", (long long)B, T);
+    memset(&h->stats, 0, sizeof(h->stats));
+    if (B == 0 || T == 0) return MPCB200_OK;
+    if (!pose0 || !path_of) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: pose0 and path_of are required");
+    for (int64_t b = 0; b < B; b++)
+        if (path_of[b] < 0 || path_of[b] > 2 || h->path_n[path_of[b]] == 0)
+            return fail(h, MPCB200_EINVAL, "mpcb200_rollout: vehicle %lld uses path %d, which was not set with mpcb200_set_path", (long long)b, path_of[b]);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    const size_t bl = (size_t)T * B * 8 * sizeof(double), bf = (size_t)B * 8 * sizeof(double);
+    if ((rc = ensure(h, h->d_pose, (size_t)B * 3 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->d_pathof, (size_t)B * sizeof(int32_t)))) return rc;
+    if (log && (rc = ensure(h, h->d_log, bl))) return rc;
+    if (final_state && (rc = ensure(h, h->d_final, bf))) return rc;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pose.p, pose0, (size_t)B * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pathof.p, path_of, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += (size_t)B * (3 * sizeof(double) + sizeof(int32_t));
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pose0 = (const double*)h->d_pose.p; a.path_of = (const int*)h->d_pathof.p;
+    for (int i = 0; i < 3; i++) {
+        const double* base = (const double*)h->d_path[i].p;
+        const int n = h->path_n[i];
+        a.paths[i].n = n;
+        if (n) { a.paths[i].t = base; a.paths[i].X = base + n; a.paths[i].Y = base + 2 * (size_t)n; a.paths[i].psi = base + 3 * (size_t)n; a.paths[i].s = base + 4 * (size_t)n; }
+    }
+    a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel;
+    a.log = log ? (double*)h->d_log.p : nullptr; a.final_state = final_state ? (double*)h->d_final.p : nullptr; a.B = (long)B;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), s));
+    long long blocks_needed = (B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    long long max_blocks = (long long)h->num_sms * h->rollout_blocks_per_sm;
+    int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    mpc_rollout_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, s>>>(make_kcfg(h), a, h->d_counter);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    h->stats.kernel_launches += 1;
+    if (log) { CUDA_TRY(h, cudaMemcpyAsync(log, h->d_log.p, bl, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bl; }
+    if (final_state) { CUDA_TRY(h, cudaMemcpyAsync(final_state, h->d_final.p, bf, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bf; }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return MPCB200_OK;
 }
 
 int mpcb200_get_stats(mpcb200_handle* h, mpcb200_stats* out) {

@@ -1069,4 +1069,139 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t 
     syncwarp();
 }
 
+
+// ======================================================================================
+// Closed-loop rollout: one warp = one vehicle for T control steps, everything on the device.
+//   plant              scripts/vehicle_simulator.py:58-112  (10 publishes x 10 Euler sub-steps per control period)
+//   reference          scripts/gps_utils/ref_gps_traj.py:131-218 (nearest sample, np.interp, heading unwrap, stop_cmd)
+//   control step       scripts/mpc_cmd_pub.jl:86-157 (warm-started solve, command fed back, stop latch)
+// ======================================================================================
+struct PathTable { const double *t, *X, *Y, *psi, *s; int n; };   // columns 0,4,5,3,6 of ref_gps_traj.py:106
+struct RolloutArgs {
+    const double* pose0;    // [B][3] X0, Y0, Psi0
+    const int* path_of;     // [B] index into paths[]
+    PathTable paths[3];
+    int T, track_using_time;
+    double target_vel;
+    double* log;            // [T][B][8] or null
+    double* final_state;    // [B][8] or null
+    long B;
+};
+
+MPC_DEV double py_mod(double a, double m) { double r = fmod(a, m); if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m; return r; }
+
+// vehicle_simulator.py:58-112, one 100 Hz publish period; st = X,Y,psi,vx,vy,wz,acc,df (every lane computes the same)
+MPC_DEV void plant_step(double* st, double acc_des, double df_des) {
+    const double lf = 1.152, lr = 1.693, m = 1840.0, Iz = 3477.0, Caf = 4.0703e4, Car = 6.4495e4;
+    const double deltaT = 0.01 / 10.0, PI = 3.141592653589793;
+    for (int i = 0; i < 10; i++) {
+        const double X = st[0], Y = st[1], psi = st[2], vx = st[3], vy = st[4], wz = st[5], acc = st[6], df = st[7];
+        double af = 0.0, ar = 0.0;
+        if (fabs(vx) > 1e-6) { af = df - atan2(vy + lf * wz, vx); ar = -atan2(vy - lf * wz, vx); }   // :77 uses lf (sic)
+        const double Fyf = Caf * af, Fyr = Car * ar;
+        double sdf, cdf, sps, cps;
+        mpc_sincos(df, &sdf, &cdf);
+        mpc_sincos(psi, &sps, &cps);
+        double vx_n = vx + deltaT * (acc - 1 / m * Fyf * sdf + wz * vy);
+        if (vx_n < 0.0) vx_n = 0.0;
+        double vy_n = 0.0, wz_n = 0.0;
+        if (vx_n > 1e-6) {
+            vy_n = vy + deltaT * (1.0 / m * (Fyf * cdf + Fyr) - wz * vx);
+            wz_n = wz + deltaT * (1.0 / Iz * (lf * Fyf * cdf - lr * Fyr));
+        }
+        const double psi_n = psi + deltaT * wz;
+        st[0] = X + deltaT * (vx * cps - vy * sps);
+        st[1] = Y + deltaT * (vx * sps + vy * cps);
+        st[2] = py_mod(psi_n + PI, 2.0 * PI) - PI;
+        st[3] = vx_n; st[4] = vy_n; st[5] = wz_n;
+        st[6] = 5.0 * (acc_des - acc) * deltaT + acc;
+        st[7] = 5.0 * (df_des - df) * deltaT + df;
+    }
+}
+
+MPC_DEV double np_interp(double xq, const double* xp, const double* fp, int n) {
+    if (xq <= xp[0]) return fp[0];
+    if (xq >= xp[n - 1]) return fp[n - 1];
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (xp[mid] <= xq) lo = mid; else hi = mid; }
+    const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+    return slope * (xq - xp[lo]) + fp[lo];
+}
+
+// get_waypoints for the whole warp: lane k returns waypoint k (k <= N); returns stop_cmd
+MPC_DEV bool get_waypoints_warp(const PathTable& p, int N, double traj_dt, double X, double Y, double yaw, bool use_vtarget,
+                                double v_target, double& xr, double& yr, double& pr) {
+    const int k = lane_id();
+    // nearest sample; numpy argmin returns the first minimum
+    double bd = 1e300; int bi = 0x7fffffff;
+    for (int i = k; i < p.n; i += 32) {
+        const double dx = p.X[i] - X, dy = p.Y[i] - Y, d = dx * dx + dy * dy;
+        if (d < bd) { bd = d; bi = i; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const double od = shfl_xor(bd, o); const int oi = shfl(bi, k ^ o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    const double* absc = use_vtarget ? p.s : p.t;
+    const double start = absc[bi];
+    xr = yr = pr = 0.0;
+    if (k <= N) {
+        const double q = use_vtarget ? ((double)(k + 1) * traj_dt * v_target + start) : ((double)k * traj_dt + start);
+        xr = np_interp(q, absc, p.X, p.n); yr = np_interp(q, absc, p.Y, p.n); pr = np_interp(q, absc, p.psi, p.n);
+    }
+    // heading wrap-around fix (:204-218)
+    const double PI = 3.141592653589793;
+    const double nxt = shfl_down(pr, 1);
+    double c1 = (k < N) ? fabs(nxt - pr) : 0.0, c2 = (k <= N) ? fabs(pr - yaw) : 0.0;
+    c1 = warp_max(c1); c2 = warp_max(c2);
+    if (!(c1 < PI && c2 < PI)) {
+        const double a0 = pr, a1 = pr + 2.0 * PI, a2 = pr - 2.0 * PI;
+        double b = a0, e = fabs(a0 - yaw);
+        if (fabs(a1 - yaw) < e) { e = fabs(a1 - yaw); b = a1; }
+        if (fabs(a2 - yaw) < e) { b = a2; }
+        pr = b;
+    }
+    const double lx = shfl(xr, N), ly = shfl(yr, N);
+    return lx == p.X[p.n - 1] && ly == p.Y[p.n - 1];
+}
+
+MPC_DEV double sel8(const double* v, int i) {   // register-friendly v[i] for a lane-dependent i
+    return (i == 0) ? v[0] : (i == 1) ? v[1] : (i == 2) ? v[2] : (i == 3) ? v[3] : (i == 4) ? v[4] : (i == 5) ? v[5] : (i == 6) ? v[6] : v[7];
+}
+
+MPC_DEV void rollout_vehicle(const KCfg& cfg, const RolloutArgs& a, long b, smem_t smem) {
+    WarpSolver S(cfg, smem);
+    const int k = S.k, N = cfg.N;
+    const PathTable& path = a.paths[a.path_of[b]];
+    double st[8] = {a.pose0[3 * b], a.pose0[3 * b + 1], a.pose0[3 * b + 2], 0, 0, 0, 0, 0};
+    double acc_des = 0.0, df_des = 0.0, up_d = 0.0, up_a = 0.0;   // commands, d_f_current, acc_current
+    const double des_speed = a.target_vel > 0.0 ? a.target_vel : 0.0;
+    bool stop = false;
+    S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;   // start = 0.0, then the previous solution
+    for (int t = 0; t < a.T; t++) {
+        for (int i = 0; i < 10; i++) plant_step(st, acc_des, df_des);
+        const bool sc = get_waypoints_warp(path, N, cfg.dt, st[0], st[1], st[2], !a.track_using_time, des_speed, S.xr, S.yr, S.pr);
+        if (sc) stop = true;   // latch, mpc_cmd_pub.jl:102-111
+        int status = -1, iters = 0;
+        if (!stop) {
+            syncwarp();
+            {
+                const double cv[8] = {st[0], st[1], st[2], st[3], up_d, up_a, des_speed, 0.0};
+                if (k < 8) sts(smem, SO(W_CONST + k), sel8(cv, k));
+            }
+            syncwarp();
+            const Result r = S.solve();
+            status = r.status; iters = r.iters;
+            acc_des = shfl(S.L.ua, 0); df_des = shfl(S.L.ud, 0);   // published whatever the status (:129-132)
+            up_d = df_des; up_a = acc_des;                           // update_current_input(df_opt, a_opt) (:140)
+        } else { acc_des = -1.0; df_des = 0.0; }                     // :148-153
+        if (a.log && k < 8) {
+            const double lv[8] = {st[0], st[1], st[2], st[3], acc_des, df_des, (double)status, (double)iters};
+            a.log[((long)t * a.B + b) * 8 + k] = sel8(lv, k);
+        }
+    }
+    if (a.final_state && k < 8) a.final_state[b * 8 + k] = sel8(st, k);
+    syncwarp();
+}
+
 }  // namespace mpcb200

@@ -59,3 +59,20 @@ def solve_batch(kcfg, state, ref, v_des, u_prev, warm=None, want_traj=False):
                         status.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)),
                         None if traj is None else traj.ctypes.data_as(dp))
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+
+def rollout(kcfg, traj_table, pose0, T, track_using_time=True, target_vel=1.0):
+    """All vehicles on the path whose (n,7) table is given.  Returns log (T,B,8), final (B,8)."""
+    lib = C.CDLL(build())
+    dp = C.POINTER(C.c_double)
+    pose0 = np.ascontiguousarray(np.atleast_2d(pose0), dtype=np.float64)
+    B = pose0.shape[0]
+    cols = [np.ascontiguousarray(traj_table[:, i]) for i in (0, 4, 5, 3, 6)]
+    path_of = np.zeros(B, dtype=np.int32)
+    log = np.zeros((T, B, 8)); final = np.zeros((B, 8))
+    lib.emu_rollout.argtypes = [C.POINTER(KCfg), C.c_long, C.c_int, dp, C.POINTER(C.c_int), C.c_int, dp, dp, dp, dp, dp,
+                                C.c_int, C.c_double, dp, dp]
+    lib.emu_rollout(C.byref(kcfg), B, T, pose0.ctypes.data_as(dp), path_of.ctypes.data_as(C.POINTER(C.c_int)), traj_table.shape[0],
+                    *[c.ctypes.data_as(dp) for c in cols], int(track_using_time), float(target_vel),
+                    log.ctypes.data_as(dp), final.ctypes.data_as(dp))
+    return log, final

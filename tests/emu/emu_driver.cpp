@@ -66,3 +66,29 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
     return 0;
 }
 extern "C" int emu_kcfg_size() { return (int)sizeof(KCfg); }
+
+struct RJob { const KCfg* cfg; const RolloutArgs* a; long b; double* smem; };
+static void lane_rollout(int, void* p) {
+    RJob* j = (RJob*)p;
+    WarpSolver::init_work(j->smem);
+    rollout_vehicle(*j->cfg, *j->a, j->b, j->smem);
+}
+extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, const int* path_of, int n0, const double* t,
+                           const double* X, const double* Y, const double* psi, const double* s, int track_using_time,
+                           double target_vel, double* log, double* final_state) {
+    KCfg kc = *cfg;
+    kcfg_finalize(kc);
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pose0 = pose0; a.path_of = path_of;
+    for (int i = 0; i < 3; i++) { a.paths[i].n = n0; a.paths[i].t = t; a.paths[i].X = X; a.paths[i].Y = Y; a.paths[i].psi = psi; a.paths[i].s = s; }
+    a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel; a.log = log; a.final_state = final_state; a.B = B;
+    std::vector<double> smem_raw(4096 + 2, 0.0);
+    double* smem = smem_raw.data();
+    if (((size_t)smem) & 15) smem++;
+    for (long b = 0; b < B; b++) {
+        RJob j{&kc, &a, b, smem};
+        emu::run_warp(lane_rollout, &j);
+    }
+    return 0;
+}

@@ -222,3 +222,59 @@ def test_closed_loop_reference_workload(capi, oracle):
         assert (glog[:, 6] == 0).mean() > 0.95
         err = closed_loop.path_errors(out["log"][20:], g.trajectory)
         assert err.max() < 1.5                                             # it follows the path
+
+
+def test_device_rollout_matches_oracle_closed_loop(capi, oracle):
+    """mpcb200_rollout (plant + reference generation + warm-started solves in one persistent kernel) against the
+    oracle's closed loop, vehicle by vehicle: same status and iteration count every step, same commands."""
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    s = capi.Solver(8)
+    trajs = [GPSRefTrajectory(mat_filename=p) for p in (1, 2, 3)]
+    for i, g in enumerate(trajs):
+        s.set_path(i, g.trajectory)
+    rng = np.random.default_rng(4)
+    poses, path_of = [(0.0, 3.0, -1.5)], [2]           # the launch file's start on path3
+    for i, g in enumerate(trajs):
+        for j in (0, 1500, 4000):
+            poses.append((g.trajectory[j, 4] + rng.normal(scale=0.4), g.trajectory[j, 5] + rng.normal(scale=0.4),
+                          g.trajectory[j, 3] + rng.normal(scale=0.05)))
+            path_of.append(i)
+    T = 80
+    out = s.rollout(np.array(poses), np.array(path_of), T)
+    assert s.stats()["kernel_launches"] == 1
+    for b, (pose, pid) in enumerate(zip(poses, path_of)):
+        path, keep = oracle.make_path(trajs[pid].trajectory)
+        olog = oracle.closed_loop(oracle.default_cfg(8), path, pose, T)
+        glog = out["log"][:, b, :]
+        assert np.array_equal(glog[:, 6], olog[:, 6]), b
+        assert np.abs(glog[:, 4:6] - olog[:, 4:6]).max() <= 1e-5, b
+        assert np.abs(glog[:, 0:4] - olog[:, 0:4]).max() <= 1e-4, b
+    # the end-of-path latch: a vehicle started 3 s before the end of path1 brakes with (-1, 0)
+    g = trajs[0]
+    j = g.trajectory.shape[0] - 300
+    out = s.rollout(np.array([[g.trajectory[j, 4], g.trajectory[j, 5], g.trajectory[j, 3]]]), np.array([0]), 60)
+    assert (out["log"][-1, 0, 4:7] == np.array([-1.0, 0.0, -1.0])).all()
+    with pytest.raises(capi.MpcB200Error):
+        capi.Solver(8).rollout(np.zeros((1, 3)), np.array([0]), 5)      # path not set
+
+
+def test_monte_carlo_rollout_properties(capi):
+    """BASELINE.json configs[3] scaled to one GPU-minute: 2,048 vehicles x 100 steps over paths 1-3; every step's solve
+    is Optimal once the vehicles are on the path, and the fleet tracks its paths."""
+    from mkz_mpc_path_follower_b200 import closed_loop
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    s = capi.Solver(8)
+    trajs = [GPSRefTrajectory(mat_filename=p) for p in (1, 2, 3)]
+    for i, g in enumerate(trajs):
+        s.set_path(i, g.trajectory)
+    B, T = 2048, 100
+    rng = np.random.default_rng(9)
+    path_of = (np.arange(B) % 3).astype(np.int32)
+    pose0 = np.stack([(trajs[p].trajectory[0, 4] + rng.normal(scale=0.3), trajs[p].trajectory[0, 5] + rng.normal(scale=0.3),
+                       trajs[p].trajectory[0, 3] + rng.normal(scale=0.05)) for p in path_of])
+    out = s.rollout(pose0, path_of, T)
+    st = out["log"][:, :, 6]
+    assert (st == 0).mean() > 0.97
+    for p in range(3):
+        err = closed_loop.path_errors(out["log"][30:, path_of == p, :], trajs[p].trajectory)
+        assert np.quantile(err, 0.99) < 1.0
