@@ -29,7 +29,7 @@ mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
     const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_warp(cfg.N));
-    WarpSolver::init_work(smem);
+    WarpSolver::init_work(smem, cfg.N);
     for (;;) {
         unsigned long long b = 0;
         if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
@@ -45,7 +45,7 @@ mpc_rollout_kernel(const KCfg cfg, const RolloutArgs args, unsigned long long* c
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
     const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_warp(cfg.N));
-    WarpSolver::init_work(smem);
+    WarpSolver::init_work(smem, cfg.N);
     for (;;) {
         unsigned long long b = 0;
         if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);

@@ -100,8 +100,8 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define W_TT 42     // 5x6: TT[c][i] = (P*M)[i][c] for c = psi,v,a,df and c = 4: P r + p
 #define W_F 72      // 6x6 stage Hessian F over (x,y,psi,v,a,df)
 #define W_FV 108    // 6   stage gradient f
-#define W_EX 114    // 6   unit vector e_x
-#define W_EY 120    // 6   unit vector e_y
+#define W_EX 114    // 4(+2) unit vector e_x over rows (x,y,psi,v)
+#define W_EY 120    // 4(+2) unit vector e_y
 #define W_Z 126     // 6   zeros
 #define W_C 132     // Ca, Cd of the current stage (copied from the record by idle lanes of round B)
 #define W_NC 134    // (-Ca, 0), (0, -Cd) of the current stage
@@ -109,27 +109,27 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define W_CONST 140 // problem constants: state[4], u_prev[2], v_des, pad
 #define W_SD 148    // stage records start here
 // stage record
-#define SD_MT 0     // 5 columns x 6: d(next state, next prev-input)/d(psi | v | a | df), then residual r
-#define SD_R 24     //   r column (dynamics residual; record N: initial-condition residual)
-#define SD_HXX 30
-#define SD_HYY 31
-#define SD_HPP 32
-#define SD_HPV 33
-#define SD_HVV 34
-#define SD_HPD 35
-#define SD_HVD 36
-#define SD_HAA 37
-#define SD_HDD 38
-#define SD_CA 39
-#define SD_CD 40
-#define SD_ZERO 41  // constant 0 (H entries that are structurally zero point here)
-#define SD_NCA 42   // -Ca
-#define SD_NCD 43   // -Cd
-#define SD_GX 46    // GX,GY,GP,GV,GA,GD (condensed gradient)
-#define SD_SRW 52   // (Sigma_s + delta_w) of the rate row [steer, acc]
-#define SD_BR 54    // -mu/ss_L + mu/ss_U of the rate row
-#define SD_DR 56    // rate-row residual used as right-hand side
-#define SDS 58      // even: records are 16-byte aligned
+#define SD_CF 0     // 5 coefficient 4-vectors over next-state rows (x,y,psi,v): columns psi | v | a | df of [A B], then r
+#define SD_R 16     //   r column (dynamics residual; record N: initial-condition residual)
+#define SD_HXX 20
+#define SD_HYY 21
+#define SD_HPP 22
+#define SD_HPV 23
+#define SD_HVV 24
+#define SD_HPD 25
+#define SD_HVD 26
+#define SD_HAA 27
+#define SD_HDD 28
+#define SD_CA 29
+#define SD_CD 30
+#define SD_ZERO 31  // constant 0 (H entries that are structurally zero point here)
+#define SD_NCA 32   // -Ca
+#define SD_NCD 33   // -Cd
+#define SD_GX 34    // GX,GY,GP,GV,GA,GD (condensed gradient)
+#define SD_SRW 40   // (Sigma_s + delta_w) of the rate row [steer, acc]
+#define SD_BR 42    // -mu/ss_L + mu/ss_U of the rate row
+#define SD_DR 44    // rate-row residual used as right-hand side
+#define SDS 46      // even: records are 16-byte aligned
 #define KST_STRIDE 14
 
 MPC_HD int smem_doubles_per_warp(int N) { return W_SD + (N + 1) * SDS + N * KST_STRIDE; }
@@ -209,11 +209,18 @@ struct WarpSolver {
     MPC_DEV double cst(int i) const { return lds(sm, SO(W_CONST + i)); }  // state[0..3], u_prev[0..1], v_des
     MPC_DEV int rec() const { return SO(W_SD + (isS ? k : 0) * SDS); }    // this lane's own stage record
 
-    MPC_DEV static void init_work(smem_t sm) {
+    MPC_DEV static void init_work(smem_t sm, int N) {
         const int l = lane_id();
         if (l < 6) { sts(sm, SO(W_EX + l), (l == 0) ? 1.0 : 0.0); sts(sm, SO(W_EY + l), (l == 1) ? 1.0 : 0.0); sts(sm, SO(W_Z + l), 0.0); }
         if (l < 4) sts(sm, SO(W_NC + l), 0.0);
         if (l < 2) sts(sm, SO(W_DUMMY + l), 0.0);
+        if (l <= N) {   // structural constants of this lane's record: never rewritten
+            const int r = SO(W_SD + l * SDS);
+            sts(sm, r + SO(SD_CF + 3), 0.0);                                        // psi column: (A02, A12, 1, 0) -- the 1 is set by assemble (0 for record N)
+            sts(sm, r + SO(SD_CF + 8), 0.0); sts(sm, r + SO(SD_CF + 9), 0.0); sts(sm, r + SO(SD_CF + 10), 0.0);   // a column: (0,0,0,dt)
+            sts(sm, r + SO(SD_CF + 15), 0.0);                                       // df column: (b0,b1,b2,0)
+            sts(sm, r + SO(SD_ZERO), 0.0);
+        }
         syncwarp();
     }
 
@@ -388,21 +395,15 @@ struct WarpSolver {
             const double A12 = isU ? c.dt * L.sv * ev.cs : 0.0, A13 = isU ? c.dt * ev.sn : 0.0;
             const double A23 = isU ? c.dt * ev.sb / c.Lb : 0.0;
             const double b0 = A02 * ev.b1, b1v = A12 * ev.b1, b2v = isU ? c.dt * L.sv * ev.cb * ev.b1 / c.Lb : 0.0;
-            const double one = 1.0, zero = 0.0;
-            sts(sm, r + SO(SD_MT + 0), A02); sts(sm, r + SO(SD_MT + 1), A12); sts(sm, r + SO(SD_MT + 2), one);
-            sts(sm, r + SO(SD_MT + 3), zero); sts(sm, r + SO(SD_MT + 4), zero); sts(sm, r + SO(SD_MT + 5), zero);
-            sts(sm, r + SO(SD_MT + 6), A03); sts(sm, r + SO(SD_MT + 7), A13); sts(sm, r + SO(SD_MT + 8), A23);
-            sts(sm, r + SO(SD_MT + 9), one); sts(sm, r + SO(SD_MT + 10), zero); sts(sm, r + SO(SD_MT + 11), zero);
-            sts(sm, r + SO(SD_MT + 12), zero); sts(sm, r + SO(SD_MT + 13), zero); sts(sm, r + SO(SD_MT + 14), zero);
-            sts(sm, r + SO(SD_MT + 15), c.dt); sts(sm, r + SO(SD_MT + 16), one); sts(sm, r + SO(SD_MT + 17), zero);
-            sts(sm, r + SO(SD_MT + 18), b0); sts(sm, r + SO(SD_MT + 19), b1v); sts(sm, r + SO(SD_MT + 20), b2v);
-            sts(sm, r + SO(SD_MT + 21), zero); sts(sm, r + SO(SD_MT + 22), zero); sts(sm, r + SO(SD_MT + 23), one);
+            const double one = isU ? 1.0 : 0.0;
+            sts(sm, r + SO(SD_CF + 0), A02); sts(sm, r + SO(SD_CF + 1), A12); sts(sm, r + SO(SD_CF + 2), one);
+            sts(sm, r + SO(SD_CF + 4), A03); sts(sm, r + SO(SD_CF + 5), A13); sts(sm, r + SO(SD_CF + 6), A23); sts(sm, r + SO(SD_CF + 7), one);
+            sts(sm, r + SO(SD_CF + 11), isU ? c.dt : 0.0);
+            sts(sm, r + SO(SD_CF + 12), b0); sts(sm, r + SO(SD_CF + 13), b1v); sts(sm, r + SO(SD_CF + 14), b2v);
             const bool z = (req == 0);
             sts(sm, r + SO(SD_R + 0), z ? 0.0 : ev.rd[0]); sts(sm, r + SO(SD_R + 1), z ? 0.0 : ev.rd[1]);
             sts(sm, r + SO(SD_R + 2), z ? 0.0 : ev.rd[2]); sts(sm, r + SO(SD_R + 3), z ? 0.0 : ev.rd[3]);
-            sts(sm, r + SO(SD_R + 4), zero); sts(sm, r + SO(SD_R + 5), zero);
             sts(sm, r + SO(SD_HPV), Hpv); sts(sm, r + SO(SD_HPD), Hpd); sts(sm, r + SO(SD_HVD), Hvd);
-            sts(sm, r + SO(SD_ZERO), zero);
             sts(sm, r + SO(SD_GX + 0), gx); sts(sm, r + SO(SD_GX + 1), gy); sts(sm, r + SO(SD_GX + 2), gp); sts(sm, r + SO(SD_GX + 3), gsv);
             sts(sm, r + SO(SD_BR), br[0]); sts(sm, r + SO(SD_BR + 1), br[1]);
             sts(sm, r + SO(SD_DR), rdr[0]); sts(sm, r + SO(SD_DR + 1), rdr[1]);
@@ -429,30 +430,34 @@ struct WarpSolver {
         const int l = k;
         // lane roles: shared-memory offsets, recomputed per call and laundered so that they stay in
         // registers through the stage loop instead of being rematerialised at every use
-        int a_p, a_m, a_ex, a_out, b_m, b_mk, b_t, b_h, b_o1, b_o2, e_f0, e_fi, e_fj, e_o1, e_o2, e_k0, e_k1;
+        int a_p, a_m, a_ex, a_out, b_m, b_mk, b_t, b_x, b_h, b_o1, b_o2, e_f0, e_fi, e_fj, e_o1, e_o2, e_k0, e_k1;
         {
+            // round A: lane (i, cc) -> TT[cc][i] = sum_{j<4} P[i][j] CF[cc][j] + X,  X = 0 | P[i][4] | P[i][5] | p[i]
             const int i = (l < 24) ? (l >> 2) : (l < 30 ? l - 24 : 0);
             const int cc = (l < 24) ? (l & 3) : 4;
             a_p = launder(SO(W_P + 6 * i));
-            a_m = launder(SO(W_SD + SD_MT + 6 * cc));
-            a_ex = launder((l >= 24 && l < 30) ? SO(W_PV + i) : SO(W_Z));
+            a_m = launder(SO(W_SD + SD_CF + 4 * cc));
+            a_ex = launder((l >= 30) ? SO(W_Z) : (cc == 2) ? SO(W_P + 6 * i + 4) : (cc == 3) ? SO(W_P + 6 * i + 5) : (cc == 4) ? SO(W_PV + i) : SO(W_Z));
             a_out = launder((l < 30) ? SO(W_TT + 6 * cc + i) : SO(W_DUMMY));
         }
         {
-            // 21 symmetric pairs (c1 <= c2) over (x,y,psi,v,a,df); 6 vector entries; 4 copy lanes
+            // round B: 21 symmetric pairs (c1 <= c2) over (x,y,psi,v,a,df); 6 vector entries; 4 copy lanes
+            //   F[c1][c2] = H + sum_{i<4} M[i][c1] That[i][c2] + X,  X = That[4][c2] (c1 = a) | That[5][c2] (c1 = df) | 0
             int c1 = 0, c2 = 0, kind = 0;  // 0 pair, 1 vector, 2 copy, 3 idle
             if (l < 21) { int t = l; while (t >= 6 - c1) { t -= 6 - c1; c1++; } c2 = c1 + t; }
             else if (l < 27) { c1 = l - 21; kind = 1; }
             else if (l < 31) kind = 2;
             else kind = 3;
-            int mb, mk, tb, h, o1, o2;
+            int mb, mk, tb, xb, hf, o1, o2;
             if (kind >= 2) { mb = SO(W_Z); mk = 0; }
             else if (c1 < 2) { mb = (c1 == 0) ? SO(W_EX) : SO(W_EY); mk = 0; }
-            else { mb = SO(W_SD + SD_MT + 6 * (c1 - 2)); mk = 1; }
+            else { mb = SO(W_SD + SD_CF + 4 * (c1 - 2)); mk = 1; }
+            // That column c2 (rows 0..5 contiguous): P row c2 (symmetric) for x,y; TT column otherwise; TT[4] for the vector
             if (kind == 1) tb = SO(W_TT + 24);
-            else if (kind == 0) tb = (c2 < 2) ? SO(W_P + 6 * c2) : SO(W_TT + 6 * (c2 - 2));  // P symmetric: column = row
+            else if (kind == 0) tb = (c2 < 2) ? SO(W_P + 6 * c2) : SO(W_TT + 6 * (c2 - 2));
             else tb = SO(W_Z);
-            int hf = SD_ZERO;
+            xb = (kind <= 1 && c1 == 4) ? tb + SO(4) : (kind <= 1 && c1 == 5) ? tb + SO(5) : SO(W_Z);
+            hf = SD_ZERO;
             if (kind == 1) hf = SD_GX + c1;
             else if (kind == 0) {
                 if (c1 == c2) hf = (c1 == 0) ? SD_HXX : (c1 == 1) ? SD_HYY : (c1 == 2) ? SD_HPP : (c1 == 3) ? SD_HVV : (c1 == 4) ? SD_HAA : SD_HDD;
@@ -460,12 +465,12 @@ struct WarpSolver {
                 else if (c1 == 2 && c2 == 5) hf = SD_HPD;
                 else if (c1 == 3 && c2 == 5) hf = SD_HVD;
             } else if (kind == 2) hf = (l == 27) ? SD_CA : (l == 28) ? SD_CD : (l == 29) ? SD_NCA : SD_NCD;
-            h = SO(W_SD + hf);
             if (kind == 0) { o1 = SO(W_F + 6 * c1 + c2); o2 = SO(W_F + 6 * c2 + c1); }
             else if (kind == 1) { o1 = o2 = SO(W_FV + c1); }
             else if (kind == 2) { o1 = o2 = (l == 27) ? SO(W_C) : (l == 28) ? SO(W_C + 1) : (l == 29) ? SO(W_NC) : SO(W_NC + 3); }
             else { o1 = o2 = SO(W_DUMMY); }
-            b_m = launder(mb); b_mk = launder(mk); b_t = launder(tb); b_h = launder(h); b_o1 = launder(o1); b_o2 = launder(o2);
+            b_m = launder(mb); b_mk = launder(mk); b_t = launder(tb); b_x = launder(xb); b_h = launder(SO(W_SD + hf));
+            b_o1 = launder(o1); b_o2 = launder(o2);
         }
         {
             // 21 symmetric pairs (i <= j) over xi, then 6 vector entries.
@@ -513,25 +518,24 @@ struct WarpSolver {
         int so = SO((N - 1) * SDS);   // byte offset of the current stage's record relative to record 0
         for (int s = N - 1; s >= 0; s--) {
             {   // ---- Round A
-                const d2 p0 = lds2(sm, a_p), p1 = lds2(sm, a_p + SO(2)), p2 = lds2(sm, a_p + SO(4));
+                const d2 p0 = lds2(sm, a_p), p1 = lds2(sm, a_p + SO(2));
                 const int m = a_m + so;
-                const d2 m0 = lds2(sm, m), m1 = lds2(sm, m + SO(2)), m2 = lds2(sm, m + SO(4));
+                const d2 m0 = lds2(sm, m), m1 = lds2(sm, m + SO(2));
                 const double ex = lds(sm, a_ex);
                 const double t0 = p0.x * m0.x + p0.y * m0.y;
-                const double t1 = p1.x * m1.x + p1.y * m1.y;
-                const double t2 = p2.x * m2.x + p2.y * m2.y + ex;
-                sts(sm, a_out, (t0 + t1) + t2);
+                const double t1 = p1.x * m1.x + p1.y * m1.y + ex;
+                sts(sm, a_out, t0 + t1);
             }
             syncwarp();
             {   // ---- Round B
                 const int m = b_m + b_mk * so;
-                const d2 m0 = lds2(sm, m), m1 = lds2(sm, m + SO(2)), m2 = lds2(sm, m + SO(4));
-                const d2 q0 = lds2(sm, b_t), q1 = lds2(sm, b_t + SO(2)), q2 = lds2(sm, b_t + SO(4));
+                const d2 m0 = lds2(sm, m), m1 = lds2(sm, m + SO(2));
+                const d2 q0 = lds2(sm, b_t), q1 = lds2(sm, b_t + SO(2));
+                const double x = lds(sm, b_x);
                 const double h = lds(sm, b_h + so);
-                const double t0 = m0.x * q0.x + m0.y * q0.y;
-                const double t1 = m1.x * q1.x + m1.y * q1.y;
-                const double t2 = m2.x * q2.x + m2.y * q2.y + h;
-                const double o = (t0 + t1) + t2;
+                const double t0 = m0.x * q0.x + m0.y * q0.y + x;
+                const double t1 = m1.x * q1.x + m1.y * q1.y + h;
+                const double o = t0 + t1;
                 sts(sm, b_o1, o); sts(sm, b_o2, o);
             }
             syncwarp();
@@ -568,8 +572,8 @@ struct WarpSolver {
         for (int s = 0; s < N; s++) {
             const d2 ka0 = lds2(sm, kp), ka1 = lds2(sm, kp + SO(2)), ka2 = lds2(sm, kp + SO(4)), kx = lds2(sm, kp + SO(6));
             const d2 kd0 = lds2(sm, kp + SO(8)), kd1 = lds2(sm, kp + SO(10)), kd2 = lds2(sm, kp + SO(12));
-            const d2 cp = lds2(sm, r + SO(SD_MT + 0)), cv = lds2(sm, r + SO(SD_MT + 6)), cd = lds2(sm, r + SO(SD_MT + 18));
-            const double a23 = lds(sm, r + SO(SD_MT + 8)), b2 = lds(sm, r + SO(SD_MT + 20));
+            const d2 cp = lds2(sm, r + SO(SD_CF + 0)), cv = lds2(sm, r + SO(SD_CF + 4)), cd = lds2(sm, r + SO(SD_CF + 12));
+            const double a23 = lds(sm, r + SO(SD_CF + 6)), b2 = lds(sm, r + SO(SD_CF + 14));
             const d2 r01 = lds2(sm, r + SO(SD_R)), r23 = lds2(sm, r + SO(SD_R + 2));
             const double ua = (ka0.x * s0 + ka0.y * s1 + ka1.x * s2) + (ka1.y * s3 + ka2.x * pa + ka2.y * pd) + kx.x;
             const double ud = (kx.y * s0 + kd0.x * s1 + kd0.y * s2) + (kd1.x * s3 + kd1.y * pa + kd2.x * pd) + kd2.y;
@@ -597,8 +601,8 @@ struct WarpSolver {
             lv = -(hpv * D.dsp + lds(sm, r + SO(SD_HVV)) * D.dsv + lds(sm, r + SO(SD_HVD)) * D.dud + lds(sm, r + SO(SD_GX + 3)));
         }
         const double hasn = isU ? 1.0 : 0.0;
-        const d2 c0 = lds2(sm, r + SO(SD_MT + 0)), c1 = lds2(sm, r + SO(SD_MT + 6));   // (A02, A12), (A03, A13)
-        const double A23 = lds(sm, r + SO(SD_MT + 8));
+        const d2 c0 = lds2(sm, r + SO(SD_CF + 0)), c1 = lds2(sm, r + SO(SD_CF + 4));   // (A02, A12), (A03, A13)
+        const double A23 = lds(sm, r + SO(SD_CF + 6));
         for (int o = 1; o < 32; o <<= 1) {   // y_x, y_y: two interleaved suffix sums
             const double tx = shfl_down(lx, o), ty = shfl_down(ly, o);
             if (k + o < 32) { lx += tx; ly += ty; }

@@ -46,7 +46,7 @@ using namespace mpcb200;
 struct Job { const KCfg* cfg; const BatchPtrs* io; long b; double* smem; };
 static void lane_main(int, void* a) {
     Job* j = (Job*)a;
-    WarpSolver::init_work(j->smem);
+    WarpSolver::init_work(j->smem, j->cfg->N);
     solve_problem(*j->cfg, *j->io, j->b, j->smem);
 }
 
@@ -70,7 +70,7 @@ extern "C" int emu_kcfg_size() { return (int)sizeof(KCfg); }
 struct RJob { const KCfg* cfg; const RolloutArgs* a; long b; double* smem; };
 static void lane_rollout(int, void* p) {
     RJob* j = (RJob*)p;
-    WarpSolver::init_work(j->smem);
+    WarpSolver::init_work(j->smem, j->cfg->N);
     rollout_vehicle(*j->cfg, *j->a, j->b, j->smem);
 }
 extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, const int* path_of, int n0, const double* t,
