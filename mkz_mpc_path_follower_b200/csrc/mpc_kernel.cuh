@@ -29,8 +29,10 @@ namespace mpcb200 {
 
 #ifdef MPC_HOST_EMU
 #define MPC_HD inline
+#define MPC_NOUNROLL
 #else
 #define MPC_HD __host__ __device__ __forceinline__
+#define MPC_NOUNROLL _Pragma("unroll 1")
 #endif
 
 struct KCfg {
@@ -137,20 +139,20 @@ MPC_HD int smem_doubles_per_warp(int N) { return W_SD + (N + 1) * SDS + N * KST_
 MPC_DEV double dmax_(double a, double b) { return a > b ? a : b; }
 MPC_DEV double dmin_(double a, double b) { return a < b ? a : b; }
 MPC_DEV double warp_max(double v) {
-    for (int o = 16; o; o >>= 1) { double t = shfl_xor(v, o); v = (t > v || t != t) ? t : v; }
+    MPC_NOUNROLL for (int o = 16; o; o >>= 1) { double t = shfl_xor(v, o); v = (t > v || t != t) ? t : v; }
     return v;
 }
 MPC_DEV double warp_min(double v) {
-    for (int o = 16; o; o >>= 1) { double t = shfl_xor(v, o); v = (t < v) ? t : v; }
+    MPC_NOUNROLL for (int o = 16; o; o >>= 1) { double t = shfl_xor(v, o); v = (t < v) ? t : v; }
     return v;
 }
 MPC_DEV double warp_sum(double v) {
-    for (int o = 16; o; o >>= 1) v += shfl_xor(v, o);
+    MPC_NOUNROLL for (int o = 16; o; o >>= 1) v += shfl_xor(v, o);
     return v;
 }
 // inclusive suffix sum over lanes: out_k = sum_{j >= k} v_j
 MPC_DEV double warp_suffix_sum(double v, int l) {
-    for (int o = 1; o < 32; o <<= 1) { double t = shfl_down(v, o); if (l + o < 32) v += t; }
+    MPC_NOUNROLL for (int o = 1; o < 32; o <<= 1) { double t = shfl_down(v, o); if (l + o < 32) v += t; }
     return v;
 }
 MPC_DEV void push_interior(double& v, double lo, double hi) {
@@ -296,7 +298,7 @@ struct WarpSolver {
         if (isR) { const double h0 = rHi(0), h1 = rHi(1); p *= (s0 + h0) * (h0 - s0) * (s1 + h1) * (h1 - s1); }
         double lb = log(p);
         double th = fabs(ev.rd[0]) + fabs(ev.rd[1]) + fabs(ev.rd[2]) + fabs(ev.rd[3]) + fabs(ev.dr[0]) + fabs(ev.dr[1]);
-        for (int o = 16; o; o >>= 1) { f += shfl_xor(f, o); lb += shfl_xor(lb, o); th += shfl_xor(th, o); }
+        MPC_NOUNROLL for (int o = 16; o; o >>= 1) { f += shfl_xor(f, o); lb += shfl_xor(lb, o); th += shfl_xor(th, o); }
         ev.f = f; ev.lb = lb; ev.theta = th;
     }
 
@@ -603,7 +605,7 @@ struct WarpSolver {
         const double hasn = isU ? 1.0 : 0.0;
         const d2 c0 = lds2(sm, r + SO(SD_CF + 0)), c1 = lds2(sm, r + SO(SD_CF + 4));   // (A02, A12), (A03, A13)
         const double A23 = lds(sm, r + SO(SD_CF + 6));
-        for (int o = 1; o < 32; o <<= 1) {   // y_x, y_y: two interleaved suffix sums
+        MPC_NOUNROLL for (int o = 1; o < 32; o <<= 1) {   // y_x, y_y: two interleaved suffix sums
             const double tx = shfl_down(lx, o), ty = shfl_down(ly, o);
             if (k + o < 32) { lx += tx; ly += ty; }
         }
@@ -882,7 +884,7 @@ struct WarpSolver {
                     cv = dmax_(cv, dmax_(fabs(ev.dr[0]), fabs(ev.dr[1])));
                     sumy = isS ? fabs(L.yx) + fabs(L.yy) + fabs(L.yp) + fabs(L.yv) + fabs(L.ryd[0]) + fabs(L.ryd[1]) : 0.0;
                     sumz = L.zvL + L.zvU + L.zaL + L.zaU + L.zdL + L.zdU + L.rvL[0] + L.rvL[1] + L.rvU[0] + L.rvU[1];
-                    for (int o = 16; o; o >>= 1) { sumy += shfl_xor(sumy, o); sumz += shfl_xor(sumz, o); }
+                    MPC_NOUNROLL for (int o = 16; o; o >>= 1) { sumy += shfl_xor(sumy, o); sumz += shfl_xor(sumz, o); }
                 }
                 const double sd = dmax_(K_S_MAX, (sumy + sumz) / (double)(my + nz)) / K_S_MAX;
                 const double sc = dmax_(K_S_MAX, sumz / (double)nz) / K_S_MAX;
@@ -904,7 +906,7 @@ struct WarpSolver {
                 // E_0 and E_mu in one pass
                 const double dcv = dmax_(di / sd, cv);
                 double e0 = dmax_(dcv, cm0 / sc), em = dmax_(dcv, cmm / sc);
-                for (int o = 16; o; o >>= 1) {
+                MPC_NOUNROLL for (int o = 16; o; o >>= 1) {
                     const double t0 = shfl_xor(e0, o), t1 = shfl_xor(em, o);
                     e0 = (t0 > e0 || t0 != t0) ? t0 : e0; em = (t1 > em || t1 != t1) ? t1 : em;
                 }
@@ -1142,7 +1144,7 @@ MPC_DEV bool get_waypoints_warp(const PathTable& p, int N, double traj_dt, doubl
         const double dx = p.X[i] - X, dy = p.Y[i] - Y, d = dx * dx + dy * dy;
         if (d < bd) { bd = d; bi = i; }
     }
-    for (int o = 16; o; o >>= 1) {
+    MPC_NOUNROLL for (int o = 16; o; o >>= 1) {
         const double od = shfl_xor(bd, o); const int oi = shfl(bi, k ^ o);
         if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
     }
