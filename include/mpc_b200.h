@@ -52,7 +52,7 @@ extern "C" {
 
 /* Replaces the module-level constants of MKZMPCPathFollower.jl:28-48. */
 typedef struct {
-    int32_t N;            /* horizon (:34), 3 <= N <= 31 in this build */
+    int32_t N;            /* horizon (:34), 3 <= N <= 95: one warp per problem up to 31, one block of 2-3 warps beyond */
     int32_t max_iter;     /* iteration cap -> MPCB200_USERLIMIT */
     int32_t start_mode;   /* MPCB200_START_* */
     int32_t device;       /* CUDA device ordinal */

@@ -28,15 +28,33 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MPC_MIN_BLOCKS)
 mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
-    const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_warp(cfg.N));
-    WarpSolver::init_work(smem, cfg.N);
+    const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_team(cfg.N));
+    TeamSolver<1>::init_work(smem, cfg.N);
     for (;;) {
         unsigned long long b = 0;
         if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= (unsigned long long)B) break;
-        solve_problem(cfg, io, (long)b, smem);
+        solve_problem<1>(cfg, io, (long)b, smem);
         __syncwarp();
+    }
+}
+
+// Long horizons (32 <= N <= 95): one problem per block of W = 2 or 3 warps, thread k = stage k.
+template <int W>
+__global__ void __launch_bounds__(W * 32, 1)
+mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned long long* counter) {
+    extern __shared__ double smem_all[];
+    __shared__ unsigned long long next_problem;
+    const smem_t smem = smem_base(smem_all);
+    TeamSolver<W>::init_work(smem, cfg.N);
+    for (;;) {
+        if (threadIdx.x == 0) next_problem = atomicAdd(counter, 1ULL);
+        __syncthreads();
+        const unsigned long long b = next_problem;
+        __syncthreads();
+        if (b >= (unsigned long long)B) break;
+        solve_problem<W>(cfg, io, (long)b, smem);
     }
 }
 
@@ -44,8 +62,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MPC_MIN_BLOCKS)
 mpc_rollout_kernel(const KCfg cfg, const RolloutArgs args, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
-    const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_warp(cfg.N));
-    WarpSolver::init_work(smem, cfg.N);
+    const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_team(cfg.N));
+    TeamSolver<1>::init_work(smem, cfg.N);
     for (;;) {
         unsigned long long b = 0;
         if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
@@ -80,6 +98,7 @@ struct mpcb200_handle {
     int device = 0;
     int num_sms = 0;
     int blocks_per_sm = 0;
+    int team_warps = 1;     /* warps per problem: 1 (N <= 31), 2 (N <= 63), 3 (N <= 95) */
     size_t smem_bytes = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -161,7 +180,7 @@ int mpcb200_default_config(mpcb200_config* c, int32_t N) {
 int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
     if (!out || !cfg) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: NULL argument");
     *out = nullptr;
-    if (cfg->N < 3 || cfg->N > 31) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: horizon N=%d outside [3,31]", cfg->N);
+    if (cfg->N < 3 || cfg->N > 95) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: horizon N=%d outside [3,95]", cfg->N);
     if (!(cfg->dt > 0) || !(cfg->dt_control > 0) || !(cfg->L_b > 0) || !(cfg->v_max > cfg->v_min) || !(cfg->a_max > 0) ||
         !(cfg->steer_max > 0 && cfg->steer_max < 1.5) || !(cfg->a_dmax > 0) || !(cfg->steer_dmax > 0) || !(cfg->tol > 0) ||
         cfg->max_iter < 0)
@@ -199,15 +218,24 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
     TRY_OR_FREE(cudaEventCreate(&h->ev0));
     TRY_OR_FREE(cudaEventCreate(&h->ev1));
     TRY_OR_FREE(cudaMalloc((void**)&h->d_counter, sizeof(unsigned long long)));
-    h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_warp(cfg->N) * sizeof(double);
-    TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
+    h->team_warps = team_warps(cfg->N);
+    if (h->team_warps == 1) {
+        h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N) * sizeof(double);
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, mpc_rollout_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
+        if (h->rollout_blocks_per_sm < 1) h->rollout_blocks_per_sm = 1;
+    } else {
+        h->smem_bytes = (size_t)smem_doubles_per_team(cfg->N) * sizeof(double);
+        const void* fn = (h->team_warps == 2) ? (const void*)mpc_solve_long_kernel<2> : (const void*)mpc_solve_long_kernel<3>;
+        TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, fn, h->team_warps * 32, h->smem_bytes));
+    }
     if (h->blocks_per_sm < 1) h->blocks_per_sm = 1;
-    TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-    TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, mpc_rollout_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
-    if (h->rollout_blocks_per_sm < 1) h->rollout_blocks_per_sm = 1;
     if (const char* e = getenv("MPCB200_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v; }  /* tuning aid */
 #undef TRY_OR_FREE
     *out = h;
@@ -243,11 +271,17 @@ int mpcb200_set_stream(mpcb200_handle* h, void* s) {
 
 static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io) {
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), h->stream));
-    long long blocks_needed = (B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const int teams_per_block = (h->team_warps == 1) ? WARPS_PER_BLOCK : 1;
+    long long blocks_needed = (B + teams_per_block - 1) / teams_per_block;
     long long max_blocks = (long long)h->num_sms * h->blocks_per_sm;
     int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
     if (grid < 1) grid = 1;
-    mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, (long long)B, h->d_counter);
+    if (h->team_warps == 1)
+        mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, (long long)B, h->d_counter);
+    else if (h->team_warps == 2)
+        mpc_solve_long_kernel<2><<<grid, 64, h->smem_bytes, h->stream>>>(make_kcfg(h), io, (long long)B, h->d_counter);
+    else
+        mpc_solve_long_kernel<3><<<grid, 96, h->smem_bytes, h->stream>>>(make_kcfg(h), io, (long long)B, h->d_counter);
     CUDA_TRY(h, cudaGetLastError());
     h->stats.kernel_launches += 1;
     return 0;
@@ -333,6 +367,7 @@ int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T, const double* pose0
     memset(&h->stats, 0, sizeof(h->stats));
     if (B == 0 || T == 0) return MPCB200_OK;
     if (!pose0 || !path_of) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: pose0 and path_of are required");
+    if (h->team_warps != 1) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: closed-loop rollouts need N <= 31 (N=%d)", h->cfg.N);
     for (int64_t b = 0; b < B; b++)
         if (path_of[b] < 0 || path_of[b] > 2 || h->path_n[path_of[b]] == 0)
             return fail(h, MPCB200_EINVAL, "mpcb200_rollout: vehicle %lld uses path %d, which was not set with mpcb200_set_path", (long long)b, path_of[b]);

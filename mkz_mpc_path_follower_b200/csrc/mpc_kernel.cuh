@@ -7,7 +7,11 @@
 //                       fraction-to-boundary, filter line search, inertia correction; MUMPS LDL^T
 //                       -> block-tridiagonal Riccati recursion on the condensed KKT system)
 //
-// Lane k of the warp owns stage k of the horizon (k = 0..N, N <= 31): its state (x,y,psi,v),
+// Thread k of a TEAM owns stage k of the horizon (k = 0..N).  A team is one warp for N <= 31 (the
+// hot configuration: four independent problems per block) and one block of W = 2 or 3 warps for
+// long horizons (N <= 63 / 95: one problem per block; cross-warp exchanges go through a small
+// shared-memory area and bar.sync, the serial Riccati recursion runs in warp 0).  Thread k holds
+// its state (x,y,psi,v),
 // input (acc,df), the multipliers of the equality rows that define s_k, its bound multipliers
 // and the rate row that ends at u_k.  Stage-parallel work (model evaluation, residuals,
 // multiplier updates, norms) runs with lanes = stages; the serial Riccati recursion switches
@@ -109,7 +113,14 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define W_NC 134    // (-Ca, 0), (0, -Cd) of the current stage
 #define W_DUMMY 138 // sink for inactive lanes (2)
 #define W_CONST 140 // problem constants: state[4], u_prev[2], v_des, pad
-#define W_SD 148    // stage records start here
+#define W_XCH 148   // teams of several warps only: exchange area (reductions, neighbour values, flags)
+#define XCH_RED 0   //   [2][3][4] per-warp partial results of a reduction
+#define XCH_DN 24   //   [2][3][8] first-lane values of each warp (read by the last lane of the warp below)
+#define XCH_UP 72   //   [2][3][8] last-lane values of each warp (read by the first lane of the warp above)
+#define XCH_FLAG 120 //  [2] broadcast scalars
+#define XCH_SIZE 128
+// stage records start at W_SD(W)
+#define W_SD_OF(W) (148 + ((W) > 1 ? XCH_SIZE : 0))
 // stage record
 #define SD_CF 0     // 5 coefficient 4-vectors over next-state rows (x,y,psi,v): columns psi | v | a | df of [A B], then r
 #define SD_R 16     //   r column (dynamics residual; record N: initial-condition residual)
@@ -134,7 +145,8 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define SDS 46      // even: records are 16-byte aligned
 #define KST_STRIDE 14
 
-MPC_HD int smem_doubles_per_warp(int N) { return W_SD + (N + 1) * SDS + N * KST_STRIDE; }
+MPC_HD int team_warps(int N) { return (N + 1 + 31) / 32; }   // warps that share one problem
+MPC_HD int smem_doubles_per_team(int N) { return W_SD_OF(team_warps(N)) + (N + 1) * SDS + N * KST_STRIDE; }
 
 MPC_DEV double dmax_(double a, double b) { return a > b ? a : b; }
 MPC_DEV double dmin_(double a, double b) { return a < b ? a : b; }
@@ -186,21 +198,110 @@ struct Recips { double vL, vU, aL, aU, dL, dU, r0L, r0U, r1L, r1U; };
 
 struct Result { int status; int iters; double cost; };
 
-struct WarpSolver {
+// W = warps per team (1: a warp per problem; 2, 3: a block per problem)
+template <int W>
+struct TeamSolver {
+    static constexpr int W_SD = W_SD_OF(W);   // first stage record
+    static constexpr int NFILT_MAX = 32 * W;  // one filter entry per thread
     const KCfg& c;
-    const smem_t sm;   // this warp's shared memory (opaque base)
-    const int k;       // lane = stage
+    const smem_t sm;   // this team's shared memory (opaque base)
+    const int k;       // thread of the team = stage
     const int N;
-    const bool isS, isU, isR;  // lane owns a state / an input / a rate row
+    const bool isS, isU, isR;  // thread owns a state / an input / a rate row
+    int xpar;                  // W > 1: parity of the exchange buffers
     double xr, yr, pr;         // this stage's reference sample
     double sigma;
     LaneState L;
     StepState D;
     EvalState ev;
 
-    MPC_DEV WarpSolver(const KCfg& cfg, smem_t smem)
-        : c(cfg), sm(smem), k(lane_id()), N(cfg.N), isS(lane_id() <= cfg.N), isU(lane_id() < cfg.N),
-          isR((lane_id() == 0 || lane_id() >= 2) && lane_id() < cfg.N) {}
+    MPC_DEV static int team_tid() { return (W == 1) ? lane_id() : thread_in_block(); }
+    MPC_DEV TeamSolver(const KCfg& cfg, smem_t smem)
+        : c(cfg), sm(smem), k(team_tid()), N(cfg.N), isS(team_tid() <= cfg.N), isU(team_tid() < cfg.N),
+          isR((team_tid() == 0 || team_tid() >= 2) && team_tid() < cfg.N), xpar(0) {}
+
+    // ------------------------------------------------------------------
+    // team collectives.  W == 1: plain warp shuffles.  W > 1: warp shuffles, then the values that
+    // cross a warp boundary go through the exchange area (double-buffered by `xpar`, so that one
+    // bar.sync per collective suffices).
+    // ------------------------------------------------------------------
+    MPC_DEV void tsync() { if (W == 1) syncwarp(); else block_sync(); }
+    MPC_DEV bool tall(bool p) { if (W == 1) return warp_all(p); else return block_all(p); }
+    MPC_DEV int xflip() { const int b = xpar; xpar ^= 1; return b; }
+    enum { OP_SUM = 0, OP_MAX = 1, OP_MIN = 2 };
+    template <int OP> MPC_DEV static double comb(double a, double b) {
+        if (OP == OP_SUM) return a + b;
+        if (OP == OP_MAX) return (b > a || b != b) ? b : a;   // NaN wins, like warp_max
+        return (b < a) ? b : a;
+    }
+    // all-reduce of n (<= 3) values at once (interleaved butterflies)
+    template <int OP, int n> MPC_DEV void treduce(double* v) {
+        MPC_NOUNROLL for (int o = 16; o; o >>= 1) {
+            double t[n];
+            for (int j = 0; j < n; j++) t[j] = shfl_xor(v[j], o);
+            for (int j = 0; j < n; j++) v[j] = comb<OP>(v[j], t[j]);
+        }
+        if (W > 1) {
+            const int base = SO(W_XCH + XCH_RED + xflip() * 12);
+            if (lane_id() == 0) for (int j = 0; j < n; j++) sts(sm, base + SO((k >> 5) * 4 + j), v[j]);
+            block_sync();
+            for (int j = 0; j < n; j++) {
+                double a = lds(sm, base + SO(j));
+                for (int w = 1; w < W; w++) a = comb<OP>(a, lds(sm, base + SO(w * 4 + j)));
+                v[j] = a;
+            }
+        }
+    }
+    MPC_DEV double tsum(double v) { treduce<OP_SUM, 1>(&v); return v; }
+    MPC_DEV double tmax(double v) { treduce<OP_MAX, 1>(&v); return v; }
+    MPC_DEV double tmin(double v) { treduce<OP_MIN, 1>(&v); return v; }
+    // inclusive suffix sums over stages of n (<= 2) values at once: out_k = sum_{j >= k} v_j
+    template <int n> MPC_DEV void tsuffix(double* v) {
+        const int l = lane_id();
+        MPC_NOUNROLL for (int o = 1; o < 32; o <<= 1) {
+            double t[n];
+            for (int j = 0; j < n; j++) t[j] = shfl_down(v[j], o);
+            if (l + o < 32) for (int j = 0; j < n; j++) v[j] += t[j];
+        }
+        if (W > 1) {
+            const int base = SO(W_XCH + XCH_RED + xflip() * 12);
+            if (l == 0) for (int j = 0; j < n; j++) sts(sm, base + SO((k >> 5) * 4 + j), v[j]);   // this warp's total
+            block_sync();
+            for (int w = W - 1; w > (k >> 5); w--) for (int j = 0; j < n; j++) v[j] += lds(sm, base + SO(w * 4 + j));
+        }
+    }
+    // neighbour exchange of nd values downwards (out = value of stage k+1) and nu values upwards
+    // (out = value of stage k-1) in one step.  wrapN >= 0: thread wrapN receives stage 0's `dn` values.
+    // Threads without that neighbour get an unspecified finite value.
+    template <int nd, int nu, bool WRAP> MPC_DEV void xchg(const double* dn, double* dn_out, const double* up, double* up_out, int wrapN = -1) {
+        if (W == 1) {
+            const int src = (k == wrapN) ? 0 : ((k + 1) & 31);
+            for (int j = 0; j < nd; j++) dn_out[j] = WRAP ? shfl(dn[j], src) : shfl_down(dn[j], 1);
+            for (int j = 0; j < nu; j++) up_out[j] = shfl_up(up[j], 1);
+        } else {
+            const int l = lane_id(), w = k >> 5;
+            for (int j = 0; j < nd; j++) dn_out[j] = shfl_down(dn[j], 1);
+            for (int j = 0; j < nu; j++) up_out[j] = shfl_up(up[j], 1);
+            const int b = xflip();
+            const int bd = SO(W_XCH + XCH_DN + b * 24), bu = SO(W_XCH + XCH_UP + b * 24);
+            if (l == 0) for (int j = 0; j < nd; j++) sts(sm, bd + SO(w * 8 + j), dn[j]);
+            if (l == 31) for (int j = 0; j < nu; j++) sts(sm, bu + SO(w * 8 + j), up[j]);
+            block_sync();
+            if (l == 31 && w + 1 < W) for (int j = 0; j < nd; j++) dn_out[j] = lds(sm, bd + SO((w + 1) * 8 + j));
+            if (l == 0 && w > 0) for (int j = 0; j < nu; j++) up_out[j] = lds(sm, bu + SO((w - 1) * 8 + j));
+            if (WRAP && k == wrapN) for (int j = 0; j < nd; j++) dn_out[j] = lds(sm, bd + SO(j));
+        }
+    }
+    template <int n> MPC_DEV void xnext(const double* in, double* out) { xchg<n, 0, false>(in, out, nullptr, nullptr); }
+    template <int n> MPC_DEV void xprev(const double* in, double* out) { xchg<0, n, false>(nullptr, nullptr, in, out); }
+    // value held by stage 0, for every thread
+    MPC_DEV double bcast0(double v) {
+        if (W == 1) return shfl(v, 0);
+        const int a = SO(W_XCH + XCH_FLAG + xflip());
+        if (k == 0) sts(sm, a, v);
+        block_sync();
+        return lds(sm, a);
+    }
 
     // cheap per-use reconstruction of lane constants (keeps them out of the register file)
     MPC_DEV double wx() const { return (k >= 1 && k <= N) ? c.w[0] : 0.0; }
@@ -212,7 +313,7 @@ struct WarpSolver {
     MPC_DEV int rec() const { return SO(W_SD + (isS ? k : 0) * SDS); }    // this lane's own stage record
 
     MPC_DEV static void init_work(smem_t sm, int N) {
-        const int l = lane_id();
+        const int l = team_tid();
         if (l < 6) { sts(sm, SO(W_EX + l), (l == 0) ? 1.0 : 0.0); sts(sm, SO(W_EY + l), (l == 1) ? 1.0 : 0.0); sts(sm, SO(W_Z + l), 0.0); }
         if (l < 4) sts(sm, SO(W_NC + l), 0.0);
         if (l < 2) sts(sm, SO(W_DUMMY + l), 0.0);
@@ -223,7 +324,7 @@ struct WarpSolver {
             sts(sm, r + SO(SD_CF + 15), 0.0);                                       // df column: (b0,b1,b2,0)
             sts(sm, r + SO(SD_ZERO), 0.0);
         }
-        syncwarp();
+        if (W == 1) syncwarp(); else block_sync();
     }
 
     MPC_DEV void recips(Recips& q) const {
@@ -271,13 +372,17 @@ struct WarpSolver {
         const double fy = sy + c.dt * (sv * ev.sn);
         const double fp = sp + c.dt * (sv / c.Lb * ev.sb);
         const double fv = sv + c.dt * ua;
-        // lane k < N takes s_{k+1}; lane N takes s_0 (for the initial-condition rows)
-        const int src = (k == N) ? 0 : ((k + 1) & 31);
-        const double nx = shfl(sx, src), ny = shfl(sy, src), np = shfl(sp, src), nv = shfl(sv, src);
+        // thread k < N takes s_{k+1}; thread N takes s_0 (for the initial-condition rows); every thread u_{k-1}
+        double nxt[4], prv[2];
+        {
+            const double dn[4] = {sx, sy, sp, sv}, up[2] = {ua, ud};
+            xchg<4, 2, true>(dn, nxt, up, prv, N);
+        }
+        const double nx = nxt[0], ny = nxt[1], np = nxt[2], nv = nxt[3];
         if (isU) { ev.rd[0] = fx - nx; ev.rd[1] = fy - ny; ev.rd[2] = fp - np; ev.rd[3] = fv - nv; }
         else if (k == N) { ev.rd[0] = cst(0) - nx; ev.rd[1] = cst(1) - ny; ev.rd[2] = cst(2) - np; ev.rd[3] = cst(3) - nv; }
         else { ev.rd[0] = ev.rd[1] = ev.rd[2] = ev.rd[3] = 0.0; }
-        const double pa = shfl_up(ua, 1), pd = shfl_up(ud, 1);
+        const double pa = prv[0], pd = prv[1];
         const bool l0 = (k == 0);
         const double ba = l0 ? cst(5) : pa, bd = l0 ? cst(4) : pd;
         ev.dr[0] = isR ? (ud - bd) - s0 : 0.0;
@@ -298,18 +403,22 @@ struct WarpSolver {
         if (isR) { const double h0 = rHi(0), h1 = rHi(1); p *= (s0 + h0) * (h0 - s0) * (s1 + h1) * (h1 - s1); }
         double lb = log(p);
         double th = fabs(ev.rd[0]) + fabs(ev.rd[1]) + fabs(ev.rd[2]) + fabs(ev.rd[3]) + fabs(ev.dr[0]) + fabs(ev.dr[1]);
-        MPC_NOUNROLL for (int o = 16; o; o >>= 1) { f += shfl_xor(f, o); lb += shfl_xor(lb, o); th += shfl_xor(th, o); }
-        ev.f = f; ev.lb = lb; ev.theta = th;
+        double r3[3] = {f, lb, th};
+        treduce<OP_SUM, 3>(r3);
+        ev.f = r3[0]; ev.lb = r3[1]; ev.theta = r3[2];
     }
 
     // scaled objective gradient at the current iterate (recomputed where needed: cheaper than six
     // doubles kept alive across the Riccati passes)
     struct Grad { double x, y, p, v, a, d; };
-    MPC_DEV Grad objective_gradient() const {
+    MPC_DEV Grad objective_gradient() {
         Grad g;
-        const int src = (k + 1) & 31;
-        const double na = shfl(L.ua, src), nd = shfl(L.ud, src);
-        const double pa = shfl_up(L.ua, 1), pd = shfl_up(L.ud, 1);
+        double nxt[2], prv[2];
+        {
+            const double u[2] = {L.ua, L.ud};
+            xchg<2, 2, false>(u, nxt, u, prv);
+        }
+        const double na = nxt[0], nd = nxt[1], pa = prv[0], pd = prv[1];
         const double s2 = 2.0 * sigma;
         g.x = s2 * wx() * (L.sx - xr);
         g.y = s2 * wy() * (L.sy - yr);
@@ -348,7 +457,9 @@ struct WarpSolver {
             if (isU) { gua = ga - L.zaL + L.zaU; gud = gd - L.zdL + L.zdU; }
         } else {
             // multipliers of the rows leaving this stage (held by lane k+1)
-            const double y1x = shfl_down(L.yx, 1), y1y = shfl_down(L.yy, 1), y1p = shfl_down(L.yp, 1);
+            double y1[3];
+            { const double y[3] = {L.yx, L.yy, L.yp}; xnext<3>(y, y1); }
+            const double y1x = y1[0], y1y = y1[1], y1p = y1[2];
             double hpp = 0.0, hdd = 0.0;
             if (isU) {
                 const double v = L.sv, dt = c.dt;
@@ -386,7 +497,9 @@ struct WarpSolver {
             if (isU) { gua = ga + ba; gud = gd + bd; }
         }
         // rate-row terms: +w of the row ending at u_k, -w of the row ending at u_{k+1}
-        const double wn0 = shfl_down(wrow[0], 1), wn1 = shfl_down(wrow[1], 1);
+        double wn[2];
+        xnext<2>(wrow, wn);
+        const double wn0 = wn[0], wn1 = wn[1];
         if (isU) {
             gua += wrow[1] - ((k + 1 < N) ? wn1 : 0.0);
             gud += wrow[0] - ((k + 1 < N) ? wn0 : 0.0);
@@ -429,7 +542,18 @@ struct WarpSolver {
     //   round E: Fuu^{-1} (every lane), gains K, cost-to-go P <- F_xixi + F_xi,u K   (27 lanes)
     // ------------------------------------------------------------------
     MPC_DEV bool riccati_backward() {
-        const int l = k;
+        if (W == 1) return riccati_backward_warp();
+        // long horizons: the recursion is serial in the stages, so warp 0 runs it while the other
+        // warps of the team wait at the barrier that also publishes the inertia verdict
+        bool ok = true;
+        if ((k >> 5) == 0) ok = riccati_backward_warp();
+        const int a = SO(W_XCH + XCH_FLAG + xflip());
+        if (k == 0) sts(sm, a, ok ? 1.0 : 0.0);
+        block_sync();
+        return lds(sm, a) != 0.0;
+    }
+    MPC_DEV bool riccati_backward_warp() {
+        const int l = lane_id();
         // lane roles: shared-memory offsets, recomputed per call and laundered so that they stay in
         // registers through the stage loop instead of being rematerialised at every use
         int a_p, a_m, a_ex, a_out, b_m, b_mk, b_t, b_x, b_h, b_o1, b_o2, e_f0, e_fi, e_fj, e_o1, e_o2, e_k0, e_k1;
@@ -605,16 +729,20 @@ struct WarpSolver {
         const double hasn = isU ? 1.0 : 0.0;
         const d2 c0 = lds2(sm, r + SO(SD_CF + 0)), c1 = lds2(sm, r + SO(SD_CF + 4));   // (A02, A12), (A03, A13)
         const double A23 = lds(sm, r + SO(SD_CF + 6));
-        MPC_NOUNROLL for (int o = 1; o < 32; o <<= 1) {   // y_x, y_y: two interleaved suffix sums
-            const double tx = shfl_down(lx, o), ty = shfl_down(ly, o);
-            if (k + o < 32) { lx += tx; ly += ty; }
-        }
-        D.nyx = lx; D.nyy = ly;
-        const double nx1 = shfl_down(lx, 1), ny1 = shfl_down(ly, 1);
-        D.nyp = warp_suffix_sum(lp + hasn * (c0.x * nx1 + c0.y * ny1), k);
-        const double np1 = shfl_down(D.nyp, 1);
-        D.nyv = warp_suffix_sum(lv + hasn * (c1.x * nx1 + c1.y * ny1 + A23 * np1), k);
-        const double pa = shfl_up(D.dua, 1), pd = shfl_up(D.dud, 1);
+        double lxy[2] = {lx, ly}, n1[2];
+        tsuffix<2>(lxy);   // y_x, y_y: two interleaved suffix sums
+        D.nyx = lxy[0]; D.nyy = lxy[1];
+        xnext<2>(lxy, n1);
+        const double nx1 = n1[0], ny1 = n1[1];
+        double t1 = lp + hasn * (c0.x * nx1 + c0.y * ny1);
+        tsuffix<1>(&t1);
+        D.nyp = t1;
+        double np1, prv[2];
+        { const double du[2] = {D.dua, D.dud}; xchg<1, 2, false>(&t1, &np1, du, prv); }
+        t1 = lv + hasn * (c1.x * nx1 + c1.y * ny1 + A23 * np1);
+        tsuffix<1>(&t1);
+        D.nyv = t1;
+        const double pa = prv[0], pd = prv[1];
         D.drs[0] = D.drs[1] = 0.0; D.nyd[0] = D.nyd[1] = 0.0;
         if (isR) {
             const double ba = (k == 0) ? 0.0 : pa, bd = (k == 0) ? 0.0 : pd;
@@ -627,7 +755,7 @@ struct WarpSolver {
     }
 
     // fraction-to-the-boundary for the primal step: tau / max_i( -dx_i / slack_i ), division-free per element
-    MPC_DEV double alpha_primal(double tau) const {
+    MPC_DEV double alpha_primal(double tau) {
         double num = 0.0, den = 1.0;   // largest ratio num/den (num >= 0, den > 0) by cross-multiplication
         auto upd = [&](double dx, double sl, double su) {
             const double n = fabs(dx), d = (dx < 0.0) ? sl : su;
@@ -637,7 +765,7 @@ struct WarpSolver {
         if (isU) { upd(D.dua, L.ua - c.aLo, c.aHi - L.ua); upd(D.dud, L.ud - c.dLo, c.dHi - L.ud); }
         if (isR) { const double h0 = rHi(0), h1 = rHi(1); upd(D.drs[0], L.rs[0] + h0, h0 - L.rs[0]); upd(D.drs[1], L.rs[1] + h1, h1 - L.rs[1]); }
         const double a = (num > 0.0) ? tau * den / num : 1.0;  // num == 0: no limit from this lane
-        return dmin_(1.0, warp_min(a));
+        return dmin_(1.0, tmin(a));
     }
 
     MPC_DEV bool nlp_feasible() const {
@@ -671,14 +799,16 @@ struct WarpSolver {
         {
             const Grad g = objective_gradient();
             double gm = dmax_(dmax_(fabs(g.x), fabs(g.y)), dmax_(fabs(g.p), fabs(g.v)));
-            gm = warp_max(dmax_(gm, dmax_(fabs(g.a), fabs(g.d))));
+            gm = tmax(dmax_(gm, dmax_(fabs(g.a), fabs(g.d))));
             sigma = (gm > K_SCALE_MAX_GRAD) ? dmax_(K_SCALE_MAX_GRAD / gm, 1e-8) : 1.0;
         }
         if (feasible) {
             // ---- push into the interior, slacks = d(x) pushed, bound multipliers = 1
             if (isS) push_interior(L.sv, c.vLo, c.vHi);
             if (isU) { push_interior(L.ua, c.aLo, c.aHi); push_interior(L.ud, c.dLo, c.dHi); }
-            const double pa = shfl_up(L.ua, 1), pd = shfl_up(L.ud, 1);
+            double prv[2];
+            { const double u[2] = {L.ua, L.ud}; xprev<2>(u, prv); }
+            const double pa = prv[0], pd = prv[1];
             if (isR) {
                 const double h0 = rHi(0), h1 = rHi(1);
                 L.rs[0] = L.ud - ((k == 0) ? cst(4) : pd);
@@ -713,10 +843,10 @@ struct WarpSolver {
             // ================= shared heavy work =================
             if (do_solve) {
                 assemble(req, mu, dw);
-                syncwarp();
+                tsync();
                 solve_ok = riccati_backward();
                 if (solve_ok) { riccati_forward(); recover_duals(); }
-                syncwarp();
+                tsync();
             }
             if (do_eval) {
                 if (eval_ftb) { ev_alpha = alpha_primal(tau); a_soc = ev_alpha; }
@@ -747,7 +877,7 @@ struct WarpSolver {
                         }
                     }
                     const bool mine = (k >= nfilt) || cmp_le(ph_t, f_phi, f_phi) || cmp_le(th_t, f_theta, f_theta);
-                    ok = warp_all(mine) && ok;
+                    ok = tall(mine) && ok;
                 }
                 if (!ok) {
                     bool want_soc = false;
@@ -766,7 +896,7 @@ struct WarpSolver {
                             sts(sm, r + SO(SD_DR), a_soc * lds(sm, r + SO(SD_DR)) + ev.dr[0]);
                             sts(sm, r + SO(SD_DR + 1), a_soc * lds(sm, r + SO(SD_DR + 1)) + ev.dr[1]);
                         }
-                        syncwarp();
+                        tsync();
                         phase = PH_SOC; do_solve = true; req = 3; do_eval = true; eval_ftb = true;
                         continue;
                     }
@@ -790,7 +920,7 @@ struct WarpSolver {
                 }
                 // ---------------- accepted ----------------
                 if (phase == PH_SOC) alpha = a_soc;
-                if (!tiny && !(ftype && arm) && nfilt < 32) {
+                if (!tiny && !(ftype && arm) && nfilt < NFILT_MAX) {
                     if (k == nfilt) { f_phi = phi - K_GAMMA_PHI * theta; f_theta = (1.0 - K_GAMMA_THETA) * theta; }
                     nfilt++;
                 }
@@ -812,7 +942,7 @@ struct WarpSolver {
                     auto lim = [&](double z, double dz) { if (dz < 0.0 && -dz * den > num * z) { num = -dz; den = z; } };
                     lim(L.zvL, dzvL); lim(L.zvU, dzvU); lim(L.zaL, dzaL); lim(L.zaU, dzaU); lim(L.zdL, dzdL); lim(L.zdU, dzdU);
                     lim(L.rvL[0], drvL[0]); lim(L.rvU[0], drvU[0]); lim(L.rvL[1], drvL[1]); lim(L.rvU[1], drvU[1]);
-                    const double az = dmin_(1.0, warp_min(num > 0.0 ? tau * den / num : 1.0));
+                    const double az = dmin_(1.0, tmin(num > 0.0 ? tau * den / num : 1.0));
                     // primal, equality multipliers (primal step size), bound multipliers (dual step size)
                     L.sx += alpha * D.dsx; L.sy += alpha * D.dsy; L.sp += alpha * D.dsp; L.sv += alpha * D.dsv;
                     L.ua += alpha * D.dua; L.ud += alpha * D.dud; L.rs[0] += alpha * D.drs[0]; L.rs[1] += alpha * D.drs[1];
@@ -851,7 +981,7 @@ struct WarpSolver {
                 if (solve_ok) {
                     double ym = dmax_(dmax_(fabs(D.nyx), fabs(D.nyy)), dmax_(fabs(D.nyp), fabs(D.nyv)));
                     ym = dmax_(ym, dmax_(fabs(D.nyd[0]), fabs(D.nyd[1])));
-                    ym = warp_max(isS ? ym : 0.0);
+                    ym = tmax(isS ? ym : 0.0);
                     use = (ym <= K_Y_INIT_MAX);
                 }
                 if (use && isS) { L.yx = D.nyx; L.yy = D.nyy; L.yp = D.nyp; L.yv = D.nyv; L.ryd[0] = D.nyd[0]; L.ryd[1] = D.nyd[1]; }
@@ -866,8 +996,9 @@ struct WarpSolver {
                 const double b0 = A02 * ev.b1, b1v = A12 * ev.b1, b2v = isU ? c.dt * L.sv * ev.cb * ev.b1 / c.Lb : 0.0;
                 double di, cv, cm0, cmm, sumy, sumz;
                 {
-                    const double y1x = shfl_down(L.yx, 1), y1y = shfl_down(L.yy, 1), y1p = shfl_down(L.yp, 1), y1v = shfl_down(L.yv, 1);
-                    const double yd1_0 = shfl_down(L.ryd[0], 1), yd1_1 = shfl_down(L.ryd[1], 1);
+                    double y1[6];
+                    { const double y[6] = {L.yx, L.yy, L.yp, L.yv, L.ryd[0], L.ryd[1]}; xnext<6>(y, y1); }
+                    const double y1x = y1[0], y1y = y1[1], y1p = y1[2], y1v = y1[3], yd1_0 = y1[4], yd1_1 = y1[5];
                     const double hn = isU ? 1.0 : 0.0;
                     const double glx = gx + L.yx - hn * y1x;
                     const double gly = gy + L.yy - hn * y1y;
@@ -884,7 +1015,9 @@ struct WarpSolver {
                     cv = dmax_(cv, dmax_(fabs(ev.dr[0]), fabs(ev.dr[1])));
                     sumy = isS ? fabs(L.yx) + fabs(L.yy) + fabs(L.yp) + fabs(L.yv) + fabs(L.ryd[0]) + fabs(L.ryd[1]) : 0.0;
                     sumz = L.zvL + L.zvU + L.zaL + L.zaU + L.zdL + L.zdU + L.rvL[0] + L.rvL[1] + L.rvU[0] + L.rvU[1];
-                    MPC_NOUNROLL for (int o = 16; o; o >>= 1) { sumy += shfl_xor(sumy, o); sumz += shfl_xor(sumz, o); }
+                    double r2[2] = {sumy, sumz};
+                    treduce<OP_SUM, 2>(r2);
+                    sumy = r2[0]; sumz = r2[1];
                 }
                 const double sd = dmax_(K_S_MAX, (sumy + sumz) / (double)(my + nz)) / K_S_MAX;
                 const double sc = dmax_(K_S_MAX, sumz / (double)nz) / K_S_MAX;
@@ -905,14 +1038,17 @@ struct WarpSolver {
                 cm0 = compl_local(0.0); cmm = compl_local(mu);
                 // E_0 and E_mu in one pass
                 const double dcv = dmax_(di / sd, cv);
-                double e0 = dmax_(dcv, cm0 / sc), em = dmax_(dcv, cmm / sc);
-                MPC_NOUNROLL for (int o = 16; o; o >>= 1) {
-                    const double t0 = shfl_xor(e0, o), t1 = shfl_xor(em, o);
-                    e0 = (t0 > e0 || t0 != t0) ? t0 : e0; em = (t1 > em || t1 != t1) ? t1 : em;
+                double e0, em;
+                {
+                    double r2[2] = {dmax_(dcv, cm0 / sc), dmax_(dcv, cmm / sc)};
+                    treduce<OP_MAX, 2>(r2);
+                    e0 = r2[0]; em = r2[1];
                 }
                 // ---- convergence (OptimalityErrorConvergenceCheck)
                 if (e0 <= dmax_(K_ACCEPT_TOL, c.tol)) {   // the unscaled checks need three more reductions: only near the end
-                    const double du = warp_max(di) / sigma, cvm = warp_max(cv), mc = warp_max(cm0) / sigma;
+                    double r3[3] = {di, cv, cm0};
+                    treduce<OP_MAX, 3>(r3);
+                    const double du = r3[0] / sigma, cvm = r3[1], mc = r3[2] / sigma;
                     if (e0 <= c.tol && du <= 1.0 && cvm <= 1e-4 && mc <= 1e-4) { ret = 0; break; }
                     if (e0 <= K_ACCEPT_TOL && du <= 1e10 && cvm <= 1e-2 && mc <= 1e-2) { if (++accept_count >= K_ACCEPT_ITER) { ret = 1; break; } }
                     else accept_count = 0;
@@ -920,7 +1056,7 @@ struct WarpSolver {
                 if (iter >= c.max_iter) { ret = -1; break; }
                 {
                     const double xm = dmax_(dmax_(fabs(L.sx), fabs(L.sy)), dmax_(fabs(L.sp), fabs(L.sv)));
-                    if (!warp_all(!isS || xm <= 1e20)) { ret = -5; break; }
+                    if (!tall(!isS || xm <= 1e20)) { ret = -5; break; }
                 }
                 // ---- monotone barrier update
                 for (;;) {
@@ -930,7 +1066,7 @@ struct WarpSolver {
                     mu = nm; tau = dmax_(K_TAU_MIN, 1.0 - mu);
                     nfilt = 0;
                     if (tiny_last) { tiny_last = false; break; }
-                    em = warp_max(dmax_(dcv, compl_local(mu) / sc));
+                    em = tmax(dmax_(dcv, compl_local(mu) / sc));
                 }
                 if (ret == -3) break;
                 dw = 0.0;
@@ -985,8 +1121,8 @@ struct WarpSolver {
                         t += brr.x * drr.x - srw.x * drr.x * (D.drs[0] - drr.x);
                         t += brr.y * drr.y - srw.y * drr.y * (D.drs[1] - drr.y);
                     }
-                    gBd = warp_sum(t);
-                    tiny = warp_all(tl) && (theta < 1e-4);
+                    gBd = tsum(t);
+                    tiny = tall(tl) && (theta < 1e-4);
                 }
                 if (theta_max < 0.0) { theta_max = 1e4 * dmax_(1.0, theta); theta_min = 1e-4 * dmax_(1.0, theta); }
                 // switching-condition ratio theta^s_theta / (-gBd)^s_phi: a threshold test, single precision suffices
@@ -1005,14 +1141,16 @@ struct WarpSolver {
             if (isU) { L.ua = dmin_(dmax_(L.ua, -c.amax), c.amax); L.ud = dmin_(dmax_(L.ud, -c.smax), c.smax); }
         }
         {   // unscaled objective at the returned point
-            const double pa = shfl_up(L.ua, 1), pd = shfl_up(L.ud, 1);
+            double prv[2];
+            { const double u[2] = {L.ua, L.ud}; xprev<2>(u, prv); }
+            const double pa = prv[0], pd = prv[1];
             const double ex = L.sx - xr, ey = L.sy - yr, ep = L.sp - pr, evv = L.sv - cst(6);
             double f = wx() * ex * ex + wy() * ey * ey + wp() * ep * ep + wv() * evv * evv;
             if (isU) {
                 f += c.w[6] * L.ua * L.ua + c.w[7] * L.ud * L.ud;
                 if (k >= 1) { const double da = L.ua - pa, dd = L.ud - pd; f += c.w[4] * da * da + c.w[5] * dd * dd; }
             }
-            res.cost = warp_sum(f);
+            res.cost = tsum(f);
         }
         return res;
     }
@@ -1032,8 +1170,9 @@ struct BatchPtrs {
     double* traj;          // [B][6N+4] or null
 };
 
+template <int W>
 MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t smem) {
-    WarpSolver S(cfg, smem);
+    TeamSolver<W> S(cfg, smem);
     const int k = S.k, N = cfg.N;
     const long nr = 3L * (N + 1), nt = 6L * N + 4;
     // ---- coalesced loads: lane k takes stage k's reference sample; lanes 0..6 the problem constants
@@ -1047,7 +1186,7 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t 
         else if (k < 6) cv = io.u_prev[2 * b + (k - 4)];
         else if (k == 6) cv = io.v_des ? io.v_des[b] : 0.0;
         if (k < 8) sts(smem, SO(W_CONST + k), cv);
-        syncwarp();
+        S.tsync();
     }
     // ---- start point
     S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;
@@ -1058,7 +1197,7 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t 
     }
     const Result r = S.solve();
     // ---- results
-    const double a0 = shfl(S.L.ua, 0), d0 = shfl(S.L.ud, 0);
+    const double a0 = S.bcast0(S.L.ua), d0 = S.bcast0(S.L.ud);
     if (k == 0) {
         io.u0[2 * b] = a0; io.u0[2 * b + 1] = d0;
         if (io.cost) io.cost[b] = r.cost;
@@ -1072,7 +1211,7 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t 
         if (k <= N) { t[k] = S.L.sx; t[(N + 1) + k] = S.L.sy; t[2 * (N + 1) + k] = S.L.sv; t[3 * (N + 1) + k] = S.L.sp; }
         if (k < N) { t[4 * (N + 1) + k] = S.L.ud; t[4 * (N + 1) + N + k] = S.L.ua; }
     }
-    syncwarp();
+    S.tsync();
 }
 
 
@@ -1176,7 +1315,7 @@ MPC_DEV double sel8(const double* v, int i) {   // register-friendly v[i] for a 
 }
 
 MPC_DEV void rollout_vehicle(const KCfg& cfg, const RolloutArgs& a, long b, smem_t smem) {
-    WarpSolver S(cfg, smem);
+    TeamSolver<1> S(cfg, smem);
     const int k = S.k, N = cfg.N;
     const PathTable& path = a.paths[a.path_of[b]];
     double st[8] = {a.pose0[3 * b], a.pose0[3 * b + 1], a.pose0[3 * b + 2], 0, 0, 0, 0, 0};

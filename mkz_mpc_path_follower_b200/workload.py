@@ -67,3 +67,16 @@ def make_batch(B, N, path_ids=(1, 2, 3), dt=0.2, b0=0, v_des=1.0):
         "u_prev": np.ascontiguousarray(u_prev), "v_des": np.full(B, float(v_des)),
         "path": pid.astype(np.int32), "idx": idx,
     }
+
+
+def reference_start(batch, N):
+    """A start point in get_solver_results order (x, y, v, psi, d_f, acc) that follows the reference
+    waypoints at the measured speed with zero inputs -- what a caller without a previous solution
+    would pass as `warm` for long horizons, where the all-zero `start=0.0` point is far away."""
+    B = batch["state"].shape[0]
+    w = np.zeros((B, 6 * N + 4))
+    w[:, 0:N + 1] = batch["ref"][:, 0]
+    w[:, N + 1:2 * (N + 1)] = batch["ref"][:, 1]
+    w[:, 2 * (N + 1):3 * (N + 1)] = batch["state"][:, 3:4]
+    w[:, 3 * (N + 1):4 * (N + 1)] = batch["ref"][:, 2]
+    return w

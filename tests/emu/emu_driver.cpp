@@ -13,21 +13,22 @@ static void trampoline(int lane) {
     w->fn(lane, w->arg);
     w->done[lane] = 1;
     // hand over to the next unfinished lane, or back to main when all are done
-    for (int i = 1; i <= 32; i++) {
-        int c = (lane + i) & 31;
+    for (int i = 1; i <= w->nl; i++) {
+        int c = (lane + i) % w->nl;
         if (!w->done[c]) { w->cur = c; setcontext(&w->ctx[c]); }
     }
     setcontext(&w->main_ctx);
 }
 
-void run_warp(void (*fn)(int, void*), void* arg) {
-    Warp w;
+void run_warp(void (*fn)(int, void*), void* arg, int warps) {
+    static thread_local Warp w;
     memset(&w, 0, sizeof(w));
     const size_t STK = 1 << 18;
-    w.stacks = (char*)malloc(32 * STK);
+    w.nl = 32 * warps;
+    w.stacks = (char*)malloc(w.nl * STK);
     w.fn = fn; w.arg = arg;
     W = &w;
-    for (int l = 0; l < 32; l++) {
+    for (int l = 0; l < w.nl; l++) {
         getcontext(&w.ctx[l]);
         w.ctx[l].uc_stack.ss_sp = w.stacks + l * STK;
         w.ctx[l].uc_stack.ss_size = STK;
@@ -44,10 +45,10 @@ void run_warp(void (*fn)(int, void*), void* arg) {
 using namespace mpcb200;
 
 struct Job { const KCfg* cfg; const BatchPtrs* io; long b; double* smem; };
-static void lane_main(int, void* a) {
+template <int W> static void lane_main(int, void* a) {
     Job* j = (Job*)a;
-    WarpSolver::init_work(j->smem, j->cfg->N);
-    solve_problem(*j->cfg, *j->io, j->b, j->smem);
+    TeamSolver<W>::init_work(j->smem, j->cfg->N);
+    solve_problem<W>(*j->cfg, *j->io, j->b, j->smem);
 }
 
 extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, const double* ref, const double* v_des,
@@ -56,12 +57,13 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
     BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj};
     KCfg kc = *cfg;
     kcfg_finalize(kc);
-    std::vector<double> smem_raw(4096 + 2, 0.0);
+    std::vector<double> smem_raw(smem_doubles_per_team(kc.N) + 2, 0.0);
     double* smem = smem_raw.data();
     if (((size_t)smem) & 15) smem++;   // 16-byte alignment like the device's shared memory
+    const int W = team_warps(kc.N);
     for (long b = 0; b < B; b++) {
         Job j{&kc, &io, b, smem};
-        emu::run_warp(lane_main, &j);
+        emu::run_warp(W == 1 ? lane_main<1> : W == 2 ? lane_main<2> : lane_main<3>, &j, W);
     }
     return 0;
 }
@@ -70,7 +72,7 @@ extern "C" int emu_kcfg_size() { return (int)sizeof(KCfg); }
 struct RJob { const KCfg* cfg; const RolloutArgs* a; long b; double* smem; };
 static void lane_rollout(int, void* p) {
     RJob* j = (RJob*)p;
-    WarpSolver::init_work(j->smem, j->cfg->N);
+    TeamSolver<1>::init_work(j->smem, j->cfg->N);
     rollout_vehicle(*j->cfg, *j->a, j->b, j->smem);
 }
 extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, const int* path_of, int n0, const double* t,

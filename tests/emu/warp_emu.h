@@ -1,7 +1,8 @@
-// warp_emu.h -- TEST ONLY.  Single-threaded emulation of one 32-lane warp with ucontext
-// coroutines, so that mkz_mpc_path_follower_b200/csrc/mpc_kernel.cuh can be compiled by g++
-// and stepped on a CPU.  Every collective is a rendezvous of all 32 lanes (full mask), checked
-// by call-site id.  Never part of the shipped library.
+// warp_emu.h -- TEST ONLY.  Single-threaded emulation of one thread block of 1..3 warps with
+// ucontext coroutines, so that mkz_mpc_path_follower_b200/csrc/mpc_kernel.cuh can be compiled by
+// g++ and stepped on a CPU.  Every warp collective is a rendezvous of the 32 lanes of the calling
+// lane's warp (full mask), checked by call-site id; block barriers wait for every lane of the
+// block.  Lanes run round-robin, each up to its next collective.  Never part of the shipped library.
 #pragma once
 #include <math.h>
 #include <stdio.h>
@@ -15,15 +16,19 @@
 
 namespace mpcb200 {
 namespace emu {
+#define MPC_EMU_MAX_LANES 96
 struct Warp {
-    ucontext_t main_ctx, ctx[32];
+    ucontext_t main_ctx, ctx[MPC_EMU_MAX_LANES];
     char* stacks;
-    int cur;          // running lane
-    int done[32];
-    double dslot[2][32];
-    int islot[2][32];
-    int site[2][32];
-    int epoch[32];    // per-lane collective counter
+    int nl;           // lanes in the block (32 * warps)
+    int cur;          // running lane (= thread index in the block)
+    int done[MPC_EMU_MAX_LANES];
+    double dslot[2][MPC_EMU_MAX_LANES];
+    int islot[2][MPC_EMU_MAX_LANES];
+    int site[2][MPC_EMU_MAX_LANES];
+    int epoch[MPC_EMU_MAX_LANES];    // per-lane warp-collective counter
+    long arrive[MPC_EMU_MAX_LANES];  // per-lane block-barrier counter
+    int bpred[2][MPC_EMU_MAX_LANES];
     void (*fn)(int lane, void* arg);
     void* arg;
 };
@@ -33,7 +38,7 @@ inline void yield_next() {
     Warp* w = W;
     int from = w->cur;
     int to = from;
-    for (int i = 1; i <= 32; i++) { int c = (from + i) & 31; if (!w->done[c]) { to = c; break; } }
+    for (int i = 1; i <= w->nl; i++) { int c = (from + i) % w->nl; if (!w->done[c]) { to = c; break; } }
     if (to == from) return;
     w->cur = to;
     swapcontext(&w->ctx[from], &w->ctx[to]);
@@ -51,27 +56,52 @@ inline void publish_i(int v, int site) {
 }
 inline void check_site(int b, int site) {
     Warp* w = W;
-    for (int i = 0; i < 32; i++) if (w->site[b][i] != site) {
+    const int w0 = w->cur & ~31;
+    for (int i = w0; i < w0 + 32; i++) if (w->site[b][i] != site) {
         fprintf(stderr, "warp_emu: divergent collective (lane %d at site %d, lane %d at site %d)\n", w->cur, site, i, w->site[b][i]);
         abort();
     }
 }
-void run_warp(void (*fn)(int, void*), void* arg);
+void run_warp(void (*fn)(int, void*), void* arg, int warps = 1);
+// block barrier: every lane of the block arrives; lanes of other warps keep taking turns meanwhile
+inline long block_arrive() {
+    Warp* w = W; const int l = w->cur;
+    const long gen = ++w->arrive[l];
+    for (;;) {
+        bool all = true;
+        for (int i = 0; i < w->nl; i++) if (w->arrive[i] < gen) { all = false; break; }
+        if (all) break;
+        yield_next();
+    }
+    return gen;
+}
 }  // namespace emu
 
-MPC_DEV int lane_id() { return emu::W->cur; }
-#define MPC_EMU_COLLECTIVE_D(expr_src)                                   \
-    emu::Warp* w = emu::W; int l = w->cur; int b = w->epoch[l] & 1;      \
-    emu::publish_d(v, __LINE__); emu::check_site(b, __LINE__);           \
-    w->epoch[l]++; int s_ = (expr_src);
-MPC_DEV double shfl(double v, int src) { MPC_EMU_COLLECTIVE_D(src & 31) return w->dslot[b][s_]; }
-MPC_DEV double shfl_down(double v, int d) { MPC_EMU_COLLECTIVE_D(l + d) return s_ < 32 ? w->dslot[b][s_] : v; }
-MPC_DEV double shfl_up(double v, int d) { MPC_EMU_COLLECTIVE_D(l - d) return s_ >= 0 ? w->dslot[b][s_] : v; }
-MPC_DEV double shfl_xor(double v, int m) { MPC_EMU_COLLECTIVE_D(l ^ m) return w->dslot[b][s_]; }
+MPC_DEV int lane_id() { return emu::W->cur & 31; }
+MPC_DEV int thread_in_block() { return emu::W->cur; }
+MPC_DEV void block_sync() { emu::block_arrive(); }
+MPC_DEV bool block_all(bool p) {
+    emu::Warp* w = emu::W; const int l = w->cur;
+    const int b = (int)((w->arrive[l] + 1) & 1);
+    w->bpred[b][l] = p ? 1 : 0;
+    emu::block_arrive();
+    int r = 1; for (int i = 0; i < w->nl; i++) r &= w->bpred[b][i];
+    return r != 0;
+}
+// l = lane within the warp, w0 = first lane of the warp
+#define MPC_EMU_COLLECTIVE_D(expr_src)                                          \
+    emu::Warp* w = emu::W; int t_ = w->cur; int b = w->epoch[t_] & 1;           \
+    const int w0 = t_ & ~31; const int l = t_ & 31; (void)l;                    \
+    emu::publish_d(v, __LINE__); emu::check_site(b, __LINE__);                  \
+    w->epoch[t_]++; int s_ = (expr_src);
+MPC_DEV double shfl(double v, int src) { MPC_EMU_COLLECTIVE_D(src & 31) return w->dslot[b][w0 + s_]; }
+MPC_DEV double shfl_down(double v, int d) { MPC_EMU_COLLECTIVE_D(l + d) return s_ < 32 ? w->dslot[b][w0 + s_] : v; }
+MPC_DEV double shfl_up(double v, int d) { MPC_EMU_COLLECTIVE_D(l - d) return s_ >= 0 ? w->dslot[b][w0 + s_] : v; }
+MPC_DEV double shfl_xor(double v, int m) { MPC_EMU_COLLECTIVE_D(l ^ m) return w->dslot[b][w0 + s_]; }
 MPC_DEV int shfl(int v, int src) {
     emu::Warp* w = emu::W; int l = w->cur; int b = w->epoch[l] & 1;
     emu::publish_i(v, __LINE__); emu::check_site(b, __LINE__); w->epoch[l]++;
-    return w->islot[b][src & 31];
+    return w->islot[b][(l & ~31) + (src & 31)];
 }
 MPC_DEV void syncwarp() {
     emu::Warp* w = emu::W; int l = w->cur; int b = w->epoch[l] & 1;
@@ -80,12 +110,12 @@ MPC_DEV void syncwarp() {
 MPC_DEV bool warp_all(bool p) {
     emu::Warp* w = emu::W; int l = w->cur; int b = w->epoch[l] & 1;
     emu::publish_i(p ? 1 : 0, __LINE__); emu::check_site(b, __LINE__); w->epoch[l]++;
-    int r = 1; for (int i = 0; i < 32; i++) r &= w->islot[b][i]; return r != 0;
+    int r = 1; for (int i = (l & ~31); i < (l & ~31) + 32; i++) r &= w->islot[b][i]; return r != 0;
 }
 MPC_DEV bool warp_any(bool p) {
     emu::Warp* w = emu::W; int l = w->cur; int b = w->epoch[l] & 1;
     emu::publish_i(p ? 1 : 0, __LINE__); emu::check_site(b, __LINE__); w->epoch[l]++;
-    int r = 0; for (int i = 0; i < 32; i++) r |= w->islot[b][i]; return r != 0;
+    int r = 0; for (int i = (l & ~31); i < (l & ~31) + 32; i++) r |= w->islot[b][i]; return r != 0;
 }
 MPC_DEV void mpc_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 MPC_DEV float fast_log2(float x) { return log2f(x); }

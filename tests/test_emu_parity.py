@@ -32,3 +32,35 @@ def test_emulated_kernel_matches_oracle(oracle, N, B):
     e2 = E.solve_batch(E.kcfg_from_oracle(cfg), b["state"], b["ref"], b["v_des"], b["u_prev"], warm=warm_e)
     assert (o2["status"] == e2["status"]).all() and (o2["iters"] == e2["iters"]).all()
     assert np.abs(o2["u0"] - e2["u0"])[o2["status"] == 0].max() <= 1e-9
+
+
+@pytest.mark.parametrize("N,B", [(32, 3), (40, 6), (63, 3), (64, 3), (80, 4)])
+def test_emulated_long_horizon_team(oracle, N, B):
+    """N > 31: one block of 2 (N <= 63) or 3 warps per problem; the emulator steps all 64/96 threads,
+    bar.sync included.  Start = the reference waypoints (the all-zero start is hundreds of metres
+    away and rarely converges within the cap at these horizons)."""
+    import emu as E
+    cfg = oracle.default_cfg(N)
+    b = W.make_batch(B, N)
+    w0 = W.reference_start(b, N)
+    wo, we = w0.copy(), w0.copy()
+    o = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], warm=wo, n_threads=4)
+    e = E.solve_batch(E.kcfg_from_oracle(cfg), b["state"], b["ref"], b["v_des"], b["u_prev"], warm=we)
+    assert (o["status"] == 0).all() and (e["status"] == 0).all()
+    assert (o["iters"] == e["iters"]).all()
+    assert np.abs(o["u0"] - e["u0"]).max() <= 1e-9
+    assert (np.abs(o["cost"] - e["cost"]) <= 1e-9 * np.maximum(1, np.abs(o["cost"]))).all()
+    assert np.abs(wo - we).max() <= 1e-8   # the whole returned trajectory
+
+
+def test_emulated_long_horizon_zero_start(oracle):
+    import emu as E
+    N, B = 40, 3
+    cfg = oracle.default_cfg(N, max_iter=120)
+    b = W.make_batch(B, N)
+    o = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=4)
+    e = E.solve_batch(E.kcfg_from_oracle(cfg), b["state"], b["ref"], b["v_des"], b["u_prev"])
+    assert (o["status"] == e["status"]).all() and (o["iters"] == e["iters"]).all()
+    ok = o["status"] == 0
+    assert ok.any()
+    assert np.abs(o["u0"] - e["u0"])[ok].max() <= 1e-9
