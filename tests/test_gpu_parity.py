@@ -71,10 +71,10 @@ def test_long_horizon_block_per_problem(capi, oracle, N, B):
     nz = min(B, 24)
     g0 = s.solve_batch(b["state"][:nz], b["ref"][:nz], b["u_prev"][:nz], v_des=b["v_des"][:nz])
     o0 = oracle.solve_batch(ocfg, b["state"][:nz], b["ref"][:nz], b["v_des"][:nz], b["u_prev"][:nz], n_threads=8)
-    both = (g0["status"] == 0) & (o0["status"] == 0)
-    assert (g0["status"] != o0["status"]).sum() <= 3
-    short = both & (o0["iters"] < 100)
+    short = o0["iters"] < 100
+    assert (g0["status"][short] == o0["status"][short]).all()
     assert (g0["iters"][short] == o0["iters"][short]).all()
+    both = (g0["status"] == 0) & (o0["status"] == 0)
     if both.any():
         assert np.abs(g0["u0"] - o0["u0"])[both].max() <= U_TOL
 
@@ -134,7 +134,9 @@ def test_edge_cases(capi, oracle):
     with pytest.raises(ValueError):
         s.solve_batch(b["state"], b["ref"][:, :, :-1], b["u_prev"])
     with pytest.raises(capi.MpcB200Error):
-        capi.Solver(64)
+        capi.Solver(96)   # horizons up to 95 (three warps per problem)
+    with pytest.raises(capi.MpcB200Error):
+        capi.Solver(2)
     with pytest.raises(capi.MpcB200Error):
         s.set_cost([-1.0] * 8)
 
