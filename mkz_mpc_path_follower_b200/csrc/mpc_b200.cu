@@ -21,8 +21,11 @@ namespace {
 
 constexpr int WARPS_PER_BLOCK = 4;
 
+// 168 registers per thread: three blocks (12 warps) per SM at the N = 20 shared-memory footprint.
+// The iterate's bound multipliers, the step and the model evaluation live in per-thread shared-memory
+// fields (mpc_kernel.cuh, LF_*), which is what lets the solver fit.
 #ifndef MPC_MIN_BLOCKS
-#define MPC_MIN_BLOCKS 2
+#define MPC_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MPC_MIN_BLOCKS)
 mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned long long* counter) {
@@ -41,8 +44,13 @@ mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned
 }
 
 // Long horizons (32 <= N <= 95): one problem per block of W = 2 or 3 warps, thread k = stage k.
+// register budget (measured at N = 40 / 80): W = 2 -> 6 blocks (12 warps) per SM at 168 registers; W = 3 -> 2 blocks at 255
+#ifndef MPC_LONG_MIN_BLOCKS2
+#define MPC_LONG_MIN_BLOCKS2 6
+#define MPC_LONG_MIN_BLOCKS3 2
+#endif
 template <int W>
-__global__ void __launch_bounds__(W * 32, 1)
+__global__ void __launch_bounds__(W * 32, W == 2 ? MPC_LONG_MIN_BLOCKS2 : MPC_LONG_MIN_BLOCKS3)
 mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     __shared__ unsigned long long next_problem;
@@ -58,7 +66,7 @@ mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const long long B, uns
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MPC_MIN_BLOCKS)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2)
 mpc_rollout_kernel(const KCfg cfg, const RolloutArgs args, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;

@@ -145,8 +145,18 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define SDS 46      // even: records are 16-byte aligned
 #define KST_STRIDE 14
 
+// per-thread fields kept in shared memory instead of registers: field f of stage k at
+// W_LF + f * (N + 2) + min(k, N + 1)   (slot N + 1 is shared by the threads that own no stage)
+#define LF_EV 0     // 12: cos/sin(psi+beta), cos/sin(beta), beta', beta'', rd[4], dr[2] of the last evaluated point
+#define LF_REF 12   // 3: x_ref, y_ref, psi_ref
+#define LF_DX 15    // 6: primal step dsx, dsy, dsp, dsv, dua, dud
+#define LF_DRS 21   // 2: slack step of the rate row
+#define LF_DY 23    // 6: new equality / rate-row multipliers (y + dy)
+#define LF_Z 29     // 10: bound multipliers zvL, zvU, zaL, zaU, zdL, zdU, rvL[2], rvU[2]
+#define LF_FIELDS 39
 MPC_HD int team_warps(int N) { return (N + 1 + 31) / 32; }   // warps that share one problem
-MPC_HD int smem_doubles_per_team(int N) { return W_SD_OF(team_warps(N)) + (N + 1) * SDS + N * KST_STRIDE; }
+MPC_HD int lf_offset(int N) { return W_SD_OF(team_warps(N)) + (N + 1) * SDS + N * KST_STRIDE; }
+MPC_HD int smem_doubles_per_team(int N) { return (lf_offset(N) + LF_FIELDS * (N + 2) + 1) & ~1; }   // even: 16-byte alignment of the next team
 
 MPC_DEV double dmax_(double a, double b) { return a > b ? a : b; }
 MPC_DEV double dmin_(double a, double b) { return a < b ? a : b; }
@@ -175,11 +185,16 @@ MPC_DEV void push_interior(double& v, double lo, double hi) {
 }
 MPC_DEV bool cmp_le(double lhs, double rhs, double bas) { return lhs - rhs <= 10.0 * K_EPS * fabs(bas); }
 
+// The iterate: primal and equality multipliers stay in registers; the bound multipliers and the
+// step live in per-thread shared-memory fields and are loaded by the routines that use them.
 struct LaneState {
     double sx, sy, sp, sv, ua, ud;        // primal
     double yx, yy, yp, yv;                // multipliers of the equality rows that define s_k
-    double zvL, zvU, zaL, zaU, zdL, zdU;  // bound multipliers
-    double rs[2], ryd[2], rvL[2], rvU[2]; // rate row ending at u_k: [0] steering, [1] acceleration
+    double rs[2], ryd[2];                 // rate row ending at u_k: slack, multiplier; [0] steering, [1] acceleration
+};
+struct BoundMult {
+    double zvL, zvU, zaL, zaU, zdL, zdU;  // bound multipliers of v, acc, df
+    double rvL[2], rvU[2];                // ... of the rate-row slacks
 };
 struct StepState {
     double dsx, dsy, dsp, dsv, dua, dud;  // primal step
@@ -187,10 +202,12 @@ struct StepState {
     double nyx, nyy, nyp, nyv;            // NEW equality multipliers (y + dy)
     double nyd[2];                        // NEW rate-row multipliers
 };
-struct EvalState {        // model evaluation at the last evaluated point
+struct EvalLane {         // model evaluation at the last evaluated point, this thread's stage (lives in shared memory)
     double cs, sn, cb, sb, b1, b2;  // cos/sin(psi+beta), cos/sin(beta), beta', beta''
     double rd[4];         // k < N: f(s_k,u_k) - s_{k+1};  k = N: state - s_0;  else 0
     double dr[2];         // rate-row defect d(x) - slack
+};
+struct EvalState {        // ... and its team-wide scalars
     double f, lb, theta;  // objective (unscaled), sum of log slacks, 1-norm constraint violation
 };
 // reciprocals of the ten bound slacks of a lane, from ONE division
@@ -209,16 +226,77 @@ struct TeamSolver {
     const int N;
     const bool isS, isU, isR;  // thread owns a state / an input / a rate row
     int xpar;                  // W > 1: parity of the exchange buffers
-    double xr, yr, pr;         // this stage's reference sample
+    const int lf;              // this thread's slot in the per-thread field area (byte offset on the device)
     double sigma;
     LaneState L;
-    StepState D;
     EvalState ev;
 
     MPC_DEV static int team_tid() { return (W == 1) ? lane_id() : thread_in_block(); }
     MPC_DEV TeamSolver(const KCfg& cfg, smem_t smem)
         : c(cfg), sm(smem), k(team_tid()), N(cfg.N), isS(team_tid() <= cfg.N), isU(team_tid() < cfg.N),
-          isR((team_tid() == 0 || team_tid() >= 2) && team_tid() < cfg.N), xpar(0) {}
+          isR((team_tid() == 0 || team_tid() >= 2) && team_tid() < cfg.N), xpar(0),
+          lf(SO(lf_offset(cfg.N) + (team_tid() <= cfg.N ? team_tid() : cfg.N + 1))) {}
+
+    // per-thread fields in shared memory
+    MPC_DEV int lfs() const { return SO(N + 2); }   // field stride
+    MPC_DEV void ev_store(const EvalLane& e) {
+        const int st = lfs(); int a = lf + LF_EV * st;
+        sts(sm, a, e.cs); a += st; sts(sm, a, e.sn); a += st; sts(sm, a, e.cb); a += st; sts(sm, a, e.sb); a += st;
+        sts(sm, a, e.b1); a += st; sts(sm, a, e.b2); a += st;
+        sts(sm, a, e.rd[0]); a += st; sts(sm, a, e.rd[1]); a += st; sts(sm, a, e.rd[2]); a += st; sts(sm, a, e.rd[3]); a += st;
+        sts(sm, a, e.dr[0]); a += st; sts(sm, a, e.dr[1]);
+    }
+    MPC_DEV void ev_load_model(EvalLane& e) const {
+        const int st = lfs(); int a = lf + LF_EV * st;
+        e.cs = lds(sm, a); a += st; e.sn = lds(sm, a); a += st; e.cb = lds(sm, a); a += st; e.sb = lds(sm, a); a += st;
+        e.b1 = lds(sm, a); a += st; e.b2 = lds(sm, a);
+    }
+    MPC_DEV void ev_load_resid(EvalLane& e) const {
+        const int st = lfs(); int a = lf + (LF_EV + 6) * st;
+        e.rd[0] = lds(sm, a); a += st; e.rd[1] = lds(sm, a); a += st; e.rd[2] = lds(sm, a); a += st; e.rd[3] = lds(sm, a); a += st;
+        e.dr[0] = lds(sm, a); a += st; e.dr[1] = lds(sm, a);
+    }
+    MPC_DEV void set_ref(double x, double y, double p) {
+        const int st = lfs(); const int a = lf + LF_REF * st;
+        sts(sm, a, x); sts(sm, a + st, y); sts(sm, a + 2 * st, p);
+    }
+    MPC_DEV double ref_x() const { return lds(sm, lf + LF_REF * lfs()); }
+    MPC_DEV double ref_y() const { return lds(sm, lf + (LF_REF + 1) * lfs()); }
+    MPC_DEV double ref_p() const { return lds(sm, lf + (LF_REF + 2) * lfs()); }
+    MPC_DEV void ld_dx(StepState& D) const {
+        const int st = lfs(); int a = lf + LF_DX * st;
+        D.dsx = lds(sm, a); a += st; D.dsy = lds(sm, a); a += st; D.dsp = lds(sm, a); a += st; D.dsv = lds(sm, a); a += st;
+        D.dua = lds(sm, a); a += st; D.dud = lds(sm, a);
+    }
+    MPC_DEV void st_dx(const StepState& D) {
+        const int st = lfs(); int a = lf + LF_DX * st;
+        sts(sm, a, D.dsx); a += st; sts(sm, a, D.dsy); a += st; sts(sm, a, D.dsp); a += st; sts(sm, a, D.dsv); a += st;
+        sts(sm, a, D.dua); a += st; sts(sm, a, D.dud);
+    }
+    MPC_DEV void ld_drs(StepState& D) const { const int st = lfs(); const int a = lf + LF_DRS * st; D.drs[0] = lds(sm, a); D.drs[1] = lds(sm, a + st); }
+    MPC_DEV void st_drs(const StepState& D) { const int st = lfs(); const int a = lf + LF_DRS * st; sts(sm, a, D.drs[0]); sts(sm, a + st, D.drs[1]); }
+    MPC_DEV void ld_dy(StepState& D) const {
+        const int st = lfs(); int a = lf + LF_DY * st;
+        D.nyx = lds(sm, a); a += st; D.nyy = lds(sm, a); a += st; D.nyp = lds(sm, a); a += st; D.nyv = lds(sm, a); a += st;
+        D.nyd[0] = lds(sm, a); a += st; D.nyd[1] = lds(sm, a);
+    }
+    MPC_DEV void st_dy(const StepState& D) {
+        const int st = lfs(); int a = lf + LF_DY * st;
+        sts(sm, a, D.nyx); a += st; sts(sm, a, D.nyy); a += st; sts(sm, a, D.nyp); a += st; sts(sm, a, D.nyv); a += st;
+        sts(sm, a, D.nyd[0]); a += st; sts(sm, a, D.nyd[1]);
+    }
+    MPC_DEV void ld_z(BoundMult& Z) const {
+        const int st = lfs(); int a = lf + LF_Z * st;
+        Z.zvL = lds(sm, a); a += st; Z.zvU = lds(sm, a); a += st; Z.zaL = lds(sm, a); a += st; Z.zaU = lds(sm, a); a += st;
+        Z.zdL = lds(sm, a); a += st; Z.zdU = lds(sm, a); a += st;
+        Z.rvL[0] = lds(sm, a); a += st; Z.rvL[1] = lds(sm, a); a += st; Z.rvU[0] = lds(sm, a); a += st; Z.rvU[1] = lds(sm, a);
+    }
+    MPC_DEV void st_z(const BoundMult& Z) {
+        const int st = lfs(); int a = lf + LF_Z * st;
+        sts(sm, a, Z.zvL); a += st; sts(sm, a, Z.zvU); a += st; sts(sm, a, Z.zaL); a += st; sts(sm, a, Z.zaU); a += st;
+        sts(sm, a, Z.zdL); a += st; sts(sm, a, Z.zdU); a += st;
+        sts(sm, a, Z.rvL[0]); a += st; sts(sm, a, Z.rvL[1]); a += st; sts(sm, a, Z.rvU[0]); a += st; sts(sm, a, Z.rvU[1]);
+    }
 
     // ------------------------------------------------------------------
     // team collectives.  W == 1: plain warp shuffles.  W > 1: warp shuffles, then the values that
@@ -349,10 +427,13 @@ struct TeamSolver {
     // model evaluation at the point  L + a * D  (a = 0: the current iterate) -> ev
     // ------------------------------------------------------------------
     MPC_DEV void eval_point(double a) {
+        StepState D;
+        ld_dx(D); ld_drs(D);
         const double sx = L.sx + a * D.dsx, sy = L.sy + a * D.dsy, sp = L.sp + a * D.dsp, sv = L.sv + a * D.dsv;
         const double ua = L.ua + a * D.dua, ud = L.ud + a * D.dud;
         const double s0 = L.rs[0] + a * D.drs[0], s1 = L.rs[1] + a * D.drs[1];
         // trig: beta = atan(r tan df) in closed form, valid for |df| < pi/2 (bounds keep |df| <= 0.5)
+        EvalLane e;
         {
             const double r = c.rfrac;
             double sd, cd, sps, cps;
@@ -361,16 +442,16 @@ struct TeamSolver {
             const double Dn = cd * cd + r * r * sd * sd;
             const double iD = 1.0 / Dn;
             const double inv = sqrt(iD);
-            ev.cb = cd * inv;
-            ev.sb = r * sd * inv;
-            ev.cs = cps * ev.cb - sps * ev.sb;
-            ev.sn = sps * ev.cb + cps * ev.sb;
-            ev.b1 = r * iD;
-            ev.b2 = r * (1.0 - r * r) * (2.0 * sd * cd) * (iD * iD);
+            e.cb = cd * inv;
+            e.sb = r * sd * inv;
+            e.cs = cps * e.cb - sps * e.sb;
+            e.sn = sps * e.cb + cps * e.sb;
+            e.b1 = r * iD;
+            e.b2 = r * (1.0 - r * r) * (2.0 * sd * cd) * (iD * iD);
         }
-        const double fx = sx + c.dt * (sv * ev.cs);
-        const double fy = sy + c.dt * (sv * ev.sn);
-        const double fp = sp + c.dt * (sv / c.Lb * ev.sb);
+        const double fx = sx + c.dt * (sv * e.cs);
+        const double fy = sy + c.dt * (sv * e.sn);
+        const double fp = sp + c.dt * (sv / c.Lb * e.sb);
         const double fv = sv + c.dt * ua;
         // thread k < N takes s_{k+1}; thread N takes s_0 (for the initial-condition rows); every thread u_{k-1}
         double nxt[4], prv[2];
@@ -379,18 +460,19 @@ struct TeamSolver {
             xchg<4, 2, true>(dn, nxt, up, prv, N);
         }
         const double nx = nxt[0], ny = nxt[1], np = nxt[2], nv = nxt[3];
-        if (isU) { ev.rd[0] = fx - nx; ev.rd[1] = fy - ny; ev.rd[2] = fp - np; ev.rd[3] = fv - nv; }
-        else if (k == N) { ev.rd[0] = cst(0) - nx; ev.rd[1] = cst(1) - ny; ev.rd[2] = cst(2) - np; ev.rd[3] = cst(3) - nv; }
-        else { ev.rd[0] = ev.rd[1] = ev.rd[2] = ev.rd[3] = 0.0; }
+        if (isU) { e.rd[0] = fx - nx; e.rd[1] = fy - ny; e.rd[2] = fp - np; e.rd[3] = fv - nv; }
+        else if (k == N) { e.rd[0] = cst(0) - nx; e.rd[1] = cst(1) - ny; e.rd[2] = cst(2) - np; e.rd[3] = cst(3) - nv; }
+        else { e.rd[0] = e.rd[1] = e.rd[2] = e.rd[3] = 0.0; }
         const double pa = prv[0], pd = prv[1];
         const bool l0 = (k == 0);
         const double ba = l0 ? cst(5) : pa, bd = l0 ? cst(4) : pd;
-        ev.dr[0] = isR ? (ud - bd) - s0 : 0.0;
-        ev.dr[1] = isR ? (ua - ba) - s1 : 0.0;
+        e.dr[0] = isR ? (ud - bd) - s0 : 0.0;
+        e.dr[1] = isR ? (ua - ba) - s1 : 0.0;
+        ev_store(e);
         // objective (MKZMPCPathFollower.jl:97-103): stage terms + rate terms counted at the later input
         double f;
         {
-            const double ex = sx - xr, ey = sy - yr, ep = sp - pr, evv = sv - cst(6);
+            const double ex = sx - ref_x(), ey = sy - ref_y(), ep = sp - ref_p(), evv = sv - cst(6);
             f = wx() * ex * ex + wy() * ey * ey + wp() * ep * ep + wv() * evv * evv;
             if (isU) {
                 f += c.w[6] * ua * ua + c.w[7] * ud * ud;
@@ -402,7 +484,7 @@ struct TeamSolver {
         if (isU) p *= (ua - c.aLo) * (c.aHi - ua) * (ud - c.dLo) * (c.dHi - ud);
         if (isR) { const double h0 = rHi(0), h1 = rHi(1); p *= (s0 + h0) * (h0 - s0) * (s1 + h1) * (h1 - s1); }
         double lb = log(p);
-        double th = fabs(ev.rd[0]) + fabs(ev.rd[1]) + fabs(ev.rd[2]) + fabs(ev.rd[3]) + fabs(ev.dr[0]) + fabs(ev.dr[1]);
+        double th = fabs(e.rd[0]) + fabs(e.rd[1]) + fabs(e.rd[2]) + fabs(e.rd[3]) + fabs(e.dr[0]) + fabs(e.dr[1]);
         double r3[3] = {f, lb, th};
         treduce<OP_SUM, 3>(r3);
         ev.f = r3[0]; ev.lb = r3[1]; ev.theta = r3[2];
@@ -420,9 +502,9 @@ struct TeamSolver {
         }
         const double na = nxt[0], nd = nxt[1], pa = prv[0], pd = prv[1];
         const double s2 = 2.0 * sigma;
-        g.x = s2 * wx() * (L.sx - xr);
-        g.y = s2 * wy() * (L.sy - yr);
-        g.p = s2 * wp() * (L.sp - pr);
+        g.x = s2 * wx() * (L.sx - ref_x());
+        g.y = s2 * wy() * (L.sy - ref_y());
+        g.p = s2 * wp() * (L.sp - ref_p());
         g.v = s2 * wv() * (L.sv - cst(6));
         g.a = 0.0; g.d = 0.0;
         if (isU) {
@@ -445,16 +527,20 @@ struct TeamSolver {
         const int r = rec();
         const Grad g = objective_gradient();
         const double gx = g.x, gy = g.y, gp = g.p, gv = g.v, ga = g.a, gd = g.d;
+        EvalLane e;
+        ev_load_model(e);
+        BoundMult Z;
+        ld_z(Z);
         double Hxx, Hyy, Hpp, Hpv = 0.0, Hvv, Hpd = 0.0, Hvd = 0.0, Haa, Hdd, Ca = 0.0, Cd = 0.0;
         double gsv, gua = 0.0, gud = 0.0;
         double SrW[2] = {0.0, 0.0}, br[2] = {0.0, 0.0}, wrow[2] = {0.0, 0.0}, rdr[2] = {0.0, 0.0};
         if (req == 0) {
-            if (isR) for (int i = 0; i < 2; i++) { SrW[i] = 1.0; br[i] = -(L.rvL[i] - L.rvU[i]); wrow[i] = br[i]; }
+            if (isR) for (int i = 0; i < 2; i++) { SrW[i] = 1.0; br[i] = -(Z.rvL[i] - Z.rvU[i]); wrow[i] = br[i]; }
             Hxx = Hyy = Hpp = Hvv = 1.0;
             Ca = (isU && isR) ? 1.0 : 0.0; Cd = Ca;
             Haa = 1.0 + Ca; Hdd = 1.0 + Cd;
-            gsv = gv + (isS ? (-L.zvL + L.zvU) : 0.0);
-            if (isU) { gua = ga - L.zaL + L.zaU; gud = gd - L.zdL + L.zdU; }
+            gsv = gv + (isS ? (-Z.zvL + Z.zvU) : 0.0);
+            if (isU) { gua = ga - Z.zaL + Z.zaU; gud = gd - Z.zdL + Z.zdU; }
         } else {
             // multipliers of the rows leaving this stage (held by lane k+1)
             double y1[3];
@@ -463,25 +549,25 @@ struct TeamSolver {
             double hpp = 0.0, hdd = 0.0;
             if (isU) {
                 const double v = L.sv, dt = c.dt;
-                const double e1 = y1x * ev.cs + y1y * ev.sn;
-                const double e2 = y1x * ev.sn - y1y * ev.cs;
+                const double e1 = y1x * e.cs + y1y * e.sn;
+                const double e2 = y1x * e.sn - y1y * e.cs;
                 hpp = dt * v * e1;
                 Hpv = dt * e2;
-                Hpd = ev.b1 * hpp;
-                Hvd = ev.b1 * Hpv - y1p * dt * ev.cb * ev.b1 / c.Lb;
-                hdd = ev.b1 * ev.b1 * hpp + v * ev.b2 * Hpv - y1p * (dt * v / c.Lb) * (ev.cb * ev.b2 - ev.sb * ev.b1 * ev.b1);
+                Hpd = e.b1 * hpp;
+                Hvd = e.b1 * Hpv - y1p * dt * e.cb * e.b1 / c.Lb;
+                hdd = e.b1 * e.b1 * hpp + v * e.b2 * Hpv - y1p * (dt * v / c.Lb) * (e.cb * e.b2 - e.sb * e.b1 * e.b1);
             }
             Recips q;
             recips(q);
             // Sigma = zL/sl + zU/su ; barrier gradient b = -mu/sl + mu/su
-            const double Sv = isS ? L.zvL * q.vL + L.zvU * q.vU : 0.0, bv = isS ? mu * (q.vU - q.vL) : 0.0;
-            const double Sa = isU ? L.zaL * q.aL + L.zaU * q.aU : 0.0, ba = isU ? mu * (q.aU - q.aL) : 0.0;
-            const double Sd = isU ? L.zdL * q.dL + L.zdU * q.dU : 0.0, bd = isU ? mu * (q.dU - q.dL) : 0.0;
+            const double Sv = isS ? Z.zvL * q.vL + Z.zvU * q.vU : 0.0, bv = isS ? mu * (q.vU - q.vL) : 0.0;
+            const double Sa = isU ? Z.zaL * q.aL + Z.zaU * q.aU : 0.0, ba = isU ? mu * (q.aU - q.aL) : 0.0;
+            const double Sd = isU ? Z.zdL * q.dL + Z.zdU * q.dU : 0.0, bd = isU ? mu * (q.dU - q.dL) : 0.0;
             if (isR) {
-                SrW[0] = L.rvL[0] * q.r0L + L.rvU[0] * q.r0U + dw; br[0] = mu * (q.r0U - q.r0L);
-                SrW[1] = L.rvL[1] * q.r1L + L.rvU[1] * q.r1U + dw; br[1] = mu * (q.r1U - q.r1L);
+                SrW[0] = Z.rvL[0] * q.r0L + Z.rvU[0] * q.r0U + dw; br[0] = mu * (q.r0U - q.r0L);
+                SrW[1] = Z.rvL[1] * q.r1L + Z.rvU[1] * q.r1U + dw; br[1] = mu * (q.r1U - q.r1L);
                 if (req == 3) { rdr[0] = lds(sm, r + SO(SD_DR)); rdr[1] = lds(sm, r + SO(SD_DR + 1)); }
-                else { rdr[0] = ev.dr[0]; rdr[1] = ev.dr[1]; }
+                else { ev_load_resid(e); rdr[0] = e.dr[0]; rdr[1] = e.dr[1]; }
                 wrow[0] = br[0] + SrW[0] * rdr[0];
                 wrow[1] = br[1] + SrW[1] * rdr[1];
             }
@@ -506,18 +592,19 @@ struct TeamSolver {
         }
         if (!isS) return;
         if (req == 0 || req == 1) {
-            const double A02 = isU ? -c.dt * L.sv * ev.sn : 0.0, A03 = isU ? c.dt * ev.cs : 0.0;
-            const double A12 = isU ? c.dt * L.sv * ev.cs : 0.0, A13 = isU ? c.dt * ev.sn : 0.0;
-            const double A23 = isU ? c.dt * ev.sb / c.Lb : 0.0;
-            const double b0 = A02 * ev.b1, b1v = A12 * ev.b1, b2v = isU ? c.dt * L.sv * ev.cb * ev.b1 / c.Lb : 0.0;
+            const double A02 = isU ? -c.dt * L.sv * e.sn : 0.0, A03 = isU ? c.dt * e.cs : 0.0;
+            const double A12 = isU ? c.dt * L.sv * e.cs : 0.0, A13 = isU ? c.dt * e.sn : 0.0;
+            const double A23 = isU ? c.dt * e.sb / c.Lb : 0.0;
+            const double b0 = A02 * e.b1, b1v = A12 * e.b1, b2v = isU ? c.dt * L.sv * e.cb * e.b1 / c.Lb : 0.0;
             const double one = isU ? 1.0 : 0.0;
             sts(sm, r + SO(SD_CF + 0), A02); sts(sm, r + SO(SD_CF + 1), A12); sts(sm, r + SO(SD_CF + 2), one);
             sts(sm, r + SO(SD_CF + 4), A03); sts(sm, r + SO(SD_CF + 5), A13); sts(sm, r + SO(SD_CF + 6), A23); sts(sm, r + SO(SD_CF + 7), one);
             sts(sm, r + SO(SD_CF + 11), isU ? c.dt : 0.0);
             sts(sm, r + SO(SD_CF + 12), b0); sts(sm, r + SO(SD_CF + 13), b1v); sts(sm, r + SO(SD_CF + 14), b2v);
             const bool z = (req == 0);
-            sts(sm, r + SO(SD_R + 0), z ? 0.0 : ev.rd[0]); sts(sm, r + SO(SD_R + 1), z ? 0.0 : ev.rd[1]);
-            sts(sm, r + SO(SD_R + 2), z ? 0.0 : ev.rd[2]); sts(sm, r + SO(SD_R + 3), z ? 0.0 : ev.rd[3]);
+            ev_load_resid(e);
+            sts(sm, r + SO(SD_R + 0), z ? 0.0 : e.rd[0]); sts(sm, r + SO(SD_R + 1), z ? 0.0 : e.rd[1]);
+            sts(sm, r + SO(SD_R + 2), z ? 0.0 : e.rd[2]); sts(sm, r + SO(SD_R + 3), z ? 0.0 : e.rd[3]);
             sts(sm, r + SO(SD_HPV), Hpv); sts(sm, r + SO(SD_HPD), Hpd); sts(sm, r + SO(SD_HVD), Hvd);
             sts(sm, r + SO(SD_GX + 0), gx); sts(sm, r + SO(SD_GX + 1), gy); sts(sm, r + SO(SD_GX + 2), gp); sts(sm, r + SO(SD_GX + 3), gsv);
             sts(sm, r + SO(SD_BR), br[0]); sts(sm, r + SO(SD_BR + 1), br[1]);
@@ -694,6 +781,7 @@ struct TeamSolver {
         const d2 i01 = lds2(sm, SO(W_SD + N * SDS + SD_R)), i23 = lds2(sm, SO(W_SD + N * SDS + SD_R + 2));  // ds_0
         double s0 = i01.x, s1 = i01.y, s2 = i23.x, s3 = i23.y;
         double pa = 0.0, pd = 0.0;
+        StepState D;
         D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0;
         for (int s = 0; s < N; s++) {
             const d2 ka0 = lds2(sm, kp), ka1 = lds2(sm, kp + SO(2)), ka2 = lds2(sm, kp + SO(4)), kx = lds2(sm, kp + SO(6));
@@ -712,12 +800,15 @@ struct TeamSolver {
             kp += SO(KST_STRIDE); r += SO(SDS);
         }
         if (k == N) { D.dsx = s0; D.dsy = s1; D.dsp = s2; D.dsv = s3; }
+        st_dx(D);
     }
 
     // new equality multipliers from stationarity in the state variables (parallel suffix sums),
     // new rate-row multipliers and slack steps; the condensed blocks are read back from the record
     MPC_DEV void recover_duals() {
         const int r = rec();
+        StepState D;
+        ld_dx(D);
         double lx = 0.0, ly = 0.0, lp = 0.0, lv = 0.0;
         const double hpv = lds(sm, r + SO(SD_HPV));
         if (isS) {
@@ -752,10 +843,13 @@ struct TeamSolver {
             D.nyd[0] = srw.x * D.drs[0] + brr.x;
             D.nyd[1] = srw.y * D.drs[1] + brr.y;
         }
+        st_drs(D); st_dy(D);
     }
 
     // fraction-to-the-boundary for the primal step: tau / max_i( -dx_i / slack_i ), division-free per element
     MPC_DEV double alpha_primal(double tau) {
+        StepState D;
+        ld_dx(D); ld_drs(D);
         double num = 0.0, den = 1.0;   // largest ratio num/den (num >= 0, den > 0) by cross-multiplication
         auto upd = [&](double dx, double sl, double su) {
             const double n = fabs(dx), d = (dx < 0.0) ? sl : su;
@@ -784,11 +878,13 @@ struct TeamSolver {
     // ------------------------------------------------------------------
     MPC_DEV Result solve() {
         Result res; res.status = 4; res.iters = 0; res.cost = 0.0;
-        D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0; D.drs[0] = D.drs[1] = 0.0;
-        D.nyx = D.nyy = D.nyp = D.nyv = 0.0; D.nyd[0] = D.nyd[1] = 0.0;
+        {
+            StepState D;
+            D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0; D.drs[0] = D.drs[1] = 0.0;
+            D.nyx = D.nyy = D.nyp = D.nyv = 0.0; D.nyd[0] = D.nyd[1] = 0.0;
+            st_dx(D); st_drs(D); st_dy(D);
+        }
         L.rs[0] = L.rs[1] = 0.0;
-        L.zvL = L.zvU = L.zaL = L.zaU = L.zdL = L.zdU = 0.0;
-        L.rvL[0] = L.rvL[1] = L.rvU[0] = L.rvU[1] = 0.0;
         L.ryd[0] = L.ryd[1] = 0.0; L.yx = L.yy = L.yp = L.yv = 0.0;
 
         const bool feasible = nlp_feasible();
@@ -815,9 +911,13 @@ struct TeamSolver {
                 L.rs[1] = L.ua - ((k == 0) ? cst(5) : pa);
                 push_interior(L.rs[0], -h0, h0); push_interior(L.rs[1], -h1, h1);
             }
-            L.zvL = L.zvU = isS ? 1.0 : 0.0;
-            L.zaL = L.zaU = L.zdL = L.zdU = isU ? 1.0 : 0.0;
-            L.rvL[0] = L.rvL[1] = L.rvU[0] = L.rvU[1] = isR ? 1.0 : 0.0;
+        }
+        {
+            BoundMult Z;
+            Z.zvL = Z.zvU = (feasible && isS) ? 1.0 : 0.0;
+            Z.zaL = Z.zaU = Z.zdL = Z.zdU = (feasible && isU) ? 1.0 : 0.0;
+            Z.rvL[0] = Z.rvL[1] = Z.rvU[0] = Z.rvU[1] = (feasible && isR) ? 1.0 : 0.0;
+            st_z(Z);
         }
 
         enum { PH_EVAL0 = 0, PH_LS, PH_BEGIN, PH_PD, PH_RESOLVE_EVAL, PH_RESOLVE, PH_TRIAL, PH_SOC };
@@ -892,9 +992,11 @@ struct TeamSolver {
                         th_soc_old = th_t;
                         if (isS) {
                             const int r = rec();
-                            for (int i = 0; i < 4; i++) sts(sm, r + SO(SD_R + i), a_soc * lds(sm, r + SO(SD_R + i)) + ev.rd[i]);
-                            sts(sm, r + SO(SD_DR), a_soc * lds(sm, r + SO(SD_DR)) + ev.dr[0]);
-                            sts(sm, r + SO(SD_DR + 1), a_soc * lds(sm, r + SO(SD_DR + 1)) + ev.dr[1]);
+                            EvalLane e;
+                            ev_load_resid(e);
+                            for (int i = 0; i < 4; i++) sts(sm, r + SO(SD_R + i), a_soc * lds(sm, r + SO(SD_R + i)) + e.rd[i]);
+                            sts(sm, r + SO(SD_DR), a_soc * lds(sm, r + SO(SD_DR)) + e.dr[0]);
+                            sts(sm, r + SO(SD_DR + 1), a_soc * lds(sm, r + SO(SD_DR + 1)) + e.dr[1]);
                         }
                         tsync();
                         phase = PH_SOC; do_solve = true; req = 3; do_eval = true; eval_ftb = true;
@@ -903,7 +1005,11 @@ struct TeamSolver {
                     if (phase == PH_SOC) {
                         // corrections exhausted: re-evaluate the current point, recompute the Newton direction, backtrack
                         phase = PH_RESOLVE_EVAL; do_eval = true; ev_alpha = 0.0;
-                        D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0; D.drs[0] = D.drs[1] = 0.0;
+                        {
+                            StepState D;
+                            D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0; D.drs[0] = D.drs[1] = 0.0;
+                            st_dx(D); st_drs(D);
+                        }
                         continue;
                     }
                     // plain backtracking
@@ -926,22 +1032,26 @@ struct TeamSolver {
                 }
                 {
                     // bound-multiplier steps from the accepted direction: dz = (mu -/+ z dx)/slack - z
+                    StepState D;
+                    ld_dx(D); ld_drs(D); ld_dy(D);
+                    BoundMult Z;
+                    ld_z(Z);
                     Recips q;
                     recips(q);
                     double dzvL = 0, dzvU = 0, dzaL = 0, dzaU = 0, dzdL = 0, dzdU = 0, drvL[2] = {0, 0}, drvU[2] = {0, 0};
-                    if (isS) { dzvL = (mu - L.zvL * D.dsv) * q.vL - L.zvL; dzvU = (mu + L.zvU * D.dsv) * q.vU - L.zvU; }
+                    if (isS) { dzvL = (mu - Z.zvL * D.dsv) * q.vL - Z.zvL; dzvU = (mu + Z.zvU * D.dsv) * q.vU - Z.zvU; }
                     if (isU) {
-                        dzaL = (mu - L.zaL * D.dua) * q.aL - L.zaL; dzaU = (mu + L.zaU * D.dua) * q.aU - L.zaU;
-                        dzdL = (mu - L.zdL * D.dud) * q.dL - L.zdL; dzdU = (mu + L.zdU * D.dud) * q.dU - L.zdU;
+                        dzaL = (mu - Z.zaL * D.dua) * q.aL - Z.zaL; dzaU = (mu + Z.zaU * D.dua) * q.aU - Z.zaU;
+                        dzdL = (mu - Z.zdL * D.dud) * q.dL - Z.zdL; dzdU = (mu + Z.zdU * D.dud) * q.dU - Z.zdU;
                     }
                     if (isR) {
-                        drvL[0] = (mu - L.rvL[0] * D.drs[0]) * q.r0L - L.rvL[0]; drvU[0] = (mu + L.rvU[0] * D.drs[0]) * q.r0U - L.rvU[0];
-                        drvL[1] = (mu - L.rvL[1] * D.drs[1]) * q.r1L - L.rvL[1]; drvU[1] = (mu + L.rvU[1] * D.drs[1]) * q.r1U - L.rvU[1];
+                        drvL[0] = (mu - Z.rvL[0] * D.drs[0]) * q.r0L - Z.rvL[0]; drvU[0] = (mu + Z.rvU[0] * D.drs[0]) * q.r0U - Z.rvU[0];
+                        drvL[1] = (mu - Z.rvL[1] * D.drs[1]) * q.r1L - Z.rvL[1]; drvU[1] = (mu + Z.rvU[1] * D.drs[1]) * q.r1U - Z.rvU[1];
                     }
                     double num = 0.0, den = 1.0;   // dual fraction-to-the-boundary: largest -dz/z by cross-multiplication
                     auto lim = [&](double z, double dz) { if (dz < 0.0 && -dz * den > num * z) { num = -dz; den = z; } };
-                    lim(L.zvL, dzvL); lim(L.zvU, dzvU); lim(L.zaL, dzaL); lim(L.zaU, dzaU); lim(L.zdL, dzdL); lim(L.zdU, dzdU);
-                    lim(L.rvL[0], drvL[0]); lim(L.rvU[0], drvU[0]); lim(L.rvL[1], drvL[1]); lim(L.rvU[1], drvU[1]);
+                    lim(Z.zvL, dzvL); lim(Z.zvU, dzvU); lim(Z.zaL, dzaL); lim(Z.zaU, dzaU); lim(Z.zdL, dzdL); lim(Z.zdU, dzdU);
+                    lim(Z.rvL[0], drvL[0]); lim(Z.rvU[0], drvU[0]); lim(Z.rvL[1], drvL[1]); lim(Z.rvU[1], drvU[1]);
                     const double az = dmin_(1.0, tmin(num > 0.0 ? tau * den / num : 1.0));
                     // primal, equality multipliers (primal step size), bound multipliers (dual step size)
                     L.sx += alpha * D.dsx; L.sy += alpha * D.dsy; L.sp += alpha * D.dsp; L.sv += alpha * D.dsv;
@@ -954,16 +1064,17 @@ struct TeamSolver {
                         if (pz > K_KAPPA_SIGMA * mu) z = K_KAPPA_SIGMA * mu / sl;
                         else if (pz * K_KAPPA_SIGMA < mu) z = mu / (K_KAPPA_SIGMA * sl);
                     };
-                    if (isS) { upd(L.zvL, dzvL, L.sv - c.vLo); upd(L.zvU, dzvU, c.vHi - L.sv); }
+                    if (isS) { upd(Z.zvL, dzvL, L.sv - c.vLo); upd(Z.zvU, dzvU, c.vHi - L.sv); }
                     if (isU) {
-                        upd(L.zaL, dzaL, L.ua - c.aLo); upd(L.zaU, dzaU, c.aHi - L.ua);
-                        upd(L.zdL, dzdL, L.ud - c.dLo); upd(L.zdU, dzdU, c.dHi - L.ud);
+                        upd(Z.zaL, dzaL, L.ua - c.aLo); upd(Z.zaU, dzaU, c.aHi - L.ua);
+                        upd(Z.zdL, dzdL, L.ud - c.dLo); upd(Z.zdU, dzdU, c.dHi - L.ud);
                     }
                     if (isR) {
                         const double h0 = rHi(0), h1 = rHi(1);
-                        upd(L.rvL[0], drvL[0], L.rs[0] + h0); upd(L.rvU[0], drvU[0], h0 - L.rs[0]);
-                        upd(L.rvL[1], drvL[1], L.rs[1] + h1); upd(L.rvU[1], drvU[1], h1 - L.rs[1]);
+                        upd(Z.rvL[0], drvL[0], L.rs[0] + h0); upd(Z.rvU[0], drvU[0], h0 - L.rs[0]);
+                        upd(Z.rvL[1], drvL[1], L.rs[1] + h1); upd(Z.rvU[1], drvU[1], h1 - L.rs[1]);
                     }
+                    st_z(Z);
                 }
                 // the accepted trial evaluation (in ev) is the next iteration's current evaluation
                 cur_theta = ev.theta; cur_f = ev.f; cur_lb = ev.lb;
@@ -978,6 +1089,8 @@ struct TeamSolver {
             }
             if (phase == PH_LS) {
                 bool use = solve_ok;
+                StepState D;
+                ld_dy(D);
                 if (solve_ok) {
                     double ym = dmax_(dmax_(fabs(D.nyx), fabs(D.nyy)), dmax_(fabs(D.nyp), fabs(D.nyv)));
                     ym = dmax_(ym, dmax_(fabs(D.nyd[0]), fabs(D.nyd[1])));
@@ -990,10 +1103,15 @@ struct TeamSolver {
             if (phase == PH_BEGIN) {
                 const Grad g = objective_gradient();
                 const double gx = g.x, gy = g.y, gp = g.p, gv = g.v, ga = g.a, gd = g.d;
-                const double A02 = isU ? -c.dt * L.sv * ev.sn : 0.0, A03 = isU ? c.dt * ev.cs : 0.0;
-                const double A12 = isU ? c.dt * L.sv * ev.cs : 0.0, A13 = isU ? c.dt * ev.sn : 0.0;
-                const double A23 = isU ? c.dt * ev.sb / c.Lb : 0.0;
-                const double b0 = A02 * ev.b1, b1v = A12 * ev.b1, b2v = isU ? c.dt * L.sv * ev.cb * ev.b1 / c.Lb : 0.0;
+                EvalLane e;
+                ev_load_model(e);
+                ev_load_resid(e);
+                BoundMult Z;
+                ld_z(Z);
+                const double A02 = isU ? -c.dt * L.sv * e.sn : 0.0, A03 = isU ? c.dt * e.cs : 0.0;
+                const double A12 = isU ? c.dt * L.sv * e.cs : 0.0, A13 = isU ? c.dt * e.sn : 0.0;
+                const double A23 = isU ? c.dt * e.sb / c.Lb : 0.0;
+                const double b0 = A02 * e.b1, b1v = A12 * e.b1, b2v = isU ? c.dt * L.sv * e.cb * e.b1 / c.Lb : 0.0;
                 double di, cv, cm0, cmm, sumy, sumz;
                 {
                     double y1[6];
@@ -1003,18 +1121,18 @@ struct TeamSolver {
                     const double glx = gx + L.yx - hn * y1x;
                     const double gly = gy + L.yy - hn * y1y;
                     const double glp = gp + L.yp - hn * (A02 * y1x + A12 * y1y + y1p);
-                    const double glv = gv + L.yv - hn * (A03 * y1x + A13 * y1y + A23 * y1p + y1v) - L.zvL + L.zvU;
+                    const double glv = gv + L.yv - hn * (A03 * y1x + A13 * y1y + A23 * y1p + y1v) - Z.zvL + Z.zvU;
                     const double nd0 = (k + 1 < N) ? yd1_0 : 0.0, nd1 = (k + 1 < N) ? yd1_1 : 0.0;
-                    const double gla = ga - hn * c.dt * y1v + (L.ryd[1] - nd1) - L.zaL + L.zaU;
-                    const double gld = gd - hn * (b0 * y1x + b1v * y1y + b2v * y1p) + (L.ryd[0] - nd0) - L.zdL + L.zdU;
+                    const double gla = ga - hn * c.dt * y1v + (L.ryd[1] - nd1) - Z.zaL + Z.zaU;
+                    const double gld = gd - hn * (b0 * y1x + b1v * y1y + b2v * y1p) + (L.ryd[0] - nd0) - Z.zdL + Z.zdU;
                     di = dmax_(dmax_(fabs(glx), fabs(gly)), dmax_(fabs(glp), fabs(glv)));
                     di = dmax_(di, dmax_(fabs(gla), fabs(gld)));
-                    di = dmax_(di, dmax_(fabs(-L.ryd[0] - L.rvL[0] + L.rvU[0]), fabs(-L.ryd[1] - L.rvL[1] + L.rvU[1])));
+                    di = dmax_(di, dmax_(fabs(-L.ryd[0] - Z.rvL[0] + Z.rvU[0]), fabs(-L.ryd[1] - Z.rvL[1] + Z.rvU[1])));
                     di = isS ? di : 0.0;
-                    cv = dmax_(dmax_(fabs(ev.rd[0]), fabs(ev.rd[1])), dmax_(fabs(ev.rd[2]), fabs(ev.rd[3])));
-                    cv = dmax_(cv, dmax_(fabs(ev.dr[0]), fabs(ev.dr[1])));
+                    cv = dmax_(dmax_(fabs(e.rd[0]), fabs(e.rd[1])), dmax_(fabs(e.rd[2]), fabs(e.rd[3])));
+                    cv = dmax_(cv, dmax_(fabs(e.dr[0]), fabs(e.dr[1])));
                     sumy = isS ? fabs(L.yx) + fabs(L.yy) + fabs(L.yp) + fabs(L.yv) + fabs(L.ryd[0]) + fabs(L.ryd[1]) : 0.0;
-                    sumz = L.zvL + L.zvU + L.zaL + L.zaU + L.zdL + L.zdU + L.rvL[0] + L.rvL[1] + L.rvU[0] + L.rvU[1];
+                    sumz = Z.zvL + Z.zvU + Z.zaL + Z.zaU + Z.zdL + Z.zdU + Z.rvL[0] + Z.rvL[1] + Z.rvU[0] + Z.rvU[1];
                     double r2[2] = {sumy, sumz};
                     treduce<OP_SUM, 2>(r2);
                     sumy = r2[0]; sumz = r2[1];
@@ -1024,14 +1142,14 @@ struct TeamSolver {
                 // complementarity of this lane: max |slack * z - t| over its bound pairs
                 auto compl_local = [&](double t) {
                     double m = 0.0;
-                    if (isS) { m = dmax_(m, fabs((L.sv - c.vLo) * L.zvL - t)); m = dmax_(m, fabs((c.vHi - L.sv) * L.zvU - t)); }
+                    if (isS) { m = dmax_(m, fabs((L.sv - c.vLo) * Z.zvL - t)); m = dmax_(m, fabs((c.vHi - L.sv) * Z.zvU - t)); }
                     if (isU) {
-                        m = dmax_(m, fabs((L.ua - c.aLo) * L.zaL - t)); m = dmax_(m, fabs((c.aHi - L.ua) * L.zaU - t));
-                        m = dmax_(m, fabs((L.ud - c.dLo) * L.zdL - t)); m = dmax_(m, fabs((c.dHi - L.ud) * L.zdU - t));
+                        m = dmax_(m, fabs((L.ua - c.aLo) * Z.zaL - t)); m = dmax_(m, fabs((c.aHi - L.ua) * Z.zaU - t));
+                        m = dmax_(m, fabs((L.ud - c.dLo) * Z.zdL - t)); m = dmax_(m, fabs((c.dHi - L.ud) * Z.zdU - t));
                     }
                     if (isR) for (int i = 0; i < 2; i++) {
                         const double h = rHi(i);
-                        m = dmax_(m, fabs((L.rs[i] + h) * L.rvL[i] - t)); m = dmax_(m, fabs((h - L.rs[i]) * L.rvU[i] - t));
+                        m = dmax_(m, fabs((L.rs[i] + h) * Z.rvL[i] - t)); m = dmax_(m, fabs((h - L.rs[i]) * Z.rvU[i] - t));
                     }
                     return m;
                 };
@@ -1105,6 +1223,8 @@ struct TeamSolver {
                     // grad(phi)'d from the condensed gradient in the record:
                     //   sum g~ dx + sum_rows [ br rdr - SrW rdr (drs - rdr) ]
                     const int r = rec();
+                    StepState D;
+                    ld_dx(D); ld_drs(D);
                     double t = 0.0;
                     bool tl = true;  // all |dx_i| < 10 eps (1 + |x_i|)
                     const double tt = 10.0 * K_EPS;
@@ -1144,7 +1264,7 @@ struct TeamSolver {
             double prv[2];
             { const double u[2] = {L.ua, L.ud}; xprev<2>(u, prv); }
             const double pa = prv[0], pd = prv[1];
-            const double ex = L.sx - xr, ey = L.sy - yr, ep = L.sp - pr, evv = L.sv - cst(6);
+            const double ex = L.sx - ref_x(), ey = L.sy - ref_y(), ep = L.sp - ref_p(), evv = L.sv - cst(6);
             double f = wx() * ex * ex + wy() * ey * ey + wp() * ep * ep + wv() * evv * evv;
             if (isU) {
                 f += c.w[6] * L.ua * L.ua + c.w[7] * L.ud * L.ud;
@@ -1177,9 +1297,7 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t 
     const long nr = 3L * (N + 1), nt = 6L * N + 4;
     // ---- coalesced loads: lane k takes stage k's reference sample; lanes 0..6 the problem constants
     const double* rf = io.ref + nr * b;
-    S.xr = (k <= N) ? rf[k] : 0.0;
-    S.yr = (k <= N) ? rf[(N + 1) + k] : 0.0;
-    S.pr = (k <= N) ? rf[2 * (N + 1) + k] : 0.0;
+    S.set_ref((k <= N) ? rf[k] : 0.0, (k <= N) ? rf[(N + 1) + k] : 0.0, (k <= N) ? rf[2 * (N + 1) + k] : 0.0);
     {
         double cv = 0.0;
         if (k < 4) cv = io.state[4 * b + k];
@@ -1325,7 +1443,9 @@ MPC_DEV void rollout_vehicle(const KCfg& cfg, const RolloutArgs& a, long b, smem
     S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;   // start = 0.0, then the previous solution
     for (int t = 0; t < a.T; t++) {
         for (int i = 0; i < 10; i++) plant_step(st, acc_des, df_des);
-        const bool sc = get_waypoints_warp(path, N, cfg.dt, st[0], st[1], st[2], !a.track_using_time, des_speed, S.xr, S.yr, S.pr);
+        double xr, yr, pr;
+        const bool sc = get_waypoints_warp(path, N, cfg.dt, st[0], st[1], st[2], !a.track_using_time, des_speed, xr, yr, pr);
+        S.set_ref(xr, yr, pr);
         if (sc) stop = true;   // latch, mpc_cmd_pub.jl:102-111
         int status = -1, iters = 0;
         if (!stop) {
