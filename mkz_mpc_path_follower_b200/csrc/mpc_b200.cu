@@ -112,6 +112,7 @@ struct mpcb200_handle {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long* d_counter = nullptr;
+    int* d_roles = nullptr;   /* lane roles of the Riccati recursion for this horizon (riccati_roles) */
     DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
     DevBuf d_path[3], d_pose, d_pathof, d_log, d_final;
     int path_n[3] = {0, 0, 0};
@@ -157,6 +158,7 @@ static KCfg make_kcfg(const mpcb200_handle* h) {
     k.admax = c.a_dmax; k.sdmax = c.steer_dmax; k.tol = c.tol;
     for (int i = 0; i < 8; i++) k.w[i] = h->w[i];
     kcfg_finalize(k);
+    k.roles = h->d_roles;
     return k;
 }
 
@@ -227,6 +229,12 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
     TRY_OR_FREE(cudaEventCreate(&h->ev1));
     TRY_OR_FREE(cudaMalloc((void**)&h->d_counter, sizeof(unsigned long long)));
     h->team_warps = team_warps(cfg->N);
+    {
+        int roles[32 * ROLE_STRIDE];
+        for (int l = 0; l < 32; l++) riccati_roles(l, cfg->N, W_SD_OF(h->team_warps), roles + l * ROLE_STRIDE);
+        TRY_OR_FREE(cudaMalloc((void**)&h->d_roles, sizeof(roles)));
+        TRY_OR_FREE(cudaMemcpy(h->d_roles, roles, sizeof(roles), cudaMemcpyHostToDevice));
+    }
     if (h->team_warps == 1) {
         h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N) * sizeof(double);
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -257,6 +265,7 @@ int mpcb200_destroy(mpcb200_handle* h) {
                       &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
+    if (h->d_roles) cudaFree(h->d_roles);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

@@ -48,6 +48,7 @@ struct KCfg {
     double rHiFirst[2], rHiLater[2];  // relaxed half-width of the rate rows [steer, acc]; rLo = -rHi
     double rfrac;                     // L_b / (L_a + L_b)
     double mu_min;
+    const int* roles;                 // [32][ROLE_STRIDE] lane roles of the Riccati recursion (riccati_roles), device memory
 };
 
 // ---- Ipopt 3.12 default constants (same values as oracle/mpc_oracle.c) ----
@@ -214,6 +215,88 @@ struct EvalState {        // ... and its team-wide scalars
 struct Recips { double vL, vU, aL, aU, dL, dU, r0L, r0U, r1L, r1U; };
 
 struct Result { int status; int iters; double cost; };
+
+// ---- lane roles of the Riccati backward recursion (lanes = matrix entries), one row of ROLE_STRIDE
+// ints per lane: shared-memory offsets (SO units) of the operands of rounds A, B and E.  They depend
+// only on the lane, the horizon and the team size, so mpcb200_create computes the table once.
+#define ROLE_STRIDE 20
+MPC_HD void riccati_roles(int l, int N, int W_SD, int* out) {
+    int a_p, a_m, a_ex, a_out, b_m, b_mk, b_t, b_x, b_h, b_o1, b_o2, e_f0, e_fi, e_fj, e_o1, e_o2, e_k0, e_k1;
+        {
+            // round A: lane (i, cc) -> TT[cc][i] = sum_{j<4} P[i][j] CF[cc][j] + X,  X = 0 | P[i][4] | P[i][5] | p[i]
+            const int i = (l < 24) ? (l >> 2) : (l < 30 ? l - 24 : 0);
+            const int cc = (l < 24) ? (l & 3) : 4;
+            a_p = (SO(W_P + 6 * i));
+            a_m = (SO(W_SD + SD_CF + 4 * cc));
+            a_ex = ((l >= 30) ? SO(W_Z) : (cc == 2) ? SO(W_P + 6 * i + 4) : (cc == 3) ? SO(W_P + 6 * i + 5) : (cc == 4) ? SO(W_PV + i) : SO(W_Z));
+            a_out = ((l < 30) ? SO(W_TT + 6 * cc + i) : SO(W_DUMMY));
+        }
+        {
+            // round B: 21 symmetric pairs (c1 <= c2) over (x,y,psi,v,a,df); 6 vector entries; 4 copy lanes
+            //   F[c1][c2] = H + sum_{i<4} M[i][c1] That[i][c2] + X,  X = That[4][c2] (c1 = a) | That[5][c2] (c1 = df) | 0
+            int c1 = 0, c2 = 0, kind = 0;  // 0 pair, 1 vector, 2 copy, 3 idle
+            if (l < 21) { int t = l; while (t >= 6 - c1) { t -= 6 - c1; c1++; } c2 = c1 + t; }
+            else if (l < 27) { c1 = l - 21; kind = 1; }
+            else if (l < 31) kind = 2;
+            else kind = 3;
+            int mb, mk, tb, xb, hf, o1, o2;
+            if (kind >= 2) { mb = SO(W_Z); mk = 0; }
+            else if (c1 < 2) { mb = (c1 == 0) ? SO(W_EX) : SO(W_EY); mk = 0; }
+            else { mb = SO(W_SD + SD_CF + 4 * (c1 - 2)); mk = 1; }
+            // That column c2 (rows 0..5 contiguous): P row c2 (symmetric) for x,y; TT column otherwise; TT[4] for the vector
+            if (kind == 1) tb = SO(W_TT + 24);
+            else if (kind == 0) tb = (c2 < 2) ? SO(W_P + 6 * c2) : SO(W_TT + 6 * (c2 - 2));
+            else tb = SO(W_Z);
+            xb = (kind <= 1 && c1 == 4) ? tb + SO(4) : (kind <= 1 && c1 == 5) ? tb + SO(5) : SO(W_Z);
+            hf = SD_ZERO;
+            if (kind == 1) hf = SD_GX + c1;
+            else if (kind == 0) {
+                if (c1 == c2) hf = (c1 == 0) ? SD_HXX : (c1 == 1) ? SD_HYY : (c1 == 2) ? SD_HPP : (c1 == 3) ? SD_HVV : (c1 == 4) ? SD_HAA : SD_HDD;
+                else if (c1 == 2 && c2 == 3) hf = SD_HPV;
+                else if (c1 == 2 && c2 == 5) hf = SD_HPD;
+                else if (c1 == 3 && c2 == 5) hf = SD_HVD;
+            } else if (kind == 2) hf = (l == 27) ? SD_CA : (l == 28) ? SD_CD : (l == 29) ? SD_NCA : SD_NCD;
+            if (kind == 0) { o1 = SO(W_F + 6 * c1 + c2); o2 = SO(W_F + 6 * c2 + c1); }
+            else if (kind == 1) { o1 = o2 = SO(W_FV + c1); }
+            else if (kind == 2) { o1 = o2 = (l == 27) ? SO(W_C) : (l == 28) ? SO(W_C + 1) : (l == 29) ? SO(W_NC) : SO(W_NC + 3); }
+            else { o1 = o2 = SO(W_DUMMY); }
+            b_m = (mb); b_mk = (mk); b_t = (tb); b_x = (xb); b_h = (SO(W_SD + hf));
+            b_o1 = (o1); b_o2 = (o2);
+        }
+        {
+            // 21 symmetric pairs (i <= j) over xi, then 6 vector entries.
+            // P'[i][j] = F8[i][j] + F8[i][a] K[0][j] + F8[i][df] K[1][j],  K[.][j] = -Fuu^{-1} (F8[j][a], F8[j][df])
+            int i = 0, j = 0, vec = 0, act = 1;
+            if (l < 21) { int t = l; while (t >= 6 - i) { t -= 6 - i; i++; } j = i + t; }
+            else if (l < 27) { i = l - 21; vec = 1; }
+            else act = 0;
+            int f0;
+            if (vec) f0 = (i < 4) ? SO(W_FV + i) : SO(W_Z);
+            else if (i < 4 && j < 4) f0 = SO(W_F + 6 * i + j);
+            else if (i == 4 && j == 4) f0 = SO(W_C);
+            else if (i == 5 && j == 5) f0 = SO(W_C + 1);
+            else f0 = SO(W_Z);
+            auto pairof = [](int q) {   // (F8[q][a], F8[q][df]) for q over xi; q = 6: (f_a, f_df)
+                return (q < 4) ? SO(W_F + 6 * q + 4) : (q == 4) ? SO(W_NC) : (q == 5) ? SO(W_NC + 2) : SO(W_FV + 4);
+            };
+            const int fi = pairof(i), fj = pairof(vec ? 6 : j);
+            int o1, o2;
+            if (!act) { o1 = o2 = SO(W_DUMMY); }
+            else if (vec) { o1 = o2 = SO(W_PV + i); }
+            else { o1 = SO(W_P + 6 * i + j); o2 = SO(W_P + 6 * j + i); }
+            // gain storage: the diagonal pairs (j,j) hold K[.][j], vector lane i = 0 holds K[.][6]
+            int ks = -1;
+            if (act && !vec && i == j) ks = j;
+            if (act && vec && i == 0) ks = 6;
+            const int kb = SO(W_SD + (N + 1) * SDS + (N - 1) * KST_STRIDE);  // gains of stage N-1
+            e_f0 = (f0); e_fi = (fi); e_fj = (fj); e_o1 = (o1); e_o2 = (o2);
+            e_k0 = (ks >= 0 ? kb + SO(ks) : SO(W_DUMMY));
+            e_k1 = (ks >= 0 ? kb + SO(7 + ks) : SO(W_DUMMY));
+        }
+    out[0] = a_p; out[1] = a_m; out[2] = a_ex; out[3] = a_out; out[4] = b_m; out[5] = b_mk; out[6] = b_t; out[7] = b_x; out[8] = b_h;
+    out[9] = b_o1; out[10] = b_o2; out[11] = e_f0; out[12] = e_fi; out[13] = e_fj; out[14] = e_o1; out[15] = e_o2;
+    out[16] = e_k0; out[17] = e_k1; out[18] = (e_k0 == SO(W_DUMMY)) ? 0 : SO(KST_STRIDE); out[19] = 0;
+}
 
 // W = warps per team (1: a warp per problem; 2, 3: a block per problem)
 template <int W>
@@ -641,81 +724,17 @@ struct TeamSolver {
     }
     MPC_DEV bool riccati_backward_warp() {
         const int l = lane_id();
-        // lane roles: shared-memory offsets, recomputed per call and laundered so that they stay in
+        // lane roles: shared-memory offsets of this lane's operands in the three rounds, read from the
+        // table mpcb200_create computed once (riccati_roles) and laundered so that they stay in
         // registers through the stage loop instead of being rematerialised at every use
-        int a_p, a_m, a_ex, a_out, b_m, b_mk, b_t, b_x, b_h, b_o1, b_o2, e_f0, e_fi, e_fj, e_o1, e_o2, e_k0, e_k1;
-        {
-            // round A: lane (i, cc) -> TT[cc][i] = sum_{j<4} P[i][j] CF[cc][j] + X,  X = 0 | P[i][4] | P[i][5] | p[i]
-            const int i = (l < 24) ? (l >> 2) : (l < 30 ? l - 24 : 0);
-            const int cc = (l < 24) ? (l & 3) : 4;
-            a_p = launder(SO(W_P + 6 * i));
-            a_m = launder(SO(W_SD + SD_CF + 4 * cc));
-            a_ex = launder((l >= 30) ? SO(W_Z) : (cc == 2) ? SO(W_P + 6 * i + 4) : (cc == 3) ? SO(W_P + 6 * i + 5) : (cc == 4) ? SO(W_PV + i) : SO(W_Z));
-            a_out = launder((l < 30) ? SO(W_TT + 6 * cc + i) : SO(W_DUMMY));
-        }
-        {
-            // round B: 21 symmetric pairs (c1 <= c2) over (x,y,psi,v,a,df); 6 vector entries; 4 copy lanes
-            //   F[c1][c2] = H + sum_{i<4} M[i][c1] That[i][c2] + X,  X = That[4][c2] (c1 = a) | That[5][c2] (c1 = df) | 0
-            int c1 = 0, c2 = 0, kind = 0;  // 0 pair, 1 vector, 2 copy, 3 idle
-            if (l < 21) { int t = l; while (t >= 6 - c1) { t -= 6 - c1; c1++; } c2 = c1 + t; }
-            else if (l < 27) { c1 = l - 21; kind = 1; }
-            else if (l < 31) kind = 2;
-            else kind = 3;
-            int mb, mk, tb, xb, hf, o1, o2;
-            if (kind >= 2) { mb = SO(W_Z); mk = 0; }
-            else if (c1 < 2) { mb = (c1 == 0) ? SO(W_EX) : SO(W_EY); mk = 0; }
-            else { mb = SO(W_SD + SD_CF + 4 * (c1 - 2)); mk = 1; }
-            // That column c2 (rows 0..5 contiguous): P row c2 (symmetric) for x,y; TT column otherwise; TT[4] for the vector
-            if (kind == 1) tb = SO(W_TT + 24);
-            else if (kind == 0) tb = (c2 < 2) ? SO(W_P + 6 * c2) : SO(W_TT + 6 * (c2 - 2));
-            else tb = SO(W_Z);
-            xb = (kind <= 1 && c1 == 4) ? tb + SO(4) : (kind <= 1 && c1 == 5) ? tb + SO(5) : SO(W_Z);
-            hf = SD_ZERO;
-            if (kind == 1) hf = SD_GX + c1;
-            else if (kind == 0) {
-                if (c1 == c2) hf = (c1 == 0) ? SD_HXX : (c1 == 1) ? SD_HYY : (c1 == 2) ? SD_HPP : (c1 == 3) ? SD_HVV : (c1 == 4) ? SD_HAA : SD_HDD;
-                else if (c1 == 2 && c2 == 3) hf = SD_HPV;
-                else if (c1 == 2 && c2 == 5) hf = SD_HPD;
-                else if (c1 == 3 && c2 == 5) hf = SD_HVD;
-            } else if (kind == 2) hf = (l == 27) ? SD_CA : (l == 28) ? SD_CD : (l == 29) ? SD_NCA : SD_NCD;
-            if (kind == 0) { o1 = SO(W_F + 6 * c1 + c2); o2 = SO(W_F + 6 * c2 + c1); }
-            else if (kind == 1) { o1 = o2 = SO(W_FV + c1); }
-            else if (kind == 2) { o1 = o2 = (l == 27) ? SO(W_C) : (l == 28) ? SO(W_C + 1) : (l == 29) ? SO(W_NC) : SO(W_NC + 3); }
-            else { o1 = o2 = SO(W_DUMMY); }
-            b_m = launder(mb); b_mk = launder(mk); b_t = launder(tb); b_x = launder(xb); b_h = launder(SO(W_SD + hf));
-            b_o1 = launder(o1); b_o2 = launder(o2);
-        }
-        {
-            // 21 symmetric pairs (i <= j) over xi, then 6 vector entries.
-            // P'[i][j] = F8[i][j] + F8[i][a] K[0][j] + F8[i][df] K[1][j],  K[.][j] = -Fuu^{-1} (F8[j][a], F8[j][df])
-            int i = 0, j = 0, vec = 0, act = 1;
-            if (l < 21) { int t = l; while (t >= 6 - i) { t -= 6 - i; i++; } j = i + t; }
-            else if (l < 27) { i = l - 21; vec = 1; }
-            else act = 0;
-            int f0;
-            if (vec) f0 = (i < 4) ? SO(W_FV + i) : SO(W_Z);
-            else if (i < 4 && j < 4) f0 = SO(W_F + 6 * i + j);
-            else if (i == 4 && j == 4) f0 = SO(W_C);
-            else if (i == 5 && j == 5) f0 = SO(W_C + 1);
-            else f0 = SO(W_Z);
-            auto pairof = [](int q) {   // (F8[q][a], F8[q][df]) for q over xi; q = 6: (f_a, f_df)
-                return (q < 4) ? SO(W_F + 6 * q + 4) : (q == 4) ? SO(W_NC) : (q == 5) ? SO(W_NC + 2) : SO(W_FV + 4);
-            };
-            const int fi = pairof(i), fj = pairof(vec ? 6 : j);
-            int o1, o2;
-            if (!act) { o1 = o2 = SO(W_DUMMY); }
-            else if (vec) { o1 = o2 = SO(W_PV + i); }
-            else { o1 = SO(W_P + 6 * i + j); o2 = SO(W_P + 6 * j + i); }
-            // gain storage: the diagonal pairs (j,j) hold K[.][j], vector lane i = 0 holds K[.][6]
-            int ks = -1;
-            if (act && !vec && i == j) ks = j;
-            if (act && vec && i == 0) ks = 6;
-            const int kb = SO(W_SD + (N + 1) * SDS + (N - 1) * KST_STRIDE);  // gains of stage N-1
-            e_f0 = launder(f0); e_fi = launder(fi); e_fj = launder(fj); e_o1 = launder(o1); e_o2 = launder(o2);
-            e_k0 = launder(ks >= 0 ? kb + SO(ks) : SO(W_DUMMY));
-            e_k1 = launder(ks >= 0 ? kb + SO(7 + ks) : SO(W_DUMMY));
-        }
-        const int kstep = launder((e_k0 == SO(W_DUMMY)) ? 0 : SO(KST_STRIDE));
+        int rl[ROLE_STRIDE];
+        ld_roles(c.roles + l * ROLE_STRIDE, rl);
+        const int a_p = launder(rl[0]), a_m = launder(rl[1]), a_ex = launder(rl[2]), a_out = launder(rl[3]);
+        const int b_m = launder(rl[4]), b_mk = launder(rl[5]), b_t = launder(rl[6]), b_x = launder(rl[7]), b_h = launder(rl[8]);
+        const int b_o1 = launder(rl[9]), b_o2 = launder(rl[10]);
+        const int e_f0 = launder(rl[11]), e_fi = launder(rl[12]), e_fj = launder(rl[13]), e_o1 = launder(rl[14]), e_o2 = launder(rl[15]);
+        int e_k0 = launder(rl[16]), e_k1 = launder(rl[17]);
+        const int kstep = launder(rl[18]);
         {   // terminal cost-to-go from record N
             const int rN = SO(W_SD + N * SDS);
             for (int e = l; e < 36; e += 32) {
@@ -761,11 +780,13 @@ struct TeamSolver {
                 const double faa = fa.x, fad = fa.y;
                 const double det = faa * fdd - fad * fad;
                 if (!(faa > 0.0) || !(det > 0.0)) { ok = false; break; }
+                // Fuu^{-1} = adj(Fuu) / det: everything that does not need 1/det is computed while the
+                // reciprocal is in flight, so only one multiply-add follows it
                 const double idet = 1.0 / det;
-                const double i00 = fdd * idet, i01 = -fad * idet, i11 = faa * idet;
-                const double k0 = -(i00 * fj.x + i01 * fj.y), k1 = -(i01 * fj.x + i11 * fj.y);
-                sts(sm, e_k0, k0); sts(sm, e_k1, k1);
-                const double o = f0 + (fi.x * k0 + fi.y * k1);
+                const double a0 = fdd * fj.x - fad * fj.y, a1 = faa * fj.y - fad * fj.x;   // adj(Fuu) (F8[j][a], F8[j][df])
+                const double num = fi.x * a0 + fi.y * a1;
+                sts(sm, e_k0, -a0 * idet); sts(sm, e_k1, -a1 * idet);
+                const double o = f0 - num * idet;
                 sts(sm, e_o1, o); sts(sm, e_o2, o);
             }
             syncwarp();
@@ -789,13 +810,15 @@ struct TeamSolver {
             const d2 cp = lds2(sm, r + SO(SD_CF + 0)), cv = lds2(sm, r + SO(SD_CF + 4)), cd = lds2(sm, r + SO(SD_CF + 12));
             const double a23 = lds(sm, r + SO(SD_CF + 6)), b2 = lds(sm, r + SO(SD_CF + 14));
             const d2 r01 = lds2(sm, r + SO(SD_R)), r23 = lds2(sm, r + SO(SD_R + 2));
-            const double ua = (ka0.x * s0 + ka0.y * s1 + ka1.x * s2) + (ka1.y * s3 + ka2.x * pa + ka2.y * pd) + kx.x;
-            const double ud = (kx.y * s0 + kd0.x * s1 + kd0.y * s2) + (kd1.x * s3 + kd1.y * pa + kd2.x * pd) + kd2.y;
+            // the recursion is one dependent chain per problem: the terms that do not need the values
+            // produced last (s0..s3 for the inputs, the inputs for the next state) are summed first
+            const double ua = ((ka2.x * pa + ka2.y * pd) + kx.x) + ((ka0.x * s0 + ka0.y * s1) + (ka1.x * s2 + ka1.y * s3));
+            const double ud = ((kd1.y * pa + kd2.x * pd) + kd2.y) + ((kx.y * s0 + kd0.x * s1) + (kd0.y * s2 + kd1.x * s3));
             if (s == k) { D.dsx = s0; D.dsy = s1; D.dsp = s2; D.dsv = s3; D.dua = ua; D.dud = ud; }
-            const double n0 = s0 + cp.x * s2 + cv.x * s3 + cd.x * ud + r01.x;
-            const double n1 = s1 + cp.y * s2 + cv.y * s3 + cd.y * ud + r01.y;
-            const double n2 = s2 + a23 * s3 + b2 * ud + r23.x;
-            const double n3 = s3 + c.dt * ua + r23.y;
+            const double n0 = ((s0 + r01.x) + (cp.x * s2 + cv.x * s3)) + cd.x * ud;
+            const double n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
+            const double n2 = ((s2 + r23.x) + a23 * s3) + b2 * ud;
+            const double n3 = (s3 + r23.y) + c.dt * ua;
             s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
             kp += SO(KST_STRIDE); r += SO(SDS);
         }
@@ -1137,28 +1160,35 @@ struct TeamSolver {
                     treduce<OP_SUM, 2>(r2);
                     sumy = r2[0]; sumz = r2[1];
                 }
-                const double sd = dmax_(K_S_MAX, (sumy + sumz) / (double)(my + nz)) / K_S_MAX;
-                const double sc = dmax_(K_S_MAX, sumz / (double)nz) / K_S_MAX;
+                // s_d, s_c = max(s_max, mean |multiplier|) / s_max: exactly 1 unless the multipliers are huge
+                const double sty = sumy + sumz;
+                const bool big_d = sty > K_S_MAX * (double)(my + nz), big_c = sumz > K_S_MAX * (double)nz;
+                double sd = 1.0, sc = 1.0;
+                if (big_d) sd = sty / (double)(my + nz) / K_S_MAX;
+                if (big_c) sc = sumz / (double)nz / K_S_MAX;
                 // complementarity of this lane: max |slack * z - t| over its bound pairs
+                // (the ten slack * z products once; pairs this thread does not own repeat its v pair,
+                // which every stage thread owns, so that they do not change the maximum)
+                double pz[10];
+                pz[0] = (L.sv - c.vLo) * Z.zvL; pz[1] = (c.vHi - L.sv) * Z.zvU;
+                pz[2] = isU ? (L.ua - c.aLo) * Z.zaL : pz[0]; pz[3] = isU ? (c.aHi - L.ua) * Z.zaU : pz[0];
+                pz[4] = isU ? (L.ud - c.dLo) * Z.zdL : pz[0]; pz[5] = isU ? (c.dHi - L.ud) * Z.zdU : pz[0];
+                {
+                    const double h0 = rHi(0), h1 = rHi(1);
+                    pz[6] = isR ? (L.rs[0] + h0) * Z.rvL[0] : pz[0]; pz[7] = isR ? (h0 - L.rs[0]) * Z.rvU[0] : pz[0];
+                    pz[8] = isR ? (L.rs[1] + h1) * Z.rvL[1] : pz[0]; pz[9] = isR ? (h1 - L.rs[1]) * Z.rvU[1] : pz[0];
+                }
                 auto compl_local = [&](double t) {
                     double m = 0.0;
-                    if (isS) { m = dmax_(m, fabs((L.sv - c.vLo) * Z.zvL - t)); m = dmax_(m, fabs((c.vHi - L.sv) * Z.zvU - t)); }
-                    if (isU) {
-                        m = dmax_(m, fabs((L.ua - c.aLo) * Z.zaL - t)); m = dmax_(m, fabs((c.aHi - L.ua) * Z.zaU - t));
-                        m = dmax_(m, fabs((L.ud - c.dLo) * Z.zdL - t)); m = dmax_(m, fabs((c.dHi - L.ud) * Z.zdU - t));
-                    }
-                    if (isR) for (int i = 0; i < 2; i++) {
-                        const double h = rHi(i);
-                        m = dmax_(m, fabs((L.rs[i] + h) * Z.rvL[i] - t)); m = dmax_(m, fabs((h - L.rs[i]) * Z.rvU[i] - t));
-                    }
-                    return m;
+                    for (int i = 0; i < 10; i++) m = dmax_(m, fabs(pz[i] - t));
+                    return isS ? m : 0.0;
                 };
                 cm0 = compl_local(0.0); cmm = compl_local(mu);
                 // E_0 and E_mu in one pass
-                const double dcv = dmax_(di / sd, cv);
+                const double dcv = dmax_(big_d ? di / sd : di, cv);
                 double e0, em;
                 {
-                    double r2[2] = {dmax_(dcv, cm0 / sc), dmax_(dcv, cmm / sc)};
+                    double r2[2] = {dmax_(dcv, big_c ? cm0 / sc : cm0), dmax_(dcv, big_c ? cmm / sc : cmm)};
                     treduce<OP_MAX, 2>(r2);
                     e0 = r2[0]; em = r2[1];
                 }
@@ -1184,7 +1214,8 @@ struct TeamSolver {
                     mu = nm; tau = dmax_(K_TAU_MIN, 1.0 - mu);
                     nfilt = 0;
                     if (tiny_last) { tiny_last = false; break; }
-                    em = tmax(dmax_(dcv, compl_local(mu) / sc));
+                    const double cl = compl_local(mu);
+                    em = tmax(dmax_(dcv, big_c ? cl / sc : cl));
                 }
                 if (ret == -3) break;
                 dw = 0.0;

@@ -57,6 +57,9 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
     BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj};
     KCfg kc = *cfg;
     kcfg_finalize(kc);
+    std::vector<int> roles(32 * ROLE_STRIDE);
+    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, W_SD_OF(team_warps(kc.N)), roles.data() + l * ROLE_STRIDE);
+    kc.roles = roles.data();
     std::vector<double> smem_raw(smem_doubles_per_team(kc.N) + 2, 0.0);
     double* smem = smem_raw.data();
     if (((size_t)smem) & 15) smem++;   // 16-byte alignment like the device's shared memory
@@ -80,12 +83,15 @@ extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, 
                            double target_vel, double* log, double* final_state) {
     KCfg kc = *cfg;
     kcfg_finalize(kc);
+    std::vector<int> roles(32 * ROLE_STRIDE);
+    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, W_SD_OF(1), roles.data() + l * ROLE_STRIDE);
+    kc.roles = roles.data();
     RolloutArgs a;
     memset(&a, 0, sizeof(a));
     a.pose0 = pose0; a.path_of = path_of;
     for (int i = 0; i < 3; i++) { a.paths[i].n = n0; a.paths[i].t = t; a.paths[i].X = X; a.paths[i].Y = Y; a.paths[i].psi = psi; a.paths[i].s = s; }
     a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel; a.log = log; a.final_state = final_state; a.B = B;
-    std::vector<double> smem_raw(4096 + 2, 0.0);
+    std::vector<double> smem_raw(smem_doubles_per_team(kc.N) + 2, 0.0);
     double* smem = smem_raw.data();
     if (((size_t)smem) & 15) smem++;
     for (long b = 0; b < B; b++) {

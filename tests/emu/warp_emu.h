@@ -129,4 +129,5 @@ struct d2 { double x, y; };
 MPC_DEV d2 lds2(smem_t b, int off) { d2 r; r.x = b[off]; r.y = b[off + 1]; return r; }
 MPC_DEV void sts(smem_t b, int off, double v) { b[off] = v; }
 MPC_DEV int launder(int v) { return v; }
+MPC_DEV void ld_roles(const int* p, int* out) { for (int i = 0; i < 20; i++) out[i] = p[i]; }
 }  // namespace mpcb200
