@@ -795,35 +795,41 @@ struct TeamSolver {
         return ok;
     }
 
-    // forward sweep (every lane runs the scalar recursion; lane k keeps stage k)
+    // forward sweep: one scalar recursion per problem.  Eight lanes of one warp run it (a quarter
+    // warp: every broadcast shared-memory load is one wavefront instead of four) and write each
+    // stage's step straight into that stage's per-thread fields.
     MPC_DEV void riccati_forward() {
-        int kp = SO(W_SD + (N + 1) * SDS);
-        int r = SO(W_SD);
-        const d2 i01 = lds2(sm, SO(W_SD + N * SDS + SD_R)), i23 = lds2(sm, SO(W_SD + N * SDS + SD_R + 2));  // ds_0
-        double s0 = i01.x, s1 = i01.y, s2 = i23.x, s3 = i23.y;
-        double pa = 0.0, pd = 0.0;
-        StepState D;
-        D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0;
-        for (int s = 0; s < N; s++) {
-            const d2 ka0 = lds2(sm, kp), ka1 = lds2(sm, kp + SO(2)), ka2 = lds2(sm, kp + SO(4)), kx = lds2(sm, kp + SO(6));
-            const d2 kd0 = lds2(sm, kp + SO(8)), kd1 = lds2(sm, kp + SO(10)), kd2 = lds2(sm, kp + SO(12));
-            const d2 cp = lds2(sm, r + SO(SD_CF + 0)), cv = lds2(sm, r + SO(SD_CF + 4)), cd = lds2(sm, r + SO(SD_CF + 12));
-            const double a23 = lds(sm, r + SO(SD_CF + 6)), b2 = lds(sm, r + SO(SD_CF + 14));
-            const d2 r01 = lds2(sm, r + SO(SD_R)), r23 = lds2(sm, r + SO(SD_R + 2));
-            // the recursion is one dependent chain per problem: the terms that do not need the values
-            // produced last (s0..s3 for the inputs, the inputs for the next state) are summed first
-            const double ua = ((ka2.x * pa + ka2.y * pd) + kx.x) + ((ka0.x * s0 + ka0.y * s1) + (ka1.x * s2 + ka1.y * s3));
-            const double ud = ((kd1.y * pa + kd2.x * pd) + kd2.y) + ((kx.y * s0 + kd0.x * s1) + (kd0.y * s2 + kd1.x * s3));
-            if (s == k) { D.dsx = s0; D.dsy = s1; D.dsp = s2; D.dsv = s3; D.dua = ua; D.dud = ud; }
-            const double n0 = ((s0 + r01.x) + (cp.x * s2 + cv.x * s3)) + cd.x * ud;
-            const double n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
-            const double n2 = ((s2 + r23.x) + a23 * s3) + b2 * ud;
-            const double n3 = (s3 + r23.y) + c.dt * ua;
-            s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
-            kp += SO(KST_STRIDE); r += SO(SDS);
+        if (lane_id() < 8 && (W == 1 || (k >> 5) == 0)) {
+            int kp = SO(W_SD + (N + 1) * SDS);
+            int r = SO(W_SD);
+            const int st = lfs();
+            int fa = SO(lf_offset(N)) + LF_DX * st;   // field LF_DX of stage 0
+            const d2 i01 = lds2(sm, SO(W_SD + N * SDS + SD_R)), i23 = lds2(sm, SO(W_SD + N * SDS + SD_R + 2));  // ds_0
+            double s0 = i01.x, s1 = i01.y, s2 = i23.x, s3 = i23.y;
+            double pa = 0.0, pd = 0.0;
+            for (int s = 0; s < N; s++) {
+                const d2 ka0 = lds2(sm, kp), ka1 = lds2(sm, kp + SO(2)), ka2 = lds2(sm, kp + SO(4)), kx = lds2(sm, kp + SO(6));
+                const d2 kd0 = lds2(sm, kp + SO(8)), kd1 = lds2(sm, kp + SO(10)), kd2 = lds2(sm, kp + SO(12));
+                const d2 cp = lds2(sm, r + SO(SD_CF + 0)), cv = lds2(sm, r + SO(SD_CF + 4)), cd = lds2(sm, r + SO(SD_CF + 12));
+                const double a23 = lds(sm, r + SO(SD_CF + 6)), b2 = lds(sm, r + SO(SD_CF + 14));
+                const d2 r01 = lds2(sm, r + SO(SD_R)), r23 = lds2(sm, r + SO(SD_R + 2));
+                // the recursion is one dependent chain per problem: the terms that do not need the values
+                // produced last (s0..s3 for the inputs, the inputs for the next state) are summed first
+                const double ua = ((ka2.x * pa + ka2.y * pd) + kx.x) + ((ka0.x * s0 + ka0.y * s1) + (ka1.x * s2 + ka1.y * s3));
+                const double ud = ((kd1.y * pa + kd2.x * pd) + kd2.y) + ((kx.y * s0 + kd0.x * s1) + (kd0.y * s2 + kd1.x * s3));
+                sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
+                sts(sm, fa + 4 * st, ua); sts(sm, fa + 5 * st, ud);
+                const double n0 = ((s0 + r01.x) + (cp.x * s2 + cv.x * s3)) + cd.x * ud;
+                const double n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
+                const double n2 = ((s2 + r23.x) + a23 * s3) + b2 * ud;
+                const double n3 = (s3 + r23.y) + c.dt * ua;
+                s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
+                kp += SO(KST_STRIDE); r += SO(SDS); fa += SO(1);
+            }
+            sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
+            sts(sm, fa + 4 * st, 0.0); sts(sm, fa + 5 * st, 0.0);
         }
-        if (k == N) { D.dsx = s0; D.dsy = s1; D.dsp = s2; D.dsv = s3; }
-        st_dx(D);
+        tsync();
     }
 
     // new equality multipliers from stationarity in the state variables (parallel suffix sums),
