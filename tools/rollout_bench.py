@@ -1,0 +1,96 @@
+#!/usr/bin/env python
+"""Monte-Carlo closed-loop rollouts (BASELINE.json configs[3]): V vehicles x T control steps, N = 8, paths 1-3
+round-robin, warm-started solve every step, plant + reference generation + solves in ONE kernel per GPU.
+
+    python tools/rollout_bench.py [--vehicles 16384] [--steps 500]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/rollout_bench.py ...
+
+Strong scaling: the fleet is cut into contiguous slices, one per rank; a vehicle stays on its GPU for all
+T steps and nothing crosses GPUs until the final all-gather of the per-vehicle summary record
+(final pose error, converged fraction, mean iterations: 4 doubles).  Prints one JSON line on rank 0."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def fleet(V, seed=20261018):
+    """Initial poses: start sample of the vehicle's path + N(0, 0.3 m), N(0, 0.3 m), N(0, 0.05 rad), v = 0."""
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    trajs = [GPSRefTrajectory(mat_filename=p) for p in (1, 2, 3)]
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    nz = rng.normal(size=(V, 3)) * np.array([0.3, 0.3, 0.05])
+    path_of = (np.arange(V) % 3).astype(np.int32)
+    start = np.stack([trajs[p].trajectory[0, [4, 5, 3]] for p in path_of])
+    return trajs, path_of, start + nz
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--vehicles", type=int, default=16384)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from mkz_mpc_path_follower_b200 import capi, closed_loop, sharding
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    trajs, path_of, pose0 = fleet(args.vehicles)
+    lo, hi = sharding.shard_range(args.vehicles, world, rank)
+    s = capi.Solver(8, device=local)
+    for i, g in enumerate(trajs):
+        s.set_path(i, g.trajectory)
+    s.rollout(pose0[lo:lo + 64], path_of[lo:lo + 64], 5)    # warm-up (module load, clocks)
+    best = 1e30
+    for _ in range(args.reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = s.rollout(pose0[lo:hi], path_of[lo:hi], args.steps)
+        kern_ms = s.stats()["kernel_ms"]
+        wall = time.perf_counter() - t0
+        tm = torch.tensor([wall, kern_ms * 1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        if tm[0].item() < best:
+            best, best_kern = tm[0].item(), tm[1].item()
+    log = out["log"]
+    solved = log[:, :, 6] >= 0
+    rec = np.zeros((hi - lo, 4))
+    rec[:, 0] = (log[:, :, 6] == 0).sum(0) / np.maximum(1, solved.sum(0))   # Optimal fraction of the solves made
+    rec[:, 1] = log[:, :, 7].sum(0) / np.maximum(1, solved.sum(0))          # mean iterations
+    rec[:, 2] = solved.sum(0)
+    for p in range(3):
+        m = path_of[lo:hi] == p
+        if m.any():
+            rec[m, 3] = closed_loop.path_errors(log[-1:, m, :], trajs[p].trajectory)[0]
+    r = torch.from_numpy(rec).to(dev)
+    if world > 1:
+        sizes = [sharding.shard_range(args.vehicles, world, q)[1] - sharding.shard_range(args.vehicles, world, q)[0] for q in range(world)]
+        r = sharding.all_gather_records(r, sizes)
+    if rank == 0:
+        r = r.cpu().numpy()
+        n_solves = float(r[:, 2].sum())
+        print(json.dumps({
+            "what": "closed-loop rollouts, configs[3]", "vehicles": args.vehicles, "control_steps": args.steps, "n_gpus": world,
+            "scaling": "strong", "wall_s": best, "kernel_s": best_kern,
+            "vehicle_steps_per_s": args.vehicles * args.steps / best, "solves": n_solves, "solves_per_s": n_solves / best,
+            "optimal_frac": float((r[:, 0] * r[:, 2]).sum() / max(1.0, n_solves)), "mean_iters": float((r[:, 1] * r[:, 2]).sum() / max(1.0, n_solves)),
+            "final_path_error_m": {"median": float(np.median(r[:, 3])), "p99": float(np.quantile(r[:, 3], 0.99))},
+            "d2h_bytes": int(s.stats()["d2h_bytes"])}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
