@@ -81,6 +81,7 @@ struct KCfg {
 #define K_Y_INIT_MAX 1e3
 #define K_ACCEPT_TOL 1e-6
 #define K_ACCEPT_ITER 15
+#define K_MAX_RESTO 3      // restorations by rollout per solve (not an Ipopt option; see rollout_restore)
 #define K_EPS 2.220446049250313e-16
 
 MPC_HD void kcfg_finalize(KCfg& c) {
@@ -891,6 +892,61 @@ struct TeamSolver {
         return dmin_(1.0, tmin(a));
     }
 
+    // ------------------------------------------------------------------
+    // Restoration by rollout (oracle: ipm_rollout_restore).  The inputs of the current iterate are
+    // projected stage by stage onto the input box, the rate rows and the speed bounds, and the states
+    // are rolled out from the measured state (MKZMPCPathFollower.jl:115-123).  One serial recursion
+    // per problem, run by a quarter warp through the per-thread step fields (dead at this point).
+    // ------------------------------------------------------------------
+    MPC_DEV void rollout_restore() {
+        const int st = lfs();
+        {
+            StepState D;
+            D.dsx = D.dsy = D.dsp = D.dsv = 0.0; D.dua = L.ua; D.dud = L.ud;
+            st_dx(D);
+        }
+        tsync();
+        if (lane_id() < 8 && (W == 1 || (k >> 5) == 0)) {
+            int fa = SO(lf_offset(N)) + LF_DX * st;   // field LF_DX of stage 0
+            double s0 = cst(0), s1 = cst(1), s2 = cst(2), s3 = cst(3);
+            double pa = cst(5), pd = cst(4);
+            for (int s = 0; s < N; s++) {
+                double ua = lds(sm, fa + 4 * st), ud = lds(sm, fa + 5 * st);
+                if (s != 1) {   // rate rows exist for the first move and for pairs (s, s-1), s >= 2
+                    const double h = (s == 0) ? c.dtc : c.dt;
+                    const double la = 0.98 * c.admax * h, ld = 0.98 * c.sdmax * h;
+                    ua = dmin_(dmax_(ua, pa - la), pa + la);
+                    ud = dmin_(dmax_(ud, pd - ld), pd + ld);
+                }
+                ua = dmin_(dmax_(ua, -c.amax), c.amax);
+                ud = dmin_(dmax_(ud, -c.smax), c.smax);
+                ua = dmin_(dmax_(ua, (c.vmin - s3) / c.dt), (c.vmax - s3) / c.dt);   // v_{s+1} = v_s + dt acc stays inside [v_min, v_max]
+                sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
+                sts(sm, fa + 4 * st, ua); sts(sm, fa + 5 * st, ud);
+                double sd, cd, sps, cps;
+                mpc_sincos(ud, &sd, &cd);
+                mpc_sincos(s2, &sps, &cps);
+                const double r = c.rfrac;
+                const double inv = sqrt(1.0 / (cd * cd + r * r * sd * sd));
+                const double cb = cd * inv, sb = r * sd * inv;
+                const double n0 = s0 + c.dt * (s3 * (cps * cb - sps * sb));
+                const double n1 = s1 + c.dt * (s3 * (sps * cb + cps * sb));
+                const double n2 = s2 + c.dt * (s3 / c.Lb * sb);
+                const double n3 = s3 + c.dt * ua;
+                s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
+                fa += SO(1);
+            }
+            sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
+            sts(sm, fa + 4 * st, 0.0); sts(sm, fa + 5 * st, 0.0);
+        }
+        tsync();
+        if (isS) {
+            StepState D;
+            ld_dx(D);
+            L.sx = D.dsx; L.sy = D.dsy; L.sp = D.dsp; L.sv = D.dsv; L.ua = D.dua; L.ud = D.dud;
+        }
+    }
+
     MPC_DEV bool nlp_feasible() const {
         const double e = 1e-8;
         const double lim_d = c.sdmax * c.dtc, lim_a = c.admax * c.dtc;
@@ -907,12 +963,6 @@ struct TeamSolver {
     // ------------------------------------------------------------------
     MPC_DEV Result solve() {
         Result res; res.status = 4; res.iters = 0; res.cost = 0.0;
-        {
-            StepState D;
-            D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0; D.drs[0] = D.drs[1] = 0.0;
-            D.nyx = D.nyy = D.nyp = D.nyv = 0.0; D.nyd[0] = D.nyd[1] = 0.0;
-            st_dx(D); st_drs(D); st_dy(D);
-        }
         L.rs[0] = L.rs[1] = 0.0;
         L.ryd[0] = L.ryd[1] = 0.0; L.yx = L.yy = L.yp = L.yv = 0.0;
 
@@ -927,31 +977,11 @@ struct TeamSolver {
             gm = tmax(dmax_(gm, dmax_(fabs(g.a), fabs(g.d))));
             sigma = (gm > K_SCALE_MAX_GRAD) ? dmax_(K_SCALE_MAX_GRAD / gm, 1e-8) : 1.0;
         }
-        if (feasible) {
-            // ---- push into the interior, slacks = d(x) pushed, bound multipliers = 1
-            if (isS) push_interior(L.sv, c.vLo, c.vHi);
-            if (isU) { push_interior(L.ua, c.aLo, c.aHi); push_interior(L.ud, c.dLo, c.dHi); }
-            double prv[2];
-            { const double u[2] = {L.ua, L.ud}; xprev<2>(u, prv); }
-            const double pa = prv[0], pd = prv[1];
-            if (isR) {
-                const double h0 = rHi(0), h1 = rHi(1);
-                L.rs[0] = L.ud - ((k == 0) ? cst(4) : pd);
-                L.rs[1] = L.ua - ((k == 0) ? cst(5) : pa);
-                push_interior(L.rs[0], -h0, h0); push_interior(L.rs[1], -h1, h1);
-            }
-        }
-        {
-            BoundMult Z;
-            Z.zvL = Z.zvU = (feasible && isS) ? 1.0 : 0.0;
-            Z.zaL = Z.zaU = Z.zdL = Z.zdU = (feasible && isU) ? 1.0 : 0.0;
-            Z.rvL[0] = Z.rvL[1] = Z.rvU[0] = Z.rvU[1] = (feasible && isR) ? 1.0 : 0.0;
-            st_z(Z);
-        }
-
-        enum { PH_EVAL0 = 0, PH_LS, PH_BEGIN, PH_PD, PH_RESOLVE_EVAL, PH_RESOLVE, PH_TRIAL, PH_SOC };
-        int phase = PH_EVAL0;
-        bool do_solve = false, do_eval = true, eval_ftb = false;
+        enum { PH_INIT = 0, PH_EVAL0, PH_LS, PH_BEGIN, PH_PD, PH_RESOLVE_EVAL, PH_RESOLVE, PH_TRIAL, PH_SOC, PH_RESTO };
+        int phase = PH_INIT;
+        bool do_solve = false, do_eval = false, eval_ftb = false;
+        bool resto_check = false;
+        int n_resto = 0;
         int req = 0;
         double ev_alpha = 0.0;
 
@@ -1049,7 +1079,10 @@ struct TeamSolver {
                     }
                     alpha_min *= K_ALPHA_MIN_FRAC;
                     alpha *= 0.5; nsteps++;
-                    if (!(alpha > alpha_min)) { ret = -2; break; }  // Ipopt would enter the restoration phase
+                    if (!(alpha > alpha_min)) {   // Ipopt would enter the restoration phase
+                        if (n_resto < K_MAX_RESTO) { phase = PH_RESTO; continue; }
+                        ret = -2; break;
+                    }
                     ev_alpha = alpha; do_eval = true; phase = PH_TRIAL;
                     continue;
                 }
@@ -1111,7 +1144,57 @@ struct TeamSolver {
                 iter++;
                 phase = PH_BEGIN;
             }
+            if (phase == PH_RESTO) {
+                // The line search failed where Ipopt would enter its restoration phase.  That phase is
+                // not restated; instead the iterate is replaced by the rollout of its own (projected)
+                // inputs, which satisfies the equality rows by construction, and the iteration is
+                // re-initialised there with mu and the filter kept (oracle: ipm_rollout_restore).
+                n_resto++;
+                if (nfilt < NFILT_MAX) {   // PrepareRestoPhaseStart: the point that is left enters the filter
+                    if (k == nfilt) { f_phi = phi - K_GAMMA_PHI * cur_theta; f_theta = (1.0 - K_GAMMA_THETA) * cur_theta; }
+                    nfilt++;
+                }
+                rollout_restore();
+                L.yx = L.yy = L.yp = L.yv = 0.0; L.ryd[0] = L.ryd[1] = 0.0;
+                resto_check = true; tiny_last = false;
+                iter++;
+                phase = PH_INIT;
+            }
+            if (phase == PH_INIT) {
+                // ---- interior start from the primal point in L (DefaultIterateInitializer): push into
+                // the interior, slacks = d(x) pushed, bound multipliers = 1, zero step
+                if (isS) push_interior(L.sv, c.vLo, c.vHi);
+                if (isU) { push_interior(L.ua, c.aLo, c.aHi); push_interior(L.ud, c.dLo, c.dHi); }
+                double prv[2];
+                { const double u[2] = {L.ua, L.ud}; xprev<2>(u, prv); }
+                const double pa = prv[0], pd = prv[1];
+                if (isR) {
+                    const double h0 = rHi(0), h1 = rHi(1);
+                    L.rs[0] = L.ud - ((k == 0) ? cst(4) : pd);
+                    L.rs[1] = L.ua - ((k == 0) ? cst(5) : pa);
+                    push_interior(L.rs[0], -h0, h0); push_interior(L.rs[1], -h1, h1);
+                }
+                BoundMult Z;
+                Z.zvL = Z.zvU = isS ? 1.0 : 0.0;
+                Z.zaL = Z.zaU = Z.zdL = Z.zdU = isU ? 1.0 : 0.0;
+                Z.rvL[0] = Z.rvL[1] = Z.rvU[0] = Z.rvU[1] = isR ? 1.0 : 0.0;
+                st_z(Z);
+                StepState D;
+                D.dsx = D.dsy = D.dsp = D.dsv = D.dua = D.dud = 0.0; D.drs[0] = D.drs[1] = 0.0;
+                D.nyx = D.nyy = D.nyp = D.nyv = 0.0; D.nyd[0] = D.nyd[1] = 0.0;
+                st_dx(D); st_drs(D); st_dy(D);
+                phase = PH_EVAL0; do_eval = true; ev_alpha = 0.0;
+                continue;
+            }
             if (phase == PH_EVAL0) {
+                if (resto_check) {   // the restored point must be acceptable to the filter
+                    const double th_r = ev.theta, ph_r = sigma * ev.f - mu * ev.lb;
+                    bool ok = (th_r == th_r) && (ph_r == ph_r) && cmp_le(th_r, theta_max, theta_max);
+                    const bool mine = (k >= nfilt) || cmp_le(ph_r, f_phi, f_phi) || cmp_le(th_r, f_theta, f_theta);
+                    ok = tall(mine) && ok;
+                    if (!ok) { ret = -2; break; }
+                    resto_check = false;
+                }
                 cur_theta = ev.theta; cur_f = ev.f; cur_lb = ev.lb;
                 phase = PH_LS; do_solve = true; req = 0;
                 continue;
@@ -1248,7 +1331,10 @@ struct TeamSolver {
                         alpha_min = dmin_(K_GAMMA_THETA, K_GAMMA_PHI * cur_theta / (-gBd));
                         if (cur_theta <= theta_min) alpha_min = dmin_(alpha_min, K_DELTA * Rft);
                     }
-                    if (!(alpha > alpha_min * K_ALPHA_MIN_FRAC)) { ret = -2; break; }
+                    if (!(alpha > alpha_min * K_ALPHA_MIN_FRAC)) {
+                        if (n_resto < K_MAX_RESTO) { phase = PH_RESTO; continue; }
+                        ret = -2; break;
+                    }
                     ev_alpha = alpha; do_eval = true; phase = PH_TRIAL;
                     continue;
                 }

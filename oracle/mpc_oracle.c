@@ -681,6 +681,74 @@ static int nlp_feasible(const mpc_oracle_cfg* c, const double* state, const doub
     return 1;
 }
 
+/* Interior start from the primal point in P->x (DefaultIterateInitializer): push x inside its
+ * bounds, slacks = d(x) pushed, bound multipliers 1, least-squares equality multipliers.
+ * Used for the user's start point and after a restoration. */
+static void ipm_init_point(ipm_t* P, double* rx, double* rs, double* rc, double* rd) {
+    const mpc_oracle_cfg* cfg = P->cfg;
+    int n = P->n, mc = P->mc, md = P->md, i;
+    for (i = 0; i < n; i++) if (P->has_b[i]) push_interior(&P->x[i], P->xL[i], P->xU[i]);
+    mpc_oracle_eval_d(cfg, P->u_prev, P->x, P->s);
+    for (i = 0; i < md; i++) push_interior(&P->s[i], P->sL[i], P->sU[i]);
+    for (i = 0; i < n; i++) { P->zL[i] = P->has_b[i] ? 1.0 : 0.0; P->zU[i] = P->has_b[i] ? 1.0 : 0.0; }
+    for (i = 0; i < md; i++) { P->vL[i] = 1.0; P->vU[i] = 1.0; }
+
+    /* ---- least-squares equality multipliers ---- */
+    mpc_oracle_eval_grad_f(cfg, P->ref, P->v_des, P->x, P->g);
+    for (i = 0; i < n; i++) P->g[i] *= P->sigma_f;
+    mpc_oracle_eval_jac(cfg, P->x, P->Jc, P->Jd);
+    ipm_factor(P, 0, NULL, NULL, 0.0);
+    for (i = 0; i < n; i++) rx[i] = -(P->g[i] - P->zL[i] + P->zU[i]);
+    for (i = 0; i < md; i++) rs[i] = -(-P->vL[i] + P->vU[i]);
+    memset(rc, 0, sizeof(double) * mc); memset(rd, 0, sizeof(double) * md);
+    ipm_solve(P, rx, rs, rc, rd, P->dx, P->ds, P->yc, P->yd);
+    {
+        double ym = 0.0;
+        for (i = 0; i < mc; i++) ym = dmax(ym, fabs(P->yc[i]));
+        for (i = 0; i < md; i++) ym = dmax(ym, fabs(P->yd[i]));
+        if (!(ym <= IPM_Y_INIT_MAX)) { memset(P->yc, 0, sizeof(double) * mc); memset(P->yd, 0, sizeof(double) * md); }
+    }
+
+}
+
+/* ---- restoration by rollout ------------------------------------------------------------------
+ * Stands in for Ipopt's restoration phase (MinC_1NrmRestorationPhase), which is NOT restated: when
+ * the filter line search fails, the iterate is replaced by a point that satisfies the equality rows
+ * by construction -- the inputs of the current iterate, projected stage by stage onto the input box
+ * and the rate rows, and the states obtained by rolling the bicycle model out from the measured
+ * state -- and the interior-point iteration is re-initialised there (push into the interior, slacks,
+ * bound multipliers 1, least-squares y) with mu and the filter kept.  Like Ipopt's restoration it
+ * returns a point with (almost) no constraint violation that must be acceptable to the filter. */
+#define IPM_MAX_RESTO 3
+static double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static void ipm_rollout_restore(ipm_t* P) {
+    const mpc_oracle_cfg* c = P->cfg;
+    int N = P->N, k, j;
+    double pa = P->u_prev[1], pd = P->u_prev[0];
+    stage_eval e;
+    for (j = 0; j < 4; j++) P->x[IX(0, j)] = P->state[j];
+    for (k = 0; k < N; k++) {
+        double ua = P->x[IX(k, JACC)], ud = P->x[IX(k, JDF)];
+        if (k != 1) {   /* rate rows exist for the first move and for pairs (k, k-1), k >= 2 (Q1) */
+            const double h = (k == 0) ? c->dt_control : c->dt;
+            const double la = 0.98 * c->a_dmax * h, ld = 0.98 * c->steer_dmax * h;   /* 1 % of the range inside, like bound_frac */
+            ua = clipd(ua, pa - la, pa + la);
+            ud = clipd(ud, pd - ld, pd + ld);
+        }
+        ua = clipd(ua, -c->a_max, c->a_max);
+        ud = clipd(ud, -c->steer_max, c->steer_max);
+        /* keep the speed inside its bounds: v_{k+1} = v_k + dt * acc */
+        {
+            const double v = P->x[IX(k, JV)];
+            ua = clipd(ua, (c->v_min - v) / c->dt, (c->v_max - v) / c->dt);
+        }
+        P->x[IX(k, JACC)] = ua; P->x[IX(k, JDF)] = ud;
+        stage_map(c, &P->x[IX(k, 0)], ua, ud, &e, 0);
+        for (j = 0; j < 4; j++) P->x[IX(k + 1, j)] = e.f[j];
+        pa = ua; pd = ud;
+    }
+}
+
 static int ipm_run(ipm_t* P, const double* warm, int* iters_out, mpc_oracle_diag* dg) {
     const mpc_oracle_cfg* cfg = P->cfg;
     int N = P->N, n = P->n, mc = P->mc, md = P->md, i, j, k, iter = 0;
@@ -688,7 +756,8 @@ static int ipm_run(ipm_t* P, const double* warm, int* iters_out, mpc_oracle_diag
     const double mu_min = dmin(cfg->tol, 1e-4) / (IPM_KAPPA_EPS + 1.0);
     double dw_last = 0.0, theta_max = -1.0, theta_min = -1.0;
     filt_entry filt[IPM_FILTER_MAX]; int nfilt = 0;
-    int accept_count = 0, ret = -1, tiny_last = 0;
+    int accept_count = 0, ret = -1, tiny_last = 0, n_resto = 0;
+    const int use_resto = getenv("MPC_ORACLE_NO_RESTO") == NULL;
     double *Sx = (double*)xcalloc(n, sizeof(double)), *Ss = (double*)xcalloc(md, sizeof(double));
     double *rx = (double*)xcalloc(n, sizeof(double)), *rs = (double*)xcalloc(md, sizeof(double));
     double *rc = (double*)xcalloc(mc, sizeof(double)), *rd = (double*)xcalloc(md, sizeof(double));
@@ -732,27 +801,7 @@ static int ipm_run(ipm_t* P, const double* warm, int* iters_out, mpc_oracle_diag
     }
     dg->obj_scale = P->sigma_f;
 
-    for (i = 0; i < n; i++) if (P->has_b[i]) push_interior(&P->x[i], P->xL[i], P->xU[i]);
-    mpc_oracle_eval_d(cfg, P->u_prev, P->x, P->s);
-    for (i = 0; i < md; i++) push_interior(&P->s[i], P->sL[i], P->sU[i]);
-    for (i = 0; i < n; i++) { P->zL[i] = P->has_b[i] ? 1.0 : 0.0; P->zU[i] = P->has_b[i] ? 1.0 : 0.0; }
-    for (i = 0; i < md; i++) { P->vL[i] = 1.0; P->vU[i] = 1.0; }
-
-    /* ---- least-squares equality multipliers ---- */
-    mpc_oracle_eval_grad_f(cfg, P->ref, P->v_des, P->x, P->g);
-    for (i = 0; i < n; i++) P->g[i] *= P->sigma_f;
-    mpc_oracle_eval_jac(cfg, P->x, P->Jc, P->Jd);
-    ipm_factor(P, 0, NULL, NULL, 0.0);
-    for (i = 0; i < n; i++) rx[i] = -(P->g[i] - P->zL[i] + P->zU[i]);
-    for (i = 0; i < md; i++) rs[i] = -(-P->vL[i] + P->vU[i]);
-    memset(rc, 0, sizeof(double) * mc); memset(rd, 0, sizeof(double) * md);
-    ipm_solve(P, rx, rs, rc, rd, P->dx, P->ds, P->yc, P->yd);
-    {
-        double ym = 0.0;
-        for (i = 0; i < mc; i++) ym = dmax(ym, fabs(P->yc[i]));
-        for (i = 0; i < md; i++) ym = dmax(ym, fabs(P->yd[i]));
-        if (!(ym <= IPM_Y_INIT_MAX)) { memset(P->yc, 0, sizeof(double) * mc); memset(P->yd, 0, sizeof(double) * md); }
-    }
+    ipm_init_point(P, rx, rs, rc, rd);
 
     for (;;) {
         err_t e0, em;
@@ -960,7 +1009,25 @@ static int ipm_run(ipm_t* P, const double* warm, int* iters_out, mpc_oracle_diag
                 fprintf(stderr, "LS FAIL it=%d amax=%.3e amin=%.3e theta=%.3e gBd=%.3e limiting var stage %d comp %d x=%.6e dx=%.3e nsteps=%d\n",
                         iter, alpha_max, alpha_min, theta, gBd, jb / 6, jb % 6, jb >= 0 ? P->x[jb] : 0.0, jb >= 0 ? P->dx[jb] : 0.0, nsteps);
             }
-            if (!accepted) { ret = -2; break; } /* Ipopt would enter the restoration phase here */
+            if (!accepted && use_resto && n_resto < IPM_MAX_RESTO) {
+                /* restoration: filter augmented with the point that is left (PrepareRestoPhaseStart) */
+                double th_r, ph_r; int ok;
+                n_resto++;
+                if (nfilt < IPM_FILTER_MAX) { filt[nfilt].phi = phi - IPM_GAMMA_PHI * theta; filt[nfilt].theta = (1.0 - IPM_GAMMA_THETA) * theta; nfilt++; }
+                ipm_rollout_restore(P);
+                ipm_init_point(P, rx, rs, rc, rd);
+                th_r = ipm_theta(P, P->x, P->s, P->ct, P->dt_);
+                ph_r = ipm_barrier(P, P->x, P->s, mu);
+                ok = (th_r == th_r) && (ph_r == ph_r) && cmp_le(th_r, theta_max, theta_max);
+                if (ok) { int f_; for (f_ = 0; f_ < nfilt; f_++)
+                    if (!(cmp_le(ph_r, filt[f_].phi, filt[f_].phi) || cmp_le(th_r, filt[f_].theta, filt[f_].theta))) { ok = 0; break; } }
+                if (!ok) { ret = -2; break; }
+                dg->n_resto++;
+                tiny_last = 0;
+                iter++;
+                continue;
+            }
+            if (!accepted) { ret = -2; break; } /* restoration budget spent */
 
             /* filter augmentation (FilterLSAcceptor::UpdateForNextIteration) */
             if (!tiny && !ftype_arm) {

@@ -63,6 +63,7 @@ typedef struct {
     int    n_soc;            /* accepted second-order corrections */
     int    n_backtrack;      /* total step halvings */
     int    ipopt_status;     /* 0 success, 1 acceptable, -1 maxiter, -2 restoration needed, -3 tiny step, -4 pert fail, 2 infeasible */
+    int    n_resto;          /* restorations by rollout (see ipm_rollout_restore) */
 } mpc_oracle_diag;
 
 /*

@@ -25,7 +25,7 @@ class Cfg(C.Structure):
 class Diag(C.Structure):
     _fields_ = [("dual_inf", C.c_double), ("constr_viol", C.c_double), ("compl_inf", C.c_double),
                 ("mu_final", C.c_double), ("obj_scale", C.c_double), ("n_inertia_corr", C.c_int),
-                ("n_soc", C.c_int), ("n_backtrack", C.c_int), ("ipopt_status", C.c_int)]
+                ("n_soc", C.c_int), ("n_backtrack", C.c_int), ("ipopt_status", C.c_int), ("n_resto", C.c_int)]
 
 
 class Path(C.Structure):

@@ -64,3 +64,29 @@ def test_emulated_long_horizon_zero_start(oracle):
     ok = o["status"] == 0
     assert ok.any()
     assert np.abs(o["u0"] - e["u0"])[ok].max() <= 1e-9
+
+
+def test_restoration_by_rollout(oracle, monkeypatch):
+    """Problems whose filter line search fails from the all-zero start (Ipopt would enter its restoration
+    phase): oracle and emulated kernel must restore identically (same iteration counts), converge, and
+    end at the optimum that the reference-waypoint start finds."""
+    import emu as E
+    N = 20
+    idx = np.array([38, 62, 79, 122, 163])
+    b = W.make_batch(int(idx.max()) + 1, N)
+    sel = {k: b[k][idx] for k in ("state", "ref", "v_des", "u_prev")}
+    cfg = oracle.default_cfg(N)
+    monkeypatch.setenv("MPC_ORACLE_NO_RESTO", "1")
+    o0 = oracle.solve_batch(cfg, sel["state"], sel["ref"], sel["v_des"], sel["u_prev"], n_threads=4)
+    assert (o0["status"] == 4).all()            # without restoration: Error
+    monkeypatch.delenv("MPC_ORACLE_NO_RESTO")
+    o = oracle.solve_batch(cfg, sel["state"], sel["ref"], sel["v_des"], sel["u_prev"], n_threads=4)
+    e = E.solve_batch(E.kcfg_from_oracle(cfg), sel["state"], sel["ref"], sel["v_des"], sel["u_prev"])
+    assert (o["status"] == 0).all() and (e["status"] == 0).all()
+    assert (o["iters"] == e["iters"]).all()
+    assert np.abs(o["u0"] - e["u0"]).max() <= 1e-9
+    w = W.reference_start(sel, N)
+    o2 = oracle.solve_batch(cfg, sel["state"], sel["ref"], sel["v_des"], sel["u_prev"], warm=w, n_threads=4)
+    assert (o2["status"] == 0).all()
+    assert np.abs(o["u0"] - o2["u0"]).max() <= 1e-5
+    assert (np.abs(o["cost"] - o2["cost"]) <= 1e-6 * np.maximum(1, o2["cost"])).all()

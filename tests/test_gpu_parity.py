@@ -185,7 +185,7 @@ def test_full_size_properties(capi, oracle, N, B, paths):
     b = W.make_batch(B, N, path_ids=paths)
     g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
     ok = g["status"] == 0
-    assert ok.mean() > 0.93
+    assert ok.mean() > 0.999    # the ~2 % whose line search fails from the all-zero start are restored by rollout
     viol = _feasibility(s.cfg, b, g, N)
     assert viol[ok].max() <= 2e-8
     # slice reproducibility
