@@ -19,6 +19,8 @@
 //
 // The iteration follows oracle/mpc_oracle.c step for step (same formulas, same constants);
 // only the linear algebra differs (condensed Riccati here, full-space Bunch-Kaufman there).
+// Ipopt's restoration phase is not restated: a failed line search is answered by a restoration by
+// rollout (rollout_restore), the same in both implementations.
 //
 // Control flow is a warp-uniform phase machine so that every heavy routine (record assembly,
 // Riccati backward/forward, dual recovery, trial-point evaluation) exists exactly once in the

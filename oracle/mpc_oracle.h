@@ -17,6 +17,11 @@
  *       2006) with the 3.12 default options, as recalled;
  * and is validated intrinsically (finite-difference derivative checks, KKT
  * residuals of the unscaled NLP, agreement with scipy SLSQP/trust-constr).
+ * One piece of Ipopt is NOT restated: its restoration phase.  Where the filter
+ * line search fails, the iterate is replaced by the rollout of its own projected
+ * inputs and the iteration is re-initialised there (ipm_rollout_restore; the
+ * CUDA kernel does the same, step for step).  MPC_ORACLE_NO_RESTO=1 switches it
+ * off (status Error instead), MPC_ORACLE_TRACE=1 prints the iteration log.
  */
 #ifndef MPC_ORACLE_H
 #define MPC_ORACLE_H
