@@ -1021,10 +1021,10 @@ static int ipm_run(ipm_t* P, const double* warm, int* iters_out, mpc_oracle_diag
                 ok = (th_r == th_r) && (ph_r == ph_r) && cmp_le(th_r, theta_max, theta_max);
                 if (ok) { int f_; for (f_ = 0; f_ < nfilt; f_++)
                     if (!(cmp_le(ph_r, filt[f_].phi, filt[f_].phi) || cmp_le(th_r, filt[f_].theta, filt[f_].theta))) { ok = 0; break; } }
+                iter++;   /* the restoration counts as one iteration */
                 if (!ok) { ret = -2; break; }
                 dg->n_resto++;
                 tiny_last = 0;
-                iter++;
                 continue;
             }
             if (!accepted) { ret = -2; break; } /* restoration budget spent */

@@ -130,6 +130,13 @@ def test_edge_cases(capi, oracle):
     s2 = capi.Solver(N, max_iter=3)
     g = s2.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
     assert (g["status"] == capi.USERLIMIT).all() and (g["iters"] == 3).all()
+    # non-finite inputs: every solve terminates with a status (never a hang), the same as the oracle's
+    st = b["state"].copy(); rf = b["ref"].copy(); up = b["u_prev"].copy()
+    st[0, 0] = np.nan; st[1, 3] = np.inf; rf[2, 0, 3] = np.nan; up[3, 1] = np.nan
+    g = s.solve_batch(st, rf, up, v_des=b["v_des"])
+    o = oracle.solve_batch(_ocfg(oracle, s), st, rf, b["v_des"], up)
+    assert (g["status"] == o["status"]).all() and (g["status"] != capi.OPTIMAL).all()
+    assert (g["iters"] == o["iters"]).all()
     # argument validation
     with pytest.raises(ValueError):
         s.solve_batch(b["state"], b["ref"][:, :, :-1], b["u_prev"])
