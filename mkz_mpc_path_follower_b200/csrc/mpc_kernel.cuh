@@ -1,4 +1,5 @@
-// mpc_kernel.cuh -- one MPC problem per warp: interior-point iteration with a Riccati KKT solve.
+// mpc_kernel.cuh -- one MPC problem per warp (or per block of 2-3 warps): interior-point iteration
+// with a Riccati KKT solve.
 //
 // What it replaces (reference file:line):
 //   NLP transcription   scripts/mpc_utils/MKZMPCPathFollower.jl:65-123  (JuMP AD -> analytic
@@ -11,11 +12,10 @@
 // hot configuration: four independent problems per block) and one block of W = 2 or 3 warps for
 // long horizons (N <= 63 / 95: one problem per block; cross-warp exchanges go through a small
 // shared-memory area and bar.sync, the serial Riccati recursion runs in warp 0).  Thread k holds
-// its state (x,y,psi,v),
-// input (acc,df), the multipliers of the equality rows that define s_k, its bound multipliers
-// and the rate row that ends at u_k.  Stage-parallel work (model evaluation, residuals,
-// multiplier updates, norms) runs with lanes = stages; the serial Riccati recursion switches
-// to lanes = matrix entries, with per-stage records staged in shared memory.
+// its state (x,y,psi,v), input (acc,df), the multipliers of the equality rows that define s_k, its
+// bound multipliers and the rate row that ends at u_k.  Stage-parallel work (model evaluation,
+// residuals, multiplier updates, norms) runs with threads = stages; the serial Riccati recursion
+// switches to lanes = matrix entries, with per-stage records staged in shared memory.
 //
 // The iteration follows oracle/mpc_oracle.c step for step (same formulas, same constants);
 // only the linear algebra differs (condensed Riccati here, full-space Bunch-Kaufman there).
@@ -26,8 +26,9 @@
 // Riccati backward/forward, dual recovery, trial-point evaluation) exists exactly once in the
 // instruction stream: least-squares multiplier solve, Newton solves with inertia-correction
 // retries, second-order corrections and line-search trials all pass through the same code.
-// Per-lane state carried across the Riccati passes is kept small (the iterate, the step and a
-// dozen scalars) so that 16 warps per SM fit in the register file.
+// The phase machine makes all solver state look live everywhere, so only the primal iterate and the
+// equality multipliers stay in registers; bound multipliers, step, model evaluation and reference
+// sample live in per-thread shared-memory fields (LF_*): 168 registers, 12 warps per SM at N = 20.
 #pragma once
 #include "warp_prims.cuh"
 
