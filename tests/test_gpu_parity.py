@@ -217,6 +217,29 @@ def test_full_size_properties(capi, oracle, N, B, paths):
     _compare({k: g[k][idx] for k in ("u0", "cost", "status")}, o)
 
 
+@pytest.mark.parametrize("N,B,start", [(8, 48, "zero"), (20, 48, "zero"), (40, 12, "ref")])
+def test_kkt_of_cuda_solutions(capi, oracle, N, B, start):
+    """Intrinsic check that does not involve the oracle's interior-point code: every Optimal point the
+    CUDA solver returns satisfies the KKT conditions of the UNSCALED reference NLP (stationarity with
+    least-squares multipliers on the active set, primal feasibility, multiplier signs).  The N = 20
+    batch contains problems that go through the restoration by rollout."""
+    import ctypes as C
+    from test_oracle_solver import _kkt_residual, _p
+    s = capi.Solver(N)
+    b = W.make_batch(B, N, b0=30 if N == 20 else 0)     # problems 38, 62 of the stream need a restoration
+    warm = W.reference_start(b, N) if start == "ref" else None
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], warm=warm, want_traj=True)
+    assert (g["status"] == 0).mean() >= 0.95
+    ocfg = _ocfg(oracle, s)
+    for j in np.nonzero(g["status"] == 0)[0]:
+        z = np.empty(6 * N + 4)
+        oracle.lib().mpc_oracle_traj_to_z(C.byref(ocfg), _p(np.ascontiguousarray(g["traj"][j])), _p(z))
+        stat, prim, sign = _kkt_residual(oracle, ocfg, (b["state"][j], b["ref"][j], 1.0, b["u_prev"][j]), z)
+        assert prim <= 1e-8 * max(1.0, np.abs(z).max()), (j, prim)
+        assert stat <= 1e-4, (j, stat)       # unscaled; Ipopt's tol 1e-8 acts on the scaled problem
+        assert sign <= 1e-6, (j, sign)
+
+
 def test_julia_module_mirror(capi, oracle):
     """The six-function API of MKZMPCPathFollower.jl:132-207, batch of one, one control step."""
     from mkz_mpc_path_follower_b200.mpc_path_follower import MKZMPCPathFollower
