@@ -1438,6 +1438,11 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t 
         const double* w = io.warm + nt * b;
         if (k <= N) { S.L.sx = w[k]; S.L.sy = w[(N + 1) + k]; S.L.sv = w[2 * (N + 1) + k]; S.L.sp = w[3 * (N + 1) + k]; }
         if (k < N) { S.L.ud = w[4 * (N + 1) + k]; S.L.ua = w[4 * (N + 1) + N + k]; }
+    } else if (cfg.start_mode == 1) {
+        // MPCB200_START_ROLLOUT (opt-in, not a reference behaviour): hold the previous command over the
+        // horizon (projected onto the box and rate rows) and roll the model out from the measured state
+        if (k < N) { S.L.ua = S.cst(5); S.L.ud = S.cst(4); }
+        S.rollout_restore();
     }
     const Result r = S.solve();
     // ---- results

@@ -1113,6 +1113,21 @@ static int solve_with(ipm_t* P, const double* state, const double* ref, double v
     return 0;
 }
 
+/* MPCB200_START_ROLLOUT of include/mpc_b200.h: the previous command held over the horizon (projected
+ * like ipm_rollout_restore does) and the model rolled out from the measured state; traj order. */
+int mpc_oracle_rollout_start(const mpc_oracle_cfg* cfg, const double* state, const double* u_prev, double* traj) {
+    ipm_t P; int k;
+    if (cfg->N < 3 || cfg->N > 512) return -1;
+    ipm_alloc(&P, cfg);
+    P.state = state; P.u_prev = u_prev;
+    memset(P.x, 0, sizeof(double) * P.n);
+    for (k = 0; k < cfg->N; k++) { P.x[IX(k, JACC)] = u_prev[1]; P.x[IX(k, JDF)] = u_prev[0]; }
+    ipm_rollout_restore(&P);
+    mpc_oracle_z_to_traj(cfg, P.x, traj);
+    ipm_free(&P);
+    return 0;
+}
+
 int mpc_oracle_solve(const mpc_oracle_cfg* cfg, const double* state, const double* ref, double v_des,
                      const double* u_prev, const double* warm, double* traj, double* u0, double* cost,
                      int* status, int* iters, mpc_oracle_diag* diag) {

@@ -86,6 +86,10 @@ int mpc_oracle_solve(const mpc_oracle_cfg* cfg, const double* state, const doubl
                      double* traj, double* u0, double* cost, int* status, int* iters,
                      mpc_oracle_diag* diag);
 
+/* The start point of MPCB200_START_ROLLOUT (include/mpc_b200.h): previous command held over the
+ * horizon, projected onto box / rate rows / speed bounds, model rolled out from `state`. */
+int mpc_oracle_rollout_start(const mpc_oracle_cfg* cfg, const double* state, const double* u_prev, double* traj);
+
 /* Batch, problem-major layouts identical to include/mpc_b200.h; OpenMP over problems
  * when n_threads > 1.  v_des may be NULL (then 0), warm/traj may be NULL. */
 int mpc_oracle_solve_batch(const mpc_oracle_cfg* cfg, long B, const double* state,

@@ -54,6 +54,7 @@ def lib():
         _lib.mpc_oracle_default_cfg.argtypes = [C.POINTER(Cfg), C.c_int]
         _lib.mpc_oracle_solve.argtypes = [C.POINTER(Cfg), dp, dp, C.c_double, dp, dp, dp, dp, dp, ip, ip, C.POINTER(Diag)]
         _lib.mpc_oracle_solve_batch.argtypes = [C.POINTER(Cfg), C.c_long, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, C.c_int]
+        _lib.mpc_oracle_rollout_start.argtypes = [C.POINTER(Cfg), dp, dp, dp]
         _lib.mpc_oracle_eval_f.restype = C.c_double
         _lib.mpc_oracle_eval_f.argtypes = [C.POINTER(Cfg), dp, C.c_double, dp]
         _lib.mpc_oracle_eval_grad_f.argtypes = [C.POINTER(Cfg), dp, C.c_double, dp, dp]
@@ -130,6 +131,15 @@ def solve_batch(cfg, state, ref, v_des, u_prev, warm=None, want_traj=False, n_th
                                       _p(cost), _pi(status), _pi(iters), _p(traj), int(n_threads))
     assert rc == 0
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+
+def rollout_start(cfg, state, u_prev):
+    """Start points of MPCB200_START_ROLLOUT for a batch: (B, 6N+4) in traj order."""
+    state = np.ascontiguousarray(state, dtype=np.float64); u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+    out = np.empty((state.shape[0], 6 * cfg.N + 4))
+    for j in range(state.shape[0]):
+        assert lib().mpc_oracle_rollout_start(C.byref(cfg), _p(state[j]), _p(u_prev[j]), _p(out[j])) == 0
+    return out
 
 
 def make_path(traj_table):

@@ -90,3 +90,22 @@ def test_restoration_by_rollout(oracle, monkeypatch):
     assert (o2["status"] == 0).all()
     assert np.abs(o["u0"] - o2["u0"]).max() <= 1e-5
     assert (np.abs(o["cost"] - o2["cost"]) <= 1e-6 * np.maximum(1, o2["cost"])).all()
+
+
+@pytest.mark.parametrize("N,B", [(8, 16), (20, 12), (40, 3)])
+def test_rollout_start_mode(oracle, N, B):
+    """MPCB200_START_ROLLOUT (opt-in): previous command held over the horizon, model rolled out from the
+    measured state.  The emulated kernel must match the oracle started from mpc_oracle_rollout_start,
+    converge in a handful of iterations, and reach the optimum of the all-zero start."""
+    import emu as E
+    cfg = oracle.default_cfg(N)
+    b = W.make_batch(B, N)
+    w = oracle.rollout_start(cfg, b["state"], b["u_prev"])
+    o = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], warm=w.copy(), n_threads=4)
+    e = E.solve_batch(E.kcfg_from_oracle(cfg, start_mode=1), b["state"], b["ref"], b["v_des"], b["u_prev"])
+    assert (o["status"] == 0).all() and (e["status"] == 0).all()
+    assert (o["iters"] == e["iters"]).all() and o["iters"].mean() < 15
+    assert np.abs(o["u0"] - e["u0"]).max() <= 1e-9
+    o0 = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=4)
+    both = o0["status"] == 0
+    assert np.abs(o["u0"] - o0["u0"])[both].max() <= 1e-5

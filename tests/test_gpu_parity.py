@@ -217,6 +217,20 @@ def test_full_size_properties(capi, oracle, N, B, paths):
     _compare({k: g[k][idx] for k in ("u0", "cost", "status")}, o)
 
 
+@pytest.mark.parametrize("N,B", [(8, 512), (20, 512), (40, 64)])
+def test_rollout_start_mode(capi, oracle, N, B):
+    """MPCB200_START_ROLLOUT (opt-in, not a reference behaviour) against the oracle started from the same
+    rolled-out point; the solves need a fraction of the all-zero start's iterations."""
+    s = capi.Solver(N, start_mode=capi.START_ROLLOUT)
+    b = W.make_batch(B, N)
+    ocfg = _ocfg(oracle, s)
+    w = oracle.rollout_start(ocfg, b["state"], b["u_prev"])
+    o = oracle.solve_batch(ocfg, b["state"], b["ref"], b["v_des"], b["u_prev"], warm=w.copy(), n_threads=8)
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
+    ok = _compare(g, o, min_conv=0.99)
+    assert (g["iters"][ok] == o["iters"][ok]).mean() > 0.98 and g["iters"].mean() < 15
+
+
 @pytest.mark.parametrize("N,B,start", [(8, 48, "zero"), (20, 48, "zero"), (40, 12, "ref")])
 def test_kkt_of_cuda_solutions(capi, oracle, N, B, start):
     """Intrinsic check that does not involve the oracle's interior-point code: every Optimal point the

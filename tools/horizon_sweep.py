@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Horizon sweep (BASELINE.json configs[4]): `python tools/horizon_sweep.py [B] [start]` solves B synthetic
 problems at N = 8, 20, 40, 80 through the C ABI (device pointers) and prints solves/s.
-start = zero | ref  (all-zero `start=0.0`, or the reference waypoints as start point)."""
+start = zero | ref | rollout  (all-zero `start=0.0`, the reference waypoints as start point, or
+MPCB200_START_ROLLOUT: previous command rolled out from the measured state)."""
 import os
 import sys
 
@@ -16,7 +17,7 @@ start = sys.argv[2] if len(sys.argv) > 2 else "ref"
 dev = torch.device("cuda", 0)
 for N in (8, 20, 40, 80):
     b = workload.make_batch(B, N)
-    s = capi.Solver(N)
+    s = capi.Solver(N, start_mode=capi.START_ROLLOUT if start == "rollout" else capi.START_ZERO)
     st = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(st)
     s.set_stream(st.cuda_stream)
