@@ -51,6 +51,7 @@ struct KCfg {
     double rHiFirst[2], rHiLater[2];  // relaxed half-width of the rate rows [steer, acc]; rLo = -rHi
     double rfrac;                     // L_b / (L_a + L_b)
     double mu_min;
+    double dtLb;                      // dt / L_b (multiplying by it avoids a division per use; 0 / x takes the slow division path)
     const int* roles;                 // [32][ROLE_STRIDE] lane roles of the Riccati recursion (riccati_roles), device memory
 };
 
@@ -101,6 +102,7 @@ MPC_HD void kcfg_finalize(KCfg& c) {
         dst[1] = la + K_BOUND_RELAX * mx(1.0, la);
     }
     c.rfrac = c.Lb / (c.La + c.Lb);
+    c.dtLb = c.dt / c.Lb;
     const double t = c.tol < 1e-4 ? c.tol : 1e-4;
     c.mu_min = t / (K_KAPPA_EPS + 1.0);
 }
@@ -219,6 +221,58 @@ struct EvalState {        // ... and its team-wide scalars
 struct Recips { double vL, vU, aL, aU, dL, dU, r0L, r0U, r1L, r1U; };
 
 struct Result { int status; int iters; double cost; };
+
+// a / b for the rare branches: a call cannot be speculated, so the division (and its slow path for
+// zero numerators) stays out of the common path
+MPC_DEV_NOINLINE double div_cold(double a, double b) { return a / b; }
+
+// kappa_sigma safeguard of the bound multipliers (Ipopt: correct_bound_multiplier); multipliers a
+// thread does not own are 0 and stay 0.  Rare: out of line.
+MPC_DEV_NOINLINE void kappa_sigma_clamp(double* z, const double* sl, double mu) {
+    MPC_NOUNROLL for (int i = 0; i < 10; i++) {
+        if (!(z[i] > 0.0)) continue;
+        const double pz = z[i] * sl[i];
+        if (pz > K_KAPPA_SIGMA * mu) z[i] = K_KAPPA_SIGMA * mu / sl[i];
+        else if (pz * K_KAPPA_SIGMA < mu) z[i] = mu / (K_KAPPA_SIGMA * sl[i]);
+    }
+}
+
+// Serial part of the restoration by rollout (see TeamSolver::rollout_restore): inputs of stage s are
+// read from / written back to field LF_DX+4, +5 of stage s, states written to fields LF_DX+0..3.
+// Rare (a few per cent of the cold starts, once each): out of line, scalars by value.
+struct RolloutConsts { double dt, dtc, dtLb, rfrac, vmin, vmax, amax, smax, admax, sdmax; };
+MPC_DEV_NOINLINE void rollout_core(smem_t sm, int fa, int st, int cbase, int N, RolloutConsts c) {
+    double s0 = lds(sm, cbase), s1 = lds(sm, cbase + SO(1)), s2 = lds(sm, cbase + SO(2)), s3 = lds(sm, cbase + SO(3));
+    double pa = lds(sm, cbase + SO(5)), pd = lds(sm, cbase + SO(4));
+    MPC_NOUNROLL for (int s = 0; s < N; s++) {
+        double ua = lds(sm, fa + 4 * st), ud = lds(sm, fa + 5 * st);
+        if (s != 1) {   // rate rows exist for the first move and for pairs (s, s-1), s >= 2
+            const double h = (s == 0) ? c.dtc : c.dt;
+            const double la = 0.98 * c.admax * h, ld = 0.98 * c.sdmax * h;
+            ua = dmin_(dmax_(ua, pa - la), pa + la);
+            ud = dmin_(dmax_(ud, pd - ld), pd + ld);
+        }
+        ua = dmin_(dmax_(ua, -c.amax), c.amax);
+        ud = dmin_(dmax_(ud, -c.smax), c.smax);
+        ua = dmin_(dmax_(ua, (c.vmin - s3) / c.dt), (c.vmax - s3) / c.dt);   // v_{s+1} = v_s + dt acc stays inside [v_min, v_max]
+        sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
+        sts(sm, fa + 4 * st, ua); sts(sm, fa + 5 * st, ud);
+        double sd, cd, sps, cps;
+        mpc_sincos(ud, &sd, &cd);
+        mpc_sincos(s2, &sps, &cps);
+        const double r = c.rfrac;
+        const double inv = sqrt(1.0 / (cd * cd + r * r * sd * sd));
+        const double cb = cd * inv, sb = r * sd * inv;
+        const double n0 = s0 + c.dt * (s3 * (cps * cb - sps * sb));
+        const double n1 = s1 + c.dt * (s3 * (sps * cb + cps * sb));
+        const double n2 = s2 + c.dtLb * (s3 * sb);
+        const double n3 = s3 + c.dt * ua;
+        s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
+        fa += SO(1);
+    }
+    sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
+    sts(sm, fa + 4 * st, 0.0); sts(sm, fa + 5 * st, 0.0);
+}
 
 // ---- lane roles of the Riccati backward recursion (lanes = matrix entries), one row of ROLE_STRIDE
 // ints per lane: shared-memory offsets (SO units) of the operands of rounds A, B and E.  They depend
@@ -538,7 +592,7 @@ struct TeamSolver {
         }
         const double fx = sx + c.dt * (sv * e.cs);
         const double fy = sy + c.dt * (sv * e.sn);
-        const double fp = sp + c.dt * (sv / c.Lb * e.sb);
+        const double fp = sp + c.dtLb * (sv * e.sb);
         const double fv = sv + c.dt * ua;
         // thread k < N takes s_{k+1}; thread N takes s_0 (for the initial-condition rows); every thread u_{k-1}
         double nxt[4], prv[2];
@@ -641,8 +695,8 @@ struct TeamSolver {
                 hpp = dt * v * e1;
                 Hpv = dt * e2;
                 Hpd = e.b1 * hpp;
-                Hvd = e.b1 * Hpv - y1p * dt * e.cb * e.b1 / c.Lb;
-                hdd = e.b1 * e.b1 * hpp + v * e.b2 * Hpv - y1p * (dt * v / c.Lb) * (e.cb * e.b2 - e.sb * e.b1 * e.b1);
+                Hvd = e.b1 * Hpv - y1p * c.dtLb * e.cb * e.b1;
+                hdd = e.b1 * e.b1 * hpp + v * e.b2 * Hpv - y1p * (c.dtLb * v) * (e.cb * e.b2 - e.sb * e.b1 * e.b1);
             }
             Recips q;
             recips(q);
@@ -681,8 +735,8 @@ struct TeamSolver {
         if (req == 0 || req == 1) {
             const double A02 = isU ? -c.dt * L.sv * e.sn : 0.0, A03 = isU ? c.dt * e.cs : 0.0;
             const double A12 = isU ? c.dt * L.sv * e.cs : 0.0, A13 = isU ? c.dt * e.sn : 0.0;
-            const double A23 = isU ? c.dt * e.sb / c.Lb : 0.0;
-            const double b0 = A02 * e.b1, b1v = A12 * e.b1, b2v = isU ? c.dt * L.sv * e.cb * e.b1 / c.Lb : 0.0;
+            const double A23 = isU ? c.dtLb * e.sb : 0.0;
+            const double b0 = A02 * e.b1, b1v = A12 * e.b1, b2v = isU ? c.dtLb * L.sv * e.cb * e.b1 : 0.0;
             const double one = isU ? 1.0 : 0.0;
             sts(sm, r + SO(SD_CF + 0), A02); sts(sm, r + SO(SD_CF + 1), A12); sts(sm, r + SO(SD_CF + 2), one);
             sts(sm, r + SO(SD_CF + 4), A03); sts(sm, r + SO(SD_CF + 5), A13); sts(sm, r + SO(SD_CF + 6), A23); sts(sm, r + SO(SD_CF + 7), one);
@@ -910,37 +964,10 @@ struct TeamSolver {
         }
         tsync();
         if (lane_id() < 8 && (W == 1 || (k >> 5) == 0)) {
-            int fa = SO(lf_offset(N)) + LF_DX * st;   // field LF_DX of stage 0
-            double s0 = cst(0), s1 = cst(1), s2 = cst(2), s3 = cst(3);
-            double pa = cst(5), pd = cst(4);
-            for (int s = 0; s < N; s++) {
-                double ua = lds(sm, fa + 4 * st), ud = lds(sm, fa + 5 * st);
-                if (s != 1) {   // rate rows exist for the first move and for pairs (s, s-1), s >= 2
-                    const double h = (s == 0) ? c.dtc : c.dt;
-                    const double la = 0.98 * c.admax * h, ld = 0.98 * c.sdmax * h;
-                    ua = dmin_(dmax_(ua, pa - la), pa + la);
-                    ud = dmin_(dmax_(ud, pd - ld), pd + ld);
-                }
-                ua = dmin_(dmax_(ua, -c.amax), c.amax);
-                ud = dmin_(dmax_(ud, -c.smax), c.smax);
-                ua = dmin_(dmax_(ua, (c.vmin - s3) / c.dt), (c.vmax - s3) / c.dt);   // v_{s+1} = v_s + dt acc stays inside [v_min, v_max]
-                sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
-                sts(sm, fa + 4 * st, ua); sts(sm, fa + 5 * st, ud);
-                double sd, cd, sps, cps;
-                mpc_sincos(ud, &sd, &cd);
-                mpc_sincos(s2, &sps, &cps);
-                const double r = c.rfrac;
-                const double inv = sqrt(1.0 / (cd * cd + r * r * sd * sd));
-                const double cb = cd * inv, sb = r * sd * inv;
-                const double n0 = s0 + c.dt * (s3 * (cps * cb - sps * sb));
-                const double n1 = s1 + c.dt * (s3 * (sps * cb + cps * sb));
-                const double n2 = s2 + c.dt * (s3 / c.Lb * sb);
-                const double n3 = s3 + c.dt * ua;
-                s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
-                fa += SO(1);
-            }
-            sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
-            sts(sm, fa + 4 * st, 0.0); sts(sm, fa + 5 * st, 0.0);
+            RolloutConsts rc;
+            rc.dt = c.dt; rc.dtc = c.dtc; rc.dtLb = c.dtLb; rc.rfrac = c.rfrac; rc.vmin = c.vmin; rc.vmax = c.vmax;
+            rc.amax = c.amax; rc.smax = c.smax; rc.admax = c.admax; rc.sdmax = c.sdmax;
+            rollout_core(sm, SO(lf_offset(N)) + LF_DX * st, st, SO(W_CONST), N, rc);
         }
         tsync();
         if (isS) {
@@ -1123,21 +1150,32 @@ struct TeamSolver {
                     L.ua += alpha * D.dua; L.ud += alpha * D.dud; L.rs[0] += alpha * D.drs[0]; L.rs[1] += alpha * D.drs[1];
                     L.yx += alpha * (D.nyx - L.yx); L.yy += alpha * (D.nyy - L.yy); L.yp += alpha * (D.nyp - L.yp); L.yv += alpha * (D.nyv - L.yv);
                     L.ryd[0] += alpha * (D.nyd[0] - L.ryd[0]); L.ryd[1] += alpha * (D.nyd[1] - L.ryd[1]);
+                    // z += az dz, then the kappa_sigma safeguard z in [mu / (kappa s), kappa mu / s].  The test is
+                    // division-free; the clamp itself (two divisions per multiplier) is rare and kept out of
+                    // line so that it does not sit, ten times over, in the middle of the hot path.
+                    bool clamp = false;
                     auto upd = [&](double& z, double dz, double sl) {
                         z += az * dz;
-                        const double pz = z * sl;   // kappa_sigma safeguard without a division in the common case
-                        if (pz > K_KAPPA_SIGMA * mu) z = K_KAPPA_SIGMA * mu / sl;
-                        else if (pz * K_KAPPA_SIGMA < mu) z = mu / (K_KAPPA_SIGMA * sl);
+                        const double pz = z * sl;
+                        clamp = clamp || (pz > K_KAPPA_SIGMA * mu) || (pz * K_KAPPA_SIGMA < mu);
                     };
+                    const double h0 = rHi(0), h1 = rHi(1);
                     if (isS) { upd(Z.zvL, dzvL, L.sv - c.vLo); upd(Z.zvU, dzvU, c.vHi - L.sv); }
                     if (isU) {
                         upd(Z.zaL, dzaL, L.ua - c.aLo); upd(Z.zaU, dzaU, c.aHi - L.ua);
                         upd(Z.zdL, dzdL, L.ud - c.dLo); upd(Z.zdU, dzdU, c.dHi - L.ud);
                     }
                     if (isR) {
-                        const double h0 = rHi(0), h1 = rHi(1);
                         upd(Z.rvL[0], drvL[0], L.rs[0] + h0); upd(Z.rvU[0], drvU[0], h0 - L.rs[0]);
                         upd(Z.rvL[1], drvL[1], L.rs[1] + h1); upd(Z.rvU[1], drvU[1], h1 - L.rs[1]);
+                    }
+                    if (clamp) {
+                        double zz[10] = {Z.zvL, Z.zvU, Z.zaL, Z.zaU, Z.zdL, Z.zdU, Z.rvL[0], Z.rvU[0], Z.rvL[1], Z.rvU[1]};
+                        const double sl[10] = {L.sv - c.vLo, c.vHi - L.sv, L.ua - c.aLo, c.aHi - L.ua, L.ud - c.dLo, c.dHi - L.ud,
+                                               L.rs[0] + h0, h0 - L.rs[0], L.rs[1] + h1, h1 - L.rs[1]};
+                        kappa_sigma_clamp(zz, sl, mu);
+                        Z.zvL = zz[0]; Z.zvU = zz[1]; Z.zaL = zz[2]; Z.zaU = zz[3]; Z.zdL = zz[4]; Z.zdU = zz[5];
+                        Z.rvL[0] = zz[6]; Z.rvU[0] = zz[7]; Z.rvL[1] = zz[8]; Z.rvU[1] = zz[9];
                     }
                     st_z(Z);
                 }
@@ -1225,8 +1263,8 @@ struct TeamSolver {
                 ld_z(Z);
                 const double A02 = isU ? -c.dt * L.sv * e.sn : 0.0, A03 = isU ? c.dt * e.cs : 0.0;
                 const double A12 = isU ? c.dt * L.sv * e.cs : 0.0, A13 = isU ? c.dt * e.sn : 0.0;
-                const double A23 = isU ? c.dt * e.sb / c.Lb : 0.0;
-                const double b0 = A02 * e.b1, b1v = A12 * e.b1, b2v = isU ? c.dt * L.sv * e.cb * e.b1 / c.Lb : 0.0;
+                const double A23 = isU ? c.dtLb * e.sb : 0.0;
+                const double b0 = A02 * e.b1, b1v = A12 * e.b1, b2v = isU ? c.dtLb * L.sv * e.cb * e.b1 : 0.0;
                 double di, cv, cm0, cmm, sumy, sumz;
                 {
                     double y1[6];
@@ -1256,8 +1294,8 @@ struct TeamSolver {
                 const double sty = sumy + sumz;
                 const bool big_d = sty > K_S_MAX * (double)(my + nz), big_c = sumz > K_S_MAX * (double)nz;
                 double sd = 1.0, sc = 1.0;
-                if (big_d) sd = sty / (double)(my + nz) / K_S_MAX;
-                if (big_c) sc = sumz / (double)nz / K_S_MAX;
+                if (big_d) sd = div_cold(sty, (double)(my + nz) * K_S_MAX);
+                if (big_c) sc = div_cold(sumz, (double)nz * K_S_MAX);
                 // complementarity of this lane: max |slack * z - t| over its bound pairs
                 // (the ten slack * z products once; pairs this thread does not own repeat its v pair,
                 // which every stage thread owns, so that they do not change the maximum)
@@ -1277,10 +1315,10 @@ struct TeamSolver {
                 };
                 cm0 = compl_local(0.0); cmm = compl_local(mu);
                 // E_0 and E_mu in one pass
-                const double dcv = dmax_(big_d ? di / sd : di, cv);
+                const double dcv = dmax_(big_d ? div_cold(di, sd) : di, cv);
                 double e0, em;
                 {
-                    double r2[2] = {dmax_(dcv, big_c ? cm0 / sc : cm0), dmax_(dcv, big_c ? cmm / sc : cmm)};
+                    double r2[2] = {dmax_(dcv, big_c ? div_cold(cm0, sc) : cm0), dmax_(dcv, big_c ? div_cold(cmm, sc) : cmm)};
                     treduce<OP_MAX, 2>(r2);
                     e0 = r2[0]; em = r2[1];
                 }
@@ -1307,7 +1345,7 @@ struct TeamSolver {
                     nfilt = 0;
                     if (tiny_last) { tiny_last = false; break; }
                     const double cl = compl_local(mu);
-                    em = tmax(dmax_(dcv, big_c ? cl / sc : cl));
+                    em = tmax(dmax_(dcv, big_c ? div_cold(cl, sc) : cl));
                 }
                 if (ret == -3) break;
                 dw = 0.0;

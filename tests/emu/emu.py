@@ -19,7 +19,7 @@ class KCfg(C.Structure):
                 # derived fields, filled by kcfg_finalize() inside the driver
                 ("vLo", C.c_double), ("vHi", C.c_double), ("aLo", C.c_double), ("aHi", C.c_double),
                 ("dLo", C.c_double), ("dHi", C.c_double), ("rHiFirst", C.c_double * 2), ("rHiLater", C.c_double * 2),
-                ("rfrac", C.c_double), ("mu_min", C.c_double),
+                ("rfrac", C.c_double), ("mu_min", C.c_double), ("dtLb", C.c_double),
                 ("roles", C.c_void_p)]   # filled inside the driver
 
 

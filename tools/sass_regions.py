@@ -35,6 +35,8 @@ def find(pat, start=0):
 
 
 marks = [  # (region, first line); a region ends where the next one starts
+    ("kappa_clamp", find(r"MPC_DEV_NOINLINE void kappa_sigma_clamp")),
+    ("roles_fn", find(r"MPC_HD void riccati_roles")),
     ("team_collectives", find(r"MPC_DEV void tsync\(\)")),
     ("init_work", find(r"static void init_work")),
     ("recips", find(r"MPC_DEV void recips")),
@@ -47,11 +49,13 @@ marks = [  # (region, first line); a region ends where the next one starts
     ("forward", find(r"MPC_DEV void riccati_forward")),
     ("duals", find(r"MPC_DEV void recover_duals")),
     ("alpha_primal", find(r"MPC_DEV double alpha_primal")),
+    ("rollout_restore", find(r"MPC_DEV void rollout_restore")),
     ("nlp_feasible", find(r"MPC_DEV bool nlp_feasible")),
     ("solve_init", find(r"MPC_DEV Result solve\(\)")),
     ("drv_heavy_dispatch", find(r"shared heavy work")),
     ("drv_trial_test", find(r"if \(phase == PH_TRIAL \|\| phase == PH_SOC\)")),
     ("drv_accept", find(r"---------------- accepted")),
+    ("drv_resto_init", find(r"if \(phase == PH_RESTO\)")),
     ("drv_eval0_ls", find(r"if \(phase == PH_EVAL0\)")),
     ("drv_begin", find(r"if \(phase == PH_BEGIN\)")),
     ("drv_resolve_pd", find(r"if \(phase == PH_RESOLVE_EVAL\)")),
@@ -59,7 +63,7 @@ marks = [  # (region, first line); a region ends where the next one starts
     ("io", find(r"Problem I/O for one warp")),
     ("rollout", find(r"Closed-loop rollout")),
 ]
-LEAF = {"recips", "eval_point", "gradient", "assemble", "backward_roles", "backward_loop", "backward_wrap", "forward", "duals",
+LEAF = {"kappa_clamp", "rollout_restore", "recips", "eval_point", "gradient", "assemble", "backward_roles", "backward_loop", "backward_wrap", "forward", "duals",
         "alpha_primal", "nlp_feasible", "init_work"}
 
 
