@@ -66,7 +66,10 @@ mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const long long B, uns
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2)
+#ifndef MPC_ROLLOUT_MIN_BLOCKS
+#define MPC_ROLLOUT_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MPC_ROLLOUT_MIN_BLOCKS)
 mpc_rollout_kernel(const KCfg cfg, const RolloutArgs args, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
