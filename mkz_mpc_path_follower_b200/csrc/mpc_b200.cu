@@ -74,14 +74,16 @@ mpc_rollout_kernel(const KCfg cfg, const RolloutArgs args, unsigned long long* c
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
     const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_team(cfg.N));
+    const smem_t px = smem_base(smem_all + (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg.N));   // plant exchange area
+    __shared__ unsigned long long next_group;
     TeamSolver<1>::init_work(smem, cfg.N);
-    for (;;) {
-        unsigned long long b = 0;
-        if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= (unsigned long long)args.B) break;
-        rollout_vehicle(cfg, args, (long)b, smem);
-        __syncwarp();
+    for (;;) {   // the block takes WARPS_PER_BLOCK vehicles at a time and steps them together
+        if (threadIdx.x == 0) next_group = atomicAdd(counter, (unsigned long long)WARPS_PER_BLOCK);
+        __syncthreads();
+        const unsigned long long b0 = next_group;
+        __syncthreads();
+        if (b0 >= (unsigned long long)args.B) break;
+        rollout_group(cfg, args, (long)b0, smem, px, WARPS_PER_BLOCK);
     }
 }
 
@@ -239,7 +241,7 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
         TRY_OR_FREE(cudaMemcpy(h->d_roles, roles, sizeof(roles), cudaMemcpyHostToDevice));
     }
     if (h->team_warps == 1) {
-        h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N) * sizeof(double);
+        h->smem_bytes = ((size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N) + WARPS_PER_BLOCK * ROLLOUT_PX) * sizeof(double);
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));

@@ -1601,17 +1601,40 @@ MPC_DEV double sel8(const double* v, int i) {   // register-friendly v[i] for a 
     return (i == 0) ? v[0] : (i == 1) ? v[1] : (i == 2) ? v[2] : (i == 3) ? v[3] : (i == 4) ? v[4] : (i == 5) ? v[5] : (i == 6) ? v[6] : v[7];
 }
 
-MPC_DEV void rollout_vehicle(const KCfg& cfg, const RolloutArgs& a, long b, smem_t smem) {
+// One block = `nwarps` vehicles (one per warp) stepping through the T control periods together.
+// The plant of all the block's vehicles is integrated by ONE warp, lane = vehicle (every lane of a
+// warp would otherwise repeat the same 100 Euler sub-steps, atan2 and sincos included: 40 % of the
+// rollout's instructions); states and commands cross through `px` ([vehicle][10] doubles) around two
+// block barriers per control period.  Warps whose vehicle index is past the fleet only keep the barriers.
+#define ROLLOUT_PX 10   // X, Y, psi, vx, vy, wz, acc, df, acc_des, df_des
+MPC_DEV void rollout_group(const KCfg& cfg, const RolloutArgs& a, long b0, smem_t smem, smem_t px, int nwarps) {
     TeamSolver<1> S(cfg, smem);
     const int k = S.k, N = cfg.N;
-    const PathTable& path = a.paths[a.path_of[b]];
-    double st[8] = {a.pose0[3 * b], a.pose0[3 * b + 1], a.pose0[3 * b + 2], 0, 0, 0, 0, 0};
+    const int w = thread_in_block() >> 5;
+    const long b = b0 + w;
+    const bool valid = b < a.B;
+    const int pxw = SO(w * ROLLOUT_PX);
+    const PathTable& path = a.paths[valid ? a.path_of[b] : 0];
+    if (k < 8) sts(px, pxw + SO(k), (valid && k < 3) ? a.pose0[3 * b + k] : 0.0);
+    double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double acc_des = 0.0, df_des = 0.0, up_d = 0.0, up_a = 0.0;   // commands, d_f_current, acc_current
     const double des_speed = a.target_vel > 0.0 ? a.target_vel : 0.0;
     bool stop = false;
     S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;   // start = 0.0, then the previous solution
     for (int t = 0; t < a.T; t++) {
-        for (int i = 0; i < 10; i++) plant_step(st, acc_des, df_des);
+        if (k == 0) { sts(px, pxw + SO(8), acc_des); sts(px, pxw + SO(9), df_des); }
+        block_sync();
+        if (w == 0 && k < nwarps) {   // lane = vehicle: ten 100 Hz publishes of ten Euler sub-steps each
+            const int pv = SO(k * ROLLOUT_PX);
+            double ps[8];
+            for (int i = 0; i < 8; i++) ps[i] = lds(px, pv + SO(i));
+            const double ad = lds(px, pv + SO(8)), dd = lds(px, pv + SO(9));
+            MPC_NOUNROLL for (int i = 0; i < 10; i++) plant_step(ps, ad, dd);
+            for (int i = 0; i < 8; i++) sts(px, pv + SO(i), ps[i]);
+        }
+        block_sync();
+        if (!valid) continue;
+        for (int i = 0; i < 8; i++) st[i] = lds(px, pxw + SO(i));
         double xr, yr, pr;
         const bool sc = get_waypoints_warp(path, N, cfg.dt, st[0], st[1], st[2], !a.track_using_time, des_speed, xr, yr, pr);
         S.set_ref(xr, yr, pr);
@@ -1634,8 +1657,8 @@ MPC_DEV void rollout_vehicle(const KCfg& cfg, const RolloutArgs& a, long b, smem
             a.log[((long)t * a.B + b) * 8 + k] = sel8(lv, k);
         }
     }
-    if (a.final_state && k < 8) a.final_state[b * 8 + k] = sel8(st, k);
-    syncwarp();
+    if (valid && a.final_state && k < 8) a.final_state[b * 8 + k] = sel8(st, k);
+    block_sync();
 }
 
 }  // namespace mpcb200

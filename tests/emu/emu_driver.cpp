@@ -72,11 +72,12 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
 }
 extern "C" int emu_kcfg_size() { return (int)sizeof(KCfg); }
 
-struct RJob { const KCfg* cfg; const RolloutArgs* a; long b; double* smem; };
-static void lane_rollout(int, void* p) {
+struct RJob { const KCfg* cfg; const RolloutArgs* a; long b0; double* smem; int per_team; };
+static void lane_rollout(int lane, void* p) {
     RJob* j = (RJob*)p;
-    TeamSolver<1>::init_work(j->smem, j->cfg->N);
-    rollout_vehicle(*j->cfg, *j->a, j->b, j->smem);
+    double* team = j->smem + (size_t)(lane >> 5) * j->per_team;
+    TeamSolver<1>::init_work(team, j->cfg->N);
+    rollout_group(*j->cfg, *j->a, j->b0, team, j->smem + (size_t)4 * j->per_team, 4);
 }
 extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, const int* path_of, int n0, const double* t,
                            const double* X, const double* Y, const double* psi, const double* s, int track_using_time,
@@ -91,12 +92,13 @@ extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, 
     a.pose0 = pose0; a.path_of = path_of;
     for (int i = 0; i < 3; i++) { a.paths[i].n = n0; a.paths[i].t = t; a.paths[i].X = X; a.paths[i].Y = Y; a.paths[i].psi = psi; a.paths[i].s = s; }
     a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel; a.log = log; a.final_state = final_state; a.B = B;
-    std::vector<double> smem_raw(smem_doubles_per_team(kc.N) + 2, 0.0);
+    const int per_team = smem_doubles_per_team(kc.N);
+    std::vector<double> smem_raw((size_t)4 * per_team + 4 * ROLLOUT_PX + 2, 0.0);
     double* smem = smem_raw.data();
     if (((size_t)smem) & 15) smem++;
-    for (long b = 0; b < B; b++) {
-        RJob j{&kc, &a, b, smem};
-        emu::run_warp(lane_rollout, &j);
+    for (long b0 = 0; b0 < B; b0 += 4) {   // one emulated block of four warps = four vehicles
+        RJob j{&kc, &a, b0, smem, per_team};
+        emu::run_warp(lane_rollout, &j, 4);
     }
     return 0;
 }

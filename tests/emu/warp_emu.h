@@ -1,4 +1,4 @@
-// warp_emu.h -- TEST ONLY.  Single-threaded emulation of one thread block of 1..3 warps with
+// warp_emu.h -- TEST ONLY.  Single-threaded emulation of one thread block of 1..4 warps with
 // ucontext coroutines, so that mkz_mpc_path_follower_b200/csrc/mpc_kernel.cuh can be compiled by
 // g++ and stepped on a CPU.  Every warp collective is a rendezvous of the 32 lanes of the calling
 // lane's warp (full mask), checked by call-site id; block barriers wait for every lane of the
@@ -16,7 +16,7 @@
 
 namespace mpcb200 {
 namespace emu {
-#define MPC_EMU_MAX_LANES 96
+#define MPC_EMU_MAX_LANES 128
 struct Warp {
     ucontext_t main_ctx, ctx[MPC_EMU_MAX_LANES];
     char* stacks;

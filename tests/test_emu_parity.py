@@ -109,3 +109,23 @@ def test_rollout_start_mode(oracle, N, B):
     o0 = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=4)
     both = o0["status"] == 0
     assert np.abs(o["u0"] - o0["u0"])[both].max() <= 1e-5
+
+
+def test_emulated_rollout_group(oracle):
+    """The closed-loop rollout kernel source on the emulator: one block of four warps = four vehicles, the
+    plant of all of them integrated by one warp (lane = vehicle) between two block barriers per control
+    period.  Five vehicles (a full group and a ragged one) against the oracle's closed loop."""
+    import emu as E
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    g = GPSRefTrajectory(mat_filename=1)
+    cfg = oracle.default_cfg(8)
+    rng = np.random.default_rng(3)
+    poses = np.array([g.trajectory[j, [4, 5, 3]] + rng.normal(scale=[0.3, 0.3, 0.03]) for j in (0, 900, 2500, 4000, 5200)])
+    T = 10
+    log, final = E.rollout(E.kcfg_from_oracle(cfg), g.trajectory, poses, T)
+    path, keep = oracle.make_path(g.trajectory)
+    for b in range(poses.shape[0]):
+        olog = oracle.closed_loop(cfg, path, poses[b], T)
+        assert np.array_equal(log[:, b, 6], olog[:, 6]) and np.array_equal(log[:, b, 7], olog[:, 7]), b
+        assert np.abs(log[:, b, 4:6] - olog[:, 4:6]).max() <= 1e-9, b
+        assert np.abs(log[:, b, 0:4] - olog[:, 0:4]).max() <= 1e-9, b
