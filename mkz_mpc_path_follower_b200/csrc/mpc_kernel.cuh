@@ -953,7 +953,7 @@ struct TeamSolver {
     // Restoration by rollout (oracle: ipm_rollout_restore).  The inputs of the current iterate are
     // projected stage by stage onto the input box, the rate rows and the speed bounds, and the states
     // are rolled out from the measured state (MKZMPCPathFollower.jl:115-123).  One serial recursion
-    // per problem, run by a quarter warp through the per-thread step fields (dead at this point).
+    // per problem, run by one thread through the per-thread step fields (dead at this point).
     // ------------------------------------------------------------------
     MPC_DEV void rollout_restore() {
         const int st = lfs();
@@ -963,7 +963,7 @@ struct TeamSolver {
             st_dx(D);
         }
         tsync();
-        if (lane_id() < 8 && (W == 1 || (k >> 5) == 0)) {
+        if (k == 0) {   // one thread: the recursion reads and rewrites the same words stage by stage
             RolloutConsts rc;
             rc.dt = c.dt; rc.dtc = c.dtc; rc.dtLb = c.dtLb; rc.rfrac = c.rfrac; rc.vmin = c.vmin; rc.vmax = c.vmax;
             rc.amax = c.amax; rc.smax = c.smax; rc.admax = c.admax; rc.sdmax = c.sdmax;

@@ -42,6 +42,17 @@ def kcfg_from_oracle(ocfg, start_mode=0):
     return k
 
 
+def race_check(on=True):
+    """Switch the emulator's shared-memory race check on (and reset its counter) or off."""
+    C.CDLL(build()).emu_race_enable(1 if on else 0)
+
+
+def race_count():
+    lib = C.CDLL(build())
+    lib.emu_race_count.restype = C.c_long
+    return lib.emu_race_count()
+
+
 def solve_batch(kcfg, state, ref, v_des, u_prev, warm=None, want_traj=False):
     lib = C.CDLL(build())
     assert lib.emu_kcfg_size() == C.sizeof(KCfg)

@@ -7,6 +7,7 @@
 
 namespace mpcb200 { namespace emu {
 thread_local Warp* W = nullptr;
+thread_local RaceState RS;
 
 static void trampoline(int lane) {
     Warp* w = W;
@@ -44,6 +45,15 @@ void run_warp(void (*fn)(int, void*), void* arg, int warps) {
 
 using namespace mpcb200;
 
+// benign words of one team's shared memory: the sink of inactive lanes and, in every per-thread
+// field, the slot shared by the threads that own no stage
+static void register_benign(double* team, int N) {
+    emu::race_benign(team + W_DUMMY, 1, 2);
+    emu::race_benign(team + lf_offset(N) + (N + 1), N + 2, LF_FIELDS);
+}
+extern "C" long emu_race_count() { return emu::RS.races; }
+extern "C" void emu_race_enable(int on) { emu::RS.enabled = on; emu::RS.races = 0; }
+
 struct Job { const KCfg* cfg; const BatchPtrs* io; long b; double* smem; };
 template <int W> static void lane_main(int, void* a) {
     Job* j = (Job*)a;
@@ -66,6 +76,8 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
     const int W = team_warps(kc.N);
     for (long b = 0; b < B; b++) {
         Job j{&kc, &io, b, smem};
+        emu::race_reset();
+        register_benign(smem, kc.N);
         emu::run_warp(W == 1 ? lane_main<1> : W == 2 ? lane_main<2> : lane_main<3>, &j, W);
     }
     return 0;
@@ -98,6 +110,8 @@ extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, 
     if (((size_t)smem) & 15) smem++;
     for (long b0 = 0; b0 < B; b0 += 4) {   // one emulated block of four warps = four vehicles
         RJob j{&kc, &a, b0, smem, per_team};
+        emu::race_reset();
+        for (int w = 0; w < 4; w++) register_benign(smem + (size_t)w * per_team, kc.N);
         emu::run_warp(lane_rollout, &j, 4);
     }
     return 0;

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <ucontext.h>
+#include <unordered_map>
 
 #define MPC_DEV inline
 #define MPC_DEV_NOINLINE inline
@@ -28,6 +29,7 @@ struct Warp {
     int site[2][MPC_EMU_MAX_LANES];
     int epoch[MPC_EMU_MAX_LANES];    // per-lane warp-collective counter
     long arrive[MPC_EMU_MAX_LANES];  // per-lane block-barrier counter
+    long wsync[MPC_EMU_MAX_LANES];   // per-lane bar.warp.sync counter
     int bpred[2][MPC_EMU_MAX_LANES];
     void (*fn)(int lane, void* arg);
     void* arg;
@@ -63,6 +65,49 @@ inline void check_site(int b, int site) {
     }
 }
 void run_warp(void (*fn)(int, void*), void* arg, int warps = 1);
+
+// ---- shared-memory race check (stands in for compute-sanitizer racecheck, which is closed on the GPU
+// pool): a lane may read or overwrite a word last written by ANOTHER lane only if a bar.warp.sync (same
+// warp) or a block barrier separates the two accesses; shuffles are rendezvous points, not fences.
+// Several lanes storing the same value to a word is not a race.  Words registered as benign (sinks of inactive lanes, the slot shared by threads that own no stage)
+// are skipped.
+struct ShadowWord { int lane; long wsync; long arrive; };
+struct BenignSet { const double* base; long stride; int count; };   // words base + i * stride, i < count
+struct RaceState {
+    std::unordered_map<const double*, ShadowWord> last_write;
+    BenignSet benign[16]; int n_benign;
+    long races; int enabled;
+};
+extern thread_local RaceState RS;
+inline void race_reset() { RS.last_write.clear(); RS.n_benign = 0; }
+inline void race_benign(const double* base, long stride, int count) {
+    if (RS.n_benign < 16) RS.benign[RS.n_benign++] = BenignSet{base, stride, count};
+}
+inline bool race_skip(const double* a) {
+    for (int i = 0; i < RS.n_benign; i++) {
+        const BenignSet& b = RS.benign[i];
+        const long d = a - b.base;
+        if (d >= 0 && d % b.stride == 0 && d / b.stride < b.count) return true;
+    }
+    return false;
+}
+inline void race_check(const double* a, bool is_write, double v = 0.0) {
+    if (!RS.enabled || race_skip(a)) return;
+    if (is_write && memcmp(a, &v, sizeof(double)) == 0) return;   // several lanes storing the same value: idempotent
+    Warp* w = W; const int l = w->cur;
+    auto it = RS.last_write.find(a);
+    if (it != RS.last_write.end() && it->second.lane != l) {
+        const ShadowWord& s = it->second;
+        const bool same_warp = (s.lane >> 5) == (l >> 5);
+        const bool fenced = (w->arrive[l] > s.arrive) || (same_warp && w->wsync[l] > s.wsync);
+        if (!fenced) {
+            if (RS.races < 10) fprintf(stderr, "warp_emu: shared-memory race on %p: lane %d %s a word lane %d wrote with no barrier in between\n",
+                                       (const void*)a, l, is_write ? "overwrites" : "reads", s.lane);
+            RS.races++;
+        }
+    }
+    if (is_write) RS.last_write[a] = ShadowWord{l, w->wsync[l], w->arrive[l]};
+}
 // block barrier: every lane of the block arrives; lanes of other warps keep taking turns meanwhile
 inline long block_arrive() {
     Warp* w = W; const int l = w->cur;
@@ -106,6 +151,7 @@ MPC_DEV int shfl(int v, int src) {
 MPC_DEV void syncwarp() {
     emu::Warp* w = emu::W; int l = w->cur; int b = w->epoch[l] & 1;
     emu::publish_i(0, __LINE__); emu::check_site(b, __LINE__); w->epoch[l]++;
+    w->wsync[l]++;
 }
 MPC_DEV bool warp_all(bool p) {
     emu::Warp* w = emu::W; int l = w->cur; int b = w->epoch[l] & 1;
@@ -124,10 +170,10 @@ MPC_DEV float fast_exp2(float x) { return exp2f(x); }
 typedef double* smem_t;
 #define SO(x) (x)
 MPC_DEV smem_t smem_base(double* p) { return p; }
-MPC_DEV double lds(smem_t b, int off) { return b[off]; }
+MPC_DEV double lds(smem_t b, int off) { emu::race_check(b + off, false); return b[off]; }
 struct d2 { double x, y; };
-MPC_DEV d2 lds2(smem_t b, int off) { d2 r; r.x = b[off]; r.y = b[off + 1]; return r; }
-MPC_DEV void sts(smem_t b, int off, double v) { b[off] = v; }
+MPC_DEV d2 lds2(smem_t b, int off) { emu::race_check(b + off, false); emu::race_check(b + off + 1, false); d2 r; r.x = b[off]; r.y = b[off + 1]; return r; }
+MPC_DEV void sts(smem_t b, int off, double v) { emu::race_check(b + off, true, v); b[off] = v; }
 MPC_DEV int launder(int v) { return v; }
 MPC_DEV void ld_roles(const int* p, int* out) { for (int i = 0; i < 20; i++) out[i] = p[i]; }
 }  // namespace mpcb200

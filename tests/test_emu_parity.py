@@ -13,6 +13,17 @@ from mkz_mpc_path_follower_b200 import workload as W
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
 
 
+@pytest.fixture(autouse=True)
+def _race_check():
+    """Every emulated run is also a shared-memory race check (compute-sanitizer's racecheck is closed on
+    the GPU pool): a word written by one lane may be read or overwritten by another only across a
+    bar.warp.sync / block barrier."""
+    import emu as E
+    E.race_check(True)
+    yield
+    assert E.race_count() == 0
+
+
 @pytest.mark.parametrize("N,B", [(8, 24), (20, 10), (3, 4)])
 def test_emulated_kernel_matches_oracle(oracle, N, B):
     import emu as E
