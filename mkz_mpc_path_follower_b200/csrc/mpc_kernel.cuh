@@ -152,18 +152,26 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define SDS 46      // even: records are 16-byte aligned
 #define KST_STRIDE 14
 
-// per-thread fields kept in shared memory instead of registers: field f of stage k at
-// W_LF + f * (N + 2) + min(k, N + 1)   (slot N + 1 is shared by the threads that own no stage)
-#define LF_EV 0     // 12: cos/sin(psi+beta), cos/sin(beta), beta', beta'', rd[4], dr[2] of the last evaluated point
-#define LF_REF 12   // 3: x_ref, y_ref, psi_ref
-#define LF_DX 15    // 6: primal step dsx, dsy, dsp, dsv, dua, dud
-#define LF_DRS 21   // 2: slack step of the rate row
-#define LF_DY 23    // 6: new equality / rate-row multipliers (y + dy)
-#define LF_Z 29     // 10: bound multipliers zvL, zvU, zaL, zaU, zdL, zdU, rvL[2], rvU[2]
-#define LF_FIELDS 39
+// per-thread state kept in shared memory instead of registers, in groups: group g of stage k is the
+// G_*_N doubles at  lf_offset(N) + G_*_OFF * (N + 2) + G_*_STRIDE * min(k, N + 1)   (slot N + 1 is shared
+// by the threads that own no stage).  The strides are chosen so that 16-byte vector accesses of a
+// quarter warp (8-byte ones of a half warp for REF) fall into distinct banks.
+#define G_EV_OFF 0      // 12 (+2 pad): cos/sin(psi+beta), cos/sin(beta), beta', beta'', rd[4], dr[2] of the last evaluated point
+#define G_EV_STRIDE 14
+#define G_REF_OFF 14    // 3 (+1 so that the next group starts even): x_ref, y_ref, psi_ref
+#define G_REF_STRIDE 3
+#define G_DX_OFF 18     // 6: primal step dsx, dsy, dsp, dsv, dua, dud
+#define G_DX_STRIDE 6
+#define G_DRS_OFF 24    // 2: slack step of the rate row
+#define G_DRS_STRIDE 2
+#define G_DY_OFF 26     // 6: new equality / rate-row multipliers (y + dy)
+#define G_DY_STRIDE 6
+#define G_Z_OFF 32      // 10: bound multipliers zvL, zvU, zaL, zaU, zdL, zdU, rvL[2], rvU[2]
+#define G_Z_STRIDE 10
+#define LF_DOUBLES 42   // per stage slot, all groups
 MPC_HD int team_warps(int N) { return (N + 1 + 31) / 32; }   // warps that share one problem
 MPC_HD int lf_offset(int N) { return W_SD_OF(team_warps(N)) + (N + 1) * SDS + N * KST_STRIDE; }
-MPC_HD int smem_doubles_per_team(int N) { return (lf_offset(N) + LF_FIELDS * (N + 2) + 1) & ~1; }   // even: 16-byte alignment of the next team
+MPC_HD int smem_doubles_per_team(int N) { return lf_offset(N) + LF_DOUBLES * (N + 2); }   // even: 16-byte alignment of the next team
 
 MPC_DEV double dmax_(double a, double b) { return a > b ? a : b; }
 MPC_DEV double dmin_(double a, double b) { return a < b ? a : b; }
@@ -238,14 +246,14 @@ MPC_DEV_NOINLINE void kappa_sigma_clamp(double* z, const double* sl, double mu) 
 }
 
 // Serial part of the restoration by rollout (see TeamSolver::rollout_restore): inputs of stage s are
-// read from / written back to field LF_DX+4, +5 of stage s, states written to fields LF_DX+0..3.
+// read from / written back to entries 4, 5 of stage s's step group, states written to entries 0..3.
 // Rare (a few per cent of the cold starts, once each): out of line, scalars by value.
 struct RolloutConsts { double dt, dtc, dtLb, rfrac, vmin, vmax, amax, smax, admax, sdmax; };
-MPC_DEV_NOINLINE void rollout_core(smem_t sm, int fa, int st, int cbase, int N, RolloutConsts c) {
+MPC_DEV_NOINLINE void rollout_core(smem_t sm, int fa, int cbase, int N, RolloutConsts c) {
     double s0 = lds(sm, cbase), s1 = lds(sm, cbase + SO(1)), s2 = lds(sm, cbase + SO(2)), s3 = lds(sm, cbase + SO(3));
     double pa = lds(sm, cbase + SO(5)), pd = lds(sm, cbase + SO(4));
     MPC_NOUNROLL for (int s = 0; s < N; s++) {
-        double ua = lds(sm, fa + 4 * st), ud = lds(sm, fa + 5 * st);
+        double ua = lds(sm, fa + SO(4)), ud = lds(sm, fa + SO(5));
         if (s != 1) {   // rate rows exist for the first move and for pairs (s, s-1), s >= 2
             const double h = (s == 0) ? c.dtc : c.dt;
             const double la = 0.98 * c.admax * h, ld = 0.98 * c.sdmax * h;
@@ -255,8 +263,7 @@ MPC_DEV_NOINLINE void rollout_core(smem_t sm, int fa, int st, int cbase, int N, 
         ua = dmin_(dmax_(ua, -c.amax), c.amax);
         ud = dmin_(dmax_(ud, -c.smax), c.smax);
         ua = dmin_(dmax_(ua, (c.vmin - s3) / c.dt), (c.vmax - s3) / c.dt);   // v_{s+1} = v_s + dt acc stays inside [v_min, v_max]
-        sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
-        sts(sm, fa + 4 * st, ua); sts(sm, fa + 5 * st, ud);
+        sts2(sm, fa, s0, s1); sts2(sm, fa + SO(2), s2, s3); sts2(sm, fa + SO(4), ua, ud);
         double sd, cd, sps, cps;
         mpc_sincos(ud, &sd, &cd);
         mpc_sincos(s2, &sps, &cps);
@@ -268,10 +275,9 @@ MPC_DEV_NOINLINE void rollout_core(smem_t sm, int fa, int st, int cbase, int N, 
         const double n2 = s2 + c.dtLb * (s3 * sb);
         const double n3 = s3 + c.dt * ua;
         s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
-        fa += SO(1);
+        fa += SO(G_DX_STRIDE);
     }
-    sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
-    sts(sm, fa + 4 * st, 0.0); sts(sm, fa + 5 * st, 0.0);
+    sts2(sm, fa, s0, s1); sts2(sm, fa + SO(2), s2, s3); sts2(sm, fa + SO(4), 0.0, 0.0);
 }
 
 // ---- lane roles of the Riccati backward recursion (lanes = matrix entries), one row of ROLE_STRIDE
@@ -367,7 +373,7 @@ struct TeamSolver {
     const int N;
     const bool isS, isU, isR;  // thread owns a state / an input / a rate row
     int xpar;                  // W > 1: parity of the exchange buffers
-    const int lf;              // this thread's slot in the per-thread field area (byte offset on the device)
+    const int slot;            // this thread's slot in the per-thread state groups: min(k, N + 1)
     double sigma;
     LaneState L;
     EvalState ev;
@@ -376,67 +382,62 @@ struct TeamSolver {
     MPC_DEV TeamSolver(const KCfg& cfg, smem_t smem)
         : c(cfg), sm(smem), k(team_tid()), N(cfg.N), isS(team_tid() <= cfg.N), isU(team_tid() < cfg.N),
           isR((team_tid() == 0 || team_tid() >= 2) && team_tid() < cfg.N), xpar(0),
-          lf(SO(lf_offset(cfg.N) + (team_tid() <= cfg.N ? team_tid() : cfg.N + 1))) {}
+          slot(team_tid() <= cfg.N ? team_tid() : cfg.N + 1) {}
 
-    // per-thread fields in shared memory
-    MPC_DEV int lfs() const { return SO(N + 2); }   // field stride
+    // per-thread state in shared memory (groups G_*)
+    MPC_DEV int grp(int off, int stride) const { return SO(lf_offset(N) + off * (N + 2)) + slot * SO(stride); }
     MPC_DEV void ev_store(const EvalLane& e) {
-        const int st = lfs(); int a = lf + LF_EV * st;
-        sts(sm, a, e.cs); a += st; sts(sm, a, e.sn); a += st; sts(sm, a, e.cb); a += st; sts(sm, a, e.sb); a += st;
-        sts(sm, a, e.b1); a += st; sts(sm, a, e.b2); a += st;
-        sts(sm, a, e.rd[0]); a += st; sts(sm, a, e.rd[1]); a += st; sts(sm, a, e.rd[2]); a += st; sts(sm, a, e.rd[3]); a += st;
-        sts(sm, a, e.dr[0]); a += st; sts(sm, a, e.dr[1]);
+        const int a = grp(G_EV_OFF, G_EV_STRIDE);
+        sts2(sm, a, e.cs, e.sn); sts2(sm, a + SO(2), e.cb, e.sb); sts2(sm, a + SO(4), e.b1, e.b2);
+        sts2(sm, a + SO(6), e.rd[0], e.rd[1]); sts2(sm, a + SO(8), e.rd[2], e.rd[3]); sts2(sm, a + SO(10), e.dr[0], e.dr[1]);
     }
     MPC_DEV void ev_load_model(EvalLane& e) const {
-        const int st = lfs(); int a = lf + LF_EV * st;
-        e.cs = lds(sm, a); a += st; e.sn = lds(sm, a); a += st; e.cb = lds(sm, a); a += st; e.sb = lds(sm, a); a += st;
-        e.b1 = lds(sm, a); a += st; e.b2 = lds(sm, a);
+        const int a = grp(G_EV_OFF, G_EV_STRIDE);
+        const d2 v0 = lds2(sm, a), v1 = lds2(sm, a + SO(2)), v2 = lds2(sm, a + SO(4));
+        e.cs = v0.x; e.sn = v0.y; e.cb = v1.x; e.sb = v1.y; e.b1 = v2.x; e.b2 = v2.y;
     }
     MPC_DEV void ev_load_resid(EvalLane& e) const {
-        const int st = lfs(); int a = lf + (LF_EV + 6) * st;
-        e.rd[0] = lds(sm, a); a += st; e.rd[1] = lds(sm, a); a += st; e.rd[2] = lds(sm, a); a += st; e.rd[3] = lds(sm, a); a += st;
-        e.dr[0] = lds(sm, a); a += st; e.dr[1] = lds(sm, a);
+        const int a = grp(G_EV_OFF, G_EV_STRIDE);
+        const d2 v0 = lds2(sm, a + SO(6)), v1 = lds2(sm, a + SO(8)), v2 = lds2(sm, a + SO(10));
+        e.rd[0] = v0.x; e.rd[1] = v0.y; e.rd[2] = v1.x; e.rd[3] = v1.y; e.dr[0] = v2.x; e.dr[1] = v2.y;
     }
     MPC_DEV void set_ref(double x, double y, double p) {
-        const int st = lfs(); const int a = lf + LF_REF * st;
-        sts(sm, a, x); sts(sm, a + st, y); sts(sm, a + 2 * st, p);
+        const int a = grp(G_REF_OFF, G_REF_STRIDE);
+        sts(sm, a, x); sts(sm, a + SO(1), y); sts(sm, a + SO(2), p);
     }
-    MPC_DEV double ref_x() const { return lds(sm, lf + LF_REF * lfs()); }
-    MPC_DEV double ref_y() const { return lds(sm, lf + (LF_REF + 1) * lfs()); }
-    MPC_DEV double ref_p() const { return lds(sm, lf + (LF_REF + 2) * lfs()); }
+    MPC_DEV double ref_x() const { return lds(sm, grp(G_REF_OFF, G_REF_STRIDE)); }
+    MPC_DEV double ref_y() const { return lds(sm, grp(G_REF_OFF, G_REF_STRIDE) + SO(1)); }
+    MPC_DEV double ref_p() const { return lds(sm, grp(G_REF_OFF, G_REF_STRIDE) + SO(2)); }
     MPC_DEV void ld_dx(StepState& D) const {
-        const int st = lfs(); int a = lf + LF_DX * st;
-        D.dsx = lds(sm, a); a += st; D.dsy = lds(sm, a); a += st; D.dsp = lds(sm, a); a += st; D.dsv = lds(sm, a); a += st;
-        D.dua = lds(sm, a); a += st; D.dud = lds(sm, a);
+        const int a = grp(G_DX_OFF, G_DX_STRIDE);
+        const d2 v0 = lds2(sm, a), v1 = lds2(sm, a + SO(2)), v2 = lds2(sm, a + SO(4));
+        D.dsx = v0.x; D.dsy = v0.y; D.dsp = v1.x; D.dsv = v1.y; D.dua = v2.x; D.dud = v2.y;
     }
     MPC_DEV void st_dx(const StepState& D) {
-        const int st = lfs(); int a = lf + LF_DX * st;
-        sts(sm, a, D.dsx); a += st; sts(sm, a, D.dsy); a += st; sts(sm, a, D.dsp); a += st; sts(sm, a, D.dsv); a += st;
-        sts(sm, a, D.dua); a += st; sts(sm, a, D.dud);
+        const int a = grp(G_DX_OFF, G_DX_STRIDE);
+        sts2(sm, a, D.dsx, D.dsy); sts2(sm, a + SO(2), D.dsp, D.dsv); sts2(sm, a + SO(4), D.dua, D.dud);
     }
-    MPC_DEV void ld_drs(StepState& D) const { const int st = lfs(); const int a = lf + LF_DRS * st; D.drs[0] = lds(sm, a); D.drs[1] = lds(sm, a + st); }
-    MPC_DEV void st_drs(const StepState& D) { const int st = lfs(); const int a = lf + LF_DRS * st; sts(sm, a, D.drs[0]); sts(sm, a + st, D.drs[1]); }
+    MPC_DEV void ld_drs(StepState& D) const { const d2 v = lds2(sm, grp(G_DRS_OFF, G_DRS_STRIDE)); D.drs[0] = v.x; D.drs[1] = v.y; }
+    MPC_DEV void st_drs(const StepState& D) { sts2(sm, grp(G_DRS_OFF, G_DRS_STRIDE), D.drs[0], D.drs[1]); }
     MPC_DEV void ld_dy(StepState& D) const {
-        const int st = lfs(); int a = lf + LF_DY * st;
-        D.nyx = lds(sm, a); a += st; D.nyy = lds(sm, a); a += st; D.nyp = lds(sm, a); a += st; D.nyv = lds(sm, a); a += st;
-        D.nyd[0] = lds(sm, a); a += st; D.nyd[1] = lds(sm, a);
+        const int a = grp(G_DY_OFF, G_DY_STRIDE);
+        const d2 v0 = lds2(sm, a), v1 = lds2(sm, a + SO(2)), v2 = lds2(sm, a + SO(4));
+        D.nyx = v0.x; D.nyy = v0.y; D.nyp = v1.x; D.nyv = v1.y; D.nyd[0] = v2.x; D.nyd[1] = v2.y;
     }
     MPC_DEV void st_dy(const StepState& D) {
-        const int st = lfs(); int a = lf + LF_DY * st;
-        sts(sm, a, D.nyx); a += st; sts(sm, a, D.nyy); a += st; sts(sm, a, D.nyp); a += st; sts(sm, a, D.nyv); a += st;
-        sts(sm, a, D.nyd[0]); a += st; sts(sm, a, D.nyd[1]);
+        const int a = grp(G_DY_OFF, G_DY_STRIDE);
+        sts2(sm, a, D.nyx, D.nyy); sts2(sm, a + SO(2), D.nyp, D.nyv); sts2(sm, a + SO(4), D.nyd[0], D.nyd[1]);
     }
     MPC_DEV void ld_z(BoundMult& Z) const {
-        const int st = lfs(); int a = lf + LF_Z * st;
-        Z.zvL = lds(sm, a); a += st; Z.zvU = lds(sm, a); a += st; Z.zaL = lds(sm, a); a += st; Z.zaU = lds(sm, a); a += st;
-        Z.zdL = lds(sm, a); a += st; Z.zdU = lds(sm, a); a += st;
-        Z.rvL[0] = lds(sm, a); a += st; Z.rvL[1] = lds(sm, a); a += st; Z.rvU[0] = lds(sm, a); a += st; Z.rvU[1] = lds(sm, a);
+        const int a = grp(G_Z_OFF, G_Z_STRIDE);
+        const d2 v0 = lds2(sm, a), v1 = lds2(sm, a + SO(2)), v2 = lds2(sm, a + SO(4)), v3 = lds2(sm, a + SO(6)), v4 = lds2(sm, a + SO(8));
+        Z.zvL = v0.x; Z.zvU = v0.y; Z.zaL = v1.x; Z.zaU = v1.y; Z.zdL = v2.x; Z.zdU = v2.y;
+        Z.rvL[0] = v3.x; Z.rvL[1] = v3.y; Z.rvU[0] = v4.x; Z.rvU[1] = v4.y;
     }
     MPC_DEV void st_z(const BoundMult& Z) {
-        const int st = lfs(); int a = lf + LF_Z * st;
-        sts(sm, a, Z.zvL); a += st; sts(sm, a, Z.zvU); a += st; sts(sm, a, Z.zaL); a += st; sts(sm, a, Z.zaU); a += st;
-        sts(sm, a, Z.zdL); a += st; sts(sm, a, Z.zdU); a += st;
-        sts(sm, a, Z.rvL[0]); a += st; sts(sm, a, Z.rvL[1]); a += st; sts(sm, a, Z.rvU[0]); a += st; sts(sm, a, Z.rvU[1]);
+        const int a = grp(G_Z_OFF, G_Z_STRIDE);
+        sts2(sm, a, Z.zvL, Z.zvU); sts2(sm, a + SO(2), Z.zaL, Z.zaU); sts2(sm, a + SO(4), Z.zdL, Z.zdU);
+        sts2(sm, a + SO(6), Z.rvL[0], Z.rvL[1]); sts2(sm, a + SO(8), Z.rvU[0], Z.rvU[1]);
     }
 
     // ------------------------------------------------------------------
@@ -860,8 +861,7 @@ struct TeamSolver {
         if (lane_id() < 8 && (W == 1 || (k >> 5) == 0)) {
             int kp = SO(W_SD + (N + 1) * SDS);
             int r = SO(W_SD);
-            const int st = lfs();
-            int fa = SO(lf_offset(N)) + LF_DX * st;   // field LF_DX of stage 0
+            int fa = SO(lf_offset(N) + G_DX_OFF * (N + 2));   // step group of stage 0
             const d2 i01 = lds2(sm, SO(W_SD + N * SDS + SD_R)), i23 = lds2(sm, SO(W_SD + N * SDS + SD_R + 2));  // ds_0
             double s0 = i01.x, s1 = i01.y, s2 = i23.x, s3 = i23.y;
             double pa = 0.0, pd = 0.0;
@@ -875,17 +875,15 @@ struct TeamSolver {
                 // produced last (s0..s3 for the inputs, the inputs for the next state) are summed first
                 const double ua = ((ka2.x * pa + ka2.y * pd) + kx.x) + ((ka0.x * s0 + ka0.y * s1) + (ka1.x * s2 + ka1.y * s3));
                 const double ud = ((kd1.y * pa + kd2.x * pd) + kd2.y) + ((kx.y * s0 + kd0.x * s1) + (kd0.y * s2 + kd1.x * s3));
-                sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
-                sts(sm, fa + 4 * st, ua); sts(sm, fa + 5 * st, ud);
+                sts2(sm, fa, s0, s1); sts2(sm, fa + SO(2), s2, s3); sts2(sm, fa + SO(4), ua, ud);
                 const double n0 = ((s0 + r01.x) + (cp.x * s2 + cv.x * s3)) + cd.x * ud;
                 const double n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
                 const double n2 = ((s2 + r23.x) + a23 * s3) + b2 * ud;
                 const double n3 = (s3 + r23.y) + c.dt * ua;
                 s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
-                kp += SO(KST_STRIDE); r += SO(SDS); fa += SO(1);
+                kp += SO(KST_STRIDE); r += SO(SDS); fa += SO(G_DX_STRIDE);
             }
-            sts(sm, fa, s0); sts(sm, fa + st, s1); sts(sm, fa + 2 * st, s2); sts(sm, fa + 3 * st, s3);
-            sts(sm, fa + 4 * st, 0.0); sts(sm, fa + 5 * st, 0.0);
+            sts2(sm, fa, s0, s1); sts2(sm, fa + SO(2), s2, s3); sts2(sm, fa + SO(4), 0.0, 0.0);
         }
         tsync();
     }
@@ -956,7 +954,6 @@ struct TeamSolver {
     // per problem, run by one thread through the per-thread step fields (dead at this point).
     // ------------------------------------------------------------------
     MPC_DEV void rollout_restore() {
-        const int st = lfs();
         {
             StepState D;
             D.dsx = D.dsy = D.dsp = D.dsv = 0.0; D.dua = L.ua; D.dud = L.ud;
@@ -967,7 +964,7 @@ struct TeamSolver {
             RolloutConsts rc;
             rc.dt = c.dt; rc.dtc = c.dtc; rc.dtLb = c.dtLb; rc.rfrac = c.rfrac; rc.vmin = c.vmin; rc.vmax = c.vmax;
             rc.amax = c.amax; rc.smax = c.smax; rc.admax = c.admax; rc.sdmax = c.sdmax;
-            rollout_core(sm, SO(lf_offset(N)) + LF_DX * st, st, SO(W_CONST), N, rc);
+            rollout_core(sm, SO(lf_offset(N) + G_DX_OFF * (N + 2)), SO(W_CONST), N, rc);
         }
         tsync();
         if (isS) {

@@ -51,6 +51,7 @@ MPC_DEV d2 lds2(smem_t b, int off) {
     return v;
 }
 MPC_DEV void sts(smem_t b, int off, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(b + off), "d"(v) : "memory"); }
+MPC_DEV void sts2(smem_t b, int off, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(b + off), "d"(x), "d"(y) : "memory"); }
 MPC_DEV int launder(int v) { int r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 // one lane's row of the role table (20 ints, 16-byte aligned) through the read-only path
 MPC_DEV void ld_roles(const int* p, int* out) {

@@ -46,10 +46,12 @@ void run_warp(void (*fn)(int, void*), void* arg, int warps) {
 using namespace mpcb200;
 
 // benign words of one team's shared memory: the sink of inactive lanes and, in every per-thread
-// field, the slot shared by the threads that own no stage
+// state group, the slot shared by the threads that own no stage
 static void register_benign(double* team, int N) {
     emu::race_benign(team + W_DUMMY, 1, 2);
-    emu::race_benign(team + lf_offset(N) + (N + 1), N + 2, LF_FIELDS);
+    const int go[6] = {G_EV_OFF, G_REF_OFF, G_DX_OFF, G_DRS_OFF, G_DY_OFF, G_Z_OFF};
+    const int gs[6] = {G_EV_STRIDE, G_REF_STRIDE, G_DX_STRIDE, G_DRS_STRIDE, G_DY_STRIDE, G_Z_STRIDE};
+    for (int g = 0; g < 6; g++) emu::race_benign(team + lf_offset(N) + go[g] * (N + 2) + gs[g] * (N + 1), 1, gs[g]);
 }
 extern "C" long emu_race_count() { return emu::RS.races; }
 extern "C" void emu_race_enable(int on) { emu::RS.enabled = on; emu::RS.races = 0; }

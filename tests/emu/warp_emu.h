@@ -75,13 +75,13 @@ struct ShadowWord { int lane; long wsync; long arrive; };
 struct BenignSet { const double* base; long stride; int count; };   // words base + i * stride, i < count
 struct RaceState {
     std::unordered_map<const double*, ShadowWord> last_write;
-    BenignSet benign[16]; int n_benign;
+    BenignSet benign[64]; int n_benign;
     long races; int enabled;
 };
 extern thread_local RaceState RS;
 inline void race_reset() { RS.last_write.clear(); RS.n_benign = 0; }
 inline void race_benign(const double* base, long stride, int count) {
-    if (RS.n_benign < 16) RS.benign[RS.n_benign++] = BenignSet{base, stride, count};
+    if (RS.n_benign < 64) RS.benign[RS.n_benign++] = BenignSet{base, stride, count};
 }
 inline bool race_skip(const double* a) {
     for (int i = 0; i < RS.n_benign; i++) {
@@ -174,6 +174,7 @@ MPC_DEV double lds(smem_t b, int off) { emu::race_check(b + off, false); return 
 struct d2 { double x, y; };
 MPC_DEV d2 lds2(smem_t b, int off) { emu::race_check(b + off, false); emu::race_check(b + off + 1, false); d2 r; r.x = b[off]; r.y = b[off + 1]; return r; }
 MPC_DEV void sts(smem_t b, int off, double v) { emu::race_check(b + off, true, v); b[off] = v; }
+MPC_DEV void sts2(smem_t b, int off, double x, double y) { sts(b, off, x); sts(b, off + 1, y); }
 MPC_DEV int launder(int v) { return v; }
 MPC_DEV void ld_roles(const int* p, int* out) { for (int i = 0; i < 20; i++) out[i] = p[i]; }
 }  // namespace mpcb200
