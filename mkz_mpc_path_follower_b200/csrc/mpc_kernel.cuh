@@ -838,10 +838,10 @@ struct TeamSolver {
                 const double f0 = lds(sm, e_f0);
                 const double faa = fa.x, fad = fa.y;
                 const double det = faa * fdd - fad * fad;
-                if (!(faa > 0.0) || !(det > 0.0)) { ok = false; break; }
+                if (!(faa > 0.0) || !(det > 1e-300)) { ok = false; break; }   // (also keeps fast_rcp away from denormals)
                 // Fuu^{-1} = adj(Fuu) / det: everything that does not need 1/det is computed while the
                 // reciprocal is in flight, so only one multiply-add follows it
-                const double idet = 1.0 / det;
+                const double idet = fast_rcp(det);
                 const double a0 = fdd * fj.x - fad * fj.y, a1 = faa * fj.y - fad * fj.x;   // adj(Fuu) (F8[j][a], F8[j][df])
                 const double num = fi.x * a0 + fi.y * a1;
                 sts(sm, e_k0, -a0 * idet); sts(sm, e_k1, -a1 * idet);

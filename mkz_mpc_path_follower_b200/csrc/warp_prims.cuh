@@ -30,6 +30,16 @@ MPC_DEV void syncwarp() { asm volatile("bar.warp.sync 0xffffffff;" ::: "memory")
 MPC_DEV bool warp_all(bool p) { return __all_sync(MPC_FULL, p); }
 MPC_DEV bool warp_any(bool p) { return __any_sync(MPC_FULL, p); }
 MPC_DEV void mpc_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+// 1 / x for a positive, normal x (checked by the caller): hardware seed + two Newton steps, no special
+// cases -- about half the instructions of the IEEE division sequence; accurate to ~1 ulp
+MPC_DEV double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 MPC_DEV float fast_log2(float x) { return __log2f(x); }
 MPC_DEV float fast_exp2(float x) { return exp2f(x); }
 

@@ -164,6 +164,7 @@ MPC_DEV bool warp_any(bool p) {
     int r = 0; for (int i = (l & ~31); i < (l & ~31) + 32; i++) r |= w->islot[b][i]; return r != 0;
 }
 MPC_DEV void mpc_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+MPC_DEV double fast_rcp(double x) { return 1.0 / x; }
 MPC_DEV float fast_log2(float x) { return log2f(x); }
 MPC_DEV float fast_exp2(float x) { return exp2f(x); }
 // shared memory: a plain double array, offsets in doubles
