@@ -237,6 +237,29 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = conv_total * args.steps / float(te.item())
 
+    # ---- the same with the waypoints generated on the device (mpcb200_solve_batch_on_path): the host sends the
+    # state, the path id and the previous command only (60 B/problem instead of 560)
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    for i, pth in enumerate((1, 2, 3)):
+        solver.set_path(i, GPSRefTrajectory(mat_filename=pth, traj_horizon=N, traj_dt=0.2).trajectory)
+    h_pathof = torch.from_numpy((b["path"] - 1).astype(np.int32)).pin_memory().numpy()
+    for _ in range(2):
+        solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        r2 = solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
+        st2 = solver.stats()
+    torch.cuda.synchronize()
+    tp = torch.tensor([time.perf_counter() - w0, float((r2["status"] == 0).sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = tp[0:1].clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        csum = tp[1:2].clone(); dist.all_reduce(csum, op=dist.ReduceOp.SUM)
+        tp = torch.cat((tmax, csum))
+    e2e_on_path = {"value": float(tp[1].item()) * args.steps / float(tp[0].item()), "unit": "solves/s",
+                   "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
+                   "what": "mpcb200_solve_batch_on_path: reference waypoints generated on the device"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -299,6 +322,7 @@ def main():
                          "sample": "first %d problems of the same batch, restated CPU interior point (oracle), NOT Ipopt" % sample},
         "parity_vs_oracle": parity,
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "e2e_on_path": e2e_on_path,
         "gpu_launches": int(args.steps * 1),
         "clocks": clocks,
     }

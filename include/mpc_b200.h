@@ -111,6 +111,25 @@ int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n,
                      const double* psi, const double* s);
 
 /*
+ * mpcb200_solve_batch with the waypoints generated ON THE DEVICE from the path tables: replaces, per
+ * problem, grt.get_waypoints(x, y, psi[, des_speed]) of mpc_cmd_pub.jl:99-112 (ref_gps_traj.py:131-218:
+ * nearest sample over the whole path, np.interp of X, Y, psi at t_closest + h*dt -- or at
+ * s_closest + (h+1)*dt*target_vel when !track_using_time --, heading unwrap, stop_cmd) followed by the
+ * update_* / solve_model sequence above.  Input shrinks from 3(N+1)+7 to 7 doubles + one int per problem.
+ *   path_of [B]  path_id (0..2) given to mpcb200_set_path
+ *   v_des   [B] or NULL = target_vel for every problem (mpc_cmd_pub.jl:116 passes des_speed)
+ *   ref_out [B][3][N+1] or NULL: the generated waypoints (what the node publishes as target_path)
+ *   stop    [B] or NULL: get_waypoints' stop_cmd (1 when the last waypoint is the end of the path)
+ * Horizons up to 31 only.  With MPCB200_DEVICE pointers all three path tables must have been set.
+ */
+int mpcb200_solve_batch_on_path(mpcb200_handle* h, int64_t B,
+                                const double* state, const int32_t* path_of,
+                                int32_t track_using_time, double target_vel,
+                                const double* v_des, const double* u_prev, double* warm,
+                                double* u0, double* cost, int32_t* status, int32_t* iters,
+                                double* traj, double* ref_out, int32_t* stop, int32_t mem_space);
+
+/*
  * Closed-loop Monte-Carlo rollout (mpc_cmd_pub.jl:86-157 driving vehicle_simulator.py:58-112):
  * B vehicles x T control steps, each step = 10 plant publishes (100 Euler sub-steps), on-device
  * reference generation (time mode if target_vel <= 0 ... see track_using_time), warm-started solve,

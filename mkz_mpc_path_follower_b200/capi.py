@@ -54,6 +54,7 @@ def lib():
     L.mpcb200_set_cost.argtypes = [vp, dp]
     L.mpcb200_set_stream.argtypes = [vp, vp]
     L.mpcb200_solve_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
+    L.mpcb200_solve_batch_on_path.argtypes = [vp, C.c_int64, vp, vp, C.c_int32, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.mpcb200_set_path.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, dp, dp]
     L.mpcb200_rollout.argtypes = [vp, C.c_int64, C.c_int32, dp, ip, C.c_int32, C.c_double, dp, dp]
     L.mpcb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -143,6 +144,42 @@ class Solver(object):
         self._check(lib().mpcb200_solve_batch(self._h, B, _ptr(state), _ptr(ref), _ptr(v_des), _ptr(u_prev), _ptr(warm),
                                               _ptr(u0), _ptr(cost), _ptr(status), _ptr(iters), _ptr(traj), HOST))
         return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+    def solve_batch_on_path(self, state, path_of, u_prev, track_using_time=True, target_vel=1.0, v_des=None, warm=None,
+                            want_traj=False, want_ref=False):
+        """mpcb200_solve_batch_on_path: like solve_batch, but the waypoints are generated on the device from the
+        path tables given to set_path (get_waypoints of ref_gps_traj.py).  path_of (B,) in 0..2.  Returns the
+        solve_batch dict plus "stop" (B,) and, with want_ref, "ref" (B,3,N+1)."""
+        N = self.N
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        B = state.shape[0]
+        path_of = np.ascontiguousarray(path_of, dtype=np.int32)
+        u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+        if state.shape != (B, 4) or path_of.shape != (B,) or u_prev.shape != (B, 2):
+            raise ValueError("solve_batch_on_path: expected state (B,4), path_of (B,), u_prev (B,2)")
+        if v_des is not None:
+            v_des = np.ascontiguousarray(v_des, dtype=np.float64)
+            if v_des.shape != (B,):
+                raise ValueError("solve_batch_on_path: v_des must be (B,)")
+        if warm is not None:
+            if not (isinstance(warm, np.ndarray) and warm.dtype == np.float64 and warm.flags.c_contiguous
+                    and warm.shape == (B, 6 * N + 4)):
+                raise ValueError("solve_batch_on_path: warm must be a C-contiguous float64 (B,6N+4) array (updated in place)")
+        u0 = np.empty((B, 2)); cost = np.empty(B)
+        status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32); stop = np.empty(B, dtype=np.int32)
+        traj = np.empty((B, 6 * N + 4)) if want_traj else None
+        ref = np.empty((B, 3, N + 1)) if want_ref else None
+        self._check(lib().mpcb200_solve_batch_on_path(self._h, B, _ptr(state), _ptr(path_of), int(bool(track_using_time)), float(target_vel),
+                                                      _ptr(v_des), _ptr(u_prev), _ptr(warm), _ptr(u0), _ptr(cost), _ptr(status),
+                                                      _ptr(iters), _ptr(traj), _ptr(ref), _ptr(stop), HOST))
+        return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj, "ref": ref, "stop": stop}
+
+    def solve_batch_on_path_device(self, B, state, path_of, u_prev, u0, track_using_time=True, target_vel=1.0, v_des=None,
+                                   warm=None, cost=None, status=None, iters=None, traj=None, ref_out=None, stop=None):
+        """Device pointers (torch CUDA tensors); only enqueues on the handle's stream."""
+        self._check(lib().mpcb200_solve_batch_on_path(self._h, B, _ptr(state), _ptr(path_of), int(bool(track_using_time)), float(target_vel),
+                                                      _ptr(v_des), _ptr(u_prev), _ptr(warm), _ptr(u0), _ptr(cost), _ptr(status),
+                                                      _ptr(iters), _ptr(traj), _ptr(ref_out), _ptr(stop), DEVICE))
 
     def solve_batch_device(self, B, state, ref, u_prev, u0, v_des=None, warm=None, cost=None, status=None,
                            iters=None, traj=None):

@@ -28,7 +28,7 @@ constexpr int WARPS_PER_BLOCK = 4;
 #define MPC_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, MPC_MIN_BLOCKS)
-mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned long long* counter) {
+mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const long long B, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
     const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_team(cfg.N));
@@ -38,7 +38,7 @@ mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned
         if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= (unsigned long long)B) break;
-        solve_problem<1>(cfg, io, (long)b, smem);
+        solve_problem<1>(cfg, io, rg, (long)b, smem);
         __syncwarp();
     }
 }
@@ -51,7 +51,7 @@ mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned
 #endif
 template <int W>
 __global__ void __launch_bounds__(W * 32, W == 2 ? MPC_LONG_MIN_BLOCKS2 : MPC_LONG_MIN_BLOCKS3)
-mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const long long B, unsigned long long* counter) {
+mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const long long B, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     __shared__ unsigned long long next_problem;
     const smem_t smem = smem_base(smem_all);
@@ -62,7 +62,7 @@ mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const long long B, uns
         const unsigned long long b = next_problem;
         __syncthreads();
         if (b >= (unsigned long long)B) break;
-        solve_problem<W>(cfg, io, (long)b, smem);
+        solve_problem<W>(cfg, io, rg, (long)b, smem);
     }
 }
 
@@ -119,7 +119,7 @@ struct mpcb200_handle {
     unsigned long long* d_counter = nullptr;
     int* d_roles = nullptr;   /* lane roles of the Riccati recursion for this horizon (riccati_roles) */
     DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
-    DevBuf d_path[3], d_pose, d_pathof, d_log, d_final;
+    DevBuf d_path[3], d_pose, d_pathof, d_log, d_final, d_stop;
     int path_n[3] = {0, 0, 0};
     int rollout_blocks_per_sm = 0;
     mpcb200_stats stats;
@@ -267,7 +267,7 @@ int mpcb200_destroy(mpcb200_handle* h) {
     if (!h) return MPCB200_EINVAL;
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj,
-                      &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final};
+                      &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_roles) cudaFree(h->d_roles);
@@ -291,7 +291,7 @@ int mpcb200_set_stream(mpcb200_handle* h, void* s) {
     return MPCB200_OK;
 }
 
-static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io) {
+static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const RefGen& rg) {
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), h->stream));
     const int teams_per_block = (h->team_warps == 1) ? WARPS_PER_BLOCK : 1;
     long long blocks_needed = (B + teams_per_block - 1) / teams_per_block;
@@ -299,37 +299,68 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io) {
     int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
     if (grid < 1) grid = 1;
     if (h->team_warps == 1)
-        mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, (long long)B, h->d_counter);
+        mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, h->d_counter);
     else if (h->team_warps == 2)
-        mpc_solve_long_kernel<2><<<grid, 64, h->smem_bytes, h->stream>>>(make_kcfg(h), io, (long long)B, h->d_counter);
+        mpc_solve_long_kernel<2><<<grid, 64, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, h->d_counter);
     else
-        mpc_solve_long_kernel<3><<<grid, 96, h->smem_bytes, h->stream>>>(make_kcfg(h), io, (long long)B, h->d_counter);
+        mpc_solve_long_kernel<3><<<grid, 96, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, h->d_counter);
     CUDA_TRY(h, cudaGetLastError());
     h->stats.kernel_launches += 1;
     return 0;
 }
 
-int mpcb200_solve_batch(mpcb200_handle* h, int64_t B, const double* state, const double* ref, const double* v_des,
-                        const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
-                        double* traj, int32_t mem_space) {
+static void fill_paths(const mpcb200_handle* h, PathTable* paths) {
+    for (int i = 0; i < 3; i++) {
+        const double* base = (const double*)h->d_path[i].p;
+        const int n = h->path_n[i];
+        memset(&paths[i], 0, sizeof(PathTable));
+        paths[i].n = n;
+        if (n) { paths[i].t = base; paths[i].X = base + n; paths[i].Y = base + 2 * (size_t)n; paths[i].psi = base + 3 * (size_t)n; paths[i].s = base + 4 * (size_t)n; }
+    }
+}
+
+/* common body of mpcb200_solve_batch (ref given) and mpcb200_solve_batch_on_path (path_of given) */
+static int solve_batch_impl(mpcb200_handle* h, const char* who, int64_t B, const double* state, const double* ref, const int32_t* path_of,
+                            int32_t track_using_time, double target_vel, const double* v_des, const double* u_prev, double* warm,
+                            double* u0, double* cost, int32_t* status, int32_t* iters, double* traj, double* ref_out, int32_t* stop,
+                            int32_t mem_space) {
     if (!h) return MPCB200_EINVAL;
-    if (B < 0) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch: B=%lld", (long long)B);
-    if (mem_space != MPCB200_HOST && mem_space != MPCB200_DEVICE) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch: mem_space=%d", mem_space);
+    if (B < 0) return fail(h, MPCB200_EINVAL, "%s: B=%lld", who, (long long)B);
+    if (mem_space != MPCB200_HOST && mem_space != MPCB200_DEVICE) return fail(h, MPCB200_EINVAL, "%s: mem_space=%d", who, mem_space);
     memset(&h->stats, 0, sizeof(h->stats));
     if (B == 0) return MPCB200_OK;
-    if (!state || !ref || !u_prev || !u0) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch: state, ref, u_prev and u0 are required");
+    const bool on_path = (path_of != nullptr);
+    if (!state || (!ref && !on_path) || !u_prev || !u0) return fail(h, MPCB200_EINVAL, "%s: state, %s, u_prev and u0 are required", who, on_path ? "path_of" : "ref");
+    if (on_path && h->team_warps != 1) return fail(h, MPCB200_EINVAL, "%s: on-device reference generation needs N <= 31 (N=%d)", who, h->cfg.N);
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int N = h->cfg.N;
     const size_t nt = 6 * (size_t)N + 4, nr = 3 * ((size_t)N + 1);
+    RefGen rg;
+    memset(&rg, 0, sizeof(rg));
+    if (on_path) {
+        fill_paths(h, rg.paths);
+        rg.track_using_time = track_using_time; rg.target_vel = target_vel;
+        if (mem_space == MPCB200_HOST) {
+            for (int64_t b = 0; b < B; b++)
+                if (path_of[b] < 0 || path_of[b] > 2 || h->path_n[path_of[b]] == 0)
+                    return fail(h, MPCB200_EINVAL, "%s: problem %lld uses path %d, which was not set with mpcb200_set_path", who, (long long)b, path_of[b]);
+        } else {
+            for (int i = 0; i < 3; i++)   /* device ids cannot be inspected here: every table must be present */
+                if (h->path_n[i] == 0) return fail(h, MPCB200_EINVAL, "%s: with device pointers all three path tables must be set (path %d is not)", who, i);
+        }
+    }
     if (mem_space == MPCB200_DEVICE) {
         BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj};
-        return launch_solve(h, B, io);
+        rg.path_of = path_of; rg.ref_out = ref_out; rg.stop = stop;
+        return launch_solve(h, B, io, rg);
     }
     /* host pointers: stage through the handle's device buffers */
     const size_t bs = B * 4 * sizeof(double), br = B * nr * sizeof(double), bu = B * 2 * sizeof(double), bt = B * nt * sizeof(double);
     int rc;
     if ((rc = ensure(h, h->d_state, bs))) return rc;
-    if ((rc = ensure(h, h->d_ref, br))) return rc;
+    if ((!on_path || ref_out) && (rc = ensure(h, h->d_ref, br))) return rc;
+    if (on_path && (rc = ensure(h, h->d_pathof, B * sizeof(int32_t)))) return rc;
+    if (on_path && stop && (rc = ensure(h, h->d_stop, B * sizeof(int32_t)))) return rc;
     if ((rc = ensure(h, h->d_uprev, bu))) return rc;
     if ((rc = ensure(h, h->d_u0, bu))) return rc;
     if (v_des && (rc = ensure(h, h->d_vdes, B * sizeof(double)))) return rc;
@@ -340,17 +371,24 @@ int mpcb200_solve_batch(mpcb200_handle* h, int64_t B, const double* state, const
     if (traj && (rc = ensure(h, h->d_traj, bt))) return rc;
     cudaStream_t s = h->stream;
     CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, state, bs, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_ref.p, ref, br, cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += bs;
+    if (on_path) { CUDA_TRY(h, cudaMemcpyAsync(h->d_pathof.p, path_of, B * sizeof(int32_t), cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += B * sizeof(int32_t); }
+    else { CUDA_TRY(h, cudaMemcpyAsync(h->d_ref.p, ref, br, cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += br; }
     CUDA_TRY(h, cudaMemcpyAsync(h->d_uprev.p, u_prev, bu, cudaMemcpyHostToDevice, s));
-    h->stats.h2d_bytes += bs + br + bu;
+    h->stats.h2d_bytes += bu;
     if (v_des) { CUDA_TRY(h, cudaMemcpyAsync(h->d_vdes.p, v_des, B * sizeof(double), cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += B * sizeof(double); }
     if (warm) { CUDA_TRY(h, cudaMemcpyAsync(h->d_warm.p, warm, bt, cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += bt; }
-    BatchPtrs io{(const double*)h->d_state.p, (const double*)h->d_ref.p, v_des ? (const double*)h->d_vdes.p : nullptr,
+    BatchPtrs io{(const double*)h->d_state.p, on_path ? nullptr : (const double*)h->d_ref.p, v_des ? (const double*)h->d_vdes.p : nullptr,
                  (const double*)h->d_uprev.p, warm ? (double*)h->d_warm.p : nullptr, (double*)h->d_u0.p,
                  cost ? (double*)h->d_cost.p : nullptr, status ? (int*)h->d_status.p : nullptr,
                  iters ? (int*)h->d_iters.p : nullptr, traj ? (double*)h->d_traj.p : nullptr};
+    if (on_path) {
+        rg.path_of = (const int*)h->d_pathof.p;
+        rg.ref_out = ref_out ? (double*)h->d_ref.p : nullptr;
+        rg.stop = stop ? (int*)h->d_stop.p : nullptr;
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
-    if ((rc = launch_solve(h, B, io))) return rc;
+    if ((rc = launch_solve(h, B, io, rg))) return rc;
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     CUDA_TRY(h, cudaMemcpyAsync(u0, h->d_u0.p, bu, cudaMemcpyDeviceToHost, s));
     h->stats.d2h_bytes += bu;
@@ -359,11 +397,28 @@ int mpcb200_solve_batch(mpcb200_handle* h, int64_t B, const double* state, const
     if (iters) { CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
     if (traj) { CUDA_TRY(h, cudaMemcpyAsync(traj, h->d_traj.p, bt, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bt; }
     if (warm) { CUDA_TRY(h, cudaMemcpyAsync(warm, h->d_warm.p, bt, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bt; }
+    if (on_path && ref_out) { CUDA_TRY(h, cudaMemcpyAsync(ref_out, h->d_ref.p, br, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += br; }
+    if (on_path && stop) { CUDA_TRY(h, cudaMemcpyAsync(stop, h->d_stop.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
     CUDA_TRY(h, cudaStreamSynchronize(s));
     float ms = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->stats.kernel_ms = ms;
     return MPCB200_OK;
+}
+
+int mpcb200_solve_batch(mpcb200_handle* h, int64_t B, const double* state, const double* ref, const double* v_des,
+                        const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
+                        double* traj, int32_t mem_space) {
+    return solve_batch_impl(h, "mpcb200_solve_batch", B, state, ref, nullptr, 1, 0.0, v_des, u_prev, warm, u0, cost, status, iters, traj,
+                            nullptr, nullptr, mem_space);
+}
+
+int mpcb200_solve_batch_on_path(mpcb200_handle* h, int64_t B, const double* state, const int32_t* path_of, int32_t track_using_time,
+                                double target_vel, const double* v_des, const double* u_prev, double* warm, double* u0, double* cost,
+                                int32_t* status, int32_t* iters, double* traj, double* ref_out, int32_t* stop, int32_t mem_space) {
+    if (h && !path_of) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch_on_path: path_of is required");
+    return solve_batch_impl(h, "mpcb200_solve_batch_on_path", B, state, nullptr, path_of, track_using_time, target_vel, v_des, u_prev, warm,
+                            u0, cost, status, iters, traj, ref_out, stop, mem_space);
 }
 
 int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n, const double* t, const double* X, const double* Y,
@@ -407,12 +462,7 @@ int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T, const double* pose0
     RolloutArgs a;
     memset(&a, 0, sizeof(a));
     a.pose0 = (const double*)h->d_pose.p; a.path_of = (const int*)h->d_pathof.p;
-    for (int i = 0; i < 3; i++) {
-        const double* base = (const double*)h->d_path[i].p;
-        const int n = h->path_n[i];
-        a.paths[i].n = n;
-        if (n) { a.paths[i].t = base; a.paths[i].X = base + n; a.paths[i].Y = base + 2 * (size_t)n; a.paths[i].psi = base + 3 * (size_t)n; a.paths[i].s = base + 4 * (size_t)n; }
-    }
+    fill_paths(h, a.paths);
     a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel;
     a.log = log ? (double*)h->d_log.p : nullptr; a.final_state = final_state ? (double*)h->d_final.p : nullptr; a.B = (long)B;
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), s));

@@ -1437,116 +1437,9 @@ struct TeamSolver {
     }
 };
 
-// Problem I/O for one warp: problem-major layouts of include/mpc_b200.h.
-struct BatchPtrs {
-    const double* state;   // [B][4]
-    const double* ref;     // [B][3][N+1]
-    const double* v_des;   // [B] or null
-    const double* u_prev;  // [B][2]
-    double* warm;          // [B][6N+4] or null
-    double* u0;            // [B][2]
-    double* cost;          // [B] or null
-    int* status;           // [B] or null
-    int* iters;            // [B] or null
-    double* traj;          // [B][6N+4] or null
-};
-
-template <int W>
-MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, long b, smem_t smem) {
-    TeamSolver<W> S(cfg, smem);
-    const int k = S.k, N = cfg.N;
-    const long nr = 3L * (N + 1), nt = 6L * N + 4;
-    // ---- coalesced loads: lane k takes stage k's reference sample; lanes 0..6 the problem constants
-    const double* rf = io.ref + nr * b;
-    S.set_ref((k <= N) ? rf[k] : 0.0, (k <= N) ? rf[(N + 1) + k] : 0.0, (k <= N) ? rf[2 * (N + 1) + k] : 0.0);
-    {
-        double cv = 0.0;
-        if (k < 4) cv = io.state[4 * b + k];
-        else if (k < 6) cv = io.u_prev[2 * b + (k - 4)];
-        else if (k == 6) cv = io.v_des ? io.v_des[b] : 0.0;
-        if (k < 8) sts(smem, SO(W_CONST + k), cv);
-        S.tsync();
-    }
-    // ---- start point
-    S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;
-    if (io.warm) {
-        const double* w = io.warm + nt * b;
-        if (k <= N) { S.L.sx = w[k]; S.L.sy = w[(N + 1) + k]; S.L.sv = w[2 * (N + 1) + k]; S.L.sp = w[3 * (N + 1) + k]; }
-        if (k < N) { S.L.ud = w[4 * (N + 1) + k]; S.L.ua = w[4 * (N + 1) + N + k]; }
-    } else if (cfg.start_mode == 1) {
-        // MPCB200_START_ROLLOUT (opt-in, not a reference behaviour): hold the previous command over the
-        // horizon (projected onto the box and rate rows) and roll the model out from the measured state
-        if (k < N) { S.L.ua = S.cst(5); S.L.ud = S.cst(4); }
-        S.rollout_restore();
-    }
-    const Result r = S.solve();
-    // ---- results
-    const double a0 = S.bcast0(S.L.ua), d0 = S.bcast0(S.L.ud);
-    if (k == 0) {
-        io.u0[2 * b] = a0; io.u0[2 * b + 1] = d0;
-        if (io.cost) io.cost[b] = r.cost;
-        if (io.status) io.status[b] = r.status;
-        if (io.iters) io.iters[b] = r.iters;
-    }
-    for (int pass = 0; pass < 2; pass++) {
-        double* t = (pass == 0) ? io.traj : io.warm;
-        if (!t) continue;
-        t += nt * b;
-        if (k <= N) { t[k] = S.L.sx; t[(N + 1) + k] = S.L.sy; t[2 * (N + 1) + k] = S.L.sv; t[3 * (N + 1) + k] = S.L.sp; }
-        if (k < N) { t[4 * (N + 1) + k] = S.L.ud; t[4 * (N + 1) + N + k] = S.L.ua; }
-    }
-    S.tsync();
-}
-
-
-// ======================================================================================
-// Closed-loop rollout: one warp = one vehicle for T control steps, everything on the device.
-//   plant              scripts/vehicle_simulator.py:58-112  (10 publishes x 10 Euler sub-steps per control period)
-//   reference          scripts/gps_utils/ref_gps_traj.py:131-218 (nearest sample, np.interp, heading unwrap, stop_cmd)
-//   control step       scripts/mpc_cmd_pub.jl:86-157 (warm-started solve, command fed back, stop latch)
-// ======================================================================================
+// ---- reference generation on the device (scripts/gps_utils/ref_gps_traj.py:131-218), used by the
+// closed-loop rollout and by mpcb200_solve_batch_on_path
 struct PathTable { const double *t, *X, *Y, *psi, *s; int n; };   // columns 0,4,5,3,6 of ref_gps_traj.py:106
-struct RolloutArgs {
-    const double* pose0;    // [B][3] X0, Y0, Psi0
-    const int* path_of;     // [B] index into paths[]
-    PathTable paths[3];
-    int T, track_using_time;
-    double target_vel;
-    double* log;            // [T][B][8] or null
-    double* final_state;    // [B][8] or null
-    long B;
-};
-
-MPC_DEV double py_mod(double a, double m) { double r = fmod(a, m); if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m; return r; }
-
-// vehicle_simulator.py:58-112, one 100 Hz publish period; st = X,Y,psi,vx,vy,wz,acc,df (every lane computes the same)
-MPC_DEV void plant_step(double* st, double acc_des, double df_des) {
-    const double lf = 1.152, lr = 1.693, m = 1840.0, Iz = 3477.0, Caf = 4.0703e4, Car = 6.4495e4;
-    const double deltaT = 0.01 / 10.0, PI = 3.141592653589793;
-    for (int i = 0; i < 10; i++) {
-        const double X = st[0], Y = st[1], psi = st[2], vx = st[3], vy = st[4], wz = st[5], acc = st[6], df = st[7];
-        double af = 0.0, ar = 0.0;
-        if (fabs(vx) > 1e-6) { af = df - atan2(vy + lf * wz, vx); ar = -atan2(vy - lf * wz, vx); }   // :77 uses lf (sic)
-        const double Fyf = Caf * af, Fyr = Car * ar;
-        double sdf, cdf, sps, cps;
-        mpc_sincos(df, &sdf, &cdf);
-        mpc_sincos(psi, &sps, &cps);
-        double vx_n = vx + deltaT * (acc - 1 / m * Fyf * sdf + wz * vy);
-        if (vx_n < 0.0) vx_n = 0.0;
-        double vy_n = 0.0, wz_n = 0.0;
-        if (vx_n > 1e-6) {
-            vy_n = vy + deltaT * (1.0 / m * (Fyf * cdf + Fyr) - wz * vx);
-            wz_n = wz + deltaT * (1.0 / Iz * (lf * Fyf * cdf - lr * Fyr));
-        }
-        const double psi_n = psi + deltaT * wz;
-        st[0] = X + deltaT * (vx * cps - vy * sps);
-        st[1] = Y + deltaT * (vx * sps + vy * cps);
-        st[2] = py_mod(psi_n + PI, 2.0 * PI) - PI;
-        st[3] = vx_n; st[4] = vy_n; st[5] = wz_n;
-        st[6] = 5.0 * (acc_des - acc) * deltaT + acc;
-        st[7] = 5.0 * (df_des - df) * deltaT + df;
-    }
-}
 
 MPC_DEV double np_interp(double xq, const double* xp, const double* fp, int n) {
     if (xq <= xp[0]) return fp[0];
@@ -1592,6 +1485,137 @@ MPC_DEV bool get_waypoints_warp(const PathTable& p, int N, double traj_dt, doubl
     }
     const double lx = shfl(xr, N), ly = shfl(yr, N);
     return lx == p.X[p.n - 1] && ly == p.Y[p.n - 1];
+}
+
+// Problem I/O for one warp: problem-major layouts of include/mpc_b200.h.
+struct BatchPtrs {
+    const double* state;   // [B][4]
+    const double* ref;     // [B][3][N+1]
+    const double* v_des;   // [B] or null
+    const double* u_prev;  // [B][2]
+    double* warm;          // [B][6N+4] or null
+    double* u0;            // [B][2]
+    double* cost;          // [B] or null
+    int* status;           // [B] or null
+    int* iters;            // [B] or null
+    double* traj;          // [B][6N+4] or null
+};
+
+// Optional on-device reference generation for a batch (path_of != null): the waypoints come from the
+// replicated path tables instead of io.ref (one warp per problem only, N <= 31).
+struct RefGen {
+    const int* path_of;     // [B] index into paths[], or null: references are read from io.ref
+    PathTable paths[3];
+    int track_using_time;
+    double target_vel;      // arc-length spacing of the waypoints when !track_using_time
+    double* ref_out;        // [B][3][N+1] or null: the generated waypoints (target_path of mpc_cmd_pub.jl:134-138)
+    int* stop;              // [B] or null: stop_cmd of get_waypoints
+};
+
+template <int W>
+MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, const RefGen& rg, long b, smem_t smem) {
+    TeamSolver<W> S(cfg, smem);
+    const int k = S.k, N = cfg.N;
+    const long nr = 3L * (N + 1), nt = 6L * N + 4;
+    if (W == 1 && rg.path_of) {
+        // ---- waypoints from the path table: nearest sample to (X, Y), then interpolation and heading unwrap
+        double xr, yr, pr;
+        const bool sc = get_waypoints_warp(rg.paths[rg.path_of[b]], N, cfg.dt, io.state[4 * b], io.state[4 * b + 1], io.state[4 * b + 2],
+                                           !rg.track_using_time, rg.target_vel, xr, yr, pr);
+        S.set_ref(xr, yr, pr);
+        if (rg.ref_out && k <= N) { double* ro = rg.ref_out + nr * b; ro[k] = xr; ro[(N + 1) + k] = yr; ro[2 * (N + 1) + k] = pr; }
+        if (rg.stop && k == 0) rg.stop[b] = sc ? 1 : 0;
+    } else {
+        // ---- coalesced loads: lane k takes stage k's reference sample
+        const double* rf = io.ref + nr * b;
+        S.set_ref((k <= N) ? rf[k] : 0.0, (k <= N) ? rf[(N + 1) + k] : 0.0, (k <= N) ? rf[2 * (N + 1) + k] : 0.0);
+    }
+    {   // lanes 0..6: the problem constants
+        double cv = 0.0;
+        if (k < 4) cv = io.state[4 * b + k];
+        else if (k < 6) cv = io.u_prev[2 * b + (k - 4)];
+        else if (k == 6) cv = io.v_des ? io.v_des[b] : ((W == 1 && rg.path_of && rg.target_vel > 0.0) ? rg.target_vel : 0.0);   // des_speed, mpc_cmd_pub.jl:58-62,116
+        if (k < 8) sts(smem, SO(W_CONST + k), cv);
+        S.tsync();
+    }
+    // ---- start point
+    S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;
+    if (io.warm) {
+        const double* w = io.warm + nt * b;
+        if (k <= N) { S.L.sx = w[k]; S.L.sy = w[(N + 1) + k]; S.L.sv = w[2 * (N + 1) + k]; S.L.sp = w[3 * (N + 1) + k]; }
+        if (k < N) { S.L.ud = w[4 * (N + 1) + k]; S.L.ua = w[4 * (N + 1) + N + k]; }
+    } else if (cfg.start_mode == 1) {
+        // MPCB200_START_ROLLOUT (opt-in, not a reference behaviour): hold the previous command over the
+        // horizon (projected onto the box and rate rows) and roll the model out from the measured state
+        if (k < N) { S.L.ua = S.cst(5); S.L.ud = S.cst(4); }
+        S.rollout_restore();
+    }
+    const Result r = S.solve();
+    // ---- results
+    const double a0 = S.bcast0(S.L.ua), d0 = S.bcast0(S.L.ud);
+    if (k == 0) {
+        io.u0[2 * b] = a0; io.u0[2 * b + 1] = d0;
+        if (io.cost) io.cost[b] = r.cost;
+        if (io.status) io.status[b] = r.status;
+        if (io.iters) io.iters[b] = r.iters;
+    }
+    for (int pass = 0; pass < 2; pass++) {
+        double* t = (pass == 0) ? io.traj : io.warm;
+        if (!t) continue;
+        t += nt * b;
+        if (k <= N) { t[k] = S.L.sx; t[(N + 1) + k] = S.L.sy; t[2 * (N + 1) + k] = S.L.sv; t[3 * (N + 1) + k] = S.L.sp; }
+        if (k < N) { t[4 * (N + 1) + k] = S.L.ud; t[4 * (N + 1) + N + k] = S.L.ua; }
+    }
+    S.tsync();
+}
+
+
+// ======================================================================================
+// Closed-loop rollout: one warp = one vehicle for T control steps, everything on the device.
+//   plant              scripts/vehicle_simulator.py:58-112  (10 publishes x 10 Euler sub-steps per control period)
+//   reference          scripts/gps_utils/ref_gps_traj.py:131-218 (nearest sample, np.interp, heading unwrap, stop_cmd)
+//   control step       scripts/mpc_cmd_pub.jl:86-157 (warm-started solve, command fed back, stop latch)
+// ======================================================================================
+struct RolloutArgs {
+    const double* pose0;    // [B][3] X0, Y0, Psi0
+    const int* path_of;     // [B] index into paths[]
+    PathTable paths[3];
+    int T, track_using_time;
+    double target_vel;
+    double* log;            // [T][B][8] or null
+    double* final_state;    // [B][8] or null
+    long B;
+};
+
+MPC_DEV double py_mod(double a, double m) { double r = fmod(a, m); if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m; return r; }
+
+// vehicle_simulator.py:58-112, one 100 Hz publish period; st = X,Y,psi,vx,vy,wz,acc,df (every lane computes the same)
+MPC_DEV void plant_step(double* st, double acc_des, double df_des) {
+    const double lf = 1.152, lr = 1.693, m = 1840.0, Iz = 3477.0, Caf = 4.0703e4, Car = 6.4495e4;
+    const double deltaT = 0.01 / 10.0, PI = 3.141592653589793;
+    for (int i = 0; i < 10; i++) {
+        const double X = st[0], Y = st[1], psi = st[2], vx = st[3], vy = st[4], wz = st[5], acc = st[6], df = st[7];
+        double af = 0.0, ar = 0.0;
+        if (fabs(vx) > 1e-6) { af = df - atan2(vy + lf * wz, vx); ar = -atan2(vy - lf * wz, vx); }   // :77 uses lf (sic)
+        const double Fyf = Caf * af, Fyr = Car * ar;
+        double sdf, cdf, sps, cps;
+        mpc_sincos(df, &sdf, &cdf);
+        mpc_sincos(psi, &sps, &cps);
+        double vx_n = vx + deltaT * (acc - 1 / m * Fyf * sdf + wz * vy);
+        if (vx_n < 0.0) vx_n = 0.0;
+        double vy_n = 0.0, wz_n = 0.0;
+        if (vx_n > 1e-6) {
+            vy_n = vy + deltaT * (1.0 / m * (Fyf * cdf + Fyr) - wz * vx);
+            wz_n = wz + deltaT * (1.0 / Iz * (lf * Fyf * cdf - lr * Fyr));
+        }
+        const double psi_n = psi + deltaT * wz;
+        st[0] = X + deltaT * (vx * cps - vy * sps);
+        st[1] = Y + deltaT * (vx * sps + vy * cps);
+        st[2] = py_mod(psi_n + PI, 2.0 * PI) - PI;
+        st[3] = vx_n; st[4] = vy_n; st[5] = wz_n;
+        st[6] = 5.0 * (acc_des - acc) * deltaT + acc;
+        st[7] = 5.0 * (df_des - df) * deltaT + df;
+    }
 }
 
 MPC_DEV double sel8(const double* v, int i) {   // register-friendly v[i] for a lane-dependent i

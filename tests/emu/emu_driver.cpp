@@ -60,7 +60,9 @@ struct Job { const KCfg* cfg; const BatchPtrs* io; long b; double* smem; };
 template <int W> static void lane_main(int, void* a) {
     Job* j = (Job*)a;
     TeamSolver<W>::init_work(j->smem, j->cfg->N);
-    solve_problem<W>(*j->cfg, *j->io, j->b, j->smem);
+    RefGen rg;
+    memset(&rg, 0, sizeof(rg));
+    solve_problem<W>(*j->cfg, *j->io, rg, j->b, j->smem);
 }
 
 extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, const double* ref, const double* v_des,

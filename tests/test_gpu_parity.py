@@ -231,6 +231,54 @@ def test_rollout_start_mode(capi, oracle, N, B):
     assert (g["iters"][ok] == o["iters"][ok]).mean() > 0.98 and g["iters"].mean() < 15
 
 
+@pytest.mark.parametrize("N", [8, 20])
+def test_solve_batch_on_path(capi, oracle, N):
+    """mpcb200_solve_batch_on_path: waypoints generated on the device (ref_gps_traj.py:131-218) must equal the host
+    restatement's (which is pinned bit-exactly to the reference's own output by tests/golden) and the solves must
+    equal solve_batch on those waypoints; plus distance mode, the stop flag and argument checks."""
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    s = capi.Solver(N)
+    trajs = [GPSRefTrajectory(mat_filename=p, traj_horizon=N, traj_dt=0.2) for p in (1, 2, 3)]
+    for i, g in enumerate(trajs):
+        s.set_path(i, g.trajectory)
+    B = 300
+    b = W.make_batch(B, N)                      # paths 1-3 round-robin -> ids 0..2
+    path_of = (b["path"] - 1).astype(np.int32)
+    g1 = s.solve_batch_on_path(b["state"], path_of, b["u_prev"], v_des=b["v_des"], want_ref=True)
+    st = s.stats()
+    assert st["kernel_launches"] == 1 and st["h2d_bytes"] == B * (4 * 8 + 4 + 2 * 8 + 8)
+    assert np.abs(g1["ref"] - b["ref"]).max() <= 1e-9          # time mode, heading unwrap included
+    hstop = np.zeros(B, dtype=bool)
+    for p in range(3):
+        m = path_of == p
+        _, hstop[m] = trajs[p].get_waypoints_batch(b["state"][m, 0], b["state"][m, 1], b["state"][m, 2])
+    assert np.array_equal(g1["stop"] != 0, hstop)
+    g0 = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
+    assert (g1["status"] == g0["status"]).all()
+    ok = g0["status"] == 0
+    assert np.abs(g1["u0"] - g0["u0"])[ok].max() <= 1e-7 and (g1["iters"] == g0["iters"])[ok].mean() > 0.99
+    # distance mode (track_using_time = False): waypoints at s_closest + (h+1) dt v_target
+    vt = 6.0
+    refd = np.empty((B, 3, N + 1))
+    for p in range(3):
+        m = path_of == p
+        refd[m], _ = trajs[p].get_waypoints_batch(b["state"][m, 0], b["state"][m, 1], b["state"][m, 2], v_target=vt)
+    g2 = s.solve_batch_on_path(b["state"], path_of, b["u_prev"], track_using_time=False, target_vel=vt, want_ref=True)
+    assert np.abs(g2["ref"] - refd).max() <= 1e-9
+    o2 = oracle.solve_batch(_ocfg(oracle, s), b["state"][:64], refd[:64], np.full(64, vt), b["u_prev"][:64], n_threads=8)
+    _compare({k: g2[k][:64] for k in ("u0", "cost", "status")}, o2, min_conv=0.5)
+    # the end of the path raises stop_cmd
+    g = trajs[0]
+    j = g.trajectory.shape[0] - 50
+    stt = np.array([[g.trajectory[j, 4], g.trajectory[j, 5], g.trajectory[j, 3], 5.0]])
+    g3 = s.solve_batch_on_path(stt, np.array([0]), np.zeros((1, 2)))
+    assert g3["stop"][0] == 1
+    with pytest.raises(capi.MpcB200Error):
+        capi.Solver(N).solve_batch_on_path(stt, np.array([0]), np.zeros((1, 2)))     # path not set
+    with pytest.raises(capi.MpcB200Error):
+        capi.Solver(40).solve_batch_on_path(stt, np.array([0]), np.zeros((1, 2)))    # long horizons: not supported
+
+
 @pytest.mark.parametrize("N,B,start", [(8, 48, "zero"), (20, 48, "zero"), (40, 12, "ref")])
 def test_kkt_of_cuda_solutions(capi, oracle, N, B, start):
     """Intrinsic check that does not involve the oracle's interior-point code: every Optimal point the
