@@ -55,3 +55,20 @@ def test_two_rank_gather_equals_single_rank(tmp_path, total):
         g = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
         assert np.array_equal(g["u0"], ref["u0"]) and np.array_equal(g["cost"], ref["cost"])
         assert np.array_equal(g["status"], ref["status"]) and np.array_equal(g["iters"], ref["iters"])
+
+
+def test_shard_range_properties():
+    """Contiguous, disjoint, covering, balanced to within one problem -- for any total and world size."""
+    from hypothesis import given, settings, strategies as st
+    from mkz_mpc_path_follower_b200 import sharding
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 2_000_000), st.integers(1, 64))
+    def check(total, world):
+        r = [sharding.shard_range(total, world, q) for q in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == total
+        assert all(r[q][1] == r[q + 1][0] for q in range(world - 1))
+        sizes = [hi - lo for lo, hi in r]
+        assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 0
+
+    check()

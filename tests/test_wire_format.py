@@ -53,3 +53,25 @@ def test_states_from_messages_takes_only_xypsiv():
     msgs = [wire.pack_state_est(i, i + 0.5, 0.1 * i, 2.0 * i, a=99.0, df=99.0) for i in range(4)]
     st = wire.states_from_messages(msgs)
     assert st.shape == (4, 4) and (st[:, 3] == [0, 2, 4, 6]).all() and (st[:, 1] == [0.5, 1.5, 2.5, 3.5]).all()
+
+
+def test_roundtrip_properties():
+    """Property check (hypothesis): pack -> unpack is the identity for arbitrary finite payloads and headers."""
+    from hypothesis import given, settings, strategies as st
+    f = st.floats(allow_nan=False, allow_infinity=False, width=64)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(f, min_size=8, max_size=8), st.integers(0, 2**32 - 1), st.integers(0, 2**32 - 1), st.text(max_size=12))
+    def state(vals, seq, secs, frame):
+        d = wire.unpack_state_est(wire.pack_state_est(*vals, seq=seq, secs=secs, nsecs=7, frame_id=frame))
+        assert [d[k] for k in wire.STATE_EST_FIELDS] == vals
+        assert d["header"] == {"seq": seq, "secs": secs, "nsecs": 7, "frame_id": frame}
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(0, 40).flatmap(lambda n: st.tuples(*[st.lists(f, min_size=n, max_size=n)] * 3)))
+    def path(arrs):
+        d = wire.unpack_mpc_path(wire.pack_mpc_path(*arrs))
+        assert all((d[k] == np.array(a)).all() for k, a in zip(("xs", "ys", "psis"), arrs))
+
+    state()
+    path()
