@@ -1587,6 +1587,29 @@ struct RolloutArgs {
     long B;
 };
 
+// atan2(y, x) for x > 0 and sincos for small arguments: the plant's slip angles and steering angle are
+// small, where a short Taylor sum is accurate to the last bits (truncation < 1e-21 for |y/x| <= 1/8 and
+// < 1e-24 for |x| <= 0.6) and several times shorter than the general routines, which stay as fall-back
+MPC_DEV double atan2_posx(double y, double x) {
+    const double t = y / x;
+    if (!(fabs(t) <= 0.125)) return atan2(y, x);
+    const double u = t * t;
+    double p = 1.0 / 21.0;
+    p = 1.0 / 19.0 - u * p; p = 1.0 / 17.0 - u * p; p = 1.0 / 15.0 - u * p; p = 1.0 / 13.0 - u * p; p = 1.0 / 11.0 - u * p;
+    p = 1.0 / 9.0 - u * p; p = 1.0 / 7.0 - u * p; p = 1.0 / 5.0 - u * p; p = 1.0 / 3.0 - u * p; p = 1.0 - u * p;
+    return t * p;
+}
+MPC_DEV void sincos_small(double x, double* s, double* c) {
+    if (!(fabs(x) <= 0.6)) { mpc_sincos(x, s, c); return; }
+    const double u = x * x;
+    double ps = -1.0 / 6.0 + u * (1.0 / 120.0 + u * (-1.0 / 5040.0 + u * (1.0 / 362880.0 + u * (-1.0 / 39916800.0 + u * (1.0 / 6227020800.0 +
+                u * (-1.0 / 1307674368000.0 + u * (1.0 / 355687428096000.0 + u * (-1.0 / 121645100408832000.0))))))));
+    double pc = -0.5 + u * (1.0 / 24.0 + u * (-1.0 / 720.0 + u * (1.0 / 40320.0 + u * (-1.0 / 3628800.0 + u * (1.0 / 479001600.0 +
+                u * (-1.0 / 87178291200.0 + u * (1.0 / 20922789888000.0 + u * (-1.0 / 6402373705728000.0 + u * (1.0 / 2432902008176640000.0)))))))));
+    *s = x + x * (u * ps);
+    *c = 1.0 + u * pc;
+}
+
 MPC_DEV double py_mod(double a, double m) { double r = fmod(a, m); if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m; return r; }
 
 // vehicle_simulator.py:58-112, one 100 Hz publish period; st = X,Y,psi,vx,vy,wz,acc,df (every lane computes the same)
@@ -1596,10 +1619,10 @@ MPC_DEV void plant_step(double* st, double acc_des, double df_des) {
     for (int i = 0; i < 10; i++) {
         const double X = st[0], Y = st[1], psi = st[2], vx = st[3], vy = st[4], wz = st[5], acc = st[6], df = st[7];
         double af = 0.0, ar = 0.0;
-        if (fabs(vx) > 1e-6) { af = df - atan2(vy + lf * wz, vx); ar = -atan2(vy - lf * wz, vx); }   // :77 uses lf (sic)
+        if (vx > 1e-6) { af = df - atan2_posx(vy + lf * wz, vx); ar = -atan2_posx(vy - lf * wz, vx); }   // :77 uses lf (sic); vx >= 0 (clamped below)
         const double Fyf = Caf * af, Fyr = Car * ar;
         double sdf, cdf, sps, cps;
-        mpc_sincos(df, &sdf, &cdf);
+        sincos_small(df, &sdf, &cdf);
         mpc_sincos(psi, &sps, &cps);
         double vx_n = vx + deltaT * (acc - 1 / m * Fyf * sdf + wz * vy);
         if (vx_n < 0.0) vx_n = 0.0;
@@ -1611,7 +1634,8 @@ MPC_DEV void plant_step(double* st, double acc_des, double df_des) {
         const double psi_n = psi + deltaT * wz;
         st[0] = X + deltaT * (vx * cps - vy * sps);
         st[1] = Y + deltaT * (vx * sps + vy * cps);
-        st[2] = py_mod(psi_n + PI, 2.0 * PI) - PI;
+        const double pw = psi_n + PI;   // np.mod(a, m) is a itself for 0 <= a < m: fmod only when the yaw really wraps
+        st[2] = ((pw >= 0.0 && pw < 2.0 * PI) ? pw : py_mod(pw, 2.0 * PI)) - PI;
         st[3] = vx_n; st[4] = vy_n; st[5] = wz_n;
         st[6] = 5.0 * (acc_des - acc) * deltaT + acc;
         st[7] = 5.0 * (df_des - df) * deltaT + df;
