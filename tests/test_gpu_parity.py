@@ -302,6 +302,35 @@ def test_kkt_of_cuda_solutions(capi, oracle, N, B, start):
         assert sign <= 1e-6, (j, sign)
 
 
+def test_cuda_solution_is_what_scipy_slsqp_finds(capi, oracle):
+    """Independent solver (scipy SLSQP, analytic derivatives of the reference NLP), started near the CUDA solver's
+    point: it must stay there.  Does not involve the oracle's interior-point code."""
+    import ctypes as C
+    from scipy.optimize import minimize
+    from test_oracle_solver import _nlp, _p
+    N = 8
+    s = capi.Solver(N)
+    ocfg = _ocfg(oracle, s)
+    b = W.make_batch(6, N)
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    rng = np.random.default_rng(0)
+    checked = 0
+    for j in np.nonzero(g["status"] == 0)[0]:
+        f, gr, c, d, jac, lo, hi, dlim = _nlp(oracle, ocfg, b["state"][j], b["ref"][j], 1.0, b["u_prev"][j])
+        z0 = np.empty(6 * N + 4)
+        oracle.lib().mpc_oracle_traj_to_z(C.byref(ocfg), _p(np.ascontiguousarray(g["traj"][j])), _p(z0))
+        cons = [{"type": "eq", "fun": c, "jac": lambda z: jac(z)[0]},
+                {"type": "ineq", "fun": lambda z: dlim - d(z), "jac": lambda z: -jac(z)[1]},
+                {"type": "ineq", "fun": lambda z: dlim + d(z), "jac": lambda z: jac(z)[1]}]
+        res = minimize(f, z0 + 1e-2 * rng.normal(size=z0.size), jac=gr, bounds=list(zip(lo, hi)), constraints=cons,
+                       method="SLSQP", options={"ftol": 1e-15, "maxiter": 500})
+        assert np.abs(c(res.x)).max() < 1e-7
+        assert abs(res.fun - g["cost"][j]) <= 1e-6 * max(1.0, abs(g["cost"][j])), (j, res.fun, g["cost"][j])
+        assert np.abs(res.x[4:6] - g["u0"][j]).max() < 1e-4, (j, res.x[4:6], g["u0"][j])
+        checked += 1
+    assert checked >= 4
+
+
 def test_large_batch_oracle_parity(capi, oracle):
     """16,384 problems of configs[2] (a quarter of the bench batch) against the oracle, every one of them.  The
     two implementations round differently (Riccati vs dense LDL^T), and from the all-zero start a handful of
