@@ -220,7 +220,7 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
         cudaError_t e2 = (expr);                                                          \
         if (e2 != cudaSuccess) {                                                          \
             fail(nullptr, MPCB200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e2));        \
-            delete h;                                                                     \
+            mpcb200_destroy(h);   /* releases whatever was created so far */              \
             return MPCB200_ECUDA;                                                         \
         }                                                                                 \
     } while (0)
