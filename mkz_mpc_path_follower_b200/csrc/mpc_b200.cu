@@ -120,6 +120,9 @@ struct mpcb200_handle {
     int* d_roles = nullptr;   /* lane roles of the Riccati recursion for this horizon (riccati_roles) */
     DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
     DevBuf d_path[3], d_pose, d_pathof, d_log, d_final, d_stop;
+    DevBuf d_stage;               /* small batches: one contiguous device buffer, one copy each way */
+    void* h_stage = nullptr;      /* its pinned host mirror */
+    size_t h_stage_cap = 0;
     int path_n[3] = {0, 0, 0};
     int rollout_blocks_per_sm = 0;
     mpcb200_stats stats;
@@ -267,10 +270,11 @@ int mpcb200_destroy(mpcb200_handle* h) {
     if (!h) return MPCB200_EINVAL;
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj,
-                      &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop};
+                      &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop, &h->d_stage};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_roles) cudaFree(h->d_roles);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -291,19 +295,20 @@ int mpcb200_set_stream(mpcb200_handle* h, void* s) {
     return MPCB200_OK;
 }
 
-static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const RefGen& rg) {
-    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), h->stream));
+static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const RefGen& rg, unsigned long long* zeroed_counter = nullptr) {
+    unsigned long long* counter = zeroed_counter ? zeroed_counter : h->d_counter;
+    if (!zeroed_counter) CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), h->stream));
     const int teams_per_block = (h->team_warps == 1) ? WARPS_PER_BLOCK : 1;
     long long blocks_needed = (B + teams_per_block - 1) / teams_per_block;
     long long max_blocks = (long long)h->num_sms * h->blocks_per_sm;
     int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
     if (grid < 1) grid = 1;
     if (h->team_warps == 1)
-        mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, h->d_counter);
+        mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     else if (h->team_warps == 2)
-        mpc_solve_long_kernel<2><<<grid, 64, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, h->d_counter);
+        mpc_solve_long_kernel<2><<<grid, 64, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     else
-        mpc_solve_long_kernel<3><<<grid, 96, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, h->d_counter);
+        mpc_solve_long_kernel<3><<<grid, 96, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     CUDA_TRY(h, cudaGetLastError());
     h->stats.kernel_launches += 1;
     return 0;
@@ -317,6 +322,63 @@ static void fill_paths(const mpcb200_handle* h, PathTable* paths) {
         paths[i].n = n;
         if (n) { paths[i].t = base; paths[i].X = base + n; paths[i].Y = base + 2 * (size_t)n; paths[i].psi = base + 3 * (size_t)n; paths[i].s = base + 4 * (size_t)n; }
     }
+}
+
+/* Host pointers, small batch (the control loop's batch of one): latency is the driver calls, not the bytes.  All
+ * inputs are packed into one pinned buffer (with the zeroed problem counter in front) and go over in ONE copy, all
+ * outputs come back in ONE copy: 7 driver calls instead of ~16. */
+static const int64_t SMALL_BATCH = 64;
+static int solve_small_host(mpcb200_handle* h, int64_t B, const double* state, const double* ref, const double* v_des,
+                            const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
+                            double* traj) {
+    const int N = h->cfg.N;
+    const size_t nt = 6 * (size_t)N + 4, nr = 3 * ((size_t)N + 1);
+    /* layout in doubles: [counter, pad] state ref uprev vdes | warm | u0 cost traj status/iters(int32 pairs) */
+    const size_t o_state = 2, o_ref = o_state + 4 * B, o_uprev = o_ref + nr * B, o_vdes = o_uprev + 2 * B, o_warm = o_vdes + B;
+    const size_t o_u0 = o_warm + nt * B, o_cost = o_u0 + 2 * B, o_traj = o_cost + B, o_stat = o_traj + nt * B, o_iter = o_stat + (B + 1) / 2;
+    const size_t total = o_iter + (B + 1) / 2;
+    const size_t bytes = total * sizeof(double);
+    int rc;
+    if ((rc = ensure(h, h->d_stage, bytes))) return rc;
+    if (bytes > h->h_stage_cap) {
+        if (h->h_stage) CUDA_TRY(h, cudaFreeHost(h->h_stage));
+        h->h_stage = nullptr; h->h_stage_cap = 0;
+        CUDA_TRY(h, cudaHostAlloc(&h->h_stage, bytes + bytes / 4, cudaHostAllocDefault));
+        h->h_stage_cap = bytes + bytes / 4;
+    }
+    double* hs = (double*)h->h_stage;
+    double* ds = (double*)h->d_stage.p;
+    hs[0] = 0.0; hs[1] = 0.0;   /* the problem counter (all-zero bits) */
+    memcpy(hs + o_state, state, 4 * B * sizeof(double));
+    memcpy(hs + o_ref, ref, nr * B * sizeof(double));
+    memcpy(hs + o_uprev, u_prev, 2 * B * sizeof(double));
+    if (v_des) memcpy(hs + o_vdes, v_des, B * sizeof(double));
+    if (warm) memcpy(hs + o_warm, warm, nt * B * sizeof(double));
+    const size_t in_doubles = warm ? o_u0 : o_warm;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(ds, hs, in_doubles * sizeof(double), cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += in_doubles * sizeof(double);
+    BatchPtrs io{ds + o_state, ds + o_ref, v_des ? ds + o_vdes : nullptr, ds + o_uprev, warm ? ds + o_warm : nullptr, ds + o_u0,
+                 ds + o_cost, (int*)(ds + o_stat), (int*)(ds + o_iter), traj ? ds + o_traj : nullptr};
+    RefGen rg;
+    memset(&rg, 0, sizeof(rg));
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    if ((rc = launch_solve(h, B, io, rg, (unsigned long long*)ds))) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    const size_t out_from = warm ? o_warm : o_u0;
+    CUDA_TRY(h, cudaMemcpyAsync(hs + out_from, ds + out_from, (total - out_from) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    h->stats.d2h_bytes += (total - out_from) * sizeof(double);
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    memcpy(u0, hs + o_u0, 2 * B * sizeof(double));
+    if (cost) memcpy(cost, hs + o_cost, B * sizeof(double));
+    if (status) memcpy(status, hs + o_stat, B * sizeof(int32_t));
+    if (iters) memcpy(iters, hs + o_iter, B * sizeof(int32_t));
+    if (traj) memcpy(traj, hs + o_traj, nt * B * sizeof(double));
+    if (warm) memcpy(warm, hs + o_warm, nt * B * sizeof(double));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return MPCB200_OK;
 }
 
 /* common body of mpcb200_solve_batch (ref given) and mpcb200_solve_batch_on_path (path_of given) */
@@ -354,6 +416,7 @@ static int solve_batch_impl(mpcb200_handle* h, const char* who, int64_t B, const
         rg.path_of = path_of; rg.ref_out = ref_out; rg.stop = stop;
         return launch_solve(h, B, io, rg);
     }
+    if (!on_path && B <= SMALL_BATCH) return solve_small_host(h, B, state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj);
     /* host pointers: stage through the handle's device buffers */
     const size_t bs = B * 4 * sizeof(double), br = B * nr * sizeof(double), bu = B * 2 * sizeof(double), bt = B * nt * sizeof(double);
     int rc;
