@@ -19,7 +19,6 @@ for mode in ("warm", "cold"):
     wall, kern, its = [], [], []
     for i in range(300):
         j = i % 64
-        w = g["traj"][(j + 1) % 64:(j + 1) % 64 + 1].copy() if mode == "warm" else None
         w = g["traj"][j:j + 1].copy() if mode == "warm" else None
         t0 = time.perf_counter()
         r = s.solve_batch(b["state"][j:j + 1], b["ref"][j:j + 1], b["u_prev"][j:j + 1], v_des=b["v_des"][j:j + 1], warm=w)
