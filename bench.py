@@ -37,6 +37,9 @@ def parse():
     ap.add_argument("--horizon", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--x0", dest="start", default="zero", choices=["zero", "rollout"],
+                    help="start point: zero = the reference's start=0.0 (the metric); rollout = MPCB200_START_ROLLOUT "
+                         "(opt-in; what the horizon sweep of configs[4] uses at N = 40 / 80)")
     return ap.parse_args()
 
 
@@ -86,15 +89,16 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": n}
 
 
-def cpu_baseline(N, sample, threads, start_b0=0):
+def cpu_baseline(N, sample, threads, start_b0=0, start="zero"):
     """The oracle (restated CPU interior point, NOT Ipopt) on a bounded sample of the same workload."""
     from oracle import oracle as O
     from mkz_mpc_path_follower_b200 import workload
     O.build()
     b = workload.make_batch(sample, N, b0=start_b0)
     cfg = O.default_cfg(N)
+    warm = O.rollout_start(cfg, b["state"], b["u_prev"]) if start == "rollout" else None
     t0 = time.perf_counter()
-    r = O.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=threads)
+    r = O.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], warm=warm, n_threads=threads)
     dt = time.perf_counter() - t0
     conv = int((r["status"] == 0).sum())
     return conv / dt, dt, conv, r
@@ -110,10 +114,10 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or max(256, 64 * cores)
     for _ in range(min(args.warmup, 1)):
-        cpu_baseline(N, min(sample, 256), cores)
+        cpu_baseline(N, min(sample, 256), cores, start=args.start)
     t_tot, conv_tot = 0.0, 0
     for s in range(args.steps):
-        v, dt, conv, _ = cpu_baseline(N, sample, cores, start_b0=s * sample)
+        v, dt, conv, _ = cpu_baseline(N, sample, cores, start_b0=s * sample, start=args.start)
         t_tot += dt
         conv_tot += conv
     val = conv_tot / t_tot
@@ -154,7 +158,7 @@ def main():
 
     # ---- synthetic batch: this rank's contiguous slice of the problem stream
     b = workload.make_batch(B, N, b0=rank * B)
-    solver = capi.Solver(N, device=local)
+    solver = capi.Solver(N, device=local, start_mode=capi.START_ROLLOUT if args.start == "rollout" else capi.START_ZERO)
     stream = torch.cuda.Stream(device=dev)  # a real (non-NULL) stream shared by torch and the library
     torch.cuda.set_stream(stream)
     solver.set_stream(stream.cuda_stream)
@@ -207,6 +211,11 @@ def main():
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     total_ms = float(tm.item())
+    km = torch.zeros(world, dtype=torch.float64, device=dev)
+    km[rank] = float(np.mean(kern_ms))
+    if world > 1:
+        dist.all_reduce(km, op=dist.ReduceOp.SUM)
+    kernel_ms_per_rank = [round(float(v), 3) for v in km.tolist()]
 
     status = d_status.cpu().numpy(); iters = d_iters.cpu().numpy()
     conv_local = int((status == 0).sum())
@@ -239,26 +248,28 @@ def main():
 
     # ---- the same with the waypoints generated on the device (mpcb200_solve_batch_on_path): the host sends the
     # state, the path id and the previous command only (60 B/problem instead of 560)
-    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
-    for i, pth in enumerate((1, 2, 3)):
-        solver.set_path(i, GPSRefTrajectory(mat_filename=pth, traj_horizon=N, traj_dt=0.2).trajectory)
-    h_pathof = torch.from_numpy((b["path"] - 1).astype(np.int32)).pin_memory().numpy()
-    for _ in range(2):
-        solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        r2 = solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
-        st2 = solver.stats()
-    torch.cuda.synchronize()
-    tp = torch.tensor([time.perf_counter() - w0, float((r2["status"] == 0).sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        tmax = tp[0:1].clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        csum = tp[1:2].clone(); dist.all_reduce(csum, op=dist.ReduceOp.SUM)
-        tp = torch.cat((tmax, csum))
-    e2e_on_path = {"value": float(tp[1].item()) * args.steps / float(tp[0].item()), "unit": "solves/s",
-                   "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
-                   "what": "mpcb200_solve_batch_on_path: reference waypoints generated on the device"}
+    e2e_on_path = None
+    if N <= 31:
+        from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+        for i, pth in enumerate((1, 2, 3)):
+            solver.set_path(i, GPSRefTrajectory(mat_filename=pth, traj_horizon=N, traj_dt=0.2).trajectory)
+        h_pathof = torch.from_numpy((b["path"] - 1).astype(np.int32)).pin_memory().numpy()
+        for _ in range(2):
+            solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            r2 = solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
+            st2 = solver.stats()
+        torch.cuda.synchronize()
+        tp = torch.tensor([time.perf_counter() - w0, float((r2["status"] == 0).sum())], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = tp[0:1].clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            csum = tp[1:2].clone(); dist.all_reduce(csum, op=dist.ReduceOp.SUM)
+            tp = torch.cat((tmax, csum))
+        e2e_on_path = {"value": float(tp[1].item()) * args.steps / float(tp[0].item()), "unit": "solves/s",
+                       "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
+                       "what": "mpcb200_solve_batch_on_path: reference waypoints generated on the device"}
 
     if rank != 0:
         if world > 1:
@@ -279,7 +290,7 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     traffic = None
     tr_file = os.path.join(ROOT, "profiles", "dram_traffic.json")
-    if os.path.exists(tr_file):
+    if os.path.exists(tr_file) and N == 20 and B == 65536:   # the capture is of this configuration
         try:
             traffic = json.load(open(tr_file)).get("bytes_per_launch")
         except Exception:
@@ -289,7 +300,7 @@ def main():
         "traffic": traffic,
         "peak_source": "FP64 FMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry)",
         "flops_model": "sum_p iters_p * (1235 + 310) * N, SURVEY.md 8(d)",
-        "kernel": "mpc_solve_kernel", "kernel_ms": k_ms,
+        "kernel": "mpc_solve_kernel", "kernel_ms": k_ms, "kernel_ms_per_rank": kernel_ms_per_rank,
         "hbm": {"achieved": io_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": io_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback of B200_PROFILING.md",
@@ -299,7 +310,7 @@ def main():
     # ---- CPU baseline beside it: oracle on a bounded sample, all cores
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or max(256, 48 * cores)
-    cpu_v, cpu_dt, cpu_conv, cpu_r = cpu_baseline(N, sample, cores)
+    cpu_v, cpu_dt, cpu_conv, cpu_r = cpu_baseline(N, sample, cores, start=args.start)
     ok = (cpu_r["status"] == 0) & (status[:sample] == 0) if rank == 0 else None
     u0 = d_u0.cpu().numpy()
     parity = {
@@ -308,14 +319,15 @@ def main():
     }
 
     line = {
-        "metric": "converged MPC solves/sec at batch 64K, N=20", "value": value, "unit": "solves/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "metric": "converged MPC solves/sec at batch 64K, N=20" if (N == 20 and B == 65536) else "converged MPC solves/sec at batch %d per GPU, N=%d" % (B, N),
+        "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2]: %d cold-start (start=0.0) solves per GPU, N=%d, paths 1-3 round-robin, "
-                               "perturbed states (SURVEY 8d)" % (B, N),
+        "config": {"workload": "configs[%d]: %d solves per GPU from the %s, N=%d, paths 1-3 round-robin, "
+                               "perturbed states (SURVEY 8d)" % (2 if (N == 20 and args.start == "zero") else 4, B,
+                                                                 "all-zero start (start=0.0)" if args.start == "zero" else "rollout start (opt-in)", N),
                    "batch_per_gpu": B, "horizon": N, "l2": "256 MiB flush between steps (inputs 36 MB < L2)",
-                   "start": "zero", "max_iter": int(solver.cfg.max_iter)},
+                   "start": args.start, "max_iter": int(solver.cfg.max_iter)},
         "converged_frac": conv_total / (world * B), "mean_iters": iters_total / (world * B),
         "roofline": roofline,
         "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port",

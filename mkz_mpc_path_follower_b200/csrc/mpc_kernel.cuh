@@ -31,6 +31,9 @@
 // sample live in per-thread shared-memory fields (LF_*): 168 registers, 12 warps per SM at N = 20.
 #pragma once
 #include "warp_prims.cuh"
+#ifdef MPC_TRACE
+#include <cstdio>
+#endif
 
 namespace mpcb200 {
 
@@ -1007,7 +1010,7 @@ struct TeamSolver {
         enum { PH_INIT = 0, PH_EVAL0, PH_LS, PH_BEGIN, PH_PD, PH_RESOLVE_EVAL, PH_RESOLVE, PH_TRIAL, PH_SOC, PH_RESTO };
         int phase = PH_INIT;
         bool do_solve = false, do_eval = false, eval_ftb = false;
-        bool resto_check = false;
+        bool resto_check = false, cur_acceptable = false, had_acceptable = false;
         int n_resto = 0;
         int req = 0;
         double ev_alpha = 0.0;
@@ -1106,7 +1109,9 @@ struct TeamSolver {
                     }
                     alpha_min *= K_ALPHA_MIN_FRAC;
                     alpha *= 0.5; nsteps++;
-                    if (!(alpha > alpha_min)) {   // Ipopt would enter the restoration phase
+                    if (!(alpha > alpha_min)) {   // Ipopt would enter the restoration phase ...
+                        if (cur_acceptable) { ret = 1; break; }   // ... unless the point is acceptable: Solved_To_Acceptable_Level
+                        if (cur_theta <= 1e-2 * c.tol) { ret = had_acceptable ? 1 : -2; break; }   // ... or almost feasible (see oracle)
                         if (n_resto < K_MAX_RESTO) { phase = PH_RESTO; continue; }
                         ret = -2; break;
                     }
@@ -1182,12 +1187,15 @@ struct TeamSolver {
                 iter++;
                 phase = PH_BEGIN;
             }
+#ifdef MPC_TRACE
+            if (phase == PH_RESTO && k == 0) printf("   RESTO at it %d: alpha %.3e gBd %.3e theta %.3e acceptable %d nsteps %d\n", iter, alpha, gBd, cur_theta, (int)cur_acceptable, nsteps);
+#endif
             if (phase == PH_RESTO) {
                 // The line search failed where Ipopt would enter its restoration phase.  That phase is
                 // not restated; instead the iterate is replaced by the rollout of its own (projected)
                 // inputs, which satisfies the equality rows by construction, and the iteration is
                 // re-initialised there with mu and the filter kept (oracle: ipm_rollout_restore).
-                n_resto++;
+                n_resto++; had_acceptable = false;
                 if (nfilt < NFILT_MAX) {   // PrepareRestoPhaseStart: the point that is left enters the filter
                     if (k == nfilt) { f_phi = phi - K_GAMMA_PHI * cur_theta; f_theta = (1.0 - K_GAMMA_THETA) * cur_theta; }
                     nfilt++;
@@ -1319,15 +1327,19 @@ struct TeamSolver {
                     treduce<OP_MAX, 2>(r2);
                     e0 = r2[0]; em = r2[1];
                 }
+#ifdef MPC_TRACE
+                if (k == 0) printf("it %3d mu %.2e e0 %.3e em %.3e theta %.2e f %.10e dcv %.2e cm0 %.2e nfilt %d\n", iter, mu, e0, em, cur_theta, cur_f, dcv, cm0, nfilt);
+#endif
                 // ---- convergence (OptimalityErrorConvergenceCheck)
                 if (e0 <= dmax_(K_ACCEPT_TOL, c.tol)) {   // the unscaled checks need three more reductions: only near the end
                     double r3[3] = {di, cv, cm0};
                     treduce<OP_MAX, 3>(r3);
                     const double du = r3[0] / sigma, cvm = r3[1], mc = r3[2] / sigma;
                     if (e0 <= c.tol && du <= 1.0 && cvm <= 1e-4 && mc <= 1e-4) { ret = 0; break; }
-                    if (e0 <= K_ACCEPT_TOL && du <= 1e10 && cvm <= 1e-2 && mc <= 1e-2) { if (++accept_count >= K_ACCEPT_ITER) { ret = 1; break; } }
+                    cur_acceptable = (e0 <= K_ACCEPT_TOL && du <= 1e10 && cvm <= 1e-2 && mc <= 1e-2);
+                    if (cur_acceptable) { had_acceptable = true; if (++accept_count >= K_ACCEPT_ITER) { ret = 1; break; } }
                     else accept_count = 0;
-                } else accept_count = 0;
+                } else { accept_count = 0; cur_acceptable = false; }
                 if (iter >= c.max_iter) { ret = -1; break; }
                 {
                     const double xm = dmax_(dmax_(fabs(L.sx), fabs(L.sy)), dmax_(fabs(L.sp), fabs(L.sv)));
@@ -1370,6 +1382,8 @@ struct TeamSolver {
                         if (cur_theta <= theta_min) alpha_min = dmin_(alpha_min, K_DELTA * Rft);
                     }
                     if (!(alpha > alpha_min * K_ALPHA_MIN_FRAC)) {
+                        if (cur_acceptable) { ret = 1; break; }
+                        if (cur_theta <= 1e-2 * c.tol) { ret = had_acceptable ? 1 : -2; break; }
                         if (n_resto < K_MAX_RESTO) { phase = PH_RESTO; continue; }
                         ret = -2; break;
                     }

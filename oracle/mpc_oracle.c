@@ -756,7 +756,7 @@ static int ipm_run(ipm_t* P, const double* warm, int* iters_out, mpc_oracle_diag
     const double mu_min = dmin(cfg->tol, 1e-4) / (IPM_KAPPA_EPS + 1.0);
     double dw_last = 0.0, theta_max = -1.0, theta_min = -1.0;
     filt_entry filt[IPM_FILTER_MAX]; int nfilt = 0;
-    int accept_count = 0, ret = -1, tiny_last = 0, n_resto = 0;
+    int accept_count = 0, ret = -1, tiny_last = 0, n_resto = 0, cur_acceptable = 0, had_acceptable = 0;
     const int use_resto = getenv("MPC_ORACLE_NO_RESTO") == NULL;
     double *Sx = (double*)xcalloc(n, sizeof(double)), *Ss = (double*)xcalloc(md, sizeof(double));
     double *rx = (double*)xcalloc(n, sizeof(double)), *rs = (double*)xcalloc(md, sizeof(double));
@@ -821,7 +821,9 @@ static int ipm_run(ipm_t* P, const double* warm, int* iters_out, mpc_oracle_diag
             double du = e0.dual_inf / P->sigma_f, cu = e0.constr_viol, mu_c = e0.compl_inf / P->sigma_f;
             dg->dual_inf = du; dg->constr_viol = cu; dg->compl_inf = mu_c; dg->mu_final = mu;
             if (E0 <= cfg->tol && du <= 1.0 && cu <= 1e-4 && mu_c <= 1e-4) { ret = 0; break; }
-            if (E0 <= IPM_ACCEPT_TOL && du <= 1e10 && cu <= 1e-2 && mu_c <= 1e-2) {
+            cur_acceptable = (E0 <= IPM_ACCEPT_TOL && du <= 1e10 && cu <= 1e-2 && mu_c <= 1e-2);
+            if (cur_acceptable) {
+                had_acceptable = 1;   /* BacktrackingLineSearch::StoreAcceptablePoint */
                 if (++accept_count >= IPM_ACCEPT_ITER) { ret = 1; break; }
             } else accept_count = 0;
         }
@@ -1009,11 +1011,20 @@ static int ipm_run(ipm_t* P, const double* warm, int* iters_out, mpc_oracle_diag
                 fprintf(stderr, "LS FAIL it=%d amax=%.3e amin=%.3e theta=%.3e gBd=%.3e limiting var stage %d comp %d x=%.6e dx=%.3e nsteps=%d\n",
                         iter, alpha_max, alpha_min, theta, gBd, jb / 6, jb % 6, jb >= 0 ? P->x[jb] : 0.0, jb >= 0 ? P->dx[jb] : 0.0, nsteps);
             }
+            /* BacktrackingLineSearch: "Restoration phase called at acceptable point" -> Solved_To_Acceptable_Level.
+             * Near the optimum the line search fails on rounding alone; the point is then returned, not restored. */
+            if (!accepted && cur_acceptable) { ret = 1; break; }
+            /* "Restoration phase is called at point that is almost feasible": theta <= 1e-2 tol.  Ipopt then goes back
+             * to the last acceptable point if it stored one (Solved_To_Acceptable_Level), else gives up
+             * (Restoration_Failed).  The stored point is not kept here: with theta at rounding level the iterate has
+             * not left it (the line search has been failing on rounding), so the current point is returned. */
+            if (!accepted && theta <= 1e-2 * cfg->tol) { ret = had_acceptable ? 1 : -2; break; }
             if (!accepted && use_resto && n_resto < IPM_MAX_RESTO) {
                 /* restoration: filter augmented with the point that is left (PrepareRestoPhaseStart) */
                 double th_r, ph_r; int ok;
                 n_resto++;
                 if (nfilt < IPM_FILTER_MAX) { filt[nfilt].phi = phi - IPM_GAMMA_PHI * theta; filt[nfilt].theta = (1.0 - IPM_GAMMA_THETA) * theta; nfilt++; }
+                had_acceptable = 0;
                 ipm_rollout_restore(P);
                 ipm_init_point(P, rx, rs, rc, rd);
                 th_r = ipm_theta(P, P->x, P->s, P->ct, P->dt_);
