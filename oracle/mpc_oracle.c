@@ -54,6 +54,16 @@ void mpc_oracle_default_cfg(mpc_oracle_cfg* c, int N) {
     c->w[4] = 100.0; c->w[5] = 1000.0; c->w[6] = 0.0; c->w[7] = 0.0;
     c->tol = 1e-8;
     c->max_iter = 200;
+    c->model = 0;
+    c->kpoly[0] = c->kpoly[1] = c->kpoly[2] = c->kpoly[3] = 0.0;
+}
+
+/* MKZMPCPathFollowerFrenet.jl:28-59: same vehicle, horizon, bounds and rate limits; cost C_ey = 9,
+ * C_epsi = 10, C_ev = 0.5, C_dacc = 100, C_ddf = 1000, C_acc = C_df = 0; nothing on s. */
+void mpc_oracle_default_cfg_frenet(mpc_oracle_cfg* c, int N) {
+    mpc_oracle_default_cfg(c, N);
+    c->model = 1;
+    c->w[0] = 0.0; c->w[1] = 9.0; c->w[2] = 10.0; c->w[3] = 0.5;
 }
 
 int mpc_oracle_nvar(const mpc_oracle_cfg* c) { return NSTG * c->N + NX; }
@@ -135,9 +145,79 @@ typedef struct {
     double Bd[4];     /* d f / d df ; d f / d acc = (0,0,0,dt) */
     /* second derivatives of f_x, f_y, f_psi over (psi, v, df): pp, pv, pd, vd, dd  (vv = 0) */
     double hx[5], hy[5], hp[5];
+    /* Frenet model: full second derivatives of f_s, f_ey, f_epsi over (s, ey, epsi, v, df) */
+    double hf[3][5][5];
 } stage_eval;
 
+/* MKZMPCPathFollowerFrenet.jl:111-123.  g = ds/dt = v cos(epsi + beta) / (1 - ey K(s)) */
+static void stage_map_frenet(const mpc_oracle_cfg* c, const double* st, double acc, double df, stage_eval* e, int order) {
+    const double dt = c->dt, Lb = c->L_b, r = c->L_b / (c->L_a + c->L_b);
+    const double s = st[0], ey = st[1], ep = st[2], v = st[3];
+    const double K = ((c->kpoly[0] * s + c->kpoly[1]) * s + c->kpoly[2]) * s + c->kpoly[3];   /* :111 */
+    const double bta = atan(r * tan(df));                                                    /* :112 */
+    const double C = cos(ep + bta), S = sin(ep + bta), sb = sin(bta), cb = cos(bta);
+    const double q = 1.0 / (1.0 - ey * K);
+    const double g = v * C * q;                                                              /* :113 */
+    e->f[0] = s + dt * g;                            /* :117 */
+    e->f[1] = ey + dt * (v * S);                     /* :118 */
+    e->f[2] = ep + dt * (v / Lb * sb - g * K);       /* :119 */
+    e->f[3] = v + dt * acc;                          /* :120 */
+    if (order < 1) return;
+    {
+        const double K1 = (3.0 * c->kpoly[0] * s + 2.0 * c->kpoly[1]) * s + c->kpoly[2];
+        const double K2 = 6.0 * c->kpoly[0] * s + 2.0 * c->kpoly[1];
+        const double cd = cos(df), sd = sin(df);
+        const double D = cd * cd + r * r * sd * sd;
+        const double b1 = r / D, b2 = r * (1.0 - r * r) * (2.0 * sd * cd) / (D * D);
+        const double q2 = q * q, q3 = q2 * q;
+        const double qs = ey * K1 * q2, qe = K * q2;
+        /* gradient of g over (s, ey, epsi, v, df) */
+        const double G[5] = {v * C * qs, v * C * qe, -v * S * q, C * q, -v * S * b1 * q};
+        int i, j;
+        for (i = 0; i < 4; i++) for (j = 0; j < 4; j++) e->A[i][j] = (i == j) ? 1.0 : 0.0;
+        for (j = 0; j < 4; j++) e->A[0][j] += dt * G[j];
+        e->Bd[0] = dt * G[4];
+        e->A[1][2] += dt * v * C; e->A[1][3] += dt * S; e->Bd[1] = dt * v * C * b1;
+        /* h = g K:  h_s = g_s K + g K', h_x = g_x K */
+        e->A[2][0] += -dt * (G[0] * K + g * K1);
+        e->A[2][1] += -dt * G[1] * K;
+        e->A[2][2] += -dt * G[2] * K;
+        e->A[2][3] += dt * (sb / Lb - G[3] * K);
+        e->Bd[2] = dt * (v * cb * b1 / Lb - G[4] * K);
+        e->Bd[3] = 0.0;
+        if (order < 2) return;
+        {
+            const double qss = ey * K2 * q2 + 2.0 * ey * ey * K1 * K1 * q3;
+            const double qse = K1 * q2 + 2.0 * ey * K * K1 * q3;
+            const double qee = 2.0 * K * K * q3;
+            double GG[5][5];
+            memset(GG, 0, sizeof(GG)); memset(e->hf, 0, sizeof(e->hf));
+            GG[0][0] = v * C * qss; GG[0][1] = v * C * qse; GG[0][2] = -v * S * qs; GG[0][3] = C * qs; GG[0][4] = -v * S * b1 * qs;
+            GG[1][1] = v * C * qee; GG[1][2] = -v * S * qe; GG[1][3] = C * qe; GG[1][4] = -v * S * b1 * qe;
+            GG[2][2] = -v * C * q;  GG[2][3] = -S * q;      GG[2][4] = -v * C * b1 * q;
+            GG[3][4] = -S * b1 * q;
+            GG[4][4] = -v * q * (C * b1 * b1 + S * b2);
+            for (i = 0; i < 5; i++) for (j = 0; j < i; j++) GG[i][j] = GG[j][i];
+            for (i = 0; i < 5; i++) for (j = 0; j < 5; j++) {
+                double hh = GG[i][j] * K;                       /* second derivatives of h = g K */
+                if (i == 0) hh += G[j] * K1;
+                if (j == 0) hh += G[i] * K1;
+                if (i == 0 && j == 0) hh += g * K2;
+                e->hf[0][i][j] = dt * GG[i][j];
+                e->hf[2][i][j] = -dt * hh;
+            }
+            e->hf[1][2][2] = -dt * v * S; e->hf[1][2][3] = e->hf[1][3][2] = dt * C;
+            e->hf[1][2][4] = e->hf[1][4][2] = -dt * v * S * b1; e->hf[1][3][4] = e->hf[1][4][3] = dt * C * b1;
+            e->hf[1][4][4] = dt * v * (-S * b1 * b1 + C * b2);
+            e->hf[2][3][4] += dt * cb * b1 / Lb; e->hf[2][4][3] += dt * cb * b1 / Lb;
+            e->hf[2][4][4] += dt * v / Lb * (-sb * b1 * b1 + cb * b2);
+        }
+    }
+}
+
 static void stage_map(const mpc_oracle_cfg* c, const double* s, double acc, double df, stage_eval* e, int order) {
+    if (c->model == 1) { stage_map_frenet(c, s, acc, df, e, order); return; }
+    {
     const double dt = c->dt, Lb = c->L_b, r = c->L_b / (c->L_a + c->L_b);
     const double x = s[JX], y = s[JY], psi = s[JPSI], v = s[JV];
     const double bta = atan(r * tan(df)); /* :115 */
@@ -170,6 +250,7 @@ static void stage_map(const mpc_oracle_cfg* c, const double* s, double acc, doub
         e->hp[0] = 0.0; e->hp[1] = 0.0; e->hp[2] = 0.0;
         e->hp[3] = dt * cb * b1 / Lb; e->hp[4] = dt * v / Lb * (-sb * b1 * b1 + cb * b2);
     }
+}
 }
 
 /* equality rows: 0..3  s_0 - state (:110-113); 4+4k+j  s_{k+1,j} - f_j(s_k,u_k) (:119-122) */
@@ -254,6 +335,16 @@ void mpc_oracle_eval_hess(const mpc_oracle_cfg* c, const double* z, double sigma
         int ip = IX(k, JPSI), iv = IX(k, JV), id = IX(k, JDF);
         double pp, pv, pd, vd, dd;
         stage_map(c, &z[IX(k, 0)], z[IX(k, JACC)], z[IX(k, JDF)], &e, 2);
+        if (c->model == 1) {
+            static const int col[5] = {0, 1, 2, 3, JDF};
+            int a, b, rw;
+            for (a = 0; a < 5; a++) for (b = 0; b < 5; b++) {
+                double t = 0.0;
+                for (rw = 0; rw < 3; rw++) t += y[rw] * e.hf[rw][a][b];
+                HH(IX(k, col[a]), IX(k, col[b])) -= t;
+            }
+            continue;
+        }
         pp = -(y[JX] * e.hx[0] + y[JY] * e.hy[0] + y[JPSI] * e.hp[0]);
         pv = -(y[JX] * e.hx[1] + y[JY] * e.hy[1] + y[JPSI] * e.hp[1]);
         pd = -(y[JX] * e.hx[2] + y[JY] * e.hy[2] + y[JPSI] * e.hp[2]);
@@ -1174,6 +1265,39 @@ int mpc_oracle_solve_batch(const mpc_oracle_cfg* cfg, long B, const double* stat
             if (warm) memcpy(warm + (size_t)nt * b, tbuf, sizeof(double) * nt);
         }
         ipm_free(&P); free(tbuf);
+    }
+    return 0;
+}
+
+/* Frenet-frame variant: one private copy of cfg per thread carries the problem's curvature polynomial;
+ * the cost is the XY cost against a zero reference (see mpc_oracle.h). */
+int mpc_oracle_solve_batch_frenet(const mpc_oracle_cfg* cfg, long B, const double* state, const double* kpoly,
+                                  const double* v_des, const double* u_prev, double* warm, double* u0,
+                                  double* cost, int* status, int* iters, double* traj, int n_threads) {
+    int N = cfg->N, nt = 6 * N + 4, nr = 3 * (N + 1);
+    if (cfg->N < 3 || cfg->N > 512 || cfg->model != 1) return -1;
+    if (n_threads < 1) n_threads = 1;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(n_threads)
+#endif
+    {
+        ipm_t P; long b;
+        mpc_oracle_cfg lc = *cfg;
+        double* tbuf = (double*)malloc(sizeof(double) * nt);
+        double* zref = (double*)xcalloc(nr, sizeof(double));
+        ipm_alloc(&P, &lc);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 4)
+#endif
+        for (b = 0; b < B; b++) {
+            memcpy(lc.kpoly, kpoly + 4 * b, sizeof(double) * 4);
+            solve_with(&P, state + 4 * b, zref, v_des ? v_des[b] : 0.0, u_prev + 2 * b,
+                       warm ? warm + (size_t)nt * b : NULL, tbuf, u0 ? u0 + 2 * b : NULL,
+                       cost ? cost + b : NULL, status ? status + b : NULL, iters ? iters + b : NULL, NULL);
+            if (traj) memcpy(traj + (size_t)nt * b, tbuf, sizeof(double) * nt);
+            if (warm) memcpy(warm + (size_t)nt * b, tbuf, sizeof(double) * nt);
+        }
+        ipm_free(&P); free(tbuf); free(zref);
     }
     return 0;
 }

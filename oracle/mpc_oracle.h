@@ -46,6 +46,12 @@ typedef struct {
      * stands in for max_cpu_time (:29), which is not reproducible. */
     double tol;          /* 1e-8 */
     int    max_iter;     /* cap */
+    /* model 0: XY kinematic bicycle (MKZMPCPathFollower.jl).  model 1: the Frenet-frame variant
+     * (MKZMPCPathFollowerFrenet.jl): states (s, e_y, e_psi, v) in the slots of (x, y, psi, v),
+     * curvature K(s) = kpoly[0] s^3 + kpoly[1] s^2 + kpoly[2] s + kpoly[3] (:40-41, :111), cost on
+     * e_y, e_psi, v only (:95-101) = the XY cost with w = (0, C_ey, C_epsi, C_ev, ...) and a zero reference. */
+    int    model;
+    double kpoly[4];
 } mpc_oracle_cfg;
 
 /* status codes = JuMP symbols returned by solve_model (MKZMPCPathFollower.jl:176-182)
@@ -96,6 +102,16 @@ int mpc_oracle_solve_batch(const mpc_oracle_cfg* cfg, long B, const double* stat
                            const double* ref, const double* v_des, const double* u_prev,
                            double* warm, double* u0, double* cost, int* status, int* iters,
                            double* traj, int n_threads);
+
+/* Frenet-frame variant (MKZMPCPathFollowerFrenet.jl): cfg->model must be 1 (mpc_oracle_default_cfg_frenet);
+ * state = (s0, ey0, epsi0, v0) (update_init_cond :132-138), kpoly = 4 curvature coefficients per problem,
+ * highest degree first (update_reference :142-147); traj = s[N+1], ey[N+1], v[N+1], epsi[N+1], d_f[N], acc[N]
+ * (get_solver_results :188-206).  cfg->kpoly is ignored here (overwritten per problem). */
+void mpc_oracle_default_cfg_frenet(mpc_oracle_cfg* cfg, int N);
+int mpc_oracle_solve_batch_frenet(const mpc_oracle_cfg* cfg, long B, const double* state,
+                                  const double* kpoly, const double* v_des, const double* u_prev,
+                                  double* warm, double* u0, double* cost, int* status, int* iters,
+                                  double* traj, int n_threads);
 
 /* NLP pieces exported for derivative / KKT tests.  z is in INTERNAL order:
  * stage-major (x,y,psi,v,acc,df) for k<N, then (x,y,psi,v) for k=N; n = 6N+4. */

@@ -19,7 +19,8 @@ class Cfg(C.Structure):
                 ("L_a", C.c_double), ("L_b", C.c_double), ("v_min", C.c_double),
                 ("v_max", C.c_double), ("a_max", C.c_double), ("steer_max", C.c_double),
                 ("a_dmax", C.c_double), ("steer_dmax", C.c_double), ("w", C.c_double * 8),
-                ("tol", C.c_double), ("max_iter", C.c_int)]
+                ("tol", C.c_double), ("max_iter", C.c_int),
+                ("model", C.c_int), ("kpoly", C.c_double * 4)]
 
 
 class Diag(C.Structure):
@@ -54,6 +55,8 @@ def lib():
         _lib.mpc_oracle_default_cfg.argtypes = [C.POINTER(Cfg), C.c_int]
         _lib.mpc_oracle_solve.argtypes = [C.POINTER(Cfg), dp, dp, C.c_double, dp, dp, dp, dp, dp, ip, ip, C.POINTER(Diag)]
         _lib.mpc_oracle_solve_batch.argtypes = [C.POINTER(Cfg), C.c_long, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, C.c_int]
+        _lib.mpc_oracle_default_cfg_frenet.argtypes = [C.POINTER(Cfg), C.c_int]
+        _lib.mpc_oracle_solve_batch_frenet.argtypes = [C.POINTER(Cfg), C.c_long, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, C.c_int]
         _lib.mpc_oracle_rollout_start.argtypes = [C.POINTER(Cfg), dp, dp, dp]
         _lib.mpc_oracle_eval_f.restype = C.c_double
         _lib.mpc_oracle_eval_f.argtypes = [C.POINTER(Cfg), dp, C.c_double, dp]
@@ -129,6 +132,40 @@ def solve_batch(cfg, state, ref, v_des, u_prev, warm=None, want_traj=False, n_th
     traj = np.empty((B, 6 * N + 4)) if want_traj else None
     rc = lib().mpc_oracle_solve_batch(C.byref(cfg), B, _p(state), _p(ref), _p(v_des), _p(u_prev), _p(warm), _p(u0),
                                       _p(cost), _pi(status), _pi(iters), _p(traj), int(n_threads))
+    assert rc == 0
+    return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+
+def default_cfg_frenet(N=8, weights=None, tol=None, max_iter=None, **kw):
+    """MKZMPCPathFollowerFrenet.jl defaults; weights in the XY slot order (0, C_ey, C_epsi, C_ev, C_dacc, C_ddf, C_acc, C_df)."""
+    c = Cfg()
+    lib().mpc_oracle_default_cfg_frenet(C.byref(c), N)
+    if weights is not None:
+        for i, v in enumerate(weights):
+            c.w[i] = float(v)
+    if tol is not None:
+        c.tol = tol
+    if max_iter is not None:
+        c.max_iter = max_iter
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def solve_batch_frenet(cfg, state, kpoly, v_des, u_prev, warm=None, want_traj=False, n_threads=1):
+    """Frenet variant: state (B,4) = s, ey, epsi, v; kpoly (B,4) highest degree first."""
+    N = cfg.N
+    B = state.shape[0]
+    state = np.ascontiguousarray(state, dtype=np.float64)
+    kpoly = np.ascontiguousarray(kpoly, dtype=np.float64)
+    assert kpoly.shape == (B, 4)
+    u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+    v_des = None if v_des is None else np.ascontiguousarray(v_des, dtype=np.float64)
+    u0 = np.empty((B, 2)); cost = np.empty(B)
+    status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
+    traj = np.empty((B, 6 * N + 4)) if want_traj else None
+    rc = lib().mpc_oracle_solve_batch_frenet(C.byref(cfg), B, _p(state), _p(kpoly), _p(v_des), _p(u_prev), _p(warm), _p(u0),
+                                             _p(cost), _pi(status), _pi(iters), _p(traj), int(n_threads))
     assert rc == 0
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
 
