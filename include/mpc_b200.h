@@ -145,6 +145,27 @@ int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T,
                     double* log, double* final_state);
 
 /* Counters of the last solve_batch/rollout call on this handle. */
+/*
+ * Frenet-frame variant of the same solver: scripts/mpc_utils/MKZMPCPathFollowerFrenet.jl (the model the Gazebo
+ * lane-keep node gazebo_sim_mpc_cmd_pub_frenet.jl:112-153 drives).  Same vehicle constants, horizon, bounds, rate
+ * rows and interior-point iteration; states (s, e_y, e_psi, v) with ds/dt = v cos(e_psi + beta) / (1 - e_y K(s)),
+ * K(s) a cubic (:111-120); cost on e_y, e_psi, v - v_target and the input terms (:95-101).
+ *   mpcb200_create_frenet            replaces module load (:28-129); N <= 31; weights start at (:51-58)
+ *   mpcb200_set_cost_frenet          replaces update_cost(cey, cep, cev, cda, cdd, ca, cd) (:158-169), same order
+ *   mpcb200_solve_batch_frenet       replaces, for B problems at once,
+ *       update_init_cond(s, ey, epsi, vel) (:132-138)        -> state    [B][4]
+ *       update_reference(path, k_coeffs, v_des) (:142-147)   -> k_coeffs [B][4] (highest degree first, :40-41), v_des [B]
+ *       update_current_input(c_swa, c_acc) (:151-154)        -> u_prev   [B][2]
+ *       solve_model() (:173-183)                             -> u0 [B][2] (acc, d_f), status, cost, iters
+ *       get_solver_results() (:188-207)                      -> traj [B][6N+4] = s[N+1], ey[N+1], v[N+1], epsi[N+1], d_f[N], acc[N]
+ *   warm as in mpcb200_solve_batch.  mpcb200_solve_batch / _on_path / _rollout refuse a Frenet handle.
+ */
+int mpcb200_create_frenet(mpcb200_handle** out, const mpcb200_config* cfg);
+int mpcb200_set_cost_frenet(mpcb200_handle* h, const double w[7]);
+int mpcb200_solve_batch_frenet(mpcb200_handle* h, int64_t B, const double* state, const double* k_coeffs,
+                               const double* v_des, const double* u_prev, double* warm, double* u0,
+                               double* cost, int32_t* status, int32_t* iters, double* traj, int32_t mem_space);
+
 typedef struct {
     int64_t kernel_launches;   /* kernels of this library launched by the call */
     int64_t h2d_bytes, d2h_bytes;

@@ -54,6 +54,9 @@ def lib():
     L.mpcb200_set_cost.argtypes = [vp, dp]
     L.mpcb200_set_stream.argtypes = [vp, vp]
     L.mpcb200_solve_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
+    L.mpcb200_create_frenet.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+    L.mpcb200_set_cost_frenet.argtypes = [vp, dp]
+    L.mpcb200_solve_batch_frenet.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.mpcb200_solve_batch_on_path.argtypes = [vp, C.c_int64, vp, vp, C.c_int32, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.mpcb200_set_path.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, dp, dp]
     L.mpcb200_rollout.argtypes = [vp, C.c_int64, C.c_int32, dp, ip, C.c_int32, C.c_double, dp, dp]
@@ -91,9 +94,12 @@ class Solver(object):
         self.cfg = config if config is not None else default_config(N, **overrides)
         self.N = self.cfg.N
         self._h = C.c_void_p()
-        rc = lib().mpcb200_create(C.byref(self._h), C.byref(self.cfg))
+        rc = self._create()(C.byref(self._h), C.byref(self.cfg))
         if rc != 0:
             raise MpcB200Error(rc, lib().mpcb200_last_error(None).decode())
+
+    def _create(self):
+        return lib().mpcb200_create
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -220,3 +226,48 @@ class Solver(object):
         v = C.c_double()
         self._check(lib().mpcb200_fp64_peak(self._h, C.byref(v)))
         return v.value
+
+
+class FrenetSolver(Solver):
+    """Frenet-frame variant (mpcb200_create_frenet; scripts/mpc_utils/MKZMPCPathFollowerFrenet.jl): N <= 31."""
+
+    def _create(self):
+        return lib().mpcb200_create_frenet
+
+    def set_cost(self, w):
+        """update_cost order of MKZMPCPathFollowerFrenet.jl:158-169: cey, cep, cev, cda, cdd, ca, cd."""
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        assert w.shape == (7,)
+        self._check(lib().mpcb200_set_cost_frenet(self._h, w.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def solve_batch(self, state, k_coeffs, u_prev, v_des=None, warm=None, want_traj=False, want_aux=True):
+        """state (B,4) = s, ey, epsi, v; k_coeffs (B,4) highest degree first; u_prev (B,2) = (d_f_current, acc_current);
+        warm / traj (B,6N+4) = s, ey, v, epsi, d_f, acc."""
+        N = self.N
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        B = state.shape[0]
+        k_coeffs = np.ascontiguousarray(k_coeffs, dtype=np.float64)
+        u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+        if state.shape != (B, 4) or k_coeffs.shape != (B, 4) or u_prev.shape != (B, 2):
+            raise ValueError("solve_batch: expected state (B,4), k_coeffs (B,4), u_prev (B,2)")
+        if v_des is not None:
+            v_des = np.ascontiguousarray(v_des, dtype=np.float64)
+            if v_des.shape != (B,):
+                raise ValueError("solve_batch: v_des must be (B,)")
+        if warm is not None:
+            if not (isinstance(warm, np.ndarray) and warm.dtype == np.float64 and warm.flags.c_contiguous
+                    and warm.shape == (B, 6 * N + 4)):
+                raise ValueError("solve_batch: warm must be a C-contiguous float64 (B,6N+4) array (updated in place)")
+        u0 = np.empty((B, 2))
+        cost = np.empty(B) if want_aux else None
+        status = np.empty(B, dtype=np.int32) if want_aux else None
+        iters = np.empty(B, dtype=np.int32) if want_aux else None
+        traj = np.empty((B, 6 * N + 4)) if want_traj else None
+        self._check(lib().mpcb200_solve_batch_frenet(self._h, B, _ptr(state), _ptr(k_coeffs), _ptr(v_des), _ptr(u_prev), _ptr(warm),
+                                                     _ptr(u0), _ptr(cost), _ptr(status), _ptr(iters), _ptr(traj), HOST))
+        return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+    def solve_batch_device(self, B, state, k_coeffs, u_prev, u0, v_des=None, warm=None, cost=None, status=None, iters=None, traj=None):
+        """Device pointers (torch CUDA tensors or ints); asynchronous on the handle's stream."""
+        self._check(lib().mpcb200_solve_batch_frenet(self._h, B, _ptr(state), _ptr(k_coeffs), _ptr(v_des), _ptr(u_prev), _ptr(warm),
+                                                     _ptr(u0), _ptr(cost), _ptr(status), _ptr(iters), _ptr(traj), DEVICE))

@@ -43,6 +43,24 @@ mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const long
     }
 }
 
+// Frenet-frame variant (MKZMPCPathFollowerFrenet.jl): same driver, dense s / e_y columns (mpc_kernel.cuh, MODEL 1);
+// 62-double records: two blocks (8 warps) per SM at N = 20
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2)
+mpc_solve_frenet_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const long long B, unsigned long long* counter) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5;
+    const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_team(cfg.N, 1));
+    TeamSolver<1, 1>::init_work(smem, cfg.N);
+    for (;;) {
+        unsigned long long b = 0;
+        if ((threadIdx.x & 31) == 0) b = atomicAdd(counter, 1ULL);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned long long)B) break;
+        solve_problem<1, 1>(cfg, io, rg, (long)b, smem);
+        __syncwarp();
+    }
+}
+
 // Long horizons (32 <= N <= 95): one problem per block of W = 2 or 3 warps, thread k = stage k.
 // register budget (measured at N = 40 / 80): W = 2 -> 6 blocks (12 warps) per SM at 168 registers; W = 3 -> 2 blocks at 255
 #ifndef MPC_LONG_MIN_BLOCKS2
@@ -112,6 +130,7 @@ struct mpcb200_handle {
     int num_sms = 0;
     int blocks_per_sm = 0;
     int team_warps = 1;     /* warps per problem: 1 (N <= 31), 2 (N <= 63), 3 (N <= 95) */
+    int model = 0;          /* 0: XY model; 1: Frenet-frame variant (mpcb200_create_frenet) */
     size_t smem_bytes = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -195,9 +214,14 @@ int mpcb200_default_config(mpcb200_config* c, int32_t N) {
     return MPCB200_OK;
 }
 
-int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
+static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int model);
+int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) { return create_impl(out, cfg, 0); }
+int mpcb200_create_frenet(mpcb200_handle** out, const mpcb200_config* cfg) { return create_impl(out, cfg, 1); }
+
+static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int model) {
     if (!out || !cfg) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: NULL argument");
     *out = nullptr;
+    if (model && cfg->N > 31) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create_frenet: horizon N=%d above 31 (one warp per problem only)", cfg->N);
     if (cfg->N < 3 || cfg->N > 95) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: horizon N=%d outside [3,95]", cfg->N);
     if (!(cfg->dt > 0) || !(cfg->dt_control > 0) || !(cfg->L_b > 0) || !(cfg->v_max > cfg->v_min) || !(cfg->a_max > 0) ||
         !(cfg->steer_max > 0 && cfg->steer_max < 1.5) || !(cfg->a_dmax > 0) || !(cfg->steer_dmax > 0) || !(cfg->tol > 0) ||
@@ -217,7 +241,10 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
     memset(&h->stats, 0, sizeof(h->stats));
     /* defaults of MKZMPCPathFollower.jl:51-59 in update_cost order */
     const double w0[8] = {9.0, 9.0, 10.0, 0.0, 100.0, 1000.0, 0.0, 0.0};
-    memcpy(h->w, w0, sizeof(w0));
+    /* MKZMPCPathFollowerFrenet.jl:51-58 in the XY slots: nothing on s, C_ey, C_epsi, C_ev, C_dacc, C_ddf, C_acc, C_df */
+    const double w1[8] = {0.0, 9.0, 10.0, 0.5, 100.0, 1000.0, 0.0, 0.0};
+    memcpy(h->w, model ? w1 : w0, sizeof(w0));
+    h->model = model;
 #define TRY_OR_FREE(expr)                                                                 \
     do {                                                                                  \
         cudaError_t e2 = (expr);                                                          \
@@ -238,12 +265,18 @@ int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) {
     TRY_OR_FREE(cudaMalloc((void**)&h->d_counter, sizeof(unsigned long long)));
     h->team_warps = team_warps(cfg->N);
     {
-        int roles[32 * ROLE_STRIDE];
-        for (int l = 0; l < 32; l++) riccati_roles(l, cfg->N, W_SD_OF(h->team_warps), roles + l * ROLE_STRIDE);
+        int roles[32 * ROLE_STRIDE_F];
+        const int rs = role_stride_of(model);
+        for (int l = 0; l < 32; l++) riccati_roles(l, cfg->N, w_sd_of(h->team_warps, model), roles + l * rs, model);
         TRY_OR_FREE(cudaMalloc((void**)&h->d_roles, sizeof(roles)));
-        TRY_OR_FREE(cudaMemcpy(h->d_roles, roles, sizeof(roles), cudaMemcpyHostToDevice));
+        TRY_OR_FREE(cudaMemcpy(h->d_roles, roles, sizeof(int) * 32 * rs, cudaMemcpyHostToDevice));
     }
-    if (h->team_warps == 1) {
+    if (model) {
+        h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N, 1) * sizeof(double);
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_frenet_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
+    } else if (h->team_warps == 1) {
         h->smem_bytes = ((size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N) + WARPS_PER_BLOCK * ROLLOUT_PX) * sizeof(double);
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -303,7 +336,9 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
     long long max_blocks = (long long)h->num_sms * h->blocks_per_sm;
     int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
     if (grid < 1) grid = 1;
-    if (h->team_warps == 1)
+    if (h->model)
+        mpc_solve_frenet_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
+    else if (h->team_warps == 1)
         mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     else if (h->team_warps == 2)
         mpc_solve_long_kernel<2><<<grid, 64, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
@@ -332,7 +367,7 @@ static int solve_small_host(mpcb200_handle* h, int64_t B, const double* state, c
                             const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
                             double* traj) {
     const int N = h->cfg.N;
-    const size_t nt = 6 * (size_t)N + 4, nr = 3 * ((size_t)N + 1);
+    const size_t nt = 6 * (size_t)N + 4, nr = h->model ? 4 : 3 * ((size_t)N + 1);
     /* layout in doubles: [counter, pad] state ref uprev vdes | warm | u0 cost traj status/iters(int32 pairs) */
     const size_t o_state = 2, o_ref = o_state + 4 * B, o_uprev = o_ref + nr * B, o_vdes = o_uprev + 2 * B, o_warm = o_vdes + B;
     const size_t o_u0 = o_warm + nt * B, o_cost = o_u0 + 2 * B, o_traj = o_cost + B, o_stat = o_traj + nt * B, o_iter = o_stat + (B + 1) / 2;
@@ -393,10 +428,11 @@ static int solve_batch_impl(mpcb200_handle* h, const char* who, int64_t B, const
     if (B == 0) return MPCB200_OK;
     const bool on_path = (path_of != nullptr);
     if (!state || (!ref && !on_path) || !u_prev || !u0) return fail(h, MPCB200_EINVAL, "%s: state, %s, u_prev and u0 are required", who, on_path ? "path_of" : "ref");
+    if (on_path && h->model) return fail(h, MPCB200_EINVAL, "%s: not available for the Frenet-frame variant", who);
     if (on_path && h->team_warps != 1) return fail(h, MPCB200_EINVAL, "%s: on-device reference generation needs N <= 31 (N=%d)", who, h->cfg.N);
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int N = h->cfg.N;
-    const size_t nt = 6 * (size_t)N + 4, nr = 3 * ((size_t)N + 1);
+    const size_t nt = 6 * (size_t)N + 4, nr = h->model ? 4 : 3 * ((size_t)N + 1);
     RefGen rg;
     memset(&rg, 0, sizeof(rg));
     if (on_path) {
@@ -469,9 +505,27 @@ static int solve_batch_impl(mpcb200_handle* h, const char* who, int64_t B, const
     return MPCB200_OK;
 }
 
+int mpcb200_solve_batch_frenet(mpcb200_handle* h, int64_t B, const double* state, const double* k_coeffs, const double* v_des,
+                               const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
+                               double* traj, int32_t mem_space) {
+    if (h && !h->model) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch_frenet: the handle was not created with mpcb200_create_frenet");
+    return solve_batch_impl(h, "mpcb200_solve_batch_frenet", B, state, k_coeffs, nullptr, 1, 0.0, v_des, u_prev, warm, u0, cost, status, iters,
+                            traj, nullptr, nullptr, mem_space);
+}
+
+int mpcb200_set_cost_frenet(mpcb200_handle* h, const double w[7]) {
+    if (!h || !w) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost_frenet: NULL argument");
+    if (!h->model) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost_frenet: the handle was not created with mpcb200_create_frenet");
+    for (int i = 0; i < 7; i++) if (!(w[i] >= 0.0)) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost_frenet: weight %d is negative or NaN", i);
+    h->w[0] = 0.0;
+    memcpy(h->w + 1, w, 7 * sizeof(double));
+    return MPCB200_OK;
+}
+
 int mpcb200_solve_batch(mpcb200_handle* h, int64_t B, const double* state, const double* ref, const double* v_des,
                         const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
                         double* traj, int32_t mem_space) {
+    if (h && h->model) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch: Frenet handle; use mpcb200_solve_batch_frenet");
     return solve_batch_impl(h, "mpcb200_solve_batch", B, state, ref, nullptr, 1, 0.0, v_des, u_prev, warm, u0, cost, status, iters, traj,
                             nullptr, nullptr, mem_space);
 }

@@ -153,6 +153,21 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define SD_BR 42    // -mu/ss_L + mu/ss_U of the rate row
 #define SD_DR 44    // rate-row residual used as right-hand side
 #define SDS 46      // even: records are 16-byte aligned
+// Frenet-frame variant (MODEL 1, MKZMPCPathFollowerFrenet.jl): the stage map has dense s and e_y columns
+// (rows s and e_psi depend on s through K(s) and on e_y) and a 5x5 Lagrangian-Hessian block over
+// (s, e_y, e_psi, v, df).  Its record is the XY record (s, e_y, e_psi, v in the slots of x, y, psi, v) plus
+#define SD_CS 46    // column s  of A over next-state rows (unit part included)
+#define SD_CE 50    // column e_y of A
+#define SD_HSE 54   // Hessian entries that are structurally zero in the XY model
+#define SD_HSP 55
+#define SD_HSV 56
+#define SD_HSD 57
+#define SD_HEP 58
+#define SD_HEV 59
+#define SD_HED 60
+#define SDS_F 62
+#define W_TT2 148   // MODEL 1: columns s | e_y of P M (2 x 6); one warp per problem only, records start at 160
+MPC_HD constexpr int sds_of(int model) { return model ? SDS_F : SDS; }
 #define KST_STRIDE 14
 
 // per-thread state kept in shared memory instead of registers, in groups: group g of stage k is the
@@ -173,8 +188,9 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define G_Z_STRIDE 10
 #define LF_DOUBLES 42   // per stage slot, all groups
 MPC_HD int team_warps(int N) { return (N + 1 + 31) / 32; }   // warps that share one problem
-MPC_HD int lf_offset(int N) { return W_SD_OF(team_warps(N)) + (N + 1) * SDS + N * KST_STRIDE; }
-MPC_HD int smem_doubles_per_team(int N) { return lf_offset(N) + LF_DOUBLES * (N + 2); }   // even: 16-byte alignment of the next team
+MPC_HD constexpr int w_sd_of(int W, int model) { return model ? 160 : W_SD_OF(W); }
+MPC_HD int lf_offset(int N, int model = 0) { return w_sd_of(team_warps(N), model) + (N + 1) * sds_of(model) + N * KST_STRIDE; }
+MPC_HD int smem_doubles_per_team(int N, int model = 0) { return lf_offset(N, model) + LF_DOUBLES * (N + 2); }   // even: 16-byte alignment of the next team
 
 MPC_DEV double dmax_(double a, double b) { return a > b ? a : b; }
 MPC_DEV double dmin_(double a, double b) { return a < b ? a : b; }
@@ -224,6 +240,7 @@ struct EvalLane {         // model evaluation at the last evaluated point, this 
     double cs, sn, cb, sb, b1, b2;  // cos/sin(psi+beta), cos/sin(beta), beta', beta''
     double rd[4];         // k < N: f(s_k,u_k) - s_{k+1};  k = N: state - s_0;  else 0
     double dr[2];         // rate-row defect d(x) - slack
+    double q, K;          // MODEL 1: 1 / (1 - e_y K(s)) and K(s)  (the two pad words of the group)
 };
 struct EvalState {        // ... and its team-wide scalars
     double f, lb, theta;  // objective (unscaled), sum of log slacks, 1-norm constraint violation
@@ -251,7 +268,7 @@ MPC_DEV_NOINLINE void kappa_sigma_clamp(double* z, const double* sl, double mu) 
 // Serial part of the restoration by rollout (see TeamSolver::rollout_restore): inputs of stage s are
 // read from / written back to entries 4, 5 of stage s's step group, states written to entries 0..3.
 // Rare (a few per cent of the cold starts, once each): out of line, scalars by value.
-struct RolloutConsts { double dt, dtc, dtLb, rfrac, vmin, vmax, amax, smax, admax, sdmax; };
+struct RolloutConsts { double dt, dtc, dtLb, rfrac, vmin, vmax, amax, smax, admax, sdmax; int model; double kp[4]; };
 MPC_DEV_NOINLINE void rollout_core(smem_t sm, int fa, int cbase, int N, RolloutConsts c) {
     double s0 = lds(sm, cbase), s1 = lds(sm, cbase + SO(1)), s2 = lds(sm, cbase + SO(2)), s3 = lds(sm, cbase + SO(3));
     double pa = lds(sm, cbase + SO(5)), pd = lds(sm, cbase + SO(4));
@@ -273,10 +290,16 @@ MPC_DEV_NOINLINE void rollout_core(smem_t sm, int fa, int cbase, int N, RolloutC
         const double r = c.rfrac;
         const double inv = sqrt(1.0 / (cd * cd + r * r * sd * sd));
         const double cb = cd * inv, sb = r * sd * inv;
-        const double n0 = s0 + c.dt * (s3 * (cps * cb - sps * sb));
+        double n0 = s0 + c.dt * (s3 * (cps * cb - sps * sb));
         const double n1 = s1 + c.dt * (s3 * (sps * cb + cps * sb));
-        const double n2 = s2 + c.dtLb * (s3 * sb);
+        double n2 = s2 + c.dtLb * (s3 * sb);
         const double n3 = s3 + c.dt * ua;
+        if (c.model) {   // Frenet frame (MKZMPCPathFollowerFrenet.jl:111-120): (s, e_y, e_psi, v)
+            const double K = ((c.kp[0] * s0 + c.kp[1]) * s0 + c.kp[2]) * s0 + c.kp[3];
+            const double g = s3 * (cps * cb - sps * sb) / (1.0 - s1 * K);
+            n0 = s0 + c.dt * g;
+            n2 = s2 + (c.dtLb * (s3 * sb) - c.dt * (g * K));
+        }
         s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
         fa += SO(G_DX_STRIDE);
     }
@@ -287,7 +310,10 @@ MPC_DEV_NOINLINE void rollout_core(smem_t sm, int fa, int cbase, int N, RolloutC
 // ints per lane: shared-memory offsets (SO units) of the operands of rounds A, B and E.  They depend
 // only on the lane, the horizon and the team size, so mpcb200_create computes the table once.
 #define ROLE_STRIDE 20
-MPC_HD void riccati_roles(int l, int N, int W_SD, int* out) {
+#define ROLE_STRIDE_F 24   // MODEL 1: + second task of round A (columns s | e_y of P M, lanes 0..11): a2_p, a2_m, a2_out
+MPC_HD constexpr int role_stride_of(int model) { return model ? ROLE_STRIDE_F : ROLE_STRIDE; }
+MPC_HD void riccati_roles(int l, int N, int W_SD, int* out, int model = 0) {
+    const int SDS_ = sds_of(model);
     int a_p, a_m, a_ex, a_out, b_m, b_mk, b_t, b_x, b_h, b_o1, b_o2, e_f0, e_fi, e_fj, e_o1, e_o2, e_k0, e_k1;
         {
             // round A: lane (i, cc) -> TT[cc][i] = sum_{j<4} P[i][j] CF[cc][j] + X,  X = 0 | P[i][4] | P[i][5] | p[i]
@@ -308,11 +334,12 @@ MPC_HD void riccati_roles(int l, int N, int W_SD, int* out) {
             else kind = 3;
             int mb, mk, tb, xb, hf, o1, o2;
             if (kind >= 2) { mb = SO(W_Z); mk = 0; }
+            else if (c1 < 2 && model) { mb = SO(W_SD + (c1 == 0 ? SD_CS : SD_CE)); mk = 1; }
             else if (c1 < 2) { mb = (c1 == 0) ? SO(W_EX) : SO(W_EY); mk = 0; }
             else { mb = SO(W_SD + SD_CF + 4 * (c1 - 2)); mk = 1; }
             // That column c2 (rows 0..5 contiguous): P row c2 (symmetric) for x,y; TT column otherwise; TT[4] for the vector
             if (kind == 1) tb = SO(W_TT + 24);
-            else if (kind == 0) tb = (c2 < 2) ? SO(W_P + 6 * c2) : SO(W_TT + 6 * (c2 - 2));
+            else if (kind == 0) tb = (c2 < 2) ? (model ? SO(W_TT2 + 6 * c2) : SO(W_P + 6 * c2)) : SO(W_TT + 6 * (c2 - 2));
             else tb = SO(W_Z);
             xb = (kind <= 1 && c1 == 4) ? tb + SO(4) : (kind <= 1 && c1 == 5) ? tb + SO(5) : SO(W_Z);
             hf = SD_ZERO;
@@ -322,6 +349,13 @@ MPC_HD void riccati_roles(int l, int N, int W_SD, int* out) {
                 else if (c1 == 2 && c2 == 3) hf = SD_HPV;
                 else if (c1 == 2 && c2 == 5) hf = SD_HPD;
                 else if (c1 == 3 && c2 == 5) hf = SD_HVD;
+                else if (model && c1 == 0 && c2 == 1) hf = SD_HSE;
+                else if (model && c1 == 0 && c2 == 2) hf = SD_HSP;
+                else if (model && c1 == 0 && c2 == 3) hf = SD_HSV;
+                else if (model && c1 == 0 && c2 == 5) hf = SD_HSD;
+                else if (model && c1 == 1 && c2 == 2) hf = SD_HEP;
+                else if (model && c1 == 1 && c2 == 3) hf = SD_HEV;
+                else if (model && c1 == 1 && c2 == 5) hf = SD_HED;
             } else if (kind == 2) hf = (l == 27) ? SD_CA : (l == 28) ? SD_CD : (l == 29) ? SD_NCA : SD_NCD;
             if (kind == 0) { o1 = SO(W_F + 6 * c1 + c2); o2 = SO(W_F + 6 * c2 + c1); }
             else if (kind == 1) { o1 = o2 = SO(W_FV + c1); }
@@ -355,7 +389,7 @@ MPC_HD void riccati_roles(int l, int N, int W_SD, int* out) {
             int ks = -1;
             if (act && !vec && i == j) ks = j;
             if (act && vec && i == 0) ks = 6;
-            const int kb = SO(W_SD + (N + 1) * SDS + (N - 1) * KST_STRIDE);  // gains of stage N-1
+            const int kb = SO(W_SD + (N + 1) * SDS_ + (N - 1) * KST_STRIDE);  // gains of stage N-1
             e_f0 = (f0); e_fi = (fi); e_fj = (fj); e_o1 = (o1); e_o2 = (o2);
             e_k0 = (ks >= 0 ? kb + SO(ks) : SO(W_DUMMY));
             e_k1 = (ks >= 0 ? kb + SO(7 + ks) : SO(W_DUMMY));
@@ -363,12 +397,23 @@ MPC_HD void riccati_roles(int l, int N, int W_SD, int* out) {
     out[0] = a_p; out[1] = a_m; out[2] = a_ex; out[3] = a_out; out[4] = b_m; out[5] = b_mk; out[6] = b_t; out[7] = b_x; out[8] = b_h;
     out[9] = b_o1; out[10] = b_o2; out[11] = e_f0; out[12] = e_fi; out[13] = e_fj; out[14] = e_o1; out[15] = e_o2;
     out[16] = e_k0; out[17] = e_k1; out[18] = (e_k0 == SO(W_DUMMY)) ? 0 : SO(KST_STRIDE); out[19] = 0;
+    if (model) {
+        // second task of round A: lane (i, cc) for l < 12 -> TT2[cc][i] = sum_{j<4} P[i][j] C[cc][j], C = column s | e_y of A
+        const int i = (l < 12) ? (l >> 1) : 0, cc = l & 1;
+        out[20] = SO(W_P + 6 * i);
+        out[21] = (l < 12) ? SO(W_SD + (cc ? SD_CE : SD_CS)) : SO(W_SD + SD_CS);
+        out[22] = (l < 12) ? SO(W_TT2 + 6 * cc + i) : SO(W_DUMMY);
+        out[23] = 0;
+    }
 }
 
 // W = warps per team (1: a warp per problem; 2, 3: a block per problem)
-template <int W>
+// MODEL 0: XY kinematic bicycle (MKZMPCPathFollower.jl); MODEL 1: Frenet-frame variant (MKZMPCPathFollowerFrenet.jl)
+template <int W, int MODEL = 0>
 struct TeamSolver {
-    static constexpr int W_SD = W_SD_OF(W);   // first stage record
+    static_assert(MODEL == 0 || W == 1, "the Frenet variant runs one warp per problem");
+    static constexpr int W_SD = w_sd_of(W, MODEL);   // first stage record
+    static constexpr int SDSZ = sds_of(MODEL);       // doubles per stage record
     static constexpr int NFILT_MAX = 32 * W;  // one filter entry per thread
     const KCfg& c;
     const smem_t sm;   // this team's shared memory (opaque base)
@@ -388,16 +433,18 @@ struct TeamSolver {
           slot(team_tid() <= cfg.N ? team_tid() : cfg.N + 1) {}
 
     // per-thread state in shared memory (groups G_*)
-    MPC_DEV int grp(int off, int stride) const { return SO(lf_offset(N) + off * (N + 2)) + slot * SO(stride); }
+    MPC_DEV int grp(int off, int stride) const { return SO(lf_offset(N, MODEL) + off * (N + 2)) + slot * SO(stride); }
     MPC_DEV void ev_store(const EvalLane& e) {
         const int a = grp(G_EV_OFF, G_EV_STRIDE);
         sts2(sm, a, e.cs, e.sn); sts2(sm, a + SO(2), e.cb, e.sb); sts2(sm, a + SO(4), e.b1, e.b2);
         sts2(sm, a + SO(6), e.rd[0], e.rd[1]); sts2(sm, a + SO(8), e.rd[2], e.rd[3]); sts2(sm, a + SO(10), e.dr[0], e.dr[1]);
+        if (MODEL) sts2(sm, a + SO(12), e.q, e.K);
     }
     MPC_DEV void ev_load_model(EvalLane& e) const {
         const int a = grp(G_EV_OFF, G_EV_STRIDE);
         const d2 v0 = lds2(sm, a), v1 = lds2(sm, a + SO(2)), v2 = lds2(sm, a + SO(4));
         e.cs = v0.x; e.sn = v0.y; e.cb = v1.x; e.sb = v1.y; e.b1 = v2.x; e.b2 = v2.y;
+        if (MODEL) { const d2 v3 = lds2(sm, a + SO(12)); e.q = v3.x; e.K = v3.y; }
     }
     MPC_DEV void ev_load_resid(EvalLane& e) const {
         const int a = grp(G_EV_OFF, G_EV_STRIDE);
@@ -408,9 +455,26 @@ struct TeamSolver {
         const int a = grp(G_REF_OFF, G_REF_STRIDE);
         sts(sm, a, x); sts(sm, a + SO(1), y); sts(sm, a + SO(2), p);
     }
-    MPC_DEV double ref_x() const { return lds(sm, grp(G_REF_OFF, G_REF_STRIDE)); }
-    MPC_DEV double ref_y() const { return lds(sm, grp(G_REF_OFF, G_REF_STRIDE) + SO(1)); }
-    MPC_DEV double ref_p() const { return lds(sm, grp(G_REF_OFF, G_REF_STRIDE) + SO(2)); }
+    // MODEL 1: the cost is on e_y, e_psi themselves (reference 0); the reference group holds each thread's copy of
+    // the curvature polynomial instead (4 doubles, the group's full width)
+    MPC_DEV double ref_x() const { return MODEL ? 0.0 : lds(sm, grp(G_REF_OFF, G_REF_STRIDE)); }
+    MPC_DEV double ref_y() const { return MODEL ? 0.0 : lds(sm, grp(G_REF_OFF, G_REF_STRIDE) + SO(1)); }
+    MPC_DEV double ref_p() const { return MODEL ? 0.0 : lds(sm, grp(G_REF_OFF, G_REF_STRIDE) + SO(2)); }
+    MPC_DEV void set_kpoly(double k0, double k1, double k2, double k3) {
+        const int a = grp(G_REF_OFF, 4);
+        sts2(sm, a, k0, k1); sts2(sm, a + SO(2), k2, k3);
+    }
+    // curvature K(s) and its derivatives at this thread's s (MKZMPCPathFollowerFrenet.jl:111)
+    struct Curv { double K, K1, K2; };
+    MPC_DEV Curv curvature(double s) const {
+        const int a = grp(G_REF_OFF, 4);
+        const d2 k01 = lds2(sm, a), k23 = lds2(sm, a + SO(2));
+        Curv r;
+        r.K = ((k01.x * s + k01.y) * s + k23.x) * s + k23.y;
+        r.K1 = (3.0 * k01.x * s + 2.0 * k01.y) * s + k23.x;
+        r.K2 = 6.0 * k01.x * s + 2.0 * k01.y;
+        return r;
+    }
     MPC_DEV void ld_dx(StepState& D) const {
         const int a = grp(G_DX_OFF, G_DX_STRIDE);
         const d2 v0 = lds2(sm, a), v1 = lds2(sm, a + SO(2)), v2 = lds2(sm, a + SO(4));
@@ -533,7 +597,7 @@ struct TeamSolver {
     MPC_DEV double wv() const { return (k >= 1 && k <= N - 1) ? c.w[3] : 0.0; }
     MPC_DEV double rHi(int i) const { return (k == 0) ? c.rHiFirst[i] : c.rHiLater[i]; }
     MPC_DEV double cst(int i) const { return lds(sm, SO(W_CONST + i)); }  // state[0..3], u_prev[0..1], v_des
-    MPC_DEV int rec() const { return SO(W_SD + (isS ? k : 0) * SDS); }    // this lane's own stage record
+    MPC_DEV int rec() const { return SO(W_SD + (isS ? k : 0) * SDSZ); }    // this lane's own stage record
 
     MPC_DEV static void init_work(smem_t sm, int N) {
         const int l = team_tid();
@@ -541,7 +605,8 @@ struct TeamSolver {
         if (l < 4) sts(sm, SO(W_NC + l), 0.0);
         if (l < 2) sts(sm, SO(W_DUMMY + l), 0.0);
         if (l <= N) {   // structural constants of this lane's record: never rewritten
-            const int r = SO(W_SD + l * SDS);
+            const int r = SO(W_SD + l * SDSZ);
+            if (MODEL) { sts(sm, r + SO(SD_CS + 3), 0.0); sts(sm, r + SO(SD_CE + 3), 0.0); sts(sm, r + SO(61), 0.0); }
             sts(sm, r + SO(SD_CF + 3), 0.0);                                        // psi column: (A02, A12, 1, 0) -- the 1 is set by assemble (0 for record N)
             sts(sm, r + SO(SD_CF + 8), 0.0); sts(sm, r + SO(SD_CF + 9), 0.0); sts(sm, r + SO(SD_CF + 10), 0.0);   // a column: (0,0,0,dt)
             sts(sm, r + SO(SD_CF + 15), 0.0);                                       // df column: (b0,b1,b2,0)
@@ -594,10 +659,18 @@ struct TeamSolver {
             e.b1 = r * iD;
             e.b2 = r * (1.0 - r * r) * (2.0 * sd * cd) * (iD * iD);
         }
-        const double fx = sx + c.dt * (sv * e.cs);
+        double fx = sx + c.dt * (sv * e.cs);
         const double fy = sy + c.dt * (sv * e.sn);
-        const double fp = sp + c.dtLb * (sv * e.sb);
+        double fp = sp + c.dtLb * (sv * e.sb);
         const double fv = sv + c.dt * ua;
+        if (MODEL) {   // MKZMPCPathFollowerFrenet.jl:111-120: ds/dt = v cos(e_psi + beta) / (1 - e_y K(s))
+            const Curv cu = curvature(sx);
+            e.K = cu.K;
+            e.q = 1.0 / (1.0 - sy * cu.K);
+            const double g = sv * e.cs * e.q;
+            fx = sx + c.dt * g;
+            fp = sp + c.dt * (sv * e.sb / c.Lb - g * cu.K);
+        }
         // thread k < N takes s_{k+1}; thread N takes s_0 (for the initial-condition rows); every thread u_{k-1}
         double nxt[4], prv[2];
         {
@@ -661,6 +734,24 @@ struct TeamSolver {
         return g;
     }
 
+    // MODEL 1: stage Jacobian at the current iterate (= the last evaluated point); all zero for threads without an input
+    struct FJac { double a00, a01, a02, a03, a12, a13, a20, a21, a22, a23, b0, b1, b2, G0, G1, G2, G3, G4, g, K1, K2; };
+    MPC_DEV FJac frenet_jac(const EvalLane& e) const {
+        FJac J;
+        const Curv cu = curvature(L.sx);
+        const double v = L.sv, dt = isU ? c.dt : 0.0, one = isU ? 1.0 : 0.0;
+        const double q2 = e.q * e.q;
+        const double qs = L.sy * cu.K1 * q2, qe = e.K * q2;
+        J.K1 = cu.K1; J.K2 = cu.K2;
+        J.g = v * e.cs * e.q;
+        J.G0 = v * e.cs * qs; J.G1 = v * e.cs * qe; J.G2 = -v * e.sn * e.q; J.G3 = e.cs * e.q; J.G4 = -v * e.sn * e.b1 * e.q;
+        J.a00 = one + dt * J.G0; J.a01 = dt * J.G1; J.a02 = dt * J.G2; J.a03 = dt * J.G3; J.b0 = dt * J.G4;
+        J.a12 = dt * v * e.cs; J.a13 = dt * e.sn; J.b1 = dt * v * e.cs * e.b1;
+        J.a20 = -dt * (J.G0 * e.K + J.g * cu.K1); J.a21 = -dt * J.G1 * e.K; J.a22 = one - dt * J.G2 * e.K;
+        J.a23 = dt * (e.sb / c.Lb - J.G3 * e.K); J.b2 = dt * (v * e.cb * e.b1 / c.Lb - J.G4 * e.K);
+        return J;
+    }
+
     // ------------------------------------------------------------------
     // Stage record assembly (lane k writes record k).
     //   req 0: least-squares multiplier system (identity Hessian, unit slack weights, zero residuals)
@@ -677,6 +768,9 @@ struct TeamSolver {
         BoundMult Z;
         ld_z(Z);
         double Hxx, Hyy, Hpp, Hpv = 0.0, Hvv, Hpd = 0.0, Hvd = 0.0, Haa, Hdd, Ca = 0.0, Cd = 0.0;
+        double Hse = 0.0, Hsp = 0.0, Hsv = 0.0, Hsd = 0.0, Hep = 0.0, Hev = 0.0, Hed = 0.0;   // MODEL 1 only
+        FJac J;
+        if (MODEL) J = frenet_jac(e);
         double gsv, gua = 0.0, gud = 0.0;
         double SrW[2] = {0.0, 0.0}, br[2] = {0.0, 0.0}, wrow[2] = {0.0, 0.0}, rdr[2] = {0.0, 0.0};
         if (req == 0) {
@@ -691,8 +785,29 @@ struct TeamSolver {
             double y1[3];
             { const double y[3] = {L.yx, L.yy, L.yp}; xnext<3>(y, y1); }
             const double y1x = y1[0], y1y = y1[1], y1p = y1[2];
-            double hpp = 0.0, hdd = 0.0;
-            if (isU) {
+            double hpp = 0.0, hdd = 0.0, hss = 0.0, hee = 0.0;
+            if (MODEL && isU) {
+                // Lagrangian Hessian of the Frenet stage map over (s, e_y, e_psi, v, df): with g = v C q,
+                // rows s and e_psi contribute  -dt [ (y_s - y_p K) hess g - y_p K' (e_s grad g' + grad g e_s') - y_p g K'' e_s e_s' ]
+                const double v = L.sv, dt = c.dt, q = e.q, K = e.K, Cc = e.cs, Sc = e.sn, b1 = e.b1, b2 = e.b2, ey = L.sy;
+                const double q2 = q * q, q3 = q2 * q, K1 = J.K1, K2 = J.K2;
+                const double qs = ey * K1 * q2, qe = K * q2;
+                const double qss = ey * K2 * q2 + 2.0 * ey * ey * K1 * K1 * q3, qse = K1 * q2 + 2.0 * ey * K * K1 * q3, qee = 2.0 * K * K * q3;
+                const double m = y1x - y1p * K, n = y1p * K1;
+                hss = -dt * (m * (v * Cc * qss) - 2.0 * n * J.G0 - y1p * J.g * K2);
+                Hse = -dt * (m * (v * Cc * qse) - n * J.G1);
+                Hsp = -dt * (m * (-v * Sc * qs) - n * J.G2);
+                Hsv = -dt * (m * (Cc * qs) - n * J.G3);
+                Hsd = -dt * (m * (-v * Sc * b1 * qs) - n * J.G4);
+                hee = -dt * m * (v * Cc * qee);
+                Hep = dt * m * (v * Sc * qe); Hev = -dt * m * (Cc * qe); Hed = dt * m * (v * Sc * b1 * qe);
+                hpp = dt * m * (v * Cc * q) + y1y * dt * v * Sc;
+                Hpv = dt * m * (Sc * q) - y1y * dt * Cc;
+                Hpd = dt * m * (v * Cc * b1 * q) + y1y * dt * v * Sc * b1;
+                Hvd = dt * m * (Sc * b1 * q) - y1y * dt * Cc * b1 - y1p * c.dtLb * e.cb * b1;
+                hdd = dt * m * (v * q * (Cc * b1 * b1 + Sc * b2)) - y1y * dt * v * (-Sc * b1 * b1 + Cc * b2)
+                      - y1p * (c.dtLb * v) * (e.cb * b2 - e.sb * b1 * b1);
+            } else if (isU) {
                 const double v = L.sv, dt = c.dt;
                 const double e1 = y1x * e.cs + y1y * e.sn;
                 const double e2 = y1x * e.sn - y1y * e.cs;
@@ -718,6 +833,7 @@ struct TeamSolver {
             }
             const double s2 = 2.0 * sigma;
             Hxx = s2 * wx() + dw; Hyy = s2 * wy() + dw; Hpp = s2 * wp() + hpp + dw; Hvv = s2 * wv() + Sv + dw;
+            if (MODEL) { Hxx += hss; Hyy += hee; }
             if (isU) {
                 if (k >= 1) { Ca = s2 * c.w[4]; Cd = s2 * c.w[5]; }
                 if (isR) { Ca += SrW[1]; Cd += SrW[0]; }
@@ -736,16 +852,27 @@ struct TeamSolver {
             gud += wrow[0] - ((k + 1 < N) ? wn0 : 0.0);
         }
         if (!isS) return;
+        if (MODEL && (req == 0 || req == 1)) {
+            sts2(sm, r + SO(SD_CS), J.a00, 0.0); sts(sm, r + SO(SD_CS + 2), J.a20);
+            sts2(sm, r + SO(SD_CE), J.a01, isU ? 1.0 : 0.0); sts(sm, r + SO(SD_CE + 2), J.a21);
+            sts2(sm, r + SO(SD_CF + 0), J.a02, J.a12); sts(sm, r + SO(SD_CF + 2), J.a22);
+            sts2(sm, r + SO(SD_CF + 4), J.a03, J.a13); sts2(sm, r + SO(SD_CF + 6), J.a23, isU ? 1.0 : 0.0);
+            sts(sm, r + SO(SD_CF + 11), isU ? c.dt : 0.0);
+            sts2(sm, r + SO(SD_CF + 12), J.b0, J.b1); sts(sm, r + SO(SD_CF + 14), J.b2);
+            sts2(sm, r + SO(SD_HSE), Hse, Hsp); sts2(sm, r + SO(SD_HSV), Hsv, Hsd); sts2(sm, r + SO(SD_HEP), Hep, Hev); sts(sm, r + SO(SD_HED), Hed);
+        }
         if (req == 0 || req == 1) {
             const double A02 = isU ? -c.dt * L.sv * e.sn : 0.0, A03 = isU ? c.dt * e.cs : 0.0;
             const double A12 = isU ? c.dt * L.sv * e.cs : 0.0, A13 = isU ? c.dt * e.sn : 0.0;
             const double A23 = isU ? c.dtLb * e.sb : 0.0;
             const double b0 = A02 * e.b1, b1v = A12 * e.b1, b2v = isU ? c.dtLb * L.sv * e.cb * e.b1 : 0.0;
             const double one = isU ? 1.0 : 0.0;
+            if (!MODEL) {
             sts(sm, r + SO(SD_CF + 0), A02); sts(sm, r + SO(SD_CF + 1), A12); sts(sm, r + SO(SD_CF + 2), one);
             sts(sm, r + SO(SD_CF + 4), A03); sts(sm, r + SO(SD_CF + 5), A13); sts(sm, r + SO(SD_CF + 6), A23); sts(sm, r + SO(SD_CF + 7), one);
             sts(sm, r + SO(SD_CF + 11), isU ? c.dt : 0.0);
             sts(sm, r + SO(SD_CF + 12), b0); sts(sm, r + SO(SD_CF + 13), b1v); sts(sm, r + SO(SD_CF + 14), b2v);
+            }
             const bool z = (req == 0);
             ev_load_resid(e);
             sts(sm, r + SO(SD_R + 0), z ? 0.0 : e.rd[0]); sts(sm, r + SO(SD_R + 1), z ? 0.0 : e.rd[1]);
@@ -789,8 +916,9 @@ struct TeamSolver {
         // lane roles: shared-memory offsets of this lane's operands in the three rounds, read from the
         // table mpcb200_create computed once (riccati_roles) and laundered so that they stay in
         // registers through the stage loop instead of being rematerialised at every use
-        int rl[ROLE_STRIDE];
-        ld_roles(c.roles + l * ROLE_STRIDE, rl);
+        int rl[role_stride_of(MODEL)];
+        ld_roles(c.roles + l * role_stride_of(MODEL), rl, role_stride_of(MODEL));
+        const int a2_p = MODEL ? launder(rl[MODEL ? 20 : 0]) : 0, a2_m = MODEL ? launder(rl[MODEL ? 21 : 0]) : 0, a2_out = MODEL ? launder(rl[MODEL ? 22 : 0]) : 0;
         const int a_p = launder(rl[0]), a_m = launder(rl[1]), a_ex = launder(rl[2]), a_out = launder(rl[3]);
         const int b_m = launder(rl[4]), b_mk = launder(rl[5]), b_t = launder(rl[6]), b_x = launder(rl[7]), b_h = launder(rl[8]);
         const int b_o1 = launder(rl[9]), b_o2 = launder(rl[10]);
@@ -798,7 +926,7 @@ struct TeamSolver {
         int e_k0 = launder(rl[16]), e_k1 = launder(rl[17]);
         const int kstep = launder(rl[18]);
         {   // terminal cost-to-go from record N
-            const int rN = SO(W_SD + N * SDS);
+            const int rN = SO(W_SD + N * SDSZ);
             for (int e = l; e < 36; e += 32) {
                 const int i = e / 6, j = e - 6 * i;
                 double v = 0.0;
@@ -809,7 +937,7 @@ struct TeamSolver {
         }
         syncwarp();
         bool ok = true;
-        int so = SO((N - 1) * SDS);   // byte offset of the current stage's record relative to record 0
+        int so = SO((N - 1) * SDSZ);   // byte offset of the current stage's record relative to record 0
         for (int s = N - 1; s >= 0; s--) {
             {   // ---- Round A
                 const d2 p0 = lds2(sm, a_p), p1 = lds2(sm, a_p + SO(2));
@@ -819,6 +947,12 @@ struct TeamSolver {
                 const double t0 = p0.x * m0.x + p0.y * m0.y;
                 const double t1 = p1.x * m1.x + p1.y * m1.y + ex;
                 sts(sm, a_out, t0 + t1);
+                if (MODEL) {   // second task: columns s | e_y of P M (lanes 0..11; the others write the sink)
+                    const d2 u0 = lds2(sm, a2_p), u1 = lds2(sm, a2_p + SO(2));
+                    const int m2 = a2_m + so;
+                    const d2 w0 = lds2(sm, m2), w1 = lds2(sm, m2 + SO(2));
+                    sts(sm, a2_out, (u0.x * w0.x + u0.y * w0.y) + (u1.x * w1.x + u1.y * w1.y));
+                }
             }
             syncwarp();
             {   // ---- Round B
@@ -852,7 +986,7 @@ struct TeamSolver {
                 sts(sm, e_o1, o); sts(sm, e_o2, o);
             }
             syncwarp();
-            so -= SO(SDS); e_k0 -= kstep; e_k1 -= kstep;
+            so -= SO(SDSZ); e_k0 -= kstep; e_k1 -= kstep;
         }
         return ok;
     }
@@ -862,10 +996,10 @@ struct TeamSolver {
     // stage's step straight into that stage's per-thread fields.
     MPC_DEV void riccati_forward() {
         if (lane_id() < 8 && (W == 1 || (k >> 5) == 0)) {
-            int kp = SO(W_SD + (N + 1) * SDS);
+            int kp = SO(W_SD + (N + 1) * SDSZ);
             int r = SO(W_SD);
-            int fa = SO(lf_offset(N) + G_DX_OFF * (N + 2));   // step group of stage 0
-            const d2 i01 = lds2(sm, SO(W_SD + N * SDS + SD_R)), i23 = lds2(sm, SO(W_SD + N * SDS + SD_R + 2));  // ds_0
+            int fa = SO(lf_offset(N, MODEL) + G_DX_OFF * (N + 2));   // step group of stage 0
+            const d2 i01 = lds2(sm, SO(W_SD + N * SDSZ + SD_R)), i23 = lds2(sm, SO(W_SD + N * SDSZ + SD_R + 2));  // ds_0
             double s0 = i01.x, s1 = i01.y, s2 = i23.x, s3 = i23.y;
             double pa = 0.0, pd = 0.0;
             for (int s = 0; s < N; s++) {
@@ -879,12 +1013,19 @@ struct TeamSolver {
                 const double ua = ((ka2.x * pa + ka2.y * pd) + kx.x) + ((ka0.x * s0 + ka0.y * s1) + (ka1.x * s2 + ka1.y * s3));
                 const double ud = ((kd1.y * pa + kd2.x * pd) + kd2.y) + ((kx.y * s0 + kd0.x * s1) + (kd0.y * s2 + kd1.x * s3));
                 sts2(sm, fa, s0, s1); sts2(sm, fa + SO(2), s2, s3); sts2(sm, fa + SO(4), ua, ud);
-                const double n0 = ((s0 + r01.x) + (cp.x * s2 + cv.x * s3)) + cd.x * ud;
-                const double n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
-                const double n2 = ((s2 + r23.x) + a23 * s3) + b2 * ud;
+                double n0 = ((s0 + r01.x) + (cp.x * s2 + cv.x * s3)) + cd.x * ud;
+                double n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
+                double n2 = ((s2 + r23.x) + a23 * s3) + b2 * ud;
                 const double n3 = (s3 + r23.y) + c.dt * ua;
+                if (MODEL) {   // dense s and e_y columns; the unit parts are in the record
+                    const double a00 = lds(sm, r + SO(SD_CS)), a20 = lds(sm, r + SO(SD_CS + 2));
+                    const double a01 = lds(sm, r + SO(SD_CE)), a21 = lds(sm, r + SO(SD_CE + 2)), a22 = lds(sm, r + SO(SD_CF + 2));
+                    n0 = (r01.x + (a00 * s0 + a01 * s1)) + ((cp.x * s2 + cv.x * s3) + cd.x * ud);
+                    n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
+                    n2 = (r23.x + (a20 * s0 + a21 * s1)) + ((a22 * s2 + a23 * s3) + b2 * ud);
+                }
                 s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
-                kp += SO(KST_STRIDE); r += SO(SDS); fa += SO(G_DX_STRIDE);
+                kp += SO(KST_STRIDE); r += SO(SDSZ); fa += SO(G_DX_STRIDE);
             }
             sts2(sm, fa, s0, s1); sts2(sm, fa + SO(2), s2, s3); sts2(sm, fa + SO(4), 0.0, 0.0);
         }
@@ -905,6 +1046,45 @@ struct TeamSolver {
             lp = -(lds(sm, r + SO(SD_HPP)) * D.dsp + hpv * D.dsv + lds(sm, r + SO(SD_HPD)) * D.dud + lds(sm, r + SO(SD_GX + 2)));
             lv = -(hpv * D.dsp + lds(sm, r + SO(SD_HVV)) * D.dsv + lds(sm, r + SO(SD_HVD)) * D.dud + lds(sm, r + SO(SD_GX + 3)));
         }
+        double prv[2];
+        if (MODEL) {
+            // the s and e_y columns of A are dense: no suffix sums; costate recursion  lambda_k = l_k + A_k' lambda_{k+1}
+            // run serially by one thread, in place, through the multiplier group
+            if (isS) {
+                const d2 h0 = lds2(sm, r + SO(SD_HSE)), h1 = lds2(sm, r + SO(SD_HSV)), h2 = lds2(sm, r + SO(SD_HEP));
+                const double hed = lds(sm, r + SO(SD_HED));
+                lx -= h0.x * D.dsy + h0.y * D.dsp + h1.x * D.dsv + h1.y * D.dud;
+                ly -= h0.x * D.dsx + h2.x * D.dsp + h2.y * D.dsv + hed * D.dud;
+                lp -= h0.y * D.dsx + h2.x * D.dsy;
+                lv -= h1.x * D.dsx + h2.y * D.dsy;
+            }
+            D.nyx = lx; D.nyy = ly; D.nyp = lp; D.nyv = lv; D.nyd[0] = D.nyd[1] = 0.0;
+            st_dy(D);
+            tsync();
+            if (k == 0) {
+                int ya = SO(lf_offset(N, MODEL) + G_DY_OFF * (N + 2)) + N * SO(G_DY_STRIDE);   // multiplier group of stage N
+                int rr = SO(W_SD + (N - 1) * SDSZ);
+                d2 y01 = lds2(sm, ya), y23 = lds2(sm, ya + SO(2));
+                for (int s = N - 1; s >= 0; s--) {
+                    ya -= SO(G_DY_STRIDE);
+                    const d2 l01 = lds2(sm, ya), l23 = lds2(sm, ya + SO(2));
+                    const double a00 = lds(sm, rr + SO(SD_CS)), a20 = lds(sm, rr + SO(SD_CS + 2));
+                    const double a01 = lds(sm, rr + SO(SD_CE)), a21 = lds(sm, rr + SO(SD_CE + 2));
+                    const d2 cp = lds2(sm, rr + SO(SD_CF + 0)), cv = lds2(sm, rr + SO(SD_CF + 4));
+                    const double a22 = lds(sm, rr + SO(SD_CF + 2)), a23 = lds(sm, rr + SO(SD_CF + 6));
+                    const double m0 = l01.x + (a00 * y01.x + a20 * y23.x);
+                    const double m1 = l01.y + ((a01 * y01.x + y01.y) + a21 * y23.x);
+                    const double m2 = l23.x + ((cp.x * y01.x + cp.y * y01.y) + a22 * y23.x);
+                    const double m3 = l23.y + ((cv.x * y01.x + cv.y * y01.y) + (a23 * y23.x + y23.y));
+                    y01.x = m0; y01.y = m1; y23.x = m2; y23.y = m3;
+                    sts2(sm, ya, m0, m1); sts2(sm, ya + SO(2), m2, m3);
+                    rr -= SO(SDSZ);
+                }
+            }
+            tsync();
+            ld_dy(D);
+            { const double du[2] = {D.dua, D.dud}; xprev<2>(du, prv); }
+        } else {
         const double hasn = isU ? 1.0 : 0.0;
         const d2 c0 = lds2(sm, r + SO(SD_CF + 0)), c1 = lds2(sm, r + SO(SD_CF + 4));   // (A02, A12), (A03, A13)
         const double A23 = lds(sm, r + SO(SD_CF + 6));
@@ -916,11 +1096,12 @@ struct TeamSolver {
         double t1 = lp + hasn * (c0.x * nx1 + c0.y * ny1);
         tsuffix<1>(&t1);
         D.nyp = t1;
-        double np1, prv[2];
+        double np1;
         { const double du[2] = {D.dua, D.dud}; xchg<1, 2, false>(&t1, &np1, du, prv); }
         t1 = lv + hasn * (c1.x * nx1 + c1.y * ny1 + A23 * np1);
         tsuffix<1>(&t1);
         D.nyv = t1;
+        }
         const double pa = prv[0], pd = prv[1];
         D.drs[0] = D.drs[1] = 0.0; D.nyd[0] = D.nyd[1] = 0.0;
         if (isR) {
@@ -967,7 +1148,9 @@ struct TeamSolver {
             RolloutConsts rc;
             rc.dt = c.dt; rc.dtc = c.dtc; rc.dtLb = c.dtLb; rc.rfrac = c.rfrac; rc.vmin = c.vmin; rc.vmax = c.vmax;
             rc.amax = c.amax; rc.smax = c.smax; rc.admax = c.admax; rc.sdmax = c.sdmax;
-            rollout_core(sm, SO(lf_offset(N) + G_DX_OFF * (N + 2)), SO(W_CONST), N, rc);
+            rc.model = MODEL; rc.kp[0] = rc.kp[1] = rc.kp[2] = rc.kp[3] = 0.0;
+            if (MODEL) { const int a = grp(G_REF_OFF, 4); rc.kp[0] = lds(sm, a); rc.kp[1] = lds(sm, a + SO(1)); rc.kp[2] = lds(sm, a + SO(2)); rc.kp[3] = lds(sm, a + SO(3)); }
+            rollout_core(sm, SO(lf_offset(N, MODEL) + G_DX_OFF * (N + 2)), SO(W_CONST), N, rc);
         }
         tsync();
         if (isS) {
@@ -1276,13 +1459,22 @@ struct TeamSolver {
                     { const double y[6] = {L.yx, L.yy, L.yp, L.yv, L.ryd[0], L.ryd[1]}; xnext<6>(y, y1); }
                     const double y1x = y1[0], y1y = y1[1], y1p = y1[2], y1v = y1[3], yd1_0 = y1[4], yd1_1 = y1[5];
                     const double hn = isU ? 1.0 : 0.0;
-                    const double glx = gx + L.yx - hn * y1x;
-                    const double gly = gy + L.yy - hn * y1y;
-                    const double glp = gp + L.yp - hn * (A02 * y1x + A12 * y1y + y1p);
-                    const double glv = gv + L.yv - hn * (A03 * y1x + A13 * y1y + A23 * y1p + y1v) - Z.zvL + Z.zvU;
+                    double glx = gx + L.yx - hn * y1x;
+                    double gly = gy + L.yy - hn * y1y;
+                    double glp = gp + L.yp - hn * (A02 * y1x + A12 * y1y + y1p);
+                    double glv = gv + L.yv - hn * (A03 * y1x + A13 * y1y + A23 * y1p + y1v) - Z.zvL + Z.zvU;
+                    double jd = b0 * y1x + b1v * y1y + b2v * y1p;
+                    if (MODEL) {
+                        const FJac J = frenet_jac(e);
+                        glx = gx + L.yx - (J.a00 * y1x + J.a20 * y1p);
+                        gly = gy + L.yy - (J.a01 * y1x + hn * y1y + J.a21 * y1p);
+                        glp = gp + L.yp - (J.a02 * y1x + J.a12 * y1y + J.a22 * y1p);
+                        glv = gv + L.yv - (J.a03 * y1x + J.a13 * y1y + J.a23 * y1p + hn * y1v) - Z.zvL + Z.zvU;
+                        jd = J.b0 * y1x + J.b1 * y1y + J.b2 * y1p;
+                    }
                     const double nd0 = (k + 1 < N) ? yd1_0 : 0.0, nd1 = (k + 1 < N) ? yd1_1 : 0.0;
                     const double gla = ga - hn * c.dt * y1v + (L.ryd[1] - nd1) - Z.zaL + Z.zaU;
-                    const double gld = gd - hn * (b0 * y1x + b1v * y1y + b2v * y1p) + (L.ryd[0] - nd0) - Z.zdL + Z.zdU;
+                    const double gld = gd - hn * jd + (L.ryd[0] - nd0) - Z.zdL + Z.zdU;
                     di = dmax_(dmax_(fabs(glx), fabs(gly)), dmax_(fabs(glp), fabs(glv)));
                     di = dmax_(di, dmax_(fabs(gla), fabs(gld)));
                     di = dmax_(di, dmax_(fabs(-L.ryd[0] - Z.rvL[0] + Z.rvU[0]), fabs(-L.ryd[1] - Z.rvL[1] + Z.rvU[1])));
@@ -1526,12 +1718,17 @@ struct RefGen {
     int* stop;              // [B] or null: stop_cmd of get_waypoints
 };
 
-template <int W>
+// MODEL 1 (Frenet-frame variant): io.state = (s, e_y, e_psi, v), io.ref = [B][4] curvature polynomial (highest degree
+// first), traj / warm = s, e_y, v, e_psi, d_f, acc (get_solver_results of MKZMPCPathFollowerFrenet.jl:188-206)
+template <int W, int MODEL = 0>
 MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, const RefGen& rg, long b, smem_t smem) {
-    TeamSolver<W> S(cfg, smem);
+    TeamSolver<W, MODEL> S(cfg, smem);
     const int k = S.k, N = cfg.N;
     const long nr = 3L * (N + 1), nt = 6L * N + 4;
-    if (W == 1 && rg.path_of) {
+    if (MODEL) {
+        const double* kp = io.ref + 4 * b;
+        S.set_kpoly(kp[0], kp[1], kp[2], kp[3]);
+    } else if (W == 1 && rg.path_of) {
         // ---- waypoints from the path table: nearest sample to (X, Y), then interpolation and heading unwrap
         double xr, yr, pr;
         const bool sc = get_waypoints_warp(rg.paths[rg.path_of[b]], N, cfg.dt, io.state[4 * b], io.state[4 * b + 1], io.state[4 * b + 2],

@@ -64,9 +64,9 @@ MPC_DEV void sts(smem_t b, int off, double v) { asm volatile("st.shared.f64 [%0]
 MPC_DEV void sts2(smem_t b, int off, double x, double y) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(b + off), "d"(x), "d"(y) : "memory"); }
 MPC_DEV int launder(int v) { int r; asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v)); return r; }
 // one lane's row of the role table (20 ints, 16-byte aligned) through the read-only path
-MPC_DEV void ld_roles(const int* p, int* out) {
+MPC_DEV void ld_roles(const int* p, int* out, int n = 20) {
     const int4* q = reinterpret_cast<const int4*>(p);
-    for (int i = 0; i < 5; i++) { const int4 v = __ldg(q + i); out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w; }
+    for (int i = 0; i < n / 4; i++) { const int4 v = __ldg(q + i); out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w; }
 }
 }  // namespace mpcb200
 #endif

@@ -73,6 +73,25 @@ def solve_batch(kcfg, state, ref, v_des, u_prev, warm=None, want_traj=False):
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
 
 
+def solve_batch_frenet(kcfg, state, kpoly, v_des, u_prev, warm=None, want_traj=False):
+    lib = C.CDLL(build())
+    assert lib.emu_kcfg_size() == C.sizeof(KCfg)
+    B = state.shape[0]
+    N = kcfg.N
+    dp = C.POINTER(C.c_double)
+    p = lambda a: None if a is None else a.ctypes.data_as(dp)
+    state = np.ascontiguousarray(state, dtype=np.float64); kpoly = np.ascontiguousarray(kpoly, dtype=np.float64)
+    u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+    v_des = None if v_des is None else np.ascontiguousarray(v_des, dtype=np.float64)
+    u0 = np.empty((B, 2)); cost = np.empty(B); status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
+    traj = np.empty((B, 6 * N + 4)) if want_traj else None
+    lib.emu_solve_batch_frenet.argtypes = [C.POINTER(KCfg), C.c_long, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp]
+    rc = lib.emu_solve_batch_frenet(C.byref(kcfg), B, p(state), p(kpoly), p(v_des), p(u_prev), p(warm), p(u0), p(cost),
+                                    status.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)), p(traj))
+    assert rc == 0
+    return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+
 def rollout(kcfg, traj_table, pose0, T, track_using_time=True, target_vel=1.0):
     """All vehicles on the path whose (n,7) table is given.  Returns log (T,B,8), final (B,8)."""
     lib = C.CDLL(build())

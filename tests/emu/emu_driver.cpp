@@ -47,11 +47,11 @@ using namespace mpcb200;
 
 // benign words of one team's shared memory: the sink of inactive lanes and, in every per-thread
 // state group, the slot shared by the threads that own no stage
-static void register_benign(double* team, int N) {
+static void register_benign(double* team, int N, int model = 0) {
     emu::race_benign(team + W_DUMMY, 1, 2);
     const int go[6] = {G_EV_OFF, G_REF_OFF, G_DX_OFF, G_DRS_OFF, G_DY_OFF, G_Z_OFF};
-    const int gs[6] = {G_EV_STRIDE, G_REF_STRIDE, G_DX_STRIDE, G_DRS_STRIDE, G_DY_STRIDE, G_Z_STRIDE};
-    for (int g = 0; g < 6; g++) emu::race_benign(team + lf_offset(N) + go[g] * (N + 2) + gs[g] * (N + 1), 1, gs[g]);
+    const int gs[6] = {G_EV_STRIDE, model ? 4 : G_REF_STRIDE, G_DX_STRIDE, G_DRS_STRIDE, G_DY_STRIDE, G_Z_STRIDE};
+    for (int g = 0; g < 6; g++) emu::race_benign(team + lf_offset(N, model) + go[g] * (N + 2) + gs[g] * (N + 1), 1, gs[g]);
 }
 extern "C" long emu_race_count() { return emu::RS.races; }
 extern "C" void emu_race_enable(int on) { emu::RS.enabled = on; emu::RS.races = 0; }
@@ -83,6 +83,35 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
         emu::race_reset();
         register_benign(smem, kc.N);
         emu::run_warp(W == 1 ? lane_main<1> : W == 2 ? lane_main<2> : lane_main<3>, &j, W);
+    }
+    return 0;
+}
+static void lane_main_frenet(int, void* a) {
+    Job* j = (Job*)a;
+    TeamSolver<1, 1>::init_work(j->smem, j->cfg->N);
+    RefGen rg;
+    memset(&rg, 0, sizeof(rg));
+    solve_problem<1, 1>(*j->cfg, *j->io, rg, j->b, j->smem);
+}
+// Frenet-frame variant: ref = [B][4] curvature polynomial
+extern "C" int emu_solve_batch_frenet(const KCfg* cfg, long B, const double* state, const double* kpoly, const double* v_des,
+                                      const double* u_prev, double* warm, double* u0, double* cost, int* status, int* iters,
+                                      double* traj) {
+    BatchPtrs io{state, kpoly, v_des, u_prev, warm, u0, cost, status, iters, traj};
+    KCfg kc = *cfg;
+    if (kc.N > 31) return -1;
+    kcfg_finalize(kc);
+    std::vector<int> roles(32 * ROLE_STRIDE_F);
+    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, w_sd_of(1, 1), roles.data() + l * ROLE_STRIDE_F, 1);
+    kc.roles = roles.data();
+    std::vector<double> smem_raw(smem_doubles_per_team(kc.N, 1) + 2, 0.0);
+    double* smem = smem_raw.data();
+    if (((size_t)smem) & 15) smem++;
+    for (long b = 0; b < B; b++) {
+        Job j{&kc, &io, b, smem};
+        emu::race_reset();
+        register_benign(smem, kc.N, 1);
+        emu::run_warp(lane_main_frenet, &j, 1);
     }
     return 0;
 }

@@ -177,5 +177,5 @@ MPC_DEV d2 lds2(smem_t b, int off) { emu::race_check(b + off, false); emu::race_
 MPC_DEV void sts(smem_t b, int off, double v) { emu::race_check(b + off, true, v); b[off] = v; }
 MPC_DEV void sts2(smem_t b, int off, double x, double y) { sts(b, off, x); sts(b, off + 1, y); }
 MPC_DEV int launder(int v) { return v; }
-MPC_DEV void ld_roles(const int* p, int* out) { for (int i = 0; i < 20; i++) out[i] = p[i]; }
+MPC_DEV void ld_roles(const int* p, int* out, int n = 20) { for (int i = 0; i < n; i++) out[i] = p[i]; }
 }  // namespace mpcb200

@@ -1,0 +1,157 @@
+"""Frenet-frame variant (scripts/mpc_utils/MKZMPCPathFollowerFrenet.jl): oracle NLP restatement
+(finite-difference checks of the analytic derivatives), the curvature-polynomial fit of
+scripts/sim_path_utils/nav_msgs_path_frenet.py, and the CUDA solver's source on the CPU warp emulator against
+the oracle, iterate for iterate.  The -m gpu tests of the same path are in test_gpu_parity.py."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from mkz_mpc_path_follower_b200 import frenet_ref, workload as W
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("N", [4, 7])
+def test_frenet_derivatives_fd(oracle, N):
+    """Jacobian and Lagrangian Hessian of the Frenet stage map (:111-120) against central differences."""
+    rng = np.random.default_rng(11)
+    cfg = oracle.default_cfg_frenet(N, weights=[0, 9, 10, 0.5, 100, 1000, 0.3, 0.7])
+    for i, v in enumerate([2e-5, -3e-4, 2e-3, 0.02]):
+        cfg.kpoly[i] = v
+    L = oracle.lib()
+    n, mc, md = 6 * N + 4, 4 * N + 4, 2 * (N - 1)
+    z = rng.normal(size=n)
+    for k in range(N + 1):
+        z[6 * k:6 * k + 4] = [rng.uniform(0, 20), rng.uniform(-1, 1), rng.uniform(-0.5, 0.5), rng.uniform(0.5, 15)]
+        if k < N:
+            z[6 * k + 4:6 * k + 6] = [rng.uniform(-1, 1), rng.uniform(-0.5, 0.5)]
+    state = rng.normal(size=4); yc = rng.normal(size=mc)
+
+    def c(zz):
+        o = np.empty(mc); L.mpc_oracle_eval_c(C.byref(cfg), _p(state), _p(zz), _p(o)); return o
+
+    def jac(zz):
+        J1 = np.empty((mc, n)); J2 = np.empty((md, n)); L.mpc_oracle_eval_jac(C.byref(cfg), _p(zz), _p(J1), _p(J2)); return J1
+
+    H = np.empty((n, n)); L.mpc_oracle_eval_hess(C.byref(cfg), _p(z), 0.0, _p(yc), _p(H))
+    J = jac(z); h = 1e-6
+    Jfd = np.empty((mc, n)); Hfd = np.empty((n, n))
+    for i in range(n):
+        e = np.zeros(n); e[i] = h
+        Jfd[:, i] = (c(z + e) - c(z - e)) / (2 * h)
+        Hfd[:, i] = (jac(z + e).T @ yc - jac(z - e).T @ yc) / (2 * h)
+    assert np.abs(J - Jfd).max() <= 1e-7
+    assert np.abs(H - Hfd).max() <= 1e-7 and np.abs(H - H.T).max() == 0.0
+    assert np.abs(H).max() > 0.1    # the test is not vacuous
+    # the stage map itself, against the formulas of the reference written out in numpy
+    k0, k1, k2, k3 = (cfg.kpoly[i] for i in range(4))
+    s, ey, ep, v, a, d = z[0:6]
+    K = k0 * s ** 3 + k1 * s ** 2 + k2 * s + k3
+    bta = np.arctan(cfg.L_b / (cfg.L_a + cfg.L_b) * np.tan(d))
+    dsdt = v * np.cos(ep + bta) / (1 - ey * K)
+    nxt = np.array([s + 0.2 * dsdt, ey + 0.2 * v * np.sin(ep + bta), ep + 0.2 * (v / cfg.L_b * np.sin(bta) - dsdt * K), v + 0.2 * a])
+    assert np.abs((z[6:10] - nxt) - c(z)[4:8]).max() <= 1e-13
+
+
+def test_frenet_reference_fit():
+    """get_reference_frenet (nav_msgs_path_frenet.py:76-86): an arc of radius 100 m gives K = 1/100 (a cubic X(s), Y(s) cannot follow much tighter arcs over 40 m) and the
+    start heading; the batched form used by the workload is the same arithmetic."""
+    R, th0 = 100.0, 0.3
+    s = np.arange(0.0, 40.0, 0.8)
+    x = R * (np.sin(th0 + s / R) - np.sin(th0)); y = -R * (np.cos(th0 + s / R) - np.cos(th0))
+    K, psi0, xi, yi = frenet_ref.get_reference_frenet({"x": x, "y": y, "s": s})
+    sq = np.linspace(0, 35, 8)
+    assert np.abs(np.polyval(K, sq) - 1.0 / R).max() <= 5e-4
+    assert abs(psi0 - th0) <= 0.02
+    s_fit = np.arange(0.0, s[-1], 0.5)
+    Kb, pb = frenet_ref.fit_windows(np.interp(s_fit, s, x)[None], np.interp(s_fit, s, y)[None], s[-1])
+    assert np.allclose(Kb[0], K, rtol=1e-9, atol=1e-12) and abs(pb[0] - psi0) <= 1e-12
+
+
+def _stress_batch(B, N, seed):
+    """Tighter curves and larger offsets than the recorded paths give: K up to ~0.05 1/m varying along s."""
+    rng = np.random.default_rng(seed)
+    b = W.make_frenet_batch(B, N)
+    b["kpoly"] = np.stack([rng.uniform(-2e-6, 2e-6, B), rng.uniform(-1e-4, 1e-4, B), rng.uniform(-2e-3, 2e-3, B),
+                           rng.uniform(-0.05, 0.05, B)], axis=1)
+    b["state"][:, 1] = rng.uniform(-1.0, 1.0, B)
+    b["state"][:, 2] = rng.uniform(-0.3, 0.3, B)
+    return b
+
+
+@pytest.mark.parametrize("N,B,stress", [(8, 16, False), (20, 10, False), (3, 6, False), (31, 3, False), (8, 12, True), (20, 8, True)])
+def test_emulated_frenet_kernel_matches_oracle(oracle, N, B, stress):
+    import emu as E
+    E.race_check(True)
+    cfg = oracle.default_cfg_frenet(N)
+    b = _stress_batch(B, N, 5) if stress else W.make_frenet_batch(B, N)
+    o = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], want_traj=True, n_threads=4)
+    e = E.solve_batch_frenet(E.kcfg_from_oracle(cfg), b["state"], b["kpoly"], b["v_des"], b["u_prev"], want_traj=True)
+    assert E.race_count() == 0
+    assert (o["status"] == e["status"]).all() and (o["iters"] == e["iters"]).all()
+    ok = o["status"] == 0
+    assert ok.sum() >= B - 1
+    assert np.abs(o["u0"] - e["u0"])[ok].max() <= 1e-9
+    assert (np.abs(o["cost"] - e["cost"])[ok] <= 1e-9 * np.maximum(1, np.abs(o["cost"][ok]))).all()
+    assert np.abs(o["traj"] - e["traj"])[ok].max() <= 1e-8
+    # warm start from the solution: a handful of iterations, same point
+    wo, we = o["traj"].copy(), o["traj"].copy()
+    o2 = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], warm=wo, n_threads=4)
+    e2 = E.solve_batch_frenet(E.kcfg_from_oracle(cfg), b["state"], b["kpoly"], b["v_des"], b["u_prev"], warm=we)
+    assert (o2["status"] == e2["status"]).all() and (o2["iters"] == e2["iters"]).all()
+    assert np.abs(o2["u0"] - e2["u0"])[o2["status"] == 0].max() <= 1e-9
+    assert np.abs(o2["u0"] - o["u0"])[ok & (o2["status"] == 0)].max() <= 1e-6
+
+
+def test_emulated_frenet_rollout_start(oracle):
+    """MPCB200_START_ROLLOUT for the Frenet variant: the rollout uses the Frenet stage map."""
+    import emu as E
+    N, B = 8, 6
+    cfg = oracle.default_cfg_frenet(N)
+    b = _stress_batch(B, N, 9)
+    e = E.solve_batch_frenet(E.kcfg_from_oracle(cfg, start_mode=1), b["state"], b["kpoly"], b["v_des"], b["u_prev"])
+    o = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], n_threads=4)
+    both = (o["status"] == 0) & (e["status"] == 0)
+    assert both.sum() >= B - 1
+    assert np.abs(o["u0"] - e["u0"])[both].max() <= 1e-5   # two start points, one optimum
+
+
+def test_frenet_kkt_of_oracle_solutions(oracle):
+    """The returned points satisfy the KKT conditions of the unscaled Frenet NLP (intrinsic check; parity unpinned)."""
+    N, B = 8, 12
+    cfg = oracle.default_cfg_frenet(N)
+    b = _stress_batch(B, N, 3)
+    o = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], want_traj=True, n_threads=4)
+    L = oracle.lib()
+    n, mc, md = 6 * N + 4, 4 * N + 4, 2 * (N - 1)
+    zero_ref = np.zeros(3 * (N + 1))
+    for j in np.nonzero(o["status"] == 0)[0]:
+        for i in range(4):
+            cfg.kpoly[i] = b["kpoly"][j, i]
+        z = np.empty(n); L.mpc_oracle_traj_to_z(C.byref(cfg), _p(np.ascontiguousarray(o["traj"][j])), _p(z))
+        cv = np.empty(mc); L.mpc_oracle_eval_c(C.byref(cfg), _p(np.ascontiguousarray(b["state"][j])), _p(z), _p(cv))
+        assert np.abs(cv).max() <= 1e-7
+        g = np.empty(n); L.mpc_oracle_eval_grad_f(C.byref(cfg), _p(zero_ref), float(b["v_des"][j]), _p(z), _p(g))
+        Jc = np.empty((mc, n)); Jd = np.empty((md, n)); L.mpc_oracle_eval_jac(C.byref(cfg), _p(z), _p(Jc), _p(Jd))
+        # stationarity in the variables that are strictly inside their bounds and off the rate rows' limits:
+        # project the gradient onto the null space of the active constraints
+        d = np.empty(md); L.mpc_oracle_eval_d(C.byref(cfg), _p(np.ascontiguousarray(b["u_prev"][j])), _p(z), _p(d))
+        lim = np.array([(cfg.steer_dmax if r % 2 == 0 else cfg.a_dmax) * (cfg.dt_control if r < 2 else cfg.dt) for r in range(md)])
+        act_rows = np.abs(np.abs(d) - lim) <= 1e-6
+        lo = np.full(n, -np.inf); hi = np.full(n, np.inf)
+        for k in range(N + 1):
+            lo[6 * k + 3], hi[6 * k + 3] = cfg.v_min, cfg.v_max
+            if k < N:
+                lo[6 * k + 4], hi[6 * k + 4] = -cfg.a_max, cfg.a_max
+                lo[6 * k + 5], hi[6 * k + 5] = -cfg.steer_max, cfg.steer_max
+        act_b = (z - lo <= 1e-6) | (hi - z <= 1e-6)
+        A = np.vstack([Jc, Jd[act_rows], np.eye(n)[act_b]])
+        lam = np.linalg.lstsq(A.T, -g, rcond=None)[0]
+        assert np.abs(g + A.T @ lam).max() <= 1e-5 * max(1.0, np.abs(g).max())

@@ -451,3 +451,86 @@ def test_monte_carlo_rollout_properties(capi):
     for p in range(3):
         err = closed_loop.path_errors(out["log"][30:, path_of == p, :], trajs[p].trajectory)
         assert np.quantile(err, 0.99) < 1.0
+
+
+# ---- Frenet-frame variant (scripts/mpc_utils/MKZMPCPathFollowerFrenet.jl) ----
+def _frenet_stress(b, seed):
+    rng = np.random.default_rng(seed)
+    B = b["state"].shape[0]
+    b["kpoly"] = np.stack([rng.uniform(-2e-6, 2e-6, B), rng.uniform(-1e-4, 1e-4, B), rng.uniform(-2e-3, 2e-3, B),
+                           rng.uniform(-0.05, 0.05, B)], axis=1)
+    b["state"][:, 1] = rng.uniform(-1.0, 1.0, B)
+    b["state"][:, 2] = rng.uniform(-0.3, 0.3, B)
+    return b
+
+
+@pytest.mark.parametrize("N,B,stress", [(8, 512, False), (20, 384, False), (3, 32, False), (31, 32, False), (8, 256, True), (20, 256, True)])
+def test_frenet_cold_and_warm_parity(capi, oracle, N, B, stress):
+    s = capi.FrenetSolver(N)
+    b = W.make_frenet_batch(B, N)
+    if stress:
+        b = _frenet_stress(b, 17)
+    ocfg = oracle.default_cfg_frenet(N, tol=s.cfg.tol, max_iter=s.cfg.max_iter)
+    g = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    o = oracle.solve_batch_frenet(ocfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], want_traj=True, n_threads=8)
+    ok = _compare(g, o, min_conv=0.95)
+    assert (g["iters"] == o["iters"])[ok].mean() >= 0.98          # iterate for iterate
+    assert np.abs(g["traj"] - o["traj"])[ok].max() <= 1e-5
+    assert s.stats()["kernel_launches"] == 1
+    wg, wo = g["traj"].copy(), g["traj"].copy()
+    g2 = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"], warm=wg)
+    o2 = oracle.solve_batch_frenet(ocfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], warm=wo, n_threads=8)
+    _compare(g2, o2, min_conv=0.95)
+    assert np.abs(wg - wo)[(g2["status"] == 0) & (o2["status"] == 0)].max() <= 1e-5
+    assert g2["iters"].mean() < g["iters"].mean()
+
+
+def test_frenet_full_size_properties(capi):
+    """65,536 Frenet problems at N = 20: all converge; the returned trajectory satisfies the Frenet dynamics
+    (:117-120), the bounds and the rate rows; solving again from the solution stays there."""
+    N, B = 20, 65536
+    s = capi.FrenetSolver(N)
+    b = W.make_frenet_batch(B, N)
+    g = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    assert (g["status"] == 0).mean() >= 0.9999
+    t = g["traj"]; n1 = N + 1
+    sv, ey, v, ep, df, acc = t[:, :n1], t[:, n1:2 * n1], t[:, 2 * n1:3 * n1], t[:, 3 * n1:4 * n1], t[:, 4 * n1:4 * n1 + N], t[:, 4 * n1 + N:]
+    k = b["kpoly"]
+    K = ((k[:, 0:1] * sv[:, :N] + k[:, 1:2]) * sv[:, :N] + k[:, 2:3]) * sv[:, :N] + k[:, 3:4]
+    bta = np.arctan(1.742 / (1.108 + 1.742) * np.tan(df))
+    dsdt = v[:, :N] * np.cos(ep[:, :N] + bta) / (1.0 - ey[:, :N] * K)
+    okm = g["status"] == 0
+    assert np.abs(sv[:, 1:] - (sv[:, :N] + 0.2 * dsdt))[okm].max() <= 1e-7
+    assert np.abs(ey[:, 1:] - (ey[:, :N] + 0.2 * v[:, :N] * np.sin(ep[:, :N] + bta)))[okm].max() <= 1e-7
+    assert np.abs(ep[:, 1:] - (ep[:, :N] + 0.2 * (v[:, :N] / 1.742 * np.sin(bta) - dsdt * K)))[okm].max() <= 1e-7
+    assert np.abs(v[:, 1:] - (v[:, :N] + 0.2 * acc))[okm].max() <= 1e-7
+    assert np.abs(t[:, [0, n1, 3 * n1, 2 * n1]] - b["state"])[okm].max() <= 1e-7
+    assert np.abs(acc).max() <= 1.0 and np.abs(df).max() <= 0.5 and v.min() >= 0.0 and v.max() <= 20.0
+    assert np.abs(df[:, 0] - b["u_prev"][:, 0])[okm].max() <= 0.05 + 1e-7 and np.abs(acc[:, 0] - b["u_prev"][:, 1])[okm].max() <= 0.15 + 1e-7
+    assert np.abs(np.diff(df[:, 1:], axis=1))[okm].max() <= 0.1 + 1e-7 and np.abs(np.diff(acc[:, 1:], axis=1))[okm].max() <= 0.3 + 1e-7
+    w = t.copy()
+    g2 = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"], warm=w)
+    both = okm & (g2["status"] == 0)
+    assert both.mean() >= 0.9999 and np.abs(g2["u0"] - g["u0"])[both].max() <= 1e-5
+
+
+def test_frenet_module_mirror_and_errors(capi):
+    """The API of MKZMPCPathFollowerFrenet.jl:132-207 as gazebo_sim_mpc_cmd_pub_frenet.jl:125-146 drives it."""
+    from mkz_mpc_path_follower_b200.mpc_path_follower import MKZMPCPathFollowerFrenet
+    kmpc = MKZMPCPathFollowerFrenet(N=8)
+    b = W.make_frenet_batch(1, 8)
+    kmpc.update_cost(9.0, 10.0, 0.5, 100.0, 1000.0, 0.0, 0.0)
+    kmpc.update_init_cond(0.0, 0.0, float(b["state"][0, 2]), float(b["state"][0, 3]))
+    kmpc.update_reference({"x": [0.0]}, b["kpoly"][0], float(b["v_des"][0]))
+    a_opt, df_opt, is_opt = kmpc.solve_model()
+    kmpc.update_current_input(df_opt, a_opt)
+    res = kmpc.get_solver_results()
+    assert is_opt == "Optimal" and len(res) == 8 and res[0].shape == (9,) and res[6].shape == (8,)
+    assert res[7][0] == a_opt and res[6][0] == df_opt and abs(res[2][0] - b["state"][0, 3]) < 1e-7
+    with pytest.raises(TypeError):
+        kmpc.update_reference({}, np.zeros(3), 1.0)
+    with pytest.raises(capi.MpcB200Error):
+        capi.FrenetSolver(40)                     # one warp per problem only
+    s = capi.FrenetSolver(8)
+    with pytest.raises(capi.MpcB200Error):        # the XY entry point refuses a Frenet handle
+        capi.Solver.solve_batch(s, np.zeros((1, 4)), np.zeros((1, 3, 9)), np.zeros((1, 2)))
