@@ -339,6 +339,41 @@ def main():
         "clocks": clocks,
     }
 
+    if N <= 31:
+        # the Frenet-frame variant (MKZMPCPathFollowerFrenet.jl) on the same batch size and horizon, outside the
+        # timed region of the headline metric: device-resident inputs, CUDA events on the shared stream, oracle on a sample
+        try:
+            fb = workload.make_frenet_batch(B, N, b0=rank * B)
+            fs = capi.FrenetSolver(N, device=local)
+            fs.set_stream(stream.cuda_stream)
+            fd = {k_: torch.from_numpy(fb[k_]).to(dev) for k_ in ("state", "kpoly", "u_prev", "v_des")}
+            f_u0 = torch.empty((B, 2), dtype=torch.float64, device=dev); f_st = torch.empty(B, dtype=torch.int32, device=dev)
+            f_it = torch.empty(B, dtype=torch.int32, device=dev)
+            f_ms = []
+            for i in range(3 + args.steps):
+                flush.fill_(1)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fs.solve_batch_device(B, fd["state"], fd["kpoly"], fd["u_prev"], f_u0, v_des=fd["v_des"], status=f_st, iters=f_it)
+                e1.record(stream); torch.cuda.synchronize()
+                if i >= 3:
+                    f_ms.append(e0.elapsed_time(e1))
+            fst = f_st.cpu().numpy(); fit = f_it.cpu().numpy()
+            from oracle import oracle as O
+            n_s = min(B, 512)
+            fo = O.solve_batch_frenet(O.default_cfg_frenet(N, max_iter=int(fs.cfg.max_iter)), fb["state"][:n_s], fb["kpoly"][:n_s],
+                                      fb["v_des"][:n_s], fb["u_prev"][:n_s], n_threads=cores)
+            fok = (fo["status"] == 0) & (fst[:n_s] == 0)
+            line["frenet_variant"] = {
+                "value": float((fst == 0).sum()) / (float(np.mean(f_ms)) * 1e-3), "unit": "solves/s", "kernel": "mpc_solve_frenet_kernel",
+                "kernel_ms": float(np.mean(f_ms)), "converged_frac": float((fst == 0).mean()), "mean_iters": float(fit.mean()),
+                "fp64_tflops": float(fit.astype(np.float64).sum()) * (F_RIC + F_EVAL) * N / (float(np.mean(f_ms)) * 1e-3) / 1e12,
+                "parity_vs_oracle": {"sample": n_s, "status_equal": bool((fo["status"] == fst[:n_s]).all()),
+                                     "max_abs_du": float(np.abs(f_u0.cpu().numpy()[:n_s] - fo["u0"])[fok].max())},
+                "what": "same batch size and horizon, rank 0's slice, all-zero start, workload.make_frenet_batch"}
+        except Exception as ex:   # the headline line must not depend on the variant
+            line["frenet_variant"] = {"error": repr(ex)}
+
     if not args.no_latency:
         # single-solve latency through the C ABI (host buffers, H2D + kernel + D2H), warm-started like the
         # control loop; CPU oracle beside it

@@ -534,3 +534,15 @@ def test_frenet_module_mirror_and_errors(capi):
     s = capi.FrenetSolver(8)
     with pytest.raises(capi.MpcB200Error):        # the XY entry point refuses a Frenet handle
         capi.Solver.solve_batch(s, np.zeros((1, 4)), np.zeros((1, 3, 9)), np.zeros((1, 2)))
+
+
+def test_line_search_failure_at_an_acceptable_point_gpu(capi, oracle):
+    """The straggler of the 4-GPU rollout-start sweep (tests/test_emu_parity.py has the story): returns the
+    point it had reached instead of restoring and running to the cap."""
+    N = 20
+    b = W.make_batch(1, N, b0=131072 + 127164)
+    s = capi.Solver(N, start_mode=capi.START_ROLLOUT)
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=1)   # all-zero start
+    assert g["status"][0] == 0 and g["iters"][0] <= 20
+    assert np.abs(g["u0"] - o["u0"]).max() <= 1e-6 and abs(g["cost"][0] - o["cost"][0]) <= 1e-6 * o["cost"][0]
