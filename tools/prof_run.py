@@ -15,12 +15,15 @@ N = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 warm_mode = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 dev = torch.device("cuda", 0)
-b = workload.make_batch(B, N)
+FRENET = os.environ.get("PROF_MODEL") == "frenet"   # the Frenet-frame variant (mpc_solve_frenet_kernel)
+b = workload.make_frenet_batch(B, N) if FRENET else workload.make_batch(B, N)
+if FRENET:
+    b["ref"] = b["kpoly"]
 if os.environ.get("PROF_SAME"):   # every problem = problem j: all warps run the same instruction stream
     j = int(os.environ["PROF_SAME"])
     for k in ("state", "ref", "u_prev", "v_des"):
         b[k] = np.ascontiguousarray(np.repeat(b[k][j:j + 1], B, axis=0))
-s = capi.Solver(N)
+s = capi.FrenetSolver(N) if FRENET else capi.Solver(N)
 st = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(st)
 s.set_stream(st.cuda_stream)
