@@ -150,7 +150,7 @@ int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T,
  * lane-keep node gazebo_sim_mpc_cmd_pub_frenet.jl:112-153 drives).  Same vehicle constants, horizon, bounds, rate
  * rows and interior-point iteration; states (s, e_y, e_psi, v) with ds/dt = v cos(e_psi + beta) / (1 - e_y K(s)),
  * K(s) a cubic (:111-120); cost on e_y, e_psi, v - v_target and the input terms (:95-101).
- *   mpcb200_create_frenet            replaces module load (:28-129); N <= 31; weights start at (:51-58)
+ *   mpcb200_create_frenet            replaces module load (:28-129); 3 <= N <= 95; weights start at (:51-58)
  *   mpcb200_set_cost_frenet          replaces update_cost(cey, cep, cev, cda, cdd, ca, cd) (:158-169), same order
  *   mpcb200_solve_batch_frenet       replaces, for B problems at once,
  *       update_init_cond(s, ey, epsi, vel) (:132-138)        -> state    [B][4]

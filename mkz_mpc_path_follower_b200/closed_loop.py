@@ -74,3 +74,57 @@ def path_errors(log, traj_table):
         d = (XY[None, :, 0] - log[t, :, 0:1]) ** 2 + (XY[None, :, 1] - log[t, :, 1:2]) ** 2
         err[t] = np.sqrt(d.min(axis=1))
     return err
+
+
+def run_frenet(path_ids, pose0, T, N=8, window=40.0, target_vel=8.0, solver=None, ey_from_path=True):
+    """Closed loop on the Frenet-frame module: the control step of
+    scripts/nodes_gazebo_sim/gazebo_sim_mpc_cmd_pub_frenet.jl:112-153 around the plant of scripts/vehicle_simulator.py
+    (Gazebo, which drives that node in the reference, is out of scope; this is the same loop on the repository's plant).
+
+    Per 10 Hz step: the next `window` metres of the path from the sample nearest to the vehicle, in the vehicle frame
+    (the node's `target_path` message, :90-119) -> K_coeffs, psi_start = get_reference_frenet (:100) ->
+    update_init_cond(0, e_y, -psi_start, v) (:125), update_reference(path, K_coeffs, des_speed) (:126), solve_model
+    (:130), publish the command whatever the status (:139-143), update_current_input(df_opt, a_opt) (:145); every solve
+    starts from the previous solution.  The node passes e_y = 0 (it relies on a path that starts at the vehicle);
+    ey_from_path = True (default) passes the vehicle's lateral offset from the fitted path start instead, which is
+    what makes the loop hold the lane on a recorded path that does not start at the vehicle.
+    Returns dict with log (T,B,8) = x, y, psi, v, acc_cmd, df_cmd, status, iters."""
+    from . import frenet_ref
+    path_ids = np.atleast_1d(np.asarray(path_ids)); pose0 = np.atleast_2d(np.asarray(pose0, dtype=np.float64))
+    B = path_ids.shape[0]
+    own = solver is None
+    if own:
+        solver = capi.FrenetSolver(N)
+    tables = {p: GPSRefTrajectory(mat_filename=int(p), traj_horizon=N, traj_dt=0.2).trajectory for p in sorted(set(path_ids.tolist()))}
+    sim = VehicleSimulator(X0=pose0[:, 0], Y0=pose0[:, 1], Psi0=pose0[:, 2], batch=B)
+    u_curr = np.zeros((B, 2)); warm = np.zeros((B, 6 * N + 4))
+    s_fit = np.arange(0.0, window, 0.5)
+    log = np.zeros((T, B, 8))
+    state = np.zeros((B, 4)); kpoly = np.zeros((B, 4))
+    for t in range(T):
+        for _ in range(10):
+            sim.update_vehicle_model()
+        st = sim.state_est()[:, :4].copy()
+        xw = np.empty((B, s_fit.size)); yw = np.empty_like(xw)
+        for b in range(B):
+            tr = tables[int(path_ids[b])]
+            i = int(np.argmin((tr[:, 4] - st[b, 0]) ** 2 + (tr[:, 5] - st[b, 1]) ** 2))
+            sq = tr[i, 6] + s_fit
+            dx = np.interp(sq, tr[:, 6], tr[:, 4]) - st[b, 0]; dy = np.interp(sq, tr[:, 6], tr[:, 5]) - st[b, 1]
+            c, s_ = np.cos(st[b, 2]), np.sin(st[b, 2])
+            xw[b] = c * dx + s_ * dy; yw[b] = -s_ * dx + c * dy
+        K, psi_start = frenet_ref.fit_windows(xw, yw, window)
+        kpoly[:] = K
+        state[:, 0] = 0.0
+        state[:, 1] = -(-np.sin(psi_start) * xw[:, 0] + np.cos(psi_start) * yw[:, 0]) if ey_from_path else 0.0
+        state[:, 2] = -psi_start
+        state[:, 3] = st[:, 3]
+        out = solver.solve_batch(state, kpoly, u_curr, v_des=np.full(B, float(target_vel)), warm=warm)
+        sim.mpc_cmd(out["u0"][:, 0], out["u0"][:, 1])
+        u_curr[:, 0] = out["u0"][:, 1]; u_curr[:, 1] = out["u0"][:, 0]
+        log[t, :, 0:4] = st
+        log[t, :, 4] = out["u0"][:, 0]; log[t, :, 5] = out["u0"][:, 1]
+        log[t, :, 6] = out["status"]; log[t, :, 7] = out["iters"]
+    if own:
+        solver.close()
+    return {"log": log, "final_state": sim.full_state()}

@@ -67,20 +67,20 @@ mpc_solve_frenet_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, con
 #define MPC_LONG_MIN_BLOCKS2 6
 #define MPC_LONG_MIN_BLOCKS3 2
 #endif
-template <int W>
-__global__ void __launch_bounds__(W * 32, W == 2 ? MPC_LONG_MIN_BLOCKS2 : MPC_LONG_MIN_BLOCKS3)
+template <int W, int MODEL = 0>
+__global__ void __launch_bounds__(W * 32, MODEL ? 2 : (W == 2 ? MPC_LONG_MIN_BLOCKS2 : MPC_LONG_MIN_BLOCKS3))
 mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const long long B, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     __shared__ unsigned long long next_problem;
     const smem_t smem = smem_base(smem_all);
-    TeamSolver<W>::init_work(smem, cfg.N);
+    TeamSolver<W, MODEL>::init_work(smem, cfg.N);
     for (;;) {
         if (threadIdx.x == 0) next_problem = atomicAdd(counter, 1ULL);
         __syncthreads();
         const unsigned long long b = next_problem;
         __syncthreads();
         if (b >= (unsigned long long)B) break;
-        solve_problem<W>(cfg, io, rg, (long)b, smem);
+        solve_problem<W, MODEL>(cfg, io, rg, (long)b, smem);
     }
 }
 
@@ -221,7 +221,6 @@ int mpcb200_create_frenet(mpcb200_handle** out, const mpcb200_config* cfg) { ret
 static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int model) {
     if (!out || !cfg) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: NULL argument");
     *out = nullptr;
-    if (model && cfg->N > 31) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create_frenet: horizon N=%d above 31 (one warp per problem only)", cfg->N);
     if (cfg->N < 3 || cfg->N > 95) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: horizon N=%d outside [3,95]", cfg->N);
     if (!(cfg->dt > 0) || !(cfg->dt_control > 0) || !(cfg->L_b > 0) || !(cfg->v_max > cfg->v_min) || !(cfg->a_max > 0) ||
         !(cfg->steer_max > 0 && cfg->steer_max < 1.5) || !(cfg->a_dmax > 0) || !(cfg->steer_dmax > 0) || !(cfg->tol > 0) ||
@@ -271,7 +270,13 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         TRY_OR_FREE(cudaMalloc((void**)&h->d_roles, sizeof(roles)));
         TRY_OR_FREE(cudaMemcpy(h->d_roles, roles, sizeof(int) * 32 * rs, cudaMemcpyHostToDevice));
     }
-    if (model) {
+    if (model && h->team_warps > 1) {
+        h->smem_bytes = (size_t)smem_doubles_per_team(cfg->N, 1) * sizeof(double);
+        const void* fn = (h->team_warps == 2) ? (const void*)mpc_solve_long_kernel<2, 1> : (const void*)mpc_solve_long_kernel<3, 1>;
+        TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, fn, h->team_warps * 32, h->smem_bytes));
+    } else if (model) {
         h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N, 1) * sizeof(double);
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -336,7 +341,11 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
     long long max_blocks = (long long)h->num_sms * h->blocks_per_sm;
     int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
     if (grid < 1) grid = 1;
-    if (h->model)
+    if (h->model && h->team_warps == 2)
+        mpc_solve_long_kernel<2, 1><<<grid, 64, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
+    else if (h->model && h->team_warps == 3)
+        mpc_solve_long_kernel<3, 1><<<grid, 96, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
+    else if (h->model)
         mpc_solve_frenet_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     else if (h->team_warps == 1)
         mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);

@@ -166,7 +166,7 @@ MPC_HD void kcfg_finalize(KCfg& c) {
 #define SD_HEV 59
 #define SD_HED 60
 #define SDS_F 62
-#define W_TT2 148   // MODEL 1: columns s | e_y of P M (2 x 6); one warp per problem only, records start at 160
+#define W_TT2 148   // MODEL 1: columns s | e_y of P M (2 x 6); the exchange area of multi-warp teams follows at 160
 MPC_HD constexpr int sds_of(int model) { return model ? SDS_F : SDS; }
 #define KST_STRIDE 14
 
@@ -188,7 +188,7 @@ MPC_HD constexpr int sds_of(int model) { return model ? SDS_F : SDS; }
 #define G_Z_STRIDE 10
 #define LF_DOUBLES 42   // per stage slot, all groups
 MPC_HD int team_warps(int N) { return (N + 1 + 31) / 32; }   // warps that share one problem
-MPC_HD constexpr int w_sd_of(int W, int model) { return model ? 160 : W_SD_OF(W); }
+MPC_HD constexpr int w_sd_of(int W, int model) { return model ? 160 + (W > 1 ? XCH_SIZE : 0) : W_SD_OF(W); }   // MODEL 1: exchange area at 160
 MPC_HD int lf_offset(int N, int model = 0) { return w_sd_of(team_warps(N), model) + (N + 1) * sds_of(model) + N * KST_STRIDE; }
 MPC_HD int smem_doubles_per_team(int N, int model = 0) { return lf_offset(N, model) + LF_DOUBLES * (N + 2); }   // even: 16-byte alignment of the next team
 
@@ -411,7 +411,7 @@ MPC_HD void riccati_roles(int l, int N, int W_SD, int* out, int model = 0) {
 // MODEL 0: XY kinematic bicycle (MKZMPCPathFollower.jl); MODEL 1: Frenet-frame variant (MKZMPCPathFollowerFrenet.jl)
 template <int W, int MODEL = 0>
 struct TeamSolver {
-    static_assert(MODEL == 0 || W == 1, "the Frenet variant runs one warp per problem");
+    static constexpr int W_XCHG = MODEL ? 160 : W_XCH;   // exchange area of multi-warp teams
     static constexpr int W_SD = w_sd_of(W, MODEL);   // first stage record
     static constexpr int SDSZ = sds_of(MODEL);       // doubles per stage record
     static constexpr int NFILT_MAX = 32 * W;  // one filter entry per thread
@@ -529,7 +529,7 @@ struct TeamSolver {
             for (int j = 0; j < n; j++) v[j] = comb<OP>(v[j], t[j]);
         }
         if (W > 1) {
-            const int base = SO(W_XCH + XCH_RED + xflip() * 12);
+            const int base = SO(W_XCHG + XCH_RED + xflip() * 12);
             if (lane_id() == 0) for (int j = 0; j < n; j++) sts(sm, base + SO((k >> 5) * 4 + j), v[j]);
             block_sync();
             for (int j = 0; j < n; j++) {
@@ -551,7 +551,7 @@ struct TeamSolver {
             if (l + o < 32) for (int j = 0; j < n; j++) v[j] += t[j];
         }
         if (W > 1) {
-            const int base = SO(W_XCH + XCH_RED + xflip() * 12);
+            const int base = SO(W_XCHG + XCH_RED + xflip() * 12);
             if (l == 0) for (int j = 0; j < n; j++) sts(sm, base + SO((k >> 5) * 4 + j), v[j]);   // this warp's total
             block_sync();
             for (int w = W - 1; w > (k >> 5); w--) for (int j = 0; j < n; j++) v[j] += lds(sm, base + SO(w * 4 + j));
@@ -570,7 +570,7 @@ struct TeamSolver {
             for (int j = 0; j < nd; j++) dn_out[j] = shfl_down(dn[j], 1);
             for (int j = 0; j < nu; j++) up_out[j] = shfl_up(up[j], 1);
             const int b = xflip();
-            const int bd = SO(W_XCH + XCH_DN + b * 24), bu = SO(W_XCH + XCH_UP + b * 24);
+            const int bd = SO(W_XCHG + XCH_DN + b * 24), bu = SO(W_XCHG + XCH_UP + b * 24);
             if (l == 0) for (int j = 0; j < nd; j++) sts(sm, bd + SO(w * 8 + j), dn[j]);
             if (l == 31) for (int j = 0; j < nu; j++) sts(sm, bu + SO(w * 8 + j), up[j]);
             block_sync();
@@ -584,7 +584,7 @@ struct TeamSolver {
     // value held by stage 0, for every thread
     MPC_DEV double bcast0(double v) {
         if (W == 1) return shfl(v, 0);
-        const int a = SO(W_XCH + XCH_FLAG + xflip());
+        const int a = SO(W_XCHG + XCH_FLAG + xflip());
         if (k == 0) sts(sm, a, v);
         block_sync();
         return lds(sm, a);
@@ -906,7 +906,7 @@ struct TeamSolver {
         // warps of the team wait at the barrier that also publishes the inertia verdict
         bool ok = true;
         if ((k >> 5) == 0) ok = riccati_backward_warp();
-        const int a = SO(W_XCH + XCH_FLAG + xflip());
+        const int a = SO(W_XCHG + XCH_FLAG + xflip());
         if (k == 0) sts(sm, a, ok ? 1.0 : 0.0);
         block_sync();
         return lds(sm, a) != 0.0;

@@ -86,12 +86,12 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
     }
     return 0;
 }
-static void lane_main_frenet(int, void* a) {
+template <int W> static void lane_main_frenet(int, void* a) {
     Job* j = (Job*)a;
-    TeamSolver<1, 1>::init_work(j->smem, j->cfg->N);
+    TeamSolver<W, 1>::init_work(j->smem, j->cfg->N);
     RefGen rg;
     memset(&rg, 0, sizeof(rg));
-    solve_problem<1, 1>(*j->cfg, *j->io, rg, j->b, j->smem);
+    solve_problem<W, 1>(*j->cfg, *j->io, rg, j->b, j->smem);
 }
 // Frenet-frame variant: ref = [B][4] curvature polynomial
 extern "C" int emu_solve_batch_frenet(const KCfg* cfg, long B, const double* state, const double* kpoly, const double* v_des,
@@ -99,10 +99,11 @@ extern "C" int emu_solve_batch_frenet(const KCfg* cfg, long B, const double* sta
                                       double* traj) {
     BatchPtrs io{state, kpoly, v_des, u_prev, warm, u0, cost, status, iters, traj};
     KCfg kc = *cfg;
-    if (kc.N > 31) return -1;
+    if (kc.N > 95) return -1;
     kcfg_finalize(kc);
+    const int W = team_warps(kc.N);
     std::vector<int> roles(32 * ROLE_STRIDE_F);
-    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, w_sd_of(1, 1), roles.data() + l * ROLE_STRIDE_F, 1);
+    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, w_sd_of(W, 1), roles.data() + l * ROLE_STRIDE_F, 1);
     kc.roles = roles.data();
     std::vector<double> smem_raw(smem_doubles_per_team(kc.N, 1) + 2, 0.0);
     double* smem = smem_raw.data();
@@ -111,7 +112,7 @@ extern "C" int emu_solve_batch_frenet(const KCfg* cfg, long B, const double* sta
         Job j{&kc, &io, b, smem};
         emu::race_reset();
         register_benign(smem, kc.N, 1);
-        emu::run_warp(lane_main_frenet, &j, 1);
+        emu::run_warp(W == 1 ? lane_main_frenet<1> : W == 2 ? lane_main_frenet<2> : lane_main_frenet<3>, &j, W);
     }
     return 0;
 }

@@ -86,7 +86,8 @@ def _stress_batch(B, N, seed):
     return b
 
 
-@pytest.mark.parametrize("N,B,stress", [(8, 16, False), (20, 10, False), (3, 6, False), (31, 3, False), (8, 12, True), (20, 8, True)])
+@pytest.mark.parametrize("N,B,stress", [(8, 16, False), (20, 10, False), (3, 6, False), (31, 3, False), (8, 12, True), (20, 8, True),
+                                            (32, 2, False), (40, 3, True), (64, 2, False), (80, 2, True)])
 def test_emulated_frenet_kernel_matches_oracle(oracle, N, B, stress):
     import emu as E
     E.race_check(True)

@@ -464,7 +464,8 @@ def _frenet_stress(b, seed):
     return b
 
 
-@pytest.mark.parametrize("N,B,stress", [(8, 512, False), (20, 384, False), (3, 32, False), (31, 32, False), (8, 256, True), (20, 256, True)])
+@pytest.mark.parametrize("N,B,stress", [(8, 512, False), (20, 384, False), (3, 32, False), (31, 32, False), (8, 256, True), (20, 256, True),
+                                            (32, 48, False), (40, 128, True), (64, 32, False), (80, 64, True), (95, 16, False)])
 def test_frenet_cold_and_warm_parity(capi, oracle, N, B, stress):
     s = capi.FrenetSolver(N)
     b = W.make_frenet_batch(B, N)
@@ -530,7 +531,7 @@ def test_frenet_module_mirror_and_errors(capi):
     with pytest.raises(TypeError):
         kmpc.update_reference({}, np.zeros(3), 1.0)
     with pytest.raises(capi.MpcB200Error):
-        capi.FrenetSolver(40)                     # one warp per problem only
+        capi.FrenetSolver(96)                     # horizons up to 95
     s = capi.FrenetSolver(8)
     with pytest.raises(capi.MpcB200Error):        # the XY entry point refuses a Frenet handle
         capi.Solver.solve_batch(s, np.zeros((1, 4)), np.zeros((1, 3, 9)), np.zeros((1, 2)))
@@ -546,3 +547,21 @@ def test_line_search_failure_at_an_acceptable_point_gpu(capi, oracle):
     o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=1)   # all-zero start
     assert g["status"][0] == 0 and g["iters"][0] <= 20
     assert np.abs(g["u0"] - o["u0"]).max() <= 1e-6 and abs(g["cost"][0] - o["cost"][0]) <= 1e-6 * o["cost"][0]
+
+
+def test_frenet_closed_loop_holds_the_path(capi):
+    """The Frenet module in closed loop (the control step of gazebo_sim_mpc_cmd_pub_frenet.jl:112-153 around the
+    repository's plant): three vehicles start 0.5-1 m off paths 1-3 with a heading error, speed up towards 8 m/s and
+    settle on the path; every solve Optimal."""
+    from mkz_mpc_path_follower_b200 import closed_loop
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    tabs = [GPSRefTrajectory(mat_filename=p).trajectory for p in (1, 2, 3)]
+    pose0 = np.array([[tb[200, 4] + 0.6, tb[200, 5] - 0.5, tb[200, 3] + 0.08] for tb in tabs])
+    out = closed_loop.run_frenet([1, 2, 3], pose0, T=150, N=8)
+    log = out["log"]
+    assert (log[:, :, 6] == 0).mean() >= 0.995
+    for b in range(3):
+        err = closed_loop.path_errors(log[:, b:b + 1], tabs[b])[:, 0]
+        assert err[0] > 0.4 and err[60:].max() < 0.25, (b, err[0], err[60:].max())
+    assert log[-1, :, 3].min() > 4.0            # they do drive
+    assert np.abs(log[:, :, 4]).max() <= 1.0 + 1e-9 and np.abs(log[:, :, 5]).max() <= 0.5 + 1e-9
