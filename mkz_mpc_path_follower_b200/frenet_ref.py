@@ -37,13 +37,35 @@ def curvature_poly(s_interp, x_coeffs, y_coeffs):
     return np.polyfit(s_interp, K_meas, 3)
 
 
+_pinv_cache = {}
+
+
+def _pinv(x):
+    """Least-squares cubic fit as a fixed 4 x n matrix (what np.polyfit solves, without its per-call scaling)."""
+    key = (x.size, float(x[0]), float(x[-1]))
+    if key not in _pinv_cache:
+        scale = np.sqrt((np.vander(x, 4) ** 2).sum(axis=0))
+        _pinv_cache[key] = np.linalg.pinv(np.vander(x, 4) / scale) / scale[:, None]
+    return _pinv_cache[key]
+
+
 def fit_windows(xw, yw, s_end):
     """Batched form for synthetic workloads: B windows resampled on the SAME arc-length grid
-    arange(0, s_end, 0.5) (xw, yw: (B, n_grid)).  Same arithmetic as get_reference_frenet with
-    s[0] = 0, s[-1] = s_end.  Returns K_coeffs (B, 4) and psi_start (B,)."""
+    arange(0, s_end, 0.5) (xw, yw: (B, n_grid)).  The fits of get_reference_frenet with s[0] = 0,
+    s[-1] = s_end, each problem on its own with fixed-shape products, so that a problem's result does
+    not depend on which batch (or which GPU's slice) it is generated in.  Agrees with np.polyfit to
+    rounding.  Returns K_coeffs (B, 4) and psi_start (B,)."""
     s_fit = np.arange(0.0, s_end, 0.5)
     assert xw.shape[1] == s_fit.size
-    xc = np.polyfit(s_fit, xw.T, 3); yc = np.polyfit(s_fit, yw.T, 3)       # (4, B)
     s_interp = np.arange(0.0, s_end, 0.25)
-    K = curvature_poly(s_interp, xc, yc)                                    # (4, B)
-    return np.ascontiguousarray(K.T), np.arctan2(yc[2], xc[2])
+    P1, P2 = _pinv(s_fit), _pinv(s_interp)
+    B = xw.shape[0]
+    K = np.empty((B, 4)); psi0 = np.empty(B)
+    for q in range(B):
+        xc = P1.dot(xw[q]); yc = P1.dot(yw[q])
+        dx = xc[2] + 2 * xc[1] * s_interp + 3 * xc[0] * s_interp ** 2
+        dy = yc[2] + 2 * yc[1] * s_interp + 3 * yc[0] * s_interp ** 2
+        ddx = 2 * xc[1] + 6 * xc[0] * s_interp; ddy = 2 * yc[1] + 6 * yc[0] * s_interp
+        K[q] = P2.dot((dx * ddy - dy * ddx) / (dx * dx + dy * dy))
+        psi0[q] = np.arctan2(yc[2], xc[2])
+    return K, psi0

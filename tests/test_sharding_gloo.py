@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, total, N, out_dir):
+def _worker(rank, world, port, total, N, out_dir, frenet=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -20,8 +20,12 @@ def _worker(rank, world, port, total, N, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = sharding.shard_range(total, world, rank)
-    b = workload.make_batch(hi - lo, N, b0=lo)
-    r = O.solve_batch(O.default_cfg(N), b["state"], b["ref"], b["v_des"], b["u_prev"])
+    if frenet:   # the Frenet-frame variant shards the same way (its workload is a counter-based stream too)
+        b = workload.make_frenet_batch(hi - lo, N, b0=lo)
+        r = O.solve_batch_frenet(O.default_cfg_frenet(N), b["state"], b["kpoly"], b["v_des"], b["u_prev"])
+    else:
+        b = workload.make_batch(hi - lo, N, b0=lo)
+        r = O.solve_batch(O.default_cfg(N), b["state"], b["ref"], b["v_des"], b["u_prev"])
     rec = sharding.pack_records(torch.from_numpy(r["u0"]), torch.from_numpy(r["cost"]),
                                 torch.from_numpy(r["status"]), torch.from_numpy(r["iters"]))
     sizes = [sharding.shard_range(total, world, q)[1] - sharding.shard_range(total, world, q)[0] for q in range(world)]
@@ -51,6 +55,21 @@ def test_two_rank_gather_equals_single_rank(tmp_path, total):
     mp.spawn(_worker, args=(world, port, total, N, str(tmp_path)), nprocs=world, join=True)
     b = workload.make_batch(total, N)
     ref = O.solve_batch(O.default_cfg(N), b["state"], b["ref"], b["v_des"], b["u_prev"])
+    for r in range(world):
+        g = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        assert np.array_equal(g["u0"], ref["u0"]) and np.array_equal(g["cost"], ref["cost"])
+        assert np.array_equal(g["status"], ref["status"]) and np.array_equal(g["iters"], ref["iters"])
+
+
+def test_two_rank_gather_equals_single_rank_frenet(tmp_path):
+    import torch.multiprocessing as mp
+    from mkz_mpc_path_follower_b200 import workload
+    from oracle import oracle as O
+    N, world, total = 8, 2, 21
+    port = 29500 + (os.getpid() % 2000) + 77
+    mp.spawn(_worker, args=(world, port, total, N, str(tmp_path), True), nprocs=world, join=True)
+    b = workload.make_frenet_batch(total, N)
+    ref = O.solve_batch_frenet(O.default_cfg_frenet(N), b["state"], b["kpoly"], b["v_des"], b["u_prev"])
     for r in range(world):
         g = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
         assert np.array_equal(g["u0"], ref["u0"]) and np.array_equal(g["cost"], ref["cost"])
