@@ -567,6 +567,7 @@ int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T, const double* pose0
                     double target_vel, double* log, double* final_state) {
     if (!h) return MPCB200_EINVAL;
     if (B < 0 || T < 0) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: B=%lld T=%d", (long long)B, T);
+    if (h->model) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: not available for the Frenet-frame variant");
     memset(&h->stats, 0, sizeof(h->stats));
     if (B == 0 || T == 0) return MPCB200_OK;
     if (!pose0 || !path_of) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: pose0 and path_of are required");

@@ -537,6 +537,8 @@ def test_frenet_module_mirror_and_errors(capi):
     s = capi.FrenetSolver(8)
     with pytest.raises(capi.MpcB200Error):        # the XY entry point refuses a Frenet handle
         capi.Solver.solve_batch(s, np.zeros((1, 4)), np.zeros((1, 3, 9)), np.zeros((1, 2)))
+    with pytest.raises(capi.MpcB200Error):        # ... and so does the closed-loop rollout
+        s.rollout(np.zeros((1, 3)), np.zeros(1, dtype=np.int32), 2)
 
 
 def test_line_search_failure_at_an_acceptable_point_gpu(capi, oracle):
@@ -567,3 +569,14 @@ def test_frenet_closed_loop_holds_the_path(capi):
         assert err[0] > 0.4 and err[60:].max() < 0.25, (b, err[0], err[60:].max())
     assert log[-1, :, 3].min() > 4.0            # they do drive
     assert np.abs(log[:, :, 4]).max() <= 1.0 + 1e-9 and np.abs(log[:, :, 5]).max() <= 0.5 + 1e-9
+
+
+@pytest.mark.parametrize("N,B", [(8, 48), (20, 32), (40, 8)])
+def test_frenet_kkt_of_cuda_solutions(capi, oracle, N, B):
+    """KKT conditions of the unscaled Frenet NLP at the CUDA solver's returned points (stress curvature), checked
+    with the oracle's NLP functions only -- none of its interior-point code."""
+    from test_frenet import frenet_kkt_check
+    s = capi.FrenetSolver(N)
+    b = _frenet_stress(W.make_frenet_batch(B, N), 23)
+    g = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    assert frenet_kkt_check(oracle, oracle.default_cfg_frenet(N), b, g["traj"], g["status"]) >= B - 2
