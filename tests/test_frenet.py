@@ -167,3 +167,29 @@ def test_frenet_kkt_of_oracle_solutions(oracle):
     b = _stress_batch(B, N, 3)
     o = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], want_traj=True, n_threads=4)
     assert frenet_kkt_check(oracle, cfg, b, o["traj"], o["status"]) >= B - 1
+
+
+def frenet_edge_batch(N):
+    """NaN curvature; 1 - e_y K = 0 at the start (the reference's ds/dt is singular there, :113); 1 - e_y K < 0;
+    v0 above v_max (the only way this NLP is infeasible); a large s0; an ordinary problem."""
+    b = W.make_frenet_batch(6, N)
+    b["kpoly"][0, :] = np.nan
+    b["kpoly"][1, :] = [0, 0, 0, 1.0]; b["state"][1, 1] = 1.0
+    b["kpoly"][2, :] = [0, 0, 0, 0.5]; b["state"][2, 1] = 2.5
+    b["state"][3, 3] = 25.0
+    b["state"][4, :] = [1e3, 0.1, 0.0, 5.0]
+    return b
+
+
+def test_emulated_frenet_edge_cases(oracle):
+    """Degenerate inputs end with the oracle's status and iteration count -- no hang, no divergence between the two."""
+    import emu as E
+    N = 8
+    b = frenet_edge_batch(N)
+    cfg = oracle.default_cfg_frenet(N, max_iter=60)
+    o = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], n_threads=1)
+    e = E.solve_batch_frenet(E.kcfg_from_oracle(cfg), b["state"], b["kpoly"], b["v_des"], b["u_prev"])
+    assert o["status"].tolist() == [4, 4, 3, 1, 0, 0]
+    assert (o["status"] == e["status"]).all() and (o["iters"] == e["iters"]).all()
+    ok = o["status"] == 0
+    assert np.abs(o["u0"] - e["u0"])[ok].max() <= 1e-9

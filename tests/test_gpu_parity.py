@@ -580,3 +580,20 @@ def test_frenet_kkt_of_cuda_solutions(capi, oracle, N, B):
     b = _frenet_stress(W.make_frenet_batch(B, N), 23)
     g = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"], want_traj=True)
     assert frenet_kkt_check(oracle, oracle.default_cfg_frenet(N), b, g["traj"], g["status"]) >= B - 2
+
+
+def test_frenet_edge_cases(capi, oracle):
+    """Empty batch, degenerate inputs (NaN curvature, singular 1 - e_y K, infeasible v0): the oracle's statuses."""
+    from test_frenet import frenet_edge_batch
+    N = 8
+    s = capi.FrenetSolver(N, max_iter=60)
+    g0 = s.solve_batch(np.zeros((0, 4)), np.zeros((0, 4)), np.zeros((0, 2)))
+    assert g0["u0"].shape == (0, 2)
+    b = frenet_edge_batch(N)
+    g = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"])
+    o = oracle.solve_batch_frenet(oracle.default_cfg_frenet(N, max_iter=60), b["state"], b["kpoly"], b["v_des"], b["u_prev"], n_threads=1)
+    assert (g["status"] == o["status"]).all() and g["status"].tolist() == [4, 4, 3, 1, 0, 0]
+    ok = o["status"] == 0
+    assert np.abs(g["u0"] - o["u0"])[ok].max() <= U_TOL
+    with pytest.raises(ValueError):
+        s.solve_batch(np.zeros((2, 4)), np.zeros((2, 3)), np.zeros((2, 2)))
