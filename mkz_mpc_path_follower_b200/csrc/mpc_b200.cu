@@ -44,8 +44,11 @@ mpc_solve_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const long
 }
 
 // Frenet-frame variant (MKZMPCPathFollowerFrenet.jl): same driver, dense s / e_y columns (mpc_kernel.cuh, MODEL 1);
-// 62-double records: two blocks (8 warps) per SM at N = 20
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2)
+// 62-double records, 21.3 KB of shared memory per problem at N = 20.  Two builds: blocks of four warps at 255 registers
+// (two per SM) and blocks of three at 168 registers with spill code (up to four per SM: 12 warps at the N = 8 footprint);
+// mpcb200_create_frenet picks per horizon (see there)
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32, WPB == 3 ? 3 : 2)
 mpc_solve_frenet_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const long long B, unsigned long long* counter) {
     extern __shared__ double smem_all[];
     const int warp = threadIdx.x >> 5;
@@ -131,6 +134,7 @@ struct mpcb200_handle {
     int blocks_per_sm = 0;
     int team_warps = 1;     /* warps per problem: 1 (N <= 31), 2 (N <= 63), 3 (N <= 95) */
     int model = 0;          /* 0: XY model; 1: Frenet-frame variant (mpcb200_create_frenet) */
+    int frenet_wpb = WARPS_PER_BLOCK;   /* warps (= problems) per block of mpc_solve_frenet_kernel */
     size_t smem_bytes = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -277,10 +281,20 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, fn, h->team_warps * 32, h->smem_bytes));
     } else if (model) {
-        h->smem_bytes = (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N, 1) * sizeof(double);
-        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_frenet_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
+        const size_t team = (size_t)smem_doubles_per_team(cfg->N, 1) * sizeof(double);
+        int b4 = 0, b3 = 0;
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * team)));
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, mpc_solve_frenet_kernel<4>, 4 * 32, 4 * team));
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * team)));
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, mpc_solve_frenet_kernel<3>, 3 * 32, 3 * team));
+        /* measured (tools/frenet_bench.py): N = 8: 12 warps at 168 registers 6.06 M solves/s vs 8 warps at 255 registers 5.80 M;
+         * N = 20: 9 warps 2.88 M vs 8 warps 3.23 M -- the spill code of the 168-register build pays only for >= 1.4x the warps */
+        h->frenet_wpb = (10 * 3 * b3 >= 14 * 4 * b4) ? 3 : 4;
+        if (const char* e = getenv("MPCB200_FRENET_WPB")) { int v = atoi(e); if (v == 3 || v == 4) h->frenet_wpb = v; }  /* tuning aid */
+        h->blocks_per_sm = (h->frenet_wpb == 3) ? b3 : b4;
+        h->smem_bytes = h->frenet_wpb * team;
     } else if (h->team_warps == 1) {
         h->smem_bytes = ((size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N) + WARPS_PER_BLOCK * ROLLOUT_PX) * sizeof(double);
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -336,7 +350,7 @@ int mpcb200_set_stream(mpcb200_handle* h, void* s) {
 static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const RefGen& rg, unsigned long long* zeroed_counter = nullptr) {
     unsigned long long* counter = zeroed_counter ? zeroed_counter : h->d_counter;
     if (!zeroed_counter) CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), h->stream));
-    const int teams_per_block = (h->team_warps == 1) ? WARPS_PER_BLOCK : 1;
+    const int teams_per_block = (h->team_warps != 1) ? 1 : (h->model ? h->frenet_wpb : WARPS_PER_BLOCK);
     long long blocks_needed = (B + teams_per_block - 1) / teams_per_block;
     long long max_blocks = (long long)h->num_sms * h->blocks_per_sm;
     int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
@@ -345,8 +359,10 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
         mpc_solve_long_kernel<2, 1><<<grid, 64, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     else if (h->model && h->team_warps == 3)
         mpc_solve_long_kernel<3, 1><<<grid, 96, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
+    else if (h->model && h->frenet_wpb == 3)
+        mpc_solve_frenet_kernel<3><<<grid, 96, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     else if (h->model)
-        mpc_solve_frenet_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
+        mpc_solve_frenet_kernel<4><<<grid, 128, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     else if (h->team_warps == 1)
         mpc_solve_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, h->stream>>>(make_kcfg(h), io, rg, (long long)B, counter);
     else if (h->team_warps == 2)

@@ -144,7 +144,6 @@ def frenet_kkt_check(oracle, cfg, b, traj, status):
         d = np.empty(md); L.mpc_oracle_eval_d(C.byref(cfg), _p(np.ascontiguousarray(b["u_prev"][j])), _p(z), _p(d))
         lim = np.array([(cfg.steer_dmax if r % 2 == 0 else cfg.a_dmax) * (cfg.dt_control if r < 2 else cfg.dt) for r in range(md)])
         assert (np.abs(d) <= lim + 1e-7).all()
-        act_rows = np.abs(np.abs(d) - lim) <= 1e-6
         lo = np.full(n, -np.inf); hi = np.full(n, np.inf)
         for k in range(N + 1):
             lo[6 * k + 3], hi[6 * k + 3] = cfg.v_min, cfg.v_max
@@ -152,10 +151,28 @@ def frenet_kkt_check(oracle, cfg, b, traj, status):
                 lo[6 * k + 4], hi[6 * k + 4] = -cfg.a_max, cfg.a_max
                 lo[6 * k + 5], hi[6 * k + 5] = -cfg.steer_max, cfg.steer_max
         assert (z >= lo - 1e-9).all() and (z <= hi + 1e-9).all()
-        act_b = (z - lo <= 1e-6) | (hi - z <= 1e-6)
-        A = np.vstack([Jc, Jd[act_rows], np.eye(n)[act_b]])
-        lam = np.linalg.lstsq(A.T, -g, rcond=None)[0]
-        assert np.abs(g + A.T @ lam).max() <= 1e-5 * max(1.0, np.abs(g).max())
+        # multipliers: free for the equality rows, >= 0 for every inequality within 1e-3 of its limit (an interior-point
+        # solution leaves weakly active constraints a slack of mu / multiplier); non-negative least squares on
+        #   g + Jc' y + sum_i m_i n_i = 0,   n_i = outward normal of inequality i
+        normals, slacks = [], []
+        for r in range(md):
+            for sgn in (1.0, -1.0):
+                sl = lim[r] - sgn * d[r]
+                if sl <= 1e-3:
+                    normals.append(sgn * Jd[r]); slacks.append(max(sl, 0.0))
+        eye = np.eye(n)
+        for i in range(n):
+            if hi[i] - z[i] <= 1e-3:
+                normals.append(eye[i]); slacks.append(max(hi[i] - z[i], 0.0))
+            if z[i] - lo[i] <= 1e-3:
+                normals.append(-eye[i]); slacks.append(max(z[i] - lo[i], 0.0))
+        cols = [Jc.T, -Jc.T] + ([np.array(normals).T] if normals else [])
+        from scipy.optimize import nnls
+        mult, _ = nnls(np.hstack(cols), -g, maxiter=20000)
+        resid = g + np.hstack(cols) @ mult
+        assert np.abs(resid).max() <= 1e-5 * max(1.0, np.abs(g).max())
+        if normals:   # complementarity
+            assert (mult[2 * mc:] * np.array(slacks)).max() <= 1e-5
         checked += 1
     return checked
 
