@@ -29,6 +29,13 @@
 // The phase machine makes all solver state look live everywhere, so only the primal iterate and the
 // equality multipliers stay in registers; bound multipliers, step, model evaluation and reference
 // sample live in per-thread shared-memory fields (LF_*): 168 registers, 12 warps per SM at N = 20.
+//
+// MODEL template parameter: 0 = the XY model above; 1 = the reference's Frenet-frame variant
+// (scripts/mpc_utils/MKZMPCPathFollowerFrenet.jl:65-123: states s, e_y, e_psi, v in the slots of x, y, psi, v;
+// ds/dt = v cos(e_psi + beta) / (1 - e_y K(s)), K a cubic per problem).  Same driver, bounds, rate rows and cost form;
+// the `if (MODEL)` branches hold what differs: the stage map and its 5x5 Lagrangian-Hessian block (eval_point,
+// frenet_jac, assemble), two more columns of P M in Riccati round A, the dense forward sweep and a serial costate
+// recursion in place of the suffix sums (recover_duals).  The XY instantiation compiles to the same code as before.
 #pragma once
 #include "warp_prims.cuh"
 #ifdef MPC_TRACE
