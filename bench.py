@@ -89,6 +89,65 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": n}
 
 
+class NvmlClockSampler(object):
+    """The same through NVML (pynvml), polled every 5 ms from a thread: the timed region is a few hundred ms, too short
+    for more than a sample or two of `nvidia-smi -lms 100`.  Falls back to ClockSampler when NVML is not usable."""
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.index = index
+        self.fallback = None
+        self.thread = None
+        self.samples = []
+        self.mask = 0
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+            self.fallback = ClockSampler(index)
+
+    def _reasons(self):
+        for fn in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            f = getattr(self.nv, fn, None)
+            if f is not None:
+                try:
+                    return int(f(self.h))
+                except Exception:
+                    pass
+        return 0
+
+    def _run(self):
+        while not self._stop:
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.mask |= self._reasons()
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.fallback is not None:
+            return self.fallback.start()
+        import threading
+        self._stop = False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.fallback is not None:
+            return self.fallback.stop()
+        self._stop = True
+        self.thread.join(timeout=2)
+        reasons = sorted(name for bit, name in self.BITS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.samples), "source": "nvml, 5 ms poll"}
+
+
 def cpu_baseline(N, sample, threads, start_b0=0, start="zero"):
     """The oracle (restated CPU interior point, NOT Ipopt) on a bounded sample of the same workload."""
     from oracle import oracle as O
@@ -189,7 +248,7 @@ def main():
     # kernel-only time of one step (events directly around the kernel) for the roofline
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ms = []
-    sampler = ClockSampler(local)
+    sampler = NvmlClockSampler(local)
     sampler.start()
     barrier()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)

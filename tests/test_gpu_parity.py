@@ -597,3 +597,19 @@ def test_frenet_edge_cases(capi, oracle):
     assert np.abs(g["u0"] - o["u0"])[ok].max() <= U_TOL
     with pytest.raises(ValueError):
         s.solve_batch(np.zeros((2, 4)), np.zeros((2, 3)), np.zeros((2, 2)))
+
+
+def test_frenet_large_batch_oracle_parity(capi, oracle):
+    """16,384 Frenet problems at N = 20, every one compared with the oracle: same status, the same iteration count
+    on (nearly) all, |du| far inside the 1e-5 bar."""
+    N, B = 20, 16384
+    s = capi.FrenetSolver(N)
+    b = W.make_frenet_batch(B, N, b0=65536)
+    g = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"])
+    o = oracle.solve_batch_frenet(oracle.default_cfg_frenet(N, tol=s.cfg.tol, max_iter=s.cfg.max_iter), b["state"], b["kpoly"],
+                                  b["v_des"], b["u_prev"], n_threads=16)
+    assert (g["status"] == o["status"]).all() and (g["status"] == 0).mean() >= 0.9999
+    ok = o["status"] == 0
+    assert (g["iters"] == o["iters"])[ok].mean() >= 0.999
+    assert np.abs(g["u0"] - o["u0"])[ok].max() <= 1e-8
+    assert (np.abs(g["cost"] - o["cost"])[ok] <= 1e-9 * np.maximum(1.0, o["cost"][ok])).all()
