@@ -229,7 +229,7 @@ class Solver(object):
 
 
 class FrenetSolver(Solver):
-    """Frenet-frame variant (mpcb200_create_frenet; scripts/mpc_utils/MKZMPCPathFollowerFrenet.jl): N <= 31."""
+    """Frenet-frame variant (mpcb200_create_frenet; scripts/mpc_utils/MKZMPCPathFollowerFrenet.jl): 3 <= N <= 95."""
 
     def _create(self):
         return lib().mpcb200_create_frenet
