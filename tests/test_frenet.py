@@ -210,3 +210,60 @@ def test_emulated_frenet_edge_cases(oracle):
     assert (o["status"] == e["status"]).all() and (o["iters"] == e["iters"]).all()
     ok = o["status"] == 0
     assert np.abs(o["u0"] - e["u0"])[ok].max() <= 1e-9
+
+
+def test_frenet_agrees_with_scipy_slsqp(oracle):
+    """Independent solver on an independent transcription: scipy SLSQP minimises the Frenet NLP whose objective and
+    constraint VALUES are written here in numpy straight from MKZMPCPathFollowerFrenet.jl:75-123 (derivatives from the
+    oracle's analytic Jacobians, which the finite-difference test above pins).  Started near the oracle's point it must
+    stay there: same cost to 1e-6 relative, same first move to 1e-4 (SLSQP's own accuracy)."""
+    from scipy.optimize import minimize
+    from test_oracle_solver import _nlp
+    N, B = 8, 6
+    cfg = oracle.default_cfg_frenet(N)
+    b = _stress_batch(B, N, 41)
+    o = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], want_traj=True, n_threads=4)
+    L = oracle.lib()
+    La, Lb, dt = cfg.L_a, cfg.L_b, cfg.dt
+    rng = np.random.default_rng(1)
+    checked = 0
+    for j in np.nonzero(o["status"] == 0)[0]:
+        kp = b["kpoly"][j]; st = b["state"][j]; vt = float(b["v_des"][j])
+        for i in range(4):
+            cfg.kpoly[i] = kp[i]
+        _, g_or, _, d, jac, lo, hi, dlim = _nlp(oracle, cfg, np.ascontiguousarray(st), np.zeros(3 * (N + 1)), vt, np.ascontiguousarray(b["u_prev"][j]))
+
+        def unpack(z):
+            Z = np.concatenate([z, [0.0, 0.0]]).reshape(N + 1, 6)
+            return Z[:, 0], Z[:, 1], Z[:, 2], Z[:, 3], Z[:N, 4], Z[:N, 5]      # s, ey, epsi, v, acc, df
+
+        def f(z):   # :95-101 (1-based i = 2..N+1 -> 0-based 1..N; speed term i = 2..N)
+            s, ey, ep, v, acc, df = unpack(z)
+            return (9.0 * (ey[1:] ** 2).sum() + 10.0 * (ep[1:] ** 2).sum() + 0.5 * ((v[1:N] - vt) ** 2).sum()
+                    + 100.0 * (np.diff(acc) ** 2).sum() + 1000.0 * (np.diff(df) ** 2).sum())
+
+        def c(z):   # :106-120
+            s, ey, ep, v, acc, df = unpack(z)
+            K = kp[0] * s[:N] ** 3 + kp[1] * s[:N] ** 2 + kp[2] * s[:N] + kp[3]
+            bta = np.arctan(Lb / (La + Lb) * np.tan(df))
+            dsdt = v[:N] * np.cos(ep[:N] + bta) / (1 - ey[:N] * K)
+            rows = [np.array([s[0], ey[0], ep[0], v[0]]) - st]
+            nxt = np.stack([s[:N] + dt * dsdt, ey[:N] + dt * (v[:N] * np.sin(ep[:N] + bta)),
+                            ep[:N] + dt * (v[:N] / Lb * np.sin(bta) - dsdt * K), v[:N] + dt * acc], axis=1)
+            cur = np.stack([s[1:], ey[1:], ep[1:], v[1:]], axis=1)
+            return np.concatenate([rows[0], (cur - nxt).reshape(-1)])
+
+        z0 = np.empty(6 * N + 4)
+        L.mpc_oracle_traj_to_z(C.byref(cfg), _p(np.ascontiguousarray(o["traj"][j])), _p(z0))
+        assert abs(f(z0) - o["cost"][j]) <= 1e-9 * max(1.0, o["cost"][j])       # the two transcriptions agree on the objective
+        assert np.abs(c(z0)).max() <= 1e-7                                      # ... and on the dynamics
+        cons = [{"type": "eq", "fun": c, "jac": lambda z: jac(z)[0]},
+                {"type": "ineq", "fun": lambda z: dlim - d(z), "jac": lambda z: -jac(z)[1]},
+                {"type": "ineq", "fun": lambda z: dlim + d(z), "jac": lambda z: jac(z)[1]}]
+        res = minimize(f, z0 + 1e-2 * rng.normal(size=z0.size), jac=g_or, bounds=list(zip(lo, hi)), constraints=cons,
+                       method="SLSQP", options={"ftol": 1e-15, "maxiter": 500})
+        assert np.abs(c(res.x)).max() < 1e-7
+        assert abs(res.fun - o["cost"][j]) <= 1e-6 * max(1.0, abs(o["cost"][j])), (j, res.fun, o["cost"][j])
+        assert np.abs(res.x[4:6] - o["u0"][j]).max() < 1e-4, (j, res.x[4:6], o["u0"][j])
+        checked += 1
+    assert checked >= 4
