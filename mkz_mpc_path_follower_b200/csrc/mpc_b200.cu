@@ -146,6 +146,12 @@ struct mpcb200_handle {
     DevBuf d_stage;               /* small batches: one contiguous device buffer, one copy each way */
     void* h_stage = nullptr;      /* its pinned host mirror */
     size_t h_stage_cap = 0;
+    /* small batches on the handle's own stream: copy in -> kernel -> copy out captured once per shape as a CUDA graph
+     * (one cudaGraphLaunch instead of five driver calls per solve); dropped when a buffer, the weights or the stream change */
+    struct SmallGraph { int64_t B; int flags; cudaGraphExec_t exec; };
+    SmallGraph graphs[8];
+    int n_graphs = 0;
+    bool graphs_ok = true;
     int path_n[3] = {0, 0, 0};
     int rollout_blocks_per_sm = 0;
     mpcb200_stats stats;
@@ -168,6 +174,11 @@ static int fail(mpcb200_handle* h, int code, const char* fmt, ...) {
         cudaError_t e_ = (expr);                                                                   \
         if (e_ != cudaSuccess) return fail(h, MPCB200_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
     } while (0)
+
+static void drop_graphs(mpcb200_handle* h) {
+    for (int i = 0; i < h->n_graphs; i++) if (h->graphs[i].exec) cudaGraphExecDestroy(h->graphs[i].exec);
+    h->n_graphs = 0;
+}
 
 static int ensure(mpcb200_handle* h, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
@@ -326,6 +337,7 @@ int mpcb200_destroy(mpcb200_handle* h) {
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_roles) cudaFree(h->d_roles);
+    drop_graphs(h);
     if (h->h_stage) cudaFreeHost(h->h_stage);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -338,12 +350,14 @@ int mpcb200_set_cost(mpcb200_handle* h, const double w[8]) {
     if (!h || !w) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost: NULL argument");
     for (int i = 0; i < 8; i++) if (!(w[i] >= 0.0)) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost: weight %d is negative or NaN", i);
     memcpy(h->w, w, 8 * sizeof(double));
+    drop_graphs(h);   /* the weights are kernel parameters */
     return MPCB200_OK;
 }
 
 int mpcb200_set_stream(mpcb200_handle* h, void* s) {
     if (!h) return MPCB200_EINVAL;
     h->stream = s ? (cudaStream_t)s : h->own_stream;
+    drop_graphs(h);
     return MPCB200_OK;
 }
 
@@ -399,6 +413,7 @@ static int solve_small_host(mpcb200_handle* h, int64_t B, const double* state, c
     const size_t total = o_iter + (B + 1) / 2;
     const size_t bytes = total * sizeof(double);
     int rc;
+    if (bytes > h->d_stage.cap || bytes > h->h_stage_cap) drop_graphs(h);   /* the graphs hold the old addresses */
     if ((rc = ensure(h, h->d_stage, bytes))) return rc;
     if (bytes > h->h_stage_cap) {
         if (h->h_stage) CUDA_TRY(h, cudaFreeHost(h->h_stage));
@@ -416,17 +431,51 @@ static int solve_small_host(mpcb200_handle* h, int64_t B, const double* state, c
     if (warm) memcpy(hs + o_warm, warm, nt * B * sizeof(double));
     const size_t in_doubles = warm ? o_u0 : o_warm;
     cudaStream_t s = h->stream;
-    CUDA_TRY(h, cudaMemcpyAsync(ds, hs, in_doubles * sizeof(double), cudaMemcpyHostToDevice, s));
-    h->stats.h2d_bytes += in_doubles * sizeof(double);
     BatchPtrs io{ds + o_state, ds + o_ref, v_des ? ds + o_vdes : nullptr, ds + o_uprev, warm ? ds + o_warm : nullptr, ds + o_u0,
                  ds + o_cost, (int*)(ds + o_stat), (int*)(ds + o_iter), traj ? ds + o_traj : nullptr};
     RefGen rg;
     memset(&rg, 0, sizeof(rg));
-    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
-    if ((rc = launch_solve(h, B, io, rg, (unsigned long long*)ds))) return rc;
-    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     const size_t out_from = warm ? o_warm : o_u0;
-    CUDA_TRY(h, cudaMemcpyAsync(hs + out_from, ds + out_from, (total - out_from) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    /* the sequence copy in -> kernel -> copy out; `ext`: events recorded from inside a graph need the external flag to be timed */
+    auto enqueue = [&](bool ext) -> int {
+        CUDA_TRY(h, cudaMemcpyAsync(ds, hs, in_doubles * sizeof(double), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(h, cudaEventRecordWithFlags(h->ev0, s, ext ? cudaEventRecordExternal : cudaEventRecordDefault));
+        int r = launch_solve(h, B, io, rg, (unsigned long long*)ds);
+        if (r) return r;
+        CUDA_TRY(h, cudaEventRecordWithFlags(h->ev1, s, ext ? cudaEventRecordExternal : cudaEventRecordDefault));
+        CUDA_TRY(h, cudaMemcpyAsync(hs + out_from, ds + out_from, (total - out_from) * sizeof(double), cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    bool launched = false;
+    if (h->graphs_ok && s == h->own_stream) {
+        const int flags = (v_des ? 1 : 0) | (warm ? 2 : 0) | (traj ? 4 : 0);
+        cudaGraphExec_t exec = nullptr;
+        for (int i = 0; i < h->n_graphs; i++) if (h->graphs[i].B == B && h->graphs[i].flags == flags) exec = h->graphs[i].exec;
+        if (!exec) {
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                const int r = enqueue(true);
+                ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && r == 0 && graph != nullptr;
+                h->stats.kernel_launches = 0;   /* counted at the graph launch below */
+            }
+            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (ok) {
+                if (h->n_graphs == 8) drop_graphs(h);
+                h->graphs[h->n_graphs].B = B; h->graphs[h->n_graphs].flags = flags; h->graphs[h->n_graphs].exec = exec;
+                h->n_graphs++;
+            } else {
+                exec = nullptr; h->graphs_ok = false; cudaGetLastError();   /* fall back to plain launches for good */
+            }
+        }
+        if (exec) {
+            if (cudaGraphLaunch(exec, s) == cudaSuccess) { launched = true; h->stats.kernel_launches += 1; }
+            else { h->graphs_ok = false; cudaGetLastError(); drop_graphs(h); }
+        }
+    }
+    if (!launched && (rc = enqueue(false))) return rc;
+    h->stats.h2d_bytes += in_doubles * sizeof(double);
     h->stats.d2h_bytes += (total - out_from) * sizeof(double);
     CUDA_TRY(h, cudaStreamSynchronize(s));
     memcpy(u0, hs + o_u0, 2 * B * sizeof(double));
@@ -544,6 +593,7 @@ int mpcb200_set_cost_frenet(mpcb200_handle* h, const double w[7]) {
     for (int i = 0; i < 7; i++) if (!(w[i] >= 0.0)) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost_frenet: weight %d is negative or NaN", i);
     h->w[0] = 0.0;
     memcpy(h->w + 1, w, 7 * sizeof(double));
+    drop_graphs(h);
     return MPCB200_OK;
 }
 
