@@ -162,3 +162,31 @@ def test_line_search_failure_at_an_acceptable_point(oracle):
     o0 = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=1)   # all-zero start
     assert o0["status"][0] == 0 and np.abs(o["u0"] - o0["u0"]).max() <= 1e-6
     assert abs(o["cost"][0] - o0["cost"][0]) <= 1e-6 * o0["cost"][0]
+
+
+def test_emulated_kernel_property(oracle):
+    """Property-based: problems of the synthetic stream with random extra offsets, speeds and previous commands,
+    started from the reference waypoints -- emulated CUDA source and oracle end with the same status and, where
+    that is Optimal, the same command."""
+    import emu as E
+    from hypothesis import given, settings, strategies as st
+    N = 5
+    cfg = oracle.default_cfg(N, max_iter=80)
+    kc = E.kcfg_from_oracle(cfg)
+    fl = lambda lo, hi: st.floats(min_value=lo, max_value=hi, allow_nan=False, allow_infinity=False)
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(st.integers(0, 10 ** 6), fl(-2.0, 2.0), fl(-2.0, 2.0), fl(-0.3, 0.3), fl(0.0, 20.0), fl(-0.5, 0.5), fl(-1.0, 1.0))
+    def check(b0, dx, dy, dpsi, v, df0, a0):
+        b = W.make_batch(1, N, b0=b0)
+        b["state"][0] += [dx, dy, dpsi, 0.0]; b["state"][0, 3] = v
+        b["u_prev"][0] = [df0, a0]
+        w = W.reference_start(b, N)
+        o = oracle.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], warm=w.copy(), n_threads=1)
+        e = E.solve_batch(kc, b["state"], b["ref"], b["v_des"], b["u_prev"], warm=w.copy())
+        assert o["status"][0] == e["status"][0]
+        if o["status"][0] == 0:
+            assert abs(int(o["iters"][0]) - int(e["iters"][0])) <= 1
+            assert np.abs(o["u0"] - e["u0"]).max() <= 1e-7
+
+    check()

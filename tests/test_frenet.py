@@ -267,3 +267,28 @@ def test_frenet_agrees_with_scipy_slsqp(oracle):
         assert np.abs(res.x[4:6] - o["u0"][j]).max() < 1e-4, (j, res.x[4:6], o["u0"][j])
         checked += 1
     assert checked >= 4
+
+
+def test_emulated_frenet_kernel_property(oracle):
+    """Property-based: for random curvature polynomials, offsets, speeds, previous commands and target speeds the
+    emulated CUDA source and the oracle end with the same status, and where that is Optimal with the same command."""
+    import emu as E
+    from hypothesis import given, settings, strategies as st
+    N = 5
+    cfg = oracle.default_cfg_frenet(N, max_iter=80)
+    kc = E.kcfg_from_oracle(cfg)
+    fl = lambda lo, hi: st.floats(min_value=lo, max_value=hi, allow_nan=False, allow_infinity=False)
+
+    @settings(max_examples=30, deadline=None, derandomize=True)
+    @given(fl(-2e-6, 2e-6), fl(-1e-4, 1e-4), fl(-3e-3, 3e-3), fl(-0.06, 0.06), fl(-1.5, 1.5), fl(-0.4, 0.4), fl(0.0, 20.0),
+           fl(-0.5, 0.5), fl(-1.0, 1.0), fl(0.0, 15.0))
+    def check(k0, k1, k2, k3, ey, ep, v, df0, a0, vt):
+        state = np.array([[0.0, ey, ep, v]]); kp = np.array([[k0, k1, k2, k3]]); up = np.array([[df0, a0]]); vd = np.array([vt])
+        o = oracle.solve_batch_frenet(cfg, state, kp, vd, up, n_threads=1)
+        e = E.solve_batch_frenet(kc, state, kp, vd, up)
+        assert o["status"][0] == e["status"][0]
+        if o["status"][0] == 0:
+            assert abs(int(o["iters"][0]) - int(e["iters"][0])) <= 1
+            assert np.abs(o["u0"] - e["u0"]).max() <= 1e-7
+
+    check()
