@@ -89,3 +89,32 @@ def test_batched_plant_equals_scalar():
         for i, s in enumerate(sims):
             s.mpc_cmd(a[i], d[i]); s.update_vehicle_model()
     assert np.array_equal(bat.full_state(), np.stack([s.full_state() for s in sims]))
+
+
+def test_frenet_reference_fit_matches_reference():
+    """frenet_ref.get_reference_frenet against golden vectors produced by RUNNING the reference's own
+    get_reference_frenet (scripts/sim_path_utils/nav_msgs_path_frenet.py:76-86; tools/make_golden_frenet.py) on 24
+    windows of the recorded paths: curvature polynomial, start heading and the resampled cubic path."""
+    from mkz_mpc_path_follower_b200 import frenet_ref
+    g = np.load(os.path.join(GOLD, "frenet_ref.npz"))
+    n = int(g["n_cases"])
+    assert n == 24
+    for c in range(n):
+        K, psi0, xi, yi = frenet_ref.get_reference_frenet({"x": g["c%d_x" % c], "y": g["c%d_y" % c], "s": g["c%d_s" % c]})
+        Kg = g["c%d_K" % c]
+        sq = np.linspace(0.0, float(g["c%d_s" % c][-1]), 9)
+        # same least-squares problems, same LAPACK: the polynomials agree to rounding (compared as functions of s:
+        # the individual coefficients of an ill-conditioned cubic fit may differ in their last digits)
+        assert np.abs(np.polyval(K, sq) - np.polyval(Kg, sq)).max() <= 1e-12 * max(1.0, np.abs(np.polyval(Kg, sq)).max())
+        assert np.allclose(K, Kg, rtol=1e-7, atol=1e-13)
+        assert abs(psi0 - float(g["c%d_psi0" % c])) <= 1e-13
+        assert np.abs(xi - g["c%d_xi" % c]).max() <= 1e-10 and np.abs(yi - g["c%d_yi" % c]).max() <= 1e-10
+    # the batched form the workload uses solves the same two fits with fixed matrices instead of np.polyfit
+    for c in (0, 7, 19):
+        s, x, y = g["c%d_s" % c], g["c%d_x" % c], g["c%d_y" % c]
+        s_fit = np.arange(0.0, s[-1], 0.5)
+        Kb, pb = frenet_ref.fit_windows(np.interp(s_fit, s, x)[None], np.interp(s_fit, s, y)[None], float(s[-1]))
+        sq = np.linspace(0.0, float(s[-1]), 9)
+        Kg = g["c%d_K" % c]
+        assert np.abs(np.polyval(Kb[0], sq) - np.polyval(Kg, sq)).max() <= 1e-9 * max(1.0, np.abs(np.polyval(Kg, sq)).max())
+        assert abs(pb[0] - float(g["c%d_psi0" % c])) <= 1e-11
