@@ -10,9 +10,17 @@
  *
  * Conventions: plain C types only; every function returns 0 on success or a negative
  * MPCB200_E* code (message via mpcb200_last_error); the caller owns every buffer, the
- * library owns the opaque handle, its device scratch and its CUDA stream.  Calls on one
+ * library owns the opaque handle, its device scratch and its CUDA stream(s).  Calls on one
  * handle must be serialised by the caller; distinct handles are independent.  There is
  * no CPU fallback: without a CUDA device mpcb200_create fails with MPCB200_ENODEVICE.
+ *
+ * Multi-GPU: a handle created with n_devices > 1 owns one stream and one set of
+ * device buffers per GPU.  Calls with HOST pointers (mpcb200_solve_batch*, mpcb200_rollout) cut the
+ * batch into contiguous slices, one per device, run them concurrently and write every slice's
+ * results straight into the caller's one set of buffers -- problems are independent, nothing
+ * crosses GPUs, and the results do not depend on the device count.  Calls with DEVICE pointers and
+ * batches of at most 64 problems run on devices[0].  (Multi-process use, one rank per GPU under
+ * torchrun, gathers mpcb200_solve_batch_records' 32-byte records with one NCCL all-gather instead.)
  */
 #ifndef MPC_B200_H
 #define MPC_B200_H
@@ -23,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MPCB200_VERSION 1
+#define MPCB200_VERSION 2
 
 /* error codes */
 #define MPCB200_OK          0
@@ -65,6 +73,8 @@ typedef struct {
     double  a_dmax;       /* :45 */
     double  steer_dmax;   /* :42 */
     double  tol;          /* Ipopt tol, default 1e-8 */
+    int32_t n_devices;    /* 0 or 1: one GPU, `device`.  2..8: the GPUs devices[0..n_devices-1] (`device` is ignored) */
+    int32_t devices[8];   /* CUDA device ordinals, distinct */
 } mpcb200_config;
 
 typedef struct mpcb200_handle mpcb200_handle;
@@ -104,6 +114,21 @@ int mpcb200_solve_batch(mpcb200_handle* h, int64_t B,
                         double* u0, double* cost, int32_t* status, int32_t* iters,
                         double* traj, int32_t mem_space);
 
+/*
+ * mpcb200_solve_batch whose per-problem results come back as ONE packed 32-byte record
+ *   rec [B][4] doubles = { accel_cmd, steer_angle_cmd, cost, (int32 status | restorations << 8, int32 iters) }
+ * written by the solve kernel itself: the unit of the multi-GPU exchange (one all-gather of these records is the only
+ * inter-GPU traffic).  `restorations` = how many times the solve went through the restoration by rollout
+ * that stands in for Ipopt's restoration phase (0 for almost every problem).  traj and warm as in mpcb200_solve_batch.
+ */
+int mpcb200_solve_batch_records(mpcb200_handle* h, int64_t B,
+                                const double* state, const double* ref, const double* v_des,
+                                const double* u_prev, double* warm, double* rec, double* traj, int32_t mem_space);
+
+/* Per-problem restoration counts of the LAST solve_batch* call on this handle (host pointer, B = that call's batch):
+ * the problems whose line search failed where Ipopt would enter its restoration phase (MKZMPCPathFollower.jl:176). */
+int mpcb200_get_restorations(mpcb200_handle* h, int64_t B, int32_t* out);
+
 /* Path table for on-device reference generation (ref_gps_traj.py:106): columns t, X, Y, psi, s
  * of the trajectory matrix, n samples each, host pointers; copied to the device. */
 int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n,
@@ -120,7 +145,8 @@ int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n,
  *   v_des   [B] or NULL = target_vel for every problem (mpc_cmd_pub.jl:116 passes des_speed)
  *   ref_out [B][3][N+1] or NULL: the generated waypoints (what the node publishes as target_path)
  *   stop    [B] or NULL: get_waypoints' stop_cmd (1 when the last waypoint is the end of the path)
- * Horizons up to 31 only.  With MPCB200_DEVICE pointers all three path tables must have been set.
+ * With MPCB200_HOST pointers a path_of entry that was not set is refused (MPCB200_EINVAL); with MPCB200_DEVICE pointers
+ * the ids cannot be inspected on the host: such a problem comes back with status MPCB200_ERROR and zero commands.
  */
 int mpcb200_solve_batch_on_path(mpcb200_handle* h, int64_t B,
                                 const double* state, const int32_t* path_of,
@@ -137,7 +163,9 @@ int mpcb200_solve_batch_on_path(mpcb200_handle* h, int64_t B,
  *   pose0    [B][3]  X0, Y0, Psi0 ;  path_of [B] path_id per vehicle
  *   log      [T][B][8]  x, y, psi, v, acc_cmd, df_cmd, status, iters  (may be NULL)
  *   final    [B][8]  plant state X,Y,psi,vx,vy,wz,acc,df after T steps (may be NULL)
- * Host pointers only.
+ * Every vehicle's first solve starts from the solution of the module-load solve of the default problem
+ * (MKZMPCPathFollower.jl:36-39,126-128), as the node's does.  Host pointers only; any horizon the handle supports;
+ * vehicles are sharded over the handle's devices.
  */
 int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T,
                     const double* pose0, const int32_t* path_of,

@@ -7,17 +7,26 @@
 #
 # NOT EXECUTED in the build container (no Julia there); the identical call sequence is exercised by the Python
 # mirror mkz_mpc_path_follower_b200/mpc_path_follower.py::MKZMPCPathFollowerFrenet.
-# Written for Julia >= 1.0; under Julia 0.6 replace `mutable struct` by `type` and `Cvoid` by `Void`.
+# Julia versions: the shim itself is written to load under Julia 0.6 (`mutable struct` exists there; `Cvoid` is aliased
+# below) as well as >= 1.0.  The reference's own node scripts are Julia 0.6-era code (`unshift!`, JuMP `sum{}`, `@sprintf`
+# without `using Printf`): on Julia 0.6 they run on top of this shim as they are; on Julia >= 1.0 they need the same
+# one-line modernisations they would need with the original module.  Neither combination has been executed (no Julia in
+# the build container); what HAS driven this exact call sequence through the C ABI is the Python mirror and the plain-C
+# caller tests/c_abi/mpc_cmd_loop.c, and tests/test_c_abi.py checks this struct's field list against the C header.
 
 module MKZMPCPathFollowerFrenet
 
 const libmpc = get(ENV, "MPCB200_LIB", "libmpc_b200.so")
+@static if VERSION < v"0.7"
+    const Cvoid = Void
+end
 
 mutable struct Config   # mpcb200_config
     N::Int32; max_iter::Int32; start_mode::Int32; device::Int32
     dt::Float64; dt_control::Float64; L_a::Float64; L_b::Float64
     v_min::Float64; v_max::Float64; a_max::Float64; steer_max::Float64
     a_dmax::Float64; steer_dmax::Float64; tol::Float64
+    n_devices::Int32; devices::NTuple{8,Int32}
     Config() = new()
 end
 

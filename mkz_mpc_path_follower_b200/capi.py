@@ -21,7 +21,8 @@ class Config(C.Structure):
     _fields_ = [("N", C.c_int32), ("max_iter", C.c_int32), ("start_mode", C.c_int32), ("device", C.c_int32),
                 ("dt", C.c_double), ("dt_control", C.c_double), ("L_a", C.c_double), ("L_b", C.c_double),
                 ("v_min", C.c_double), ("v_max", C.c_double), ("a_max", C.c_double), ("steer_max", C.c_double),
-                ("a_dmax", C.c_double), ("steer_dmax", C.c_double), ("tol", C.c_double)]
+                ("a_dmax", C.c_double), ("steer_dmax", C.c_double), ("tol", C.c_double),
+                ("n_devices", C.c_int32), ("devices", C.c_int32 * 8)]
 
 
 class Stats(C.Structure):
@@ -54,6 +55,8 @@ def lib():
     L.mpcb200_set_cost.argtypes = [vp, dp]
     L.mpcb200_set_stream.argtypes = [vp, vp]
     L.mpcb200_solve_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
+    L.mpcb200_solve_batch_records.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
+    L.mpcb200_get_restorations.argtypes = [vp, C.c_int64, vp]
     L.mpcb200_create_frenet.argtypes = [C.POINTER(vp), C.POINTER(Config)]
     L.mpcb200_set_cost_frenet.argtypes = [vp, dp]
     L.mpcb200_solve_batch_frenet.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
@@ -68,13 +71,21 @@ def lib():
     return L
 
 
-def default_config(N=8, **overrides):
+def default_config(N=8, devices=None, **overrides):
+    """devices: list of CUDA ordinals for a multi-GPU handle (mpcb200_config.devices / n_devices); None = `device`."""
     c = Config()
     rc = lib().mpcb200_default_config(C.byref(c), N)
     if rc != 0:
         raise MpcB200Error(rc, "default_config")
     for k, v in overrides.items():
         setattr(c, k, v)
+    if devices is not None:
+        devices = list(devices)
+        if not 1 <= len(devices) <= 8:
+            raise ValueError("devices: 1 to 8 CUDA ordinals")
+        c.n_devices = len(devices)
+        for i, d in enumerate(devices):
+            c.devices[i] = int(d)
     return c
 
 
@@ -186,6 +197,33 @@ class Solver(object):
         self._check(lib().mpcb200_solve_batch_on_path(self._h, B, _ptr(state), _ptr(path_of), int(bool(track_using_time)), float(target_vel),
                                                       _ptr(v_des), _ptr(u_prev), _ptr(warm), _ptr(u0), _ptr(cost), _ptr(status),
                                                       _ptr(iters), _ptr(traj), _ptr(ref_out), _ptr(stop), DEVICE))
+
+    def solve_batch_records(self, state, ref, u_prev, v_des=None, warm=None):
+        """mpcb200_solve_batch_records with host arrays: returns the (B,4) float64 array of packed 32-byte records
+        (unpack with sharding.unpack_records_np)."""
+        N = self.N
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        B = state.shape[0]
+        ref = np.ascontiguousarray(ref, dtype=np.float64); u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+        if state.shape != (B, 4) or ref.shape != (B, 3, N + 1) or u_prev.shape != (B, 2):
+            raise ValueError("solve_batch_records: expected state (B,4), ref (B,3,N+1), u_prev (B,2)")
+        if v_des is not None:
+            v_des = np.ascontiguousarray(v_des, dtype=np.float64)
+        rec = np.empty((B, 4))
+        self._check(lib().mpcb200_solve_batch_records(self._h, B, _ptr(state), _ptr(ref), _ptr(v_des), _ptr(u_prev), _ptr(warm),
+                                                      _ptr(rec), None, HOST))
+        return rec
+
+    def solve_batch_records_device(self, B, state, ref, u_prev, rec, v_des=None, warm=None, traj=None):
+        """Device pointers; the kernel writes the (B,4) f64 record tensor `rec` itself; only enqueues on the handle's stream."""
+        self._check(lib().mpcb200_solve_batch_records(self._h, B, _ptr(state), _ptr(ref), _ptr(v_des), _ptr(u_prev), _ptr(warm),
+                                                      _ptr(rec), _ptr(traj), DEVICE))
+
+    def restorations(self, B):
+        """Per-problem count of restorations by rollout in the last solve_batch* call (mpcb200_get_restorations)."""
+        out = np.empty(B, dtype=np.int32)
+        self._check(lib().mpcb200_get_restorations(self._h, B, _ptr(out)))
+        return out
 
     def solve_batch_device(self, B, state, ref, u_prev, u0, v_des=None, warm=None, cost=None, status=None,
                            iters=None, traj=None):

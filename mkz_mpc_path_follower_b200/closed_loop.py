@@ -36,7 +36,9 @@ def run(path_ids, pose0, T, N=8, dt=0.2, track_using_time=True, target_vel=1.0, 
     sim = VehicleSimulator(X0=pose0[:, 0], Y0=pose0[:, 1], Psi0=pose0[:, 2], batch=B)
     des_speed = target_vel if target_vel > 0.0 else 0.0          # mpc_cmd_pub.jl:58-62
     u_curr = np.zeros((B, 2))                                    # d_f_current, acc_current = 0 (:75,:82)
-    warm = np.zeros((B, 6 * N + 4))                              # start = 0.0 (:65-72)
+    # the first solve starts from the solution of the module-load solve of the default problem (MKZMPCPathFollower.jl:
+    # 126-128; JuMP re-solves from the previous primal values), every later one from the previous solution
+    warm = np.repeat(module_load_solution(N, device=solver.cfg.device)[None], B, axis=0)
     command_stop = np.zeros(B, dtype=bool)
     log = np.zeros((T, B, 8))
     ref = np.empty((B, 3, N + 1))
@@ -62,6 +64,21 @@ def run(path_ids, pose0, T, N=8, dt=0.2, track_using_time=True, target_vel=1.0, 
     if own:
         solver.close()
     return {"log": log, "final_state": sim.full_state(), "command_stop": command_stop}
+
+
+_seed_cache = {}
+
+
+def module_load_solution(N, device=0):
+    """(6N+4,) solution of the default problem of MKZMPCPathFollower.jl:36-39,75,82,110-113 (zero state and previous
+    command, x_ref = 15 t, y_ref = psi_ref = 0, v_target = 15, module-default weights, start = 0.0), solved by the library."""
+    if N not in _seed_cache:
+        s = capi.Solver(N, device=device)   # a fresh handle holds the module-default weights
+        ref = np.zeros((1, 3, N + 1)); ref[0, 0] = 15.0 * (np.arange(N + 1) * s.cfg.dt)
+        out = s.solve_batch(np.zeros((1, 4)), ref, np.zeros((1, 2)), v_des=np.array([15.0]), want_traj=True)
+        s.close()
+        _seed_cache[N] = out["traj"][0].copy()
+    return _seed_cache[N]
 
 
 def path_errors(log, traj_table):

@@ -104,7 +104,26 @@ mpc_rollout_kernel(const KCfg cfg, const RolloutArgs args, unsigned long long* c
         const unsigned long long b0 = next_group;
         __syncthreads();
         if (b0 >= (unsigned long long)args.B) break;
-        rollout_group(cfg, args, (long)b0, smem, px, WARPS_PER_BLOCK);
+        rollout_group<1>(cfg, args, (long)b0, smem, px, WARPS_PER_BLOCK);
+    }
+}
+
+// Closed-loop rollouts at long horizons (32 <= N <= 95): one vehicle per block of W = 2 or 3 warps
+template <int W>
+__global__ void __launch_bounds__(W * 32, W == 2 ? 4 : 2)
+mpc_rollout_long_kernel(const KCfg cfg, const RolloutArgs args, unsigned long long* counter) {
+    extern __shared__ double smem_all[];
+    __shared__ unsigned long long next_vehicle;
+    const smem_t smem = smem_base(smem_all);
+    const smem_t px = smem_base(smem_all + (size_t)smem_doubles_per_team(cfg.N));
+    TeamSolver<W>::init_work(smem, cfg.N);
+    for (;;) {
+        if (threadIdx.x == 0) next_vehicle = atomicAdd(counter, 1ULL);
+        __syncthreads();
+        const unsigned long long b0 = next_vehicle;
+        __syncthreads();
+        if (b0 >= (unsigned long long)args.B) break;
+        rollout_group<W>(cfg, args, (long)b0, smem, px, 1);
     }
 }
 
@@ -143,6 +162,15 @@ struct mpcb200_handle {
     int* d_roles = nullptr;   /* lane roles of the Riccati recursion for this horizon (riccati_roles) */
     DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
     DevBuf d_path[3], d_pose, d_pathof, d_log, d_final, d_stop;
+    DevBuf d_rec, d_resto;        /* packed 32-byte records; restoration count per problem of the last solve */
+    DevBuf d_seed;                /* the module-load solution (start point of a rollout's first solve), [6N+4] */
+    bool seed_valid = false;
+    int64_t last_B = 0;           /* batch of the last solve (mpcb200_get_restorations) */
+    /* multi-GPU: the handle itself works on devices[0]; sub[i] on devices[i + 1] */
+    int n_sub = 0;
+    mpcb200_handle* sub[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t slice_lo[8] = {0, 0, 0, 0, 0, 0, 0, 0}, slice_hi[8] = {0, 0, 0, 0, 0, 0, 0, 0};   /* slices of the last sharded call */
+    bool last_sharded = false;
     DevBuf d_stage;               /* small batches: one contiguous device buffer, one copy each way */
     void* h_stage = nullptr;      /* its pinned host mirror */
     size_t h_stage_cap = 0;
@@ -226,12 +254,41 @@ int mpcb200_default_config(mpcb200_config* c, int32_t N) {
     c->a_dmax = 1.5;       /* :45 */
     c->steer_dmax = 0.5;   /* :42 */
     c->tol = 1e-8;
+    c->n_devices = 0;      /* one GPU: `device` */
     return MPCB200_OK;
 }
 
 static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int model);
-int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) { return create_impl(out, cfg, 0); }
-int mpcb200_create_frenet(mpcb200_handle** out, const mpcb200_config* cfg) { return create_impl(out, cfg, 1); }
+static int create_multi(mpcb200_handle** out, const mpcb200_config* cfg, int model);
+int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) { return create_multi(out, cfg, 0); }
+int mpcb200_create_frenet(mpcb200_handle** out, const mpcb200_config* cfg) { return create_multi(out, cfg, 1); }
+
+/* n_devices > 1: one full single-GPU handle per device; the first one is the handle the caller holds */
+static int create_multi(mpcb200_handle** out, const mpcb200_config* cfg, int model) {
+    if (!out || !cfg) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: NULL argument");
+    *out = nullptr;
+    if (cfg->n_devices < 0 || cfg->n_devices > 8) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: n_devices=%d outside [0,8]", cfg->n_devices);
+    if (cfg->n_devices <= 1) {
+        mpcb200_config c1 = *cfg;
+        if (cfg->n_devices == 1) c1.device = cfg->devices[0];
+        return create_impl(out, &c1, model);
+    }
+    for (int i = 0; i < cfg->n_devices; i++)
+        for (int j = 0; j < i; j++)
+            if (cfg->devices[i] == cfg->devices[j]) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: device %d listed twice", cfg->devices[i]);
+    mpcb200_handle* first = nullptr;
+    for (int i = 0; i < cfg->n_devices; i++) {
+        mpcb200_config ci = *cfg;
+        ci.device = cfg->devices[i];
+        mpcb200_handle* hi = nullptr;
+        const int rc = create_impl(&hi, &ci, model);
+        if (rc) { if (first) mpcb200_destroy(first); return rc; }
+        if (i == 0) first = hi; else first->sub[first->n_sub++] = hi;
+    }
+    first->cfg.n_devices = cfg->n_devices;
+    *out = first;
+    return MPCB200_OK;
+}
 
 static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int model) {
     if (!out || !cfg) return fail(nullptr, MPCB200_EINVAL, "mpcb200_create: NULL argument");
@@ -321,6 +378,12 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
         TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, fn, h->team_warps * 32, h->smem_bytes));
+        const void* fr = (h->team_warps == 2) ? (const void*)mpc_rollout_long_kernel<2> : (const void*)mpc_rollout_long_kernel<3>;
+        const size_t rb = h->smem_bytes + ROLLOUT_PX * sizeof(double);
+        TRY_OR_FREE(cudaFuncSetAttribute(fr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb));
+        TRY_OR_FREE(cudaFuncSetAttribute(fr, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, fr, h->team_warps * 32, rb));
+        if (h->rollout_blocks_per_sm < 1) h->rollout_blocks_per_sm = 1;
     }
     if (h->blocks_per_sm < 1) h->blocks_per_sm = 1;
     if (const char* e = getenv("MPCB200_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v; }  /* tuning aid */
@@ -331,9 +394,12 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
 
 int mpcb200_destroy(mpcb200_handle* h) {
     if (!h) return MPCB200_EINVAL;
+    for (int i = 0; i < h->n_sub; i++) if (h->sub[i]) mpcb200_destroy(h->sub[i]);
+    h->n_sub = 0;
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj,
-                      &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop, &h->d_stage};
+                      &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop, &h->d_stage,
+                      &h->d_rec, &h->d_resto, &h->d_seed};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_roles) cudaFree(h->d_roles);
@@ -351,9 +417,11 @@ int mpcb200_set_cost(mpcb200_handle* h, const double w[8]) {
     for (int i = 0; i < 8; i++) if (!(w[i] >= 0.0)) return fail(h, MPCB200_EINVAL, "mpcb200_set_cost: weight %d is negative or NaN", i);
     memcpy(h->w, w, 8 * sizeof(double));
     drop_graphs(h);   /* the weights are kernel parameters */
+    for (int i = 0; i < h->n_sub; i++) { memcpy(h->sub[i]->w, w, 8 * sizeof(double)); drop_graphs(h->sub[i]); }
     return MPCB200_OK;
 }
 
+/* the stream of devices[0]; the other devices of a multi-GPU handle keep their own streams */
 int mpcb200_set_stream(mpcb200_handle* h, void* s) {
     if (!h) return MPCB200_EINVAL;
     h->stream = s ? (cudaStream_t)s : h->own_stream;
@@ -398,19 +466,56 @@ static void fill_paths(const mpcb200_handle* h, PathTable* paths) {
     }
 }
 
+/* the arguments of one solve call (host or device pointers) */
+struct SolveArgs {
+    const char* who;
+    const double* state; const double* ref; const int32_t* path_of;
+    int32_t track_using_time; double target_vel;
+    const double* v_des; const double* u_prev; double* warm;
+    double* u0; double* cost; int32_t* status; int32_t* iters; double* traj;
+    double* ref_out; int32_t* stop; double* rec;
+};
+
+/* a contiguous slice [lo, lo + n) of a call's problems */
+static SolveArgs slice_args(const SolveArgs& a, int64_t lo, int N, int model) {
+    const size_t nt = 6 * (size_t)N + 4, nr = model ? 4 : 3 * ((size_t)N + 1);
+    SolveArgs s = a;
+    s.state = a.state + 4 * lo;
+    if (a.ref) s.ref = a.ref + nr * lo;
+    if (a.path_of) s.path_of = a.path_of + lo;
+    if (a.v_des) s.v_des = a.v_des + lo;
+    s.u_prev = a.u_prev + 2 * lo;
+    if (a.warm) s.warm = a.warm + nt * lo;
+    if (a.u0) s.u0 = a.u0 + 2 * lo;
+    if (a.cost) s.cost = a.cost + lo;
+    if (a.status) s.status = a.status + lo;
+    if (a.iters) s.iters = a.iters + lo;
+    if (a.traj) s.traj = a.traj + nt * lo;
+    if (a.ref_out) s.ref_out = a.ref_out + 3 * ((size_t)N + 1) * lo;
+    if (a.stop) s.stop = a.stop + lo;
+    if (a.rec) s.rec = a.rec + 4 * lo;
+    return s;
+}
+
+/* contiguous slice of `total` owned by part `i` of `parts`; sizes differ by at most one (same rule as sharding.shard_range) */
+static void shard_range(int64_t total, int parts, int i, int64_t* lo, int64_t* hi) {
+    const int64_t base = total / parts, rem = total % parts;
+    *lo = i * base + (i < rem ? i : rem);
+    *hi = *lo + base + (i < rem ? 1 : 0);
+}
+
 /* Host pointers, small batch (the control loop's batch of one): latency is the driver calls, not the bytes.  All
  * inputs are packed into one pinned buffer (with the zeroed problem counter in front) and go over in ONE copy, all
  * outputs come back in ONE copy: 7 driver calls instead of ~16. */
 static const int64_t SMALL_BATCH = 64;
-static int solve_small_host(mpcb200_handle* h, int64_t B, const double* state, const double* ref, const double* v_des,
-                            const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
-                            double* traj) {
+static int solve_small_host(mpcb200_handle* h, int64_t B, const SolveArgs& a) {
     const int N = h->cfg.N;
     const size_t nt = 6 * (size_t)N + 4, nr = h->model ? 4 : 3 * ((size_t)N + 1);
-    /* layout in doubles: [counter, pad] state ref uprev vdes | warm | u0 cost traj status/iters(int32 pairs) */
+    /* layout in doubles: [counter, pad] state ref uprev vdes | warm | u0 cost traj status/iters(int32 pairs) resto rec */
     const size_t o_state = 2, o_ref = o_state + 4 * B, o_uprev = o_ref + nr * B, o_vdes = o_uprev + 2 * B, o_warm = o_vdes + B;
     const size_t o_u0 = o_warm + nt * B, o_cost = o_u0 + 2 * B, o_traj = o_cost + B, o_stat = o_traj + nt * B, o_iter = o_stat + (B + 1) / 2;
-    const size_t total = o_iter + (B + 1) / 2;
+    const size_t o_resto = o_iter + (B + 1) / 2, o_rec = o_resto + (B + 1) / 2;
+    const size_t total = o_rec + (a.rec ? 4 * B : 0);
     const size_t bytes = total * sizeof(double);
     int rc;
     if (bytes > h->d_stage.cap || bytes > h->h_stage_cap) drop_graphs(h);   /* the graphs hold the old addresses */
@@ -424,18 +529,19 @@ static int solve_small_host(mpcb200_handle* h, int64_t B, const double* state, c
     double* hs = (double*)h->h_stage;
     double* ds = (double*)h->d_stage.p;
     hs[0] = 0.0; hs[1] = 0.0;   /* the problem counter (all-zero bits) */
-    memcpy(hs + o_state, state, 4 * B * sizeof(double));
-    memcpy(hs + o_ref, ref, nr * B * sizeof(double));
-    memcpy(hs + o_uprev, u_prev, 2 * B * sizeof(double));
-    if (v_des) memcpy(hs + o_vdes, v_des, B * sizeof(double));
-    if (warm) memcpy(hs + o_warm, warm, nt * B * sizeof(double));
-    const size_t in_doubles = warm ? o_u0 : o_warm;
+    memcpy(hs + o_state, a.state, 4 * B * sizeof(double));
+    memcpy(hs + o_ref, a.ref, nr * B * sizeof(double));
+    memcpy(hs + o_uprev, a.u_prev, 2 * B * sizeof(double));
+    if (a.v_des) memcpy(hs + o_vdes, a.v_des, B * sizeof(double));
+    if (a.warm) memcpy(hs + o_warm, a.warm, nt * B * sizeof(double));
+    const size_t in_doubles = a.warm ? o_u0 : o_warm;
     cudaStream_t s = h->stream;
-    BatchPtrs io{ds + o_state, ds + o_ref, v_des ? ds + o_vdes : nullptr, ds + o_uprev, warm ? ds + o_warm : nullptr, ds + o_u0,
-                 ds + o_cost, (int*)(ds + o_stat), (int*)(ds + o_iter), traj ? ds + o_traj : nullptr};
+    BatchPtrs io{ds + o_state, ds + o_ref, a.v_des ? ds + o_vdes : nullptr, ds + o_uprev, a.warm ? ds + o_warm : nullptr, ds + o_u0,
+                 ds + o_cost, (int*)(ds + o_stat), (int*)(ds + o_iter), a.traj ? ds + o_traj : nullptr,
+                 a.rec ? ds + o_rec : nullptr, (int*)(ds + o_resto)};
     RefGen rg;
     memset(&rg, 0, sizeof(rg));
-    const size_t out_from = warm ? o_warm : o_u0;
+    const size_t out_from = a.warm ? o_warm : o_u0;
     /* the sequence copy in -> kernel -> copy out; `ext`: events recorded from inside a graph need the external flag to be timed */
     auto enqueue = [&](bool ext) -> int {
         CUDA_TRY(h, cudaMemcpyAsync(ds, hs, in_doubles * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -448,7 +554,7 @@ static int solve_small_host(mpcb200_handle* h, int64_t B, const double* state, c
     };
     bool launched = false;
     if (h->graphs_ok && s == h->own_stream) {
-        const int flags = (v_des ? 1 : 0) | (warm ? 2 : 0) | (traj ? 4 : 0);
+        const int flags = (a.v_des ? 1 : 0) | (a.warm ? 2 : 0) | (a.traj ? 4 : 0) | (a.rec ? 8 : 0);
         cudaGraphExec_t exec = nullptr;
         for (int i = 0; i < h->n_graphs; i++) if (h->graphs[i].B == B && h->graphs[i].flags == flags) exec = h->graphs[i].exec;
         if (!exec) {
@@ -478,100 +584,16 @@ static int solve_small_host(mpcb200_handle* h, int64_t B, const double* state, c
     h->stats.h2d_bytes += in_doubles * sizeof(double);
     h->stats.d2h_bytes += (total - out_from) * sizeof(double);
     CUDA_TRY(h, cudaStreamSynchronize(s));
-    memcpy(u0, hs + o_u0, 2 * B * sizeof(double));
-    if (cost) memcpy(cost, hs + o_cost, B * sizeof(double));
-    if (status) memcpy(status, hs + o_stat, B * sizeof(int32_t));
-    if (iters) memcpy(iters, hs + o_iter, B * sizeof(int32_t));
-    if (traj) memcpy(traj, hs + o_traj, nt * B * sizeof(double));
-    if (warm) memcpy(warm, hs + o_warm, nt * B * sizeof(double));
-    float ms = 0.f;
-    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    h->stats.kernel_ms = ms;
-    return MPCB200_OK;
-}
-
-/* common body of mpcb200_solve_batch (ref given) and mpcb200_solve_batch_on_path (path_of given) */
-static int solve_batch_impl(mpcb200_handle* h, const char* who, int64_t B, const double* state, const double* ref, const int32_t* path_of,
-                            int32_t track_using_time, double target_vel, const double* v_des, const double* u_prev, double* warm,
-                            double* u0, double* cost, int32_t* status, int32_t* iters, double* traj, double* ref_out, int32_t* stop,
-                            int32_t mem_space) {
-    if (!h) return MPCB200_EINVAL;
-    if (B < 0) return fail(h, MPCB200_EINVAL, "%s: B=%lld", who, (long long)B);
-    if (mem_space != MPCB200_HOST && mem_space != MPCB200_DEVICE) return fail(h, MPCB200_EINVAL, "%s: mem_space=%d", who, mem_space);
-    memset(&h->stats, 0, sizeof(h->stats));
-    if (B == 0) return MPCB200_OK;
-    const bool on_path = (path_of != nullptr);
-    if (!state || (!ref && !on_path) || !u_prev || !u0) return fail(h, MPCB200_EINVAL, "%s: state, %s, u_prev and u0 are required", who, on_path ? "path_of" : "ref");
-    if (on_path && h->model) return fail(h, MPCB200_EINVAL, "%s: not available for the Frenet-frame variant", who);
-    if (on_path && h->team_warps != 1) return fail(h, MPCB200_EINVAL, "%s: on-device reference generation needs N <= 31 (N=%d)", who, h->cfg.N);
-    CUDA_TRY(h, cudaSetDevice(h->device));
-    const int N = h->cfg.N;
-    const size_t nt = 6 * (size_t)N + 4, nr = h->model ? 4 : 3 * ((size_t)N + 1);
-    RefGen rg;
-    memset(&rg, 0, sizeof(rg));
-    if (on_path) {
-        fill_paths(h, rg.paths);
-        rg.track_using_time = track_using_time; rg.target_vel = target_vel;
-        if (mem_space == MPCB200_HOST) {
-            for (int64_t b = 0; b < B; b++)
-                if (path_of[b] < 0 || path_of[b] > 2 || h->path_n[path_of[b]] == 0)
-                    return fail(h, MPCB200_EINVAL, "%s: problem %lld uses path %d, which was not set with mpcb200_set_path", who, (long long)b, path_of[b]);
-        } else {
-            for (int i = 0; i < 3; i++)   /* device ids cannot be inspected here: every table must be present */
-                if (h->path_n[i] == 0) return fail(h, MPCB200_EINVAL, "%s: with device pointers all three path tables must be set (path %d is not)", who, i);
-        }
-    }
-    if (mem_space == MPCB200_DEVICE) {
-        BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj};
-        rg.path_of = path_of; rg.ref_out = ref_out; rg.stop = stop;
-        return launch_solve(h, B, io, rg);
-    }
-    if (!on_path && B <= SMALL_BATCH) return solve_small_host(h, B, state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj);
-    /* host pointers: stage through the handle's device buffers */
-    const size_t bs = B * 4 * sizeof(double), br = B * nr * sizeof(double), bu = B * 2 * sizeof(double), bt = B * nt * sizeof(double);
-    int rc;
-    if ((rc = ensure(h, h->d_state, bs))) return rc;
-    if ((!on_path || ref_out) && (rc = ensure(h, h->d_ref, br))) return rc;
-    if (on_path && (rc = ensure(h, h->d_pathof, B * sizeof(int32_t)))) return rc;
-    if (on_path && stop && (rc = ensure(h, h->d_stop, B * sizeof(int32_t)))) return rc;
-    if ((rc = ensure(h, h->d_uprev, bu))) return rc;
-    if ((rc = ensure(h, h->d_u0, bu))) return rc;
-    if (v_des && (rc = ensure(h, h->d_vdes, B * sizeof(double)))) return rc;
-    if (warm && (rc = ensure(h, h->d_warm, bt))) return rc;
-    if (cost && (rc = ensure(h, h->d_cost, B * sizeof(double)))) return rc;
-    if (status && (rc = ensure(h, h->d_status, B * sizeof(int32_t)))) return rc;
-    if (iters && (rc = ensure(h, h->d_iters, B * sizeof(int32_t)))) return rc;
-    if (traj && (rc = ensure(h, h->d_traj, bt))) return rc;
-    cudaStream_t s = h->stream;
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, state, bs, cudaMemcpyHostToDevice, s));
-    h->stats.h2d_bytes += bs;
-    if (on_path) { CUDA_TRY(h, cudaMemcpyAsync(h->d_pathof.p, path_of, B * sizeof(int32_t), cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += B * sizeof(int32_t); }
-    else { CUDA_TRY(h, cudaMemcpyAsync(h->d_ref.p, ref, br, cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += br; }
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_uprev.p, u_prev, bu, cudaMemcpyHostToDevice, s));
-    h->stats.h2d_bytes += bu;
-    if (v_des) { CUDA_TRY(h, cudaMemcpyAsync(h->d_vdes.p, v_des, B * sizeof(double), cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += B * sizeof(double); }
-    if (warm) { CUDA_TRY(h, cudaMemcpyAsync(h->d_warm.p, warm, bt, cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += bt; }
-    BatchPtrs io{(const double*)h->d_state.p, on_path ? nullptr : (const double*)h->d_ref.p, v_des ? (const double*)h->d_vdes.p : nullptr,
-                 (const double*)h->d_uprev.p, warm ? (double*)h->d_warm.p : nullptr, (double*)h->d_u0.p,
-                 cost ? (double*)h->d_cost.p : nullptr, status ? (int*)h->d_status.p : nullptr,
-                 iters ? (int*)h->d_iters.p : nullptr, traj ? (double*)h->d_traj.p : nullptr};
-    if (on_path) {
-        rg.path_of = (const int*)h->d_pathof.p;
-        rg.ref_out = ref_out ? (double*)h->d_ref.p : nullptr;
-        rg.stop = stop ? (int*)h->d_stop.p : nullptr;
-    }
-    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
-    if ((rc = launch_solve(h, B, io, rg))) return rc;
-    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
-    CUDA_TRY(h, cudaMemcpyAsync(u0, h->d_u0.p, bu, cudaMemcpyDeviceToHost, s));
-    h->stats.d2h_bytes += bu;
-    if (cost) { CUDA_TRY(h, cudaMemcpyAsync(cost, h->d_cost.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(double); }
-    if (status) { CUDA_TRY(h, cudaMemcpyAsync(status, h->d_status.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
-    if (iters) { CUDA_TRY(h, cudaMemcpyAsync(iters, h->d_iters.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
-    if (traj) { CUDA_TRY(h, cudaMemcpyAsync(traj, h->d_traj.p, bt, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bt; }
-    if (warm) { CUDA_TRY(h, cudaMemcpyAsync(warm, h->d_warm.p, bt, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bt; }
-    if (on_path && ref_out) { CUDA_TRY(h, cudaMemcpyAsync(ref_out, h->d_ref.p, br, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += br; }
-    if (on_path && stop) { CUDA_TRY(h, cudaMemcpyAsync(stop, h->d_stop.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
+    if (a.u0) memcpy(a.u0, hs + o_u0, 2 * B * sizeof(double));
+    if (a.cost) memcpy(a.cost, hs + o_cost, B * sizeof(double));
+    if (a.status) memcpy(a.status, hs + o_stat, B * sizeof(int32_t));
+    if (a.iters) memcpy(a.iters, hs + o_iter, B * sizeof(int32_t));
+    if (a.traj) memcpy(a.traj, hs + o_traj, nt * B * sizeof(double));
+    if (a.warm) memcpy(a.warm, hs + o_warm, nt * B * sizeof(double));
+    if (a.rec) memcpy(a.rec, hs + o_rec, 4 * B * sizeof(double));
+    /* keep the restoration counts where mpcb200_get_restorations looks for them */
+    if ((rc = ensure(h, h->d_resto, B * sizeof(int32_t)))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_resto.p, hs + o_resto, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     float ms = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -579,12 +601,172 @@ static int solve_batch_impl(mpcb200_handle* h, const char* who, int64_t B, const
     return MPCB200_OK;
 }
 
+/* HOST pointers, one device: stage the slice through the handle's device buffers and launch (asynchronous) ... */
+static int host_enqueue(mpcb200_handle* h, int64_t B, const SolveArgs& a, const RefGen& rg0) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool on_path = (a.path_of != nullptr);
+    const int N = h->cfg.N;
+    const size_t nt = 6 * (size_t)N + 4, nr = h->model ? 4 : 3 * ((size_t)N + 1);
+    const size_t bs = B * 4 * sizeof(double), br = B * nr * sizeof(double), bu = B * 2 * sizeof(double), bt = B * nt * sizeof(double);
+    int rc;
+    if ((rc = ensure(h, h->d_state, bs))) return rc;
+    if ((!on_path || a.ref_out) && (rc = ensure(h, h->d_ref, br))) return rc;
+    if (on_path && (rc = ensure(h, h->d_pathof, B * sizeof(int32_t)))) return rc;
+    if (on_path && a.stop && (rc = ensure(h, h->d_stop, B * sizeof(int32_t)))) return rc;
+    if ((rc = ensure(h, h->d_uprev, bu))) return rc;
+    if ((rc = ensure(h, h->d_u0, bu))) return rc;
+    if (a.v_des && (rc = ensure(h, h->d_vdes, B * sizeof(double)))) return rc;
+    if (a.warm && (rc = ensure(h, h->d_warm, bt))) return rc;
+    if (a.cost && (rc = ensure(h, h->d_cost, B * sizeof(double)))) return rc;
+    if (a.status && (rc = ensure(h, h->d_status, B * sizeof(int32_t)))) return rc;
+    if (a.iters && (rc = ensure(h, h->d_iters, B * sizeof(int32_t)))) return rc;
+    if (a.traj && (rc = ensure(h, h->d_traj, bt))) return rc;
+    if (a.rec && (rc = ensure(h, h->d_rec, B * 4 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->d_resto, B * sizeof(int32_t)))) return rc;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_state.p, a.state, bs, cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += bs;
+    if (on_path) { CUDA_TRY(h, cudaMemcpyAsync(h->d_pathof.p, a.path_of, B * sizeof(int32_t), cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += B * sizeof(int32_t); }
+    else { CUDA_TRY(h, cudaMemcpyAsync(h->d_ref.p, a.ref, br, cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += br; }
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_uprev.p, a.u_prev, bu, cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += bu;
+    if (a.v_des) { CUDA_TRY(h, cudaMemcpyAsync(h->d_vdes.p, a.v_des, B * sizeof(double), cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += B * sizeof(double); }
+    if (a.warm) { CUDA_TRY(h, cudaMemcpyAsync(h->d_warm.p, a.warm, bt, cudaMemcpyHostToDevice, s)); h->stats.h2d_bytes += bt; }
+    BatchPtrs io{(const double*)h->d_state.p, on_path ? nullptr : (const double*)h->d_ref.p, a.v_des ? (const double*)h->d_vdes.p : nullptr,
+                 (const double*)h->d_uprev.p, a.warm ? (double*)h->d_warm.p : nullptr, (double*)h->d_u0.p,
+                 a.cost ? (double*)h->d_cost.p : nullptr, a.status ? (int*)h->d_status.p : nullptr,
+                 a.iters ? (int*)h->d_iters.p : nullptr, a.traj ? (double*)h->d_traj.p : nullptr,
+                 a.rec ? (double*)h->d_rec.p : nullptr, (int*)h->d_resto.p};
+    RefGen rg = rg0;
+    if (on_path) {
+        fill_paths(h, rg.paths);   /* this device's copies of the tables */
+        rg.path_of = (const int*)h->d_pathof.p;
+        rg.ref_out = a.ref_out ? (double*)h->d_ref.p : nullptr;
+        rg.stop = a.stop ? (int*)h->d_stop.p : nullptr;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    if ((rc = launch_solve(h, B, io, rg))) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    return MPCB200_OK;
+}
+
+/* ... and bring the slice's results back into the caller's buffers (synchronises the device's stream) */
+static int host_collect(mpcb200_handle* h, int64_t B, const SolveArgs& a) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool on_path = (a.path_of != nullptr);
+    const int N = h->cfg.N;
+    const size_t nt = 6 * (size_t)N + 4, nr = h->model ? 4 : 3 * ((size_t)N + 1);
+    const size_t br = B * nr * sizeof(double), bu = B * 2 * sizeof(double), bt = B * nt * sizeof(double);
+    cudaStream_t s = h->stream;
+    if (a.u0) { CUDA_TRY(h, cudaMemcpyAsync(a.u0, h->d_u0.p, bu, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bu; }
+    if (a.cost) { CUDA_TRY(h, cudaMemcpyAsync(a.cost, h->d_cost.p, B * sizeof(double), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(double); }
+    if (a.status) { CUDA_TRY(h, cudaMemcpyAsync(a.status, h->d_status.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
+    if (a.iters) { CUDA_TRY(h, cudaMemcpyAsync(a.iters, h->d_iters.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
+    if (a.traj) { CUDA_TRY(h, cudaMemcpyAsync(a.traj, h->d_traj.p, bt, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bt; }
+    if (a.warm) { CUDA_TRY(h, cudaMemcpyAsync(a.warm, h->d_warm.p, bt, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bt; }
+    if (a.rec) { CUDA_TRY(h, cudaMemcpyAsync(a.rec, h->d_rec.p, B * 4 * sizeof(double), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * 4 * sizeof(double); }
+    if (on_path && a.ref_out) { CUDA_TRY(h, cudaMemcpyAsync(a.ref_out, h->d_ref.p, br, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += br; }
+    if (on_path && a.stop) { CUDA_TRY(h, cudaMemcpyAsync(a.stop, h->d_stop.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += B * sizeof(int32_t); }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
+    return MPCB200_OK;
+}
+
+/* a sub-handle's error text and counters surface through the handle the caller holds */
+static int sub_fail(mpcb200_handle* h, mpcb200_handle* d, int rc) {
+    if (d != h) snprintf(h->err, sizeof(h->err), "device %d: %.400s", d->device, d->err);
+    return rc;
+}
+
+/* common body of mpcb200_solve_batch* (ref given) and mpcb200_solve_batch_on_path (path_of given) */
+static int solve_batch_impl(mpcb200_handle* h, int64_t B, const SolveArgs& a, int32_t mem_space) {
+    const char* who = a.who;
+    if (!h) return MPCB200_EINVAL;
+    if (B < 0) return fail(h, MPCB200_EINVAL, "%s: B=%lld", who, (long long)B);
+    if (mem_space != MPCB200_HOST && mem_space != MPCB200_DEVICE) return fail(h, MPCB200_EINVAL, "%s: mem_space=%d", who, mem_space);
+    memset(&h->stats, 0, sizeof(h->stats));
+    h->last_B = B; h->last_sharded = false;
+    if (B == 0) return MPCB200_OK;
+    const bool on_path = (a.path_of != nullptr);
+    if (!a.state || (!a.ref && !on_path) || !a.u_prev || (!a.u0 && !a.rec))
+        return fail(h, MPCB200_EINVAL, "%s: state, %s, u_prev and %s are required", who, on_path ? "path_of" : "ref", a.rec ? "rec" : "u0");
+    if (on_path && h->model) return fail(h, MPCB200_EINVAL, "%s: not available for the Frenet-frame variant", who);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    RefGen rg;
+    memset(&rg, 0, sizeof(rg));
+    if (on_path) {
+        fill_paths(h, rg.paths);
+        rg.track_using_time = a.track_using_time;
+        rg.target_vel = a.target_vel > 0.0 ? a.target_vel : 0.0;   /* des_speed, mpc_cmd_pub.jl:58-62 */
+        if (mem_space == MPCB200_HOST) {
+            for (int64_t b = 0; b < B; b++)
+                if (a.path_of[b] < 0 || a.path_of[b] > 2 || h->path_n[a.path_of[b]] == 0)
+                    return fail(h, MPCB200_EINVAL, "%s: problem %lld uses path %d, which was not set with mpcb200_set_path", who, (long long)b, a.path_of[b]);
+        }
+    }
+    if (mem_space == MPCB200_DEVICE) {
+        int rc;
+        if ((rc = ensure(h, h->d_resto, B * sizeof(int32_t)))) return rc;
+        BatchPtrs io{a.state, a.ref, a.v_des, a.u_prev, a.warm, a.u0, a.cost, a.status, a.iters, a.traj, a.rec, (int*)h->d_resto.p};
+        rg.path_of = a.path_of; rg.ref_out = a.ref_out; rg.stop = a.stop;
+        return launch_solve(h, B, io, rg);
+    }
+    if (!on_path && B <= SMALL_BATCH) return solve_small_host(h, B, a);
+    /* host pointers: one contiguous slice per device, all devices working at once */
+    const int parts = (B >= 2 * (int64_t)(h->n_sub + 1)) ? h->n_sub + 1 : 1;
+    mpcb200_handle* dev[8];
+    dev[0] = h;
+    for (int i = 0; i < h->n_sub; i++) dev[i + 1] = h->sub[i];
+    int rc;
+    for (int i = 0; i < parts; i++) {
+        shard_range(B, parts, i, &h->slice_lo[i], &h->slice_hi[i]);
+        if (i) memset(&dev[i]->stats, 0, sizeof(mpcb200_stats));
+        if ((rc = host_enqueue(dev[i], h->slice_hi[i] - h->slice_lo[i], slice_args(a, h->slice_lo[i], h->cfg.N, h->model), rg))) return sub_fail(h, dev[i], rc);
+    }
+    for (int i = 0; i < parts; i++)
+        if ((rc = host_collect(dev[i], h->slice_hi[i] - h->slice_lo[i], slice_args(a, h->slice_lo[i], h->cfg.N, h->model)))) return sub_fail(h, dev[i], rc);
+    for (int i = 1; i < parts; i++) {
+        h->stats.kernel_launches += dev[i]->stats.kernel_launches;
+        h->stats.h2d_bytes += dev[i]->stats.h2d_bytes; h->stats.d2h_bytes += dev[i]->stats.d2h_bytes;
+        if (dev[i]->stats.kernel_ms > h->stats.kernel_ms) h->stats.kernel_ms = dev[i]->stats.kernel_ms;   /* the devices run concurrently */
+    }
+    h->last_sharded = parts > 1;
+    for (int i = parts; i < 8; i++) h->slice_lo[i] = h->slice_hi[i] = 0;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return MPCB200_OK;
+}
+
+int mpcb200_get_restorations(mpcb200_handle* h, int64_t B, int32_t* out) {
+    if (!h || !out) return fail(h, MPCB200_EINVAL, "mpcb200_get_restorations: NULL argument");
+    if (B != h->last_B) return fail(h, MPCB200_EINVAL, "mpcb200_get_restorations: B=%lld, the last solve had %lld problems", (long long)B, (long long)h->last_B);
+    if (B == 0) return MPCB200_OK;
+    if (!h->last_sharded) {
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        CUDA_TRY(h, cudaMemcpyAsync(out, h->d_resto.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        return MPCB200_OK;
+    }
+    for (int i = 0; i <= h->n_sub; i++) {
+        mpcb200_handle* d = i ? h->sub[i - 1] : h;
+        const int64_t n = h->slice_hi[i] - h->slice_lo[i];
+        if (n <= 0) continue;
+        CUDA_TRY(h, cudaSetDevice(d->device));
+        CUDA_TRY(h, cudaMemcpyAsync(out + h->slice_lo[i], d->d_resto.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(d->stream));
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return MPCB200_OK;
+}
+
 int mpcb200_solve_batch_frenet(mpcb200_handle* h, int64_t B, const double* state, const double* k_coeffs, const double* v_des,
                                const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
                                double* traj, int32_t mem_space) {
     if (h && !h->model) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch_frenet: the handle was not created with mpcb200_create_frenet");
-    return solve_batch_impl(h, "mpcb200_solve_batch_frenet", B, state, k_coeffs, nullptr, 1, 0.0, v_des, u_prev, warm, u0, cost, status, iters,
-                            traj, nullptr, nullptr, mem_space);
+    const SolveArgs a{"mpcb200_solve_batch_frenet", state, k_coeffs, nullptr, 1, 0.0, v_des, u_prev, warm, u0, cost, status, iters, traj,
+                      nullptr, nullptr, nullptr};
+    return solve_batch_impl(h, B, a, mem_space);
 }
 
 int mpcb200_set_cost_frenet(mpcb200_handle* h, const double w[7]) {
@@ -594,6 +776,7 @@ int mpcb200_set_cost_frenet(mpcb200_handle* h, const double w[7]) {
     h->w[0] = 0.0;
     memcpy(h->w + 1, w, 7 * sizeof(double));
     drop_graphs(h);
+    for (int i = 0; i < h->n_sub; i++) { memcpy(h->sub[i]->w, h->w, 8 * sizeof(double)); drop_graphs(h->sub[i]); }
     return MPCB200_OK;
 }
 
@@ -601,16 +784,27 @@ int mpcb200_solve_batch(mpcb200_handle* h, int64_t B, const double* state, const
                         const double* u_prev, double* warm, double* u0, double* cost, int32_t* status, int32_t* iters,
                         double* traj, int32_t mem_space) {
     if (h && h->model) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch: Frenet handle; use mpcb200_solve_batch_frenet");
-    return solve_batch_impl(h, "mpcb200_solve_batch", B, state, ref, nullptr, 1, 0.0, v_des, u_prev, warm, u0, cost, status, iters, traj,
-                            nullptr, nullptr, mem_space);
+    const SolveArgs a{"mpcb200_solve_batch", state, ref, nullptr, 1, 0.0, v_des, u_prev, warm, u0, cost, status, iters, traj,
+                      nullptr, nullptr, nullptr};
+    return solve_batch_impl(h, B, a, mem_space);
+}
+
+int mpcb200_solve_batch_records(mpcb200_handle* h, int64_t B, const double* state, const double* ref, const double* v_des,
+                                const double* u_prev, double* warm, double* rec, double* traj, int32_t mem_space) {
+    if (h && !rec) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch_records: rec is required");
+    /* u0 is part of the record; the kernel still wants a place for it in DEVICE mode: none is needed, it skips NULL */
+    const SolveArgs a{"mpcb200_solve_batch_records", state, ref, nullptr, 1, 0.0, v_des, u_prev, warm, nullptr, nullptr, nullptr, nullptr, traj,
+                      nullptr, nullptr, rec};
+    return solve_batch_impl(h, B, a, mem_space);
 }
 
 int mpcb200_solve_batch_on_path(mpcb200_handle* h, int64_t B, const double* state, const int32_t* path_of, int32_t track_using_time,
                                 double target_vel, const double* v_des, const double* u_prev, double* warm, double* u0, double* cost,
                                 int32_t* status, int32_t* iters, double* traj, double* ref_out, int32_t* stop, int32_t mem_space) {
     if (h && !path_of) return fail(h, MPCB200_EINVAL, "mpcb200_solve_batch_on_path: path_of is required");
-    return solve_batch_impl(h, "mpcb200_solve_batch_on_path", B, state, nullptr, path_of, track_using_time, target_vel, v_des, u_prev, warm,
-                            u0, cost, status, iters, traj, ref_out, stop, mem_space);
+    const SolveArgs a{"mpcb200_solve_batch_on_path", state, nullptr, path_of, track_using_time, target_vel, v_des, u_prev, warm, u0, cost,
+                      status, iters, traj, ref_out, stop, nullptr};
+    return solve_batch_impl(h, B, a, mem_space);
 }
 
 int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n, const double* t, const double* X, const double* Y,
@@ -626,6 +820,104 @@ int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n, const double
         CUDA_TRY(h, cudaMemcpyAsync((double*)h->d_path[path_id].p + (size_t)i * n, cols[i], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->path_n[path_id] = n;
+    for (int i = 0; i < h->n_sub; i++)   /* the tables are replicated on every device */
+        if ((rc = mpcb200_set_path(h->sub[i], path_id, n, t, X, Y, psi, s))) return sub_fail(h, h->sub[i], rc);
+    if (h->n_sub) CUDA_TRY(h, cudaSetDevice(h->device));
+    return MPCB200_OK;
+}
+
+/* The start point of a vehicle's FIRST solve: the solution of the module-load solve of the default problem
+ * (MKZMPCPathFollower.jl:36-39,75,82,110-113,126-128: zero state and previous command, x_ref = 15 t, y_ref = psi_ref = 0,
+ * module-default weights, start = 0.0), which JuMP re-solves from.  Solved once per handle with this library. */
+static int ensure_seed(mpcb200_handle* h) {
+    if (h->seed_valid) return MPCB200_OK;
+    const int N = h->cfg.N;
+    const size_t nt = 6 * (size_t)N + 4;
+    double* buf = (double*)calloc(4 + 3 * ((size_t)N + 1) + 2 + 1 + 2 + nt, sizeof(double));
+    if (!buf) return fail(h, MPCB200_ENOMEM, "mpcb200_rollout: out of host memory");
+    double *state = buf, *ref = state + 4, *u_prev = ref + 3 * (N + 1), *v_des = u_prev + 2, *u0 = v_des + 1, *traj = u0 + 2;
+    for (int k = 0; k <= N; k++) ref[k] = 15.0 * ((double)k * h->cfg.dt);
+    v_des[0] = 15.0;
+    double w_keep[8];
+    const double w0[8] = {9.0, 9.0, 10.0, 0.0, 100.0, 1000.0, 0.0, 0.0};
+    memcpy(w_keep, h->w, sizeof(w_keep));
+    memcpy(h->w, w0, sizeof(w0));
+    const int start_keep = h->cfg.start_mode;
+    h->cfg.start_mode = MPCB200_START_ZERO;
+    drop_graphs(h);   /* weights and start mode are kernel parameters */
+    const mpcb200_stats keep = h->stats;
+    const SolveArgs a{"mpcb200_rollout (module-load solve)", state, ref, nullptr, 1, 0.0, v_des, u_prev, nullptr, u0, nullptr, nullptr, nullptr,
+                      traj, nullptr, nullptr, nullptr};
+    int rc = solve_small_host(h, 1, a);
+    memcpy(h->w, w_keep, sizeof(w_keep));
+    h->cfg.start_mode = start_keep;
+    drop_graphs(h);
+    h->stats = keep;
+    if (!rc) rc = ensure(h, h->d_seed, nt * sizeof(double));
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(h->d_seed.p, traj, nt * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, MPCB200_ECUDA, "mpcb200_rollout: %s", cudaGetErrorString(e));
+    }
+    free(buf);
+    if (!rc) h->seed_valid = true;
+    return rc;
+}
+
+/* one device's share of a rollout: vehicles [lo, lo + n) of B; enqueue ... */
+static int rollout_enqueue(mpcb200_handle* h, int64_t n, int32_t T, const double* pose0, const int32_t* path_of, int32_t track_using_time,
+                           double target_vel, bool want_log, bool want_final) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    if ((rc = ensure_seed(h))) return rc;
+    const size_t bl = (size_t)T * n * 8 * sizeof(double), bf = (size_t)n * 8 * sizeof(double);
+    if ((rc = ensure(h, h->d_pose, (size_t)n * 3 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->d_pathof, (size_t)n * sizeof(int32_t)))) return rc;
+    if (want_log && (rc = ensure(h, h->d_log, bl))) return rc;
+    if (want_final && (rc = ensure(h, h->d_final, bf))) return rc;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pose.p, pose0, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pathof.p, path_of, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += (size_t)n * (3 * sizeof(double) + sizeof(int32_t));
+    RolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pose0 = (const double*)h->d_pose.p; a.path_of = (const int*)h->d_pathof.p;
+    fill_paths(h, a.paths);
+    a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel;
+    a.log = want_log ? (double*)h->d_log.p : nullptr; a.final_state = want_final ? (double*)h->d_final.p : nullptr; a.B = (long)n;
+    a.warm0 = (const double*)h->d_seed.p;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), s));
+    const int per_block = (h->team_warps == 1) ? WARPS_PER_BLOCK : 1;
+    long long blocks_needed = (n + per_block - 1) / per_block;
+    long long max_blocks = (long long)h->num_sms * h->rollout_blocks_per_sm;
+    int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    if (h->team_warps == 1)
+        mpc_rollout_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, s>>>(make_kcfg(h), a, h->d_counter);
+    else if (h->team_warps == 2)
+        mpc_rollout_long_kernel<2><<<grid, 64, h->smem_bytes + ROLLOUT_PX * sizeof(double), s>>>(make_kcfg(h), a, h->d_counter);
+    else
+        mpc_rollout_long_kernel<3><<<grid, 96, h->smem_bytes + ROLLOUT_PX * sizeof(double), s>>>(make_kcfg(h), a, h->d_counter);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    h->stats.kernel_launches += 1;
+    return MPCB200_OK;
+}
+
+/* ... and copy the share's rows of log [T][B][8] (a strided block when the fleet is sharded) and final [B][8] back */
+static int rollout_collect(mpcb200_handle* h, int64_t lo, int64_t n, int64_t B, int32_t T, double* log, double* final_state) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    const size_t row = (size_t)n * 8 * sizeof(double);
+    if (log) {
+        CUDA_TRY(h, cudaMemcpy2DAsync(log + (size_t)lo * 8, (size_t)B * 8 * sizeof(double), h->d_log.p, row, row, (size_t)T, cudaMemcpyDeviceToHost, s));
+        h->stats.d2h_bytes += row * T;
+    }
+    if (final_state) { CUDA_TRY(h, cudaMemcpyAsync(final_state + (size_t)lo * 8, h->d_final.p, row, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += row; }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
     return MPCB200_OK;
 }
 
@@ -637,42 +929,31 @@ int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T, const double* pose0
     memset(&h->stats, 0, sizeof(h->stats));
     if (B == 0 || T == 0) return MPCB200_OK;
     if (!pose0 || !path_of) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: pose0 and path_of are required");
-    if (h->team_warps != 1) return fail(h, MPCB200_EINVAL, "mpcb200_rollout: closed-loop rollouts need N <= 31 (N=%d)", h->cfg.N);
     for (int64_t b = 0; b < B; b++)
         if (path_of[b] < 0 || path_of[b] > 2 || h->path_n[path_of[b]] == 0)
             return fail(h, MPCB200_EINVAL, "mpcb200_rollout: vehicle %lld uses path %d, which was not set with mpcb200_set_path", (long long)b, path_of[b]);
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    /* a vehicle stays on one GPU for all T steps: contiguous slices of the fleet, every device at once */
+    const int parts = (B >= 2 * (int64_t)(h->n_sub + 1)) ? h->n_sub + 1 : 1;
+    mpcb200_handle* dev[8];
+    dev[0] = h;
+    for (int i = 0; i < h->n_sub; i++) dev[i + 1] = h->sub[i];
+    int64_t lo[8], hi[8];
     int rc;
-    const size_t bl = (size_t)T * B * 8 * sizeof(double), bf = (size_t)B * 8 * sizeof(double);
-    if ((rc = ensure(h, h->d_pose, (size_t)B * 3 * sizeof(double)))) return rc;
-    if ((rc = ensure(h, h->d_pathof, (size_t)B * sizeof(int32_t)))) return rc;
-    if (log && (rc = ensure(h, h->d_log, bl))) return rc;
-    if (final_state && (rc = ensure(h, h->d_final, bf))) return rc;
-    cudaStream_t s = h->stream;
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_pose.p, pose0, (size_t)B * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_pathof.p, path_of, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    h->stats.h2d_bytes += (size_t)B * (3 * sizeof(double) + sizeof(int32_t));
-    RolloutArgs a;
-    memset(&a, 0, sizeof(a));
-    a.pose0 = (const double*)h->d_pose.p; a.path_of = (const int*)h->d_pathof.p;
-    fill_paths(h, a.paths);
-    a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel;
-    a.log = log ? (double*)h->d_log.p : nullptr; a.final_state = final_state ? (double*)h->d_final.p : nullptr; a.B = (long)B;
-    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), s));
-    long long blocks_needed = (B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    long long max_blocks = (long long)h->num_sms * h->rollout_blocks_per_sm;
-    int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
-    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
-    mpc_rollout_kernel<<<grid, WARPS_PER_BLOCK * 32, h->smem_bytes, s>>>(make_kcfg(h), a, h->d_counter);
-    CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
-    h->stats.kernel_launches += 1;
-    if (log) { CUDA_TRY(h, cudaMemcpyAsync(log, h->d_log.p, bl, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bl; }
-    if (final_state) { CUDA_TRY(h, cudaMemcpyAsync(final_state, h->d_final.p, bf, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bf; }
-    CUDA_TRY(h, cudaStreamSynchronize(s));
-    float ms = 0.f;
-    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    h->stats.kernel_ms = ms;
+    for (int i = 0; i < parts; i++) {
+        shard_range(B, parts, i, &lo[i], &hi[i]);
+        if (i) memset(&dev[i]->stats, 0, sizeof(mpcb200_stats));
+        if ((rc = rollout_enqueue(dev[i], hi[i] - lo[i], T, pose0 + 3 * lo[i], path_of + lo[i], track_using_time, target_vel, log != nullptr,
+                                  final_state != nullptr)))
+            return sub_fail(h, dev[i], rc);
+    }
+    for (int i = 0; i < parts; i++)
+        if ((rc = rollout_collect(dev[i], lo[i], hi[i] - lo[i], B, T, log, final_state))) return sub_fail(h, dev[i], rc);
+    for (int i = 1; i < parts; i++) {
+        h->stats.kernel_launches += dev[i]->stats.kernel_launches;
+        h->stats.h2d_bytes += dev[i]->stats.h2d_bytes; h->stats.d2h_bytes += dev[i]->stats.d2h_bytes;
+        if (dev[i]->stats.kernel_ms > h->stats.kernel_ms) h->stats.kernel_ms = dev[i]->stats.kernel_ms;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
     return MPCB200_OK;
 }
 

@@ -255,7 +255,21 @@ struct EvalState {        // ... and its team-wide scalars
 // reciprocals of the ten bound slacks of a lane, from ONE division
 struct Recips { double vL, vU, aL, aU, dL, dU, r0L, r0U, r1L, r1U; };
 
-struct Result { int status; int iters; double cost; };
+struct Result { int status; int iters; double cost; int n_resto; };
+
+// The two line-search tests that involve theta^s_theta / (-grad(phi)'d)^s_phi (Ipopt: FilterLSAcceptor::IsFtype and
+// CalculateAlphaMin) are decided in double precision exactly as the oracle writes them; the single-precision
+// estimate of the ratio only screens out the (almost all) cases that are more than 0.1 % away from the threshold.
+//   form 0:  a (-gBd)^s_phi > delta theta^s_theta           form 1:  a > alpha_min_frac * delta theta^s_theta / (-gBd)^s_phi
+MPC_DEV_NOINLINE bool ratio_test_exact(int form, double a, double theta, double mgbd) {
+    if (form == 0) return a * pow(mgbd, K_S_PHI) > K_DELTA * pow(theta, K_S_THETA);
+    return a > K_ALPHA_MIN_FRAC * (K_DELTA * pow(theta, K_S_THETA) / pow(mgbd, K_S_PHI));
+}
+MPC_DEV bool ratio_test(int form, double a, double thr32, double theta, double mgbd) {
+    if (a > thr32 * 1.001) return true;
+    if (a < thr32 * 0.999) return false;
+    return ratio_test_exact(form, a, theta, mgbd);
+}
 
 // a / b for the rare branches: a call cannot be speculated, so the division (and its slow path for
 // zero numerators) stays out of the common path
@@ -412,6 +426,20 @@ MPC_HD void riccati_roles(int l, int N, int W_SD, int* out, int model = 0) {
         out[22] = (l < 12) ? SO(W_TT2 + 6 * cc + i) : SO(W_DUMMY);
         out[23] = 0;
     }
+}
+
+// ---- reference generation on the device (scripts/gps_utils/ref_gps_traj.py:131-218), used by the
+// closed-loop rollout and by mpcb200_solve_batch_on_path (TeamSolver::get_waypoints)
+struct PathTable { const double *t, *X, *Y, *psi, *s; int n; };   // columns 0,4,5,3,6 of ref_gps_traj.py:106
+
+// np.interp(xq, xp, fp): every operation rounded on its own like numpy's compiled loop (no FMA contraction)
+MPC_DEV double np_interp(double xq, const double* xp, const double* fp, int n) {
+    if (xq <= xp[0]) return fp[0];
+    if (xq >= xp[n - 1]) return fp[n - 1];
+    int lo = 0, hi = n - 1;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (xp[mid] <= xq) lo = mid; else hi = mid; }
+    const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
+    return add_rn(mul_rn(slope, xq - xp[lo]), fp[lo]);
 }
 
 // W = warps per team (1: a warp per problem; 2, 3: a block per problem)
@@ -595,6 +623,32 @@ struct TeamSolver {
         if (k == 0) sts(sm, a, v);
         block_sync();
         return lds(sm, a);
+    }
+
+    // value held by stage `src`, for every thread
+    MPC_DEV double bcast_from(double v, int src) {
+        if (W == 1) return shfl(v, src);
+        const int a = SO(W_XCHG + XCH_FLAG + xflip());
+        if (k == src) sts(sm, a, v);
+        block_sync();
+        return lds(sm, a);
+    }
+    // smallest (d, i) pair over the team, ties to the smaller index (numpy argmin returns the first minimum)
+    MPC_DEV void targmin(double& d, int& i) {
+        MPC_NOUNROLL for (int o = 16; o; o >>= 1) {
+            const double od = shfl_xor(d, o); const int oi = shfl(i, lane_id() ^ o);
+            if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+        }
+        if (W > 1) {
+            const int base = SO(W_XCHG + XCH_RED + xflip() * 12);
+            if (lane_id() == 0) { sts(sm, base + SO((k >> 5) * 4), d); sts(sm, base + SO((k >> 5) * 4 + 1), (double)i); }
+            block_sync();
+            d = lds(sm, base); i = (int)lds(sm, base + SO(1));
+            for (int w = 1; w < W; w++) {
+                const double od = lds(sm, base + SO(w * 4)); const int oi = (int)lds(sm, base + SO(w * 4 + 1));
+                if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+            }
+        }
     }
 
     // cheap per-use reconstruction of lane constants (keeps them out of the register file)
@@ -1167,6 +1221,42 @@ struct TeamSolver {
         }
     }
 
+    // get_waypoints (ref_gps_traj.py:131-218) for the whole team: thread k returns waypoint k (k <= N); returns stop_cmd.
+    // Nearest sample over the whole path (:136-137), np.interp of X, Y, psi at t_closest + k dt -- or at
+    // s_closest + (k + 1) dt v_target in distance mode (:175) --, heading unwrap (:204-218), stop_cmd (:198-200).
+    MPC_DEV bool get_waypoints(const PathTable& p, double traj_dt, double X, double Y, double yaw, bool use_vtarget,
+                               double v_target, double& xr, double& yr, double& pr) {
+        double bd = 1e300; int bi = 0x7fffffff;
+        for (int i = k; i < p.n; i += 32 * W) {
+            const double dx = p.X[i] - X, dy = p.Y[i] - Y, d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+            if (d < bd) { bd = d; bi = i; }
+        }
+        targmin(bd, bi);
+        const double* absc = use_vtarget ? p.s : p.t;
+        const double start = absc[bi];
+        xr = yr = pr = 0.0;
+        if (k <= N) {
+            const double q = use_vtarget ? add_rn(mul_rn(mul_rn((double)(k + 1), traj_dt), v_target), start)
+                                         : add_rn(mul_rn((double)k, traj_dt), start);
+            xr = np_interp(q, absc, p.X, p.n); yr = np_interp(q, absc, p.Y, p.n); pr = np_interp(q, absc, p.psi, p.n);
+        }
+        // heading wrap-around fix (:204-218)
+        const double PI = 3.141592653589793;
+        double nxt;
+        xnext<1>(&pr, &nxt);
+        double c12[2] = {(k < N) ? fabs(nxt - pr) : 0.0, (k <= N) ? fabs(pr - yaw) : 0.0};
+        treduce<OP_MAX, 2>(c12);
+        if (!(c12[0] < PI && c12[1] < PI)) {
+            const double a0 = pr, a1 = pr + 2.0 * PI, a2 = pr - 2.0 * PI;
+            double b = a0, e = fabs(a0 - yaw);
+            if (fabs(a1 - yaw) < e) { e = fabs(a1 - yaw); b = a1; }
+            if (fabs(a2 - yaw) < e) { b = a2; }
+            pr = b;
+        }
+        const double lx = bcast_from(xr, N), ly = bcast_from(yr, N);
+        return lx == p.X[p.n - 1] && ly == p.Y[p.n - 1];
+    }
+
     MPC_DEV bool nlp_feasible() const {
         const double e = 1e-8;
         const double lim_d = c.sdmax * c.dtc, lim_a = c.admax * c.dtc;
@@ -1239,7 +1329,7 @@ struct TeamSolver {
                 const double th_t = ev.theta;
                 const double ph_t = sigma * ev.f - mu * ev.lb;
                 const double theta = cur_theta;
-                const bool ftype = (gBd < 0.0) && (alpha_test > K_DELTA * Rft);
+                const bool ftype = (gBd < 0.0) && ratio_test(0, alpha_test, K_DELTA * Rft, theta, -gBd);
                 const bool arm = cmp_le(ph_t - phi, K_ETA_PHI * alpha_test * gBd, phi);
                 bool ok = tiny;
                 if (!tiny) {
@@ -1293,13 +1383,13 @@ struct TeamSolver {
                     }
                     // plain backtracking
                     double alpha_min = K_GAMMA_THETA;
-                    if (gBd < 0.0) {
-                        alpha_min = dmin_(K_GAMMA_THETA, K_GAMMA_PHI * theta / (-gBd));
-                        if (theta <= theta_min) alpha_min = dmin_(alpha_min, K_DELTA * Rft);
-                    }
+                    if (gBd < 0.0) alpha_min = dmin_(K_GAMMA_THETA, K_GAMMA_PHI * theta / (-gBd));
                     alpha_min *= K_ALPHA_MIN_FRAC;
                     alpha *= 0.5; nsteps++;
-                    if (!(alpha > alpha_min)) {   // Ipopt would enter the restoration phase ...
+                    bool above_min = alpha > alpha_min;   // alpha > alpha_min_frac * min(gamma_theta, gamma_phi theta / -gBd, delta R)
+                    if (!above_min && gBd < 0.0 && theta <= theta_min)
+                        above_min = ratio_test(1, alpha, K_ALPHA_MIN_FRAC * (K_DELTA * Rft), theta, -gBd);
+                    if (!above_min) {   // Ipopt would enter the restoration phase ...
                         if (cur_acceptable) { ret = 1; break; }   // ... unless the point is acceptable: Solved_To_Acceptable_Level
                         if (cur_theta <= 1e-2 * c.tol) { ret = had_acceptable ? 1 : -2; break; }   // ... or almost feasible (see oracle)
                         if (n_resto < K_MAX_RESTO) { phase = PH_RESTO; continue; }
@@ -1576,11 +1666,11 @@ struct TeamSolver {
                 if (phase == PH_RESOLVE) {
                     alpha = alpha_max * 0.5; nsteps = 1;
                     double alpha_min = K_GAMMA_THETA;
-                    if (gBd < 0.0) {
-                        alpha_min = dmin_(K_GAMMA_THETA, K_GAMMA_PHI * cur_theta / (-gBd));
-                        if (cur_theta <= theta_min) alpha_min = dmin_(alpha_min, K_DELTA * Rft);
-                    }
-                    if (!(alpha > alpha_min * K_ALPHA_MIN_FRAC)) {
+                    if (gBd < 0.0) alpha_min = dmin_(K_GAMMA_THETA, K_GAMMA_PHI * cur_theta / (-gBd));
+                    bool above_min = alpha > alpha_min * K_ALPHA_MIN_FRAC;
+                    if (!above_min && gBd < 0.0 && cur_theta <= theta_min)
+                        above_min = ratio_test(1, alpha, K_ALPHA_MIN_FRAC * (K_DELTA * Rft), cur_theta, -gBd);
+                    if (!above_min) {
                         if (cur_acceptable) { ret = 1; break; }
                         if (cur_theta <= 1e-2 * c.tol) { ret = had_acceptable ? 1 : -2; break; }
                         if (n_resto < K_MAX_RESTO) { phase = PH_RESTO; continue; }
@@ -1619,7 +1709,7 @@ struct TeamSolver {
                     tiny = tall(tl) && (theta < 1e-4);
                 }
                 if (theta_max < 0.0) { theta_max = 1e4 * dmax_(1.0, theta); theta_min = 1e-4 * dmax_(1.0, theta); }
-                // switching-condition ratio theta^s_theta / (-gBd)^s_phi: a threshold test, single precision suffices
+                // switching-condition ratio theta^s_theta / (-gBd)^s_phi, single-precision estimate (see ratio_test)
                 Rft = (gBd < 0.0) ? (double)fast_exp2((float)K_S_THETA * fast_log2((float)theta) - (float)K_S_PHI * fast_log2((float)(-gBd))) : 0.0;
                 alpha_max = alpha_primal(tau);
                 alpha = alpha_max; nsteps = 0;
@@ -1627,7 +1717,7 @@ struct TeamSolver {
                 continue;
             }
         }
-        res.iters = iter;
+        res.iters = iter; res.n_resto = n_resto;
         res.status = (ret == 0 || ret == 1) ? 0 : (ret == 2 ? 1 : (ret == -1 ? 3 : (ret == -5 ? 2 : 4)));
         // honor_original_bounds
         if (feasible) {
@@ -1650,56 +1740,6 @@ struct TeamSolver {
     }
 };
 
-// ---- reference generation on the device (scripts/gps_utils/ref_gps_traj.py:131-218), used by the
-// closed-loop rollout and by mpcb200_solve_batch_on_path
-struct PathTable { const double *t, *X, *Y, *psi, *s; int n; };   // columns 0,4,5,3,6 of ref_gps_traj.py:106
-
-MPC_DEV double np_interp(double xq, const double* xp, const double* fp, int n) {
-    if (xq <= xp[0]) return fp[0];
-    if (xq >= xp[n - 1]) return fp[n - 1];
-    int lo = 0, hi = n - 1;
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (xp[mid] <= xq) lo = mid; else hi = mid; }
-    const double slope = (fp[lo + 1] - fp[lo]) / (xp[lo + 1] - xp[lo]);
-    return slope * (xq - xp[lo]) + fp[lo];
-}
-
-// get_waypoints for the whole warp: lane k returns waypoint k (k <= N); returns stop_cmd
-MPC_DEV bool get_waypoints_warp(const PathTable& p, int N, double traj_dt, double X, double Y, double yaw, bool use_vtarget,
-                                double v_target, double& xr, double& yr, double& pr) {
-    const int k = lane_id();
-    // nearest sample; numpy argmin returns the first minimum
-    double bd = 1e300; int bi = 0x7fffffff;
-    for (int i = k; i < p.n; i += 32) {
-        const double dx = p.X[i] - X, dy = p.Y[i] - Y, d = dx * dx + dy * dy;
-        if (d < bd) { bd = d; bi = i; }
-    }
-    MPC_NOUNROLL for (int o = 16; o; o >>= 1) {
-        const double od = shfl_xor(bd, o); const int oi = shfl(bi, k ^ o);
-        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
-    }
-    const double* absc = use_vtarget ? p.s : p.t;
-    const double start = absc[bi];
-    xr = yr = pr = 0.0;
-    if (k <= N) {
-        const double q = use_vtarget ? ((double)(k + 1) * traj_dt * v_target + start) : ((double)k * traj_dt + start);
-        xr = np_interp(q, absc, p.X, p.n); yr = np_interp(q, absc, p.Y, p.n); pr = np_interp(q, absc, p.psi, p.n);
-    }
-    // heading wrap-around fix (:204-218)
-    const double PI = 3.141592653589793;
-    const double nxt = shfl_down(pr, 1);
-    double c1 = (k < N) ? fabs(nxt - pr) : 0.0, c2 = (k <= N) ? fabs(pr - yaw) : 0.0;
-    c1 = warp_max(c1); c2 = warp_max(c2);
-    if (!(c1 < PI && c2 < PI)) {
-        const double a0 = pr, a1 = pr + 2.0 * PI, a2 = pr - 2.0 * PI;
-        double b = a0, e = fabs(a0 - yaw);
-        if (fabs(a1 - yaw) < e) { e = fabs(a1 - yaw); b = a1; }
-        if (fabs(a2 - yaw) < e) { b = a2; }
-        pr = b;
-    }
-    const double lx = shfl(xr, N), ly = shfl(yr, N);
-    return lx == p.X[p.n - 1] && ly == p.Y[p.n - 1];
-}
-
 // Problem I/O for one warp: problem-major layouts of include/mpc_b200.h.
 struct BatchPtrs {
     const double* state;   // [B][4]
@@ -1707,15 +1747,18 @@ struct BatchPtrs {
     const double* v_des;   // [B] or null
     const double* u_prev;  // [B][2]
     double* warm;          // [B][6N+4] or null
-    double* u0;            // [B][2]
+    double* u0;            // [B][2] or null (when rec is given)
     double* cost;          // [B] or null
     int* status;           // [B] or null
     int* iters;            // [B] or null
     double* traj;          // [B][6N+4] or null
+    double* rec;           // [B][4] or null: the packed 32-byte result record {acc, df, cost: f64; status, iters: i32} that the
+                           //   multi-GPU all-gather moves; its status word carries the restoration count in bits 8..15
+    int* resto;            // [B] or null: restorations by rollout this solve went through (0 for almost every problem)
 };
 
 // Optional on-device reference generation for a batch (path_of != null): the waypoints come from the
-// replicated path tables instead of io.ref (one warp per problem only, N <= 31).
+// replicated path tables instead of io.ref.
 struct RefGen {
     const int* path_of;     // [B] index into paths[], or null: references are read from io.ref
     PathTable paths[3];
@@ -1735,11 +1778,26 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, const RefGen& r
     if (MODEL) {
         const double* kp = io.ref + 4 * b;
         S.set_kpoly(kp[0], kp[1], kp[2], kp[3]);
-    } else if (W == 1 && rg.path_of) {
+    } else if (rg.path_of) {
         // ---- waypoints from the path table: nearest sample to (X, Y), then interpolation and heading unwrap
+        const int pid = rg.path_of[b];
+        if (pid < 0 || pid > 2 || rg.paths[pid].n < 2) {
+            // a path id that was never given to mpcb200_set_path (device pointers cannot be checked on the host):
+            // the problem is answered with MPCB200_ERROR and zero commands instead of indexing outside the tables
+            if (k == 0) {
+                if (io.u0) { io.u0[2 * b] = 0.0; io.u0[2 * b + 1] = 0.0; }
+                if (io.cost) io.cost[b] = 0.0;
+                if (io.status) io.status[b] = 4;
+                if (io.iters) io.iters[b] = 0;
+                if (io.rec) { st_global_v2(io.rec + 4 * b, 0.0, 0.0); st_global_v2(io.rec + 4 * b + 2, 0.0, int2_as_double(4, 0)); }
+                if (io.resto) io.resto[b] = 0;
+                if (rg.stop) rg.stop[b] = 0;
+            }
+            return;
+        }
         double xr, yr, pr;
-        const bool sc = get_waypoints_warp(rg.paths[rg.path_of[b]], N, cfg.dt, io.state[4 * b], io.state[4 * b + 1], io.state[4 * b + 2],
-                                           !rg.track_using_time, rg.target_vel, xr, yr, pr);
+        const bool sc = S.get_waypoints(rg.paths[pid], cfg.dt, io.state[4 * b], io.state[4 * b + 1], io.state[4 * b + 2],
+                                        !rg.track_using_time, rg.target_vel, xr, yr, pr);
         S.set_ref(xr, yr, pr);
         if (rg.ref_out && k <= N) { double* ro = rg.ref_out + nr * b; ro[k] = xr; ro[(N + 1) + k] = yr; ro[2 * (N + 1) + k] = pr; }
         if (rg.stop && k == 0) rg.stop[b] = sc ? 1 : 0;
@@ -1752,7 +1810,7 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, const RefGen& r
         double cv = 0.0;
         if (k < 4) cv = io.state[4 * b + k];
         else if (k < 6) cv = io.u_prev[2 * b + (k - 4)];
-        else if (k == 6) cv = io.v_des ? io.v_des[b] : ((W == 1 && rg.path_of && rg.target_vel > 0.0) ? rg.target_vel : 0.0);   // des_speed, mpc_cmd_pub.jl:58-62,116
+        else if (k == 6) cv = io.v_des ? io.v_des[b] : (rg.path_of ? rg.target_vel : 0.0);   // des_speed (clamped on the host), mpc_cmd_pub.jl:58-62,116
         if (k < 8) sts(smem, SO(W_CONST + k), cv);
         S.tsync();
     }
@@ -1772,10 +1830,12 @@ MPC_DEV void solve_problem(const KCfg& cfg, const BatchPtrs& io, const RefGen& r
     // ---- results
     const double a0 = S.bcast0(S.L.ua), d0 = S.bcast0(S.L.ud);
     if (k == 0) {
-        io.u0[2 * b] = a0; io.u0[2 * b + 1] = d0;
+        if (io.u0) { io.u0[2 * b] = a0; io.u0[2 * b + 1] = d0; }
         if (io.cost) io.cost[b] = r.cost;
         if (io.status) io.status[b] = r.status;
         if (io.iters) io.iters[b] = r.iters;
+        if (io.rec) { st_global_v2(io.rec + 4 * b, a0, d0); st_global_v2(io.rec + 4 * b + 2, r.cost, int2_as_double(r.status | (r.n_resto << 8), r.iters)); }
+        if (io.resto) io.resto[b] = r.n_resto;
     }
     for (int pass = 0; pass < 2; pass++) {
         double* t = (pass == 0) ? io.traj : io.warm;
@@ -1803,6 +1863,7 @@ struct RolloutArgs {
     double* log;            // [T][B][8] or null
     double* final_state;    // [B][8] or null
     long B;
+    const double* warm0;    // [6N+4] or null: start point of every vehicle's FIRST solve (the module-load solution)
 };
 
 // atan2(y, x) for x > 0 and sincos for small arguments: the plant's slip angles and steering angle are
@@ -1842,7 +1903,8 @@ MPC_DEV void plant_step(double* st, double acc_des, double df_des) {
         double sdf, cdf, sps, cps;
         sincos_small(df, &sdf, &cdf);
         mpc_sincos(psi, &sps, &cps);
-        double vx_n = vx + deltaT * (acc - 1 / m * Fyf * sdf + wz * vy);
+        // :86 `1/m*Fyf*np.sin(self.df)`: the node is Python 2 and m an int, so 1/m == 0 and the term is (+-)0
+        double vx_n = vx + deltaT * (acc - 0.0 * Fyf * sdf + wz * vy);
         if (vx_n < 0.0) vx_n = 0.0;
         double vy_n = 0.0, wz_n = 0.0;
         if (vx_n > 1e-6) {
@@ -1864,16 +1926,19 @@ MPC_DEV double sel8(const double* v, int i) {   // register-friendly v[i] for a 
     return (i == 0) ? v[0] : (i == 1) ? v[1] : (i == 2) ? v[2] : (i == 3) ? v[3] : (i == 4) ? v[4] : (i == 5) ? v[5] : (i == 6) ? v[6] : v[7];
 }
 
-// One block = `nwarps` vehicles (one per warp) stepping through the T control periods together.
+// One block = `nwarps` vehicles (one per warp, W = 1) stepping through the T control periods together, or ONE vehicle
+// whose problem is shared by the W = 2, 3 warps of the block (long horizons).
 // The plant of all the block's vehicles is integrated by ONE warp, lane = vehicle (every lane of a
 // warp would otherwise repeat the same 100 Euler sub-steps, atan2 and sincos included: 40 % of the
 // rollout's instructions); states and commands cross through `px` ([vehicle][10] doubles) around two
 // block barriers per control period.  Warps whose vehicle index is past the fleet only keep the barriers.
 #define ROLLOUT_PX 10   // X, Y, psi, vx, vy, wz, acc, df, acc_des, df_des
+template <int W>
 MPC_DEV void rollout_group(const KCfg& cfg, const RolloutArgs& a, long b0, smem_t smem, smem_t px, int nwarps) {
-    TeamSolver<1> S(cfg, smem);
+    TeamSolver<W> S(cfg, smem);
     const int k = S.k, N = cfg.N;
-    const int w = thread_in_block() >> 5;
+    const int w = (W == 1) ? (thread_in_block() >> 5) : 0;   // vehicle of this thread within the block
+    const int nveh = (W == 1) ? nwarps : 1;
     const long b = b0 + w;
     const bool valid = b < a.B;
     const int pxw = SO(w * ROLLOUT_PX);
@@ -1883,12 +1948,19 @@ MPC_DEV void rollout_group(const KCfg& cfg, const RolloutArgs& a, long b0, smem_
     double acc_des = 0.0, df_des = 0.0, up_d = 0.0, up_a = 0.0;   // commands, d_f_current, acc_current
     const double des_speed = a.target_vel > 0.0 ? a.target_vel : 0.0;
     bool stop = false;
-    S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;   // start = 0.0, then the previous solution
+    // the first solve of the node starts from the solution of the module-load solve of the default problem
+    // (MKZMPCPathFollower.jl:126-128: JuMP re-solves from the previous primal values); later ones from the previous solution
+    S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;
+    if (a.warm0) {
+        const double* w0 = a.warm0;
+        if (k <= N) { S.L.sx = w0[k]; S.L.sy = w0[(N + 1) + k]; S.L.sv = w0[2 * (N + 1) + k]; S.L.sp = w0[3 * (N + 1) + k]; }
+        if (k < N) { S.L.ud = w0[4 * (N + 1) + k]; S.L.ua = w0[4 * (N + 1) + N + k]; }
+    }
     for (int t = 0; t < a.T; t++) {
         if (k == 0) { sts(px, pxw + SO(8), acc_des); sts(px, pxw + SO(9), df_des); }
         block_sync();
-        if (w == 0 && k < nwarps) {   // lane = vehicle: ten 100 Hz publishes of ten Euler sub-steps each
-            const int pv = SO(k * ROLLOUT_PX);
+        if (thread_in_block() < nveh) {   // lane = vehicle: ten 100 Hz publishes of ten Euler sub-steps each
+            const int pv = SO(thread_in_block() * ROLLOUT_PX);
             double ps[8];
             for (int i = 0; i < 8; i++) ps[i] = lds(px, pv + SO(i));
             const double ad = lds(px, pv + SO(8)), dd = lds(px, pv + SO(9));
@@ -1899,20 +1971,20 @@ MPC_DEV void rollout_group(const KCfg& cfg, const RolloutArgs& a, long b0, smem_
         if (!valid) continue;
         for (int i = 0; i < 8; i++) st[i] = lds(px, pxw + SO(i));
         double xr, yr, pr;
-        const bool sc = get_waypoints_warp(path, N, cfg.dt, st[0], st[1], st[2], !a.track_using_time, des_speed, xr, yr, pr);
+        const bool sc = S.get_waypoints(path, cfg.dt, st[0], st[1], st[2], !a.track_using_time, des_speed, xr, yr, pr);
         S.set_ref(xr, yr, pr);
         if (sc) stop = true;   // latch, mpc_cmd_pub.jl:102-111
         int status = -1, iters = 0;
         if (!stop) {
-            syncwarp();
+            S.tsync();
             {
                 const double cv[8] = {st[0], st[1], st[2], st[3], up_d, up_a, des_speed, 0.0};
                 if (k < 8) sts(smem, SO(W_CONST + k), sel8(cv, k));
             }
-            syncwarp();
+            S.tsync();
             const Result r = S.solve();
             status = r.status; iters = r.iters;
-            acc_des = shfl(S.L.ua, 0); df_des = shfl(S.L.ud, 0);   // published whatever the status (:129-132)
+            acc_des = S.bcast0(S.L.ua); df_des = S.bcast0(S.L.ud);   // published whatever the status (:129-132)
             up_d = df_des; up_a = acc_des;                           // update_current_input(df_opt, a_opt) (:140)
         } else { acc_des = -1.0; df_des = 0.0; }                     // :148-153
         if (a.log && k < 8) {

@@ -42,6 +42,12 @@ MPC_DEV double fast_rcp(double x) {
 }
 MPC_DEV float fast_log2(float x) { return __log2f(x); }
 MPC_DEV float fast_exp2(float x) { return exp2f(x); }
+// a * b and a + b rounded separately (never contracted into an FMA): the reference generator is numpy, which
+// rounds every operation, and its nearest-sample search and np.interp are reproduced bit for bit
+MPC_DEV double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+MPC_DEV double add_rn(double a, double b) { return __dadd_rn(a, b); }
+MPC_DEV void st_global_v2(double* p, double x, double y) { *reinterpret_cast<double2*>(p) = make_double2(x, y); }
+MPC_DEV double int2_as_double(int lo, int hi) { return __hiloint2double(hi, lo); }
 
 // Shared memory through 32-bit shared-window addresses and explicit ld/st.shared: the base is an
 // opaque register value, so the compiler cannot rematerialise generic->shared conversions or lane

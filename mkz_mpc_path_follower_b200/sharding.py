@@ -36,6 +36,14 @@ def unpack_records(rec):
     return rec[:, 0:2], rec[:, 2], si[:, 0], si[:, 1]
 
 
+def unpack_records_np(rec):
+    """The same for a (B,4) float64 numpy array of records written by the solve kernel (mpcb200_solve_batch_records):
+    returns u0, cost, status, iters, restorations (status word: low 8 bits status, bits 8..15 restoration count)."""
+    rec = np.ascontiguousarray(rec, dtype=np.float64)
+    si = rec[:, 3].copy().view(np.int32).reshape(-1, 2)
+    return rec[:, 0:2], rec[:, 2], si[:, 0] & 0xFF, si[:, 1], (si[:, 0] >> 8) & 0xFF
+
+
 def all_gather_records(rec, sizes=None):
     """One all-gather of the result records.  Equal slices use all_gather_into_tensor; ragged slices
     (total not divisible by world) are padded to the largest slice and trimmed."""

@@ -11,6 +11,10 @@ import numpy as np
 
 # vehicle_simulator.py:61-67
 LF, LR, M, IZ, C_ALPHA_F, C_ALPHA_R = 1.152, 1.693, 1840, 3477, 4.0703e4, 6.4495e4
+# The reference node is Python 2 and `m = 1840` is an int, so `1/m` in the vx equation (:86) is integer
+# division = 0: the tyre-force term drops out of the longitudinal equation AS THE REFERENCE RUNS (the vy and
+# wz equations, :90-91, use 1.0/m and 1.0/Iz and keep theirs).  Restated as it runs.
+INV_M_VX = 1 // M
 
 
 class VehicleSimulator(object):
@@ -40,7 +44,7 @@ class VehicleSimulator(object):
             alpha_r = np.where(moving, -np.arctan2(self.vy - LF * self.wz, vxs), 0.0)   # :77 uses lf (sic)
             Fyf = C_ALPHA_F * alpha_f
             Fyr = C_ALPHA_R * alpha_r
-            vx_n = np.maximum(0.0, self.vx + deltaT * (self.acc - 1 / M * Fyf * np.sin(self.df) + self.wz * self.vy))
+            vx_n = np.maximum(0.0, self.vx + deltaT * (self.acc - INV_M_VX * Fyf * np.sin(self.df) + self.wz * self.vy))
             fwd = vx_n > 1e-6
             vy_n = np.where(fwd, self.vy + deltaT * (1.0 / M * (Fyf * np.cos(self.df) + Fyr) - self.wz * self.vx), 0.0)
             wz_n = np.where(fwd, self.wz + deltaT * (1.0 / IZ * (LF * Fyf * np.cos(self.df) - LR * Fyr)), 0.0)

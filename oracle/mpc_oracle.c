@@ -1241,9 +1241,10 @@ int mpc_oracle_solve(const mpc_oracle_cfg* cfg, const double* state, const doubl
     return 0;
 }
 
-int mpc_oracle_solve_batch(const mpc_oracle_cfg* cfg, long B, const double* state, const double* ref,
-                           const double* v_des, const double* u_prev, double* warm, double* u0,
-                           double* cost, int* status, int* iters, double* traj, int n_threads) {
+/* n_resto: optional [B] restorations by rollout per problem (see mpc_oracle_diag) */
+int mpc_oracle_solve_batch_resto(const mpc_oracle_cfg* cfg, long B, const double* state, const double* ref,
+                                 const double* v_des, const double* u_prev, double* warm, double* u0,
+                                 double* cost, int* status, int* iters, double* traj, int* n_resto, int n_threads) {
     int N = cfg->N, nt = 6 * N + 4, nr = 3 * (N + 1);
     if (cfg->N < 3 || cfg->N > 512) return -1;
     if (n_threads < 1) n_threads = 1;
@@ -1251,7 +1252,7 @@ int mpc_oracle_solve_batch(const mpc_oracle_cfg* cfg, long B, const double* stat
 #pragma omp parallel num_threads(n_threads)
 #endif
     {
-        ipm_t P; long b;
+        ipm_t P; long b; mpc_oracle_diag dg;
         double* tbuf = (double*)malloc(sizeof(double) * nt);
         ipm_alloc(&P, cfg);
 #ifdef _OPENMP
@@ -1260,13 +1261,20 @@ int mpc_oracle_solve_batch(const mpc_oracle_cfg* cfg, long B, const double* stat
         for (b = 0; b < B; b++) {
             solve_with(&P, state + 4 * b, ref + (size_t)nr * b, v_des ? v_des[b] : 0.0, u_prev + 2 * b,
                        warm ? warm + (size_t)nt * b : NULL, tbuf, u0 ? u0 + 2 * b : NULL,
-                       cost ? cost + b : NULL, status ? status + b : NULL, iters ? iters + b : NULL, NULL);
+                       cost ? cost + b : NULL, status ? status + b : NULL, iters ? iters + b : NULL, &dg);
+            if (n_resto) n_resto[b] = dg.n_resto;
             if (traj) memcpy(traj + (size_t)nt * b, tbuf, sizeof(double) * nt);
             if (warm) memcpy(warm + (size_t)nt * b, tbuf, sizeof(double) * nt);
         }
         ipm_free(&P); free(tbuf);
     }
     return 0;
+}
+
+int mpc_oracle_solve_batch(const mpc_oracle_cfg* cfg, long B, const double* state, const double* ref,
+                           const double* v_des, const double* u_prev, double* warm, double* u0,
+                           double* cost, int* status, int* iters, double* traj, int n_threads) {
+    return mpc_oracle_solve_batch_resto(cfg, B, state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj, NULL, n_threads);
 }
 
 /* Frenet-frame variant: one private copy of cfg per thread carries the problem's curvature polynomial;
@@ -1360,6 +1368,7 @@ static double py_mod(double a, double m) { double r = fmod(a, m); if (r != 0.0 &
 void mpc_oracle_plant_step(double* st, double acc_des, double df_des) {
     const double lf = 1.152, lr = 1.693, m = 1840.0, Iz = 3477.0, Caf = 4.0703e4, Car = 6.4495e4; /* :61-67 */
     const double deltaT = 0.01 / 10.0; /* :69 */
+    const double inv_m_vx = (double)(1 / 1840); /* = 0, see :86 below */
     int i;
     for (i = 0; i < 10; i++) {
         double X = st[0], Y = st[1], psi = st[2], vx = st[3], vy = st[4], wz = st[5], acc = st[6], df = st[7];
@@ -1369,7 +1378,8 @@ void mpc_oracle_plant_step(double* st, double acc_des, double df_des) {
             ar = -atan2(vy - lf * wz, vx); /* :77 uses lf (sic) */
         }
         Fyf = Caf * af; Fyr = Car * ar;
-        vx_n = vx + deltaT * (acc - 1 / m * Fyf * sin(df) + wz * vy);
+        /* :86 is `1/m*Fyf*np.sin(self.df)` in a Python 2 node with the int m = 1840: integer division, 1/m == 0 */
+        vx_n = vx + deltaT * (acc - inv_m_vx * Fyf * sin(df) + wz * vy);
         if (vx_n < 0.0) vx_n = 0.0;
         if (vx_n > 1e-6) {
             vy_n = vy + deltaT * (1.0 / m * (Fyf * cos(df) + Fyr) - wz * vx);
@@ -1389,6 +1399,23 @@ void mpc_oracle_plant_step(double* st, double acc_des, double df_des) {
 /* ------------------------------------------------------------------------- */
 /* closed loop, mpc_cmd_pub.jl:86-157 driving the plant at 100 Hz             */
 /* ------------------------------------------------------------------------- */
+/* The solution of the module-load solve (MKZMPCPathFollower.jl:126-128) of the default problem: zero state and
+ * previous command (:75,82,110-113), x_ref = 15 t, y_ref = psi_ref = 0, v_target = 15 (:36-39,93), module-default
+ * weights (:51-59), start = 0.0 (:65-72).  JuMP <= 0.18 re-solves from the previous primal values, so this is the
+ * start point of the node's FIRST solve. */
+int mpc_oracle_module_load_solution(const mpc_oracle_cfg* cfg, double* traj) {
+    mpc_oracle_cfg c = *cfg;
+    const double w0[8] = {9.0, 9.0, 10.0, 0.0, 100.0, 1000.0, 0.0, 0.0};
+    int N = cfg->N, k, status = 0, iters = 0;
+    double state[4] = {0, 0, 0, 0}, u_prev[2] = {0, 0}, u0[2], cost;
+    double* ref = (double*)calloc(3 * (N + 1), sizeof(double));
+    memcpy(c.w, w0, sizeof(w0));
+    for (k = 0; k <= N; k++) ref[k] = 15.0 * ((double)k * cfg->dt);
+    mpc_oracle_solve(&c, state, ref, 15.0, u_prev, NULL, traj, u0, &cost, &status, &iters, NULL);
+    free(ref);
+    return status;
+}
+
 int mpc_oracle_closed_loop(const mpc_oracle_cfg* cfg, const mpc_oracle_path* p, const double* pose0, int T,
                            int track_using_time, double target_vel, int warm_start, double* log) {
     int N = cfg->N, nt = 6 * N + 4, step, i, stop = 0;
@@ -1400,6 +1427,7 @@ int mpc_oracle_closed_loop(const mpc_oracle_cfg* cfg, const mpc_oracle_path* p, 
     double* warm = (double*)calloc(nt, sizeof(double));
     double* traj = (double*)malloc(sizeof(double) * nt);
     ipm_t P;
+    if (warm_start) mpc_oracle_module_load_solution(cfg, warm);
     ipm_alloc(&P, cfg);
     for (step = 0; step < T; step++) {
         double state[4], u0[2] = {0, 0}, cost = 0;

@@ -103,6 +103,12 @@ int mpc_oracle_solve_batch(const mpc_oracle_cfg* cfg, long B, const double* stat
                            double* warm, double* u0, double* cost, int* status, int* iters,
                            double* traj, int n_threads);
 
+/* the same, also reporting per problem how many restorations by rollout the solve went through (n_resto [B] or NULL) */
+int mpc_oracle_solve_batch_resto(const mpc_oracle_cfg* cfg, long B, const double* state,
+                                 const double* ref, const double* v_des, const double* u_prev,
+                                 double* warm, double* u0, double* cost, int* status, int* iters,
+                                 double* traj, int* n_resto, int n_threads);
+
 /* Frenet-frame variant (MKZMPCPathFollowerFrenet.jl): cfg->model must be 1 (mpc_oracle_default_cfg_frenet);
  * state = (s0, ey0, epsi0, v0) (update_init_cond :132-138), kpoly = 4 curvature coefficients per problem,
  * highest degree first (update_reference :142-147); traj = s[N+1], ey[N+1], v[N+1], epsi[N+1], d_f[N], acc[N]
@@ -146,8 +152,13 @@ int mpc_oracle_get_waypoints(const mpc_oracle_path* p, int horizon, double traj_
  * disc_steps(10) Euler sub-steps of 1 ms (vehicle_simulator.py:58-106) */
 void mpc_oracle_plant_step(double* st /*8*/, double acc_des, double df_des);
 
+/* Solution (traj order, 6N+4) of the module-load solve of the default problem (MKZMPCPathFollower.jl:36-39,126-128):
+ * the start point of the node's first solve.  Returns its status. */
+int mpc_oracle_module_load_solution(const mpc_oracle_cfg* cfg, double* traj);
+
 /* Closed loop of mpc_cmd_pub.jl:86-157 + plant: T control steps (10 Hz), each
- * followed by 10 plant publishes.  Returns number of steps executed before the
+ * followed by 10 plant publishes; with warm_start the first solve starts from the module-load solution,
+ * every later one from the previous solution.  Returns number of steps executed before the
  * stop latch (or T).  log: per step [x,y,psi,v, acc_cmd, df_cmd, status, iters] (8 doubles). */
 int mpc_oracle_closed_loop(const mpc_oracle_cfg* cfg, const mpc_oracle_path* p,
                            const double* pose0 /* X0,Y0,Psi0 */, int T, int track_using_time,

@@ -130,10 +130,15 @@ def solve_batch(cfg, state, ref, v_des, u_prev, warm=None, want_traj=False, n_th
     status = np.empty(B, dtype=np.int32)
     iters = np.empty(B, dtype=np.int32)
     traj = np.empty((B, 6 * N + 4)) if want_traj else None
-    rc = lib().mpc_oracle_solve_batch(C.byref(cfg), B, _p(state), _p(ref), _p(v_des), _p(u_prev), _p(warm), _p(u0),
-                                      _p(cost), _pi(status), _pi(iters), _p(traj), int(n_threads))
+    n_resto = np.zeros(B, dtype=np.int32)
+    L = lib()
+    L.mpc_oracle_solve_batch_resto.argtypes = [C.POINTER(Cfg), C.c_long] + [C.c_void_p] * 11 + [C.c_int]
+    rc = L.mpc_oracle_solve_batch_resto(C.byref(cfg), B, state.ctypes.data, ref.ctypes.data, None if v_des is None else v_des.ctypes.data,
+                                        u_prev.ctypes.data, None if warm is None else warm.ctypes.data, u0.ctypes.data, cost.ctypes.data,
+                                        status.ctypes.data, iters.ctypes.data, None if traj is None else traj.ctypes.data,
+                                        n_resto.ctypes.data, int(n_threads))
     assert rc == 0
-    return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+    return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj, "n_resto": n_resto}
 
 
 def default_cfg_frenet(N=8, weights=None, tol=None, max_iter=None, **kw):
@@ -168,6 +173,15 @@ def solve_batch_frenet(cfg, state, kpoly, v_des, u_prev, warm=None, want_traj=Fa
                                              _p(cost), _pi(status), _pi(iters), _p(traj), int(n_threads))
     assert rc == 0
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+
+def module_load_solution(cfg):
+    """Solution (traj order) of the module-load solve of the default problem (MKZMPCPathFollower.jl:126-128): the start
+    point of the node's first solve."""
+    t = np.zeros(6 * cfg.N + 4)
+    lib().mpc_oracle_module_load_solution.argtypes = [C.POINTER(Cfg), C.POINTER(C.c_double)]
+    lib().mpc_oracle_module_load_solution(C.byref(cfg), _p(t))
+    return t
 
 
 def rollout_start(cfg, state, u_prev):

@@ -25,7 +25,7 @@ class KCfg(C.Structure):
 
 def build():
     if (not os.path.exists(_LIB)) or any(os.path.getmtime(s) > os.path.getmtime(_LIB) for s in _SRCS):
-        subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-DMPC_HOST_EMU",
+        subprocess.check_call(["/usr/bin/g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-DMPC_HOST_EMU",
                                "-I" + _HERE, "-I" + os.path.join(_ROOT, "mkz_mpc_path_follower_b200", "csrc"),
                                "-x", "c++", _SRCS[0], "-o", _LIB])
     return _LIB
@@ -92,8 +92,9 @@ def solve_batch_frenet(kcfg, state, kpoly, v_des, u_prev, warm=None, want_traj=F
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
 
 
-def rollout(kcfg, traj_table, pose0, T, track_using_time=True, target_vel=1.0):
-    """All vehicles on the path whose (n,7) table is given.  Returns log (T,B,8), final (B,8)."""
+def rollout(kcfg, traj_table, pose0, T, track_using_time=True, target_vel=1.0, warm0=None):
+    """All vehicles on the path whose (n,7) table is given.  warm0 (6N+4,): start point of the first solve (None = zeros).
+    Horizons above 31 run one emulated block of 2-3 warps per vehicle.  Returns log (T,B,8), final (B,8)."""
     lib = C.CDLL(build())
     dp = C.POINTER(C.c_double)
     pose0 = np.ascontiguousarray(np.atleast_2d(pose0), dtype=np.float64)
@@ -102,8 +103,30 @@ def rollout(kcfg, traj_table, pose0, T, track_using_time=True, target_vel=1.0):
     path_of = np.zeros(B, dtype=np.int32)
     log = np.zeros((T, B, 8)); final = np.zeros((B, 8))
     lib.emu_rollout.argtypes = [C.POINTER(KCfg), C.c_long, C.c_int, dp, C.POINTER(C.c_int), C.c_int, dp, dp, dp, dp, dp,
-                                C.c_int, C.c_double, dp, dp]
+                                C.c_int, C.c_double, dp, dp, dp]
+    w0 = None if warm0 is None else np.ascontiguousarray(warm0, dtype=np.float64)
     lib.emu_rollout(C.byref(kcfg), B, T, pose0.ctypes.data_as(dp), path_of.ctypes.data_as(C.POINTER(C.c_int)), traj_table.shape[0],
                     *[c.ctypes.data_as(dp) for c in cols], int(track_using_time), float(target_vel),
-                    log.ctypes.data_as(dp), final.ctypes.data_as(dp))
+                    log.ctypes.data_as(dp), final.ctypes.data_as(dp), None if w0 is None else w0.ctypes.data_as(dp))
     return log, final
+
+
+def solve_batch_on_path(kcfg, traj_table, state, u_prev, track_using_time=True, target_vel=1.0, path_of=None):
+    """mpcb200_solve_batch_on_path on the emulator: waypoints generated by the kernel source from one path table (id 0).
+    Returns dict with u0, cost, status, iters, traj, ref (B,3,N+1), stop."""
+    lib = C.CDLL(build())
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    N = kcfg.N
+    state = np.ascontiguousarray(state, dtype=np.float64); u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+    B = state.shape[0]
+    cols = [np.ascontiguousarray(traj_table[:, i]) for i in (0, 4, 5, 3, 6)]
+    path_of = np.zeros(B, dtype=np.int32) if path_of is None else np.ascontiguousarray(path_of, dtype=np.int32)
+    u0 = np.zeros((B, 2)); cost = np.zeros(B); status = np.zeros(B, dtype=np.int32); iters = np.zeros(B, dtype=np.int32)
+    traj = np.zeros((B, 6 * N + 4)); ref = np.zeros((B, 3, N + 1)); stop = np.zeros(B, dtype=np.int32)
+    lib.emu_solve_batch_on_path.argtypes = [C.POINTER(KCfg), C.c_long, dp, ip, C.c_int, dp, dp, dp, dp, dp, C.c_int, C.c_double,
+                                            dp, dp, dp, ip, ip, dp, dp, ip]
+    lib.emu_solve_batch_on_path(C.byref(kcfg), B, state.ctypes.data_as(dp), path_of.ctypes.data_as(ip), traj_table.shape[0],
+                                *[c.ctypes.data_as(dp) for c in cols], int(track_using_time), float(target_vel),
+                                u_prev.ctypes.data_as(dp), u0.ctypes.data_as(dp), cost.ctypes.data_as(dp), status.ctypes.data_as(ip),
+                                iters.ctypes.data_as(ip), traj.ctypes.data_as(dp), ref.ctypes.data_as(dp), stop.ctypes.data_as(ip))
+    return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj, "ref": ref, "stop": stop}

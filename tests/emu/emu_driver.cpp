@@ -68,7 +68,7 @@ template <int W> static void lane_main(int, void* a) {
 extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, const double* ref, const double* v_des,
                                const double* u_prev, double* warm, double* u0, double* cost, int* status, int* iters,
                                double* traj) {
-    BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj};
+    BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj, nullptr, nullptr};
     KCfg kc = *cfg;
     kcfg_finalize(kc);
     std::vector<int> roles(32 * ROLE_STRIDE);
@@ -97,7 +97,7 @@ template <int W> static void lane_main_frenet(int, void* a) {
 extern "C" int emu_solve_batch_frenet(const KCfg* cfg, long B, const double* state, const double* kpoly, const double* v_des,
                                       const double* u_prev, double* warm, double* u0, double* cost, int* status, int* iters,
                                       double* traj) {
-    BatchPtrs io{state, kpoly, v_des, u_prev, warm, u0, cost, status, iters, traj};
+    BatchPtrs io{state, kpoly, v_des, u_prev, warm, u0, cost, status, iters, traj, nullptr, nullptr};
     KCfg kc = *cfg;
     if (kc.N > 95) return -1;
     kcfg_finalize(kc);
@@ -123,30 +123,82 @@ static void lane_rollout(int lane, void* p) {
     RJob* j = (RJob*)p;
     double* team = j->smem + (size_t)(lane >> 5) * j->per_team;
     TeamSolver<1>::init_work(team, j->cfg->N);
-    rollout_group(*j->cfg, *j->a, j->b0, team, j->smem + (size_t)4 * j->per_team, 4);
+    rollout_group<1>(*j->cfg, *j->a, j->b0, team, j->smem + (size_t)4 * j->per_team, 4);
 }
+template <int W> static void lane_rollout_long(int, void* p) {
+    RJob* j = (RJob*)p;
+    TeamSolver<W>::init_work(j->smem, j->cfg->N);
+    rollout_group<W>(*j->cfg, *j->a, j->b0, j->smem, j->smem + (size_t)j->per_team, 1);
+}
+// warm0: [6N+4] start point of every vehicle's first solve, or null (all zeros)
 extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, const int* path_of, int n0, const double* t,
                            const double* X, const double* Y, const double* psi, const double* s, int track_using_time,
-                           double target_vel, double* log, double* final_state) {
+                           double target_vel, double* log, double* final_state, const double* warm0) {
     KCfg kc = *cfg;
     kcfg_finalize(kc);
+    const int W = team_warps(kc.N);
     std::vector<int> roles(32 * ROLE_STRIDE);
-    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, W_SD_OF(1), roles.data() + l * ROLE_STRIDE);
+    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, W_SD_OF(W), roles.data() + l * ROLE_STRIDE);
     kc.roles = roles.data();
     RolloutArgs a;
     memset(&a, 0, sizeof(a));
     a.pose0 = pose0; a.path_of = path_of;
     for (int i = 0; i < 3; i++) { a.paths[i].n = n0; a.paths[i].t = t; a.paths[i].X = X; a.paths[i].Y = Y; a.paths[i].psi = psi; a.paths[i].s = s; }
     a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel; a.log = log; a.final_state = final_state; a.B = B;
+    a.warm0 = warm0;
     const int per_team = smem_doubles_per_team(kc.N);
     std::vector<double> smem_raw((size_t)4 * per_team + 4 * ROLLOUT_PX + 2, 0.0);
     double* smem = smem_raw.data();
     if (((size_t)smem) & 15) smem++;
+    if (W > 1) {   // long horizons: one emulated block of W warps = one vehicle
+        for (long b0 = 0; b0 < B; b0++) {
+            RJob j{&kc, &a, b0, smem, per_team};
+            emu::race_reset();
+            register_benign(smem, kc.N);
+            emu::run_warp(W == 2 ? lane_rollout_long<2> : lane_rollout_long<3>, &j, W);
+        }
+        return 0;
+    }
     for (long b0 = 0; b0 < B; b0 += 4) {   // one emulated block of four warps = four vehicles
         RJob j{&kc, &a, b0, smem, per_team};
         emu::race_reset();
         for (int w = 0; w < 4; w++) register_benign(smem + (size_t)w * per_team, kc.N);
         emu::run_warp(lane_rollout, &j, 4);
+    }
+    return 0;
+}
+
+// open-loop batch with the waypoints generated by the kernel from one path table (mpcb200_solve_batch_on_path)
+struct PJob { const KCfg* cfg; const BatchPtrs* io; const RefGen* rg; long b; double* smem; };
+template <int W> static void lane_on_path(int, void* p) {
+    PJob* j = (PJob*)p;
+    TeamSolver<W>::init_work(j->smem, j->cfg->N);
+    solve_problem<W>(*j->cfg, *j->io, *j->rg, j->b, j->smem);
+}
+extern "C" int emu_solve_batch_on_path(const KCfg* cfg, long B, const double* state, const int* path_of, int n0, const double* t,
+                                       const double* X, const double* Y, const double* psi, const double* s, int track_using_time,
+                                       double target_vel, const double* u_prev, double* u0, double* cost, int* status, int* iters,
+                                       double* traj, double* ref_out, int* stop) {
+    KCfg kc = *cfg;
+    kcfg_finalize(kc);
+    const int W = team_warps(kc.N);
+    std::vector<int> roles(32 * ROLE_STRIDE);
+    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, W_SD_OF(W), roles.data() + l * ROLE_STRIDE);
+    kc.roles = roles.data();
+    BatchPtrs io{state, nullptr, nullptr, u_prev, nullptr, u0, cost, status, iters, traj, nullptr, nullptr};
+    RefGen rg;
+    memset(&rg, 0, sizeof(rg));
+    rg.path_of = path_of;
+    rg.paths[0].n = n0; rg.paths[0].t = t; rg.paths[0].X = X; rg.paths[0].Y = Y; rg.paths[0].psi = psi; rg.paths[0].s = s;
+    rg.track_using_time = track_using_time; rg.target_vel = target_vel > 0.0 ? target_vel : 0.0; rg.ref_out = ref_out; rg.stop = stop;
+    std::vector<double> smem_raw(smem_doubles_per_team(kc.N) + 2, 0.0);
+    double* smem = smem_raw.data();
+    if (((size_t)smem) & 15) smem++;
+    for (long b = 0; b < B; b++) {
+        PJob j{&kc, &io, &rg, b, smem};
+        emu::race_reset();
+        register_benign(smem, kc.N);
+        emu::run_warp(W == 1 ? lane_on_path<1> : W == 2 ? lane_on_path<2> : lane_on_path<3>, &j, W);
     }
     return 0;
 }

@@ -167,6 +167,10 @@ MPC_DEV void mpc_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(
 MPC_DEV double fast_rcp(double x) { return 1.0 / x; }
 MPC_DEV float fast_log2(float x) { return log2f(x); }
 MPC_DEV float fast_exp2(float x) { return exp2f(x); }
+MPC_DEV double mul_rn(double a, double b) { volatile double r = a * b; return r; }   // the emulator is built with -ffp-contract=off
+MPC_DEV double add_rn(double a, double b) { volatile double r = a + b; return r; }
+MPC_DEV void st_global_v2(double* p, double x, double y) { p[0] = x; p[1] = y; }
+MPC_DEV double int2_as_double(int lo, int hi) { double d; int v[2] = {lo, hi}; memcpy(&d, v, 8); return d; }
 // shared memory: a plain double array, offsets in doubles
 typedef double* smem_t;
 #define SO(x) (x)

@@ -22,7 +22,8 @@ def test_header_symbols_exported():
     assert "mpcb200_solve_batch" in names and "mpcb200_create" in names and len(names) >= 10
     for n in names:
         assert hasattr(L, n), n
-    assert L.mpcb200_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "mpc_b200.h")).read()
+    assert L.mpcb200_version() == int(re.search(r"#define MPCB200_VERSION (\d+)", hdr).group(1))
 
 
 def test_default_config_matches_reference_constants():

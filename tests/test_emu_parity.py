@@ -133,13 +133,62 @@ def test_emulated_rollout_group(oracle):
     rng = np.random.default_rng(3)
     poses = np.array([g.trajectory[j, [4, 5, 3]] + rng.normal(scale=[0.3, 0.3, 0.03]) for j in (0, 900, 2500, 4000, 5200)])
     T = 10
-    log, final = E.rollout(E.kcfg_from_oracle(cfg), g.trajectory, poses, T)
+    seed = oracle.module_load_solution(cfg)    # the first solve starts from the module-load solution (MKZMPCPathFollower.jl:126-128)
+    log, final = E.rollout(E.kcfg_from_oracle(cfg), g.trajectory, poses, T, warm0=seed)
     path, keep = oracle.make_path(g.trajectory)
     for b in range(poses.shape[0]):
         olog = oracle.closed_loop(cfg, path, poses[b], T)
         assert np.array_equal(log[:, b, 6], olog[:, 6]) and np.array_equal(log[:, b, 7], olog[:, 7]), b
         assert np.abs(log[:, b, 4:6] - olog[:, 4:6]).max() <= 1e-9, b
         assert np.abs(log[:, b, 0:4] - olog[:, 0:4]).max() <= 1e-9, b
+
+
+def test_emulated_long_horizon_rollout_and_on_path(oracle):
+    """N = 40: one block of two warps per vehicle.  The team-wide get_waypoints (nearest-sample arg-min reduced across
+    the warps, neighbour exchange for the heading unwrap) against the host generator bit for bit, and three closed-loop
+    steps of the long-horizon rollout against the oracle's closed loop."""
+    import emu as E
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    N = 40
+    g = GPSRefTrajectory(mat_filename=2, traj_horizon=N, traj_dt=0.2)
+    cfg = oracle.default_cfg(N, max_iter=60)
+    rng = np.random.default_rng(5)
+    n = g.trajectory.shape[0]
+    jumps = np.nonzero(np.abs(np.diff(g.trajectory[:, 3])) > np.pi)[0]
+    idx = [100, 2000, int(jumps[0]) - 300 if len(jumps) else 3000, n - 50]
+    state = np.array([[g.trajectory[j, 4] + rng.normal(scale=0.3), g.trajectory[j, 5] + rng.normal(scale=0.3),
+                       g.trajectory[j, 3] + rng.normal(scale=0.03), 5.0] for j in idx])
+    state[1, 2] += 2 * np.pi    # forces the wrap-around fix
+    for mode_time, vt in ((True, 1.0), (False, 6.5)):
+        e = E.solve_batch_on_path(E.kcfg_from_oracle(cfg), g.trajectory, state, np.zeros((len(idx), 2)), track_using_time=mode_time, target_vel=vt)
+        ref, stop = g.get_waypoints_batch(state[:, 0], state[:, 1], state[:, 2], v_target=None if mode_time else vt)
+        assert np.array_equal(e["ref"], ref)          # bit for bit: every operation rounded like numpy's
+        assert np.array_equal(e["stop"].astype(bool), stop)
+    assert E.race_count() == 0
+    # closed loop, two vehicles, three control steps
+    cfg = oracle.default_cfg(N, max_iter=200)
+    poses = np.array([g.trajectory[j, [4, 5, 3]] + rng.normal(scale=[0.2, 0.2, 0.02]) for j in (500, 3000)])
+    seed = oracle.module_load_solution(cfg)
+    log, final = E.rollout(E.kcfg_from_oracle(cfg), g.trajectory, poses, 3, warm0=seed)
+    path, keep = oracle.make_path(g.trajectory)
+    for b in range(2):
+        olog = oracle.closed_loop(cfg, path, poses[b], 3)
+        assert np.array_equal(log[:, b, 6], olog[:, 6]), (b, log[:, b, 6:8], olog[:, 6:8])
+        assert np.abs(log[:, b, 7] - olog[:, 7]).max() <= 2
+        assert np.abs(log[:, b, 4:6] - olog[:, 4:6]).max() <= 1e-6, b
+        assert np.abs(log[:, b, 0:4] - olog[:, 0:4]).max() <= 1e-9, b
+
+
+def test_emulated_on_path_bad_path_id(oracle):
+    """A path id outside the tables (possible only with device pointers, which the host cannot inspect) is answered with
+    status Error and zero commands instead of an out-of-range table access."""
+    import emu as E
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    g = GPSRefTrajectory(mat_filename=1)
+    cfg = oracle.default_cfg(8)
+    state = np.array([[g.trajectory[50, 4], g.trajectory[50, 5], g.trajectory[50, 3], 3.0]] * 3)
+    e = E.solve_batch_on_path(E.kcfg_from_oracle(cfg), g.trajectory, state, np.zeros((3, 2)), path_of=np.array([0, 7, -1]))
+    assert e["status"].tolist() == [0, 4, 4] and np.all(e["u0"][1:] == 0.0) and e["iters"][1:].tolist() == [0, 0]
 
 
 def test_line_search_failure_at_an_acceptable_point(oracle):

@@ -47,7 +47,14 @@ def stub_modules():
 
 def load_py2(path, name):
     src = open(path).read()
-    src = re.sub(r"^(\s*)print\s+'([^']*)'\s*$", r"\1print('\2')", src, flags=re.M)  # the only py2-isms
+    src = re.sub(r"^(\s*)print\s+'([^']*)'\s*$", r"\1print('\2')", src, flags=re.M)
+    # the other Python-2-ism: `1/m` with the int m = 1840 (vehicle_simulator.py:86) is INTEGER division there
+    # (= 0: the tyre-force term drops out of the vx equation as the node runs); keep that under Python 3
+    n_div = src.count("1/m*")
+    src = src.replace("1/m*", "(1//m)*")
+    if name == "vehicle_simulator":
+        assert n_div == 1, "expected exactly one int/int division in vehicle_simulator.py"
+
     mod = types.ModuleType(name)
     mod.__dict__["__name__"] = name
     exec(compile(src, path, "exec"), mod.__dict__)
