@@ -37,6 +37,11 @@ def parse():
     ap.add_argument("--horizon", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs beside the headline (config1, rollout_config3, horizon_sweep, strong_64k)")
+    ap.add_argument("--parity", default="full", choices=["full", "sample"],
+                    help="full: every problem of every rank's slice is checked against the oracle (the converged count); sample: a bounded sample")
+    ap.add_argument("--rollout-vehicles", type=int, default=16384)
+    ap.add_argument("--rollout-steps", type=int, default=500)
     ap.add_argument("--x0", dest="start", default="zero", choices=["zero", "rollout"],
                     help="start point: zero = the reference's start=0.0 (the metric); rollout = MPCB200_START_ROLLOUT "
                          "(opt-in; what the horizon sweep of configs[4] uses at N = 40 / 80)")
@@ -148,13 +153,13 @@ class NvmlClockSampler(object):
                 "reasons": reasons, "samples": len(self.samples), "source": "nvml, 5 ms poll"}
 
 
-def cpu_baseline(N, sample, threads, start_b0=0, start="zero"):
+def cpu_baseline(N, sample, threads, start_b0=0, start="zero", max_iter=None):
     """The oracle (restated CPU interior point, NOT Ipopt) on a bounded sample of the same workload."""
     from oracle import oracle as O
     from mkz_mpc_path_follower_b200 import workload
     O.build()
     b = workload.make_batch(sample, N, b0=start_b0)
-    cfg = O.default_cfg(N)
+    cfg = O.default_cfg(N, max_iter=max_iter)
     warm = O.rollout_start(cfg, b["state"], b["u_prev"]) if start == "rollout" else None
     t0 = time.perf_counter()
     r = O.solve_batch(cfg, b["state"], b["ref"], b["v_des"], b["u_prev"], warm=warm, n_threads=threads)
@@ -163,15 +168,44 @@ def cpu_baseline(N, sample, threads, start_b0=0, start="zero"):
     return conv / dt, dt, conv, r
 
 
+def ipopt_probe(dump_dir=None, N=20, n_dump=256):
+    """is the reference's real solver stack reachable on THIS box at run time?  Looks for `julia`, an
+    `ipopt` executable and an importable `cyipopt`.  If cyipopt is there, the first n_dump problems of the bench batch
+    are solved with the real Ipopt (tools/ipopt_golden.py: the oracle's NLP callbacks behind cyipopt.Problem) and dumped
+    as golden vectors.  The probe itself never fails the bench."""
+    import shutil
+    found = {"julia": shutil.which("julia"), "ipopt": shutil.which("ipopt"), "cyipopt": False}
+    try:
+        import cyipopt  # noqa: F401
+        found["cyipopt"] = getattr(cyipopt, "__version__", True)
+    except Exception:
+        pass
+    if found["julia"]:
+        try:
+            found["julia_version"] = subprocess.check_output([found["julia"], "--version"], text=True, timeout=60).strip()
+        except Exception as ex:
+            found["julia_version"] = repr(ex)
+    if found["cyipopt"] and dump_dir:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import ipopt_golden
+            found["golden"] = ipopt_golden.dump(os.path.join(dump_dir, "ipopt_N%d.npz" % N), N, n_dump)
+        except Exception as ex:
+            found["golden"] = {"error": repr(ex)}
+    found["reachable"] = bool(found["julia"] or found["ipopt"] or found["cyipopt"])
+    return found
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU path.  Julia/JuMP/Ipopt cannot run here, so
-    this arm times the oracle port with every host core, one bounded sample per step."""
+    """--impl reference: the reference's CPU path.  Julia/JuMP/Ipopt cannot run here (probed again at run
+    time below), so this arm times the oracle port with every host core, one bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     N = args.horizon
     cores = os.cpu_count() or 1
     sample = args.cpu_sample or max(256, 64 * cores)
+    probe = ipopt_probe(os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else None, N)
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(N, min(sample, 256), cores, start=args.start)
     t_tot, conv_tot = 0.0, 0
@@ -185,13 +219,33 @@ def run_reference(args):
         "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_tot / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[2]: N=%d cold-start solves along path1-3, bounded sample of %d problems/step" % (N, sample)},
+        "config": {"workload": "configs[2]: N=%d cold-start solves along path1-3, bounded sample of %d problems/step "
+                               "(problems [s*%d, (s+1)*%d) of the GPU arm's batch stream)" % (N, sample, sample, sample)},
         "cpu_baseline": {"value": val, "unit": "solves/s", "cores": cores, "kind": "port",
                          "sample": "%d problems/step x %d steps, restated CPU interior point (oracle), NOT Ipopt" % (sample, args.steps)},
+        "ipopt_probe": probe,
         "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def parity_counts(g_u0, g_cost, g_status, o, ids0=0):
+    """a solve is converged only with status Optimal AND parity with the oracle: same status,
+    |du| <= 1e-5 on the first move, relative cost <= 1e-6."""
+    st_eq = g_status == o["status"]
+    both = (g_status == 0) & (o["status"] == 0)
+    du = np.abs(g_u0 - o["u0"]).max(axis=1)
+    rc = np.abs(g_cost - o["cost"]) / np.maximum(1.0, np.abs(o["cost"]))
+    ok = both & (du <= 1e-5) & (rc <= 1e-6)
+    bad = np.nonzero(~st_eq | (both & ~ok))[0]
+    return ok, {
+        "sample": int(g_status.shape[0]), "status_mismatch": int((~st_eq).sum()),
+        "du_gt_1e-5": int((both & (du > 1e-5)).sum()), "relcost_gt_1e-6": int((both & (rc > 1e-6)).sum()),
+        "converged_and_in_parity": int(ok.sum()), "gpu_optimal": int((g_status == 0).sum()), "oracle_optimal": int((o["status"] == 0).sum()),
+        "max_abs_du": float(du[both].max()) if both.any() else None, "p999_abs_du": float(np.quantile(du[both], 0.999)) if both.any() else None,
+        "mismatch_ids": [int(i) + ids0 for i in bad[:32]],
+        "tolerance": "status equal, |du| <= 1e-5, |dcost| <= 1e-6 max(1, |cost|) (north_star)"}
 
 
 def main():
@@ -213,7 +267,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     N, B = args.horizon, args.batch
-    nt = 6 * N + 4
+    cores = os.cpu_count() or 1
+
+    def allmax(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(vs):
+        t = torch.tensor([float(v) for v in vs], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
 
     # ---- synthetic batch: this rank's contiguous slice of the problem stream
     b = workload.make_batch(B, N, b0=rank * B)
@@ -225,17 +291,15 @@ def main():
     d_ref = torch.from_numpy(b["ref"]).to(dev)
     d_uprev = torch.from_numpy(b["u_prev"]).to(dev)
     d_vdes = torch.from_numpy(b["v_des"]).to(dev)
-    d_u0 = torch.empty((B, 2), dtype=torch.float64, device=dev)
-    d_cost = torch.empty(B, dtype=torch.float64, device=dev)
-    d_status = torch.empty(B, dtype=torch.int32, device=dev)
-    d_iters = torch.empty(B, dtype=torch.int32, device=dev)
+    d_rec = torch.empty((B, 4), dtype=torch.float64, device=dev)   # the packed 32-byte records, written by the kernel
+    d_all = torch.empty((world * B, 4), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step():
         flush.zero_()  # L2 flush between timed iterations (inputs are 36 MB < L2)
-        solver.solve_batch_device(B, d_state, d_ref, d_uprev, d_u0, v_des=d_vdes, cost=d_cost, status=d_status, iters=d_iters)
-        if world > 1:   # the one exchange step: all-gather of the 32 B/problem result record
-            sharding.all_gather_records(sharding.pack_records(d_u0, d_cost, d_status, d_iters))
+        solver.solve_batch_records_device(B, d_state, d_ref, d_uprev, d_rec, v_des=d_vdes)
+        if world > 1:   # the one exchange step: all-gather of the 32 B/problem result record the kernel wrote
+            dist.all_gather_into_tensor(d_all, d_rec)
 
     def barrier():
         if world > 1:
@@ -256,79 +320,239 @@ def main():
     for _ in range(args.steps):
         flush.zero_()
         e0.record()
-        solver.solve_batch_device(B, d_state, d_ref, d_uprev, d_u0, v_des=d_vdes, cost=d_cost, status=d_status, iters=d_iters)
+        solver.solve_batch_records_device(B, d_state, d_ref, d_uprev, d_rec, v_des=d_vdes)
         e1.record()
-        if world > 1:   # the one exchange step: all-gather of the 32 B/problem result record
-            sharding.all_gather_records(sharding.pack_records(d_u0, d_cost, d_status, d_iters))
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_rec)
         e1.synchronize()
         kern_ms.append(e0.elapsed_time(e1))
     t1.record()
     barrier()
     clocks = sampler.stop()
-    total_ms = t0.elapsed_time(t1)
-    tm = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    total_ms = float(tm.item())
+    total_ms = allmax(t0.elapsed_time(t1))
     km = torch.zeros(world, dtype=torch.float64, device=dev)
     km[rank] = float(np.mean(kern_ms))
     if world > 1:
         dist.all_reduce(km, op=dist.ReduceOp.SUM)
     kernel_ms_per_rank = [round(float(v), 3) for v in km.tolist()]
 
-    status = d_status.cpu().numpy(); iters = d_iters.cpu().numpy()
-    conv_local = int((status == 0).sum())
-    cnt = torch.tensor([conv_local, int(iters.sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    conv_total, iters_total = float(cnt[0].item()), float(cnt[1].item())
+    u0, cost, status, iters, resto = sharding.unpack_records_np(d_rec.cpu().numpy())
+    u0 = u0.copy(); cost = cost.copy()
+    optimal_local = int((status == 0).sum())
+
+    # ---- parity against the oracle on EVERY problem of this rank's slice (converged = Optimal AND within
+    # tolerance of the oracle); at one GPU this run is also the cpu_baseline (the oracle timed on the box's cores)
+    from oracle import oracle as O
+    O.build()
+    ocfg = O.default_cfg(N, max_iter=int(solver.cfg.max_iter))
+    threads = max(1, cores // world)
+    n_par = B if args.parity == "full" else min(B, args.cpu_sample or max(256, 48 * cores))
+    owarm = O.rollout_start(ocfg, b["state"][:n_par], b["u_prev"][:n_par]) if args.start == "rollout" else None
+    tc0 = time.perf_counter()
+    o = O.solve_batch(ocfg, b["state"][:n_par], b["ref"][:n_par], b["v_des"][:n_par], b["u_prev"][:n_par], warm=owarm, n_threads=threads)
+    cpu_dt = time.perf_counter() - tc0
+    ok, parity = parity_counts(u0[:n_par], cost[:n_par], status[:n_par], o, ids0=rank * B)
+    parity["oracle_restored"] = int((o["n_resto"] > 0).sum())
+    parity["restored_sets_equal"] = bool(np.array_equal(o["n_resto"] > 0, resto[:n_par] > 0))
+    # converged: checked problems count when in parity; problems outside the checked sample (only with --parity sample) count by status
+    conv_local = int(ok.sum()) + int((status[n_par:] == 0).sum())
+    conv_nores_local = int((ok & (resto[:n_par] == 0)).sum()) + int(((status[n_par:] == 0) & (resto[n_par:] == 0)).sum())
+    conv_total, conv_nores_total, optimal_total, iters_total, resto_total, checked_total, inpar_total = allsum(
+        [conv_local, conv_nores_local, optimal_local, int(iters.sum()), int((resto > 0).sum()), n_par, int(ok.sum())])
     value = conv_total * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the C ABI with pinned host buffers (H2D + kernel + D2H timed)
+    # ---- end to end through the C ABI with pinned host buffers (H2D + kernel + D2H timed; at N > 1 the all-gather too)
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
     h_state, h_ref, h_uprev, h_vdes = pin(b["state"]), pin(b["ref"]), pin(b["u_prev"]), pin(b["v_des"])
     solver.set_stream(None)  # back to the handle's own stream
+    gather_bytes = 0
+
+    def e2e_step():
+        r = solver.solve_batch_records(h_state, h_ref, h_uprev, v_des=h_vdes)
+        if world > 1:   # every rank ends the step holding every problem's record, on the host
+            d_rec.copy_(torch.from_numpy(r))
+            dist.all_gather_into_tensor(d_all, d_rec)
+            return d_all.cpu().numpy()
+        return r
     for _ in range(2):
-        solver.solve_batch(h_state, h_ref, h_uprev, v_des=h_vdes)
+        e2e_step()
     barrier()
     w0 = time.perf_counter()
-    h2d = d2h = launches = 0
+    h2d = d2h = 0
     for _ in range(args.steps):
-        r = solver.solve_batch(h_state, h_ref, h_uprev, v_des=h_vdes)
+        e2e_step()
         st = solver.stats()
         h2d, d2h = st["h2d_bytes"], st["d2h_bytes"]
-        launches += st["kernel_launches"]
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - w0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    e2e_value = conv_total * args.steps / allmax(time.perf_counter() - w0)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = conv_total * args.steps / float(te.item())
+        h2d += B * 32; d2h += world * B * 32; gather_bytes = world * B * 32
 
     # ---- the same with the waypoints generated on the device (mpcb200_solve_batch_on_path): the host sends the
     # state, the path id and the previous command only (60 B/problem instead of 560)
-    e2e_on_path = None
-    if N <= 31:
-        from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
-        for i, pth in enumerate((1, 2, 3)):
-            solver.set_path(i, GPSRefTrajectory(mat_filename=pth, traj_horizon=N, traj_dt=0.2).trajectory)
-        h_pathof = torch.from_numpy((b["path"] - 1).astype(np.int32)).pin_memory().numpy()
-        for _ in range(2):
-            solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    for i, pth in enumerate((1, 2, 3)):
+        solver.set_path(i, GPSRefTrajectory(mat_filename=pth, traj_horizon=N, traj_dt=0.2).trajectory)
+    h_pathof = torch.from_numpy((b["path"] - 1).astype(np.int32)).pin_memory().numpy()
+    for _ in range(2):
+        solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        r2 = solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
+        st2 = solver.stats()
+    torch.cuda.synchronize()
+    t_op = allmax(time.perf_counter() - w0)
+    same_as_ref = bool(np.array_equal(r2["u0"], u0) and np.array_equal(r2["status"], status))
+    e2e_on_path = {"value": allsum([float((r2["status"] == 0).sum())])[0] * args.steps / t_op, "unit": "solves/s",
+                   "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
+                   "bitwise_equal_to_host_references": same_as_ref,
+                   "what": "mpcb200_solve_batch_on_path: reference waypoints generated on the device"}
+
+    extras = {}
+
+    def extra(name, fn):
+        """the configs beside the headline: outside its timed region, never allowed to break the line"""
+        try:
+            extras[name] = fn()
+        except Exception as ex:
+            extras[name] = {"error": repr(ex)}
+
+    def timed_device_solve(Nh, Bh, start_mode, max_iter=None, reps=2, b0=0, rollout_warm=False):
+        bb = workload.make_batch(Bh, Nh, b0=b0)
+        kw = {} if max_iter is None else {"max_iter": max_iter}
+        sv = capi.Solver(Nh, device=local, start_mode=start_mode, **kw)
+        sv.set_stream(stream.cuda_stream)
+        dd = {k_: torch.from_numpy(bb[k_]).to(dev) for k_ in ("state", "ref", "u_prev", "v_des")}
+        rec = torch.empty((Bh, 4), dtype=torch.float64, device=dev)
+        best = 1e30
+        for _ in range(1 + reps):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            sv.solve_batch_records_device(Bh, dd["state"], dd["ref"], dd["u_prev"], rec, v_des=dd["v_des"])
+            a1.record(stream); torch.cuda.synchronize()
+            best = min(best, a0.elapsed_time(a1))
+        uu, cc, ss, ii, rr = sharding.unpack_records_np(rec.cpu().numpy())
+        sv.close()
+        return bb, best, uu.copy(), cc.copy(), ss, ii, rr
+
+    # configs[1]: 4,096 cold solves at N = 8 along path 1 (one GPU's worth: every rank runs the same batch, rank 0 reports)
+    def config1():
+        bb, ms, uu, cc, ss, ii, rr = timed_device_solve(8, 4096, capi.START_ZERO)
+        bb = workload.make_batch(4096, 8, path_ids=(1,))
+        sv = capi.Solver(8, device=local); sv.set_stream(stream.cuda_stream)
+        dd = {k_: torch.from_numpy(bb[k_]).to(dev) for k_ in ("state", "ref", "u_prev", "v_des")}
+        rec = torch.empty((4096, 4), dtype=torch.float64, device=dev)
+        ms = 1e30
+        for _ in range(4):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            sv.solve_batch_records_device(4096, dd["state"], dd["ref"], dd["u_prev"], rec, v_des=dd["v_des"])
+            a1.record(stream); torch.cuda.synchronize()
+            ms = min(ms, a0.elapsed_time(a1))
+        uu, cc, ss, ii, rr = sharding.unpack_records_np(rec.cpu().numpy())
+        tq = time.perf_counter()
+        oo = O.solve_batch(O.default_cfg(8, max_iter=int(sv.cfg.max_iter)), bb["state"], bb["ref"], bb["v_des"], bb["u_prev"], n_threads=threads)
+        cdt = time.perf_counter() - tq
+        sv.close()
+        okk, par = parity_counts(uu.copy(), cc.copy(), ss, oo)
+        return {"what": "configs[1]: 4,096 cold solves from perturbed states along path1, N=8, one GPU", "kernel_ms": ms,
+                "value": float(okk.sum()) / (ms * 1e-3), "unit": "converged solves/s", "mean_iters": float(ii.mean()),
+                "restored": int((rr > 0).sum()), "parity_vs_oracle": par,
+                "cpu_oracle": {"value": float((oo["status"] == 0).sum()) / cdt, "unit": "solves/s", "cores": threads, "kind": "port"}}
+
+    # configs[3]: 16,384 vehicles x 500 control steps, closed loop on the device, the fleet sharded over the ranks
+    def rollout_config3():
+        from mkz_mpc_path_follower_b200 import closed_loop
+        V, T = args.rollout_vehicles, args.rollout_steps
+        trajs = [GPSRefTrajectory(mat_filename=p_) for p_ in (1, 2, 3)]
+        rng = np.random.Generator(np.random.Philox(key=20261018))
+        nz = rng.normal(size=(V, 3)) * np.array([0.3, 0.3, 0.05])
+        path_of = (np.arange(V) % 3).astype(np.int32)
+        pose0 = np.stack([trajs[p_].trajectory[0, [4, 5, 3]] for p_ in path_of]) + nz
+        lo, hi = sharding.shard_range(V, world, rank)
+        sv = capi.Solver(8, device=local)
+        for i_, g_ in enumerate(trajs):
+            sv.set_path(i_, g_.trajectory)
+        sv.rollout(pose0[lo:lo + 64], path_of[lo:lo + 64], 5)    # warm-up (module-load solve, clocks)
         barrier()
-        w0 = time.perf_counter()
-        for _ in range(args.steps):
-            r2 = solver.solve_batch_on_path(h_state, h_pathof, h_uprev, v_des=h_vdes)
-            st2 = solver.stats()
-        torch.cuda.synchronize()
-        tp = torch.tensor([time.perf_counter() - w0, float((r2["status"] == 0).sum())], dtype=torch.float64, device=dev)
+        tq = time.perf_counter()
+        out = sv.rollout(pose0[lo:hi], path_of[lo:hi], T)
+        wall = allmax(time.perf_counter() - tq)
+        kms = allmax(sv.stats()["kernel_ms"])
+        log = out["log"]
+        solved = log[:, :, 6] >= 0
+        err = np.zeros(hi - lo)
+        for p_ in range(3):
+            m = path_of[lo:hi] == p_
+            if m.any():
+                err[m] = closed_loop.path_errors(log[-1:, m, :], trajs[p_].trajectory)[0]
+        n_solved, n_opt, n_it = allsum([float(solved.sum()), float((log[:, :, 6] == 0).sum()), float(log[:, :, 7].sum())])
         if world > 1:
-            tmax = tp[0:1].clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            csum = tp[1:2].clone(); dist.all_reduce(csum, op=dist.ReduceOp.SUM)
-            tp = torch.cat((tmax, csum))
-        e2e_on_path = {"value": float(tp[1].item()) * args.steps / float(tp[0].item()), "unit": "solves/s",
-                       "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
-                       "what": "mpcb200_solve_batch_on_path: reference waypoints generated on the device"}
+            ea = torch.zeros(V, dtype=torch.float64, device=dev); ea[lo:hi] = torch.from_numpy(err).to(dev)
+            dist.all_reduce(ea, op=dist.ReduceOp.SUM); err = ea.cpu().numpy()
+        sv.close()
+        return {"what": "configs[3]: %d vehicles x %d control steps (N=8, paths 1-3, warm-started solve each step) through "
+                        "mpcb200_rollout, fleet sharded over %d GPU(s)" % (V, T, world), "scaling": "strong",
+                "wall_s": wall, "kernel_ms": kms, "solves": n_solved, "solves_per_s": n_solved / wall,
+                "vehicle_steps_per_s": V * T / wall, "optimal_frac": n_opt / max(1.0, n_solved), "mean_iters": n_it / max(1.0, n_solved),
+                "final_path_error_m": {"median": float(np.median(err)), "p99": float(np.quantile(err, 0.99))}}
+
+    # configs[4]: horizon sweep N = 8 / 40 / 80 (N = 20 is the headline), per GPU, from the reference's all-zero start
+    # (with its converged fraction inside the iteration cap) and from MPCB200_START_ROLLOUT (opt-in)
+    def horizon_sweep():
+        res = {}
+        for Nh, Bh in ((8, 65536), (40, 16384), (80, 8192)):
+            row = {"batch_per_gpu": Bh}
+            for nm, mode in (("zero_start", capi.START_ZERO), ("rollout_start", capi.START_ROLLOUT)):
+                bb, ms, uu, cc, ss, ii, rr = timed_device_solve(Nh, Bh, mode, reps=1, b0=rank * Bh)
+                conv, nit = allsum([float((ss == 0).sum()), float(ii.sum())])
+                msx = allmax(ms)
+                row[nm] = {"kernel_ms": msx, "converged_frac": conv / (world * Bh), "mean_iters": nit / (world * Bh),
+                           "value": conv / (msx * 1e-3), "unit": "converged solves/s", "max_iter": 200,
+                           "fp64_tflops": nit * (F_RIC + F_EVAL) * Nh / (msx * 1e-3) / 1e12}
+            res["N%d" % Nh] = row
+        res["what"] = ("configs[4] per GPU (weak): all-zero start = the reference's start=0.0, converged fraction inside the "
+                       "200-iteration cap; rollout start = MPCB200_START_ROLLOUT (opt-in, not a reference behaviour)")
+        return res
+
+    # strong scaling of configs[2]: ONE 65,536-problem batch cut into contiguous slices over the ranks
+    def strong_64k():
+        lo, hi = sharding.shard_range(B, world, rank)
+        n = hi - lo
+        if world == 1:
+            return {"what": "one 65,536 batch on one GPU = the headline", "ms": total_ms / args.steps, "efficiency_vs_one_gpu": 1.0}
+        bb = workload.make_batch(n, N, b0=lo)
+        dd = {k_: torch.from_numpy(bb[k_]).to(dev) for k_ in ("state", "ref", "u_prev", "v_des")}
+        rec = torch.empty((n, 4), dtype=torch.float64, device=dev)
+        sizes = [sharding.shard_range(B, world, q)[1] - sharding.shard_range(B, world, q)[0] for q in range(world)]
+        solver.set_stream(stream.cuda_stream)
+        ms = []
+        for i_ in range(2 + args.steps):
+            flush.zero_()
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            solver.solve_batch_records_device(n, dd["state"], dd["ref"], dd["u_prev"], rec, v_des=dd["v_des"])
+            allrec = sharding.all_gather_records(rec, sizes)
+            a1.record(stream); torch.cuda.synchronize()
+            if i_ >= 2:
+                ms.append(allmax(a0.elapsed_time(a1)))
+        solver.set_stream(None)
+        st_all = sharding.unpack_records_np(allrec.cpu().numpy())[2]
+        one = float(np.mean(kernel_ms_per_rank))     # one GPU's time for 65,536 problems (this run, weak-scaling step)
+        m = float(np.mean(ms))
+        return {"what": "ONE 65,536-problem batch of configs[2] split over %d GPUs (contiguous slices, all-gather of the records)" % world,
+                "ms": m, "value": float((st_all == 0).sum()) / (m * 1e-3), "unit": "Optimal solves/s",
+                "efficiency_vs_one_gpu": one / (world * m), "problems_per_gpu": n}
+
+    if not args.no_extras:
+        extra("config1", config1)
+        extra("rollout_config3", rollout_config3)
+        extra("horizon_sweep", horizon_sweep)
+        extra("strong_64k", strong_64k)
 
     if rank != 0:
         if world > 1:
@@ -366,17 +590,6 @@ def main():
                 "algorithmic_bytes_per_solve": io_bytes // B},
     }
 
-    # ---- CPU baseline beside it: oracle on a bounded sample, all cores
-    cores = os.cpu_count() or 1
-    sample = args.cpu_sample or max(256, 48 * cores)
-    cpu_v, cpu_dt, cpu_conv, cpu_r = cpu_baseline(N, sample, cores, start=args.start)
-    ok = (cpu_r["status"] == 0) & (status[:sample] == 0) if rank == 0 else None
-    u0 = d_u0.cpu().numpy()
-    parity = {
-        "sample": sample, "status_equal": bool((cpu_r["status"] == status[:sample]).all()),
-        "max_abs_du": float(np.abs(u0[:sample] - cpu_r["u0"])[ok].max()) if ok.any() else None,
-    }
-
     line = {
         "metric": "converged MPC solves/sec at batch 64K, N=20" if (N == 20 and B == 65536) else "converged MPC solves/sec at batch %d per GPU, N=%d" % (B, N),
         "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -387,16 +600,31 @@ def main():
                                                                  "all-zero start (start=0.0)" if args.start == "zero" else "rollout start (opt-in)", N),
                    "batch_per_gpu": B, "horizon": N, "l2": "256 MiB flush between steps (inputs 36 MB < L2)",
                    "start": args.start, "max_iter": int(solver.cfg.max_iter)},
+        "converged": {"definition": "status Optimal AND in parity with the oracle on the same inputs (SURVEY 8d), every problem of "
+                                    "every rank's slice checked" if args.parity == "full" else "status Optimal; oracle parity on a sample only",
+                      "converged_frac": conv_total / (world * B), "optimal_frac": optimal_total / (world * B),
+                      "checked": int(checked_total), "in_parity": int(inpar_total)},
         "converged_frac": conv_total / (world * B), "mean_iters": iters_total / (world * B),
+        "restored": {"what": "problems whose line search failed where Ipopt would enter its restoration phase (not restated: "
+                             "restoration by rollout instead, DESIGN 5); what Ipopt returns on them is unknown",
+                     "count": int(resto_total), "frac": resto_total / (world * B),
+                     "value_excluding_restored": conv_nores_total * args.steps / (total_ms * 1e-3)},
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cores, "kind": "port",
-                         "sample": "first %d problems of the same batch, restated CPU interior point (oracle), NOT Ipopt" % sample},
+        "cpu_baseline": {"value": float((o["status"] == 0).sum()) / cpu_dt, "unit": "solves/s", "cores": threads, "kind": "port",
+                         "seconds": cpu_dt,
+                         "sample": "%s %d problems of rank 0's batch, restated CPU interior point (oracle), NOT Ipopt" %
+                                   ("all" if n_par == B else "first", n_par)},
         "parity_vs_oracle": parity,
-        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "ipopt_probe": ipopt_probe(),
+        "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "gather_bytes_per_step": int(gather_bytes),
+                "what": "mpcb200_solve_batch_records with pinned HOST buffers (H2D + kernel + D2H inside the call)" +
+                        ("; then the all-gather of the records and its read-back, all inside the timed region" if world > 1 else "")},
         "e2e_on_path": e2e_on_path,
         "gpu_launches": int(args.steps * 1),
         "clocks": clocks,
     }
+    line.update(extras)
 
     if N <= 31:
         # the Frenet-frame variant (MKZMPCPathFollowerFrenet.jl) on the same batch size and horizon, outside the
