@@ -172,7 +172,6 @@ int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T,
                     int32_t track_using_time, double target_vel,
                     double* log, double* final_state);
 
-/* Counters of the last solve_batch/rollout call on this handle. */
 /*
  * Frenet-frame variant of the same solver: scripts/mpc_utils/MKZMPCPathFollowerFrenet.jl (the model the Gazebo
  * lane-keep node gazebo_sim_mpc_cmd_pub_frenet.jl:112-153 drives).  Same vehicle constants, horizon, bounds, rate
@@ -194,6 +193,20 @@ int mpcb200_solve_batch_frenet(mpcb200_handle* h, int64_t B, const double* state
                                const double* v_des, const double* u_prev, double* warm, double* u0,
                                double* cost, int32_t* status, int32_t* iters, double* traj, int32_t mem_space);
 
+/*
+ * Closed loop on the Frenet-frame module, on the device (scripts/nodes_gazebo_sim/gazebo_sim_mpc_cmd_pub_frenet.jl:112-153
+ * around the plant of scripts/vehicle_simulator.py:58-112; Gazebo itself is out of scope): B vehicles x T control steps.
+ * Per step and vehicle: the next `window` metres of its path (mpcb200_set_path) from the sample nearest to the vehicle,
+ * seen from the vehicle -> K_coeffs, psi_start = get_reference_frenet (scripts/sim_path_utils/nav_msgs_path_frenet.py:44-86:
+ * two cubic least-squares fits on fixed grids) -> update_init_cond(0, e_y, -psi_start, v) (:125; e_y = 0 like the node, or
+ * the vehicle's lateral offset from the fitted path start when ey_from_path != 0), update_reference(path, K_coeffs,
+ * target_vel) (:126), solve_model from the previous solution (:130), command published whatever the status (:139-143),
+ * update_current_input(df_opt, a_opt) (:145).  log / final as in mpcb200_rollout.  Frenet handles, N <= 31, host pointers.
+ */
+int mpcb200_rollout_frenet(mpcb200_handle* h, int64_t B, int32_t T, const double* pose0, const int32_t* path_of,
+                           double window, double target_vel, int32_t ey_from_path, double* log, double* final_state);
+
+/* Counters of the last solve_batch/rollout call on this handle. */
 typedef struct {
     int64_t kernel_launches;   /* kernels of this library launched by the call */
     int64_t h2d_bytes, d2h_bytes;

@@ -63,6 +63,7 @@ def lib():
     L.mpcb200_solve_batch_on_path.argtypes = [vp, C.c_int64, vp, vp, C.c_int32, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.mpcb200_set_path.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, dp, dp]
     L.mpcb200_rollout.argtypes = [vp, C.c_int64, C.c_int32, dp, ip, C.c_int32, C.c_double, dp, dp]
+    L.mpcb200_rollout_frenet.argtypes = [vp, C.c_int64, C.c_int32, dp, ip, C.c_double, C.c_double, C.c_int32, dp, dp]
     L.mpcb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mpcb200_fp64_peak.argtypes = [vp, dp]
     L.mpcb200_last_error.argtypes = [vp]
@@ -304,6 +305,22 @@ class FrenetSolver(Solver):
         self._check(lib().mpcb200_solve_batch_frenet(self._h, B, _ptr(state), _ptr(k_coeffs), _ptr(v_des), _ptr(u_prev), _ptr(warm),
                                                      _ptr(u0), _ptr(cost), _ptr(status), _ptr(iters), _ptr(traj), HOST))
         return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+    def rollout(self, pose0, path_of, T, window=40.0, target_vel=8.0, ey_from_path=True, want_log=True):
+        """Closed loop on the Frenet-frame module on the device (mpcb200_rollout_frenet; what closed_loop.run_frenet does on the
+        host).  pose0 (B,3); path_of (B,) ids given to set_path.  Returns log (T,B,8) and final (B,8) like Solver.rollout."""
+        pose0 = np.ascontiguousarray(np.atleast_2d(pose0), dtype=np.float64)
+        B = pose0.shape[0]
+        path_of = np.ascontiguousarray(path_of, dtype=np.int32)
+        if pose0.shape != (B, 3) or path_of.shape != (B,):
+            raise ValueError("rollout: pose0 must be (B,3) and path_of (B,)")
+        log = np.empty((T, B, 8)) if want_log else None
+        final = np.empty((B, 8))
+        dp = C.POINTER(C.c_double)
+        self._check(lib().mpcb200_rollout_frenet(self._h, B, int(T), pose0.ctypes.data_as(dp), path_of.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                 float(window), float(target_vel), int(bool(ey_from_path)),
+                                                 None if log is None else log.ctypes.data_as(dp), final.ctypes.data_as(dp)))
+        return {"log": log, "final_state": final}
 
     def solve_batch_device(self, B, state, k_coeffs, u_prev, u0, v_des=None, warm=None, cost=None, status=None, iters=None, traj=None):
         """Device pointers (torch CUDA tensors or ints); asynchronous on the handle's stream."""

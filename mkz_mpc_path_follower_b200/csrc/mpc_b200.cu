@@ -9,6 +9,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -127,6 +128,25 @@ mpc_rollout_long_kernel(const KCfg cfg, const RolloutArgs args, unsigned long lo
     }
 }
 
+// Closed loop on the Frenet-frame module (gazebo_sim_mpc_cmd_pub_frenet.jl:112-153): four vehicles per block
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2)
+mpc_rollout_frenet_kernel(const KCfg cfg, const FrenetRolloutArgs args, unsigned long long* counter) {
+    extern __shared__ double smem_all[];
+    const int warp = threadIdx.x >> 5;
+    const smem_t smem = smem_base(smem_all + (size_t)warp * smem_doubles_per_team(cfg.N, 1));
+    const smem_t px = smem_base(smem_all + (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg.N, 1));
+    __shared__ unsigned long long next_group;
+    TeamSolver<1, 1>::init_work(smem, cfg.N);
+    for (;;) {
+        if (threadIdx.x == 0) next_group = atomicAdd(counter, (unsigned long long)WARPS_PER_BLOCK);
+        __syncthreads();
+        const unsigned long long b0 = next_group;
+        __syncthreads();
+        if (b0 >= (unsigned long long)args.B) break;
+        rollout_group_frenet(cfg, args, (long)b0, smem, px, WARPS_PER_BLOCK);
+    }
+}
+
 // FP64 FMA throughput probe: 8 independent chains per thread
 __global__ void fp64_peak_kernel(double* out, int iters) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -164,6 +184,10 @@ struct mpcb200_handle {
     DevBuf d_path[3], d_pose, d_pathof, d_log, d_final, d_stop;
     DevBuf d_rec, d_resto;        /* packed 32-byte records; restoration count per problem of the last solve */
     DevBuf d_seed;                /* the module-load solution (start point of a rollout's first solve), [6N+4] */
+    DevBuf d_fit;                 /* Frenet rollouts: the two least-squares fit matrices [4][n1], [4][n2] */
+    double fit_window = -1.0;     /* ... built for this window length */
+    int fit_n1 = 0, fit_n2 = 0;
+    int frenet_rollout_blocks_per_sm = 0;
     bool seed_valid = false;
     int64_t last_B = 0;           /* batch of the last solve (mpcb200_get_restorations) */
     /* multi-GPU: the handle itself works on devices[0]; sub[i] on devices[i + 1] */
@@ -336,11 +360,12 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
     TRY_OR_FREE(cudaMalloc((void**)&h->d_counter, sizeof(unsigned long long)));
     h->team_warps = team_warps(cfg->N);
     {
-        int roles[32 * ROLE_STRIDE_F];
+        int roles[32 * ROLE_STRIDE_F + 32 * RS_STRIDE];   /* shared-memory version, then the register version (MODEL 0) */
         const int rs = role_stride_of(model);
         for (int l = 0; l < 32; l++) riccati_roles(l, cfg->N, w_sd_of(h->team_warps, model), roles + l * rs, model);
+        for (int l = 0; l < 32; l++) riccati_roles_shfl(l, cfg->N, w_sd_of(h->team_warps, model), roles + 32 * rs + l * RS_STRIDE);
         TRY_OR_FREE(cudaMalloc((void**)&h->d_roles, sizeof(roles)));
-        TRY_OR_FREE(cudaMemcpy(h->d_roles, roles, sizeof(int) * 32 * rs, cudaMemcpyHostToDevice));
+        TRY_OR_FREE(cudaMemcpy(h->d_roles, roles, sizeof(int) * (32 * rs + 32 * RS_STRIDE), cudaMemcpyHostToDevice));
     }
     if (model && h->team_warps > 1) {
         h->smem_bytes = (size_t)smem_doubles_per_team(cfg->N, 1) * sizeof(double);
@@ -363,6 +388,11 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         if (const char* e = getenv("MPCB200_FRENET_WPB")) { int v = atoi(e); if (v == 3 || v == 4) h->frenet_wpb = v; }  /* tuning aid */
         h->blocks_per_sm = (h->frenet_wpb == 3) ? b3 : b4;
         h->smem_bytes = h->frenet_wpb * team;
+        const size_t rb = WARPS_PER_BLOCK * team + WARPS_PER_BLOCK * ROLLOUT_PX * sizeof(double);
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_frenet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb));
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_frenet_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->frenet_rollout_blocks_per_sm, mpc_rollout_frenet_kernel, WARPS_PER_BLOCK * 32, rb));
+        if (h->frenet_rollout_blocks_per_sm < 1) h->frenet_rollout_blocks_per_sm = 1;
     } else if (h->team_warps == 1) {
         h->smem_bytes = ((size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N) + WARPS_PER_BLOCK * ROLLOUT_PX) * sizeof(double);
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -399,7 +429,7 @@ int mpcb200_destroy(mpcb200_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj,
                       &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop, &h->d_stage,
-                      &h->d_rec, &h->d_resto, &h->d_seed};
+                      &h->d_rec, &h->d_resto, &h->d_seed, &h->d_fit};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_roles) cudaFree(h->d_roles);
@@ -954,6 +984,71 @@ int mpcb200_rollout(mpcb200_handle* h, int64_t B, int32_t T, const double* pose0
         if (dev[i]->stats.kernel_ms > h->stats.kernel_ms) h->stats.kernel_ms = dev[i]->stats.kernel_ms;
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
+    return MPCB200_OK;
+}
+
+int mpcb200_rollout_frenet(mpcb200_handle* h, int64_t B, int32_t T, const double* pose0, const int32_t* path_of, double window,
+                           double target_vel, int32_t ey_from_path, double* log, double* final_state) {
+    if (!h) return MPCB200_EINVAL;
+    if (B < 0 || T < 0) return fail(h, MPCB200_EINVAL, "mpcb200_rollout_frenet: B=%lld T=%d", (long long)B, T);
+    if (!h->model) return fail(h, MPCB200_EINVAL, "mpcb200_rollout_frenet: the handle was not created with mpcb200_create_frenet");
+    if (h->team_warps != 1) return fail(h, MPCB200_EINVAL, "mpcb200_rollout_frenet: N <= 31 (N=%d)", h->cfg.N);
+    if (!(window >= 4.0 && window <= 500.0)) return fail(h, MPCB200_EINVAL, "mpcb200_rollout_frenet: window %.3g m outside [4, 500]", window);
+    memset(&h->stats, 0, sizeof(h->stats));
+    if (B == 0 || T == 0) return MPCB200_OK;
+    if (!pose0 || !path_of) return fail(h, MPCB200_EINVAL, "mpcb200_rollout_frenet: pose0 and path_of are required");
+    for (int64_t b = 0; b < B; b++)
+        if (path_of[b] < 0 || path_of[b] > 2 || h->path_n[path_of[b]] == 0)
+            return fail(h, MPCB200_EINVAL, "mpcb200_rollout_frenet: vehicle %lld uses path %d, which was not set with mpcb200_set_path", (long long)b, path_of[b]);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    int rc;
+    if (h->fit_window != window) {   /* grids of nav_msgs_path_frenet.py:63,79: arange(0, window, 0.5) and arange(0, window, 0.25) */
+        const int n1 = (int)ceil(window / 0.5 - 1e-9), n2 = (int)ceil(window / 0.25 - 1e-9);
+        double* P = (double*)malloc(sizeof(double) * 4 * ((size_t)n1 + n2));
+        if (!P) return fail(h, MPCB200_ENOMEM, "mpcb200_rollout_frenet: out of host memory");
+        cubic_fit_matrix(n1, 0.5, P); cubic_fit_matrix(n2, 0.25, P + 4 * (size_t)n1);
+        rc = ensure(h, h->d_fit, sizeof(double) * 4 * ((size_t)n1 + n2));
+        if (!rc) {
+            cudaError_t e = cudaMemcpyAsync(h->d_fit.p, P, sizeof(double) * 4 * ((size_t)n1 + n2), cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) rc = fail(h, MPCB200_ECUDA, "mpcb200_rollout_frenet: %s", cudaGetErrorString(e));
+        }
+        free(P);
+        if (rc) return rc;
+        h->fit_window = window; h->fit_n1 = n1; h->fit_n2 = n2;
+    }
+    const size_t bl = (size_t)T * B * 8 * sizeof(double), bf = (size_t)B * 8 * sizeof(double);
+    if ((rc = ensure(h, h->d_pose, (size_t)B * 3 * sizeof(double)))) return rc;
+    if ((rc = ensure(h, h->d_pathof, (size_t)B * sizeof(int32_t)))) return rc;
+    if (log && (rc = ensure(h, h->d_log, bl))) return rc;
+    if (final_state && (rc = ensure(h, h->d_final, bf))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pose.p, pose0, (size_t)B * 3 * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_pathof.p, path_of, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    h->stats.h2d_bytes += (size_t)B * (3 * sizeof(double) + sizeof(int32_t));
+    FrenetRolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pose0 = (const double*)h->d_pose.p; a.path_of = (const int*)h->d_pathof.p;
+    fill_paths(h, a.paths);
+    a.T = T; a.ey_from_path = ey_from_path; a.target_vel = target_vel;
+    a.log = log ? (double*)h->d_log.p : nullptr; a.final_state = final_state ? (double*)h->d_final.p : nullptr; a.B = (long)B;
+    a.P1 = (const double*)h->d_fit.p; a.P2 = a.P1 + 4 * (size_t)h->fit_n1; a.n1 = h->fit_n1; a.n2 = h->fit_n2;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), s));
+    long long blocks_needed = (B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    long long max_blocks = (long long)h->num_sms * h->frenet_rollout_blocks_per_sm;
+    int grid = (int)(blocks_needed < max_blocks ? blocks_needed : max_blocks);
+    const size_t smem = (size_t)WARPS_PER_BLOCK * smem_doubles_per_team(h->cfg.N, 1) * sizeof(double) + WARPS_PER_BLOCK * ROLLOUT_PX * sizeof(double);
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    mpc_rollout_frenet_kernel<<<grid, WARPS_PER_BLOCK * 32, smem, s>>>(make_kcfg(h), a, h->d_counter);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    h->stats.kernel_launches += 1;
+    if (log) { CUDA_TRY(h, cudaMemcpyAsync(log, h->d_log.p, bl, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bl; }
+    if (final_state) { CUDA_TRY(h, cudaMemcpyAsync(final_state, h->d_final.p, bf, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bf; }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->stats.kernel_ms = ms;
     return MPCB200_OK;
 }
 

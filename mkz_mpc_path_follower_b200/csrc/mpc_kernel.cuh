@@ -442,6 +442,98 @@ MPC_DEV double np_interp(double xq, const double* xp, const double* fp, int n) {
     return add_rn(mul_rn(slope, xq - xp[lo]), fp[lo]);
 }
 
+// ---- lane roles of the REGISTER version of the Riccati backward recursion (MODEL 0): the cost-to-go P (one entry per
+// lane), the products P M and the stage Hessian F never leave registers; operands move between lanes with warp shuffles.
+// Per lane: source lanes of the shuffles of rounds A, B and E (five 5-bit fields per int), shared-memory offsets of the
+// operands that still come from the stage record, and a few flags.
+#define RS_STRIDE 12
+//   [0] A: source lanes of P[i][0..3] and of the extra term, 5 bits each      [1] A: offset of column cc of [A B] in the record
+//   [2] B: source lanes of That[0..3][c2] and of the extra term                [3] B: offset of column c1 of M (record or constant area)
+//   [4] B: 1 if that offset is relative to the current record                  [5] B: offset of the H / g entry in the record
+//   [6] E: source lanes of F[i][a], F[i][df], F[j][a], F[j][df]                [7] flags (RSF_*)
+//   [8], [9] gain addresses of stage N-1 (or the sink)   [10] gain step per stage   [11] pad
+#define RSF_B_OWN 2      // round B: F = H + own P entry (both columns are unit vectors)
+// Lane 31 holds 0 in all three registers at all times (its operands are zeros), so "no extra term" is a shuffle from
+// lane 31; in round B the otherwise idle lanes 27..30 pick up -Ca, -Cd, Ca, Cd from the record, which round E reads for the
+// rows a_prev / df_prev of F8 -- no selects in the loop except RSF_B_OWN.
+#define RS_ZERO_LANE 31
+#define RS_NCA_LANE 27
+#define RS_NCD_LANE 28
+#define RS_CA_LANE 29
+#define RS_CD_LANE 30
+MPC_HD int pair_lane(int i, int j) { if (i > j) { const int t = i; i = j; j = t; } return i * 6 - i * (i - 1) / 2 + (j - i); }
+MPC_HD void riccati_roles_shfl(int l, int N, int W_SD, int* out) {
+    int flags = 0;
+    const int Z = RS_ZERO_LANE;
+    {   // round A: lane (i, cc) -> TT[cc][i] = sum_{j<4} P[i][j] CF[cc][j] + X,  X = 0 | P[i][4] | P[i][5] | p[i]
+        const int i = (l < 24) ? (l >> 2) : (l < 30 ? l - 24 : 0);
+        const int cc = (l < 24) ? (l & 3) : 4;
+        int src = 0, sx = Z;
+        for (int j = 0; j < 4; j++) src |= ((l < 30) ? pair_lane(i, j) : Z) << (5 * j);
+        if (l < 30 && cc == 2) sx = pair_lane(i, 4);
+        if (l < 30 && cc == 3) sx = pair_lane(i, 5);
+        if (l < 30 && cc == 4) sx = 21 + i;
+        out[0] = src | (sx << 20);
+        out[1] = (l < 30) ? SO(W_SD + SD_CF + 4 * cc) : SO(W_Z);
+        out[11] = (l < 30) ? 1 : 0;    // offset relative to the current record
+    }
+    {   // round B: 21 symmetric pairs (c1 <= c2) over (x,y,psi,v,a,df); 6 vector entries; lanes 27..30 stage -Ca, -Cd, Ca, Cd
+        int c1 = 0, c2 = 0, kind = 0;  // 0 pair, 1 vector, 3 other
+        if (l < 21) { int t = l; while (t >= 6 - c1) { t -= 6 - c1; c1++; } c2 = c1 + t; }
+        else if (l < 27) { c1 = l - 21; kind = 1; }
+        else kind = 3;
+        int src = Z | (Z << 5) | (Z << 10) | (Z << 15), sx = Z, mb = SO(W_Z), mk = 0, hf = SD_ZERO;
+        if (kind == 0 && c2 < 2) flags |= RSF_B_OWN;
+        if (kind <= 1) {
+            const int col = (kind == 1) ? 4 : (c2 >= 2 ? c2 - 2 : 0);              // TT column that is That[.][c2]
+            src = 0;
+            for (int r = 0; r < 4; r++) src |= ((col == 4) ? 24 + r : 4 * r + col) << (5 * r);
+            if (c1 >= 4) sx = (col == 4) ? 24 + c1 : 4 * c1 + col;
+            if (c1 < 2) { mb = (c1 == 0) ? SO(W_EX) : SO(W_EY); mk = 0; }
+            else { mb = SO(W_SD + SD_CF + 4 * (c1 - 2)); mk = 1; }
+            if (kind == 1) hf = SD_GX + c1;
+            else if (c1 == c2) hf = (c1 == 0) ? SD_HXX : (c1 == 1) ? SD_HYY : (c1 == 2) ? SD_HPP : (c1 == 3) ? SD_HVV : (c1 == 4) ? SD_HAA : SD_HDD;
+            else if (c1 == 2 && c2 == 3) hf = SD_HPV;
+            else if (c1 == 2 && c2 == 5) hf = SD_HPD;
+            else if (c1 == 3 && c2 == 5) hf = SD_HVD;
+        } else {
+            hf = (l == RS_NCA_LANE) ? SD_NCA : (l == RS_NCD_LANE) ? SD_NCD : (l == RS_CA_LANE) ? SD_CA : (l == RS_CD_LANE) ? SD_CD : SD_ZERO;
+        }
+        out[2] = src | (sx << 20); out[3] = mb; out[4] = mk; out[5] = SO(W_SD + hf);
+    }
+    {   // round E: 21 symmetric pairs (i <= j) over xi = (x,y,psi,v,a_prev,df_prev), then 6 vector entries
+        int i = 0, j = 0, vec = 0, act = 1;
+        if (l < 21) { int t = l; while (t >= 6 - i) { t -= 6 - i; i++; } j = i + t; }
+        else if (l < 27) { i = l - 21; vec = 1; }
+        else act = 0;
+        // (F8[q][a], F8[q][df]) for q over xi; q = 6: (f_a, f_df)
+        int six = Z, siy = Z, sjx = Z, sjy = Z, sf0 = Z;
+        if (act) {
+            if (i < 4) { six = pair_lane(i, 4); siy = pair_lane(i, 5); }
+            else if (i == 4) six = RS_NCA_LANE;
+            else siy = RS_NCD_LANE;
+            const int q = vec ? 6 : j;
+            if (q < 4) { sjx = pair_lane(q, 4); sjy = pair_lane(q, 5); }
+            else if (q == 4) sjx = RS_NCA_LANE;
+            else if (q == 5) sjy = RS_NCD_LANE;
+            else { sjx = 21 + 4; sjy = 21 + 5; }
+            if (vec) sf0 = (i < 4) ? l : Z;
+            else if (i < 4 && j < 4) sf0 = l;
+            else if (i == 4 && j == 4) sf0 = RS_CA_LANE;
+            else if (i == 5 && j == 5) sf0 = RS_CD_LANE;
+        }
+        out[6] = six | (siy << 5) | (sjx << 10) | (sjy << 15) | (sf0 << 20);
+        int ks = -1;   // gain storage: the diagonal pairs (j,j) hold K[.][j], vector lane i = 0 holds K[.][6]
+        if (act && !vec && i == j) ks = j;
+        if (act && vec && i == 0) ks = 6;
+        const int kb = SO(W_SD + (N + 1) * SDS + (N - 1) * KST_STRIDE);  // gains of stage N-1
+        out[8] = (ks >= 0 ? kb + SO(ks) : SO(W_DUMMY));
+        out[9] = (ks >= 0 ? kb + SO(7 + ks) : SO(W_DUMMY));
+        out[10] = (ks >= 0) ? SO(KST_STRIDE) : 0;
+    }
+    out[7] = flags;
+}
+
 // W = warps per team (1: a warp per problem; 2, 3: a block per problem)
 // MODEL 0: XY kinematic bicycle (MKZMPCPathFollower.jl); MODEL 1: Frenet-frame variant (MKZMPCPathFollowerFrenet.jl)
 template <int W, int MODEL = 0>
@@ -972,7 +1064,77 @@ struct TeamSolver {
         block_sync();
         return lds(sm, a) != 0.0;
     }
+#ifndef MPC_RICCATI_SMEM
+    // Register version (MODEL 0): lane = one entry of P (21 symmetric pairs + 6 gradient entries), of P M (30 entries)
+    // and of F (21 + 6); the three rounds of a stage hand their operands over with warp shuffles instead of a
+    // store -> bar.warp.sync -> load round trip through shared memory.  Same arithmetic, term for term, as the
+    // shared-memory version below (which MODEL 1 keeps).
+    MPC_DEV bool riccati_backward_regs() {
+        const int l = lane_id();
+        int rl[RS_STRIDE];
+        ld_roles(c.roles + 32 * role_stride_of(MODEL) + l * RS_STRIDE, rl, RS_STRIDE);
+        const int a_src = launder(rl[0]), a_m = launder(rl[1]), a_mk = launder(rl[11]);
+        const int b_src = launder(rl[2]), b_m = launder(rl[3]), b_mk = launder(rl[4]), b_h = launder(rl[5]);
+        const int e_src = launder(rl[6]);
+        const bool b_own = (launder(rl[7]) & RSF_B_OWN) != 0;
+        int e_k0 = launder(rl[8]), e_k1 = launder(rl[9]);
+        const int kstep = launder(rl[10]);
+        double Pv;   // this lane's entry of the cost-to-go: P[i][j] (lanes 0..20), p[i] (21..26), 0 (27..31)
+        {   // terminal cost-to-go from record N
+            const int rN = SO(W_SD + N * SDSZ);
+            int hf = SD_ZERO;
+            if (l == 0) hf = SD_HXX; else if (l == 6) hf = SD_HYY; else if (l == 11) hf = SD_HPP; else if (l == 15) hf = SD_HVV;
+            else if (l >= 21 && l < 25) hf = SD_GX + (l - 21);
+            Pv = lds(sm, rN + SO(hf));
+        }
+        bool ok = true;
+        int so = SO((N - 1) * SDSZ);   // byte offset of the current stage's record relative to record 0
+        for (int s = N - 1; s >= 0; s--) {
+            // operands from the stage record: independent of the recursion, so their loads are issued first
+            const int ma = a_m + a_mk * so;
+            const d2 am0 = lds2(sm, ma), am1 = lds2(sm, ma + SO(2));
+            const int mb = b_m + b_mk * so;
+            const d2 bm0 = lds2(sm, mb), bm1 = lds2(sm, mb + SO(2));
+            const double h = lds(sm, b_h + so);
+            double Tv;
+            {   // ---- Round A
+                const double p0 = shfl(Pv, a_src), p1 = shfl(Pv, a_src >> 5), p2 = shfl(Pv, a_src >> 10),
+                             p3 = shfl(Pv, a_src >> 15), ex = shfl(Pv, a_src >> 20);
+                const double t0 = p0 * am0.x + p1 * am0.y;
+                const double t1 = p2 * am1.x + p3 * am1.y + ex;
+                Tv = t0 + t1;
+            }
+            double Fv;
+            {   // ---- Round B
+                const double q0 = shfl(Tv, b_src), q1 = shfl(Tv, b_src >> 5), q2 = shfl(Tv, b_src >> 10),
+                             q3 = shfl(Tv, b_src >> 15), x = shfl(Tv, b_src >> 20);
+                const double t0 = bm0.x * q0 + bm0.y * q1 + x;
+                const double t1 = bm1.x * q2 + bm1.y * q3 + h;
+                Fv = b_own ? Pv + h : t0 + t1;
+            }
+            {   // ---- Round E (with the 2x2 inverse computed by every lane)
+                const double faa = shfl(Fv, 18), fad = shfl(Fv, 19), fdd = shfl(Fv, 20);
+                const double fjx = shfl(Fv, e_src >> 10), fjy = shfl(Fv, e_src >> 15);
+                const double fix = shfl(Fv, e_src), fiy = shfl(Fv, e_src >> 5);
+                const double f0 = shfl(Fv, e_src >> 20);
+                const double det = faa * fdd - fad * fad;
+                if (!(faa > 0.0) || !(det > 1e-300)) { ok = false; break; }   // (also keeps fast_rcp away from denormals)
+                const double idet = fast_rcp(det);
+                const double a0 = fdd * fjx - fad * fjy, a1 = faa * fjy - fad * fjx;   // adj(Fuu) (F8[j][a], F8[j][df])
+                const double num = fix * a0 + fiy * a1;
+                sts(sm, e_k0, -a0 * idet); sts(sm, e_k1, -a1 * idet);
+                Pv = f0 - num * idet;
+            }
+            so -= SO(SDSZ); e_k0 -= kstep; e_k1 -= kstep;
+        }
+        syncwarp();   // the gains are read by other lanes (forward sweep)
+        return ok;
+    }
+#endif
     MPC_DEV bool riccati_backward_warp() {
+#ifndef MPC_RICCATI_SMEM
+        if (MODEL == 0) return riccati_backward_regs();
+#endif
         const int l = lane_id();
         // lane roles: shared-memory offsets of this lane's operands in the three rounds, read from the
         // table mpcb200_create computed once (riccati_roles) and laundered so that they stay in
@@ -1063,30 +1225,44 @@ struct TeamSolver {
             const d2 i01 = lds2(sm, SO(W_SD + N * SDSZ + SD_R)), i23 = lds2(sm, SO(W_SD + N * SDSZ + SD_R + 2));  // ds_0
             double s0 = i01.x, s1 = i01.y, s2 = i23.x, s3 = i23.y;
             double pa = 0.0, pd = 0.0;
+            // The recursion is one dependent chain per problem (s -> u -> next s).  The gains of a stage are what the
+            // chain needs first, so they are loaded one stage ahead (while the previous stage's next-state sums run);
+            // the record columns are needed only after the inputs, so their loads, issued at the top, are covered by
+            // the input sums.
+            d2 ka0 = lds2(sm, kp), ka1 = lds2(sm, kp + SO(2)), ka2 = lds2(sm, kp + SO(4)), kx = lds2(sm, kp + SO(6));
+            d2 kd0 = lds2(sm, kp + SO(8)), kd1 = lds2(sm, kp + SO(10)), kd2 = lds2(sm, kp + SO(12));
+            const int kp_last = kp + (N - 1) * SO(KST_STRIDE);
             for (int s = 0; s < N; s++) {
-                const d2 ka0 = lds2(sm, kp), ka1 = lds2(sm, kp + SO(2)), ka2 = lds2(sm, kp + SO(4)), kx = lds2(sm, kp + SO(6));
-                const d2 kd0 = lds2(sm, kp + SO(8)), kd1 = lds2(sm, kp + SO(10)), kd2 = lds2(sm, kp + SO(12));
                 const d2 cp = lds2(sm, r + SO(SD_CF + 0)), cv = lds2(sm, r + SO(SD_CF + 4)), cd = lds2(sm, r + SO(SD_CF + 12));
                 const double a23 = lds(sm, r + SO(SD_CF + 6)), b2 = lds(sm, r + SO(SD_CF + 14));
                 const d2 r01 = lds2(sm, r + SO(SD_R)), r23 = lds2(sm, r + SO(SD_R + 2));
-                // the recursion is one dependent chain per problem: the terms that do not need the values
-                // produced last (s0..s3 for the inputs, the inputs for the next state) are summed first
+                double a00 = 0.0, a20 = 0.0, a01 = 0.0, a21 = 0.0, a22 = 0.0;
+                if (MODEL) {   // dense s and e_y columns; the unit parts are in the record
+                    a00 = lds(sm, r + SO(SD_CS)); a20 = lds(sm, r + SO(SD_CS + 2));
+                    a01 = lds(sm, r + SO(SD_CE)); a21 = lds(sm, r + SO(SD_CE + 2)); a22 = lds(sm, r + SO(SD_CF + 2));
+                }
+                // the terms that do not need the values produced last (s0..s3 for the inputs, the inputs for the next
+                // state) are summed first
                 const double ua = ((ka2.x * pa + ka2.y * pd) + kx.x) + ((ka0.x * s0 + ka0.y * s1) + (ka1.x * s2 + ka1.y * s3));
                 const double ud = ((kd1.y * pa + kd2.x * pd) + kd2.y) + ((kx.y * s0 + kd0.x * s1) + (kd0.y * s2 + kd1.x * s3));
                 sts2(sm, fa, s0, s1); sts2(sm, fa + SO(2), s2, s3); sts2(sm, fa + SO(4), ua, ud);
+                kp += SO(KST_STRIDE);
+                {   // gains of the next stage (the last stage re-reads its own: no access past the gain area)
+                    const int kn = (kp <= kp_last) ? kp : kp_last;
+                    ka0 = lds2(sm, kn); ka1 = lds2(sm, kn + SO(2)); ka2 = lds2(sm, kn + SO(4)); kx = lds2(sm, kn + SO(6));
+                    kd0 = lds2(sm, kn + SO(8)); kd1 = lds2(sm, kn + SO(10)); kd2 = lds2(sm, kn + SO(12));
+                }
                 double n0 = ((s0 + r01.x) + (cp.x * s2 + cv.x * s3)) + cd.x * ud;
                 double n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
                 double n2 = ((s2 + r23.x) + a23 * s3) + b2 * ud;
                 const double n3 = (s3 + r23.y) + c.dt * ua;
-                if (MODEL) {   // dense s and e_y columns; the unit parts are in the record
-                    const double a00 = lds(sm, r + SO(SD_CS)), a20 = lds(sm, r + SO(SD_CS + 2));
-                    const double a01 = lds(sm, r + SO(SD_CE)), a21 = lds(sm, r + SO(SD_CE + 2)), a22 = lds(sm, r + SO(SD_CF + 2));
+                if (MODEL) {
                     n0 = (r01.x + (a00 * s0 + a01 * s1)) + ((cp.x * s2 + cv.x * s3) + cd.x * ud);
                     n1 = ((s1 + r01.y) + (cp.y * s2 + cv.y * s3)) + cd.y * ud;
                     n2 = (r23.x + (a20 * s0 + a21 * s1)) + ((a22 * s2 + a23 * s3) + b2 * ud);
                 }
                 s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
-                kp += SO(KST_STRIDE); r += SO(SDSZ); fa += SO(G_DX_STRIDE);
+                r += SO(SDSZ); fa += SO(G_DX_STRIDE);
             }
             sts2(sm, fa, s0, s1); sts2(sm, fa + SO(2), s2, s3); sts2(sm, fa + SO(4), 0.0, 0.0);
         }
@@ -1989,6 +2165,142 @@ MPC_DEV void rollout_group(const KCfg& cfg, const RolloutArgs& a, long b0, smem_
         } else { acc_des = -1.0; df_des = 0.0; }                     // :148-153
         if (a.log && k < 8) {
             const double lv[8] = {st[0], st[1], st[2], st[3], acc_des, df_des, (double)status, (double)iters};
+            a.log[((long)t * a.B + b) * 8 + k] = sel8(lv, k);
+        }
+    }
+    if (valid && a.final_state && k < 8) a.final_state[b * 8 + k] = sel8(st, k);
+    block_sync();
+}
+
+
+// ======================================================================================
+// Closed loop on the Frenet-frame module, everything on the device: one warp = one vehicle.
+//   control step       scripts/nodes_gazebo_sim/gazebo_sim_mpc_cmd_pub_frenet.jl:112-153 (state (0, e_y, -psi_start, v),
+//                      K_coeffs from the path ahead, warm-started solve, command fed back)
+//   curvature fit      scripts/sim_path_utils/nav_msgs_path_frenet.py:44-86: cubics X(s), Y(s) fitted to the path ahead
+//                      resampled every 0.5 m (:60-72), curvature of those cubics every 0.25 m fitted by a cubic (:44-58),
+//                      psi_start = atan2(Y'(0), X'(0)) (:84).  Both least-squares fits are on FIXED grids, so each is one
+//                      fixed 4 x n matrix (the pseudo-inverse of the Vandermonde matrix, built once by the host) times the
+//                      samples: lanes stride the samples, the 4 + 4 + 4 partial sums are reduced over the warp.
+//   path ahead         the next `window` metres of the recorded path from the sample nearest to the vehicle, seen from the
+//                      vehicle (what the node receives as `target_path`, :90-119), as closed_loop.run_frenet builds it
+//   plant              scripts/vehicle_simulator.py:58-112 (Gazebo, which drives that node in the reference, is out of scope)
+// ======================================================================================
+struct FrenetRolloutArgs {
+    const double* pose0;    // [B][3] X0, Y0, Psi0
+    const int* path_of;     // [B]
+    PathTable paths[3];
+    int T, ey_from_path;
+    double target_vel;
+    double* log;            // [T][B][8] or null: x, y, psi, v, acc_cmd, df_cmd, status, iters
+    double* final_state;    // [B][8] or null
+    long B;
+    const double* P1;       // [4][n1] least-squares cubic fit on the grid 0, 0.5, ... (n1 samples)
+    const double* P2;       // [4][n2] ... on the grid 0, 0.25, ... (n2 samples)
+    int n1, n2;
+};
+
+// host side: the fit matrices of FrenetRolloutArgs
+// Least-squares cubic fit on the fixed grid x_g = g * step, g < n, as a 4 x n matrix P (coefficients, highest degree first,
+// = P * samples): P = (V'V)^-1 V' with the Vandermonde columns scaled to unit norm, normal equations in long double.
+inline void cubic_fit_matrix(int n, double step, double* P) {
+    long double scale[4], G[4][4], Ginv[4][8];
+    for (int c = 0; c < 4; c++) {
+        long double ss = 0;
+        for (int g = 0; g < n; g++) { const long double x = (long double)step * g; long double v = 1; for (int e = 0; e < 3 - c; e++) v *= x; ss += v * v; }
+        scale[c] = sqrtl(ss);
+    }
+    auto V = [&](int g, int c) { const long double x = (long double)step * g; long double v = 1; for (int e = 0; e < 3 - c; e++) v *= x; return v / scale[c]; };
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { long double t = 0; for (int g = 0; g < n; g++) t += V(g, a) * V(g, b); G[a][b] = t; }
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 8; b++) Ginv[a][b] = (b < 4) ? G[a][b] : (b - 4 == a ? 1.0L : 0.0L);
+    for (int c = 0; c < 4; c++) {   /* Gauss-Jordan with partial pivoting on a 4 x 4 SPD matrix */
+        int piv = c;
+        for (int r = c + 1; r < 4; r++) if (fabsl(Ginv[r][c]) > fabsl(Ginv[piv][c])) piv = r;
+        if (piv != c) for (int b = 0; b < 8; b++) { const long double t = Ginv[c][b]; Ginv[c][b] = Ginv[piv][b]; Ginv[piv][b] = t; }
+        const long double d = Ginv[c][c];
+        for (int b = 0; b < 8; b++) Ginv[c][b] /= d;
+        for (int r = 0; r < 4; r++) if (r != c) { const long double f = Ginv[r][c]; for (int b = 0; b < 8; b++) Ginv[r][b] -= f * Ginv[c][b]; }
+    }
+    for (int a = 0; a < 4; a++)
+        for (int g = 0; g < n; g++) { long double t = 0; for (int b = 0; b < 4; b++) t += Ginv[a][4 + b] * V(g, b); P[(size_t)a * n + g] = (double)(t / scale[a]); }
+}
+
+
+MPC_DEV void rollout_group_frenet(const KCfg& cfg, const FrenetRolloutArgs& a, long b0, smem_t smem, smem_t px, int nwarps) {
+    TeamSolver<1, 1> S(cfg, smem);
+    const int k = S.k, N = cfg.N;
+    const int w = thread_in_block() >> 5;
+    const long b = b0 + w;
+    const bool valid = b < a.B;
+    const int pxw = SO(w * ROLLOUT_PX);
+    const PathTable& path = a.paths[valid ? a.path_of[b] : 0];
+    if (k < 8) sts(px, pxw + SO(k), (valid && k < 3) ? a.pose0[3 * b + k] : 0.0);
+    double st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double acc_des = 0.0, df_des = 0.0, up_d = 0.0, up_a = 0.0;
+    S.L.sx = S.L.sy = S.L.sp = S.L.sv = S.L.ua = S.L.ud = 0.0;   // start = 0.0, then the previous solution
+    for (int t = 0; t < a.T; t++) {
+        if (k == 0) { sts(px, pxw + SO(8), acc_des); sts(px, pxw + SO(9), df_des); }
+        block_sync();
+        if (thread_in_block() < nwarps) {   // lane = vehicle: ten 100 Hz publishes of ten Euler sub-steps each
+            const int pv = SO(thread_in_block() * ROLLOUT_PX);
+            double ps[8];
+            for (int i = 0; i < 8; i++) ps[i] = lds(px, pv + SO(i));
+            const double ad = lds(px, pv + SO(8)), dd = lds(px, pv + SO(9));
+            MPC_NOUNROLL for (int i = 0; i < 10; i++) plant_step(ps, ad, dd);
+            for (int i = 0; i < 8; i++) sts(px, pv + SO(i), ps[i]);
+        }
+        block_sync();
+        if (!valid) continue;
+        for (int i = 0; i < 8; i++) st[i] = lds(px, pxw + SO(i));
+        // ---- the path ahead: nearest sample, then the window resampled every 0.5 m in the vehicle frame
+        double bd = 1e300; int bi = 0x7fffffff;
+        for (int i = k; i < path.n; i += 32) {
+            const double dx = path.X[i] - st[0], dy = path.Y[i] - st[1], d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+            if (d < bd) { bd = d; bi = i; }
+        }
+        S.targmin(bd, bi);
+        const double s_i = path.s[bi];
+        double sps, cps;
+        mpc_sincos(st[2], &sps, &cps);
+        double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xw0 = 0.0, yw0 = 0.0;
+        for (int g = k; g < a.n1; g += 32) {
+            const double sq = s_i + 0.5 * (double)g;
+            const double dx = np_interp(sq, path.s, path.X, path.n) - st[0], dy = np_interp(sq, path.s, path.Y, path.n) - st[1];
+            const double xw = cps * dx + sps * dy, yw = -sps * dx + cps * dy;
+            if (g == 0) { xw0 = xw; yw0 = yw; }
+            for (int r = 0; r < 4; r++) { const double pr = a.P1[r * a.n1 + g]; acc8[r] += pr * xw; acc8[4 + r] += pr * yw; }
+        }
+        S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8); S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8 + 3);
+        S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(acc8 + 6);
+        xw0 = shfl(xw0, 0); yw0 = shfl(yw0, 0);
+        const double* xc = acc8; const double* yc = acc8 + 4;   // cubic coefficients, highest degree first
+        // ---- curvature of the fitted cubics every 0.25 m, fitted by a cubic
+        double kc[4] = {0, 0, 0, 0};
+        for (int g = k; g < a.n2; g += 32) {
+            const double tt = 0.25 * (double)g;
+            const double dx = xc[2] + 2.0 * xc[1] * tt + 3.0 * xc[0] * (tt * tt), dy = yc[2] + 2.0 * yc[1] * tt + 3.0 * yc[0] * (tt * tt);
+            const double ddx = 2.0 * xc[1] + 6.0 * xc[0] * tt, ddy = 2.0 * yc[1] + 6.0 * yc[0] * tt;
+            const double Km = (dx * ddy - dy * ddx) / (dx * dx + dy * dy);
+            for (int r = 0; r < 4; r++) kc[r] += a.P2[r * a.n2 + g] * Km;
+        }
+        S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc); S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc + 2);
+        const double psi0 = atan2(yc[2], xc[2]);
+        double sp0, cp0;
+        mpc_sincos(psi0, &sp0, &cp0);
+        const double ey = a.ey_from_path ? -(-sp0 * xw0 + cp0 * yw0) : 0.0;
+        // ---- update_init_cond(0, e_y, -psi_start, v), update_reference(path, K_coeffs, des_speed), solve_model (:125-130)
+        S.set_kpoly(kc[0], kc[1], kc[2], kc[3]);
+        syncwarp();
+        {
+            const double cv[8] = {0.0, ey, -psi0, st[3], up_d, up_a, a.target_vel, 0.0};
+            if (k < 8) sts(smem, SO(W_CONST + k), sel8(cv, k));
+        }
+        syncwarp();
+        const Result r = S.solve();
+        acc_des = shfl(S.L.ua, 0); df_des = shfl(S.L.ud, 0);   // published whatever the status (:139-143)
+        up_d = df_des; up_a = acc_des;                           // update_current_input(df_opt, a_opt) (:145)
+        if (a.log && k < 8) {
+            const double lv[8] = {st[0], st[1], st[2], st[3], acc_des, df_des, (double)r.status, (double)r.iters};
             a.log[((long)t * a.B + b) * 8 + k] = sel8(lv, k);
         }
     }

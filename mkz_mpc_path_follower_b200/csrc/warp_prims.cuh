@@ -21,7 +21,10 @@ MPC_DEV int lane_id() { return threadIdx.x & 31; }
 MPC_DEV int thread_in_block() { return threadIdx.x; }
 MPC_DEV void block_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 MPC_DEV bool block_all(bool p) { return __syncthreads_and(p ? 1 : 0) != 0; }
-MPC_DEV double shfl(double v, int src) { return __shfl_sync(MPC_FULL, v, src); }
+MPC_DEV double shfl(double v, int src) {   // src is taken modulo 32 by the hardware
+    const int lo = __shfl_sync(MPC_FULL, __double2loint(v), src), hi = __shfl_sync(MPC_FULL, __double2hiint(v), src);
+    return __hiloint2double(hi, lo);
+}
 MPC_DEV int shfl(int v, int src) { return __shfl_sync(MPC_FULL, v, src); }
 MPC_DEV double shfl_down(double v, int d) { return __shfl_down_sync(MPC_FULL, v, d); }
 MPC_DEV double shfl_up(double v, int d) { return __shfl_up_sync(MPC_FULL, v, d); }

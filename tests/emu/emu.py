@@ -130,3 +130,20 @@ def solve_batch_on_path(kcfg, traj_table, state, u_prev, track_using_time=True, 
                                 u_prev.ctypes.data_as(dp), u0.ctypes.data_as(dp), cost.ctypes.data_as(dp), status.ctypes.data_as(ip),
                                 iters.ctypes.data_as(ip), traj.ctypes.data_as(dp), ref.ctypes.data_as(dp), stop.ctypes.data_as(ip))
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj, "ref": ref, "stop": stop}
+
+
+def rollout_frenet(kcfg, traj_table, pose0, T, window=40.0, target_vel=8.0, ey_from_path=True):
+    """mpcb200_rollout_frenet on the emulator: all vehicles on the path whose (n,7) table is given.  Returns log (T,B,8), final (B,8)."""
+    lib = C.CDLL(build())
+    dp = C.POINTER(C.c_double)
+    pose0 = np.ascontiguousarray(np.atleast_2d(pose0), dtype=np.float64)
+    B = pose0.shape[0]
+    cols = [np.ascontiguousarray(traj_table[:, i]) for i in (0, 4, 5, 3, 6)]
+    path_of = np.zeros(B, dtype=np.int32)
+    log = np.zeros((T, B, 8)); final = np.zeros((B, 8))
+    lib.emu_rollout_frenet.argtypes = [C.POINTER(KCfg), C.c_long, C.c_int, dp, C.POINTER(C.c_int), C.c_int, dp, dp, dp, dp, dp,
+                                       C.c_double, C.c_double, C.c_int, dp, dp]
+    lib.emu_rollout_frenet(C.byref(kcfg), B, T, pose0.ctypes.data_as(dp), path_of.ctypes.data_as(C.POINTER(C.c_int)), traj_table.shape[0],
+                           *[c.ctypes.data_as(dp) for c in cols], float(window), float(target_vel), int(bool(ey_from_path)),
+                           log.ctypes.data_as(dp), final.ctypes.data_as(dp))
+    return log, final

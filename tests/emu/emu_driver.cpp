@@ -71,8 +71,9 @@ extern "C" int emu_solve_batch(const KCfg* cfg, long B, const double* state, con
     BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj, nullptr, nullptr};
     KCfg kc = *cfg;
     kcfg_finalize(kc);
-    std::vector<int> roles(32 * ROLE_STRIDE);
+    std::vector<int> roles(32 * ROLE_STRIDE + 32 * RS_STRIDE);
     for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, W_SD_OF(team_warps(kc.N)), roles.data() + l * ROLE_STRIDE);
+    for (int l = 0; l < 32; l++) riccati_roles_shfl(l, kc.N, W_SD_OF(team_warps(kc.N)), roles.data() + 32 * ROLE_STRIDE + l * RS_STRIDE);
     kc.roles = roles.data();
     std::vector<double> smem_raw(smem_doubles_per_team(kc.N) + 2, 0.0);
     double* smem = smem_raw.data();
@@ -137,8 +138,9 @@ extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, 
     KCfg kc = *cfg;
     kcfg_finalize(kc);
     const int W = team_warps(kc.N);
-    std::vector<int> roles(32 * ROLE_STRIDE);
+    std::vector<int> roles(32 * ROLE_STRIDE + 32 * RS_STRIDE);
     for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, W_SD_OF(W), roles.data() + l * ROLE_STRIDE);
+    for (int l = 0; l < 32; l++) riccati_roles_shfl(l, kc.N, W_SD_OF(W), roles.data() + 32 * ROLE_STRIDE + l * RS_STRIDE);
     kc.roles = roles.data();
     RolloutArgs a;
     memset(&a, 0, sizeof(a));
@@ -182,8 +184,9 @@ extern "C" int emu_solve_batch_on_path(const KCfg* cfg, long B, const double* st
     KCfg kc = *cfg;
     kcfg_finalize(kc);
     const int W = team_warps(kc.N);
-    std::vector<int> roles(32 * ROLE_STRIDE);
+    std::vector<int> roles(32 * ROLE_STRIDE + 32 * RS_STRIDE);
     for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, W_SD_OF(W), roles.data() + l * ROLE_STRIDE);
+    for (int l = 0; l < 32; l++) riccati_roles_shfl(l, kc.N, W_SD_OF(W), roles.data() + 32 * ROLE_STRIDE + l * RS_STRIDE);
     kc.roles = roles.data();
     BatchPtrs io{state, nullptr, nullptr, u_prev, nullptr, u0, cost, status, iters, traj, nullptr, nullptr};
     RefGen rg;
@@ -199,6 +202,44 @@ extern "C" int emu_solve_batch_on_path(const KCfg* cfg, long B, const double* st
         emu::race_reset();
         register_benign(smem, kc.N);
         emu::run_warp(W == 1 ? lane_on_path<1> : W == 2 ? lane_on_path<2> : lane_on_path<3>, &j, W);
+    }
+    return 0;
+}
+
+// closed loop on the Frenet-frame module (rollout_group_frenet): one emulated block of four warps = four vehicles
+struct FJob { const KCfg* cfg; const FrenetRolloutArgs* a; long b0; double* smem; int per_team; };
+static void lane_rollout_frenet(int lane, void* p) {
+    FJob* j = (FJob*)p;
+    double* team = j->smem + (size_t)(lane >> 5) * j->per_team;
+    TeamSolver<1, 1>::init_work(team, j->cfg->N);
+    rollout_group_frenet(*j->cfg, *j->a, j->b0, team, j->smem + (size_t)4 * j->per_team, 4);
+}
+extern "C" int emu_rollout_frenet(const KCfg* cfg, long B, int T, const double* pose0, const int* path_of, int n0, const double* t,
+                                  const double* X, const double* Y, const double* psi, const double* s, double window,
+                                  double target_vel, int ey_from_path, double* log, double* final_state) {
+    KCfg kc = *cfg;
+    kcfg_finalize(kc);
+    std::vector<int> roles(32 * ROLE_STRIDE_F);
+    for (int l = 0; l < 32; l++) riccati_roles(l, kc.N, w_sd_of(1, 1), roles.data() + l * ROLE_STRIDE_F, 1);
+    kc.roles = roles.data();
+    const int n1 = (int)ceil(window / 0.5 - 1e-9), n2 = (int)ceil(window / 0.25 - 1e-9);
+    std::vector<double> P(4 * (size_t)(n1 + n2));
+    cubic_fit_matrix(n1, 0.5, P.data()); cubic_fit_matrix(n2, 0.25, P.data() + 4 * (size_t)n1);
+    FrenetRolloutArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pose0 = pose0; a.path_of = path_of;
+    for (int i = 0; i < 3; i++) { a.paths[i].n = n0; a.paths[i].t = t; a.paths[i].X = X; a.paths[i].Y = Y; a.paths[i].psi = psi; a.paths[i].s = s; }
+    a.T = T; a.ey_from_path = ey_from_path; a.target_vel = target_vel; a.log = log; a.final_state = final_state; a.B = B;
+    a.P1 = P.data(); a.P2 = P.data() + 4 * (size_t)n1; a.n1 = n1; a.n2 = n2;
+    const int per_team = smem_doubles_per_team(kc.N, 1);
+    std::vector<double> smem_raw((size_t)4 * per_team + 4 * ROLLOUT_PX + 2, 0.0);
+    double* smem = smem_raw.data();
+    if (((size_t)smem) & 15) smem++;
+    for (long b0 = 0; b0 < B; b0 += 4) {
+        FJob j{&kc, &a, b0, smem, per_team};
+        emu::race_reset();
+        for (int w = 0; w < 4; w++) register_benign(smem + (size_t)w * per_team, kc.N, 1);
+        emu::run_warp(lane_rollout_frenet, &j, 4);
     }
     return 0;
 }

@@ -705,6 +705,40 @@ def test_frenet_closed_loop_holds_the_path(capi):
     assert np.abs(log[:, :, 4]).max() <= 1.0 + 1e-9 and np.abs(log[:, :, 5]).max() <= 0.5 + 1e-9
 
 
+def test_frenet_device_rollout_matches_host_loop(capi):
+    """mpcb200_rollout_frenet (path ahead, curvature fit, warm-started Frenet solves and the plant in one persistent
+    kernel) against closed_loop.run_frenet, which runs the same control step on the host around the same library."""
+    from mkz_mpc_path_follower_b200 import closed_loop
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    N, T = 8, 40
+    s = capi.FrenetSolver(N)
+    trajs = [GPSRefTrajectory(mat_filename=p) for p in (1, 2, 3)]
+    for i, g in enumerate(trajs):
+        s.set_path(i, g.trajectory)
+    rng = np.random.default_rng(12)
+    path_ids, poses = [], []
+    for p in (1, 2, 3):
+        g = trajs[p - 1]
+        for j in (200, 2600):
+            nrm = np.array([-np.sin(g.trajectory[j, 3]), np.cos(g.trajectory[j, 3])])
+            xy = g.trajectory[j, 4:6] + 0.7 * nrm
+            poses.append((xy[0], xy[1], g.trajectory[j, 3] + rng.normal(scale=0.05))); path_ids.append(p)
+    poses = np.array(poses); path_ids = np.array(path_ids)
+    out = s.rollout(poses, (path_ids - 1).astype(np.int32), T, window=40.0, target_vel=8.0)
+    assert s.stats()["kernel_launches"] == 1
+    ref = closed_loop.run_frenet(path_ids, poses, T, N=N, window=40.0, target_vel=8.0)
+    assert np.array_equal(out["log"][:, :, 6], ref["log"][:, :, 6]) and (out["log"][:, :, 6] == 0).all()
+    assert np.abs(out["log"][:, :, 4:6] - ref["log"][:, :, 4:6]).max() <= 1e-5
+    assert np.abs(out["log"][:, :, 0:4] - ref["log"][:, :, 0:4]).max() <= 1e-4
+    for p in (1, 2, 3):
+        err = closed_loop.path_errors(out["log"][-10:, path_ids == p, :], trajs[p - 1].trajectory)
+        assert err.max() < 0.3          # started 0.7 m beside the path
+    with pytest.raises(capi.MpcB200Error):
+        capi.FrenetSolver(N).rollout(poses[:1], np.zeros(1, dtype=np.int32), 2)     # path not set
+    with pytest.raises(capi.MpcB200Error):
+        s.rollout(poses[:1], np.zeros(1, dtype=np.int32), 2, window=1.0)            # window too short for a cubic fit
+
+
 @pytest.mark.parametrize("N,B", [(8, 48), (20, 32), (40, 8)])
 def test_frenet_kkt_of_cuda_solutions(capi, oracle, N, B):
     """KKT conditions of the unscaled Frenet NLP at the CUDA solver's returned points (stress curvature), checked
