@@ -190,6 +190,8 @@ struct mpcb200_handle {
     int frenet_rollout_blocks_per_sm = 0;
     bool seed_valid = false;
     int64_t last_B = 0;           /* batch of the last solve (mpcb200_get_restorations) */
+    int32_t small_resto[64];      /* ... its restoration counts when it went through the small-batch path */
+    bool resto_on_host = false;
     /* multi-GPU: the handle itself works on devices[0]; sub[i] on devices[i + 1] */
     int n_sub = 0;
     mpcb200_handle* sub[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -621,10 +623,8 @@ static int solve_small_host(mpcb200_handle* h, int64_t B, const SolveArgs& a) {
     if (a.traj) memcpy(a.traj, hs + o_traj, nt * B * sizeof(double));
     if (a.warm) memcpy(a.warm, hs + o_warm, nt * B * sizeof(double));
     if (a.rec) memcpy(a.rec, hs + o_rec, 4 * B * sizeof(double));
-    /* keep the restoration counts where mpcb200_get_restorations looks for them */
-    if ((rc = ensure(h, h->d_resto, B * sizeof(int32_t)))) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_resto.p, hs + o_resto, B * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaStreamSynchronize(s));
+    memcpy(h->small_resto, hs + o_resto, B * sizeof(int32_t));   /* where mpcb200_get_restorations looks after a small batch */
+    h->resto_on_host = true;
     float ms = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->stats.kernel_ms = ms;
@@ -717,7 +717,7 @@ static int solve_batch_impl(mpcb200_handle* h, int64_t B, const SolveArgs& a, in
     if (B < 0) return fail(h, MPCB200_EINVAL, "%s: B=%lld", who, (long long)B);
     if (mem_space != MPCB200_HOST && mem_space != MPCB200_DEVICE) return fail(h, MPCB200_EINVAL, "%s: mem_space=%d", who, mem_space);
     memset(&h->stats, 0, sizeof(h->stats));
-    h->last_B = B; h->last_sharded = false;
+    h->last_B = B; h->last_sharded = false; h->resto_on_host = false;
     if (B == 0) return MPCB200_OK;
     const bool on_path = (a.path_of != nullptr);
     if (!a.state || (!a.ref && !on_path) || !a.u_prev || (!a.u0 && !a.rec))
@@ -772,6 +772,7 @@ int mpcb200_get_restorations(mpcb200_handle* h, int64_t B, int32_t* out) {
     if (!h || !out) return fail(h, MPCB200_EINVAL, "mpcb200_get_restorations: NULL argument");
     if (B != h->last_B) return fail(h, MPCB200_EINVAL, "mpcb200_get_restorations: B=%lld, the last solve had %lld problems", (long long)B, (long long)h->last_B);
     if (B == 0) return MPCB200_OK;
+    if (h->resto_on_host) { memcpy(out, h->small_resto, B * sizeof(int32_t)); return MPCB200_OK; }
     if (!h->last_sharded) {
         CUDA_TRY(h, cudaSetDevice(h->device));
         CUDA_TRY(h, cudaMemcpyAsync(out, h->d_resto.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));

@@ -91,3 +91,21 @@ def test_shard_range_properties():
         assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 0
 
     check()
+
+
+def test_kernel_record_layout_roundtrip():
+    """The 32-byte record the solve kernel writes (status | restorations << 8 in the low int32 of the fourth double, iters in
+    the high one) unpacks to the same fields pack_records / unpack_records move."""
+    import torch
+    from mkz_mpc_path_follower_b200 import sharding
+    rng = np.random.default_rng(1)
+    B = 257
+    u0 = rng.normal(size=(B, 2)); cost = rng.normal(size=B) ** 2
+    status = rng.integers(0, 5, B).astype(np.int32); iters = rng.integers(0, 3000, B).astype(np.int32)
+    resto = rng.integers(0, 4, B).astype(np.int32)
+    rec = sharding.pack_records(torch.from_numpy(u0), torch.from_numpy(cost), torch.from_numpy(status | (resto << 8)), torch.from_numpy(iters))
+    a, c, s, i, r = sharding.unpack_records_np(rec.numpy())
+    assert np.array_equal(a, u0) and np.array_equal(c, cost) and np.array_equal(s, status) and np.array_equal(i, iters) and np.array_equal(r, resto)
+    # the C library's slice rule is the Python one
+    import ctypes as C
+    assert [sharding.shard_range(65537, 8, q) for q in range(8)][3] == (24577, 32769)

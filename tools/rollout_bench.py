@@ -3,6 +3,7 @@
 round-robin, warm-started solve every step, plant + reference generation + solves in ONE kernel per GPU.
 
     python tools/rollout_bench.py [--vehicles 16384] [--steps 500]
+    python tools/rollout_bench.py --devices 8          # ONE process: a multi-GPU handle (mpcb200_config.devices) shards the fleet
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 tools/rollout_bench.py ...
 
 Strong scaling: the fleet is cut into contiguous slices, one per rank; a vehicle stays on its GPU for all
@@ -35,6 +36,7 @@ def main():
     ap.add_argument("--vehicles", type=int, default=16384)
     ap.add_argument("--steps", type=int, default=500)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--devices", type=int, default=0, help="single process: shard the fleet over this many GPUs inside libmpc_b200.so")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -46,7 +48,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     trajs, path_of, pose0 = fleet(args.vehicles)
     lo, hi = sharding.shard_range(args.vehicles, world, rank)
-    s = capi.Solver(8, device=local)
+    s = capi.Solver(config=capi.default_config(8, devices=list(range(args.devices)))) if args.devices > 1 else capi.Solver(8, device=local)
     for i, g in enumerate(trajs):
         s.set_path(i, g.trajectory)
     s.rollout(pose0[lo:lo + 64], path_of[lo:lo + 64], 5)    # warm-up (module load, clocks)
@@ -82,7 +84,8 @@ def main():
         r = r.cpu().numpy()
         n_solves = float(r[:, 2].sum())
         print(json.dumps({
-            "what": "closed-loop rollouts, configs[3]", "vehicles": args.vehicles, "control_steps": args.steps, "n_gpus": world,
+            "what": "closed-loop rollouts, configs[3]", "vehicles": args.vehicles, "control_steps": args.steps, "n_gpus": max(world, args.devices),
+            "sharding": "inside libmpc_b200.so (one process)" if args.devices > 1 else "one rank per GPU (torchrun)",
             "scaling": "strong", "wall_s": best, "kernel_s": best_kern,
             "vehicle_steps_per_s": args.vehicles * args.steps / best, "solves": n_solves, "solves_per_s": n_solves / best,
             "optimal_frac": float((r[:, 0] * r[:, 2]).sum() / max(1.0, n_solves)), "mean_iters": float((r[:, 1] * r[:, 2]).sum() / max(1.0, n_solves)),
