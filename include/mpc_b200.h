@@ -95,6 +95,17 @@ int mpcb200_set_cost(mpcb200_handle* h, const double w[8]);
  * NULL restores the handle's own stream. */
 int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
 
+/* Which kernel solves mpcb200_solve_batch / _records batches of the XY model (no reference counterpart: the reference
+ * solves one problem at a time, MKZMPCPathFollower.jl:176).  Two device layouts of the same solver exist: one warp per
+ * problem with the iterate on chip (every batch size, lowest latency) and one THREAD per problem with the iterate
+ * streamed from HBM (csrc/tpp_solver.cuh: faster for large batches at short horizons, e.g. 1.5x at 65,536 problems and
+ * 2.1x at 262,144 problems for N = 8; slower for N >= 12 below ~131,072 problems).  Both follow the same iteration and
+ * agree to rounding, not bit for bit.
+ *   min_batch  > 0: batches (per device) of at least min_batch problems use one thread per problem
+ *   min_batch == 0: always one warp per problem
+ *   min_batch  < 0: the default rule (N <= 10: 32,768; otherwise never), also what a new handle starts with */
+int mpcb200_set_large_batch_path(mpcb200_handle* h, int64_t min_batch);
+
 /*
  * Replaces, for B independent problems at once, the per-step sequence of mpc_cmd_pub.jl:115-141:
  *   update_init_cond(x, y, psi, v)                 -> state  [B][4]

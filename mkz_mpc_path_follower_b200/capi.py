@@ -54,6 +54,7 @@ def lib():
     L.mpcb200_destroy.argtypes = [vp]
     L.mpcb200_set_cost.argtypes = [vp, dp]
     L.mpcb200_set_stream.argtypes = [vp, vp]
+    L.mpcb200_set_large_batch_path.argtypes = [vp, C.c_int64]
     L.mpcb200_solve_batch.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.mpcb200_solve_batch_records.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.mpcb200_get_restorations.argtypes = [vp, C.c_int64, vp]
@@ -132,6 +133,10 @@ class Solver(object):
         w = np.ascontiguousarray(w, dtype=np.float64)
         assert w.shape == (8,)
         self._check(lib().mpcb200_set_cost(self._h, w.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def set_large_batch_path(self, min_batch=-1):
+        """Batches of at least `min_batch` problems (per device) use the thread-per-problem kernel; 0: never; < 0: default rule."""
+        self._check(lib().mpcb200_set_large_batch_path(self._h, int(min_batch)))
 
     def set_stream(self, cuda_stream_ptr):
         self._check(lib().mpcb200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))

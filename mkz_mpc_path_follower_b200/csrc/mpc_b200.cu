@@ -6,6 +6,7 @@
 // writes the per-problem record.  No CPU path exists in this library.
 #include "../../include/mpc_b200.h"
 #include "mpc_kernel.cuh"
+#include "tpp_solver.cuh"
 
 #include <cuda_runtime.h>
 
@@ -85,6 +86,33 @@ mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const
         __syncthreads();
         if (b >= (unsigned long long)B) break;
         solve_problem<W, MODEL>(cfg, io, rg, (long)b, smem);
+    }
+}
+
+
+// Large batches of the XY model: one THREAD per problem (tpp_solver.cuh).  A lane owns a slot of the state arrays
+// ([field][stage][slot]: the 32 lanes of a warp touch 256 contiguous bytes per access) for the whole launch; when its
+// problem ends it writes the result and takes the next problem index from the device counter.  The warp leaves when the
+// counter has run past the batch and every lane is idle.
+#ifndef MPC_TPP_BLOCK
+#define MPC_TPP_BLOCK 256
+#define MPC_TPP_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(MPC_TPP_BLOCK, MPC_TPP_MIN_BLOCKS)
+mpc_solve_tpp_kernel(const KCfg cfg, const BatchPtrs io, const long long B, double* st, double* filt, unsigned long long* counter) {
+    const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const TppMem mem(st, filt, cfg.N, slot);
+    TppSolver sv(cfg, mem);
+    bool alive = true;   // the counter has not run past the batch for this lane yet
+    long b = -1;
+    while (__syncthreads_or(alive)) {
+        if (alive && b < 0) {
+            const unsigned long long nb = atomicAdd(counter, 1ULL);
+            if (nb >= (unsigned long long)B) alive = false;
+            else { b = (long)nb; sv.begin(io, b); }
+        }
+        const bool done = sv.tick(b >= 0);
+        if (b >= 0 && done) { sv.finish(io, b); b = -1; }
     }
 }
 
@@ -182,6 +210,10 @@ struct mpcb200_handle {
     int* d_roles = nullptr;   /* lane roles of the Riccati recursion for this horizon (riccati_roles) */
     DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
     DevBuf d_path[3], d_pose, d_pathof, d_log, d_final, d_stop;
+    DevBuf d_tpp_state, d_tpp_filt;   /* thread-per-problem path: slot state [field][stage][slot], filters */
+    int tpp_blocks_per_sm = 0;        /* resident blocks of mpc_solve_tpp_kernel per SM */
+    int tpp_block = MPC_TPP_BLOCK;    /* threads per block of mpc_solve_tpp_kernel (a multiple of 32, <= MPC_TPP_BLOCK) */
+    int64_t tpp_min_batch = 0;        /* batches of at least this many problems take the thread-per-problem path (0: never) */
     DevBuf d_rec, d_resto;        /* packed 32-byte records; restoration count per problem of the last solve */
     DevBuf d_seed;                /* the module-load solution (start point of a rollout's first solve), [6N+4] */
     DevBuf d_fit;                 /* Frenet rollouts: the two least-squares fit matrices [4][n1], [4][n2] */
@@ -417,6 +449,18 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, fr, h->team_warps * 32, rb));
         if (h->rollout_blocks_per_sm < 1) h->rollout_blocks_per_sm = 1;
     }
+    if (!model) {
+        /* thread-per-problem path for large batches (any horizon): needs B >> resident lanes to keep them busy */
+        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_tpp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tpp_blocks_per_sm, mpc_solve_tpp_kernel, MPC_TPP_BLOCK, 0));
+        if (h->tpp_blocks_per_sm < 1) h->tpp_blocks_per_sm = 1;
+        if (const char* e = getenv("MPCB200_TPP_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->tpp_blocks_per_sm) h->tpp_blocks_per_sm = v; }  /* tuning aid */
+        if (const char* e = getenv("MPCB200_TPP_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= MPC_TPP_BLOCK && v % 32 == 0) h->tpp_block = v; }  /* tuning aid */
+        /* measured (tools/tpp_ab.py, gpurun_out/r02_tpp_thresholds.log): N = 8: 0.8x / 1.2x / 1.5x / 1.8x the warp-per-problem
+         * kernel at 16 K / 32 K / 64 K / 128 K problems; N = 12, 16: break-even at ~128 K; N = 20: 0.65x at 64 K, 0.97x at 256 K */
+        h->tpp_min_batch = (cfg->N <= 10) ? 32768 : 0;
+        if (const char* e = getenv("MPCB200_TPP_MIN_BATCH")) h->tpp_min_batch = atoll(e);   /* tuning aid; 0 switches the path off */
+    }
     if (h->blocks_per_sm < 1) h->blocks_per_sm = 1;
     if (const char* e = getenv("MPCB200_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v; }  /* tuning aid */
 #undef TRY_OR_FREE
@@ -431,7 +475,7 @@ int mpcb200_destroy(mpcb200_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj,
                       &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop, &h->d_stage,
-                      &h->d_rec, &h->d_resto, &h->d_seed, &h->d_fit};
+                      &h->d_rec, &h->d_resto, &h->d_seed, &h->d_fit, &h->d_tpp_state, &h->d_tpp_filt};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_roles) cudaFree(h->d_roles);
@@ -453,6 +497,16 @@ int mpcb200_set_cost(mpcb200_handle* h, const double w[8]) {
     return MPCB200_OK;
 }
 
+int mpcb200_set_large_batch_path(mpcb200_handle* h, int64_t min_batch) {
+    if (!h) return MPCB200_EINVAL;
+    if (h->model) return fail(h, MPCB200_EINVAL, "mpcb200_set_large_batch_path: the Frenet-frame variant has one kernel layout");
+    const int64_t v = (min_batch < 0) ? ((h->cfg.N <= 10) ? 32768 : 0) : min_batch;
+    h->tpp_min_batch = v;
+    drop_graphs(h);   /* a captured small-batch graph holds the kernel it was captured with */
+    for (int i = 0; i < h->n_sub; i++) { h->sub[i]->tpp_min_batch = v; drop_graphs(h->sub[i]); }
+    return MPCB200_OK;
+}
+
 /* the stream of devices[0]; the other devices of a multi-GPU handle keep their own streams */
 int mpcb200_set_stream(mpcb200_handle* h, void* s) {
     if (!h) return MPCB200_EINVAL;
@@ -464,6 +518,22 @@ int mpcb200_set_stream(mpcb200_handle* h, void* s) {
 static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const RefGen& rg, unsigned long long* zeroed_counter = nullptr) {
     unsigned long long* counter = zeroed_counter ? zeroed_counter : h->d_counter;
     if (!zeroed_counter) CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), h->stream));
+    if (!h->model && !rg.path_of && h->tpp_min_batch > 0 && B >= h->tpp_min_batch) {
+        /* thread-per-problem: as many slots as lanes can be resident, never more than problems */
+        const int tb = h->tpp_block;
+        long long blocks = (long long)h->num_sms * h->tpp_blocks_per_sm;
+        const long long need = (B + tb - 1) / tb;
+        if (blocks > need) blocks = need;
+        const long long S = blocks * tb;
+        int rc;
+        if ((rc = ensure(h, h->d_tpp_state, tpp_state_doubles(h->cfg.N, (long)S) * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_tpp_filt, tpp_filter_doubles((long)S) * sizeof(double)))) return rc;
+        mpc_solve_tpp_kernel<<<(int)blocks, tb, 0, h->stream>>>(make_kcfg(h), io, (long long)B, (double*)h->d_tpp_state.p,
+                                                               (double*)h->d_tpp_filt.p, counter);
+        CUDA_TRY(h, cudaGetLastError());
+        h->stats.kernel_launches += 1;
+        return 0;
+    }
     const int teams_per_block = (h->team_warps != 1) ? 1 : (h->model ? h->frenet_wpb : WARPS_PER_BLOCK);
     long long blocks_needed = (B + teams_per_block - 1) / teams_per_block;
     long long max_blocks = (long long)h->num_sms * h->blocks_per_sm;

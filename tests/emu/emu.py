@@ -8,7 +8,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _LIB = os.path.join(_HERE, "libmpc_emu.so")
 _SRCS = [os.path.join(_HERE, "emu_driver.cpp"), os.path.join(_HERE, "warp_emu.h"),
-         os.path.join(_ROOT, "mkz_mpc_path_follower_b200", "csrc", "mpc_kernel.cuh")]
+         os.path.join(_ROOT, "mkz_mpc_path_follower_b200", "csrc", "mpc_kernel.cuh"),
+         os.path.join(_ROOT, "mkz_mpc_path_follower_b200", "csrc", "tpp_solver.cuh")]
 
 
 class KCfg(C.Structure):
@@ -71,6 +72,29 @@ def solve_batch(kcfg, state, ref, v_des, u_prev, warm=None, want_traj=False):
                         status.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)),
                         None if traj is None else traj.ctypes.data_as(dp))
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
+
+
+def solve_batch_tpp(kcfg, state, ref, v_des, u_prev, warm=None, want_traj=False, slots=3):
+    """The thread-per-problem solver (csrc/tpp_solver.cuh) compiled for the host; problems round-robin over `slots` slots."""
+    lib = C.CDLL(build())
+    assert lib.emu_kcfg_size() == C.sizeof(KCfg)
+    dp = C.POINTER(C.c_double); ip = C.POINTER(C.c_int)
+    N = kcfg.N
+    B = state.shape[0]
+    p = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)
+    state = np.ascontiguousarray(state, dtype=np.float64); ref = np.ascontiguousarray(ref, dtype=np.float64)
+    u_prev = np.ascontiguousarray(u_prev, dtype=np.float64)
+    v_des = None if v_des is None else np.ascontiguousarray(v_des, dtype=np.float64)
+    u0 = np.empty((B, 2)); cost = np.empty(B); status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
+    resto = np.empty(B, dtype=np.int32); ticks = np.empty(B, dtype=np.int64)
+    traj = np.empty((B, 6 * N + 4)) if want_traj else None
+    lib.emu_solve_batch_tpp.argtypes = [C.POINTER(KCfg), C.c_long, dp, dp, dp, dp, dp, dp, dp, ip, ip, dp, ip, C.c_long, C.POINTER(C.c_long)]
+    lib.emu_solve_batch_tpp(C.byref(kcfg), B, p(state), p(ref), p(v_des), p(u_prev),
+                            None if warm is None else warm.ctypes.data_as(dp), p(u0), p(cost),
+                            status.ctypes.data_as(ip), iters.ctypes.data_as(ip),
+                            None if traj is None else traj.ctypes.data_as(dp), resto.ctypes.data_as(ip), slots,
+                            ticks.ctypes.data_as(C.POINTER(C.c_long)))
+    return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj, "n_resto": resto, "ticks": ticks}
 
 
 def solve_batch_frenet(kcfg, state, kpoly, v_des, u_prev, warm=None, want_traj=False):

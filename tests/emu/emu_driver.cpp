@@ -243,3 +243,26 @@ extern "C" int emu_rollout_frenet(const KCfg* cfg, long B, int T, const double* 
     }
     return 0;
 }
+
+// ---- thread-per-problem solver (csrc/tpp_solver.cuh): plain scalar code, no emulated warp needed.  The problems go
+// round-robin over S slots of one state array, so the [field][stage][slot] addressing of the device layout is exercised.
+#include "tpp_solver.cuh"
+extern "C" int emu_solve_batch_tpp(const KCfg* cfg, long B, const double* state, const double* ref, const double* v_des,
+                                   const double* u_prev, double* warm, double* u0, double* cost, int* status, int* iters,
+                                   double* traj, int* resto, long S, long* ticks) {
+    BatchPtrs io{state, ref, v_des, u_prev, warm, u0, cost, status, iters, traj, nullptr, resto};
+    KCfg kc = *cfg;
+    kcfg_finalize(kc);
+    if (S < 1) S = 1;
+    std::vector<double> st(tpp_state_doubles(kc.N, S), 0.0 / 0.0), filt(tpp_filter_doubles(S), 0.0 / 0.0);   // NaN: a field read before it is written shows
+    for (long b = 0; b < B; b++) {
+        TppMem m(st.data(), filt.data(), kc.N, b % S);
+        TppSolver sv(kc, m);
+        sv.begin(io, b);
+        long t = 0;
+        while (!sv.tick(true)) t++;
+        if (ticks) ticks[b] = t;
+        sv.finish(io, b);
+    }
+    return 0;
+}

@@ -1,0 +1,152 @@
+"""GPU parity tests of the thread-per-problem layout of the solver (csrc/tpp_solver.cuh, mpc_solve_tpp_kernel), through the
+C ABI: forced with mpcb200_set_large_batch_path(1) on small batches, and under its default rule on a large one.  Same
+tolerances as tests/test_gpu_parity.py (BASELINE.json): same status, |du| <= 1e-5, relative cost <= 1e-6."""
+import numpy as np
+import pytest
+
+from mkz_mpc_path_follower_b200 import workload as W
+
+pytestmark = pytest.mark.gpu
+
+U_TOL = 1e-5
+COST_RTOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from mkz_mpc_path_follower_b200 import capi as c
+    c.lib()
+    return c
+
+
+def _ocfg(oracle, solver):
+    c = solver.cfg
+    return oracle.default_cfg(c.N, tol=c.tol, max_iter=c.max_iter)
+
+
+def _compare(g, o, min_conv=0.9, max_status_mismatch=0):
+    mism = np.nonzero(g["status"] != o["status"])[0]
+    assert mism.size <= max_status_mismatch, mism
+    ok = (o["status"] == 0) & (g["status"] == 0)
+    assert ok.mean() >= min_conv
+    assert np.abs(g["u0"] - o["u0"])[ok].max() <= U_TOL
+    assert (np.abs(g["cost"] - o["cost"])[ok] / np.maximum(1.0, np.abs(o["cost"][ok]))).max() <= COST_RTOL
+    return ok
+
+
+@pytest.mark.parametrize("N,B,paths", [(8, 300, (1,)), (20, 200, (1, 2, 3)), (3, 40, (2,)), (31, 24, (3,))])
+def test_tpp_cold_and_warm_parity(capi, oracle, N, B, paths):
+    s = capi.Solver(N)
+    s.set_large_batch_path(1)
+    b = W.make_batch(B, N, path_ids=paths)
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    assert s.stats()["kernel_launches"] == 1
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], want_traj=True, n_threads=8)
+    ok = _compare(g, o, min_conv=0.7 if N == 31 else 0.9, max_status_mismatch=1 if N == 31 else 0)
+    assert np.abs(g["traj"] - o["traj"])[ok].max() <= 1e-5
+    if N <= 20:
+        assert (g["iters"] == o["iters"]).mean() >= 0.99
+    # warm start from the solution: in/out buffer, a handful of iterations, identical counts
+    wg, wo = o["traj"].copy(), o["traj"].copy()
+    g2 = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], warm=wg)
+    o2 = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], warm=wo, n_threads=8)
+    ok2 = _compare(g2, o2, min_conv=0.7 if N == 31 else 0.9, max_status_mismatch=1 if N == 31 else 0)
+    assert (g2["iters"][ok2] == o2["iters"][ok2]).mean() >= 0.99
+    assert np.abs(wg - wo)[ok2].max() <= 1e-5
+    # ... and the same batch through the warp-per-problem kernel
+    s.set_large_batch_path(0)
+    w = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    assert (w["status"] == g["status"]).sum() >= B - (1 if N == 31 else 0)
+    both = (w["status"] == 0) & (g["status"] == 0)
+    assert np.abs(w["u0"] - g["u0"])[both].max() <= U_TOL
+
+
+@pytest.mark.parametrize("N,B", [(40, 96), (80, 48)])
+def test_tpp_long_horizons(capi, oracle, N, B):
+    """The thread-per-problem passes are loops over the stages: any horizon, no team size."""
+    s = capi.Solver(N)
+    s.set_large_batch_path(1)
+    b = W.make_batch(B, N)
+    w0 = W.reference_start(b, N)
+    wg, wo = w0.copy(), w0.copy()
+    g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], warm=wg)
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], warm=wo, n_threads=8)
+    ok = _compare(g, o, min_conv=0.99)
+    assert (g["iters"][ok] == o["iters"][ok]).all()
+    assert np.abs(wg - wo)[ok].max() <= 1e-5
+
+
+def test_tpp_edge_cases_records_and_restorations(capi, oracle):
+    from mkz_mpc_path_follower_b200 import sharding
+    N = 8
+    s = capi.Solver(N)
+    s.set_large_batch_path(1)
+    b = W.make_batch(64, N)
+    st = b["state"].copy(); up = b["u_prev"].copy()
+    st[0, 3] = 25.0; st[1, 3] = -1.0; up[2, 0] = 0.9       # infeasible by the initial speed / the previous command
+    g = s.solve_batch(st, b["ref"], up, v_des=b["v_des"])
+    o = oracle.solve_batch(_ocfg(oracle, s), st, b["ref"], b["v_des"], up, n_threads=4)
+    assert (g["status"] == o["status"]).all() and (g["status"][:3] == 1).all() and (g["iters"][:3] == 0).all()
+    # iteration cap -> UserLimit with the iterate returned
+    s2 = capi.Solver(config=capi.default_config(N, max_iter=7))
+    s2.set_large_batch_path(1)
+    g = s2.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
+    o = oracle.solve_batch(_ocfg(oracle, s2), b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=4)
+    assert (g["status"] == 3).all() and (o["status"] == 3).all() and np.abs(g["u0"] - o["u0"]).max() <= 1e-8
+    # records and restoration counts (N = 20: a few per cent of the cold starts are restored by rollout)
+    N = 20
+    s = capi.Solver(N)
+    s.set_large_batch_path(1)
+    b = W.make_batch(512, N)
+    rec = s.solve_batch_records(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
+    a, c, stt, it, r = sharding.unpack_records_np(rec)
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=8)
+    assert (stt == o["status"]).all() and (r == o["n_resto"]).all() and r.sum() > 0
+    assert (s.restorations(512) == o["n_resto"]).all()
+    ok = o["status"] == 0
+    assert np.abs(a - o["u0"])[ok].max() <= U_TOL and (it[ok] == o["iters"][ok]).mean() >= 0.99
+    # empty batch
+    e = s.solve_batch(np.zeros((0, 4)), np.zeros((0, 3, N + 1)), np.zeros((0, 2)))
+    assert e["u0"].shape == (0, 2)
+
+
+def test_tpp_default_rule_large_batch(capi, oracle):
+    """N = 8, 32,768 problems: the default rule sends the batch to the thread-per-problem kernel (lanes refill from the
+    queue: 37,888 resident lanes at most, so every lane gets a problem and most are refilled at 65,536).  Every problem
+    is checked against the oracle; the warp-per-problem kernel on the same batch gives the same statuses."""
+    import torch
+    N, B = 8, 65536
+    s = capi.Solver(N)
+    b = W.make_batch(B, N)
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(b[k]).to(dev) for k in ("state", "ref", "u_prev", "v_des")}
+    out = {}
+    for name, mb in (("tpp", -1), ("warp", 0)):
+        s.set_large_batch_path(mb)
+        u0 = torch.empty((B, 2), dtype=torch.float64, device=dev)
+        cost = torch.empty(B, dtype=torch.float64, device=dev)
+        status = torch.empty(B, dtype=torch.int32, device=dev)
+        iters = torch.empty(B, dtype=torch.int32, device=dev)
+        st = torch.cuda.Stream(device=dev)
+        s.set_stream(st.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(st):
+            e0.record(st)
+            s.solve_batch_device(B, d["state"], d["ref"], d["u_prev"], u0, v_des=d["v_des"], cost=cost, status=status, iters=iters)
+            e1.record(st)
+        torch.cuda.synchronize()
+        out[name] = dict(u0=u0.cpu().numpy(), cost=cost.cpu().numpy(), status=status.cpu().numpy(), iters=iters.cpu().numpy(), ms=e0.elapsed_time(e1))
+        s.set_stream(0)
+    t, w = out["tpp"], out["warp"]
+    assert (t["status"] == w["status"]).mean() >= 0.9999
+    assert (t["iters"] == w["iters"]).mean() >= 0.999
+    both = (t["status"] == 0) & (w["status"] == 0)
+    assert (np.abs(t["u0"] - w["u0"])[both].max(axis=1) > U_TOL).sum() <= 3
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=16)
+    assert (t["status"] != o["status"]).sum() <= 3
+    ok = (t["status"] == 0) & (o["status"] == 0)
+    assert ok.mean() >= 0.999
+    assert (np.abs(t["u0"] - o["u0"])[ok].max(axis=1) > U_TOL).sum() <= 3
+    assert (t["iters"][ok] == o["iters"][ok]).mean() >= 0.998
+    print("N=8 B=65536: thread-per-problem %.2f ms, warp-per-problem %.2f ms" % (t["ms"], w["ms"]))
+    assert t["ms"] < w["ms"]      # what the default rule is for
