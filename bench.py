@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--horizon", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-latency", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the configs beside the headline (config1, rollout_config3, horizon_sweep, strong_64k)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the configs beside the headline (config1, rollout_config3, horizon_sweep, strong_64k, layouts_n8)")
     ap.add_argument("--parity", default="full", choices=["full", "sample"],
                     help="full: every problem of every rank's slice is checked against the oracle (the converged count); sample: a bounded sample")
     ap.add_argument("--rollout-vehicles", type=int, default=16384)
@@ -418,10 +418,13 @@ def main():
         except Exception as ex:
             extras[name] = {"error": repr(ex)}
 
-    def timed_device_solve(Nh, Bh, start_mode, max_iter=None, reps=2, b0=0, rollout_warm=False):
-        bb = workload.make_batch(Bh, Nh, b0=b0)
+    def timed_device_solve(Nh, Bh, start_mode, max_iter=None, reps=2, b0=0, rollout_warm=False, min_batch=None, bb=None):
+        """min_batch: None = the library's default rule for the kernel layout, 0 = one warp per problem, 1 = one thread per problem"""
+        bb = workload.make_batch(Bh, Nh, b0=b0) if bb is None else bb
         kw = {} if max_iter is None else {"max_iter": max_iter}
         sv = capi.Solver(Nh, device=local, start_mode=start_mode, **kw)
+        if min_batch is not None:
+            sv.set_large_batch_path(min_batch)
         sv.set_stream(stream.cuda_stream)
         dd = {k_: torch.from_numpy(bb[k_]).to(dev) for k_ in ("state", "ref", "u_prev", "v_des")}
         rec = torch.empty((Bh, 4), dtype=torch.float64, device=dev)
@@ -510,12 +513,35 @@ def main():
                 bb, ms, uu, cc, ss, ii, rr = timed_device_solve(Nh, Bh, mode, reps=1, b0=rank * Bh)
                 conv, nit = allsum([float((ss == 0).sum()), float(ii.sum())])
                 msx = allmax(ms)
-                row[nm] = {"kernel_ms": msx, "converged_frac": conv / (world * Bh), "mean_iters": nit / (world * Bh),
+                row[nm] = {"kernel": "mpc_solve_tpp_kernel" if (Nh <= 10 and Bh >= 32768) else ("mpc_solve_kernel" if Nh <= 31 else "mpc_solve_long_kernel"),
+                           "kernel_ms": msx, "converged_frac": conv / (world * Bh), "mean_iters": nit / (world * Bh),
                            "value": conv / (msx * 1e-3), "unit": "converged solves/s", "max_iter": 200,
                            "fp64_tflops": nit * (F_RIC + F_EVAL) * Nh / (msx * 1e-3) / 1e12}
             res["N%d" % Nh] = row
         res["what"] = ("configs[4] per GPU (weak): all-zero start = the reference's start=0.0, converged fraction inside the "
                        "200-iteration cap; rollout start = MPCB200_START_ROLLOUT (opt-in, not a reference behaviour)")
+        return res
+
+    # the two device layouts of the solver on large batches at the reference's own horizon (N = 8): one warp per problem
+    # (iterate on chip) against one thread per problem (iterate streamed from HBM, csrc/tpp_solver.cuh); rank 0's GPU only
+    def layouts_n8():
+        res = {"what": "N = 8, all-zero start, kernel time of ONE launch per layout on the same batch; the default rule "
+                       "(mpcb200_set_large_batch_path) picks one thread per problem from 32,768 problems at N <= 10"}
+        for Bh in (65536, 262144):
+            bb = workload.make_batch(Bh, 8)
+            row = {}
+            out = {}
+            for nm, mb in (("warp_per_problem", 0), ("thread_per_problem", 1)):
+                _, ms, uu, cc, ss, ii, rr = timed_device_solve(8, Bh, capi.START_ZERO, reps=1, min_batch=mb, bb=bb)
+                out[nm] = (uu, ss, ii)
+                row[nm] = {"kernel_ms": ms, "value": float((ss == 0).sum()) / (ms * 1e-3), "unit": "converged solves/s",
+                           "converged_frac": float((ss == 0).mean()), "mean_iters": float(ii.mean())}
+            (uw, sw_, iw), (ut, st_, it_) = out["warp_per_problem"], out["thread_per_problem"]
+            both = (sw_ == 0) & (st_ == 0)
+            row["agreement"] = {"status_equal": int((sw_ == st_).sum()), "iters_equal": int((iw == it_).sum()), "of": Bh,
+                                "du_gt_1e-5": int((np.abs(uw - ut)[both].max(axis=1) > 1e-5).sum())}
+            row["speedup"] = row["warp_per_problem"]["kernel_ms"] / row["thread_per_problem"]["kernel_ms"]
+            res["B%d" % Bh] = row
         return res
 
     # strong scaling of configs[2]: ONE 65,536-problem batch cut into contiguous slices over the ranks
@@ -553,6 +579,8 @@ def main():
         extra("rollout_config3", rollout_config3)
         extra("horizon_sweep", horizon_sweep)
         extra("strong_64k", strong_64k)
+        if rank == 0:
+            extra("layouts_n8", layouts_n8)
 
     if rank != 0:
         if world > 1:

@@ -103,7 +103,8 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
  * agree to rounding, not bit for bit.
  *   min_batch  > 0: batches (per device) of at least min_batch problems use one thread per problem
  *   min_batch == 0: always one warp per problem
- *   min_batch  < 0: the default rule (N <= 10: 32,768; otherwise never), also what a new handle starts with */
+ *   min_batch  < 0: the default rule (N <= 10: 32,768, and 16,384 for warm-started or rollout-started batches, whose
+ *                   solves all take about the same handful of iterations; N > 10: never), what a new handle starts with */
 int mpcb200_set_large_batch_path(mpcb200_handle* h, int64_t min_batch);
 
 /*

@@ -214,6 +214,7 @@ struct mpcb200_handle {
     int tpp_blocks_per_sm = 0;        /* resident blocks of mpc_solve_tpp_kernel per SM */
     int tpp_block = MPC_TPP_BLOCK;    /* threads per block of mpc_solve_tpp_kernel (a multiple of 32, <= MPC_TPP_BLOCK) */
     int64_t tpp_min_batch = 0;        /* batches of at least this many problems take the thread-per-problem path (0: never) */
+    bool tpp_default_rule = true;     /* ... as set by the default rule (then warm / rollout starts switch at half of it) */
     DevBuf d_rec, d_resto;        /* packed 32-byte records; restoration count per problem of the last solve */
     DevBuf d_seed;                /* the module-load solution (start point of a rollout's first solve), [6N+4] */
     DevBuf d_fit;                 /* Frenet rollouts: the two least-squares fit matrices [4][n1], [4][n2] */
@@ -459,7 +460,7 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         /* measured (tools/tpp_ab.py, gpurun_out/r02_tpp_thresholds.log): N = 8: 0.8x / 1.2x / 1.5x / 1.8x the warp-per-problem
          * kernel at 16 K / 32 K / 64 K / 128 K problems; N = 12, 16: break-even at ~128 K; N = 20: 0.65x at 64 K, 0.97x at 256 K */
         h->tpp_min_batch = (cfg->N <= 10) ? 32768 : 0;
-        if (const char* e = getenv("MPCB200_TPP_MIN_BATCH")) h->tpp_min_batch = atoll(e);   /* tuning aid; 0 switches the path off */
+        if (const char* e = getenv("MPCB200_TPP_MIN_BATCH")) { h->tpp_min_batch = atoll(e); h->tpp_default_rule = false; }   /* tuning aid; 0 switches the path off */
     }
     if (h->blocks_per_sm < 1) h->blocks_per_sm = 1;
     if (const char* e = getenv("MPCB200_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->blocks_per_sm) h->blocks_per_sm = v; }  /* tuning aid */
@@ -501,9 +502,9 @@ int mpcb200_set_large_batch_path(mpcb200_handle* h, int64_t min_batch) {
     if (!h) return MPCB200_EINVAL;
     if (h->model) return fail(h, MPCB200_EINVAL, "mpcb200_set_large_batch_path: the Frenet-frame variant has one kernel layout");
     const int64_t v = (min_batch < 0) ? ((h->cfg.N <= 10) ? 32768 : 0) : min_batch;
-    h->tpp_min_batch = v;
+    h->tpp_min_batch = v; h->tpp_default_rule = (min_batch < 0);
     drop_graphs(h);   /* a captured small-batch graph holds the kernel it was captured with */
-    for (int i = 0; i < h->n_sub; i++) { h->sub[i]->tpp_min_batch = v; drop_graphs(h->sub[i]); }
+    for (int i = 0; i < h->n_sub; i++) { h->sub[i]->tpp_min_batch = v; h->sub[i]->tpp_default_rule = (min_batch < 0); drop_graphs(h->sub[i]); }
     return MPCB200_OK;
 }
 
@@ -518,7 +519,12 @@ int mpcb200_set_stream(mpcb200_handle* h, void* s) {
 static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const RefGen& rg, unsigned long long* zeroed_counter = nullptr) {
     unsigned long long* counter = zeroed_counter ? zeroed_counter : h->d_counter;
     if (!zeroed_counter) CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), h->stream));
-    if (!h->model && !rg.path_of && h->tpp_min_batch > 0 && B >= h->tpp_min_batch) {
+    /* (never for the packed small-batch path, which brings its own counter and may be inside a graph capture) */
+    /* starts next to the solution (warm start, rollout start) take a handful of iterations each, all about the same number:
+     * no tail of long solves, so the streaming layout already pays at half the batch (measured at N = 8, 16,384 problems:
+     * 1.06x warm, 1.30x from the rollout start; gpurun_out/r02_tpp_warm.log) */
+    const int64_t tpp_from = (h->tpp_default_rule && (io.warm || h->cfg.start_mode == MPCB200_START_ROLLOUT)) ? h->tpp_min_batch / 2 : h->tpp_min_batch;
+    if (!h->model && !rg.path_of && !zeroed_counter && h->tpp_min_batch > 0 && B >= tpp_from) {
         /* thread-per-problem: as many slots as lanes can be resident, never more than problems */
         const int tb = h->tpp_block;
         long long blocks = (long long)h->num_sms * h->tpp_blocks_per_sm;

@@ -34,15 +34,15 @@ def _compare(g, o, min_conv=0.9, max_status_mismatch=0):
     return ok
 
 
-@pytest.mark.parametrize("N,B,paths", [(8, 300, (1,)), (20, 200, (1, 2, 3)), (3, 40, (2,)), (31, 24, (3,))])
+@pytest.mark.parametrize("N,B,paths", [(8, 300, (1,)), (20, 200, (1, 2, 3)), (3, 80, (2,)), (31, 72, (3,))])
 def test_tpp_cold_and_warm_parity(capi, oracle, N, B, paths):
     s = capi.Solver(N)
     s.set_large_batch_path(1)
     b = W.make_batch(B, N, path_ids=paths)
     g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
-    assert s.stats()["kernel_launches"] == 1
+    assert s.stats()["kernel_launches"] == 1 and B > 64
     o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], want_traj=True, n_threads=8)
-    ok = _compare(g, o, min_conv=0.7 if N == 31 else 0.9, max_status_mismatch=1 if N == 31 else 0)
+    ok = _compare(g, o, min_conv=0.7 if N == 31 else 0.9, max_status_mismatch=3 if N == 31 else 0)
     assert np.abs(g["traj"] - o["traj"])[ok].max() <= 1e-5
     if N <= 20:
         assert (g["iters"] == o["iters"]).mean() >= 0.99
@@ -50,18 +50,18 @@ def test_tpp_cold_and_warm_parity(capi, oracle, N, B, paths):
     wg, wo = o["traj"].copy(), o["traj"].copy()
     g2 = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], warm=wg)
     o2 = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], warm=wo, n_threads=8)
-    ok2 = _compare(g2, o2, min_conv=0.7 if N == 31 else 0.9, max_status_mismatch=1 if N == 31 else 0)
+    ok2 = _compare(g2, o2, min_conv=0.7 if N == 31 else 0.9, max_status_mismatch=3 if N == 31 else 0)
     assert (g2["iters"][ok2] == o2["iters"][ok2]).mean() >= 0.99
     assert np.abs(wg - wo)[ok2].max() <= 1e-5
     # ... and the same batch through the warp-per-problem kernel
     s.set_large_batch_path(0)
     w = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
-    assert (w["status"] == g["status"]).sum() >= B - (1 if N == 31 else 0)
+    assert (w["status"] == g["status"]).sum() >= B - (3 if N == 31 else 0)
     both = (w["status"] == 0) & (g["status"] == 0)
     assert np.abs(w["u0"] - g["u0"])[both].max() <= U_TOL
 
 
-@pytest.mark.parametrize("N,B", [(40, 96), (80, 48)])
+@pytest.mark.parametrize("N,B", [(40, 96), (80, 80)])
 def test_tpp_long_horizons(capi, oracle, N, B):
     """The thread-per-problem passes are loops over the stages: any horizon, no team size."""
     s = capi.Solver(N)
@@ -81,7 +81,7 @@ def test_tpp_edge_cases_records_and_restorations(capi, oracle):
     N = 8
     s = capi.Solver(N)
     s.set_large_batch_path(1)
-    b = W.make_batch(64, N)
+    b = W.make_batch(96, N)      # (host batches of up to 64 problems always take the packed small-batch path)
     st = b["state"].copy(); up = b["u_prev"].copy()
     st[0, 3] = 25.0; st[1, 3] = -1.0; up[2, 0] = 0.9       # infeasible by the initial speed / the previous command
     g = s.solve_batch(st, b["ref"], up, v_des=b["v_des"])

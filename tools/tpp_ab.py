@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the two solve paths on one synthetic batch: thread-per-problem (large batches) vs warp-per-problem.
-    python tools/tpp_ab.py [B] [N] [reps]
+    python tools/tpp_ab.py [B] [N] [reps] [start]      start: zero (default) | warm (the problem's own solution) | rollout
 Prints kernel ms of each path and how their results differ (status, iterations, first input)."""
 import os
 import sys
@@ -14,13 +14,14 @@ from mkz_mpc_path_follower_b200 import capi, workload  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+start = sys.argv[4] if len(sys.argv) > 4 else "zero"
 dev = torch.device("cuda", 0)
 b = workload.make_batch(B, N)
 d = {k: torch.from_numpy(b[k]).to(dev) for k in ("state", "ref", "u_prev", "v_des")}
 out = {}
 for name, thr in (("warp", "0"), ("tpp", "1")):
     os.environ["MPCB200_TPP_MIN_BATCH"] = thr
-    s = capi.Solver(N)
+    s = capi.Solver(N, start_mode=capi.START_ROLLOUT if start == "rollout" else capi.START_ZERO)
     st = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(st)
     s.set_stream(st.cuda_stream)
@@ -30,10 +31,16 @@ for name, thr in (("warp", "0"), ("tpp", "1")):
     iters = torch.empty(B, dtype=torch.int32, device=dev)
     traj = torch.empty((B, 6 * N + 4), dtype=torch.float64, device=dev)
     best = 1e9
+    sol = None
+    if start == "warm":
+        s.solve_batch_device(B, d["state"], d["ref"], d["u_prev"], u0, v_des=d["v_des"], status=status, traj=traj)
+        torch.cuda.synchronize()
+        sol = traj.clone()
     for r in range(reps):
+        warm = sol.clone() if sol is not None else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        s.solve_batch_device(B, d["state"], d["ref"], d["u_prev"], u0, v_des=d["v_des"], cost=cost, status=status, iters=iters, traj=traj)
+        s.solve_batch_device(B, d["state"], d["ref"], d["u_prev"], u0, v_des=d["v_des"], warm=warm, cost=cost, status=status, iters=iters, traj=traj)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
