@@ -15,7 +15,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
+#include <utility>
 
 using namespace mpcb200;
 
@@ -247,6 +250,21 @@ struct mpcb200_handle {
 
 static thread_local char g_err[512] = "";
 
+/* The dynamic shared-memory limit of a kernel is an attribute of the FUNCTION (per device), not of a launch, and the team
+ * footprint depends on the horizon: handles with different horizons in one process share it.  It is therefore only ever
+ * raised (a larger limit is fine for a smaller launch); lowering it made the next launch of a longer-horizon handle fail
+ * with "invalid argument". */
+static cudaError_t raise_dyn_smem(const void* fn, int device, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> current;
+    std::lock_guard<std::mutex> g(mu);
+    size_t& cur = current[std::make_pair(fn, device)];
+    if (cur >= bytes) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
+
 static int fail(mpcb200_handle* h, int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -405,16 +423,16 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
     if (model && h->team_warps > 1) {
         h->smem_bytes = (size_t)smem_doubles_per_team(cfg->N, 1) * sizeof(double);
         const void* fn = (h->team_warps == 2) ? (const void*)mpc_solve_long_kernel<2, 1> : (const void*)mpc_solve_long_kernel<3, 1>;
-        TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(raise_dyn_smem((const void*)fn, h->device, (size_t)(h->smem_bytes)));
         TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, fn, h->team_warps * 32, h->smem_bytes));
     } else if (model) {
         const size_t team = (size_t)smem_doubles_per_team(cfg->N, 1) * sizeof(double);
         int b4 = 0, b3 = 0;
-        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * team)));
+        TRY_OR_FREE(raise_dyn_smem((const void*)mpc_solve_frenet_kernel<4>, h->device, (size_t)(4 * team)));
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4, mpc_solve_frenet_kernel<4>, 4 * 32, 4 * team));
-        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * team)));
+        TRY_OR_FREE(raise_dyn_smem((const void*)mpc_solve_frenet_kernel<3>, h->device, (size_t)(3 * team)));
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_frenet_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b3, mpc_solve_frenet_kernel<3>, 3 * 32, 3 * team));
         /* measured (tools/frenet_bench.py): N = 8: 12 warps at 168 registers 6.06 M solves/s vs 8 warps at 255 registers 5.80 M;
@@ -424,28 +442,28 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         h->blocks_per_sm = (h->frenet_wpb == 3) ? b3 : b4;
         h->smem_bytes = h->frenet_wpb * team;
         const size_t rb = WARPS_PER_BLOCK * team + WARPS_PER_BLOCK * ROLLOUT_PX * sizeof(double);
-        TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_frenet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb));
+        TRY_OR_FREE(raise_dyn_smem((const void*)mpc_rollout_frenet_kernel, h->device, (size_t)(rb)));
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_frenet_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->frenet_rollout_blocks_per_sm, mpc_rollout_frenet_kernel, WARPS_PER_BLOCK * 32, rb));
         if (h->frenet_rollout_blocks_per_sm < 1) h->frenet_rollout_blocks_per_sm = 1;
     } else if (h->team_warps == 1) {
         h->smem_bytes = ((size_t)WARPS_PER_BLOCK * smem_doubles_per_team(cfg->N) + WARPS_PER_BLOCK * ROLLOUT_PX) * sizeof(double);
-        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(raise_dyn_smem((const void*)mpc_solve_kernel, h->device, (size_t)(h->smem_bytes)));
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, mpc_solve_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
-        TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(raise_dyn_smem((const void*)mpc_rollout_kernel, h->device, (size_t)(h->smem_bytes)));
         TRY_OR_FREE(cudaFuncSetAttribute(mpc_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, mpc_rollout_kernel, WARPS_PER_BLOCK * 32, h->smem_bytes));
         if (h->rollout_blocks_per_sm < 1) h->rollout_blocks_per_sm = 1;
     } else {
         h->smem_bytes = (size_t)smem_doubles_per_team(cfg->N) * sizeof(double);
         const void* fn = (h->team_warps == 2) ? (const void*)mpc_solve_long_kernel<2> : (const void*)mpc_solve_long_kernel<3>;
-        TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+        TRY_OR_FREE(raise_dyn_smem((const void*)fn, h->device, (size_t)(h->smem_bytes)));
         TRY_OR_FREE(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->blocks_per_sm, fn, h->team_warps * 32, h->smem_bytes));
         const void* fr = (h->team_warps == 2) ? (const void*)mpc_rollout_long_kernel<2> : (const void*)mpc_rollout_long_kernel<3>;
         const size_t rb = h->smem_bytes + ROLLOUT_PX * sizeof(double);
-        TRY_OR_FREE(cudaFuncSetAttribute(fr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rb));
+        TRY_OR_FREE(raise_dyn_smem((const void*)fr, h->device, (size_t)(rb)));
         TRY_OR_FREE(cudaFuncSetAttribute(fr, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, fr, h->team_warps * 32, rb));
         if (h->rollout_blocks_per_sm < 1) h->rollout_blocks_per_sm = 1;

@@ -781,3 +781,24 @@ def test_frenet_large_batch_oracle_parity(capi, oracle):
     assert (g["iters"] == o["iters"])[ok].mean() >= 0.999
     assert np.abs(g["u0"] - o["u0"])[ok].max() <= 1e-8
     assert (np.abs(g["cost"] - o["cost"])[ok] <= 1e-9 * np.maximum(1.0, o["cost"][ok])).all()
+
+
+def test_handles_with_different_horizons_in_one_process(capi, oracle):
+    """The dynamic shared-memory limit is an attribute of the kernel function, shared by every handle of the process: creating
+    a short-horizon handle must not take the room a long-horizon handle needs (it did: `invalid argument` at the next launch of
+    the N = 20 handle, which is what bench.py's strong-scaling key ran into on 2 GPUs)."""
+    s20 = capi.Solver(20)
+    b20 = W.make_batch(96, 20)
+    g0 = s20.solve_batch(b20["state"], b20["ref"], b20["u_prev"], v_des=b20["v_des"])
+    s8 = capi.Solver(8)                       # same kernels, smaller team footprint
+    b8 = W.make_batch(96, 8)
+    g8 = s8.solve_batch(b8["state"], b8["ref"], b8["u_prev"], v_des=b8["v_des"])
+    s31 = capi.Solver(31)
+    g1 = s20.solve_batch(b20["state"], b20["ref"], b20["u_prev"], v_des=b20["v_des"])
+    assert (g0["status"] == g1["status"]).all() and np.array_equal(g0["u0"], g1["u0"]) and np.array_equal(g0["iters"], g1["iters"])
+    o8 = oracle.solve_batch(_ocfg(oracle, s8), b8["state"], b8["ref"], b8["v_des"], b8["u_prev"], n_threads=4)
+    _compare(g8, o8)
+    b31 = W.make_batch(72, 31)
+    s31.solve_batch(b31["state"], b31["ref"], b31["u_prev"], v_des=b31["v_des"])
+    g2 = s8.solve_batch(b8["state"], b8["ref"], b8["u_prev"], v_des=b8["v_des"])
+    assert np.array_equal(g8["u0"], g2["u0"])
