@@ -475,7 +475,7 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         if (h->tpp_blocks_per_sm < 1) h->tpp_blocks_per_sm = 1;
         if (const char* e = getenv("MPCB200_TPP_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->tpp_blocks_per_sm) h->tpp_blocks_per_sm = v; }  /* tuning aid */
         if (const char* e = getenv("MPCB200_TPP_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= MPC_TPP_BLOCK && v % 32 == 0) h->tpp_block = v; }  /* tuning aid */
-        /* measured (tools/tpp_ab.py, gpurun_out/r02_tpp_thresholds.log): N = 8: 0.8x / 1.2x / 1.5x / 1.8x the warp-per-problem
+        /* measured (tools/tpp_ab.py, profiles/r02_logs/r02_tpp_thresholds.log): N = 8: 0.8x / 1.2x / 1.5x / 1.8x the warp-per-problem
          * kernel at 16 K / 32 K / 64 K / 128 K problems; N = 12, 16: break-even at ~128 K; N = 20: 0.65x at 64 K, 0.97x at 256 K */
         h->tpp_min_batch = (cfg->N <= 10) ? 32768 : 0;
         if (const char* e = getenv("MPCB200_TPP_MIN_BATCH")) { h->tpp_min_batch = atoll(e); h->tpp_default_rule = false; }   /* tuning aid; 0 switches the path off */
@@ -540,7 +540,7 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
     /* (never for the packed small-batch path, which brings its own counter and may be inside a graph capture) */
     /* starts next to the solution (warm start, rollout start) take a handful of iterations each, all about the same number:
      * no tail of long solves, so the streaming layout already pays at half the batch (measured at N = 8, 16,384 problems:
-     * 1.06x warm, 1.30x from the rollout start; gpurun_out/r02_tpp_warm.log) */
+     * 1.06x warm, 1.30x from the rollout start; profiles/r02_logs/r02_tpp_warm.log) */
     const int64_t tpp_from = (h->tpp_default_rule && (io.warm || h->cfg.start_mode == MPCB200_START_ROLLOUT)) ? h->tpp_min_batch / 2 : h->tpp_min_batch;
     if (!h->model && !rg.path_of && !zeroed_counter && h->tpp_min_batch > 0 && B >= tpp_from) {
         /* thread-per-problem: as many slots as lanes can be resident, never more than problems */
