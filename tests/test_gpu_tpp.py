@@ -150,3 +150,22 @@ def test_tpp_default_rule_large_batch(capi, oracle):
     assert (t["iters"][ok] == o["iters"][ok]).mean() >= 0.998
     print("N=8 B=65536: thread-per-problem %.2f ms, warp-per-problem %.2f ms" % (t["ms"], w["ms"]))
     assert t["ms"] < w["ms"]      # what the default rule is for
+
+
+def test_tpp_multi_device_handle(capi):
+    """A handle over several GPUs with the thread-per-problem layout on every slice: bit-identical to one device (a problem's
+    result does not depend on its slot or on its neighbours in the warp).  With one GPU the test is the n_devices = 1 path."""
+    import torch
+    N, B = 8, 3000
+    b = W.make_batch(B, N)
+    one = capi.Solver(N)
+    one.set_large_batch_path(1)
+    ref = one.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    ndev = min(torch.cuda.device_count(), 4)
+    multi = capi.Solver(config=capi.default_config(N, devices=list(range(ndev))))
+    multi.set_large_batch_path(1)
+    out = multi.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], want_traj=True)
+    for k in ("u0", "cost", "status", "iters", "traj"):
+        assert np.array_equal(out[k], ref[k]), k
+    assert multi.stats()["kernel_launches"] == ndev
+    assert np.array_equal(multi.restorations(B), one.restorations(B))
