@@ -169,3 +169,35 @@ def test_tpp_multi_device_handle(capi):
         assert np.array_equal(out[k], ref[k]), k
     assert multi.stats()["kernel_launches"] == ndev
     assert np.array_equal(multi.restorations(B), one.restorations(B))
+
+
+def test_tpp_nonfinite_inputs_weights_and_standstill(capi, oracle):
+    """Non-finite inputs end with a status (never a hang), the same one as the oracle's; custom weights and v_des;
+    the standstill start on the bound v_min (vehicle_simulator.py:31); v_des NULL."""
+    N, B = 8, 96
+    s = capi.Solver(N)
+    s.set_large_batch_path(1)
+    b = W.make_batch(B, N)
+    st = b["state"].copy(); rf = b["ref"].copy(); up = b["u_prev"].copy()
+    st[0, 0] = np.nan; st[1, 3] = np.inf; rf[2, 0, 3] = np.nan; up[3, 1] = np.nan
+    g = s.solve_batch(st, rf, up, v_des=b["v_des"])
+    o = oracle.solve_batch(_ocfg(oracle, s), st, rf, b["v_des"], up, n_threads=4)
+    assert (g["status"] == o["status"]).all() and (g["status"][:4] != capi.OPTIMAL).all()
+    assert (g["iters"][:4] == o["iters"][:4]).all()
+    _compare({k: v[4:] for k, v in g.items() if v is not None}, {k: v[4:] for k, v in o.items() if k in ("u0", "cost", "status")})
+    # weights and a desired speed
+    w = [5.0, 7.0, 20.0, 3.0, 50.0, 500.0, 0.5, 2.0]
+    s.set_cost(w)
+    b2 = W.make_batch(B, N, v_des=6.0)
+    g = s.solve_batch(b2["state"], b2["ref"], b2["u_prev"], v_des=b2["v_des"])
+    o = oracle.solve_batch(oracle.default_cfg(N, weights=w, max_iter=s.cfg.max_iter), b2["state"], b2["ref"], b2["v_des"], b2["u_prev"], n_threads=8)
+    _compare(g, o, min_conv=0.8)
+    # standstill, v_des NULL
+    s3 = capi.Solver(N)
+    s3.set_large_batch_path(1)
+    b3 = W.make_batch(B, N, path_ids=(3,))
+    st = b3["state"].copy(); st[:, 3] = 0.0
+    up = np.zeros((B, 2))
+    g = s3.solve_batch(st, b3["ref"], up)
+    o = oracle.solve_batch(_ocfg(oracle, s3), st, b3["ref"], None, up, n_threads=4)
+    _compare(g, o, min_conv=0.5)
