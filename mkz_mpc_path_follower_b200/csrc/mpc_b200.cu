@@ -119,6 +119,92 @@ mpc_solve_tpp_kernel(const KCfg cfg, const BatchPtrs io, const long long B, doub
     }
 }
 
+// ---- Closed-loop fleets with the thread-per-problem layout: one control period = three launches over the whole fleet
+// instead of one persistent kernel that carries four vehicles per block through all their periods.
+//   plant      thread = vehicle: the ten 100 Hz publishes of ten Euler sub-steps (vehicle_simulator.py:58-112): every lane of a
+//              warp integrates its own vehicle (in mpc_rollout_kernel one warp per block does it for four while three wait)
+//   waypoints  warp = vehicle: get_waypoints (ref_gps_traj.py:131-218) written straight into the vehicle's slot of the solver state
+//   solve      thread = vehicle: the slot still holds the previous solution = the warm start (mpc_cmd_pub.jl:115-141), all
+//              vehicles start together and take about the same handful of iterations, which is where this layout is at its best
+// Vehicle state is structure-of-arrays [12][Bp]: X Y psi vx vy wz acc df | acc_des df_des | d_f_current acc_current.
+#define RV_NF 12
+__global__ void __launch_bounds__(128)
+rollout_plant_kernel(const long long B, const long long Bp, double* veh, const double* pose0, const int first) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    double st[8], ad, dd;
+    if (first) {
+        st[0] = pose0[3 * v]; st[1] = pose0[3 * v + 1]; st[2] = pose0[3 * v + 2];
+        for (int i = 3; i < 8; i++) st[i] = 0.0;
+        ad = 0.0; dd = 0.0;
+        veh[8 * Bp + v] = 0.0; veh[9 * Bp + v] = 0.0; veh[10 * Bp + v] = 0.0; veh[11 * Bp + v] = 0.0;
+    } else {
+        for (int i = 0; i < 8; i++) st[i] = veh[i * Bp + v];
+        ad = veh[8 * Bp + v]; dd = veh[9 * Bp + v];
+    }
+    MPC_NOUNROLL for (int i = 0; i < 10; i++) plant_step(st, ad, dd);
+    for (int i = 0; i < 8; i++) veh[i * Bp + v] = st[i];
+}
+
+__global__ void __launch_bounds__(128)
+rollout_waypoints_kernel(const KCfg cfg, const long long B, const long long Bp, const double* veh, const int* path_of, const RefGen rg,
+                         double* tpp_state, double* tpp_filt, int* stop, const int first) {
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    TeamSolver<1> S(cfg, (smem_t)0);   // (one-warp teams use no shared memory in get_waypoints)
+    for (long long v = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < B; v += warps) {
+        if (first && lane == 0) stop[v] = 0;
+        if (!first && stop[v]) continue;   // the stop latch (mpc_cmd_pub.jl:102-111): no more solves, no more references
+        double xr, yr, pr;
+        const bool sc = S.get_waypoints(rg.paths[path_of[v]], cfg.dt, veh[v], veh[Bp + v], veh[2 * Bp + v], !rg.track_using_time, rg.target_vel, xr, yr, pr);
+        if (lane <= cfg.N) {
+            const TppMem mem(tpp_state, tpp_filt, cfg.N, (long)v);
+            mem.sto(TF_XR, lane, xr); mem.sto(TF_YR, lane, yr); mem.sto(TF_PR, lane, pr);
+        }
+        if (sc && lane == 0) stop[v] = 1;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(MPC_TPP_BLOCK, MPC_TPP_MIN_BLOCKS)
+rollout_solve_tpp_kernel(const KCfg cfg, const long long B, const long long Bp, double* veh, const int* stop, double* tpp_state, double* tpp_filt,
+                         const double* warm0, const double des_speed, BatchPtrs out, double* log_row) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = v < B;
+    const TppMem mem(tpp_state, tpp_filt, cfg.N, (long)(valid ? v : 0));
+    TppSolver sv(cfg, mem);
+    const bool stopped = valid && stop[v] != 0;
+    bool live = valid && !stopped;
+    double st4[4] = {0.0, 0.0, 0.0, 0.0};
+    if (valid) for (int i = 0; i < 4; i++) st4[i] = veh[i * Bp + v];
+    if (live) {
+        const double c7[7] = {st4[0], st4[1], st4[2], st4[3], veh[10 * Bp + v], veh[11 * Bp + v], des_speed};
+        sv.begin_in_place(c7, warm0);
+    }
+    bool solved = false;
+    while (__syncthreads_or(live)) {
+        const bool done = sv.tick(live);
+        if (live && done) { sv.finish(out, (long)v); live = false; solved = true; }
+    }
+    if (!valid) return;
+    double acc_des = -1.0, df_des = 0.0, status = -1.0, iters = 0.0;   // stopped: mpc_cmd_pub.jl:148-153
+    if (solved) {
+        acc_des = out.u0[2 * v]; df_des = out.u0[2 * v + 1]; status = (double)out.status[v]; iters = (double)out.iters[v];
+        veh[10 * Bp + v] = df_des; veh[11 * Bp + v] = acc_des;   // update_current_input(df_opt, a_opt) (:140)
+    }
+    veh[8 * Bp + v] = acc_des; veh[9 * Bp + v] = df_des;         // published whatever the status (:129-132)
+    if (log_row) {
+        double* r = log_row + 8 * v;
+        r[0] = st4[0]; r[1] = st4[1]; r[2] = st4[2]; r[3] = st4[3]; r[4] = acc_des; r[5] = df_des; r[6] = status; r[7] = iters;
+    }
+}
+
+__global__ void rollout_final_kernel(const long long B, const long long Bp, const double* veh, double* final_state) {
+    const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= B) return;
+    for (int i = 0; i < 8; i++) final_state[8 * v + i] = veh[i * Bp + v];
+}
+
 #ifndef MPC_ROLLOUT_MIN_BLOCKS
 #define MPC_ROLLOUT_MIN_BLOCKS 3
 #endif
@@ -213,7 +299,8 @@ struct mpcb200_handle {
     int* d_roles = nullptr;   /* lane roles of the Riccati recursion for this horizon (riccati_roles) */
     DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
     DevBuf d_path[3], d_pose, d_pathof, d_log, d_final, d_stop;
-    DevBuf d_tpp_state, d_tpp_filt;   /* thread-per-problem path: slot state [field][stage][slot], filters */
+    DevBuf d_tpp_state, d_tpp_filt;   /* thread-per-problem path: slot state [warp][stage][field][lane], filters */
+    DevBuf d_veh, d_vstop;            /* ... closed-loop fleets: vehicle state [12][Bp], stop latches */
     int tpp_blocks_per_sm = 0;        /* resident blocks of mpc_solve_tpp_kernel per SM */
     int tpp_block = MPC_TPP_BLOCK;    /* threads per block of mpc_solve_tpp_kernel (a multiple of 32, <= MPC_TPP_BLOCK) */
     int64_t tpp_min_batch = 0;        /* batches of at least this many problems take the thread-per-problem path (0: never) */
@@ -494,7 +581,7 @@ int mpcb200_destroy(mpcb200_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj,
                       &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop, &h->d_stage,
-                      &h->d_rec, &h->d_resto, &h->d_seed, &h->d_fit, &h->d_tpp_state, &h->d_tpp_filt};
+                      &h->d_rec, &h->d_resto, &h->d_seed, &h->d_fit, &h->d_tpp_state, &h->d_tpp_filt, &h->d_veh, &h->d_vstop};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_roles) cudaFree(h->d_roles);
@@ -1011,6 +1098,50 @@ static int rollout_enqueue(mpcb200_handle* h, int64_t n, int32_t T, const double
     a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel;
     a.log = want_log ? (double*)h->d_log.p : nullptr; a.final_state = want_final ? (double*)h->d_final.p : nullptr; a.B = (long)n;
     a.warm0 = (const double*)h->d_seed.p;
+    /* large fleets at short horizons: one control period = plant / waypoints / thread-per-problem solve over the whole fleet
+     * (warm-started solves: the batch rule for warm starts, half the cold-start threshold) */
+    const int64_t roll_from = h->tpp_default_rule ? h->tpp_min_batch / 2 : h->tpp_min_batch;
+    if (h->tpp_min_batch > 0 && n >= roll_from) {
+        const long long Bp = (n + 31) / 32 * 32;
+        const int tb = h->tpp_block;
+        const long long sblocks = (n + tb - 1) / tb, S = sblocks * tb;
+        if ((rc = ensure(h, h->d_tpp_state, tpp_state_doubles(h->cfg.N, (long)S) * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_tpp_filt, tpp_filter_doubles((long)S) * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_veh, (size_t)RV_NF * Bp * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_vstop, (size_t)Bp * sizeof(int)))) return rc;
+        if ((rc = ensure(h, h->d_u0, (size_t)n * 2 * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_status, (size_t)n * sizeof(int32_t)))) return rc;
+        if ((rc = ensure(h, h->d_iters, (size_t)n * sizeof(int32_t)))) return rc;
+        BatchPtrs out;
+        memset(&out, 0, sizeof(out));
+        out.u0 = (double*)h->d_u0.p; out.status = (int*)h->d_status.p; out.iters = (int*)h->d_iters.p;
+        RefGen rg;
+        memset(&rg, 0, sizeof(rg));
+        fill_paths(h, rg.paths);
+        rg.track_using_time = track_using_time;
+        const double des_speed = target_vel > 0.0 ? target_vel : 0.0;   /* mpc_cmd_pub.jl:58-62 */
+        rg.target_vel = des_speed;
+        const KCfg kc = make_kcfg(h);
+        double* veh = (double*)h->d_veh.p;
+        const int pgrid = (int)((n + 127) / 128);
+        long long wblocks = (n + 3) / 4, wmax = (long long)h->num_sms * 16;
+        const int wgrid = (int)(wblocks < wmax ? wblocks : wmax);
+        CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+        for (int t = 0; t < T; t++) {
+            rollout_plant_kernel<<<pgrid, 128, 0, s>>>((long long)n, Bp, veh, a.pose0, t == 0);
+            rollout_waypoints_kernel<<<wgrid, 128, 0, s>>>(kc, (long long)n, Bp, veh, a.path_of, rg, (double*)h->d_tpp_state.p, (double*)h->d_tpp_filt.p,
+                                                          (int*)h->d_vstop.p, t == 0);
+            rollout_solve_tpp_kernel<<<(int)sblocks, tb, 0, s>>>(kc, (long long)n, Bp, veh, (const int*)h->d_vstop.p, (double*)h->d_tpp_state.p,
+                                                                (double*)h->d_tpp_filt.p, t == 0 ? a.warm0 : nullptr, des_speed, out,
+                                                                a.log ? a.log + (size_t)t * n * 8 : nullptr);
+            CUDA_TRY(h, cudaGetLastError());
+        }
+        if (a.final_state) rollout_final_kernel<<<pgrid, 128, 0, s>>>((long long)n, Bp, veh, a.final_state);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+        h->stats.kernel_launches += 3 * (int64_t)T + (a.final_state ? 1 : 0);
+        return MPCB200_OK;
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), s));
     const int per_block = (h->team_warps == 1) ? WARPS_PER_BLOCK : 1;
     long long blocks_needed = (n + per_block - 1) / per_block;

@@ -156,11 +156,30 @@ struct TppSolver {
             for (int k = 0; k < N; k++) { m.sto(TF_UA, k, cst[5]); m.sto(TF_UD, k, cst[4]); }
             rollout_restore();
         }
-        // ---- TeamSolver::solve prologue
+        prologue();
+    }
+
+    // A problem whose reference samples are already in the slot (written by the waypoint kernel of a closed-loop step) and
+    // whose start point is either `warm0` ([6N+4], the layout of BatchPtrs::warm) or whatever the slot holds -- the
+    // previous solution of the same vehicle: the control loop's warm start without moving a byte.
+    MPC_DEV void begin_in_place(const double c7[7], const double* warm0) {
+        for (int i = 0; i < 7; i++) cst[i] = c7[i];
+        if (warm0) {
+            for (int k = 0; k <= N; k++) {
+                m.sto(TF_SX, k, warm0[k]); m.sto(TF_SY, k, warm0[(N + 1) + k]);
+                m.sto(TF_SV, k, warm0[2 * (N + 1) + k]); m.sto(TF_SP, k, warm0[3 * (N + 1) + k]);
+                m.sto(TF_UD, k, (k < N) ? warm0[4 * (N + 1) + k] : 0.0); m.sto(TF_UA, k, (k < N) ? warm0[4 * (N + 1) + N + k] : 0.0);
+            }
+        }
+        prologue();
+    }
+
+    // TeamSolver::solve's prologue: feasibility of the NLP, objective scaling from the gradient at the start point, driver reset
+    MPC_DEV void prologue() {
         feasible = nlp_feasible();
         ret = feasible ? RUNNING : 2;
         sigma = 1.0;
-        {   // objective scaling from the gradient at the user's start point
+        {
             double gm = 0.0, pa = 0.0, pd = 0.0;
             double ua = m.ld(TF_UA, 0), ud = m.ld(TF_UD, 0);
             for (int k = 0; k <= N; k++) {

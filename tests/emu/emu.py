@@ -116,9 +116,10 @@ def solve_batch_frenet(kcfg, state, kpoly, v_des, u_prev, warm=None, want_traj=F
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj}
 
 
-def rollout(kcfg, traj_table, pose0, T, track_using_time=True, target_vel=1.0, warm0=None):
+def rollout(kcfg, traj_table, pose0, T, track_using_time=True, target_vel=1.0, warm0=None, tpp=False):
     """All vehicles on the path whose (n,7) table is given.  warm0 (6N+4,): start point of the first solve (None = zeros).
-    Horizons above 31 run one emulated block of 2-3 warps per vehicle.  Returns log (T,B,8), final (B,8)."""
+    Horizons above 31 run one emulated block of 2-3 warps per vehicle.  tpp: the plant / waypoints / thread-per-problem-solve
+    pipeline mpcb200_rollout uses for large fleets instead of the fused kernel.  Returns log (T,B,8), final (B,8)."""
     lib = C.CDLL(build())
     dp = C.POINTER(C.c_double)
     pose0 = np.ascontiguousarray(np.atleast_2d(pose0), dtype=np.float64)
@@ -126,10 +127,11 @@ def rollout(kcfg, traj_table, pose0, T, track_using_time=True, target_vel=1.0, w
     cols = [np.ascontiguousarray(traj_table[:, i]) for i in (0, 4, 5, 3, 6)]
     path_of = np.zeros(B, dtype=np.int32)
     log = np.zeros((T, B, 8)); final = np.zeros((B, 8))
-    lib.emu_rollout.argtypes = [C.POINTER(KCfg), C.c_long, C.c_int, dp, C.POINTER(C.c_int), C.c_int, dp, dp, dp, dp, dp,
-                                C.c_int, C.c_double, dp, dp, dp]
+    fn = lib.emu_rollout_tpp if tpp else lib.emu_rollout
+    fn.argtypes = [C.POINTER(KCfg), C.c_long, C.c_int, dp, C.POINTER(C.c_int), C.c_int, dp, dp, dp, dp, dp,
+                   C.c_int, C.c_double, dp, dp, dp]
     w0 = None if warm0 is None else np.ascontiguousarray(warm0, dtype=np.float64)
-    lib.emu_rollout(C.byref(kcfg), B, T, pose0.ctypes.data_as(dp), path_of.ctypes.data_as(C.POINTER(C.c_int)), traj_table.shape[0],
+    fn(C.byref(kcfg), B, T, pose0.ctypes.data_as(dp), path_of.ctypes.data_as(C.POINTER(C.c_int)), traj_table.shape[0],
                     *[c.ctypes.data_as(dp) for c in cols], int(track_using_time), float(target_vel),
                     log.ctypes.data_as(dp), final.ctypes.data_as(dp), None if w0 is None else w0.ctypes.data_as(dp))
     return log, final

@@ -266,3 +266,62 @@ extern "C" int emu_solve_batch_tpp(const KCfg* cfg, long B, const double* state,
     }
     return 0;
 }
+
+// closed loop with the thread-per-problem solve, as mpcb200_rollout runs it for large fleets (plant / waypoints / solve per
+// control period; csrc/mpc_b200.cu: rollout_plant_kernel, rollout_waypoints_kernel, rollout_solve_tpp_kernel), vehicle by vehicle
+struct WJob { const KCfg* cfg; const PathTable* path; double X, Y, yaw; int use_vt; double vt; TppMem* mem; int stop; };
+static void lane_waypoints(int lane, void* p) {
+    WJob* j = (WJob*)p;
+    TeamSolver<1> S(*j->cfg, (smem_t) nullptr);
+    double xr, yr, pr;
+    const bool sc = S.get_waypoints(*j->path, j->cfg->dt, j->X, j->Y, j->yaw, j->use_vt != 0, j->vt, xr, yr, pr);
+    if (lane <= j->cfg->N) { j->mem->sto(TF_XR, lane, xr); j->mem->sto(TF_YR, lane, yr); j->mem->sto(TF_PR, lane, pr); }
+    if (sc && lane == 0) j->stop = 1;
+}
+extern "C" int emu_rollout_tpp(const KCfg* cfg, long B, int T, const double* pose0, const int* path_of, int n0, const double* t,
+                               const double* X, const double* Y, const double* psi, const double* s, int track_using_time,
+                               double target_vel, double* log, double* final_state, const double* warm0) {
+    KCfg kc = *cfg;
+    kcfg_finalize(kc);
+    PathTable path;
+    path.n = n0; path.t = t; path.X = X; path.Y = Y; path.psi = psi; path.s = s;
+    (void)path_of;   // (the emulator gets one path table, like emu_rollout)
+    const double des_speed = target_vel > 0.0 ? target_vel : 0.0;
+    const long S = 40;
+    std::vector<double> st(tpp_state_doubles(kc.N, S), 0.0 / 0.0), filt(tpp_filter_doubles(S), 0.0 / 0.0);
+    std::vector<double> u0(2 * B); std::vector<int> status(B), iters(B);
+    BatchPtrs out;
+    memset(&out, 0, sizeof(out));
+    out.u0 = u0.data(); out.status = status.data(); out.iters = iters.data();
+    for (long v = 0; v < B; v++) {
+        TppMem m(st.data(), filt.data(), kc.N, v % S);
+        double veh[8] = {pose0[3 * v], pose0[3 * v + 1], pose0[3 * v + 2], 0, 0, 0, 0, 0};
+        double acc_des = 0.0, df_des = 0.0, up_d = 0.0, up_a = 0.0;
+        int stop = 0;
+        for (int step = 0; step < T; step++) {
+            for (int i = 0; i < 10; i++) plant_step(veh, acc_des, df_des);
+            double status_f = -1.0, iters_f = 0.0;
+            if (!stop) {
+                WJob j{&kc, &path, veh[0], veh[1], veh[2], !track_using_time, des_speed, &m, 0};
+                emu::race_reset();
+                emu::run_warp(lane_waypoints, &j, 1);
+                stop = j.stop;
+            }
+            if (!stop) {
+                TppSolver sv(kc, m);
+                const double c7[7] = {veh[0], veh[1], veh[2], veh[3], up_d, up_a, des_speed};
+                sv.begin_in_place(c7, step == 0 ? warm0 : nullptr);
+                while (!sv.tick(true)) {}
+                sv.finish(out, v);
+                acc_des = u0[2 * v]; df_des = u0[2 * v + 1]; status_f = status[v]; iters_f = iters[v];
+                up_d = df_des; up_a = acc_des;
+            } else { acc_des = -1.0; df_des = 0.0; }
+            if (log) {
+                double* r = log + ((size_t)step * B + v) * 8;
+                r[0] = veh[0]; r[1] = veh[1]; r[2] = veh[2]; r[3] = veh[3]; r[4] = acc_des; r[5] = df_des; r[6] = status_f; r[7] = iters_f;
+            }
+        }
+        if (final_state) for (int i = 0; i < 8; i++) final_state[8 * v + i] = veh[i];
+    }
+    return 0;
+}

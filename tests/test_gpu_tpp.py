@@ -201,3 +201,45 @@ def test_tpp_nonfinite_inputs_weights_and_standstill(capi, oracle):
     g = s3.solve_batch(st, b3["ref"], up)
     o = oracle.solve_batch(_ocfg(oracle, s3), st, b3["ref"], None, up, n_threads=4)
     _compare(g, o, min_conv=0.5)
+
+
+def test_tpp_closed_loop_fleet(capi, oracle):
+    """mpcb200_rollout with the per-period pipeline (plant / waypoints / thread-per-problem solve over the whole fleet) against
+    the fused rollout kernel on the same fleet, and a few vehicles against the oracle's closed loop."""
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    N, B, T = 8, 700, 40
+    trajs = [GPSRefTrajectory(mat_filename=p) for p in (1, 2, 3)]
+    rng = np.random.default_rng(21)
+    path_of = (np.arange(B) % 3).astype(np.int32)
+    pose0 = np.stack([trajs[p].trajectory[(37 * (i + 1)) % (trajs[p].trajectory.shape[0] - 200), [4, 5, 3]] + rng.normal(scale=[0.3, 0.3, 0.03])
+                      for i, p in enumerate(path_of)])
+    pose0[5] = trajs[path_of[5]].trajectory[-30, [4, 5, 3]]      # runs into the stop latch
+    out = {}
+    for name, mb in (("warp", 0), ("tpp", 1)):
+        s = capi.Solver(N)
+        s.set_large_batch_path(mb)
+        for i, g in enumerate(trajs):
+            s.set_path(i, g.trajectory)
+        out[name] = s.rollout(pose0, path_of, T)
+        out[name + "_launches"] = s.stats()["kernel_launches"]
+    assert out["warp_launches"] == 1 and out["tpp_launches"] == 3 * T + 1
+    lw, lt = out["warp"]["log"], out["tpp"]["log"]
+    assert np.array_equal(lw[:, :, 6], lt[:, :, 6])                       # statuses (and the stop latch: -1)
+    assert (lw[:, :, 7] == lt[:, :, 7]).mean() >= 0.999                   # iteration counts
+    # Vehicles that keep driving agree to rounding.  A vehicle behind the stop latch brakes to a standstill, where the plant is
+    # discontinuous (vehicle_simulator.py:77,88-89: slip angles and lateral dynamics switch off at vx <= 1e-6, vx is clamped at
+    # 0): differences of 1e-15 before that point come out as ~1e-6 in the resting pose.
+    d = np.abs(lw[:, :, 0:6] - lt[:, :, 0:6]).max(axis=(0, 2))
+    same = (lw[:, :, 7] == lt[:, :, 7]).all(axis=0)
+    driving = (lt[:, :, 6] != -1).all(axis=0)
+    print("closed loop: max |warp - tpp| %.2e over the %d vehicles that keep driving, %.2e over the %d that stop" %
+          (d[driving].max(), driving.sum(), d[~driving].max() if (~driving).any() else 0.0, (~driving).sum()))
+    assert same.mean() >= 0.97 and d[driving & same].max() <= 1e-8 and d.max() <= 1e-4 and driving.sum() >= B // 2
+    assert np.abs(out["warp"]["final_state"] - out["tpp"]["final_state"]).max() <= 1e-4
+    assert (lt[:, 5, 6] == -1).any() and (lt[-1, 5, 4:6] == [-1.0, 0.0]).all()
+    cfg = _ocfg(oracle, s)
+    for b in (0, 1, 2, 5, 333):
+        path, keep = oracle.make_path(trajs[path_of[b]].trajectory)
+        olog = oracle.closed_loop(cfg, path, pose0[b], T)
+        assert np.array_equal(lt[:, b, 6], olog[:, 6]), b
+        assert np.abs(lt[:, b, 0:6] - olog[:, 0:6]).max() <= (1e-8 if np.array_equal(lt[:, b, 7], olog[:, 7]) else 1e-4), b

@@ -98,3 +98,29 @@ def test_thread_per_problem_edge_cases(oracle):
     assert o["n_resto"].sum() > 0 and (o["n_resto"] == e["n_resto"]).all()
     r = o["n_resto"] > 0
     assert (o["status"][r] == e["status"][r]).all() and np.abs(o["u0"] - e["u0"])[r & (o["status"] == 0)].max() <= 1e-7
+
+
+def test_thread_per_problem_closed_loop(oracle):
+    """The closed loop as mpcb200_rollout runs it for large fleets: per control period the plant, get_waypoints written into the
+    vehicle's slot of the solver state, and the thread-per-problem solve warm-started from what the slot still holds.  Against
+    the oracle's closed loop (plant, reference generation, warm-started solves, command feedback, stop latch), a vehicle that
+    reaches the end of the path included, and against the fused rollout kernel's source."""
+    import emu as E
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    g = GPSRefTrajectory(mat_filename=1)
+    cfg = oracle.default_cfg(8)
+    rng = np.random.default_rng(3)
+    n = g.trajectory.shape[0]
+    poses = np.array([g.trajectory[j, [4, 5, 3]] + rng.normal(scale=[0.3, 0.3, 0.03]) for j in (0, 900, 2500, 4000, 5200, n - 40)])
+    T = 12
+    seed = oracle.module_load_solution(cfg)
+    log, final = E.rollout(E.kcfg_from_oracle(cfg), g.trajectory, poses, T, warm0=seed, tpp=True)
+    path, keep = oracle.make_path(g.trajectory)
+    for b in range(poses.shape[0]):
+        olog = oracle.closed_loop(cfg, path, poses[b], T)
+        assert np.array_equal(log[:, b, 6], olog[:, 6]) and np.array_equal(log[:, b, 7], olog[:, 7]), b
+        assert np.abs(log[:, b, 4:6] - olog[:, 4:6]).max() <= 1e-9, b
+        assert np.abs(log[:, b, 0:4] - olog[:, 0:4]).max() <= 1e-9, b
+    assert (log[:, -1, 6] == -1).any() and (log[-1, -1, 4:6] == [-1.0, 0.0]).all()     # the last vehicle ran into the stop latch
+    wlog, wfinal = E.rollout(E.kcfg_from_oracle(cfg), g.trajectory, poses, T, warm0=seed)
+    assert np.array_equal(log[:, :, 6:8], wlog[:, :, 6:8]) and np.abs(log - wlog).max() <= 1e-9 and np.abs(final - wfinal).max() <= 1e-9
