@@ -104,7 +104,11 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
  *   min_batch  > 0: batches (per device) of at least min_batch problems use one thread per problem
  *   min_batch == 0: always one warp per problem
  *   min_batch  < 0: the default rule (N <= 10: 32,768, and 16,384 for warm-started or rollout-started batches, whose
- *                   solves all take about the same handful of iterations; N > 10: never), what a new handle starts with */
+ *                   solves all take about the same handful of iterations; N > 10: never), what a new handle starts with
+ * mpcb200_rollout follows the same switch: fleets of at least min_batch vehicles per device (default rule: 8,192 at N <= 10) run
+ * each control period as three launches over the whole fleet -- plant, waypoints, thread-per-problem solve warm-started in place
+ * -- instead of one persistent kernel (16,384 vehicles x 500 periods: 0.67 s instead of 1.26 s; 65,536 x 100: 0.38 s instead of
+ * 1.39 s). */
 int mpcb200_set_large_batch_path(mpcb200_handle* h, int64_t min_batch);
 
 /*

@@ -1098,12 +1098,16 @@ static int rollout_enqueue(mpcb200_handle* h, int64_t n, int32_t T, const double
     a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel;
     a.log = want_log ? (double*)h->d_log.p : nullptr; a.final_state = want_final ? (double*)h->d_final.p : nullptr; a.B = (long)n;
     a.warm0 = (const double*)h->d_seed.p;
-    /* large fleets at short horizons: one control period = plant / waypoints / thread-per-problem solve over the whole fleet
-     * (warm-started solves: the batch rule for warm starts, half the cold-start threshold) */
-    const int64_t roll_from = h->tpp_default_rule ? h->tpp_min_batch / 2 : h->tpp_min_batch;
+    /* large fleets at short horizons: one control period = plant / waypoints / thread-per-problem solve over the whole fleet.
+     * Measured at N = 8, 200 periods (profiles/r02_logs/r02_rollout_thresholds.log): a period of the pipeline takes ~0.9 ms up to
+     * 8,192 vehicles (the slowest vehicle's dozen solver trips) and grows slowly after that, the fused kernel takes 0.5 / 0.8 /
+     * 1.4 / 2.5 ms at 2,048 / 4,096 / 8,192 / 16,384 vehicles: the default rule switches at a quarter of the cold-start batch */
+    const int64_t roll_from = h->tpp_default_rule ? h->tpp_min_batch / 4 : h->tpp_min_batch;
     if (h->tpp_min_batch > 0 && n >= roll_from) {
         const long long Bp = (n + 31) / 32 * 32;
-        const int tb = h->tpp_block;
+        /* blocks of 128 vehicles (two resident per SM): every vehicle solves at once and a block keeps its vehicles, so smaller
+         * blocks mean less idle SMs in the last wave (16,384 vehicles: 0.89 instead of 1.07 ms per period; never slower) */
+        const int tb = h->tpp_block < 128 ? h->tpp_block : 128;
         const long long sblocks = (n + tb - 1) / tb, S = sblocks * tb;
         if ((rc = ensure(h, h->d_tpp_state, tpp_state_doubles(h->cfg.N, (long)S) * sizeof(double)))) return rc;
         if ((rc = ensure(h, h->d_tpp_filt, tpp_filter_doubles((long)S) * sizeof(double)))) return rc;
