@@ -485,6 +485,17 @@ def main():
         out = sv.rollout(pose0[lo:hi], path_of[lo:hi], T)
         wall = allmax(time.perf_counter() - tq)
         kms = allmax(sv.stats()["kernel_ms"])
+        launches = sv.stats()["kernel_launches"]
+        fused = None
+        if launches > 1 and rank == 0 and world == 1:
+            # the library ran the per-period pipeline (plant / waypoints / thread-per-problem solve): the fused kernel beside it
+            sv.set_large_batch_path(0)
+            tq2 = time.perf_counter()
+            out_f = sv.rollout(pose0[lo:hi], path_of[lo:hi], T)
+            fused = {"wall_s": time.perf_counter() - tq2, "kernel_ms": sv.stats()["kernel_ms"], "kernel": "mpc_rollout_kernel",
+                     "statuses_equal": bool(np.array_equal(out_f["log"][:, :, 6], out["log"][:, :, 6])),
+                     "max_abs_diff_driving_vehicles": float(np.abs(out_f["log"][:, :, 0:6] - out["log"][:, :, 0:6])[:, (out["log"][:, :, 6] != -1).all(axis=0), :].max())}
+            sv.set_large_batch_path(-1)
         log = out["log"]
         solved = log[:, :, 6] >= 0
         err = np.zeros(hi - lo)
@@ -499,6 +510,8 @@ def main():
         sv.close()
         return {"what": "configs[3]: %d vehicles x %d control steps (N=8, paths 1-3, warm-started solve each step) through "
                         "mpcb200_rollout, fleet sharded over %d GPU(s)" % (V, T, world), "scaling": "strong",
+                "kernels": ("rollout_plant_kernel + rollout_waypoints_kernel + rollout_solve_tpp_kernel per control period" if launches > 1
+                            else "mpc_rollout_kernel (one persistent launch)"), "kernel_launches": int(launches), "fused_kernel_for_comparison": fused,
                 "wall_s": wall, "kernel_ms": kms, "solves": n_solved, "solves_per_s": n_solved / wall,
                 "vehicle_steps_per_s": V * T / wall, "optimal_frac": n_opt / max(1.0, n_solved), "mean_iters": n_it / max(1.0, n_solved),
                 "final_path_error_m": {"median": float(np.median(err)), "p99": float(np.quantile(err, 0.99))}}
