@@ -391,8 +391,9 @@ def test_multi_device_handle(capi):
         assert np.array_equal(o1[k], om[k]), k
 
 
+@pytest.mark.parametrize("layout", ["warp", "thread"])
 @pytest.mark.parametrize("N,B,start", [(8, 48, "zero"), (20, 48, "zero"), (40, 12, "ref")])
-def test_kkt_of_cuda_solutions(capi, oracle, N, B, start):
+def test_kkt_of_cuda_solutions(capi, oracle, N, B, start, layout):
     """Intrinsic check that does not involve the oracle's interior-point code: every Optimal point the
     CUDA solver returns satisfies the KKT conditions of the UNSCALED reference NLP (stationarity with
     least-squares multipliers on the active set, primal feasibility, multiplier signs).  The N = 20
@@ -400,6 +401,9 @@ def test_kkt_of_cuda_solutions(capi, oracle, N, B, start):
     import ctypes as C
     from test_oracle_solver import _kkt_residual, _p
     s = capi.Solver(N)
+    s.set_large_batch_path(0 if layout == "warp" else 1)     # both device layouts of the solver (the second: csrc/tpp_solver.cuh)
+    if layout == "thread":
+        B += 64                                              # (host batches of up to 64 problems always take the small-batch path)
     b = W.make_batch(B, N, b0=30 if N == 20 else 0)     # problems 38, 62 of the stream need a restoration
     warm = W.reference_start(b, N) if start == "ref" else None
     g = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"], warm=warm, want_traj=True)
