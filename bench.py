@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--horizon", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="problems in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--sweep-batch", type=int, default=131072, help="problems per GPU and horizon of the horizon_sweep key (configs[4]: 1 M over 8 GPUs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the configs beside the headline (config1, rollout_config3, horizon_sweep, strong_64k, layouts_n8)")
     ap.add_argument("--parity", default="full", choices=["full", "sample"],
                     help="full: every problem of every rank's slice is checked against the oracle (the converged count); sample: a bounded sample")
@@ -520,19 +521,25 @@ def main():
     # (with its converged fraction inside the iteration cap) and from MPCB200_START_ROLLOUT (opt-in)
     def horizon_sweep():
         res = {}
-        for Nh, Bh in ((8, 65536), (40, 16384), (80, 8192)):
+        Bh = args.sweep_batch     # configs[4]: 1 M problems over 8 GPUs = 131,072 per GPU, at every horizon
+        for Nh in (8, 40, 80):
             row = {"batch_per_gpu": Bh}
+            bb = workload.make_batch(Bh, Nh, b0=rank * Bh)
             for nm, mode in (("zero_start", capi.START_ZERO), ("rollout_start", capi.START_ROLLOUT)):
-                bb, ms, uu, cc, ss, ii, rr = timed_device_solve(Nh, Bh, mode, reps=1, b0=rank * Bh)
+                _, ms, uu, cc, ss, ii, rr = timed_device_solve(Nh, Bh, mode, reps=1, bb=bb)
                 conv, nit = allsum([float((ss == 0).sum()), float(ii.sum())])
                 msx = allmax(ms)
-                row[nm] = {"kernel": "mpc_solve_tpp_kernel" if (Nh <= 10 and Bh >= 32768) else ("mpc_solve_kernel" if Nh <= 31 else "mpc_solve_long_kernel"),
+                tpp = Nh <= 10 and Bh >= (16384 if mode == capi.START_ROLLOUT else 32768)     # the library's default rule
+                row[nm] = {"kernel": "mpc_solve_tpp_kernel" if tpp else ("mpc_solve_kernel" if Nh <= 31 else "mpc_solve_long_kernel"),
                            "kernel_ms": msx, "converged_frac": conv / (world * Bh), "mean_iters": nit / (world * Bh),
                            "value": conv / (msx * 1e-3), "unit": "converged solves/s", "max_iter": 200,
                            "fp64_tflops": nit * (F_RIC + F_EVAL) * Nh / (msx * 1e-3) / 1e12}
             res["N%d" % Nh] = row
-        res["what"] = ("configs[4] per GPU (weak): all-zero start = the reference's start=0.0, converged fraction inside the "
-                       "200-iteration cap; rollout start = MPCB200_START_ROLLOUT (opt-in, not a reference behaviour)")
+            del bb
+        res["what"] = ("configs[4] per GPU (weak; 131,072 per GPU = 1 M problems on 8 GPUs): all-zero start = the reference's start=0.0, "
+                       "converged fraction inside the library's 200-iteration cap (under Ipopt's own cap of 3000 every problem converges at "
+                       "N = 40 and N = 80: tools/long_horizon_cap.py, DESIGN 5); rollout start = MPCB200_START_ROLLOUT (opt-in, not a "
+                       "reference behaviour)")
         return res
 
     # the two device layouts of the solver on large batches at the reference's own horizon (N = 8): one warp per problem
