@@ -237,6 +237,24 @@ def test_tpp_closed_loop_fleet(capi, oracle):
     assert same.mean() >= 0.97 and d[driving & same].max() <= 1e-8 and d.max() <= 1e-4 and driving.sum() >= B // 2
     assert np.abs(out["warp"]["final_state"] - out["tpp"]["final_state"]).max() <= 1e-4
     assert (lt[:, 5, 6] == -1).any() and (lt[-1, 5, 4:6] == [-1.0, 0.0]).all()
+    # distance mode (track_with_time = false, mpc_cmd_pub.jl:99-101), a target speed, no log, non-positive target speed
+    res = {}
+    for name, mb in (("warp", 0), ("tpp", 1)):
+        s2 = capi.Solver(N)
+        s2.set_large_batch_path(mb)
+        for i, g in enumerate(trajs):
+            s2.set_path(i, g.trajectory)
+        res[name] = (s2.rollout(pose0[:200], path_of[:200], 25, track_using_time=False, target_vel=6.5),
+                     s2.rollout(pose0[:200], path_of[:200], 10, track_using_time=False, target_vel=-2.0),
+                     s2.rollout(pose0[:200], path_of[:200], 10, track_using_time=False, target_vel=6.5, want_log=False))
+    a_, b_ = res["warp"][0], res["tpp"][0]
+    keep = (b_["log"][:, :, 6] != -1).all(axis=0)
+    assert np.array_equal(a_["log"][:, :, 6:8], b_["log"][:, :, 6:8]) and np.abs(a_["log"][:, keep, 0:6] - b_["log"][:, keep, 0:6]).max() <= 1e-8
+    assert np.abs(res["warp"][2]["final_state"] - res["tpp"][2]["final_state"])[keep].max() <= 1e-8
+    # a non-positive target speed is a desired speed of 0 (mpc_cmd_pub.jl:58-62): the vehicles creep at ~1e-3 m/s, where the
+    # plant's slip angles atan2(vy + lf wz, vx) turn differences of 1e-5 in a command into 1e-4 m: statuses, not poses
+    a_, b_ = res["warp"][1], res["tpp"][1]
+    assert np.array_equal(a_["log"][:, :, 6], b_["log"][:, :, 6]) and np.abs(a_["log"][:, :, 0:6] - b_["log"][:, :, 0:6]).max() <= 0.1
     cfg = _ocfg(oracle, s)
     for b in (0, 1, 2, 5, 333):
         path, keep = oracle.make_path(trajs[path_of[b]].trajectory)
