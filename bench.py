@@ -481,10 +481,13 @@ def main():
         for i_, g_ in enumerate(trajs):
             sv.set_path(i_, g_.trajectory)
         sv.rollout(pose0[lo:lo + 64], path_of[lo:lo + 64], 5)    # warm-up (module-load solve, clocks)
-        barrier()
-        tq = time.perf_counter()
-        out = sv.rollout(pose0[lo:hi], path_of[lo:hi], T)
-        wall = allmax(time.perf_counter() - tq)
+        walls = []
+        for _ in range(2):     # the first call also allocates the fleet's device buffers and touches the log's pages for the first time
+            barrier()
+            tq = time.perf_counter()
+            out = sv.rollout(pose0[lo:hi], path_of[lo:hi], T)
+            walls.append(allmax(time.perf_counter() - tq))
+        wall = min(walls)
         kms = allmax(sv.stats()["kernel_ms"])
         launches = sv.stats()["kernel_launches"]
         fused = None
@@ -513,7 +516,7 @@ def main():
                         "mpcb200_rollout, fleet sharded over %d GPU(s)" % (V, T, world), "scaling": "strong",
                 "kernels": ("rollout_plant_kernel + rollout_waypoints_kernel + rollout_solve_tpp_kernel per control period" if launches > 1
                             else "mpc_rollout_kernel (one persistent launch)"), "kernel_launches": int(launches), "fused_kernel_for_comparison": fused,
-                "wall_s": wall, "kernel_ms": kms, "solves": n_solved, "solves_per_s": n_solved / wall,
+                "wall_s": wall, "wall_s_first_call": walls[0], "kernel_ms": kms, "solves": n_solved, "solves_per_s": n_solved / wall,
                 "vehicle_steps_per_s": V * T / wall, "optimal_frac": n_opt / max(1.0, n_solved), "mean_iters": n_it / max(1.0, n_solved),
                 "final_path_error_m": {"median": float(np.median(err)), "p99": float(np.quantile(err, 0.99))}}
 
