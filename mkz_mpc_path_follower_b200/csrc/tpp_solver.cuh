@@ -51,22 +51,29 @@ enum {
     TF_HPP, TF_HPV, TF_HVV, TF_HPD, TF_HVD,                // ... its condensed Hessian entries that are not constants
     TF_SRW0, TF_SRW1, TF_BR0, TF_BR1,                      // ... (Sigma_s + delta_w) and barrier gradient of the rate rows
     TF_C,                                                  // 6: second-order-correction right-hand side (rd[4], dr[2])
-    TF_EV = TF_C + 6,                                      // 2 x 12: model evaluation at the current / the trial point
-    TF_NFIELD = TF_EV + 24
+    TF_EV = TF_C + 6                                       // 2 x TEV_N: model evaluation at the current / the trial point
 };
-enum { TEV_CS = 0, TEV_SN, TEV_CB, TEV_SB, TEV_B1, TEV_B2, TEV_RD, TEV_DR = TEV_RD + 4, TEV_N = 12 };
+enum { TEV_CS = 0, TEV_SN, TEV_CB, TEV_SB, TEV_B1, TEV_B2, TEV_RD, TEV_DR = TEV_RD + 4, TEV_Q = TEV_DR + 2, TEV_K };
+// MODEL 1 (Frenet-frame variant, MKZMPCPathFollowerFrenet.jl): the evaluation also holds q = 1 / (1 - e_y K(s)) and K(s), and the
+// condensed Hessian has nine more entries that are constants or zeros in the XY model
+enum { TFH_SS = 0, TFH_EE, TFH_SE, TFH_SP, TFH_SV, TFH_SD, TFH_EP, TFH_EV, TFH_ED, TFH_N };
+MPC_HD constexpr int tev_n(int model) { return model ? 14 : 12; }
+MPC_HD constexpr int tf_fh(int model) { return TF_EV + 2 * tev_n(model); }               // first of the TFH_* fields (MODEL 1)
+MPC_HD constexpr int tf_nfield(int model) { return tf_fh(model) + (model ? TFH_N : 0); }
 #define TPP_NFILT 32   // filter entries per problem (as many as the one-warp kernel holds)
 
 // Layout: [warp][stage][field][lane].  A warp owns one contiguous region; the 32 lanes of an access are 256 contiguous
 // bytes, a stage's fields sit 256 bytes apart (so every field of the current and the neighbouring stages is an immediate
 // offset from one per-stage pointer: no address arithmetic per access), and a warp walks its region linearly.
-struct TppMem {
+template <int MODEL>
+struct TppMemT {
+    static constexpr int NF = tf_nfield(MODEL);
     double* wb;     // this lane's element of field 0, stage 0 of its warp's region
     double* fb;     // ... of filter entry 0
-    MPC_DEV TppMem(double* st, double* filt, int N, long slot)
-        : wb(st + (slot >> 5) * ((long)(N + 1) * TF_NFIELD * 32) + (slot & 31)), fb(filt + (slot >> 5) * (2L * TPP_NFILT * 32) + (slot & 31)) {}
-    MPC_DEV double ld(int f, int k) const { return (wb + (long)k * (TF_NFIELD * 32))[f * 32]; }
-    MPC_DEV void sto(int f, int k, double v) const { (wb + (long)k * (TF_NFIELD * 32))[f * 32] = v; }
+    MPC_DEV TppMemT(double* st, double* filt, int N, long slot)
+        : wb(st + (slot >> 5) * ((long)(N + 1) * NF * 32) + (slot & 31)), fb(filt + (slot >> 5) * (2L * TPP_NFILT * 32) + (slot & 31)) {}
+    MPC_DEV double ld(int f, int k) const { return (wb + (long)k * (NF * 32))[f * 32]; }
+    MPC_DEV void sto(int f, int k, double v) const { (wb + (long)k * (NF * 32))[f * 32] = v; }
     // L2 prefetch of fields [f0, f0 + nf) of stage k for the whole warp (one bulk instruction from one active lane): the
     // passes walk the horizon one stage at a time, so the block they touch next is known a whole stage body ahead
     MPC_DEV void prefetch(int k, int f0, int nf) const {
@@ -74,7 +81,7 @@ struct TppMem {
         const unsigned am = __activemask();
         const int lane = threadIdx.x & 31;
         if (lane == __ffs(am) - 1)
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wb - lane + ((long)k * TF_NFIELD + f0) * 32), "r"(nf * 256) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(wb - lane + ((long)k * NF + f0) * 32), "r"(nf * 256) : "memory");
 #else
         (void)k; (void)f0; (void)nf;
 #endif
@@ -82,8 +89,9 @@ struct TppMem {
     MPC_DEV double fld(int e) const { return fb[e * 32]; }
     MPC_DEV void fst(int e, double v) const { fb[e * 32] = v; }
 };
+typedef TppMemT<0> TppMem;
 // slots are rounded up to whole warps
-MPC_HD size_t tpp_state_doubles(int N, long S) { return (size_t)TF_NFIELD * (size_t)(N + 1) * (size_t)((S + 31) / 32 * 32); }
+MPC_HD size_t tpp_state_doubles(int N, long S, int model = 0) { return (size_t)tf_nfield(model) * (size_t)(N + 1) * (size_t)((S + 31) / 32 * 32); }
 MPC_HD size_t tpp_filter_doubles(long S) { return (size_t)2 * TPP_NFILT * (size_t)((S + 31) / 32 * 32); }
 
 struct TrueT { static constexpr bool value = true; };
@@ -91,11 +99,14 @@ struct FalseT { static constexpr bool value = false; };
 MPC_DEV double nanmax(double v, double t) { return (t > v || t != t) ? t : v; }   // NaN wins, like warp_max
 MPC_DEV constexpr int sidx(int i, int j) { return (i <= j) ? (i * 6 - i * (i - 1) / 2 + (j - i)) : (j * 6 - j * (j - 1) / 2 + (i - j)); }
 
-struct TppSolver {
+template <int MODEL = 0>
+struct TppSolverT {
+    static constexpr int TEVN = tev_n(MODEL), TF_FH = tf_fh(MODEL);
     const KCfg& c;
-    const TppMem m;
+    const TppMemT<MODEL> m;
     const int N;
     double cst[7];   // state[4], u_prev (df, acc), v_des
+    double kp[4];    // MODEL 1: the problem's curvature polynomial K(s), highest degree first
     // ---- interior-point driver state (TeamSolver::solve's locals)
     double sigma, mu, tau, dw, dw_last, theta_max, theta_min, phi, gBd, alpha, alpha_max, Rft, a_soc, th_soc_old;
     double cur_theta, cur_f, cur_lb, ev_f, ev_lb, ev_theta, ev_alpha;
@@ -106,7 +117,7 @@ struct TppSolver {
     enum { PH_INIT = 0, PH_EVAL0, PH_LS, PH_BEGIN, PH_PD, PH_RESOLVE, PH_TRIAL, PH_SOC, PH_RESTO };
     enum { RUNNING = -100 };
 
-    MPC_DEV TppSolver(const KCfg& cfg, const TppMem& mem) : c(cfg), m(mem), N(cfg.N) {}
+    MPC_DEV TppSolverT(const KCfg& cfg, const TppMemT<MODEL>& mem) : c(cfg), m(mem), N(cfg.N) {}
 
     MPC_DEV bool isU(int k) const { return k < N; }
     MPC_DEV bool isR(int k) const { return (k == 0 || k >= 2) && k < N; }
@@ -115,7 +126,35 @@ struct TppSolver {
     MPC_DEV double wp(int k) const { return (k >= 1) ? c.w[2] : 0.0; }
     MPC_DEV double wv(int k) const { return (k >= 1 && k <= N - 1) ? c.w[3] : 0.0; }
     MPC_DEV double rHi(int k, int i) const { return (k == 0) ? c.rHiFirst[i] : c.rHiLater[i]; }
-    MPC_DEV int evb(int which) const { return TF_EV + TEV_N * which; }
+    MPC_DEV int evb(int which) const { return TF_EV + TEVN * which; }
+
+    // MODEL 1 (MKZMPCPathFollowerFrenet.jl:111-120): curvature K(s) of the problem's cubic and its derivatives; the stage
+    // Jacobian of  ds/dt = g = v cos(e_psi + beta) / (1 - e_y K(s)),  d e_psi/dt = v sin(beta) / L_b - g K  at a stage that owns an
+    // input (TeamSolver::frenet_jac, same expressions)
+    struct Curv { double K, K1, K2; };
+    MPC_DEV Curv curvature(double s) const {
+        Curv r;
+        r.K = ((kp[0] * s + kp[1]) * s + kp[2]) * s + kp[3];
+        r.K1 = (3.0 * kp[0] * s + 2.0 * kp[1]) * s + kp[2];
+        r.K2 = 6.0 * kp[0] * s + 2.0 * kp[1];
+        return r;
+    }
+    struct FJac { double a00, a01, a02, a03, a12, a13, a20, a21, a22, a23, b0, b1, b2, G0, G1, G2, G3, G4, g, K1, K2; };
+    MPC_DEV FJac frenet_jac(double cs, double sn, double cb, double sb, double b1e, double q, double K, double s, double ey, double v) const {
+        FJac J;
+        const Curv cu = curvature(s);
+        const double dt = c.dt;
+        const double q2 = q * q;
+        const double qs = ey * cu.K1 * q2, qe = K * q2;
+        J.K1 = cu.K1; J.K2 = cu.K2;
+        J.g = v * cs * q;
+        J.G0 = v * cs * qs; J.G1 = v * cs * qe; J.G2 = -v * sn * q; J.G3 = cs * q; J.G4 = -v * sn * b1e * q;
+        J.a00 = 1.0 + dt * J.G0; J.a01 = dt * J.G1; J.a02 = dt * J.G2; J.a03 = dt * J.G3; J.b0 = dt * J.G4;
+        J.a12 = dt * v * cs; J.a13 = dt * sn; J.b1 = dt * v * cs * b1e;
+        J.a20 = -dt * (J.G0 * K + J.g * cu.K1); J.a21 = -dt * J.G1 * K; J.a22 = 1.0 - dt * J.G2 * K;
+        J.a23 = dt * (sb / c.Lb - J.G3 * K); J.b2 = dt * (v * cb * b1e / c.Lb - J.G4 * K);
+        return J;
+    }
 
     // reciprocals of the ten bound slacks of stage k from one division (TeamSolver::recips)
     MPC_DEV void recips(int k, bool u, bool r, double sv, double ua, double ud, double rs0, double rs1, Recips& q) const {
@@ -144,10 +183,12 @@ struct TppSolver {
         for (int i = 0; i < 4; i++) cst[i] = io.state[4 * b + i];
         cst[4] = io.u_prev[2 * b]; cst[5] = io.u_prev[2 * b + 1];
         cst[6] = io.v_des ? io.v_des[b] : 0.0;
-        const double* rf = io.ref + nr * b;
+        // MODEL 1: io.ref = [B][4] curvature polynomial; the cost is on e_y, e_psi themselves (reference 0)
+        const double* rf = MODEL ? io.ref + 4 * b : io.ref + nr * b;
+        if (MODEL) for (int i = 0; i < 4; i++) kp[i] = rf[i];
         const double* w = io.warm ? io.warm + nt * b : nullptr;
         for (int k = 0; k <= N; k++) {
-            m.sto(TF_XR, k, rf[k]); m.sto(TF_YR, k, rf[(N + 1) + k]); m.sto(TF_PR, k, rf[2 * (N + 1) + k]);
+            m.sto(TF_XR, k, MODEL ? 0.0 : rf[k]); m.sto(TF_YR, k, MODEL ? 0.0 : rf[(N + 1) + k]); m.sto(TF_PR, k, MODEL ? 0.0 : rf[2 * (N + 1) + k]);
             m.sto(TF_SX, k, w ? w[k] : 0.0); m.sto(TF_SY, k, w ? w[(N + 1) + k] : 0.0);
             m.sto(TF_SV, k, w ? w[2 * (N + 1) + k] : 0.0); m.sto(TF_SP, k, w ? w[3 * (N + 1) + k] : 0.0);
             m.sto(TF_UD, k, (w && k < N) ? w[4 * (N + 1) + k] : 0.0); m.sto(TF_UA, k, (w && k < N) ? w[4 * (N + 1) + N + k] : 0.0);
@@ -305,7 +346,7 @@ struct TppSolver {
             }
             // ---- arithmetic
             double rd0 = 0.0, rd1 = 0.0, rd2 = 0.0, rd3 = 0.0, dr0 = 0.0, dr1 = 0.0;
-            double cs = 0.0, sn = 0.0, cb = 0.0, sb = 0.0, b1 = 0.0, b2 = 0.0;
+            double cs = 0.0, sn = 0.0, cb = 0.0, sb = 0.0, b1 = 0.0, b2 = 0.0, qv = 0.0, Kv = 0.0;
             if (u) {
                 // beta = atan(r tan df) in closed form, valid for |df| < pi/2 (bounds keep |df| <= 0.5)
                 const double rr = c.rfrac;
@@ -318,7 +359,15 @@ struct TppSolver {
                 cb = cd * inv; sb = rr * sd * inv;
                 cs = cps * cb - sps * sb; sn = sps * cb + cps * sb;
                 b1 = rr * iD; b2 = rr * (1.0 - rr * rr) * (2.0 * sd * cd) * (iD * iD);
-                const double fx = sx + c.dt * (sv * cs), fy = sy + c.dt * (sv * sn), fp = sp + c.dtLb * (sv * sb), fv = sv + c.dt * ua;
+                double fx = sx + c.dt * (sv * cs), fp = sp + c.dtLb * (sv * sb);
+                const double fy = sy + c.dt * (sv * sn), fv = sv + c.dt * ua;
+                if (MODEL) {   // MKZMPCPathFollowerFrenet.jl:111-120: ds/dt = v cos(e_psi + beta) / (1 - e_y K(s))
+                    Kv = curvature(sx).K;
+                    qv = 1.0 / (1.0 - sy * Kv);
+                    const double g = sv * cs * qv;
+                    fx = sx + c.dt * g;
+                    fp = sp + c.dt * (sv * sb / c.Lb - g * Kv);
+                }
                 rd0 = fx - nx; rd1 = fy - ny; rd2 = fp - np; rd3 = fv - nv;
             }
             if (r) { dr0 = (ud - pd) - s0; dr1 = (ua - pa) - s1; }
@@ -343,6 +392,7 @@ struct TppSolver {
                 m.sto(eb + TEV_B1, k, b1); m.sto(eb + TEV_B2, k, b2);
                 m.sto(eb + TEV_RD + 0, k, rd0); m.sto(eb + TEV_RD + 1, k, rd1); m.sto(eb + TEV_RD + 2, k, rd2); m.sto(eb + TEV_RD + 3, k, rd3);
                 m.sto(eb + TEV_DR, k, dr0); m.sto(eb + TEV_DR + 1, k, dr1);
+                if (MODEL) { m.sto(eb + TEV_Q, k, qv); m.sto(eb + TEV_K, k, Kv); }
             } else {   // slot N of the evaluation holds the initial-condition residual
                 m.sto(eb + TEV_RD + 0, k, i0); m.sto(eb + TEV_RD + 1, k, i1); m.sto(eb + TEV_RD + 2, k, i2); m.sto(eb + TEV_RD + 3, k, i3);
             }
@@ -375,7 +425,7 @@ struct TppSolver {
         auto body = [&](const int k, auto UT) -> bool {
             constexpr bool u = decltype(UT)::value;
             const bool r = u && isR(k);
-            if (k >= 1) { m.prefetch(k - 1, 0, TF_DX); m.prefetch(k - 1, soc ? TF_C : ec, soc ? 6 : TEV_N); }
+            if (k >= 1) { m.prefetch(k - 1, 0, TF_DX); m.prefetch(k - 1, soc ? TF_C : ec, soc ? 6 : TEVN); }
             // ---- loads
             const int kp = (k >= 1) ? k - 1 : 0;
             const double sx = m.ld(TF_SX, k), sy = m.ld(TF_SY, k), sp = m.ld(TF_SP, k), sv = m.ld(TF_SV, k);
@@ -384,7 +434,7 @@ struct TppSolver {
             const double yxk = m.ld(TF_YX, k), yyk = m.ld(TF_YY, k), ypk = m.ld(TF_YP, k);
             const double zvL = m.ld(TF_ZVL, k), zvU = m.ld(TF_ZVU, k);
             double zaL = 0.0, zaU = 0.0, zdL = 0.0, zdU = 0.0, rvL0 = 0.0, rvL1 = 0.0, rvU0 = 0.0, rvU1 = 0.0, rs0 = 0.0, rs1 = 0.0;
-            double cs = 0.0, sn = 0.0, cb = 0.0, sb = 0.0, b1 = 0.0, b2 = 0.0;
+            double cs = 0.0, sn = 0.0, cb = 0.0, sb = 0.0, b1 = 0.0, b2 = 0.0, eq = 0.0, eK = 0.0;
             double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0, rdr0 = 0.0, rdr1 = 0.0;
             if (u) {
                 zaL = m.ld(TF_ZAL, k); zaU = m.ld(TF_ZAU, k); zdL = m.ld(TF_ZDL, k); zdU = m.ld(TF_ZDU, k);
@@ -392,6 +442,7 @@ struct TppSolver {
                 rs0 = m.ld(TF_RS0, k); rs1 = m.ld(TF_RS1, k);
                 cs = m.ld(ec + TEV_CS, k); sn = m.ld(ec + TEV_SN, k); cb = m.ld(ec + TEV_CB, k); sb = m.ld(ec + TEV_SB, k);
                 b1 = m.ld(ec + TEV_B1, k); b2 = m.ld(ec + TEV_B2, k);
+                if (MODEL) { eq = m.ld(ec + TEV_Q, k); eK = m.ld(ec + TEV_K, k); }
                 r0 = m.ld(rb + 0, k); r1 = m.ld(rb + 1, k); r2 = m.ld(rb + 2, k); r3 = m.ld(rb + 3, k);
                 rdr0 = m.ld(db, k); rdr1 = m.ld(db + 1, k);
                 if (ls) { r0 = r1 = r2 = r3 = 0.0; }
@@ -400,6 +451,8 @@ struct TppSolver {
             }
             // ---- arithmetic
             if (!u) { ua = 0.0; ud = 0.0; }
+            FJac J;
+            if (MODEL && u) J = frenet_jac(cs, sn, cb, sb, b1, eq, eK, sx, sy, sv);
             Grad g;
             {
                 g.x = s2 * wx(k) * (sx - xr); g.y = s2 * wy(k) * (sy - yr); g.p = s2 * wp(k) * (sp - pr); g.v = s2 * wv(k) * (sv - cst[6]);
@@ -412,6 +465,7 @@ struct TppSolver {
                 }
             }
             double Hxx, Hyy, Hpp, Hpv = 0.0, Hvv, Hpd = 0.0, Hvd = 0.0, Haa, Hdd, Ca = 0.0, Cd = 0.0;
+            double hss = 0.0, hee = 0.0, Hse = 0.0, Hsp = 0.0, Hsv = 0.0, Hsd = 0.0, Hep = 0.0, Hev = 0.0, Hed = 0.0;   // MODEL 1 only
             double gsv, gua = 0.0, gud = 0.0;
             double SrW0 = 0.0, SrW1 = 0.0, br0 = 0.0, br1 = 0.0, wrow0 = 0.0, wrow1 = 0.0;
             if (ls) {
@@ -423,7 +477,28 @@ struct TppSolver {
                 if (u) { gua = g.a - zaL + zaU; gud = g.d - zdL + zdU; }
             } else {
                 double hpp = 0.0, hdd = 0.0;
-                if (u) {
+                if (MODEL && u) {
+                    // Lagrangian Hessian of the Frenet stage map over (s, e_y, e_psi, v, df): with g = v C q, rows s and e_psi contribute
+                    //   -dt [ (y_s - y_p K) hess g - y_p K' (e_s grad g' + grad g e_s') - y_p g K'' e_s e_s' ]   (TeamSolver::assemble)
+                    const double v = sv, dt = c.dt, q = eq, K = eK, Cc = cs, Sc = sn, ey = sy;
+                    const double q2 = q * q, q3 = q2 * q, K1 = J.K1, K2 = J.K2;
+                    const double qs = ey * K1 * q2, qe = K * q2;
+                    const double qss = ey * K2 * q2 + 2.0 * ey * ey * K1 * K1 * q3, qse = K1 * q2 + 2.0 * ey * K * K1 * q3, qee = 2.0 * K * K * q3;
+                    const double mm = y1x - y1p * K, nn = y1p * K1;
+                    hss = -dt * (mm * (v * Cc * qss) - 2.0 * nn * J.G0 - y1p * J.g * K2);
+                    Hse = -dt * (mm * (v * Cc * qse) - nn * J.G1);
+                    Hsp = -dt * (mm * (-v * Sc * qs) - nn * J.G2);
+                    Hsv = -dt * (mm * (Cc * qs) - nn * J.G3);
+                    Hsd = -dt * (mm * (-v * Sc * b1 * qs) - nn * J.G4);
+                    hee = -dt * mm * (v * Cc * qee);
+                    Hep = dt * mm * (v * Sc * qe); Hev = -dt * mm * (Cc * qe); Hed = dt * mm * (v * Sc * b1 * qe);
+                    hpp = dt * mm * (v * Cc * q) + y1y * dt * v * Sc;
+                    Hpv = dt * mm * (Sc * q) - y1y * dt * Cc;
+                    Hpd = dt * mm * (v * Cc * b1 * q) + y1y * dt * v * Sc * b1;
+                    Hvd = dt * mm * (Sc * b1 * q) - y1y * dt * Cc * b1 - y1p * c.dtLb * cb * b1;
+                    hdd = dt * mm * (v * q * (Cc * b1 * b1 + Sc * b2)) - y1y * dt * v * (-Sc * b1 * b1 + Cc * b2)
+                          - y1p * (c.dtLb * v) * (cb * b2 - sb * b1 * b1);
+                } else if (u) {
                     const double dt = c.dt;
                     const double e1 = y1x * cs + y1y * sn;
                     const double e2 = y1x * sn - y1y * cs;
@@ -445,6 +520,7 @@ struct TppSolver {
                     wrow1 = br1 + SrW1 * rdr1;
                 }
                 Hxx = s2 * wx(k) + dw; Hyy = s2 * wy(k) + dw; Hpp = s2 * wp(k) + hpp + dw; Hvv = s2 * wv(k) + Sv + dw;
+                if (MODEL) { Hxx += hss; Hyy += hee; }
                 if (u) {
                     if (k >= 1) { Ca = s2 * c.w[4]; Cd = s2 * c.w[5]; }
                     if (r) { Ca += SrW1; Cd += SrW0; }
@@ -464,6 +540,49 @@ struct TppSolver {
             if (!u) {   // terminal cost-to-go
                 P[sidx(0, 0)] = Hxx; P[sidx(1, 1)] = Hyy; P[sidx(2, 2)] = Hpp; P[sidx(3, 3)] = Hvv;
                 pv[0] = g.x; pv[1] = g.y; pv[2] = g.p; pv[3] = gsv;
+            } else if (MODEL) {
+                // the s and e_y columns of A are dense and the Hessian has its full 5x5 block: every column of P M, every entry of F
+                const double dt = c.dt;
+                double Ts[6], Te[6], Tp[6], Tv[6], Ta[6], Td[6], tr[6];
+                MPC_UNROLL for (int i = 0; i < 6; i++) {
+                    const double p0 = P[sidx(i, 0)], p1 = P[sidx(i, 1)], p2 = P[sidx(i, 2)], p3 = P[sidx(i, 3)], p4 = P[sidx(i, 4)], p5 = P[sidx(i, 5)];
+                    Ts[i] = p0 * J.a00 + p2 * J.a20;
+                    Te[i] = (p0 * J.a01 + p1) + p2 * J.a21;
+                    Tp[i] = (p0 * J.a02 + p1 * J.a12) + p2 * J.a22;
+                    Tv[i] = (p0 * J.a03 + p1 * J.a13) + (p2 * J.a23 + p3);
+                    Ta[i] = p3 * dt + p4;
+                    Td[i] = (p0 * J.b0 + p1 * J.b1) + (p2 * J.b2 + p5);
+                    tr[i] = (p0 * r0 + p1 * r1) + (p2 * r2 + p3 * r3 + pv[i]);
+                }
+                // M' applied to a column T of P M (or to P r + p), row by row of (s, e_y, e_psi, v, a, df)
+                auto ms = [&](const double* T) { return J.a00 * T[0] + J.a20 * T[2]; };
+                auto me = [&](const double* T) { return (J.a01 * T[0] + T[1]) + J.a21 * T[2]; };
+                auto mp = [&](const double* T) { return (J.a02 * T[0] + J.a12 * T[1]) + J.a22 * T[2]; };
+                auto mv = [&](const double* T) { return (J.a03 * T[0] + J.a13 * T[1]) + (J.a23 * T[2] + T[3]); };
+                auto ma = [&](const double* T) { return T[4] + dt * T[3]; };
+                auto md = [&](const double* T) { return (J.b0 * T[0] + J.b1 * T[1] + T[5]) + J.b2 * T[2]; };
+                const double Fss = ms(Ts) + Hxx, Fse = ms(Te) + Hse, Fsp = ms(Tp) + Hsp, Fsv = ms(Tv) + Hsv, Fsa = ms(Ta), Fsd = ms(Td) + Hsd;
+                const double Fee = me(Te) + Hyy, Fep = me(Tp) + Hep, Fev = me(Tv) + Hev, Fea = me(Ta), Fed = me(Td) + Hed;
+                const double Fpp = mp(Tp) + Hpp, Fpv = mp(Tv) + Hpv, Fpa = mp(Ta), Fpd = mp(Td) + Hpd;
+                const double Fvv = mv(Tv) + Hvv, Fva = mv(Ta), Fvd = mv(Td) + Hvd;
+                const double Faa = ma(Ta) + Haa, Fad = ma(Td);
+                const double Fdd = md(Td) + Hdd;
+                const double fs = ms(tr) + g.x, fe = me(tr) + g.y, fp = mp(tr) + g.p, fv = mv(tr) + gsv, fa = ma(tr) + gua, fd = md(tr) + gud;
+                const double det = Faa * Fdd - Fad * Fad;
+                pd_ok = (Faa > 0.0) && (det > 1e-300);
+                const double idet = fast_rcp(pd_ok ? det : 1.0);
+                const double ja[7] = {Fsa, Fea, Fpa, Fva, -Ca, 0.0, fa}, jd[7] = {Fsd, Fed, Fpd, Fvd, 0.0, -Cd, fd};
+                double a0[7], a1[7];
+                MPC_UNROLL for (int j = 0; j < 7; j++) {
+                    a0[j] = Fdd * ja[j] - Fad * jd[j];
+                    a1[j] = Faa * jd[j] - Fad * ja[j];
+                    K0[j] = -a0[j] * idet; K1[j] = -a1[j] * idet;
+                }
+                const double F0[21] = {Fss, Fse, Fsp, Fsv, 0.0, 0.0, Fee, Fep, Fev, 0.0, 0.0, Fpp, Fpv, 0.0, 0.0, Fvv, 0.0, 0.0, Ca, 0.0, Cd};
+                MPC_UNROLL for (int i = 0; i < 6; i++)
+                    MPC_UNROLL for (int j = i; j < 6; j++) P[sidx(i, j)] = F0[sidx(i, j)] - (ja[i] * a0[j] + jd[i] * a1[j]) * idet;
+                const double f0[6] = {fs, fe, fp, fv, 0.0, 0.0};
+                MPC_UNROLL for (int i = 0; i < 6; i++) pv[i] = f0[i] - (ja[i] * a0[6] + jd[i] * a1[6]) * idet;
             } else {
                 const double A02 = -c.dt * sv * sn, A03 = c.dt * cs, A12 = c.dt * sv * cs, A13 = c.dt * sn, A23 = c.dtLb * sb;
                 const double b0 = A02 * b1, b1v = A12 * b1, b2v = c.dtLb * sv * cb * b1, dt = c.dt;
@@ -516,6 +635,11 @@ struct TppSolver {
             // ---- stores
             m.sto(TF_GX, k, g.x); m.sto(TF_GY, k, g.y); m.sto(TF_GP, k, g.p); m.sto(TF_GV, k, gsv); m.sto(TF_GA, k, gua); m.sto(TF_GD, k, gud);
             m.sto(TF_HPP, k, Hpp); m.sto(TF_HPV, k, Hpv); m.sto(TF_HVV, k, Hvv); m.sto(TF_HPD, k, Hpd); m.sto(TF_HVD, k, Hvd);
+            if (MODEL) {
+                m.sto(TF_FH + TFH_SS, k, Hxx); m.sto(TF_FH + TFH_EE, k, Hyy); m.sto(TF_FH + TFH_SE, k, Hse); m.sto(TF_FH + TFH_SP, k, Hsp);
+                m.sto(TF_FH + TFH_SV, k, Hsv); m.sto(TF_FH + TFH_SD, k, Hsd); m.sto(TF_FH + TFH_EP, k, Hep); m.sto(TF_FH + TFH_EV, k, Hev);
+                m.sto(TF_FH + TFH_ED, k, Hed);
+            }
             if (u) {
                 m.sto(TF_SRW0, k, SrW0); m.sto(TF_SRW1, k, SrW1); m.sto(TF_BR0, k, br0); m.sto(TF_BR1, k, br1);
                 MPC_UNROLL for (int j = 0; j < 7; j++) { m.sto(TF_K + j, k, K0[j]); m.sto(TF_K + 7 + j, k, K1[j]); }
@@ -572,7 +696,7 @@ struct TppSolver {
         auto body = [&](const int k, auto UT) {
             constexpr bool u = decltype(UT)::value;
             const bool r = u && isR(k);
-            if (k + 1 <= N) { m.prefetch(k + 1, 0, TF_C); m.prefetch(k + 1, soc ? TF_C : ec, soc ? 6 : TEV_N); }
+            if (k + 1 <= N) { m.prefetch(k + 1, 0, TF_C); m.prefetch(k + 1, soc ? TF_C : ec, soc ? 6 : TEVN); }
             // ---- loads
             const double sx = m.ld(TF_SX, k), sy = m.ld(TF_SY, k), sp = m.ld(TF_SP, k), sv = m.ld(TF_SV, k);
             const double g0 = m.ld(TF_GX, k), g1 = m.ld(TF_GY, k), g2 = m.ld(TF_GP, k), g3 = m.ld(TF_GV, k);
@@ -581,12 +705,13 @@ struct TppSolver {
             double ua = 0.0, ud = 0.0, rs0 = 0.0, rs1 = 0.0, g4 = 0.0, g5 = 0.0;
             double K0[7], K1[7];
             double cs = 0.0, sn = 0.0, cb = 0.0, sb = 0.0, b1 = 0.0, r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0, drr0 = 0.0, drr1 = 0.0;
-            double srw0 = 0.0, srw1 = 0.0, brr0 = 0.0, brr1 = 0.0;
+            double srw0 = 0.0, srw1 = 0.0, brr0 = 0.0, brr1 = 0.0, eq = 0.0, eK = 0.0;
             if (u) {
                 ua = m.ld(TF_UA, k); ud = m.ld(TF_UD, k); rs0 = m.ld(TF_RS0, k); rs1 = m.ld(TF_RS1, k);
                 g4 = m.ld(TF_GA, k); g5 = m.ld(TF_GD, k);
                 MPC_UNROLL for (int j = 0; j < 7; j++) { K0[j] = m.ld(TF_K + j, k); K1[j] = m.ld(TF_K + 7 + j, k); }
                 cs = m.ld(ec + TEV_CS, k); sn = m.ld(ec + TEV_SN, k); cb = m.ld(ec + TEV_CB, k); sb = m.ld(ec + TEV_SB, k); b1 = m.ld(ec + TEV_B1, k);
+                if (MODEL) { eq = m.ld(ec + TEV_Q, k); eK = m.ld(ec + TEV_K, k); }
                 r0 = m.ld(rb + 0, k); r1 = m.ld(rb + 1, k); r2 = m.ld(rb + 2, k); r3 = m.ld(rb + 3, k);
                 drr0 = m.ld(db, k); drr1 = m.ld(db + 1, k);
                 srw0 = m.ld(TF_SRW0, k); srw1 = m.ld(TF_SRW1, k); brr0 = m.ld(TF_BR0, k); brr1 = m.ld(TF_BR1, k);
@@ -606,6 +731,12 @@ struct TppSolver {
                 n1 = ((s1 + r1) + (A12 * s2 + A13 * s3)) + b1v * dud;
                 n2 = ((s2 + r2) + A23 * s3) + b2v * dud;
                 n3 = (s3 + r3) + c.dt * dua;
+                if (MODEL) {   // dense s and e_y columns (TeamSolver::riccati_forward)
+                    const FJac J = frenet_jac(cs, sn, cb, sb, b1, eq, eK, sx, sy, sv);
+                    n0 = (r0 + (J.a00 * s0 + J.a01 * s1)) + ((J.a02 * s2 + J.a03 * s3) + J.b0 * dud);
+                    n1 = ((s1 + r1) + (J.a12 * s2 + J.a13 * s3)) + J.b1 * dud;
+                    n2 = (r2 + (J.a20 * s0 + J.a21 * s1)) + ((J.a22 * s2 + J.a23 * s3) + J.b2 * dud);
+                }
             }
             double t = g0 * s0 + g1 * s1 + g2 * s2 + g3 * s3 + g4 * dua + g5 * dud;
             if (r) {
@@ -669,7 +800,7 @@ struct TppSolver {
         auto body = [&](const int k, auto UT) {
             constexpr bool u = decltype(UT)::value;
             const bool r = u && isR(k);
-            if (k >= 1) { m.prefetch(k - 1, 0, TF_C); m.prefetch(k - 1, TF_EV, 2 * TEV_N); }
+            if (k >= 1) { m.prefetch(k - 1, 0, TF_C); m.prefetch(k - 1, TF_EV, 2 * TEVN + (MODEL ? TFH_N : 0)); }
             // ---- loads
             const int kp = (k >= 1) ? k - 1 : 0;
             double sx = m.ld(TF_SX, k), sy = m.ld(TF_SY, k), sp = m.ld(TF_SP, k), sv = m.ld(TF_SV, k);
@@ -686,6 +817,13 @@ struct TppSolver {
             double ua = 0.0, ud = 0.0, rs0 = 0.0, rs1 = 0.0, ry0 = 0.0, ry1 = 0.0, dua = 0.0, dud = 0.0, drs0 = 0.0, drs1 = 0.0;
             double srw0 = 0.0, srw1 = 0.0, brr0 = 0.0, brr1 = 0.0, dr0 = 0.0, dr1 = 0.0;
             double ocs = 0.0, osn = 0.0, osb = 0.0, ncs = 0.0, nsn = 0.0, ncb = 0.0, nsb = 0.0, nb1 = 0.0;
+            double ocb = 0.0, ob1 = 0.0, oq = 0.0, oK = 0.0, nq = 0.0, nK = 0.0;                                  // MODEL 1 only
+            double fhss = 0.0, fhee = 0.0, fhse = 0.0, fhsp = 0.0, fhsv = 0.0, fhsd = 0.0, fhep = 0.0, fhev = 0.0, fhed = 0.0;
+            if (MODEL) {
+                fhss = m.ld(TF_FH + TFH_SS, k); fhee = m.ld(TF_FH + TFH_EE, k); fhse = m.ld(TF_FH + TFH_SE, k); fhsp = m.ld(TF_FH + TFH_SP, k);
+                fhsv = m.ld(TF_FH + TFH_SV, k); fhsd = m.ld(TF_FH + TFH_SD, k); fhep = m.ld(TF_FH + TFH_EP, k); fhev = m.ld(TF_FH + TFH_EV, k);
+                fhed = m.ld(TF_FH + TFH_ED, k);
+            }
             if (u) {
                 ua = m.ld(TF_UA, k); ud = m.ld(TF_UD, k); rs0 = m.ld(TF_RS0, k); rs1 = m.ld(TF_RS1, k);
                 ry0 = m.ld(TF_RY0, k); ry1 = m.ld(TF_RY1, k);
@@ -693,6 +831,10 @@ struct TppSolver {
                 srw0 = m.ld(TF_SRW0, k); srw1 = m.ld(TF_SRW1, k); brr0 = m.ld(TF_BR0, k); brr1 = m.ld(TF_BR1, k);
                 ocs = m.ld(eo + TEV_CS, k); osn = m.ld(eo + TEV_SN, k); osb = m.ld(eo + TEV_SB, k);
                 ncs = m.ld(en + TEV_CS, k); nsn = m.ld(en + TEV_SN, k); ncb = m.ld(en + TEV_CB, k); nsb = m.ld(en + TEV_SB, k); nb1 = m.ld(en + TEV_B1, k);
+                if (MODEL) {
+                    ocb = m.ld(eo + TEV_CB, k); ob1 = m.ld(eo + TEV_B1, k); oq = m.ld(eo + TEV_Q, k); oK = m.ld(eo + TEV_K, k);
+                    nq = m.ld(en + TEV_Q, k); nK = m.ld(en + TEV_K, k);
+                }
                 dr0 = m.ld(en + TEV_DR, k); dr1 = m.ld(en + TEV_DR + 1, k);
                 if (!r) { rs0 = rs1 = ry0 = ry1 = drs0 = drs1 = 0.0; }
             }
@@ -700,13 +842,25 @@ struct TppSolver {
             bool wr_primal = false;
             if (mode != 2) {
                 // ---- costates
-                const double Hxx = lsm ? 1.0 : s2 * wx(k) + dw, Hyy = lsm ? 1.0 : s2 * wy(k) + dw;
-                const double lx = -(Hxx * dsx + gx);
-                const double ly = -(Hyy * dsy + gy);
-                const double lp = -(hpp * dsp + hpv * dsv + hpd * dud + gp);
-                const double lv = -(hpv * dsp + hvv * dsv + hvd * dud + gv);
+                const double Hxx = MODEL ? fhss : (lsm ? 1.0 : s2 * wx(k) + dw), Hyy = MODEL ? fhee : (lsm ? 1.0 : s2 * wy(k) + dw);
+                double lx = -(Hxx * dsx + gx);
+                double ly = -(Hyy * dsy + gy);
+                double lp = -(hpp * dsp + hpv * dsv + hpd * dud + gp);
+                double lv = -(hpv * dsp + hvv * dsv + hvd * dud + gv);
+                if (MODEL) {   // the rest of the 5x5 block (TeamSolver::recover_duals)
+                    lx -= fhse * dsy + fhsp * dsp + fhsv * dsv + fhsd * dud;
+                    ly -= fhse * dsx + fhep * dsp + fhev * dsv + fhed * dud;
+                    lp -= fhsp * dsx + fhep * dsy;
+                    lv -= fhsv * dsx + fhev * dsy;
+                }
                 double nyx = lx + ny1x, nyy = ly + ny1y, nyp = lp + ny1p, nyv = lv + ny1v;
-                if (u) {
+                if (MODEL && u) {   // lambda_k = l_k + A_k' lambda_{k+1} with the dense s and e_y columns, A at the old point
+                    const FJac J = frenet_jac(ocs, osn, ocb, osb, ob1, oq, oK, sx, sy, sv);
+                    nyx = lx + (J.a00 * ny1x + J.a20 * ny1p);
+                    nyy = ly + ((J.a01 * ny1x + ny1y) + J.a21 * ny1p);
+                    nyp = lp + ((J.a02 * ny1x + J.a12 * ny1y) + J.a22 * ny1p);
+                    nyv = lv + ((J.a03 * ny1x + J.a13 * ny1y) + (J.a23 * ny1p + ny1v));
+                } else if (u) {
                     const double A02 = -c.dt * sv * osn, A03 = c.dt * ocs, A12 = c.dt * sv * ocs, A13 = c.dt * osn, A23 = c.dtLb * osb;
                     nyp = (lp + (A02 * ny1x + A12 * ny1y)) + ny1p;
                     nyv = (lv + (A03 * ny1x + A13 * ny1y + A23 * ny1p)) + ny1v;
@@ -764,11 +918,19 @@ struct TppSolver {
                 A02 = -c.dt * sv * nsn; A03 = c.dt * ncs; A12 = c.dt * sv * ncs; A13 = c.dt * nsn; A23 = c.dtLb * nsb;
                 b0 = A02 * nb1; b1v = A12 * nb1; b2v = c.dtLb * sv * ncb * nb1;
             }
-            const double glx = g.x + yx - hn * y1x;
-            const double gly = g.y + yy - hn * y1y;
-            const double glp = g.p + yp - hn * (A02 * y1x + A12 * y1y + y1p);
-            const double glv = g.v + yv - hn * (A03 * y1x + A13 * y1y + A23 * y1p + y1v) - z[0] + z[1];
-            const double jd = b0 * y1x + b1v * y1y + b2v * y1p;
+            double glx = g.x + yx - hn * y1x;
+            double gly = g.y + yy - hn * y1y;
+            double glp = g.p + yp - hn * (A02 * y1x + A12 * y1y + y1p);
+            double glv = g.v + yv - hn * (A03 * y1x + A13 * y1y + A23 * y1p + y1v) - z[0] + z[1];
+            double jd = b0 * y1x + b1v * y1y + b2v * y1p;
+            if (MODEL && u) {   // the stage Jacobian of the Frenet map at the resulting point
+                const FJac J = frenet_jac(ncs, nsn, ncb, nsb, nb1, nq, nK, sx, sy, sv);
+                glx = g.x + yx - (J.a00 * y1x + J.a20 * y1p);
+                gly = g.y + yy - (J.a01 * y1x + hn * y1y + J.a21 * y1p);
+                glp = g.p + yp - (J.a02 * y1x + J.a12 * y1y + J.a22 * y1p);
+                glv = g.v + yv - (J.a03 * y1x + J.a13 * y1y + J.a23 * y1p + hn * y1v) - z[0] + z[1];
+                jd = J.b0 * y1x + J.b1 * y1y + J.b2 * y1p;
+            }
             const double nd0 = (k + 1 < N) ? yd1_0 : 0.0, nd1 = (k + 1 < N) ? yd1_1 : 0.0;
             const double gla = g.a - hn * c.dt * y1v + (ry1 - nd1) - z[2] + z[3];
             const double gld = g.d - hn * jd + (ry0 - nd0) - z[4] + z[5];
@@ -862,10 +1024,16 @@ struct TppSolver {
             const double rr = c.rfrac;
             const double inv = sqrt(1.0 / (cd * cd + rr * rr * sd * sd));
             const double cb = cd * inv, sb = rr * sd * inv;
-            const double n0 = s0 + c.dt * (s3 * (cps * cb - sps * sb));
+            double n0 = s0 + c.dt * (s3 * (cps * cb - sps * sb));
             const double n1 = s1 + c.dt * (s3 * (sps * cb + cps * sb));
-            const double n2 = s2 + c.dtLb * (s3 * sb);
+            double n2 = s2 + c.dtLb * (s3 * sb);
             const double n3 = s3 + c.dt * ua;
+            if (MODEL) {   // Frenet frame (MKZMPCPathFollowerFrenet.jl:111-120): (s, e_y, e_psi, v)
+                const double K = curvature(s0).K;
+                const double g = s3 * (cps * cb - sps * sb) / (1.0 - s1 * K);
+                n0 = s0 + c.dt * g;
+                n2 = s2 + (c.dtLb * (s3 * sb) - c.dt * (g * K));
+            }
             s0 = n0; s1 = n1; s2 = n2; s3 = n3; pa = ua; pd = ud;
         }
         m.sto(TF_SX, N, s0); m.sto(TF_SY, N, s1); m.sto(TF_SP, N, s2); m.sto(TF_SV, N, s3); m.sto(TF_UA, N, 0.0); m.sto(TF_UD, N, 0.0);
@@ -1163,5 +1331,6 @@ struct TppSolver {
         if (io.resto) io.resto[b] = n_resto;
     }
 };
+typedef TppSolverT<0> TppSolver;
 
 }  // namespace mpcb200

@@ -97,7 +97,8 @@ def solve_batch_tpp(kcfg, state, ref, v_des, u_prev, warm=None, want_traj=False,
     return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj, "n_resto": resto, "ticks": ticks}
 
 
-def solve_batch_frenet(kcfg, state, kpoly, v_des, u_prev, warm=None, want_traj=False):
+def solve_batch_frenet(kcfg, state, kpoly, v_des, u_prev, warm=None, want_traj=False, tpp=False, slots=3):
+    """Frenet-frame variant on the emulator; tpp: the thread-per-problem solver (TppSolverT<1>) instead of the warp kernel."""
     lib = C.CDLL(build())
     assert lib.emu_kcfg_size() == C.sizeof(KCfg)
     B = state.shape[0]
@@ -109,6 +110,15 @@ def solve_batch_frenet(kcfg, state, kpoly, v_des, u_prev, warm=None, want_traj=F
     v_des = None if v_des is None else np.ascontiguousarray(v_des, dtype=np.float64)
     u0 = np.empty((B, 2)); cost = np.empty(B); status = np.empty(B, dtype=np.int32); iters = np.empty(B, dtype=np.int32)
     traj = np.empty((B, 6 * N + 4)) if want_traj else None
+    if tpp:
+        resto = np.empty(B, dtype=np.int32)
+        lib.emu_solve_batch_tpp_frenet.argtypes = [C.POINTER(KCfg), C.c_long, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp,
+                                                   C.POINTER(C.c_int), C.c_long]
+        rc = lib.emu_solve_batch_tpp_frenet(C.byref(kcfg), B, p(state), p(kpoly), p(v_des), p(u_prev), p(warm), p(u0), p(cost),
+                                            status.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)), p(traj),
+                                            resto.ctypes.data_as(C.POINTER(C.c_int)), slots)
+        assert rc == 0
+        return {"u0": u0, "cost": cost, "status": status, "iters": iters, "traj": traj, "n_resto": resto}
     lib.emu_solve_batch_frenet.argtypes = [C.POINTER(KCfg), C.c_long, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp]
     rc = lib.emu_solve_batch_frenet(C.byref(kcfg), B, p(state), p(kpoly), p(v_des), p(u_prev), p(warm), p(u0), p(cost),
                                     status.ctypes.data_as(C.POINTER(C.c_int)), iters.ctypes.data_as(C.POINTER(C.c_int)), p(traj))

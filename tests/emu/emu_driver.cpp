@@ -325,3 +325,22 @@ extern "C" int emu_rollout_tpp(const KCfg* cfg, long B, int T, const double* pos
     }
     return 0;
 }
+
+// thread-per-problem solver, Frenet-frame variant (MODEL 1): ref = [B][4] curvature polynomial
+extern "C" int emu_solve_batch_tpp_frenet(const KCfg* cfg, long B, const double* state, const double* kpoly, const double* v_des,
+                                          const double* u_prev, double* warm, double* u0, double* cost, int* status, int* iters,
+                                          double* traj, int* resto, long S) {
+    BatchPtrs io{state, kpoly, v_des, u_prev, warm, u0, cost, status, iters, traj, nullptr, resto};
+    KCfg kc = *cfg;
+    kcfg_finalize(kc);
+    if (S < 1) S = 1;
+    std::vector<double> st(tpp_state_doubles(kc.N, S, 1), 0.0 / 0.0), filt(tpp_filter_doubles(S), 0.0 / 0.0);
+    for (long b = 0; b < B; b++) {
+        TppMemT<1> m(st.data(), filt.data(), kc.N, b % S);
+        TppSolverT<1> sv(kc, m);
+        sv.begin(io, b);
+        while (!sv.tick(true)) {}
+        sv.finish(io, b);
+    }
+    return 0;
+}

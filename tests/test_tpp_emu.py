@@ -124,3 +124,45 @@ def test_thread_per_problem_closed_loop(oracle):
     assert (log[:, -1, 6] == -1).any() and (log[-1, -1, 4:6] == [-1.0, 0.0]).all()     # the last vehicle ran into the stop latch
     wlog, wfinal = E.rollout(E.kcfg_from_oracle(cfg), g.trajectory, poses, T, warm0=seed)
     assert np.array_equal(log[:, :, 6:8], wlog[:, :, 6:8]) and np.abs(log - wlog).max() <= 1e-9 and np.abs(final - wfinal).max() <= 1e-9
+
+
+def _frenet_stress_batch(B, N, seed):
+    """Tighter curves and larger offsets than the recorded paths give (as in tests/test_frenet.py)."""
+    rng = np.random.default_rng(seed)
+    b = W.make_frenet_batch(B, N)
+    b["kpoly"] = np.stack([rng.uniform(-2e-6, 2e-6, B), rng.uniform(-1e-4, 1e-4, B), rng.uniform(-2e-3, 2e-3, B),
+                           rng.uniform(-0.05, 0.05, B)], axis=1)
+    b["state"][:, 1] = rng.uniform(-1.0, 1.0, B)
+    b["state"][:, 2] = rng.uniform(-0.3, 0.3, B)
+    return b
+
+
+@pytest.mark.parametrize("N,B,stress", [(8, 64, False), (20, 40, False), (3, 12, False), (8, 48, True), (20, 32, True), (40, 6, True)])
+def test_thread_per_problem_frenet_matches_oracle(oracle, N, B, stress):
+    """The Frenet-frame variant (MKZMPCPathFollowerFrenet.jl) in the thread-per-problem layout: dense s / e_y columns of the stage
+    Jacobian, the 5x5 Lagrangian-Hessian block, the dense costate recursion -- against the oracle iterate for iterate, and against the
+    emulated warp kernel."""
+    import emu as E
+    cfg = oracle.default_cfg_frenet(N)
+    b = _frenet_stress_batch(B, N, 5) if stress else W.make_frenet_batch(B, N)
+    o = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], want_traj=True, n_threads=4)
+    e = E.solve_batch_frenet(E.kcfg_from_oracle(cfg), b["state"], b["kpoly"], b["v_des"], b["u_prev"], want_traj=True, tpp=True, slots=33)
+    assert (o["status"] == e["status"]).all() and (o["iters"] == e["iters"]).all()
+    ok = o["status"] == 0
+    assert ok.sum() >= B - 1
+    assert np.abs(o["u0"] - e["u0"])[ok].max() <= 1e-9
+    assert (np.abs(o["cost"] - e["cost"])[ok] <= 1e-9 * np.maximum(1, np.abs(o["cost"][ok]))).all()
+    assert np.abs(o["traj"] - e["traj"])[ok].max() <= 1e-8
+    wo, we = o["traj"].copy(), o["traj"].copy()
+    o2 = oracle.solve_batch_frenet(cfg, b["state"], b["kpoly"], b["v_des"], b["u_prev"], warm=wo, n_threads=4)
+    e2 = E.solve_batch_frenet(E.kcfg_from_oracle(cfg), b["state"], b["kpoly"], b["v_des"], b["u_prev"], warm=we, tpp=True)
+    assert (o2["status"] == e2["status"]).all() and (o2["iters"] == e2["iters"]).all()
+    assert np.abs(o2["u0"] - e2["u0"])[o2["status"] == 0].max() <= 1e-9
+    if N <= 20:
+        w = E.solve_batch_frenet(E.kcfg_from_oracle(cfg), b["state"][:8], b["kpoly"][:8], b["v_des"][:8], b["u_prev"][:8], want_traj=True)
+        assert (w["status"] == e["status"][:8]).all() and (w["iters"] == e["iters"][:8]).all() and np.abs(w["traj"] - e["traj"][:8]).max() <= 1e-9
+    # MPCB200_START_ROLLOUT rolls the Frenet map out
+    k1 = E.kcfg_from_oracle(cfg, start_mode=1)
+    r = E.solve_batch_frenet(k1, b["state"][:8], b["kpoly"][:8], b["v_des"][:8], b["u_prev"][:8], tpp=True)
+    both = (o["status"][:8] == 0) & (r["status"] == 0)
+    assert both.sum() >= 6 and np.abs(o["u0"][:8] - r["u0"])[both].max() <= 1e-5
