@@ -103,8 +103,10 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
  * agree to rounding, not bit for bit.
  *   min_batch  > 0: batches (per device) of at least min_batch problems use one thread per problem
  *   min_batch == 0: always one warp per problem
- *   min_batch  < 0: the default rule (N <= 10: 32,768, and 16,384 for warm-started or rollout-started batches, whose
- *                   solves all take about the same handful of iterations; N > 10: never), what a new handle starts with
+ *   min_batch  < 0: the default rule, what a new handle starts with.  XY model: N <= 10: 32,768, and 16,384 for warm-started or
+ *                   rollout-started batches, whose solves all take about the same handful of iterations; N > 10: never.
+ *                   Frenet-frame handles (every solve takes 14-17 iterations): 16,384 at N <= 10, 32,768 at longer horizons
+ *                   (N = 20, 65,536 problems: 4.2 M instead of 3.2 M solves/s)
  * mpcb200_rollout follows the same switch: fleets of at least min_batch vehicles per device (default rule: 8,192 at N <= 10) run
  * each control period as three launches over the whole fleet -- plant, waypoints, thread-per-problem solve warm-started in place
  * -- instead of one persistent kernel (16,384 vehicles x 500 periods: 0.67 s instead of 1.26 s; 65,536 x 100: 0.38 s instead of

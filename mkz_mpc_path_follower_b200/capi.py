@@ -284,6 +284,10 @@ class FrenetSolver(Solver):
         assert w.shape == (7,)
         self._check(lib().mpcb200_set_cost_frenet(self._h, w.ctypes.data_as(C.POINTER(C.c_double))))
 
+    def set_large_batch_path(self, min_batch=-1):
+        """Batches of at least `min_batch` problems use the thread-per-problem kernel (TppSolverT<1>); 0: never; < 0: the default rule."""
+        self._check(lib().mpcb200_set_large_batch_path(self._h, int(min_batch)))
+
     def solve_batch(self, state, k_coeffs, u_prev, v_des=None, warm=None, want_traj=False, want_aux=True):
         """state (B,4) = s, ey, epsi, v; k_coeffs (B,4) highest degree first; u_prev (B,2) = (d_f_current, acc_current);
         warm / traj (B,6N+4) = s, ey, v, epsi, d_f, acc."""

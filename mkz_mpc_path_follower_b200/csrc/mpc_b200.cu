@@ -101,11 +101,12 @@ mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const
 #define MPC_TPP_BLOCK 256
 #define MPC_TPP_MIN_BLOCKS 1
 #endif
+template <int MODEL>
 __global__ void __launch_bounds__(MPC_TPP_BLOCK, MPC_TPP_MIN_BLOCKS)
 mpc_solve_tpp_kernel(const KCfg cfg, const BatchPtrs io, const long long B, double* st, double* filt, unsigned long long* counter) {
     const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const TppMem mem(st, filt, cfg.N, slot);
-    TppSolver sv(cfg, mem);
+    const TppMemT<MODEL> mem(st, filt, cfg.N, slot);
+    TppSolverT<MODEL> sv(cfg, mem);
     bool alive = true;   // the counter has not run past the batch for this lane yet
     long b = -1;
     while (__syncthreads_or(alive)) {
@@ -422,6 +423,16 @@ int mpcb200_default_config(mpcb200_config* c, int32_t N) {
     return MPCB200_OK;
 }
 
+/* The default rule of mpcb200_set_large_batch_path, from measurements on the B200 (profiles/r02_logs/r02_tpp_thresholds.log,
+ * r02_tpp_frenet.log).  XY model from the all-zero start: iteration counts spread from 25 to 200, the streaming layout pays for
+ * the tail of long solves: N <= 10 only, from 32,768 problems.  Frenet-frame variant: every solve takes 14-17 iterations, the
+ * streaming layout wins at every horizon tried (N = 8: 1.3x / 1.9x / 2.1x at 16 K / 64 K / 256 K problems; N = 20: 0.94x / 1.47x /
+ * 1.30x at 16 K / 32 K / 64 K; N = 31, 40: 1.29x at 64 K). */
+static int64_t tpp_default_min_batch(int model, int N) {
+    if (model) return (N <= 10) ? 16384 : 32768;
+    return (N <= 10) ? 32768 : 0;
+}
+
 static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int model);
 static int create_multi(mpcb200_handle** out, const mpcb200_config* cfg, int model);
 int mpcb200_create(mpcb200_handle** out, const mpcb200_config* cfg) { return create_multi(out, cfg, 0); }
@@ -555,16 +566,17 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->rollout_blocks_per_sm, fr, h->team_warps * 32, rb));
         if (h->rollout_blocks_per_sm < 1) h->rollout_blocks_per_sm = 1;
     }
-    if (!model) {
+    {
         /* thread-per-problem path for large batches (any horizon): needs B >> resident lanes to keep them busy */
-        TRY_OR_FREE(cudaFuncSetAttribute(mpc_solve_tpp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
-        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tpp_blocks_per_sm, mpc_solve_tpp_kernel, MPC_TPP_BLOCK, 0));
+        const void* tk = model ? (const void*)mpc_solve_tpp_kernel<1> : (const void*)mpc_solve_tpp_kernel<0>;
+        TRY_OR_FREE(cudaFuncSetAttribute(tk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
+        TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tpp_blocks_per_sm, tk, MPC_TPP_BLOCK, 0));
         if (h->tpp_blocks_per_sm < 1) h->tpp_blocks_per_sm = 1;
         if (const char* e = getenv("MPCB200_TPP_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->tpp_blocks_per_sm) h->tpp_blocks_per_sm = v; }  /* tuning aid */
         if (const char* e = getenv("MPCB200_TPP_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= MPC_TPP_BLOCK && v % 32 == 0) h->tpp_block = v; }  /* tuning aid */
         /* measured (tools/tpp_ab.py, profiles/r02_logs/r02_tpp_thresholds.log): N = 8: 0.8x / 1.2x / 1.5x / 1.8x the warp-per-problem
          * kernel at 16 K / 32 K / 64 K / 128 K problems; N = 12, 16: break-even at ~128 K; N = 20: 0.65x at 64 K, 0.97x at 256 K */
-        h->tpp_min_batch = (cfg->N <= 10) ? 32768 : 0;
+        h->tpp_min_batch = tpp_default_min_batch(model, cfg->N);
         if (const char* e = getenv("MPCB200_TPP_MIN_BATCH")) { h->tpp_min_batch = atoll(e); h->tpp_default_rule = false; }   /* tuning aid; 0 switches the path off */
     }
     if (h->blocks_per_sm < 1) h->blocks_per_sm = 1;
@@ -605,8 +617,7 @@ int mpcb200_set_cost(mpcb200_handle* h, const double w[8]) {
 
 int mpcb200_set_large_batch_path(mpcb200_handle* h, int64_t min_batch) {
     if (!h) return MPCB200_EINVAL;
-    if (h->model) return fail(h, MPCB200_EINVAL, "mpcb200_set_large_batch_path: the Frenet-frame variant has one kernel layout");
-    const int64_t v = (min_batch < 0) ? ((h->cfg.N <= 10) ? 32768 : 0) : min_batch;
+    const int64_t v = (min_batch < 0) ? tpp_default_min_batch(h->model, h->cfg.N) : min_batch;
     h->tpp_min_batch = v; h->tpp_default_rule = (min_batch < 0);
     drop_graphs(h);   /* a captured small-batch graph holds the kernel it was captured with */
     for (int i = 0; i < h->n_sub; i++) { h->sub[i]->tpp_min_batch = v; h->sub[i]->tpp_default_rule = (min_batch < 0); drop_graphs(h->sub[i]); }
@@ -628,8 +639,8 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
     /* starts next to the solution (warm start, rollout start) take a handful of iterations each, all about the same number:
      * no tail of long solves, so the streaming layout already pays at half the batch (measured at N = 8, 16,384 problems:
      * 1.06x warm, 1.30x from the rollout start; profiles/r02_logs/r02_tpp_warm.log) */
-    const int64_t tpp_from = (h->tpp_default_rule && (io.warm || h->cfg.start_mode == MPCB200_START_ROLLOUT)) ? h->tpp_min_batch / 2 : h->tpp_min_batch;
-    if (!h->model && !rg.path_of && !zeroed_counter && h->tpp_min_batch > 0 && B >= tpp_from) {
+    const int64_t tpp_from = (h->tpp_default_rule && !h->model && (io.warm || h->cfg.start_mode == MPCB200_START_ROLLOUT)) ? h->tpp_min_batch / 2 : h->tpp_min_batch;
+    if (!rg.path_of && !zeroed_counter && h->tpp_min_batch > 0 && B >= tpp_from) {
         /* thread-per-problem: as many slots as lanes can be resident, never more than problems */
         const int tb = h->tpp_block;
         long long blocks = (long long)h->num_sms * h->tpp_blocks_per_sm;
@@ -637,10 +648,14 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
         if (blocks > need) blocks = need;
         const long long S = blocks * tb;
         int rc;
-        if ((rc = ensure(h, h->d_tpp_state, tpp_state_doubles(h->cfg.N, (long)S) * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_tpp_state, tpp_state_doubles(h->cfg.N, (long)S, h->model) * sizeof(double)))) return rc;
         if ((rc = ensure(h, h->d_tpp_filt, tpp_filter_doubles((long)S) * sizeof(double)))) return rc;
-        mpc_solve_tpp_kernel<<<(int)blocks, tb, 0, h->stream>>>(make_kcfg(h), io, (long long)B, (double*)h->d_tpp_state.p,
-                                                               (double*)h->d_tpp_filt.p, counter);
+        if (h->model)
+            mpc_solve_tpp_kernel<1><<<(int)blocks, tb, 0, h->stream>>>(make_kcfg(h), io, (long long)B, (double*)h->d_tpp_state.p,
+                                                                      (double*)h->d_tpp_filt.p, counter);
+        else
+            mpc_solve_tpp_kernel<0><<<(int)blocks, tb, 0, h->stream>>>(make_kcfg(h), io, (long long)B, (double*)h->d_tpp_state.p,
+                                                                      (double*)h->d_tpp_filt.p, counter);
         CUDA_TRY(h, cudaGetLastError());
         h->stats.kernel_launches += 1;
         return 0;

@@ -604,8 +604,12 @@ def _frenet_stress(b, seed):
 
 @pytest.mark.parametrize("N,B,stress", [(8, 512, False), (20, 384, False), (3, 32, False), (31, 32, False), (8, 256, True), (20, 256, True),
                                             (32, 48, False), (40, 128, True), (64, 32, False), (80, 64, True), (95, 16, False)])
-def test_frenet_cold_and_warm_parity(capi, oracle, N, B, stress):
+@pytest.mark.parametrize("layout", ["warp", "thread"])
+def test_frenet_cold_and_warm_parity(capi, oracle, N, B, stress, layout):
     s = capi.FrenetSolver(N)
+    s.set_large_batch_path(0 if layout == "warp" else 1)     # both device layouts (the second: TppSolverT<1>, csrc/tpp_solver.cuh)
+    if layout == "thread":
+        B += 64                                              # (host batches of up to 64 problems always take the small-batch path)
     b = W.make_frenet_batch(B, N)
     if stress:
         b = _frenet_stress(b, 17)
@@ -769,13 +773,21 @@ def test_frenet_edge_cases(capi, oracle):
     assert np.abs(g["u0"] - o["u0"])[ok].max() <= U_TOL
     with pytest.raises(ValueError):
         s.solve_batch(np.zeros((2, 4)), np.zeros((2, 3)), np.zeros((2, 2)))
+    # the same degenerate problems (tiled past the small-batch path) through the thread-per-problem layout
+    s.set_large_batch_path(1)
+    rep = 12
+    gt = s.solve_batch(np.tile(b["state"], (rep, 1)), np.tile(b["kpoly"], (rep, 1)), np.tile(b["u_prev"], (rep, 1)), v_des=np.tile(b["v_des"], rep))
+    assert gt["status"].tolist() == [4, 4, 3, 1, 0, 0] * rep
+    assert np.abs(gt["u0"][:6] - o["u0"])[ok].max() <= U_TOL and np.array_equal(gt["u0"][6:12][ok], gt["u0"][:6][ok])
 
 
-def test_frenet_large_batch_oracle_parity(capi, oracle):
+@pytest.mark.parametrize("layout", ["warp", "thread"])
+def test_frenet_large_batch_oracle_parity(capi, oracle, layout):
     """16,384 Frenet problems at N = 20, every one compared with the oracle: same status, the same iteration count
-    on (nearly) all, |du| far inside the 1e-5 bar."""
+    on (nearly) all, |du| far inside the 1e-5 bar.  Both device layouts."""
     N, B = 20, 16384
     s = capi.FrenetSolver(N)
+    s.set_large_batch_path(0 if layout == "warp" else 1)
     b = W.make_frenet_batch(B, N, b0=65536)
     g = s.solve_batch(b["state"], b["kpoly"], b["u_prev"], v_des=b["v_des"])
     o = oracle.solve_batch_frenet(oracle.default_cfg_frenet(N, tol=s.cfg.tol, max_iter=s.cfg.max_iter), b["state"], b["kpoly"],
