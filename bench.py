@@ -687,6 +687,7 @@ def main():
             fd = {k_: torch.from_numpy(fb[k_]).to(dev) for k_ in ("state", "kpoly", "u_prev", "v_des")}
             f_u0 = torch.empty((B, 2), dtype=torch.float64, device=dev); f_st = torch.empty(B, dtype=torch.int32, device=dev)
             f_it = torch.empty(B, dtype=torch.int32, device=dev)
+            f_u0w = torch.empty_like(f_u0); f_stw = torch.empty_like(f_st); f_itw = torch.empty_like(f_it)
             f_ms = []
             for i in range(3 + args.steps):
                 flush.fill_(1)
@@ -697,13 +698,33 @@ def main():
                 if i >= 3:
                     f_ms.append(e0.elapsed_time(e1))
             fst = f_st.cpu().numpy(); fit = f_it.cpu().numpy()
+            # the same batch through the warp-per-problem kernel (the library's default rule takes the thread-per-problem layout
+            # for Frenet batches of >= 32,768 problems, >= 16,384 at N <= 10)
+            f_tpp = B >= (16384 if N <= 10 else 32768)
+            f_warp_ms = None
+            if f_tpp:
+                fs.set_large_batch_path(0)
+                w_ms = []
+                for i in range(2):
+                    flush.fill_(1)
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    fs.solve_batch_device(B, fd["state"], fd["kpoly"], fd["u_prev"], f_u0w, v_des=fd["v_des"], status=f_stw, iters=f_itw)
+                    e1.record(stream); torch.cuda.synchronize()
+                    w_ms.append(e0.elapsed_time(e1))
+                f_warp_ms = float(min(w_ms))
+                fs.set_large_batch_path(-1)
             from oracle import oracle as O
             n_s = min(B, 512)
             fo = O.solve_batch_frenet(O.default_cfg_frenet(N, max_iter=int(fs.cfg.max_iter)), fb["state"][:n_s], fb["kpoly"][:n_s],
                                       fb["v_des"][:n_s], fb["u_prev"][:n_s], n_threads=cores)
             fok = (fo["status"] == 0) & (fst[:n_s] == 0)
             line["frenet_variant"] = {
-                "value": float((fst == 0).sum()) / (float(np.mean(f_ms)) * 1e-3), "unit": "solves/s", "kernel": "mpc_solve_frenet_kernel",
+                "value": float((fst == 0).sum()) / (float(np.mean(f_ms)) * 1e-3), "unit": "solves/s",
+                "kernel": "mpc_solve_tpp_kernel<1> (thread per problem)" if f_tpp else "mpc_solve_frenet_kernel",
+                "warp_per_problem_kernel_ms": f_warp_ms,
+                "layouts_agree": None if f_warp_ms is None else {"status_equal": bool((f_stw.cpu().numpy() == fst).all()), "iters_equal": bool((f_itw.cpu().numpy() == fit).all()),
+                                                                 "max_abs_du": float(np.abs(f_u0w.cpu().numpy() - f_u0.cpu().numpy()).max())},
                 "kernel_ms": float(np.mean(f_ms)), "converged_frac": float((fst == 0).mean()), "mean_iters": float(fit.mean()),
                 "fp64_tflops": float(fit.astype(np.float64).sum()) * (F_RIC + F_EVAL) * N / (float(np.mean(f_ms)) * 1e-3) / 1e12,
                 "parity_vs_oracle": {"sample": n_s, "status_equal": bool((fo["status"] == fst[:n_s]).all()),
