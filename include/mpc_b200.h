@@ -107,7 +107,8 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
  *                   rollout-started batches, whose solves all take about the same handful of iterations; N > 10: never.
  *                   Frenet-frame handles (every solve takes 14-17 iterations): 16,384 at N <= 10, 32,768 at longer horizons
  *                   (N = 20, 65,536 problems: 4.2 M instead of 3.2 M solves/s)
- * mpcb200_rollout follows the same switch: fleets of at least min_batch vehicles per device (default rule: 8,192 at N <= 10) run
+ * mpcb200_rollout and mpcb200_rollout_frenet follow the same switch: fleets of at least min_batch vehicles per device (default rule:
+ * a quarter of the batch rule, i.e. 8,192 vehicles at N <= 10 for the XY model, 4,096 for the Frenet node) run
  * each control period as three launches over the whole fleet -- plant, waypoints, thread-per-problem solve warm-started in place
  * -- instead of one persistent kernel (16,384 vehicles x 500 periods: 0.67 s instead of 1.26 s; 65,536 x 100: 0.38 s instead of
  * 1.39 s). */

@@ -167,20 +167,34 @@ rollout_waypoints_kernel(const KCfg cfg, const long long B, const long long Bp, 
     }
 }
 
+// MODEL 0: reference samples already in the slots, stop latch, the first solve from the module-load solution `warm0`.
+// MODEL 1 (closed loop of the Frenet node, gazebo_sim_mpc_cmd_pub_frenet.jl:112-153): `fref` = [6][Bp] curvature polynomial (4),
+// e_y, psi_start per vehicle from rollout_frenet_ref_kernel; state (0, e_y, -psi_start, v); the first solve from all zeros.
+template <int MODEL>
 __global__ void __launch_bounds__(MPC_TPP_BLOCK, MPC_TPP_MIN_BLOCKS)
 rollout_solve_tpp_kernel(const KCfg cfg, const long long B, const long long Bp, double* veh, const int* stop, double* tpp_state, double* tpp_filt,
-                         const double* warm0, const double des_speed, BatchPtrs out, double* log_row) {
+                         const double* warm0, const double des_speed, BatchPtrs out, double* log_row, const double* fref, const int first) {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = v < B;
-    const TppMem mem(tpp_state, tpp_filt, cfg.N, (long)(valid ? v : 0));
-    TppSolver sv(cfg, mem);
-    const bool stopped = valid && stop[v] != 0;
+    const TppMemT<MODEL> mem(tpp_state, tpp_filt, cfg.N, (long)(valid ? v : 0));
+    TppSolverT<MODEL> sv(cfg, mem);
+    const bool stopped = valid && !MODEL && stop[v] != 0;
     bool live = valid && !stopped;
     double st4[4] = {0.0, 0.0, 0.0, 0.0};
     if (valid) for (int i = 0; i < 4; i++) st4[i] = veh[i * Bp + v];
     if (live) {
-        const double c7[7] = {st4[0], st4[1], st4[2], st4[3], veh[10 * Bp + v], veh[11 * Bp + v], des_speed};
-        sv.begin_in_place(c7, warm0);
+        if (MODEL) {
+            for (int i = 0; i < 4; i++) sv.kp[i] = fref[i * Bp + v];
+            const double c7[7] = {0.0, fref[4 * Bp + v], -fref[5 * Bp + v], st4[3], veh[10 * Bp + v], veh[11 * Bp + v], des_speed};
+            if (first) {   // start = 0.0, then the previous solution
+                for (int k = 0; k <= cfg.N; k++) for (int f = TF_SX; f <= TF_UD; f++) mem.sto(f, k, 0.0);
+                for (int k = 0; k <= cfg.N; k++) { mem.sto(TF_XR, k, 0.0); mem.sto(TF_YR, k, 0.0); mem.sto(TF_PR, k, 0.0); }
+            }
+            sv.begin_in_place(c7, nullptr);
+        } else {
+            const double c7[7] = {st4[0], st4[1], st4[2], st4[3], veh[10 * Bp + v], veh[11 * Bp + v], des_speed};
+            sv.begin_in_place(c7, warm0);
+        }
     }
     bool solved = false;
     while (__syncthreads_or(live)) {
@@ -197,6 +211,56 @@ rollout_solve_tpp_kernel(const KCfg cfg, const long long B, const long long Bp, 
     if (log_row) {
         double* r = log_row + 8 * v;
         r[0] = st4[0]; r[1] = st4[1]; r[2] = st4[2]; r[3] = st4[3]; r[4] = acc_des; r[5] = df_des; r[6] = status; r[7] = iters;
+    }
+}
+
+// Frenet node, per control period and vehicle (warp = vehicle): the path ahead of the nearest sample resampled every 0.5 m in the
+// vehicle frame, two cubic least-squares fits X(s), Y(s) on that fixed grid, the curvature of the fitted cubics every 0.25 m fitted
+// by a cubic (nav_msgs_path_frenet.py:44-86), psi_start and e_y -- what rollout_group_frenet does inside the fused kernel
+__global__ void __launch_bounds__(128)
+rollout_frenet_ref_kernel(const KCfg cfg, const FrenetRolloutArgs a, const long long Bp, const double* veh, double* fref) {
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int k = threadIdx.x & 31;
+    TeamSolver<1, 1> S(cfg, (smem_t)0);   // (one-warp teams: collectives are shuffles only)
+    for (long long v = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < a.B; v += warps) {
+        const PathTable& path = a.paths[a.path_of[v]];
+        const double X = veh[v], Y = veh[Bp + v], yaw = veh[2 * Bp + v];
+        double bd = 1e300; int bi = 0x7fffffff;
+        for (int i = k; i < path.n; i += 32) {
+            const double dx = path.X[i] - X, dy = path.Y[i] - Y, d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+            if (d < bd) { bd = d; bi = i; }
+        }
+        S.targmin(bd, bi);
+        const double s_i = path.s[bi];
+        double sps, cps;
+        mpc_sincos(yaw, &sps, &cps);
+        double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xw0 = 0.0, yw0 = 0.0;
+        for (int g = k; g < a.n1; g += 32) {
+            const double sq = s_i + 0.5 * (double)g;
+            const double dx = np_interp(sq, path.s, path.X, path.n) - X, dy = np_interp(sq, path.s, path.Y, path.n) - Y;
+            const double xw = cps * dx + sps * dy, yw = -sps * dx + cps * dy;
+            if (g == 0) { xw0 = xw; yw0 = yw; }
+            for (int r = 0; r < 4; r++) { const double pr = a.P1[r * a.n1 + g]; acc8[r] += pr * xw; acc8[4 + r] += pr * yw; }
+        }
+        S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8); S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8 + 3);
+        S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(acc8 + 6);
+        xw0 = shfl(xw0, 0); yw0 = shfl(yw0, 0);
+        const double* xc = acc8; const double* yc = acc8 + 4;   // cubic coefficients, highest degree first
+        double kc[4] = {0, 0, 0, 0};
+        for (int g = k; g < a.n2; g += 32) {
+            const double tt = 0.25 * (double)g;
+            const double dx = xc[2] + 2.0 * xc[1] * tt + 3.0 * xc[0] * (tt * tt), dy = yc[2] + 2.0 * yc[1] * tt + 3.0 * yc[0] * (tt * tt);
+            const double ddx = 2.0 * xc[1] + 6.0 * xc[0] * tt, ddy = 2.0 * yc[1] + 6.0 * yc[0] * tt;
+            const double Km = (dx * ddy - dy * ddx) / (dx * dx + dy * dy);
+            for (int r = 0; r < 4; r++) kc[r] += a.P2[r * a.n2 + g] * Km;
+        }
+        S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc); S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc + 2);
+        const double psi0 = atan2(yc[2], xc[2]);
+        double sp0, cp0;
+        mpc_sincos(psi0, &sp0, &cp0);
+        const double ey = a.ey_from_path ? -(-sp0 * xw0 + cp0 * yw0) : 0.0;
+        if (k < 6) fref[k * Bp + v] = (k < 4) ? sel8(kc, k) : (k == 4 ? ey : psi0);
+        __syncwarp();
     }
 }
 
@@ -1150,9 +1214,9 @@ static int rollout_enqueue(mpcb200_handle* h, int64_t n, int32_t T, const double
             rollout_plant_kernel<<<pgrid, 128, 0, s>>>((long long)n, Bp, veh, a.pose0, t == 0);
             rollout_waypoints_kernel<<<wgrid, 128, 0, s>>>(kc, (long long)n, Bp, veh, a.path_of, rg, (double*)h->d_tpp_state.p, (double*)h->d_tpp_filt.p,
                                                           (int*)h->d_vstop.p, t == 0);
-            rollout_solve_tpp_kernel<<<(int)sblocks, tb, 0, s>>>(kc, (long long)n, Bp, veh, (const int*)h->d_vstop.p, (double*)h->d_tpp_state.p,
-                                                                (double*)h->d_tpp_filt.p, t == 0 ? a.warm0 : nullptr, des_speed, out,
-                                                                a.log ? a.log + (size_t)t * n * 8 : nullptr);
+            rollout_solve_tpp_kernel<0><<<(int)sblocks, tb, 0, s>>>(kc, (long long)n, Bp, veh, (const int*)h->d_vstop.p, (double*)h->d_tpp_state.p,
+                                                                   (double*)h->d_tpp_filt.p, t == 0 ? a.warm0 : nullptr, des_speed, out,
+                                                                   a.log ? a.log + (size_t)t * n * 8 : nullptr, nullptr, t == 0);
             CUDA_TRY(h, cudaGetLastError());
         }
         if (a.final_state) rollout_final_kernel<<<pgrid, 128, 0, s>>>((long long)n, Bp, veh, a.final_state);
@@ -1278,6 +1342,48 @@ int mpcb200_rollout_frenet(mpcb200_handle* h, int64_t B, int32_t T, const double
     a.T = T; a.ey_from_path = ey_from_path; a.target_vel = target_vel;
     a.log = log ? (double*)h->d_log.p : nullptr; a.final_state = final_state ? (double*)h->d_final.p : nullptr; a.B = (long)B;
     a.P1 = (const double*)h->d_fit.p; a.P2 = a.P1 + 4 * (size_t)h->fit_n1; a.n1 = h->fit_n1; a.n2 = h->fit_n2;
+    /* large fleets: one control period = plant / Frenet reference / thread-per-problem solve over the whole fleet (as mpcb200_rollout
+     * does for the XY model); the default switch is a quarter of the batch rule */
+    const int64_t roll_from = h->tpp_default_rule ? h->tpp_min_batch / 4 : h->tpp_min_batch;
+    if (h->tpp_min_batch > 0 && B >= roll_from) {
+        const long long Bp = (B + 31) / 32 * 32;
+        const int tb = h->tpp_block < 128 ? h->tpp_block : 128;
+        const long long sblocks = (B + tb - 1) / tb, S = sblocks * tb;
+        if ((rc = ensure(h, h->d_tpp_state, tpp_state_doubles(h->cfg.N, (long)S, 1) * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_tpp_filt, tpp_filter_doubles((long)S) * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_veh, (size_t)(RV_NF + 6) * Bp * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_u0, (size_t)B * 2 * sizeof(double)))) return rc;
+        if ((rc = ensure(h, h->d_status, (size_t)B * sizeof(int32_t)))) return rc;
+        if ((rc = ensure(h, h->d_iters, (size_t)B * sizeof(int32_t)))) return rc;
+        BatchPtrs out;
+        memset(&out, 0, sizeof(out));
+        out.u0 = (double*)h->d_u0.p; out.status = (int*)h->d_status.p; out.iters = (int*)h->d_iters.p;
+        const KCfg kc = make_kcfg(h);
+        double* veh = (double*)h->d_veh.p;
+        double* fref = veh + (size_t)RV_NF * Bp;
+        const int pgrid = (int)((B + 127) / 128);
+        long long wblocks = (B + 3) / 4, wmax = (long long)h->num_sms * 16;
+        const int wgrid = (int)(wblocks < wmax ? wblocks : wmax);
+        CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+        for (int t = 0; t < T; t++) {
+            rollout_plant_kernel<<<pgrid, 128, 0, s>>>((long long)B, Bp, veh, a.pose0, t == 0);
+            rollout_frenet_ref_kernel<<<wgrid, 128, 0, s>>>(kc, a, Bp, veh, fref);
+            rollout_solve_tpp_kernel<1><<<(int)sblocks, tb, 0, s>>>(kc, (long long)B, Bp, veh, nullptr, (double*)h->d_tpp_state.p, (double*)h->d_tpp_filt.p,
+                                                                   nullptr, target_vel, out, a.log ? a.log + (size_t)t * B * 8 : nullptr, fref, t == 0);
+            CUDA_TRY(h, cudaGetLastError());
+        }
+        if (a.final_state) rollout_final_kernel<<<pgrid, 128, 0, s>>>((long long)B, Bp, veh, a.final_state);
+        CUDA_TRY(h, cudaGetLastError());
+        CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+        h->stats.kernel_launches += 3 * (int64_t)T + (a.final_state ? 1 : 0);
+        if (log) { CUDA_TRY(h, cudaMemcpyAsync(log, h->d_log.p, bl, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bl; }
+        if (final_state) { CUDA_TRY(h, cudaMemcpyAsync(final_state, h->d_final.p, bf, cudaMemcpyDeviceToHost, s)); h->stats.d2h_bytes += bf; }
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        float ms2 = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms2, h->ev0, h->ev1));
+        h->stats.kernel_ms = ms2;
+        return MPCB200_OK;
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned long long), s));
     long long blocks_needed = (B + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     long long max_blocks = (long long)h->num_sms * h->frenet_rollout_blocks_per_sm;

@@ -261,3 +261,28 @@ def test_tpp_closed_loop_fleet(capi, oracle):
         olog = oracle.closed_loop(cfg, path, pose0[b], T)
         assert np.array_equal(lt[:, b, 6], olog[:, 6]), b
         assert np.abs(lt[:, b, 0:6] - olog[:, 0:6]).max() <= (1e-8 if np.array_equal(lt[:, b, 7], olog[:, 7]) else 1e-4), b
+
+
+def test_tpp_frenet_closed_loop_fleet(capi):
+    """mpcb200_rollout_frenet as a per-period pipeline (plant / path ahead + the two cubic fits / thread-per-problem Frenet solve)
+    against the fused kernel on the same fleet: same statuses and iteration counts, poses and commands equal to rounding."""
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    N, B, T = 8, 300, 25
+    trajs = [GPSRefTrajectory(mat_filename=p) for p in (1, 2, 3)]
+    rng = np.random.default_rng(33)
+    path_of = (np.arange(B) % 3).astype(np.int32)
+    pose0 = np.stack([trajs[p].trajectory[(53 * (i + 1)) % (trajs[p].trajectory.shape[0] - 1500), [4, 5, 3]] + rng.normal(scale=[0.3, 0.3, 0.03])
+                      for i, p in enumerate(path_of)])
+    out = {}
+    for name, mb in (("warp", 0), ("tpp", 1)):
+        s = capi.FrenetSolver(N)
+        s.set_large_batch_path(mb)
+        for i, g in enumerate(trajs):
+            s.set_path(i, g.trajectory)
+        out[name] = s.rollout(pose0, path_of, T)
+        out[name + "_launches"] = s.stats()["kernel_launches"]
+    assert out["warp_launches"] == 1 and out["tpp_launches"] == 3 * T + 1
+    lw, lt = out["warp"]["log"], out["tpp"]["log"]
+    assert np.array_equal(lw[:, :, 6:8], lt[:, :, 6:8]) and (lt[:, :, 6] == 0).mean() >= 0.99
+    assert np.abs(lw[:, :, 0:6] - lt[:, :, 0:6]).max() <= 1e-8
+    assert np.abs(out["warp"]["final_state"] - out["tpp"]["final_state"]).max() <= 1e-8
