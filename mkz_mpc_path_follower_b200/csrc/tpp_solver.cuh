@@ -1,7 +1,7 @@
 // tpp_solver.cuh -- the large-batch solve path: ONE THREAD PER PROBLEM, the iterate streamed from HBM.
 //
-// What it replaces (reference file:line): the same solve(mdl) of scripts/mpc_utils/MKZMPCPathFollower.jl:176 as
-// mpc_kernel.cuh, on the same NLP (:65-123), with the same interior-point iteration (Ipopt 3.12 defaults, restated
+// What it replaces (reference file:line): the same solve(mdl) of scripts/mpc_utils/MKZMPCPathFollower.jl:176 (MODEL 1:
+// MKZMPCPathFollowerFrenet.jl:176) as mpc_kernel.cuh, on the same NLP (:65-123), with the same interior-point iteration (Ipopt 3.12 defaults, restated
 // formula for formula from TeamSolver::solve) and the same condensed Riccati linear algebra.
 //
 // Why a second layout.  The warp-per-problem kernel keeps a problem on chip (registers + 18 KB of shared memory), which
@@ -21,9 +21,12 @@
 // second-order correction) and extra trial points (backtracking) cost the lane that needs them one more trip.
 // Lanes are persistent: a lane whose problem ends writes the result and takes the next problem index from a device
 // counter, so a slot is always busy while work is left and a problem never changes its slot (coalescing is preserved).
-// Measured on the B200: the layout is HBM-bound (5.5 TB/s at N = 8); it beats the warp-per-problem kernel
-// at short horizons and large batches (N = 8: 1.5x at 65,536 problems, 2.1x at 262,144) and ties with it at N = 20, which
-// is why mpcb200_set_large_batch_path's default rule uses it for N <= 10 only.
+// Measured on the B200: the layout is HBM-bound (5.5 TB/s at N = 8).  It is at its best when the solves of a batch
+// take about the same number of iterations (no tail of long solves once the queue is empty): warm-started batches, closed-loop
+// fleets (one control period = plant / waypoints / this solve in place: configs[3] in 0.57 s instead of 1.25 s), and the
+// Frenet-frame variant (MODEL 1: 4.2 M instead of 3.2 M solves/s at N = 20).  From the XY model's all-zero start (25 to 200
+// iterations) it beats the warp-per-problem kernel at short horizons and large batches (N = 8: 1.5x at 65,536 problems, 2.1x at
+// 262,144) and ties with it at N = 20, which is what mpcb200_set_large_batch_path's default rule encodes.
 //
 // The file is plain scalar C++ behind MPC_DEV, so tests/emu compiles it with g++ and checks it against the oracle
 // iterate for iterate on the CPU (tests/test_tpp_emu.py).
