@@ -231,6 +231,21 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def frenet_roofline(kernel_ms, B, N):
+    """HBM roofline of the thread-per-problem Frenet kernel (it streams the iterate from HBM): DRAM bytes per launch as ncu measured
+    them for this very workload (profiles/dram_traffic_tpp_frenet.json), over the live kernel time, against the measured copy peak."""
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic_tpp_frenet.json")))
+        if tr["problems_per_launch"] != B or tr["horizon"] != N:
+            return None
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        ach = tr["bytes_per_launch"] / (kernel_ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if peak else None, "traffic": tr["bytes_per_launch"],
+                "traffic_source": tr["source"]}
+    except Exception:
+        return None
+
+
 def parity_counts(g_u0, g_cost, g_status, o, ids0=0):
     """a solve is converged only with status Optimal AND parity with the oracle: same status,
     |du| <= 1e-5 on the first move, relative cost <= 1e-6."""
@@ -729,6 +744,7 @@ def main():
                 "fp64_tflops": float(fit.astype(np.float64).sum()) * (F_RIC + F_EVAL) * N / (float(np.mean(f_ms)) * 1e-3) / 1e12,
                 "parity_vs_oracle": {"sample": n_s, "status_equal": bool((fo["status"] == fst[:n_s]).all()),
                                      "max_abs_du": float(np.abs(f_u0.cpu().numpy()[:n_s] - fo["u0"])[fok].max())},
+                "roofline": frenet_roofline(float(np.mean(f_ms)), B, N) if f_tpp else None,
                 "what": "same batch size and horizon, rank 0's slice, all-zero start, workload.make_frenet_batch"}
         except Exception as ex:   # the headline line must not depend on the variant
             line["frenet_variant"] = {"error": repr(ex)}

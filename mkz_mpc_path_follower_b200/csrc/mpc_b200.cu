@@ -214,51 +214,16 @@ rollout_solve_tpp_kernel(const KCfg cfg, const long long B, const long long Bp, 
     }
 }
 
-// Frenet node, per control period and vehicle (warp = vehicle): the path ahead of the nearest sample resampled every 0.5 m in the
-// vehicle frame, two cubic least-squares fits X(s), Y(s) on that fixed grid, the curvature of the fitted cubics every 0.25 m fitted
-// by a cubic (nav_msgs_path_frenet.py:44-86), psi_start and e_y -- what rollout_group_frenet does inside the fused kernel
+// Frenet node, per control period and vehicle (warp = vehicle): frenet_reference (mpc_kernel.cuh; nav_msgs_path_frenet.py:44-86) ->
+// curvature polynomial, e_y, psi_start, kept per vehicle for the solve kernel
 __global__ void __launch_bounds__(128)
 rollout_frenet_ref_kernel(const KCfg cfg, const FrenetRolloutArgs a, const long long Bp, const double* veh, double* fref) {
     const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int k = threadIdx.x & 31;
     TeamSolver<1, 1> S(cfg, (smem_t)0);   // (one-warp teams: collectives are shuffles only)
     for (long long v = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < a.B; v += warps) {
-        const PathTable& path = a.paths[a.path_of[v]];
-        const double X = veh[v], Y = veh[Bp + v], yaw = veh[2 * Bp + v];
-        double bd = 1e300; int bi = 0x7fffffff;
-        for (int i = k; i < path.n; i += 32) {
-            const double dx = path.X[i] - X, dy = path.Y[i] - Y, d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-            if (d < bd) { bd = d; bi = i; }
-        }
-        S.targmin(bd, bi);
-        const double s_i = path.s[bi];
-        double sps, cps;
-        mpc_sincos(yaw, &sps, &cps);
-        double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xw0 = 0.0, yw0 = 0.0;
-        for (int g = k; g < a.n1; g += 32) {
-            const double sq = s_i + 0.5 * (double)g;
-            const double dx = np_interp(sq, path.s, path.X, path.n) - X, dy = np_interp(sq, path.s, path.Y, path.n) - Y;
-            const double xw = cps * dx + sps * dy, yw = -sps * dx + cps * dy;
-            if (g == 0) { xw0 = xw; yw0 = yw; }
-            for (int r = 0; r < 4; r++) { const double pr = a.P1[r * a.n1 + g]; acc8[r] += pr * xw; acc8[4 + r] += pr * yw; }
-        }
-        S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8); S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8 + 3);
-        S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(acc8 + 6);
-        xw0 = shfl(xw0, 0); yw0 = shfl(yw0, 0);
-        const double* xc = acc8; const double* yc = acc8 + 4;   // cubic coefficients, highest degree first
-        double kc[4] = {0, 0, 0, 0};
-        for (int g = k; g < a.n2; g += 32) {
-            const double tt = 0.25 * (double)g;
-            const double dx = xc[2] + 2.0 * xc[1] * tt + 3.0 * xc[0] * (tt * tt), dy = yc[2] + 2.0 * yc[1] * tt + 3.0 * yc[0] * (tt * tt);
-            const double ddx = 2.0 * xc[1] + 6.0 * xc[0] * tt, ddy = 2.0 * yc[1] + 6.0 * yc[0] * tt;
-            const double Km = (dx * ddy - dy * ddx) / (dx * dx + dy * dy);
-            for (int r = 0; r < 4; r++) kc[r] += a.P2[r * a.n2 + g] * Km;
-        }
-        S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc); S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc + 2);
-        const double psi0 = atan2(yc[2], xc[2]);
-        double sp0, cp0;
-        mpc_sincos(psi0, &sp0, &cp0);
-        const double ey = a.ey_from_path ? -(-sp0 * xw0 + cp0 * yw0) : 0.0;
+        double kc[4], ey, psi0;
+        frenet_reference(S, a.paths[a.path_of[v]], a, veh[v], veh[Bp + v], veh[2 * Bp + v], kc, ey, psi0);
         if (k < 6) fref[k * Bp + v] = (k < 4) ? sel8(kc, k) : (k == 4 ? ey : psi0);
         __syncwarp();
     }

@@ -2226,6 +2226,51 @@ inline void cubic_fit_matrix(int n, double step, double* P) {
 }
 
 
+// The Frenet node's reference for one vehicle, computed by one warp (lane k): the path ahead of the nearest sample resampled every
+// 0.5 m in the vehicle frame, X(s) and Y(s) fitted by cubics on that fixed grid (nav_msgs_path_frenet.py:60-72), the curvature of the
+// fitted cubics every 0.25 m fitted by a cubic (:44-58), psi_start = atan2(Y'(0), X'(0)) (:84) and e_y.  Both least-squares fits are
+// the host-built matrices P1, P2 times the samples: lanes stride the samples, the partial sums are reduced over the warp.  Used by
+// the fused closed-loop kernel (rollout_group_frenet) and by the per-period pipeline (rollout_frenet_ref_kernel).
+MPC_DEV void frenet_reference(TeamSolver<1, 1>& S, const PathTable& path, const FrenetRolloutArgs& a, double X, double Y, double yaw,
+                              double kc[4], double& ey, double& psi0) {
+    const int k = S.k;
+    double bd = 1e300; int bi = 0x7fffffff;
+    for (int i = k; i < path.n; i += 32) {
+        const double dx = path.X[i] - X, dy = path.Y[i] - Y, d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+        if (d < bd) { bd = d; bi = i; }
+    }
+    S.targmin(bd, bi);
+    const double s_i = path.s[bi];
+    double sps, cps;
+    mpc_sincos(yaw, &sps, &cps);
+    double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xw0 = 0.0, yw0 = 0.0;
+    for (int g = k; g < a.n1; g += 32) {
+        const double sq = s_i + 0.5 * (double)g;
+        const double dx = np_interp(sq, path.s, path.X, path.n) - X, dy = np_interp(sq, path.s, path.Y, path.n) - Y;
+        const double xw = cps * dx + sps * dy, yw = -sps * dx + cps * dy;
+        if (g == 0) { xw0 = xw; yw0 = yw; }
+        for (int r = 0; r < 4; r++) { const double pr = a.P1[r * a.n1 + g]; acc8[r] += pr * xw; acc8[4 + r] += pr * yw; }
+    }
+    S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8); S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8 + 3);
+    S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(acc8 + 6);
+    xw0 = shfl(xw0, 0); yw0 = shfl(yw0, 0);
+    const double* xc = acc8; const double* yc = acc8 + 4;   // cubic coefficients, highest degree first
+    // ---- curvature of the fitted cubics every 0.25 m, fitted by a cubic
+    kc[0] = kc[1] = kc[2] = kc[3] = 0.0;
+    for (int g = k; g < a.n2; g += 32) {
+        const double tt = 0.25 * (double)g;
+        const double dx = xc[2] + 2.0 * xc[1] * tt + 3.0 * xc[0] * (tt * tt), dy = yc[2] + 2.0 * yc[1] * tt + 3.0 * yc[0] * (tt * tt);
+        const double ddx = 2.0 * xc[1] + 6.0 * xc[0] * tt, ddy = 2.0 * yc[1] + 6.0 * yc[0] * tt;
+        const double Km = (dx * ddy - dy * ddx) / (dx * dx + dy * dy);
+        for (int r = 0; r < 4; r++) kc[r] += a.P2[r * a.n2 + g] * Km;
+    }
+    S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc); S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc + 2);
+    psi0 = atan2(yc[2], xc[2]);
+    double sp0, cp0;
+    mpc_sincos(psi0, &sp0, &cp0);
+    ey = a.ey_from_path ? -(-sp0 * xw0 + cp0 * yw0) : 0.0;
+}
+
 MPC_DEV void rollout_group_frenet(const KCfg& cfg, const FrenetRolloutArgs& a, long b0, smem_t smem, smem_t px, int nwarps) {
     TeamSolver<1, 1> S(cfg, smem);
     const int k = S.k, N = cfg.N;
@@ -2252,42 +2297,9 @@ MPC_DEV void rollout_group_frenet(const KCfg& cfg, const FrenetRolloutArgs& a, l
         block_sync();
         if (!valid) continue;
         for (int i = 0; i < 8; i++) st[i] = lds(px, pxw + SO(i));
-        // ---- the path ahead: nearest sample, then the window resampled every 0.5 m in the vehicle frame
-        double bd = 1e300; int bi = 0x7fffffff;
-        for (int i = k; i < path.n; i += 32) {
-            const double dx = path.X[i] - st[0], dy = path.Y[i] - st[1], d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-            if (d < bd) { bd = d; bi = i; }
-        }
-        S.targmin(bd, bi);
-        const double s_i = path.s[bi];
-        double sps, cps;
-        mpc_sincos(st[2], &sps, &cps);
-        double acc8[8] = {0, 0, 0, 0, 0, 0, 0, 0}, xw0 = 0.0, yw0 = 0.0;
-        for (int g = k; g < a.n1; g += 32) {
-            const double sq = s_i + 0.5 * (double)g;
-            const double dx = np_interp(sq, path.s, path.X, path.n) - st[0], dy = np_interp(sq, path.s, path.Y, path.n) - st[1];
-            const double xw = cps * dx + sps * dy, yw = -sps * dx + cps * dy;
-            if (g == 0) { xw0 = xw; yw0 = yw; }
-            for (int r = 0; r < 4; r++) { const double pr = a.P1[r * a.n1 + g]; acc8[r] += pr * xw; acc8[4 + r] += pr * yw; }
-        }
-        S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8); S.template treduce<TeamSolver<1, 1>::OP_SUM, 3>(acc8 + 3);
-        S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(acc8 + 6);
-        xw0 = shfl(xw0, 0); yw0 = shfl(yw0, 0);
-        const double* xc = acc8; const double* yc = acc8 + 4;   // cubic coefficients, highest degree first
-        // ---- curvature of the fitted cubics every 0.25 m, fitted by a cubic
-        double kc[4] = {0, 0, 0, 0};
-        for (int g = k; g < a.n2; g += 32) {
-            const double tt = 0.25 * (double)g;
-            const double dx = xc[2] + 2.0 * xc[1] * tt + 3.0 * xc[0] * (tt * tt), dy = yc[2] + 2.0 * yc[1] * tt + 3.0 * yc[0] * (tt * tt);
-            const double ddx = 2.0 * xc[1] + 6.0 * xc[0] * tt, ddy = 2.0 * yc[1] + 6.0 * yc[0] * tt;
-            const double Km = (dx * ddy - dy * ddx) / (dx * dx + dy * dy);
-            for (int r = 0; r < 4; r++) kc[r] += a.P2[r * a.n2 + g] * Km;
-        }
-        S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc); S.template treduce<TeamSolver<1, 1>::OP_SUM, 2>(kc + 2);
-        const double psi0 = atan2(yc[2], xc[2]);
-        double sp0, cp0;
-        mpc_sincos(psi0, &sp0, &cp0);
-        const double ey = a.ey_from_path ? -(-sp0 * xw0 + cp0 * yw0) : 0.0;
+        // ---- the path ahead -> curvature polynomial, e_y, psi_start
+        double kc[4], ey, psi0;
+        frenet_reference(S, path, a, st[0], st[1], st[2], kc, ey, psi0);
         // ---- update_init_cond(0, e_y, -psi_start, v), update_reference(path, K_coeffs, des_speed), solve_model (:125-130)
         S.set_kpoly(kc[0], kc[1], kc[2], kc[3]);
         syncwarp();
