@@ -106,7 +106,7 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
  *   min_batch  < 0: the default rule, what a new handle starts with.  XY model: N <= 10: 32,768, and 16,384 for warm-started or
  *                   rollout-started batches, whose solves all take about the same handful of iterations; N > 10: never.
  *                   Frenet-frame handles (every solve takes 14-17 iterations): 16,384 at N <= 10, 32,768 at longer horizons
- *                   (N = 20, 65,536 problems: 4.2 M instead of 3.2 M solves/s)
+ *                   (N = 20, 65,536 problems: 4.6 M instead of 3.2 M solves/s)
  * mpcb200_rollout and mpcb200_rollout_frenet follow the same switch: fleets of at least min_batch vehicles per device (default rule:
  * a quarter of the batch rule, i.e. 8,192 vehicles at N <= 10 for the XY model, 4,096 for the Frenet node) run
  * each control period as three launches over the whole fleet -- plant, waypoints, thread-per-problem solve warm-started in place

@@ -333,6 +333,7 @@ struct mpcb200_handle {
     DevBuf d_veh, d_vstop;            /* ... closed-loop fleets: vehicle state [12][Bp], stop latches */
     int tpp_blocks_per_sm = 0;        /* resident blocks of mpc_solve_tpp_kernel per SM */
     int tpp_block = MPC_TPP_BLOCK;    /* threads per block of mpc_solve_tpp_kernel (a multiple of 32, <= MPC_TPP_BLOCK) */
+    bool tpp_block_forced = false;    /* ... given by MPCB200_TPP_BLOCK: no per-batch choice */
     int64_t tpp_min_batch = 0;        /* batches of at least this many problems take the thread-per-problem path (0: never) */
     bool tpp_default_rule = true;     /* ... as set by the default rule (then warm / rollout starts switch at half of it) */
     DevBuf d_rec, d_resto;        /* packed 32-byte records; restoration count per problem of the last solve */
@@ -602,7 +603,7 @@ static int create_impl(mpcb200_handle** out, const mpcb200_config* cfg, int mode
         TRY_OR_FREE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&h->tpp_blocks_per_sm, tk, MPC_TPP_BLOCK, 0));
         if (h->tpp_blocks_per_sm < 1) h->tpp_blocks_per_sm = 1;
         if (const char* e = getenv("MPCB200_TPP_BLOCKS_PER_SM")) { int v = atoi(e); if (v >= 1 && v < h->tpp_blocks_per_sm) h->tpp_blocks_per_sm = v; }  /* tuning aid */
-        if (const char* e = getenv("MPCB200_TPP_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= MPC_TPP_BLOCK && v % 32 == 0) h->tpp_block = v; }  /* tuning aid */
+        if (const char* e = getenv("MPCB200_TPP_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= MPC_TPP_BLOCK && v % 32 == 0) { h->tpp_block = v; h->tpp_block_forced = true; } }  /* tuning aid */
         /* measured (tools/tpp_ab.py, profiles/r02_logs/r02_tpp_thresholds.log): N = 8: 0.8x / 1.2x / 1.5x / 1.8x the warp-per-problem
          * kernel at 16 K / 32 K / 64 K / 128 K problems; N = 12, 16: break-even at ~128 K; N = 20: 0.65x at 64 K, 0.97x at 256 K */
         h->tpp_min_batch = tpp_default_min_batch(model, cfg->N);
@@ -670,8 +671,19 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
      * 1.06x warm, 1.30x from the rollout start; profiles/r02_logs/r02_tpp_warm.log) */
     const int64_t tpp_from = (h->tpp_default_rule && !h->model && (io.warm || h->cfg.start_mode == MPCB200_START_ROLLOUT)) ? h->tpp_min_batch / 2 : h->tpp_min_batch;
     if (!rg.path_of && !zeroed_counter && h->tpp_min_batch > 0 && B >= tpp_from) {
-        /* thread-per-problem: as many slots as lanes can be resident, never more than problems */
-        const int tb = h->tpp_block;
+        /* thread-per-problem: as many slots as lanes can be resident, never more than problems.  The block size is the one that
+         * fills the last wave best: when every solve takes about the same number of trips (Frenet variant, warm starts) a batch of
+         * 1.73 x the resident lanes leaves a quarter of them idle for the second half of the launch (Frenet N = 20, 65,536
+         * problems: 14.2 ms with 224-thread blocks = 1.98 waves, 15.5 ms with 256) */
+        int tb = h->tpp_block;
+        if (!h->tpp_block_forced) {
+            long long best = -1;
+            for (int cand = MPC_TPP_BLOCK; cand >= MPC_TPP_BLOCK - 96; cand -= 32) {
+                const long long per_wave = (long long)h->num_sms * h->tpp_blocks_per_sm * cand;
+                const long long cost = ((B + per_wave - 1) / per_wave) * cand;     /* lane-slots reserved per SM over the launch */
+                if (best < 0 || cost < best) { best = cost; tb = cand; }
+            }
+        }
         long long blocks = (long long)h->num_sms * h->tpp_blocks_per_sm;
         const long long need = (B + tb - 1) / tb;
         if (blocks > need) blocks = need;

@@ -24,7 +24,7 @@
 // Measured on the B200: the layout is HBM-bound (5.5 TB/s at N = 8).  It is at its best when the solves of a batch
 // take about the same number of iterations (no tail of long solves once the queue is empty): warm-started batches, closed-loop
 // fleets (one control period = plant / waypoints / this solve in place: configs[3] in 0.57 s instead of 1.25 s), and the
-// Frenet-frame variant (MODEL 1: 4.2 M instead of 3.2 M solves/s at N = 20).  From the XY model's all-zero start (25 to 200
+// Frenet-frame variant (MODEL 1: 4.6 M instead of 3.2 M solves/s at N = 20, at 97 % of the measured HBM bandwidth).  From the XY model's all-zero start (25 to 200
 // iterations) it beats the warp-per-problem kernel at short horizons and large batches (N = 8: 1.5x at 65,536 problems, 2.1x at
 // 262,144) and ties with it at N = 20, which is what mpcb200_set_large_batch_path's default rule encodes.
 //
