@@ -77,10 +77,12 @@ struct TppMemT {
         : wb(st + (slot >> 5) * ((long)(N + 1) * NF * 32) + (slot & 31)), fb(filt + (slot >> 5) * (2L * TPP_NFILT * 32) + (slot & 31)) {}
     MPC_DEV double ld(int f, int k) const { return (wb + (long)k * (NF * 32))[f * 32]; }
     MPC_DEV void sto(int f, int k, double v) const { (wb + (long)k * (NF * 32))[f * 32] = v; }
-    // L2 prefetch of fields [f0, f0 + nf) of stage k for the whole warp (one bulk instruction from one active lane): the
-    // passes walk the horizon one stage at a time, so the block they touch next is known a whole stage body ahead
+    // L2 prefetch of fields [f0, f0 + nf) of stage k for the whole warp (one bulk instruction from one active lane).  Off by
+    // default: it never paid (the stage bodies issue all their loads up front, which covers the latency), and once the kernel was
+    // HBM-bound the fields a coarse range fetches without need cost 3-5 % (profiles/r02_logs/r02_tpp_noprefetch.log);
+    // -DMPC_TPP_PREFETCH brings it back
     MPC_DEV void prefetch(int k, int f0, int nf) const {
-#ifndef MPC_HOST_EMU
+#if !defined(MPC_HOST_EMU) && defined(MPC_TPP_PREFETCH)
         const unsigned am = __activemask();
         const int lane = threadIdx.x & 31;
         if (lane == __ffs(am) - 1)
