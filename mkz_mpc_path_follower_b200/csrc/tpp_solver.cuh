@@ -132,6 +132,8 @@ struct TppSolverT {
     MPC_DEV double wv(int k) const { return (k >= 1 && k <= N - 1) ? c.w[3] : 0.0; }
     MPC_DEV double rHi(int k, int i) const { return (k == 0) ? c.rHiFirst[i] : c.rHiLater[i]; }
     MPC_DEV int evb(int which) const { return TF_EV + TEVN * which; }
+    // reference sample of stage k; MODEL 1: the cost is on e_y, e_psi themselves (reference 0): nothing to read
+    MPC_DEV double ref(int f, int k) const { return MODEL ? 0.0 : m.ld(f, k); }
 
     // MODEL 1 (MKZMPCPathFollowerFrenet.jl:111-120): curvature K(s) of the problem's cubic and its derivatives; the stage
     // Jacobian of  ds/dt = g = v cos(e_psi + beta) / (1 - e_y K(s)),  d e_psi/dt = v sin(beta) / L_b - g K  at a stage that owns an
@@ -269,9 +271,9 @@ struct TppSolverT {
     MPC_DEV Grad objective_gradient(int k, bool u, double sx, double sy, double sp, double sv, double ua, double ud, double pa, double pd, double na, double nd) const {
         Grad g;
         const double s2 = 2.0 * sigma;
-        g.x = s2 * wx(k) * (sx - m.ld(TF_XR, k));
-        g.y = s2 * wy(k) * (sy - m.ld(TF_YR, k));
-        g.p = s2 * wp(k) * (sp - m.ld(TF_PR, k));
+        g.x = s2 * wx(k) * (sx - ref(TF_XR, k));
+        g.y = s2 * wy(k) * (sy - ref(TF_YR, k));
+        g.p = s2 * wp(k) * (sp - ref(TF_PR, k));
         g.v = s2 * wv(k) * (sv - cst[6]);
         g.a = 0.0; g.d = 0.0;
         if (u) {
@@ -337,7 +339,7 @@ struct TppSolverT {
             const bool r = u && isR(k);
             if (k + 2 <= N) m.prefetch(k + 2, 0, TF_K);
             // ---- loads
-            const double xr = m.ld(TF_XR, k), yr = m.ld(TF_YR, k), pr = m.ld(TF_PR, k);
+            const double xr = ref(TF_XR, k), yr = ref(TF_YR, k), pr = ref(TF_PR, k);
             double ua = 0.0, ud = 0.0, s0 = 0.0, s1 = 0.0;
             double nx = 0.0, ny = 0.0, np = 0.0, nv = 0.0;
             if (u) {
@@ -435,7 +437,7 @@ struct TppSolverT {
             const int kp = (k >= 1) ? k - 1 : 0;
             const double sx = m.ld(TF_SX, k), sy = m.ld(TF_SY, k), sp = m.ld(TF_SP, k), sv = m.ld(TF_SV, k);
             const double pa = m.ld(TF_UA, kp), pd = m.ld(TF_UD, kp);   // (not used at k = 0)
-            const double xr = m.ld(TF_XR, k), yr = m.ld(TF_YR, k), pr = m.ld(TF_PR, k);
+            const double xr = ref(TF_XR, k), yr = ref(TF_YR, k), pr = ref(TF_PR, k);
             const double yxk = m.ld(TF_YX, k), yyk = m.ld(TF_YY, k), ypk = m.ld(TF_YP, k);
             const double zvL = m.ld(TF_ZVL, k), zvU = m.ld(TF_ZVU, k);
             double zaL = 0.0, zaU = 0.0, zdL = 0.0, zdU = 0.0, rvL0 = 0.0, rvL1 = 0.0, rvU0 = 0.0, rvU1 = 0.0, rs0 = 0.0, rs1 = 0.0;
@@ -810,7 +812,7 @@ struct TppSolverT {
             const int kp = (k >= 1) ? k - 1 : 0;
             double sx = m.ld(TF_SX, k), sy = m.ld(TF_SY, k), sp = m.ld(TF_SP, k), sv = m.ld(TF_SV, k);
             double yx = m.ld(TF_YX, k), yy = m.ld(TF_YY, k), yp = m.ld(TF_YP, k), yv = m.ld(TF_YV, k);
-            const double xr = m.ld(TF_XR, k), yr = m.ld(TF_YR, k), pr = m.ld(TF_PR, k);
+            const double xr = ref(TF_XR, k), yr = ref(TF_YR, k), pr = ref(TF_PR, k);
             const double dsx = m.ld(TF_DX, k), dsy = m.ld(TF_DY, k), dsp = m.ld(TF_DP, k), dsv = m.ld(TF_DV, k);
             const double gx = m.ld(TF_GX, k), gy = m.ld(TF_GY, k), gp = m.ld(TF_GP, k), gv = m.ld(TF_GV, k);
             const double hpp = m.ld(TF_HPP, k), hpv = m.ld(TF_HPV, k), hvv = m.ld(TF_HVV, k), hpd = m.ld(TF_HPD, k), hvd = m.ld(TF_HVD, k);
@@ -1312,7 +1314,7 @@ struct TppSolverT {
                 sv = dmin_(dmax_(sv, c.vmin), c.vmax);
                 if (isU(k)) { ua = dmin_(dmax_(ua, -c.amax), c.amax); ud = dmin_(dmax_(ud, -c.smax), c.smax); }
             }
-            const double ex = sx - m.ld(TF_XR, k), ey = sy - m.ld(TF_YR, k), ep = sp - m.ld(TF_PR, k), evv = sv - cst[6];
+            const double ex = sx - ref(TF_XR, k), ey = sy - ref(TF_YR, k), ep = sp - ref(TF_PR, k), evv = sv - cst[6];
             double fk = wx(k) * ex * ex + wy(k) * ey * ey + wp(k) * ep * ep + wv(k) * evv * evv;
             if (isU(k)) {
                 fk += c.w[6] * ua * ua + c.w[7] * ud * ud;
