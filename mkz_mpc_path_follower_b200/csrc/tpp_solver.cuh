@@ -24,7 +24,7 @@
 // Measured on the B200: the layout is HBM-bound (5.5 TB/s at N = 8).  It is at its best when the solves of a batch
 // take about the same number of iterations (no tail of long solves once the queue is empty): warm-started batches, closed-loop
 // fleets (one control period = plant / waypoints / this solve in place: configs[3] in 0.57 s instead of 1.25 s), and the
-// Frenet-frame variant (MODEL 1: 4.6 M instead of 3.2 M solves/s at N = 20, at 97 % of the measured HBM bandwidth).  From the XY model's all-zero start (25 to 200
+// Frenet-frame variant (MODEL 1: 4.8 M instead of 3.2 M solves/s at N = 20, 4.9 TB/s = 75 % of the measured HBM bandwidth).  From the XY model's all-zero start (25 to 200
 // iterations) it beats the warp-per-problem kernel at short horizons and large batches (N = 8: 1.5x at 65,536 problems, 2.1x at
 // 262,144) and ties with it at N = 20, which is what mpcb200_set_large_batch_path's default rule encodes.
 //
@@ -80,9 +80,12 @@ struct TppMemT {
     // L2 prefetch of fields [f0, f0 + nf) of stage k for the whole warp (one bulk instruction from one active lane).  Off by
     // default: it never paid (the stage bodies issue all their loads up front, which covers the latency), and once the kernel was
     // HBM-bound the fields a coarse range fetches without need cost 3-5 % (profiles/r02_logs/r02_tpp_noprefetch.log);
-    // -DMPC_TPP_PREFETCH brings it back
+    // -DMPC_TPP_PREFETCH=<mask of passes: 1 trial, 2 backward, 4 forward, 8 accept> brings it back.  The backward pass's ranges are
+    // exactly what it loads, and prefetching only those changes nothing either (13.73 vs 13.76 ms, r02_tpp_prefetch_per_pass.log)
+    template <int PASS>
     MPC_DEV void prefetch(int k, int f0, int nf) const {
 #if !defined(MPC_HOST_EMU) && defined(MPC_TPP_PREFETCH)
+        if (!((MPC_TPP_PREFETCH) & PASS)) return;
         const unsigned am = __activemask();
         const int lane = threadIdx.x & 31;
         if (lane == __ffs(am) - 1)
@@ -337,7 +340,7 @@ struct TppSolverT {
         auto body = [&](const int k, auto UT) {
             constexpr bool u = decltype(UT)::value;
             const bool r = u && isR(k);
-            if (k + 2 <= N) m.prefetch(k + 2, 0, TF_K);
+            if (k + 2 <= N) m.template prefetch<1>(k + 2, 0, TF_K);
             // ---- loads
             const double xr = ref(TF_XR, k), yr = ref(TF_YR, k), pr = ref(TF_PR, k);
             double ua = 0.0, ud = 0.0, s0 = 0.0, s1 = 0.0;
@@ -432,7 +435,7 @@ struct TppSolverT {
         auto body = [&](const int k, auto UT) -> bool {
             constexpr bool u = decltype(UT)::value;
             const bool r = u && isR(k);
-            if (k >= 1) { m.prefetch(k - 1, 0, TF_DX); m.prefetch(k - 1, soc ? TF_C : ec, soc ? 6 : TEVN); }
+            if (k >= 1) { m.template prefetch<2>(k - 1, 0, TF_DX); m.template prefetch<2>(k - 1, soc ? TF_C : ec, soc ? 6 : TEVN); }
             // ---- loads
             const int kp = (k >= 1) ? k - 1 : 0;
             const double sx = m.ld(TF_SX, k), sy = m.ld(TF_SY, k), sp = m.ld(TF_SP, k), sv = m.ld(TF_SV, k);
@@ -703,7 +706,7 @@ struct TppSolverT {
         auto body = [&](const int k, auto UT) {
             constexpr bool u = decltype(UT)::value;
             const bool r = u && isR(k);
-            if (k + 1 <= N) { m.prefetch(k + 1, 0, TF_C); m.prefetch(k + 1, soc ? TF_C : ec, soc ? 6 : TEVN); }
+            if (k + 1 <= N) { m.template prefetch<4>(k + 1, 0, TF_C); m.template prefetch<4>(k + 1, soc ? TF_C : ec, soc ? 6 : TEVN); }
             // ---- loads
             const double sx = m.ld(TF_SX, k), sy = m.ld(TF_SY, k), sp = m.ld(TF_SP, k), sv = m.ld(TF_SV, k);
             const double g0 = m.ld(TF_GX, k), g1 = m.ld(TF_GY, k), g2 = m.ld(TF_GP, k), g3 = m.ld(TF_GV, k);
@@ -807,7 +810,7 @@ struct TppSolverT {
         auto body = [&](const int k, auto UT) {
             constexpr bool u = decltype(UT)::value;
             const bool r = u && isR(k);
-            if (k >= 1) { m.prefetch(k - 1, 0, TF_C); m.prefetch(k - 1, TF_EV, 2 * TEVN + (MODEL ? TFH_N : 0)); }
+            if (k >= 1) { m.template prefetch<8>(k - 1, 0, TF_C); m.template prefetch<8>(k - 1, TF_EV, 2 * TEVN + (MODEL ? TFH_N : 0)); }
             // ---- loads
             const int kp = (k >= 1) ? k - 1 : 0;
             double sx = m.ld(TF_SX, k), sy = m.ld(TF_SY, k), sp = m.ld(TF_SP, k), sv = m.ld(TF_SV, k);
