@@ -95,7 +95,7 @@ int mpcb200_set_cost(mpcb200_handle* h, const double w[8]);
  * NULL restores the handle's own stream. */
 int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
 
-/* Which kernel solves mpcb200_solve_batch / _records batches of the XY model (no reference counterpart: the reference
+/* Which kernel solves mpcb200_solve_batch / _records / _on_path batches of the XY model (no reference counterpart: the reference
  * solves one problem at a time, MKZMPCPathFollower.jl:176).  Two device layouts of the same solver exist: one warp per
  * problem with the iterate on chip (every batch size, lowest latency) and one THREAD per problem with the iterate
  * streamed from HBM (csrc/tpp_solver.cuh: faster for large batches at short horizons, e.g. 1.5x at 65,536 problems and
@@ -106,7 +106,10 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
  *   min_batch  < 0: the default rule, what a new handle starts with.  XY model: N <= 10: 32,768, and 16,384 for warm-started or
  *                   rollout-started batches, whose solves all take about the same handful of iterations; N > 10: never.
  *                   Frenet-frame handles (every solve takes 14-17 iterations): 16,384 at N <= 10, 32,768 at longer horizons
- *                   (N = 20, 65,536 problems: 4.6 M instead of 3.2 M solves/s)
+ *                   (N = 20, 65,536 problems: 4.8 M instead of 3.2 M solves/s)
+ * mpcb200_solve_batch_on_path follows the switch for N <= 31: the waypoints of the batch are generated by a kernel of their own
+ * (same generator, same bits), then the thread-per-problem solve, then the answers of problems with an unknown path id: three
+ * launches (N = 8, host buffers, whole call: 3.3 M instead of 1.9 M solves/s at 65,536 problems, 4.1 M at 262,144).
  * mpcb200_rollout and mpcb200_rollout_frenet follow the same switch: fleets of at least min_batch vehicles per device (default rule:
  * a quarter of the batch rule, i.e. 8,192 vehicles at N <= 10 for the XY model, 4,096 for the Frenet node) run
  * each control period as three launches over the whole fleet -- plant, waypoints, thread-per-problem solve warm-started in place

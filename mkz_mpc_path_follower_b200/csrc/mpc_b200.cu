@@ -103,7 +103,8 @@ mpc_solve_long_kernel(const KCfg cfg, const BatchPtrs io, const RefGen rg, const
 #endif
 template <int MODEL>
 __global__ void __launch_bounds__(MPC_TPP_BLOCK, MPC_TPP_MIN_BLOCKS)
-mpc_solve_tpp_kernel(const KCfg cfg, const BatchPtrs io, const long long B, double* st, double* filt, unsigned long long* counter) {
+mpc_solve_tpp_kernel(const KCfg cfg, const BatchPtrs io, const long long B, double* st, double* filt, unsigned long long* counter,
+                     const double v_des0) {
     const long slot = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const TppMemT<MODEL> mem(st, filt, cfg.N, slot);
     TppSolverT<MODEL> sv(cfg, mem);
@@ -113,11 +114,46 @@ mpc_solve_tpp_kernel(const KCfg cfg, const BatchPtrs io, const long long B, doub
         if (alive && b < 0) {
             const unsigned long long nb = atomicAdd(counter, 1ULL);
             if (nb >= (unsigned long long)B) alive = false;
-            else { b = (long)nb; sv.begin(io, b); }
+            else { b = (long)nb; sv.begin(io, b, v_des0); }
         }
         const bool done = sv.tick(b >= 0);
         if (b >= 0 && done) { sv.finish(io, b); b = -1; }
     }
+}
+
+// ---- mpcb200_solve_batch_on_path with the thread-per-problem layout: the waypoints of the whole batch first (warp = problem,
+// get_waypoints as in solve_problem), into `ref` = [B][3][N+1] (the caller's ref_out if it asked for one), which the solve kernel
+// then reads like references that came from the host; a problem whose path id was never set gets NaN references (its solve ends
+// at once) and on_path_invalid_kernel gives it the answer solve_problem gives: MPCB200_ERROR, zero commands.
+__global__ void __launch_bounds__(128)
+on_path_ref_kernel(const KCfg cfg, const long long B, const double* state, const RefGen rg, double* ref) {
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, N = cfg.N;
+    TeamSolver<1> S(cfg, (smem_t)0);   // (one-warp teams use no shared memory in get_waypoints)
+    for (long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < B; b += warps) {
+        const int pid = rg.path_of[b];
+        double xr = __longlong_as_double(0x7ff8000000000000LL), yr = xr, pr = xr;
+        bool sc = false;
+        if (!(pid < 0 || pid > 2 || rg.paths[pid].n < 2))
+            sc = S.get_waypoints(rg.paths[pid], cfg.dt, state[4 * b], state[4 * b + 1], state[4 * b + 2], !rg.track_using_time, rg.target_vel, xr, yr, pr);
+        if (lane <= N) { double* ro = ref + 3LL * (N + 1) * b; ro[lane] = xr; ro[(N + 1) + lane] = yr; ro[2 * (N + 1) + lane] = pr; }
+        if (rg.stop && lane == 0) rg.stop[b] = sc ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+on_path_invalid_kernel(const long long B, const RefGen rg, const BatchPtrs io) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int pid = rg.path_of[b];
+    if (!(pid < 0 || pid > 2 || rg.paths[pid].n < 2)) return;
+    if (io.u0) { io.u0[2 * b] = 0.0; io.u0[2 * b + 1] = 0.0; }
+    if (io.cost) io.cost[b] = 0.0;
+    if (io.status) io.status[b] = 4;
+    if (io.iters) io.iters[b] = 0;
+    if (io.rec) { st_global_v2(io.rec + 4 * b, 0.0, 0.0); st_global_v2(io.rec + 4 * b + 2, 0.0, int2_as_double(4, 0)); }
+    if (io.resto) io.resto[b] = 0;
 }
 
 // ---- Closed-loop fleets with the thread-per-problem layout: one control period = three launches over the whole fleet
@@ -330,6 +366,7 @@ struct mpcb200_handle {
     DevBuf d_state, d_ref, d_vdes, d_uprev, d_warm, d_u0, d_cost, d_status, d_iters, d_traj;
     DevBuf d_path[3], d_pose, d_pathof, d_log, d_final, d_stop;
     DevBuf d_tpp_state, d_tpp_filt;   /* thread-per-problem path: slot state [warp][stage][field][lane], filters */
+    DevBuf d_genref;                  /* ... on a path: the generated waypoints [B][3][N+1] when the caller did not ask for them */
     DevBuf d_veh, d_vstop;            /* ... closed-loop fleets: vehicle state [12][Bp], stop latches */
     int tpp_blocks_per_sm = 0;        /* resident blocks of mpc_solve_tpp_kernel per SM */
     int tpp_block = MPC_TPP_BLOCK;    /* threads per block of mpc_solve_tpp_kernel (a multiple of 32, <= MPC_TPP_BLOCK) */
@@ -623,7 +660,7 @@ int mpcb200_destroy(mpcb200_handle* h) {
     cudaSetDevice(h->device);
     DevBuf* bufs[] = {&h->d_state, &h->d_ref, &h->d_vdes, &h->d_uprev, &h->d_warm, &h->d_u0, &h->d_cost, &h->d_status, &h->d_iters, &h->d_traj,
                       &h->d_path[0], &h->d_path[1], &h->d_path[2], &h->d_pose, &h->d_pathof, &h->d_log, &h->d_final, &h->d_stop, &h->d_stage,
-                      &h->d_rec, &h->d_resto, &h->d_seed, &h->d_fit, &h->d_tpp_state, &h->d_tpp_filt, &h->d_veh, &h->d_vstop};
+                      &h->d_rec, &h->d_resto, &h->d_seed, &h->d_fit, &h->d_tpp_state, &h->d_tpp_filt, &h->d_veh, &h->d_vstop, &h->d_genref};
     for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
     if (h->d_counter) cudaFree(h->d_counter);
     if (h->d_roles) cudaFree(h->d_roles);
@@ -670,7 +707,8 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
      * no tail of long solves, so the streaming layout already pays at half the batch (measured at N = 8, 16,384 problems:
      * 1.06x warm, 1.30x from the rollout start; profiles/r02_logs/r02_tpp_warm.log) */
     const int64_t tpp_from = (h->tpp_default_rule && !h->model && (io.warm || h->cfg.start_mode == MPCB200_START_ROLLOUT)) ? h->tpp_min_batch / 2 : h->tpp_min_batch;
-    if (!rg.path_of && !zeroed_counter && h->tpp_min_batch > 0 && B >= tpp_from) {
+    const bool tpp_path_ok = !rg.path_of || (!h->model && h->team_warps == 1);   /* waypoints by one-warp teams: N <= 31 */
+    if (tpp_path_ok && !zeroed_counter && h->tpp_min_batch > 0 && B >= tpp_from) {
         /* thread-per-problem: as many slots as lanes can be resident, never more than problems.  The block size is the one that
          * fills the last wave best: when every solve takes about the same number of trips (Frenet variant, warm starts) a batch of
          * 1.73 x the resident lanes leaves a quarter of them idle for the second half of the launch (Frenet N = 20, 65,536
@@ -691,14 +729,33 @@ static int launch_solve(mpcb200_handle* h, int64_t B, const BatchPtrs& io, const
         int rc;
         if ((rc = ensure(h, h->d_tpp_state, tpp_state_doubles(h->cfg.N, (long)S, h->model) * sizeof(double)))) return rc;
         if ((rc = ensure(h, h->d_tpp_filt, tpp_filter_doubles((long)S) * sizeof(double)))) return rc;
+        BatchPtrs io2 = io;
+        if (rg.path_of) {
+            double* ref = rg.ref_out;
+            if (!ref) {
+                if ((rc = ensure(h, h->d_genref, (size_t)B * 3 * ((size_t)h->cfg.N + 1) * sizeof(double)))) return rc;
+                ref = (double*)h->d_genref.p;
+            }
+            const long long wblocks = (B + 3) / 4, wmax = (long long)h->num_sms * 16;
+            on_path_ref_kernel<<<(int)(wblocks < wmax ? wblocks : wmax), 128, 0, h->stream>>>(make_kcfg(h), (long long)B, io.state, rg, ref);
+            CUDA_TRY(h, cudaGetLastError());
+            io2.ref = ref;
+            h->stats.kernel_launches += 1;
+        }
+        const double v_des0 = rg.path_of ? rg.target_vel : 0.0;   /* des_speed when the caller gives no v_des, mpc_cmd_pub.jl:58-62,116 */
         if (h->model)
-            mpc_solve_tpp_kernel<1><<<(int)blocks, tb, 0, h->stream>>>(make_kcfg(h), io, (long long)B, (double*)h->d_tpp_state.p,
-                                                                      (double*)h->d_tpp_filt.p, counter);
+            mpc_solve_tpp_kernel<1><<<(int)blocks, tb, 0, h->stream>>>(make_kcfg(h), io2, (long long)B, (double*)h->d_tpp_state.p,
+                                                                      (double*)h->d_tpp_filt.p, counter, v_des0);
         else
-            mpc_solve_tpp_kernel<0><<<(int)blocks, tb, 0, h->stream>>>(make_kcfg(h), io, (long long)B, (double*)h->d_tpp_state.p,
-                                                                      (double*)h->d_tpp_filt.p, counter);
+            mpc_solve_tpp_kernel<0><<<(int)blocks, tb, 0, h->stream>>>(make_kcfg(h), io2, (long long)B, (double*)h->d_tpp_state.p,
+                                                                      (double*)h->d_tpp_filt.p, counter, v_des0);
         CUDA_TRY(h, cudaGetLastError());
         h->stats.kernel_launches += 1;
+        if (rg.path_of) {
+            on_path_invalid_kernel<<<(int)((B + 127) / 128), 128, 0, h->stream>>>((long long)B, rg, io);
+            CUDA_TRY(h, cudaGetLastError());
+            h->stats.kernel_launches += 1;
+        }
         return 0;
     }
     const int teams_per_block = (h->team_warps != 1) ? 1 : (h->model ? h->frenet_wpb : WARPS_PER_BLOCK);

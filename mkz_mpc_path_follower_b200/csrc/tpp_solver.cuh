@@ -188,11 +188,11 @@ struct TppSolverT {
     // ------------------------------------------------------------------
     // problem set-up: inputs into the slot, driver state reset, first driver step (interior start)
     // ------------------------------------------------------------------
-    MPC_DEV void begin(const BatchPtrs& io, long b) {
+    MPC_DEV void begin(const BatchPtrs& io, long b, double v_des0 = 0.0) {
         const long nr = 3L * (N + 1), nt = 6L * N + 4;
         for (int i = 0; i < 4; i++) cst[i] = io.state[4 * b + i];
         cst[4] = io.u_prev[2 * b]; cst[5] = io.u_prev[2 * b + 1];
-        cst[6] = io.v_des ? io.v_des[b] : 0.0;
+        cst[6] = io.v_des ? io.v_des[b] : v_des0;
         // MODEL 1: io.ref = [B][4] curvature polynomial; the cost is on e_y, e_psi themselves (reference 0)
         const double* rf = MODEL ? io.ref + 4 * b : io.ref + nr * b;
         if (MODEL) for (int i = 0; i < 4; i++) kp[i] = rf[i];

@@ -286,3 +286,66 @@ def test_tpp_frenet_closed_loop_fleet(capi):
     assert np.array_equal(lw[:, :, 6:8], lt[:, :, 6:8]) and (lt[:, :, 6] == 0).mean() >= 0.99
     assert np.abs(lw[:, :, 0:6] - lt[:, :, 0:6]).max() <= 1e-8
     assert np.abs(out["warp"]["final_state"] - out["tpp"]["final_state"]).max() <= 1e-8
+
+
+@pytest.mark.parametrize("N", [8, 20])
+def test_tpp_solve_batch_on_path(capi, oracle, N):
+    """mpcb200_solve_batch_on_path through the thread-per-problem layout (on_path_ref_kernel -> mpc_solve_tpp_kernel ->
+    on_path_invalid_kernel): waypoints bit-equal to the host restatement's, stop flags, the solves equal solve_batch on
+    those waypoints and the warp-per-problem kernel's answers; v_des defaulting to the clamped target speed; distance mode;
+    a path id outside the tables under DEVICE pointers."""
+    import torch
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    s, w = capi.Solver(N), capi.Solver(N)
+    s.set_large_batch_path(1)
+    w.set_large_batch_path(0)
+    trajs = [GPSRefTrajectory(mat_filename=p, traj_horizon=N, traj_dt=0.2) for p in (1, 2, 3)]
+    for i, g in enumerate(trajs):
+        s.set_path(i, g.trajectory)
+        w.set_path(i, g.trajectory)
+    B = 300
+    b = W.make_batch(B, N)
+    path_of = (b["path"] - 1).astype(np.int32)
+    g1 = s.solve_batch_on_path(b["state"], path_of, b["u_prev"], v_des=b["v_des"], want_ref=True)
+    assert s.stats()["kernel_launches"] == 3
+    assert np.array_equal(g1["ref"], b["ref"])
+    hstop = np.zeros(B, dtype=bool)
+    for p in range(3):
+        m = path_of == p
+        _, hstop[m] = trajs[p].get_waypoints_batch(b["state"][m, 0], b["state"][m, 1], b["state"][m, 2])
+    assert np.array_equal(g1["stop"] != 0, hstop)
+    g0 = s.solve_batch(b["state"], b["ref"], b["u_prev"], v_des=b["v_des"])
+    assert np.array_equal(g1["status"], g0["status"]) and np.array_equal(g1["u0"], g0["u0"]) and np.array_equal(g1["iters"], g0["iters"])
+    o = oracle.solve_batch(_ocfg(oracle, s), b["state"], b["ref"], b["v_des"], b["u_prev"], n_threads=8)
+    _compare(g1, o, min_conv=0.95, max_status_mismatch=1)
+    # without ref_out (the library's own buffer), without v_des (des_speed = max(target_vel, 0)), distance mode
+    for kw in ({}, {"track_using_time": False, "target_vel": 6.0}, {"track_using_time": False, "target_vel": -3.0}):
+        gt = s.solve_batch_on_path(b["state"][:128], path_of[:128], b["u_prev"][:128], **kw)
+        gw = w.solve_batch_on_path(b["state"][:128], path_of[:128], b["u_prev"][:128], **kw)
+        assert w.stats()["kernel_launches"] == 1
+        assert np.array_equal(gt["stop"], gw["stop"])
+        assert (gt["status"] == gw["status"]).mean() >= 0.98
+        both = (gt["status"] == 0) & (gw["status"] == 0)
+        assert both.mean() > 0.5 and np.abs(gt["u0"] - gw["u0"])[both].max() <= 1e-7
+    # DEVICE pointers and a path id that was never set: status Error, zero commands, neighbours solved
+    one = capi.Solver(N)
+    one.set_large_batch_path(1)
+    one.set_path(0, trajs[0].trajectory)
+    b1 = W.make_batch(70, N, path_ids=(1,))
+    dev = torch.device("cuda", 0)
+    st = torch.from_numpy(b1["state"]).to(dev); up = torch.from_numpy(b1["u_prev"]).to(dev)
+    pid_h = np.zeros(70, dtype=np.int32)
+    pid_h[[1, 3, 4, 69]] = [5, -2, 1, 2]
+    pid = torch.from_numpy(pid_h).to(dev)
+    u0 = torch.full((70, 2), 7.0, dtype=torch.float64, device=dev); status = torch.full((70,), 9, dtype=torch.int32, device=dev)
+    iters = torch.full((70,), 9, dtype=torch.int32, device=dev); stop = torch.full((70,), 9, dtype=torch.int32, device=dev)
+    rec = torch.zeros((70, 4), dtype=torch.float64, device=dev)
+    one.solve_batch_on_path_device(70, st, pid, up, u0, status=status, iters=iters, stop=stop)
+    torch.cuda.synchronize()
+    bad = [1, 3, 4, 69]
+    good = [i for i in range(70) if i not in bad]
+    assert (status.cpu().numpy()[bad] == 4).all() and (u0.cpu().numpy()[bad] == 0.0).all() and (iters.cpu().numpy()[bad] == 0).all()
+    assert (stop.cpu().numpy()[bad] == 0).all()
+    ref = one.solve_batch_on_path(b1["state"], np.zeros(70, dtype=np.int32), b1["u_prev"])
+    assert np.array_equal(status.cpu().numpy()[good], ref["status"][good]) and np.array_equal(u0.cpu().numpy()[good], ref["u0"][good])
+    del rec
