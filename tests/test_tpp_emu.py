@@ -11,6 +11,7 @@ import pytest
 from mkz_mpc_path_follower_b200 import workload as W
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("N,B", [(8, 256), (20, 192), (3, 64), (31, 24)])
@@ -166,3 +167,38 @@ def test_thread_per_problem_frenet_matches_oracle(oracle, N, B, stress):
     r = E.solve_batch_frenet(k1, b["state"][:8], b["kpoly"][:8], b["v_des"][:8], b["u_prev"][:8], tpp=True)
     both = (o["status"][:8] == 0) & (r["status"] == 0)
     assert both.sum() >= 6 and np.abs(o["u0"][:8] - r["u0"])[both].max() <= 1e-5
+
+
+@pytest.mark.parametrize("model", ["xy", "frenet"])
+def test_fuzz_classes(oracle, model):
+    """One small round of every input class of tests/fuzz_layouts.py (pose errors of metres, speeds and previous commands at and
+    outside their bounds, random weights, stand-still, jumping references; Frenet: also 1 - e_y K <= 0) through the oracle and
+    both emulated device layouts: wherever the solves are short enough to be comparable (under 100 iterations on both sides,
+    inside the model's domain) status and first move agree; infeasible inputs end Infeasible everywhere."""
+    import emu as E
+    import fuzz_layouts as F
+    N, B = 8, 12
+    rng = np.random.default_rng(7)
+    seen = set()
+    for kind in range(F.XY_KINDS if model == "xy" else F.FRENET_KINDS):
+        if model == "xy":
+            st, ref, vd, up, weights = F.perturb_xy(rng, kind, W.make_batch(B, N, b0=1000 * kind), N)
+            cfg = oracle.default_cfg(N, weights=weights)
+            k = E.kcfg_from_oracle(cfg)
+            o = oracle.solve_batch(cfg, st, ref, vd, up, n_threads=4)
+            gs = [E.solve_batch(k, st, ref, vd, up), E.solve_batch_tpp(k, st, ref, vd, up, slots=5)]
+        else:
+            st, kp, vd, up, weights = F.perturb_frenet(rng, kind, W.make_frenet_batch(B, N, b0=1000 * kind), N)
+            cfg = oracle.default_cfg_frenet(N, weights=weights)
+            k = E.kcfg_from_oracle(cfg)
+            o = oracle.solve_batch_frenet(cfg, st, kp, vd, up, n_threads=4)
+            gs = [E.solve_batch_frenet(k, st, kp, vd, up), E.solve_batch_frenet(k, st, kp, vd, up, tpp=True, slots=5)]
+        seen.update(int(s) for s in o["status"])
+        for g in gs:
+            short = (g["iters"] < 100) & (o["iters"] < 100)
+            if model == "frenet" and kind == 3:
+                short &= (1.0 - st[:, 1] * kp[:, 3]) > 0.05    # the vehicle beyond the centre of curvature: outside the model
+            sm, dm, _ = F.disagreements(g, o)
+            assert not short[sm].any() and not short[dm].any(), (model, kind, sm, dm)
+            assert ((g["status"] == 1) == (o["status"] == 1)).all()    # Infeasible is decided a priori, the same everywhere
+    assert 0 in seen and 1 in seen
