@@ -788,7 +788,8 @@ static void fill_paths(const mpcb200_handle* h, PathTable* paths) {
         const int n = h->path_n[i];
         memset(&paths[i], 0, sizeof(PathTable));
         paths[i].n = n;
-        if (n) { paths[i].t = base; paths[i].X = base + n; paths[i].Y = base + 2 * (size_t)n; paths[i].psi = base + 3 * (size_t)n; paths[i].s = base + 4 * (size_t)n; }
+        if (n) { paths[i].t = base; paths[i].X = base + n; paths[i].Y = base + 2 * (size_t)n; paths[i].psi = base + 3 * (size_t)n; paths[i].s = base + 4 * (size_t)n;
+                 paths[i].cb = base + 5 * (size_t)n; paths[i].nch = path_chunks(n); }
     }
 }
 
@@ -1138,12 +1139,21 @@ int mpcb200_set_path(mpcb200_handle* h, int32_t path_id, int32_t n, const double
     if (path_id < 0 || path_id > 2) return fail(h, MPCB200_EINVAL, "mpcb200_set_path: path_id %d outside [0,2]", path_id);
     if (n < 2 || !t || !X || !Y || !psi || !s) return fail(h, MPCB200_EINVAL, "mpcb200_set_path: need n >= 2 samples and five columns");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    int rc = ensure(h, h->d_path[path_id], (size_t)5 * n * sizeof(double));
+    const int nch = path_chunks(n);
+    int rc = ensure(h, h->d_path[path_id], ((size_t)5 * n + (size_t)3 * nch) * sizeof(double));
     if (rc) return rc;
     const double* cols[5] = {t, X, Y, psi, s};
     for (int i = 0; i < 5; i++)
         CUDA_TRY(h, cudaMemcpyAsync((double*)h->d_path[path_id].p + (size_t)i * n, cols[i], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    /* bounding circles of the chunks of samples the nearest-sample search skips (TeamSolver::nearest_sample) */
+    double* cb = (double*)malloc((size_t)3 * nch * sizeof(double));
+    if (!cb) return fail(h, MPCB200_ENOMEM, "mpcb200_set_path: out of host memory");
+    path_chunk_bounds(n, X, Y, cb);
+    const cudaError_t ce = cudaMemcpyAsync((double*)h->d_path[path_id].p + (size_t)5 * n, cb, (size_t)3 * nch * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    const cudaError_t cs = cudaStreamSynchronize(h->stream);
+    free(cb);
+    CUDA_TRY(h, ce);
+    CUDA_TRY(h, cs);
     h->path_n[path_id] = n;
     for (int i = 0; i < h->n_sub; i++)   /* the tables are replicated on every device */
         if ((rc = mpcb200_set_path(h->sub[i], path_id, n, t, X, Y, psi, s))) return sub_fail(h, h->sub[i], rc);

@@ -430,7 +430,27 @@ MPC_HD void riccati_roles(int l, int N, int W_SD, int* out, int model = 0) {
 
 // ---- reference generation on the device (scripts/gps_utils/ref_gps_traj.py:131-218), used by the
 // closed-loop rollout and by mpcb200_solve_batch_on_path (TeamSolver::get_waypoints)
-struct PathTable { const double *t, *X, *Y, *psi, *s; int n; };   // columns 0,4,5,3,6 of ref_gps_traj.py:106
+struct PathTable {
+    const double *t, *X, *Y, *psi, *s; int n;   // columns 0,4,5,3,6 of ref_gps_traj.py:106
+    const double* cb; int nch;                  // bounding circles of chunks of PATH_CHUNK samples: cx[nch], cy[nch], r[nch] (null: none)
+};
+#define PATH_CHUNK 16
+inline int path_chunks(int n) { return (n + PATH_CHUNK - 1) / PATH_CHUNK; }
+// host: the bounding circles for nearest_sample: centre of the chunk's bounding box, radius = largest distance to one of its
+// samples, inflated so that rounding can only make a circle larger than the samples need
+inline void path_chunk_bounds(int n, const double* X, const double* Y, double* out) {
+    const int nch = path_chunks(n);
+    for (int c = 0; c < nch; c++) {
+        const int i0 = c * PATH_CHUNK, i1 = (i0 + PATH_CHUNK < n) ? i0 + PATH_CHUNK : n;
+        double x0 = X[i0], x1 = X[i0], y0 = Y[i0], y1 = Y[i0];
+        for (int i = i0; i < i1; i++) { x0 = X[i] < x0 ? X[i] : x0; x1 = X[i] > x1 ? X[i] : x1; y0 = Y[i] < y0 ? Y[i] : y0; y1 = Y[i] > y1 ? Y[i] : y1; }
+        const double cx = 0.5 * (x0 + x1), cy = 0.5 * (y0 + y1);
+        double r2 = 0.0;
+        for (int i = i0; i < i1; i++) { const double dx = X[i] - cx, dy = Y[i] - cy, d = dx * dx + dy * dy; r2 = d > r2 ? d : r2; }
+        out[c] = cx; out[nch + c] = cy;
+        out[2 * nch + c] = sqrt(r2) * (1.0 + 1e-9) + 1e-12 * (fabs(cx) + fabs(cy)) + 1e-300;
+    }
+}
 
 // np.interp(xq, xp, fp): every operation rounded on its own like numpy's compiled loop (no FMA contraction)
 MPC_DEV double np_interp(double xq, const double* xp, const double* fp, int n) {
@@ -1397,17 +1417,50 @@ struct TeamSolver {
         }
     }
 
+    // np.argmin of the squared distance to (X, Y) over all samples of the path (ref_gps_traj.py:136-137; first index on ties),
+    // each distance rounded operation by operation like numpy's.  Not a scan of all samples: a chunk of PATH_CHUNK consecutive
+    // samples whose bounding circle lies further away than the far side of the nearest circle cannot hold the minimum (margins
+    // far above the rounding of the bounds), so a lane scans only those of its chunks that can -- usually the two or three
+    // around the vehicle, spread over as many lanes.  A pose that is not finite gives index 0, like argmin of an all-NaN array.
+    MPC_DEV int nearest_sample(const PathTable& p, double X, double Y) {
+        double bd = 1e300; int bi = 0x7fffffff;
+        double ub = 1e300;
+        if (p.cb) {
+            const double *cx = p.cb, *cy = p.cb + p.nch, *cr = p.cb + 2 * p.nch;
+            for (int c = k; c < p.nch; c += 32 * W) {
+                const double dx = cx[c] - X, dy = cy[c] - Y, u = sqrt(dx * dx + dy * dy) + cr[c];
+                if (u < ub) ub = u;
+            }
+            ub = tmin(ub);
+        }
+        if (ub < 1e300) {
+            const double *cx = p.cb, *cy = p.cb + p.nch, *cr = p.cb + 2 * p.nch;
+            const double thr = ub * (1.0 + 1e-9) + 1e-9 + 1e-12 * (fabs(X) + fabs(Y));
+            for (int c = k; c < p.nch; c += 32 * W) {
+                const double cdx = cx[c] - X, cdy = cy[c] - Y;
+                if (sqrt(cdx * cdx + cdy * cdy) - cr[c] > thr) continue;
+                const int i0 = c * PATH_CHUNK, i1 = (i0 + PATH_CHUNK < p.n) ? i0 + PATH_CHUNK : p.n;
+                for (int i = i0; i < i1; i++) {
+                    const double dx = p.X[i] - X, dy = p.Y[i] - Y, d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+                    if (d < bd) { bd = d; bi = i; }
+                }
+            }
+        } else {
+            for (int i = k; i < p.n; i += 32 * W) {
+                const double dx = p.X[i] - X, dy = p.Y[i] - Y, d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
+                if (d < bd) { bd = d; bi = i; }
+            }
+        }
+        targmin(bd, bi);
+        return (bi < p.n) ? bi : 0;
+    }
+
     // get_waypoints (ref_gps_traj.py:131-218) for the whole team: thread k returns waypoint k (k <= N); returns stop_cmd.
     // Nearest sample over the whole path (:136-137), np.interp of X, Y, psi at t_closest + k dt -- or at
     // s_closest + (k + 1) dt v_target in distance mode (:175) --, heading unwrap (:204-218), stop_cmd (:198-200).
     MPC_DEV bool get_waypoints(const PathTable& p, double traj_dt, double X, double Y, double yaw, bool use_vtarget,
                                double v_target, double& xr, double& yr, double& pr) {
-        double bd = 1e300; int bi = 0x7fffffff;
-        for (int i = k; i < p.n; i += 32 * W) {
-            const double dx = p.X[i] - X, dy = p.Y[i] - Y, d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-            if (d < bd) { bd = d; bi = i; }
-        }
-        targmin(bd, bi);
+        const int bi = nearest_sample(p, X, Y);
         const double* absc = use_vtarget ? p.s : p.t;
         const double start = absc[bi];
         xr = yr = pr = 0.0;
@@ -2234,12 +2287,7 @@ inline void cubic_fit_matrix(int n, double step, double* P) {
 MPC_DEV void frenet_reference(TeamSolver<1, 1>& S, const PathTable& path, const FrenetRolloutArgs& a, double X, double Y, double yaw,
                               double kc[4], double& ey, double& psi0) {
     const int k = S.k;
-    double bd = 1e300; int bi = 0x7fffffff;
-    for (int i = k; i < path.n; i += 32) {
-        const double dx = path.X[i] - X, dy = path.Y[i] - Y, d = add_rn(mul_rn(dx, dx), mul_rn(dy, dy));
-        if (d < bd) { bd = d; bi = i; }
-    }
-    S.targmin(bd, bi);
+    const int bi = S.nearest_sample(path, X, Y);
     const double s_i = path.s[bi];
     double sps, cps;
     mpc_sincos(yaw, &sps, &cps);

@@ -45,6 +45,18 @@ void run_warp(void (*fn)(int, void*), void* arg, int warps) {
 
 using namespace mpcb200;
 
+// PathTable over the caller's columns, with the chunk bounds mpcb200_set_path computes (kept alive in `store`)
+static PathTable make_path(int n0, const double* t, const double* X, const double* Y, const double* psi, const double* s, std::vector<double>& store) {
+    PathTable p;
+    p.n = n0; p.t = t; p.X = X; p.Y = Y; p.psi = psi; p.s = s;
+    p.nch = path_chunks(n0);
+    store.resize((size_t)3 * p.nch);
+    path_chunk_bounds(n0, X, Y, store.data());
+    p.cb = store.data();
+    return p;
+}
+
+
 // benign words of one team's shared memory: the sink of inactive lanes and, in every per-thread
 // state group, the slot shared by the threads that own no stage
 static void register_benign(double* team, int N, int model = 0) {
@@ -145,7 +157,8 @@ extern "C" int emu_rollout(const KCfg* cfg, long B, int T, const double* pose0, 
     RolloutArgs a;
     memset(&a, 0, sizeof(a));
     a.pose0 = pose0; a.path_of = path_of;
-    for (int i = 0; i < 3; i++) { a.paths[i].n = n0; a.paths[i].t = t; a.paths[i].X = X; a.paths[i].Y = Y; a.paths[i].psi = psi; a.paths[i].s = s; }
+    std::vector<double> cb_store;
+    for (int i = 0; i < 3; i++) a.paths[i] = make_path(n0, t, X, Y, psi, s, cb_store);
     a.T = T; a.track_using_time = track_using_time; a.target_vel = target_vel; a.log = log; a.final_state = final_state; a.B = B;
     a.warm0 = warm0;
     const int per_team = smem_doubles_per_team(kc.N);
@@ -192,7 +205,8 @@ extern "C" int emu_solve_batch_on_path(const KCfg* cfg, long B, const double* st
     RefGen rg;
     memset(&rg, 0, sizeof(rg));
     rg.path_of = path_of;
-    rg.paths[0].n = n0; rg.paths[0].t = t; rg.paths[0].X = X; rg.paths[0].Y = Y; rg.paths[0].psi = psi; rg.paths[0].s = s;
+    std::vector<double> cb_store;
+    rg.paths[0] = make_path(n0, t, X, Y, psi, s, cb_store);
     rg.track_using_time = track_using_time; rg.target_vel = target_vel > 0.0 ? target_vel : 0.0; rg.ref_out = ref_out; rg.stop = stop;
     std::vector<double> smem_raw(smem_doubles_per_team(kc.N) + 2, 0.0);
     double* smem = smem_raw.data();
@@ -228,7 +242,8 @@ extern "C" int emu_rollout_frenet(const KCfg* cfg, long B, int T, const double* 
     FrenetRolloutArgs a;
     memset(&a, 0, sizeof(a));
     a.pose0 = pose0; a.path_of = path_of;
-    for (int i = 0; i < 3; i++) { a.paths[i].n = n0; a.paths[i].t = t; a.paths[i].X = X; a.paths[i].Y = Y; a.paths[i].psi = psi; a.paths[i].s = s; }
+    std::vector<double> cb_store;
+    for (int i = 0; i < 3; i++) a.paths[i] = make_path(n0, t, X, Y, psi, s, cb_store);
     a.T = T; a.ey_from_path = ey_from_path; a.target_vel = target_vel; a.log = log; a.final_state = final_state; a.B = B;
     a.P1 = P.data(); a.P2 = P.data() + 4 * (size_t)n1; a.n1 = n1; a.n2 = n2;
     const int per_team = smem_doubles_per_team(kc.N, 1);
@@ -283,8 +298,8 @@ extern "C" int emu_rollout_tpp(const KCfg* cfg, long B, int T, const double* pos
                                double target_vel, double* log, double* final_state, const double* warm0) {
     KCfg kc = *cfg;
     kcfg_finalize(kc);
-    PathTable path;
-    path.n = n0; path.t = t; path.X = X; path.Y = Y; path.psi = psi; path.s = s;
+    std::vector<double> cb_store;
+    PathTable path = make_path(n0, t, X, Y, psi, s, cb_store);
     (void)path_of;   // (the emulator gets one path table, like emu_rollout)
     const double des_speed = target_vel > 0.0 ? target_vel : 0.0;
     const long S = 40;

@@ -239,3 +239,37 @@ def test_emulated_kernel_property(oracle):
             assert np.abs(o["u0"] - e["u0"]).max() <= 1e-7
 
     check()
+
+
+@pytest.mark.parametrize("N", [3, 40])
+def test_emulated_nearest_sample_search(oracle, N):
+    """TeamSolver::nearest_sample skips the chunks of path samples whose bounding circle cannot hold the nearest one; the result
+    must still be np.argmin over the whole path (ref_gps_traj.py:136-137), so the generated waypoints stay bit-equal to the host
+    generator's: poses on the samples, between two samples (near-ties across chunk borders), metres to tens of kilometres
+    away, at the centroid of the path, and not finite (argmin of an all-NaN array is 0, not an out-of-range index)."""
+    import emu as E
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    k = E.kcfg_from_oracle(oracle.default_cfg(N, max_iter=1))
+    rng = np.random.default_rng(3)
+    m = 12 if N > 31 else 40
+    for pid in (1, 2, 3):
+        g = GPSRefTrajectory(mat_filename=pid, traj_horizon=N, traj_dt=0.2)
+        tr = g.trajectory
+        n = tr.shape[0]
+        poses = []
+        for scale in (0.0, 1e-9, 0.3, 5.0, 50.0, 500.0, 5e4):
+            j = rng.integers(0, n, m)
+            poses.append(np.stack([tr[j, 4] + rng.normal(0, 1, m) * scale, tr[j, 5] + rng.normal(0, 1, m) * scale,
+                                   tr[j, 3] + rng.normal(0, 0.1, m), np.full(m, 5.0)], 1))
+        j = np.arange(14, n - 2, 16 * 13)[:m]      # sample 15 | 16 is a chunk border
+        for o in (0, 1):
+            poses.append(np.stack([0.5 * (tr[j + o, 4] + tr[j + o + 1, 4]), 0.5 * (tr[j + o, 5] + tr[j + o + 1, 5]), tr[j, 3], np.full(len(j), 5.0)], 1))
+        poses.append(np.array([[tr[:, 4].mean(), tr[:, 5].mean(), 0.0, 5.0], [tr[:, 4].min() - 10, tr[:, 5].max() + 10, 1.0, 5.0],
+                               [np.nan, 0.0, 0.0, 5.0], [0.0, np.inf, 0.0, 5.0], [1e200, 1e200, 0.0, 5.0]]))
+        st = np.concatenate(poses)
+        for mode_time, vt in ((True, 1.0), (False, 6.5)):
+            e = E.solve_batch_on_path(k, tr, st, np.zeros((len(st), 2)), track_using_time=mode_time, target_vel=vt)
+            with np.errstate(all="ignore"):
+                ref, stop = g.get_waypoints_batch(st[:, 0], st[:, 1], st[:, 2], v_target=None if mode_time else vt)
+            assert np.array_equal(e["ref"], ref, equal_nan=True)
+            assert np.array_equal(e["stop"].astype(bool), stop)

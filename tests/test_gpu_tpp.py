@@ -148,8 +148,9 @@ def test_tpp_default_rule_large_batch(capi, oracle):
     assert ok.mean() >= 0.999
     assert (np.abs(t["u0"] - o["u0"])[ok].max(axis=1) > U_TOL).sum() <= 3
     assert (t["iters"][ok] == o["iters"][ok]).mean() >= 0.998
-    print("N=8 B=65536: thread-per-problem %.2f ms, warp-per-problem %.2f ms" % (t["ms"], w["ms"]))
-    assert t["ms"] < w["ms"]      # what the default rule is for
+    # (no assertion on the times: the first launch of a layout allocates its device buffers inside the timed region;
+    # bench.py's layouts_n8 key measures the two layouts)
+    print("N=8 B=65536, first launch of each: thread-per-problem %.2f ms, warp-per-problem %.2f ms" % (t["ms"], w["ms"]))
 
 
 def test_tpp_multi_device_handle(capi):
