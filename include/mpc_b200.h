@@ -113,7 +113,7 @@ int mpcb200_set_stream(mpcb200_handle* h, void* cuda_stream);
  * mpcb200_rollout and mpcb200_rollout_frenet follow the same switch: fleets of at least min_batch vehicles per device (default rule:
  * a quarter of the batch rule, i.e. 8,192 vehicles at N <= 10 for the XY model, 4,096 for the Frenet node) run
  * each control period as three launches over the whole fleet -- plant, waypoints, thread-per-problem solve warm-started in place
- * -- instead of one persistent kernel (16,384 vehicles x 500 periods: 0.67 s instead of 1.26 s; 65,536 x 100: 0.38 s instead of
+ * -- instead of one persistent kernel (16,384 vehicles x 500 periods: 0.64 s instead of 1.38 s; 65,536 x 100: 0.38 s instead of
  * 1.39 s). */
 int mpcb200_set_large_batch_path(mpcb200_handle* h, int64_t min_batch);
 
