@@ -3,7 +3,7 @@
 against the oracle, on inputs the synthetic workload does not produce: larger perturbations, random weights, speeds at and
 outside the bounds, previous commands outside the box, stand-still, warm starts from another problem's solution; for the
 Frenet-frame variant also curvatures with 1 - e_y K(s) <= 0 (outside the model's domain).
-    python tests/fuzz_layouts.py [seconds] [seed] [frenet]
+    python tests/fuzz_layouts.py [seconds] [seed] [frenet | rollout]
 Prints every problem where the three disagree (status, or |du| > 1e-5 with all three Optimal).  Not collected by pytest (a
 long-running hunt, not a check); tests/test_tpp_emu.py::test_fuzz_classes runs one small round of every input class.
 What it found is in DESIGN.md 4."""
@@ -121,5 +121,49 @@ def main():
     print("%d problems in %d rounds, %d disagreements, oracle statuses %s, %.0f s" % (tot, rnd, bad, dict(sorted(hist.items())), time.time() - t0))
 
 
+def main_rollout():
+    """python tests/fuzz_layouts.py [seconds] [seed] rollout: closed loops of 12 control steps (fused rollout kernel's source and
+    the per-period pipeline with the thread-per-problem solve, both emulated) against the oracle's closed loop, vehicle by vehicle:
+    random poses around the three paths (one per round near the end: stop latch), time and distance mode, target speeds <= 0 too."""
+    from oracle import oracle as O
+    import emu as E
+    from mkz_mpc_path_follower_b200.gps_ref_traj import GPSRefTrajectory
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 600.0
+    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    t0 = time.time()
+    tot = bad = 0
+    B, T = 6, 12
+    while time.time() - t0 < budget:
+        N = int(rng.choice([8, 8, 12, 20])); pid = int(rng.choice([1, 2, 3]))
+        g = GPSRefTrajectory(mat_filename=pid, traj_horizon=N, traj_dt=0.2)
+        tr = g.trajectory
+        n = tr.shape[0]
+        cfg = O.default_cfg(N)
+        k = E.kcfg_from_oracle(cfg)
+        seed = O.module_load_solution(cfg)
+        j = rng.integers(0, n - 200, B); j[0] = n - rng.integers(2, 120)
+        sc = rng.choice([0.1, 0.5, 2.0])
+        poses = np.stack([tr[j, 4] + rng.normal(0, sc, B), tr[j, 5] + rng.normal(0, sc, B), tr[j, 3] + rng.normal(0, 0.1 * sc, B)], 1)
+        mode = bool(rng.integers(0, 2)); vt = float(rng.choice([-1.0, 0.0, 3.0, 8.0]))
+        path, keep = O.make_path(tr)
+        for tpp in (False, True):
+            log, final = E.rollout(k, tr, poses, T, track_using_time=mode, target_vel=vt, warm0=seed, tpp=tpp)
+            for b in range(B):
+                ol = O.closed_loop(cfg, path, poses[b], T, track_using_time=mode, target_vel=vt)
+                m = len(ol)
+                st_eq = np.array_equal(log[:m, b, 6], ol[:, 6])
+                du = np.abs(log[:m, b, 4:6] - ol[:, 4:6]).max() if m else 0.0
+                dp = np.abs(log[:m, b, 0:4] - ol[:, 0:4]).max() if m else 0.0
+                tot += 1
+                if not st_eq or du > 1e-5 or dp > 1e-6:
+                    bad += 1
+                    print("N %d path %d %s vehicle %d time mode %s target_vel %g spread %g: statuses equal %s, |du| %.2e, |dpose| %.2e, most iterations %d / %d" % (
+                        N, pid, "pipeline" if tpp else "fused", b, mode, vt, sc, st_eq, du, dp, log[:m, b, 7].max(), ol[:, 7].max()), flush=True)
+    print("%d closed loops, %d disagreements, %.0f s" % (tot, bad, time.time() - t0))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 3 and sys.argv[3] == "rollout":
+        main_rollout()
+    else:
+        main()
